@@ -1,0 +1,71 @@
+"""Pin oracle/remap_ref.c to the real cv::remap (reference call site
+opencv/FrameSourceWarp.cpp:306-312): committed cv2 outputs + live cv2 when present."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.conftest import GOLDEN
+
+
+def test_remap_golden_vectors(oracle):
+    g = np.load(os.path.join(GOLDEN, "remap_cases.npz"))
+    mx, my = g["map_x"], g["map_y"]
+    for cn in (1, 2, 3):
+        src = g[f"src{cn}"]
+        for bi, border in enumerate(g["borders"]):
+            got = oracle.remap_u8(src, mx, my, border=border[:cn])
+            assert np.array_equal(got, g[f"dst{cn}_b{bi}"]), (cn, bi)
+
+
+def test_remap_documented_cases(oracle):
+    """SURVEY 9.2 known answers: partial-border blends and specials."""
+    src = np.full((16, 16), 221, np.uint8)
+    mx = np.array([[15.5, -0.5, np.nan, np.inf, -np.inf, 1e9, -1e9, 3.0]], np.float32)
+    my = np.full_like(mx, 4.0)
+    out = oracle.remap_u8(src, mx, my, border=(0,))
+    assert out[0, 0] == 111          # x = 15.5: tap 16 is outside, blends with border 0
+    assert out[0, 1] == 111          # x = -0.5
+    assert list(out[0, 2:7]) == [0] * 5
+    assert out[0, 7] == 221
+    src2 = np.full((8, 8, 2), 200, np.uint8)
+    o2 = oracle.remap_u8(src2, np.array([[-0.5]], np.float32), np.array([[3.0]], np.float32), border=(128, 128))
+    assert list(o2[0, 0]) == [164, 164]
+    o3 = oracle.remap_u8(src2, np.array([[-0.5]], np.float32), np.array([[3.0]], np.float32), border=(0, 0))
+    assert list(o3[0, 0]) == [100, 100]
+
+
+def test_remap_33_levels(oracle):
+    """A 0/255 step sampled at 257 sub-pixel offsets gives exactly 33 levels (1/32-px buckets)."""
+    src = np.zeros((4, 8), np.uint8)
+    src[:, 4:] = 255
+    mx = (3.0 + np.arange(257) / 256.0).astype(np.float32)[None, :]
+    my = np.full_like(mx, 1.0)
+    out = oracle.remap_u8(src, mx, my)
+    assert len(np.unique(out)) == 33
+
+
+@pytest.mark.parametrize("cn", [1, 2, 3])
+def test_remap_live_cv2(oracle, cn):
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(7 + cn)
+    src = rng.integers(0, 256, (113, 75) if cn == 1 else (113, 75, cn), dtype=np.uint8)
+    mx = rng.uniform(-4, 79, (200, 300)).astype(np.float32)
+    my = rng.uniform(-4, 117, (200, 300)).astype(np.float32)
+    # exact 1/64 ties everywhere in one block
+    mx[:50] = np.round(mx[:50] * 64) / 64
+    my[:50] = np.round(my[:50] * 64) / 64
+    for border in [(0, 0, 0), (128, 128, 128), (255, 1, 77)]:
+        bv = tuple(float(b) for b in border[:cn])
+        ref = cv2.remap(src, mx, my, cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT,
+                        borderValue=bv if cn > 1 else bv[0])
+        got = oracle.remap_u8(src, mx, my, border=border[:cn])
+        assert np.array_equal(ref, got)
+
+
+def test_remap_threads_agree(oracle):
+    rng = np.random.default_rng(3)
+    src = rng.integers(0, 256, (64, 64), dtype=np.uint8)
+    mx = rng.uniform(-2, 66, (33, 47)).astype(np.float32)
+    my = rng.uniform(-2, 66, (33, 47)).astype(np.float32)
+    assert np.array_equal(oracle.remap_u8(src, mx, my, threads=1), oracle.remap_u8(src, mx, my, threads=5))
