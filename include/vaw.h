@@ -1,0 +1,185 @@
+/*
+ * vaw.h -- C-ABI of the B200-native warp path (libvaw.so).
+ *
+ * "vaw" = video-annotator warp.  This is the drop-in boundary for ONE path of
+ * hedgepigdaniel/video-annotator: the per-frame fisheye->rectilinear projection with
+ * per-frame camera rotation that the reference computes as a remap map
+ * (opencv/createMap.cl:1-51) and applies with cv::remap inside
+ * FrameSourceWarp::warp_frame (opencv/FrameSourceWarp.cpp:272-314).
+ *
+ * Plain C: opaque handle, POD structs, raw device/host pointers, sizes and CUDA
+ * stream handles passed as void*.  No torch, OpenCV or C++ types cross the boundary.
+ * There is NO CPU fallback: every entry point that computes needs a CUDA device and
+ * returns VAW_ERR_CUDA otherwise.
+ *
+ * Each declaration cites the reference interface it replaces (paths relative to the
+ * reference repository root).  INTEGRATION.md shows the reference-side binding.
+ */
+#ifndef VAW_H
+#define VAW_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VAW_VERSION 100 /* 0.1.0 */
+
+/* ---- error convention -------------------------------------------------------------
+ * The reference throws ints (-1 on kernel failure, opencv/FrameSourceWarp.cpp:301-304;
+ * EOF at end of stream, :465-467) and std::string on program build failure (:191-195).
+ * The C-ABI returns 0 or a negative code; text via vaw_last_error().  The C++ shim
+ * (video_annotator_b200/host/FrameSourceWarp.cpp) turns non-zero into `throw int`. */
+enum {
+    VAW_OK = 0,
+    VAW_ERR_INVALID = -2,     /* bad argument / unsupported parameter               */
+    VAW_ERR_CUDA = -3,        /* CUDA runtime or driver error, or no device          */
+    VAW_ERR_UNSUPPORTED = -4, /* e.g. interpolation other than INTER_LINEAR          */
+    VAW_ERR_NOMEM = -5
+};
+
+/* ---- pixel formats ----------------------------------------------------------------
+ * VAW_FORMAT_NV12: the buffer FrameSourceFfmpegOpenCl produces
+ *   (opencv/FrameSourceFfmpegOpenCl.cpp:58,75-85): one 8-bit plane, `pitch` bytes per
+ *   row, Y rows 0..H-1 then H/2 rows of interleaved U,V.  W and H even.
+ * VAW_FORMAT_BGR24: interleaved 8UC3 -- what the reference actually hands to
+ *   warp_frame after cvtColor (opencv/FrameSourceWarp.cpp:401,445).
+ * VAW_FORMAT_GRAY8: single 8-bit plane. */
+enum { VAW_FORMAT_NV12 = 0, VAW_FORMAT_BGR24 = 1, VAW_FORMAT_GRAY8 = 2 };
+
+/* cv::InterpolationFlags values (opencv/FrameSourceWarp.hpp:90); only LINEAR exists. */
+enum { VAW_INTER_NEAREST = 0, VAW_INTER_LINEAR = 1, VAW_INTER_CUBIC = 2 };
+
+/* Kernel variants (all bit-identical in output; for A/B measurement). */
+enum {
+    VAW_VARIANT_AUTO = 0,
+    VAW_VARIANT_GATHER = 1, /* per-tap loads through L1/L2                         */
+    VAW_VARIANT_TEX = 2,    /* texture-unit 2x2 gather (tld4) + integer blend      */
+    VAW_VARIANT_TILED = 3   /* persistent CTAs, source tiles staged in shared mem  */
+};
+
+/* ---- parameters -------------------------------------------------------------------
+ * The 8 scalars FrameSourceWarp::warp_frame passes to createMap, in its order
+ * (opencv/FrameSourceWarp.cpp:283-290), kept as doubles and cast to float inside the
+ * library exactly where the reference casts to cl_float; plus sizes, format, border. */
+typedef struct vaw_params {
+    double src_center_x, src_center_y; /* m_input_camera.matrix(0,2), (1,2)          */
+    double src_focal_x, src_focal_y;   /* m_input_camera.matrix(0,0), (1,1)          */
+    double map_center_x, map_center_y; /* m_output_camera.matrix(0,2), (1,2)         */
+    double map_focal_x, map_focal_y;   /* m_output_camera.matrix(0,0), (1,1)         */
+    int32_t src_width, src_height;     /* input image size (luma), <= 32766          */
+    int32_t out_width, out_height;     /* m_output_camera.size, <= 32766             */
+    int32_t format;                    /* VAW_FORMAT_*                               */
+    int32_t interpolation;             /* VAW_INTER_LINEAR                           */
+    uint8_t border[4];                 /* NV12: Y,U,V  BGR24: B,G,R  (cv::remap's
+                                          borderValue; OpenCV default is 0; the NV12
+                                          neutral chroma is 128)                     */
+    int32_t variant;                   /* VAW_VARIANT_*                              */
+    int32_t reserved[7];
+} vaw_params;
+
+/* Camera description (opencv/FrameSourceWarp.hpp:14-34). */
+typedef struct vaw_camera {
+    int32_t model;     /* 0 RECTILINEAR, 1 FISHEYE (CameraModel, FrameSourceWarp.hpp:23-26) */
+    int32_t width, height;
+    int32_t reserved;
+    double matrix[9];  /* row-major 3x3 */
+    double distortion[4];
+} vaw_camera;
+
+/* CameraPreset, opencv/FrameSourceWarp.hpp:14-21 (same order, same values). */
+enum {
+    VAW_GOPRO_H4B_WIDE43_PUBLISHED = 0,
+    VAW_GOPRO_H4B_WIDE43_MEASURED = 1,
+    VAW_GOPRO_H4B_WIDE43_MEASURED_STABILISATION = 2,
+    VAW_GOPRO_H4B_WIDE169_PUBLISHED = 3,
+    VAW_GOPRO_H4B_WIDE169_MEASURED = 4,
+    VAW_GOPRO_H4B_WIDE169_MEASURED_STABILISATION = 5
+};
+
+typedef struct vaw_ctx vaw_ctx;
+
+/* ---- camera producers (host only, double precision) -------------------------------
+ * Replace get_preset_camera (opencv/FrameSourceWarp.cpp:27-86) and get_output_camera
+ * (:88-165), quirks included (int FOV constants, height-scaled fx, integer diagonals,
+ * truncated size). */
+int vaw_get_preset_camera(int preset, int width, int height, vaw_camera *out);
+int vaw_get_output_camera(const vaw_camera *input, double scale, int crop_borders, double zoom,
+                          vaw_camera *out);
+/* Fill the 8 scalars + sizes of `p` from two cameras (FrameSourceWarp.cpp:283-290);
+ * for NV12 the output size is rounded down to even. Other fields are left untouched. */
+int vaw_params_from_cameras(const vaw_camera *input, const vaw_camera *output, int format,
+                            vaw_params *p);
+
+/* ---- context ----------------------------------------------------------------------
+ * Replaces the state FrameSourceWarp's constructor builds (cameras, map buffers, the
+ * compiled createMap program: opencv/FrameSourceWarp.cpp:199-226).  No map buffer is
+ * allocated: the map is computed on the fly inside the sampler.  One ctx per device
+ * per host thread; not thread-safe. */
+int vaw_create(const vaw_params *params, int device, vaw_ctx **out);
+void vaw_destroy(vaw_ctx *ctx);
+const char *vaw_last_error(const vaw_ctx *ctx); /* ctx may be NULL: last create error */
+const char *vaw_strerror(int code);
+/* Bytes of one frame buffer with row pitch `pitch` (NV12: pitch*H*3/2). */
+size_t vaw_frame_bytes(int format, int width, int height, int pitch);
+/* Number of this library's kernels launched through ctx so far. */
+uint64_t vaw_launch_count(const vaw_ctx *ctx);
+
+/* ---- the warp ---------------------------------------------------------------------
+ * vaw_warp replaces `cv::UMat FrameSourceWarp::warp_frame(cv::UMat input, cv::Mat rotation)`
+ * (opencv/FrameSourceWarp.hpp:76, opencv/FrameSourceWarp.cpp:272-314): rotation is the
+ * 3x3 CV_64F matrix row-major, cast to float per element as at :291-299.  src/dst are
+ * DEVICE pointers; asynchronous on `stream` (a cudaStream_t; NULL = default stream).
+ * Unlike the reference the caller owns the output buffer. */
+int vaw_warp(vaw_ctx *ctx, const uint8_t *src, int src_pitch, uint8_t *dst, int dst_pitch,
+             const double rotation[9], void *stream);
+
+/* Same for n_frames frames in ONE launch: frame i is read at src + i*src_frame_stride,
+ * written at dst + i*dst_frame_stride, with rotation rotations[9*i .. 9*i+8] (fp32,
+ * row-major, DEVICE memory).  This is how a 3-4 us frame stays off the launch-latency
+ * floor. */
+int vaw_warp_batch(vaw_ctx *ctx, const uint8_t *src, int src_pitch, size_t src_frame_stride,
+                   uint8_t *dst, int dst_pitch, size_t dst_frame_stride,
+                   const float *rotations, int n_frames, void *stream);
+
+/* double[9*n] (host) -> float[9*n] (device), the (cl_float) cast of FrameSourceWarp.cpp:291-299.
+ * Synchronous with respect to the host buffer. */
+int vaw_upload_rotations(vaw_ctx *ctx, const double *rotations_host, int n_frames,
+                         float *rotations_dev, void *stream);
+
+/* Whole path with HOST buffers (tightly packed frames: pitch = width*channels):
+ * pinned staging, host->device copy, warp, device->host copy, pipelined in chunks on
+ * the ctx's own streams.  Returns when dst_host is complete.  This is the call a
+ * FrameSource-style user makes when frames live in host memory. */
+int vaw_warp_batch_host(vaw_ctx *ctx, const uint8_t *src_host, uint8_t *dst_host,
+                        const double *rotations_host, int n_frames);
+
+/* The map createMap.cl would have written (opencv/createMap.cl:42-49), from the same
+ * device function the sampler uses.  plane 0: luma map (out_h x out_w); plane 1: NV12
+ * chroma map (out_h/2 x out_w/2).  map pitch in floats.  For parity tests/debugging. */
+int vaw_dump_coords(vaw_ctx *ctx, const double rotation[9], int plane, float *map_x,
+                    float *map_y, int map_pitch, void *stream);
+
+/* ---- synthetic frames (decode is out of scope; BASELINE.json north_star) ------------
+ * Fill n_frames NV12 frames in device memory with the integer test pattern
+ * (frame index first_index + i). */
+int vaw_synth_nv12(uint8_t *dst, int width, int height, int pitch, size_t frame_stride,
+                   int first_index, int n_frames, uint32_t seed, int white_noise, int device,
+                   void *stream);
+
+/* ---- diagnostics ------------------------------------------------------------------
+ * vaw_set_option(ctx, "force_exact", 1): evaluate every pixel with the IEEE library
+ * division/sqrt sequences instead of the range-certified shared-reciprocal ones (the two
+ * are bit-identical; tests compare them).
+ * vaw_selftest_math: on-device comparison of those fast sequences with __frcp_rn /
+ * __fdiv_rn / __fsqrt_rn / the k = atan(r)/r step on random operands in the certified
+ * ranges; mismatches[4] = {rcp, div, sqrt, k}. */
+int vaw_set_option(vaw_ctx *ctx, const char *name, int value);
+int vaw_selftest_math(int device, uint32_t seed, uint64_t n_per_thread, uint64_t mismatches[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VAW_H */

@@ -1,0 +1,59 @@
+"""Build recipe for libvaw.so (hand-written CUDA for sm_100a behind the C-ABI of include/vaw.h).
+
+nvcc cross-compiles without a GPU.  The library is built IN-TREE
+(video_annotator_b200/libvaw.so) so that it travels with the repository snapshot.
+"""
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libvaw.so")
+
+SOURCES = ["vaw_kernels.cu", "vaw_api.cu", "vaw_camera.cpp"]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    # the coordinate code is written with explicit _rn intrinsics; this is belt and braces
+    "-fmad=false",
+    "-Xcompiler", "-fPIC,-O2,-Wall",
+    "--shared", "-cudart", "static",
+]
+
+
+def nvcc():
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(exe):
+        raise RuntimeError("nvcc not found: libvaw.so cannot be built (there is no CPU fallback)")
+    return exe
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    deps.append(os.path.join(os.path.dirname(HERE), "include", "vaw.h"))
+    deps.append(os.path.abspath(__file__))
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    env = dict(os.environ)
+    # use the system host compiler regardless of CC/CXX wrappers
+    cmd = [nvcc(), *NVCC_FLAGS, "-ccbin", shutil.which("g++") or "g++", "-o", LIB,
+           *[os.path.join(CSRC, s) for s in SOURCES]]
+    if verbose:
+        cmd.insert(1, "-Xptxas")
+        cmd.insert(2, "-v")
+    subprocess.check_call(cmd, env=env)
+    return LIB
+
+
+if __name__ == "__main__":
+    import sys
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

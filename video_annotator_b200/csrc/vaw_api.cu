@@ -1,0 +1,419 @@
+// vaw_api.cu -- the C-ABI of libvaw.so (declared in include/vaw.h).
+//
+// Replaces the state and the call FrameSourceWarp builds/makes for its warp
+// (/root/reference/opencv/FrameSourceWarp.cpp:199-226 constructor, :272-314 warp_frame):
+// a context holds the camera scalars cast to float exactly where the reference casts to
+// cl_float (:283-299), the per-column/per-row ray tables, and -- for the host-buffer
+// entry point -- a small ring of device staging buffers and streams.  No map buffers.
+// There is no CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include "../../include/vaw.h"
+#include "vaw_internal.h"
+
+namespace {
+
+constexpr int kStages = 3;                      // host-path pipeline depth
+constexpr size_t kChunkBytes = 96u << 20;       // target bytes of source frames per chunk
+thread_local std::string g_create_error;
+
+struct Stage {
+    cudaStream_t stream = nullptr;
+    uint8_t *dev_in = nullptr, *dev_out = nullptr, *pin_in = nullptr, *pin_out = nullptr;
+    float *dev_rot = nullptr, *pin_rot = nullptr;
+    // pending output of the chunk in flight on this stage
+    uint8_t* host_dst = nullptr;
+    size_t out_bytes = 0;
+    bool busy = false, out_staged = false;
+};
+
+}  // namespace
+
+struct vaw_ctx {
+    vaw_params p{};
+    int device = 0;
+    vaw::Geom g{};
+    float *xtab = nullptr, *ytab = nullptr;
+    int channels = 1;
+    size_t src_frame_bytes = 0, dst_frame_bytes = 0;  // tightly packed
+    uint64_t launches = 0;
+    std::string err;
+    // host path
+    Stage stage[kStages];
+    int chunk_frames = 0;
+    bool host_ready = false;
+};
+
+namespace {
+
+int fail(vaw_ctx* ctx, int code, const std::string& msg)
+{
+    if (ctx) ctx->err = msg;
+    else g_create_error = msg;
+    return code;
+}
+
+int cuda_fail(vaw_ctx* ctx, cudaError_t e, const char* what)
+{
+    return fail(ctx, VAW_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define VAW_CUDA(ctx, call)                                        \
+    do {                                                           \
+        cudaError_t e_ = (call);                                   \
+        if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call);   \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+vaw::Rot rot_from_double(const double r[9])
+{
+    vaw::Rot R;
+    for (int i = 0; i < 9; ++i) R.r[i] = (float)r[i];  // the (cl_float) cast, FrameSourceWarp.cpp:291-299
+    return R;
+}
+
+bool centre_ok(float c) { return c == 0.0f || std::fabs(c) >= 8.67361738e-19f /* 2^-60 */; }
+
+int check_buffers(vaw_ctx* ctx, const void* src, int src_pitch, void* dst, int dst_pitch)
+{
+    if (!ctx) return VAW_ERR_INVALID;
+    if (!src || !dst) return fail(ctx, VAW_ERR_INVALID, "null frame pointer");
+    if (src_pitch < ctx->p.src_width * ctx->channels || dst_pitch < ctx->p.out_width * ctx->channels)
+        return fail(ctx, VAW_ERR_INVALID, "pitch smaller than a row");
+    if (ctx->p.format == VAW_FORMAT_NV12 &&
+        ((src_pitch & 1) || (reinterpret_cast<uintptr_t>(src) & 1)))
+        return fail(ctx, VAW_ERR_INVALID, "NV12 source base and pitch must be even");
+    return VAW_OK;
+}
+
+int launch(vaw_ctx* ctx, const uint8_t* src, int src_pitch, size_t src_stride, uint8_t* dst,
+           int dst_pitch, size_t dst_stride, const float* rots, const vaw::Rot* rot0, int n_frames,
+           cudaStream_t st)
+{
+    vaw::Geom g = ctx->g;
+    g.src_pitch = src_pitch;
+    g.dst_pitch = dst_pitch;
+    vaw::FrameBatch b{};
+    b.src = src;
+    b.dst = dst;
+    b.src_frame_stride = src_stride;
+    b.dst_frame_stride = dst_stride;
+    b.rots = rots;
+    if (rot0) b.rot0 = *rot0;
+    // grid.z is limited to 65535 frames per launch
+    for (int first = 0; first < n_frames; first += 65535) {
+        vaw::FrameBatch bb = b;
+        bb.n_frames = n_frames - first < 65535 ? n_frames - first : 65535;
+        bb.src = src + (size_t)first * src_stride;
+        bb.dst = dst + (size_t)first * dst_stride;
+        if (rots) bb.rots = rots + (size_t)first * 9;
+        cudaError_t e;
+        switch (ctx->p.format) {
+        case VAW_FORMAT_NV12: e = vaw::launch_warp_nv12_gather(g, bb, st); break;
+        case VAW_FORMAT_BGR24: e = vaw::launch_warp_packed_gather(g, bb, 3, st); break;
+        default: e = vaw::launch_warp_packed_gather(g, bb, 1, st); break;
+        }
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "warp kernel launch");
+        ctx->launches++;
+    }
+    return VAW_OK;
+}
+
+void free_host_path(vaw_ctx* ctx)
+{
+    for (Stage& s : ctx->stage) {
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        cudaFree(s.dev_in); cudaFree(s.dev_out); cudaFree(s.dev_rot);
+        cudaFreeHost(s.pin_in); cudaFreeHost(s.pin_out); cudaFreeHost(s.pin_rot);
+        if (s.stream) cudaStreamDestroy(s.stream);
+        s = Stage{};
+    }
+    ctx->host_ready = false;
+}
+
+int init_host_path(vaw_ctx* ctx)
+{
+    if (ctx->host_ready) return VAW_OK;
+    size_t per = ctx->src_frame_bytes;
+    int cf = (int)(kChunkBytes / per);
+    ctx->chunk_frames = cf < 1 ? 1 : (cf > 64 ? 64 : cf);
+    for (Stage& s : ctx->stage) {
+        VAW_CUDA(ctx, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        VAW_CUDA(ctx, cudaMalloc(&s.dev_in, ctx->src_frame_bytes * ctx->chunk_frames));
+        VAW_CUDA(ctx, cudaMalloc(&s.dev_out, ctx->dst_frame_bytes * ctx->chunk_frames));
+        VAW_CUDA(ctx, cudaMalloc(&s.dev_rot, sizeof(float) * 9 * ctx->chunk_frames));
+        VAW_CUDA(ctx, cudaMallocHost(&s.pin_rot, sizeof(float) * 9 * ctx->chunk_frames));
+    }
+    ctx->host_ready = true;
+    return VAW_OK;
+}
+
+bool is_pinned(const void* p)
+{
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* vaw_strerror(int code)
+{
+    switch (code) {
+    case VAW_OK: return "ok";
+    case VAW_ERR_INVALID: return "invalid argument";
+    case VAW_ERR_CUDA: return "CUDA error or no device";
+    case VAW_ERR_UNSUPPORTED: return "unsupported";
+    case VAW_ERR_NOMEM: return "out of memory";
+    default: return "unknown error";
+    }
+}
+
+const char* vaw_last_error(const vaw_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+size_t vaw_frame_bytes(int format, int width, int height, int pitch)
+{
+    (void)width;
+    if (format == VAW_FORMAT_NV12) return (size_t)pitch * (size_t)(height + height / 2);
+    return (size_t)pitch * (size_t)height;
+}
+
+uint64_t vaw_launch_count(const vaw_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
+{
+    if (!params || !out) return fail(nullptr, VAW_ERR_INVALID, "null argument");
+    *out = nullptr;
+    const vaw_params& p = *params;
+    if (p.interpolation != VAW_INTER_LINEAR)
+        return fail(nullptr, VAW_ERR_UNSUPPORTED, "only INTER_LINEAR is implemented");
+    if (p.format != VAW_FORMAT_NV12 && p.format != VAW_FORMAT_BGR24 && p.format != VAW_FORMAT_GRAY8)
+        return fail(nullptr, VAW_ERR_INVALID, "unknown pixel format");
+    if (p.variant != VAW_VARIANT_AUTO && p.variant != VAW_VARIANT_GATHER)
+        return fail(nullptr, VAW_ERR_UNSUPPORTED, "kernel variant not available in this build");
+    // `short` indices in createMap.cl:10-11 and int16 taps in cv::remap cap both sizes
+    if (p.src_width < 2 || p.src_height < 2 || p.out_width < 1 || p.out_height < 1 ||
+        p.src_width > 32766 || p.src_height > 32766 || p.out_width > 32766 || p.out_height > 32766)
+        return fail(nullptr, VAW_ERR_INVALID, "sizes must be in [2, 32766]");
+    if (p.format == VAW_FORMAT_NV12 &&
+        ((p.src_width | p.src_height | p.out_width | p.out_height) & 1))
+        return fail(nullptr, VAW_ERR_INVALID, "NV12 sizes must be even");
+
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, VAW_ERR_CUDA, "no CUDA device: libvaw has no CPU fallback");
+    }
+    if (device < 0 || device >= n_dev) return fail(nullptr, VAW_ERR_INVALID, "bad device ordinal");
+
+    vaw_ctx* ctx = new (std::nothrow) vaw_ctx;
+    if (!ctx) return fail(nullptr, VAW_ERR_NOMEM, "out of host memory");
+    ctx->p = p;
+    ctx->device = device;
+    ctx->channels = p.format == VAW_FORMAT_BGR24 ? 3 : 1;
+    vaw::Geom& g = ctx->g;
+    g.scx = (float)p.src_center_x; g.scy = (float)p.src_center_y;   // FrameSourceWarp.cpp:283-284
+    g.sfx = (float)p.src_focal_x;  g.sfy = (float)p.src_focal_y;    // :285-286
+    g.mcx = (float)p.map_center_x; g.mcy = (float)p.map_center_y;   // :287-288
+    g.mfx = (float)p.map_focal_x;  g.mfy = (float)p.map_focal_y;    // :289-290
+    g.src_w = p.src_width; g.src_h = p.src_height;
+    g.out_w = p.out_width; g.out_h = p.out_height;
+    g.border = (unsigned)p.border[0] | ((unsigned)p.border[1] << 8) | ((unsigned)p.border[2] << 16) |
+               ((unsigned)p.border[3] << 24);
+    g.force_exact = (!centre_ok(g.scx) || !centre_ok(g.scy)) ? 1 : 0;
+    ctx->src_frame_bytes = vaw_frame_bytes(p.format, p.src_width, p.src_height, p.src_width * ctx->channels);
+    ctx->dst_frame_bytes = vaw_frame_bytes(p.format, p.out_width, p.out_height, p.out_width * ctx->channels);
+
+    DeviceGuard dg(device);
+    const int n_x = ((p.out_width + 127) / 128) * 128 + 4, n_y = ((p.out_height + 15) / 16) * 16 + 2;
+    cudaError_t e = cudaMalloc(&ctx->xtab, sizeof(float) * n_x);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->ytab, sizeof(float) * n_y);
+    if (e == cudaSuccess) e = vaw::launch_ray_tables(ctx->xtab, n_x, ctx->ytab, n_y, g.mcx, g.mfx, g.mcy, g.mfy, nullptr);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        int rc = cuda_fail(nullptr, e, "vaw_create");
+        cudaFree(ctx->xtab); cudaFree(ctx->ytab);
+        delete ctx;
+        return rc;
+    }
+    ctx->launches = 1;
+    g.xtab = ctx->xtab;
+    g.ytab = ctx->ytab;
+    *out = ctx;
+    return VAW_OK;
+}
+
+void vaw_destroy(vaw_ctx* ctx)
+{
+    if (!ctx) return;
+    DeviceGuard dg(ctx->device);
+    free_host_path(ctx);
+    cudaFree(ctx->xtab);
+    cudaFree(ctx->ytab);
+    delete ctx;
+}
+
+int vaw_set_option(vaw_ctx* ctx, const char* name, int value)
+{
+    if (!ctx || !name) return VAW_ERR_INVALID;
+    if (!std::strcmp(name, "force_exact")) { ctx->g.force_exact = value ? 1 : 0; return VAW_OK; }
+    return fail(ctx, VAW_ERR_INVALID, std::string("unknown option ") + name);
+}
+
+int vaw_warp(vaw_ctx* ctx, const uint8_t* src, int src_pitch, uint8_t* dst, int dst_pitch,
+             const double rotation[9], void* stream)
+{
+    int rc = check_buffers(ctx, src, src_pitch, dst, dst_pitch);
+    if (rc) return rc;
+    if (!rotation) return fail(ctx, VAW_ERR_INVALID, "null rotation");
+    DeviceGuard dg(ctx->device);
+    vaw::Rot R = rot_from_double(rotation);
+    return launch(ctx, src, src_pitch, 0, dst, dst_pitch, 0, nullptr, &R, 1, (cudaStream_t)stream);
+}
+
+int vaw_warp_batch(vaw_ctx* ctx, const uint8_t* src, int src_pitch, size_t src_frame_stride,
+                   uint8_t* dst, int dst_pitch, size_t dst_frame_stride, const float* rotations,
+                   int n_frames, void* stream)
+{
+    int rc = check_buffers(ctx, src, src_pitch, dst, dst_pitch);
+    if (rc) return rc;
+    if (n_frames < 0 || (n_frames > 0 && !rotations)) return fail(ctx, VAW_ERR_INVALID, "bad batch");
+    if (n_frames == 0) return VAW_OK;
+    if (ctx->p.format == VAW_FORMAT_NV12 && (src_frame_stride & 1))
+        return fail(ctx, VAW_ERR_INVALID, "NV12 frame stride must be even");
+    DeviceGuard dg(ctx->device);
+    return launch(ctx, src, src_pitch, src_frame_stride, dst, dst_pitch, dst_frame_stride, rotations,
+                  nullptr, n_frames, (cudaStream_t)stream);
+}
+
+int vaw_upload_rotations(vaw_ctx* ctx, const double* rotations_host, int n_frames,
+                         float* rotations_dev, void* stream)
+{
+    if (!ctx) return VAW_ERR_INVALID;
+    if (!rotations_host || !rotations_dev || n_frames < 0) return fail(ctx, VAW_ERR_INVALID, "bad rotations");
+    DeviceGuard dg(ctx->device);
+    std::string tmp(sizeof(float) * 9 * (size_t)n_frames, '\0');
+    float* f = reinterpret_cast<float*>(&tmp[0]);
+    for (size_t i = 0; i < (size_t)n_frames * 9; ++i) f[i] = (float)rotations_host[i];
+    VAW_CUDA(ctx, cudaMemcpyAsync(rotations_dev, f, tmp.size(), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    VAW_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+    return VAW_OK;
+}
+
+int vaw_warp_batch_host(vaw_ctx* ctx, const uint8_t* src_host, uint8_t* dst_host,
+                        const double* rotations_host, int n_frames)
+{
+    if (!ctx) return VAW_ERR_INVALID;
+    if (!src_host || !dst_host || !rotations_host || n_frames < 0)
+        return fail(ctx, VAW_ERR_INVALID, "null host buffer");
+    if (n_frames == 0) return VAW_OK;
+    DeviceGuard dg(ctx->device);
+    int rc = init_host_path(ctx);
+    if (rc) return rc;
+    const size_t sfb = ctx->src_frame_bytes, dfb = ctx->dst_frame_bytes;
+    const int src_pitch = ctx->p.src_width * ctx->channels, dst_pitch = ctx->p.out_width * ctx->channels;
+    // Pinned (page-locked) user buffers are copied from/to directly; pageable ones go
+    // through lazily allocated pinned staging so that the copies stay asynchronous.
+    const bool src_pinned = is_pinned(src_host), dst_pinned = is_pinned(dst_host);
+
+    auto drain = [&](Stage& s) -> int {
+        if (!s.busy) return VAW_OK;
+        VAW_CUDA(ctx, cudaStreamSynchronize(s.stream));
+        if (s.out_staged) std::memcpy(s.host_dst, s.pin_out, s.out_bytes);
+        s.busy = false;
+        return VAW_OK;
+    };
+
+    int k = 0;
+    for (int first = 0; first < n_frames; first += ctx->chunk_frames, ++k) {
+        Stage& s = ctx->stage[k % kStages];
+        if ((rc = drain(s))) return rc;
+        const int n = n_frames - first < ctx->chunk_frames ? n_frames - first : ctx->chunk_frames;
+        const uint8_t* hsrc = src_host + (size_t)first * sfb;
+        uint8_t* hdst = dst_host + (size_t)first * dfb;
+        for (int i = 0; i < n * 9; ++i) s.pin_rot[i] = (float)rotations_host[(size_t)first * 9 + i];
+        VAW_CUDA(ctx, cudaMemcpyAsync(s.dev_rot, s.pin_rot, sizeof(float) * 9 * n, cudaMemcpyHostToDevice, s.stream));
+        if (!src_pinned) {
+            if (!s.pin_in) VAW_CUDA(ctx, cudaMallocHost(&s.pin_in, sfb * ctx->chunk_frames));
+            std::memcpy(s.pin_in, hsrc, sfb * n);
+            hsrc = s.pin_in;
+        }
+        VAW_CUDA(ctx, cudaMemcpyAsync(s.dev_in, hsrc, sfb * n, cudaMemcpyHostToDevice, s.stream));
+        rc = launch(ctx, s.dev_in, src_pitch, sfb, s.dev_out, dst_pitch, dfb, s.dev_rot, nullptr, n, s.stream);
+        if (rc) return rc;
+        s.out_staged = !dst_pinned;
+        if (s.out_staged && !s.pin_out) VAW_CUDA(ctx, cudaMallocHost(&s.pin_out, dfb * ctx->chunk_frames));
+        VAW_CUDA(ctx, cudaMemcpyAsync(s.out_staged ? s.pin_out : hdst, s.dev_out, dfb * n, cudaMemcpyDeviceToHost, s.stream));
+        s.host_dst = hdst;
+        s.out_bytes = dfb * n;
+        s.busy = true;
+    }
+    // drain in submission order
+    for (int i = 0; i < kStages; ++i)
+        if ((rc = drain(ctx->stage[(k + i) % kStages]))) return rc;
+    return VAW_OK;
+}
+
+int vaw_dump_coords(vaw_ctx* ctx, const double rotation[9], int plane, float* map_x, float* map_y,
+                    int map_pitch, void* stream)
+{
+    if (!ctx) return VAW_ERR_INVALID;
+    if (!rotation || !map_x || !map_y) return fail(ctx, VAW_ERR_INVALID, "null argument");
+    if (plane != 0 && !(plane == 1 && ctx->p.format == VAW_FORMAT_NV12))
+        return fail(ctx, VAW_ERR_INVALID, "plane 1 exists for NV12 only");
+    const int need = plane ? ctx->p.out_width / 2 : ctx->p.out_width;
+    if (map_pitch < need) return fail(ctx, VAW_ERR_INVALID, "map pitch smaller than a row");
+    DeviceGuard dg(ctx->device);
+    cudaError_t e = vaw::launch_dump_coords(ctx->g, rot_from_double(rotation), plane, map_x, map_y,
+                                            map_pitch, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "dump_coords launch");
+    ctx->launches++;
+    return VAW_OK;
+}
+
+int vaw_synth_nv12(uint8_t* dst, int width, int height, int pitch, size_t frame_stride,
+                   int first_index, int n_frames, uint32_t seed, int white_noise, int device,
+                   void* stream)
+{
+    if (!dst || width < 2 || height < 2 || ((width | height) & 1) || pitch < width || n_frames < 0)
+        return fail(nullptr, VAW_ERR_INVALID, "bad synth arguments");
+    DeviceGuard dg(device);
+    for (int first = 0; first < n_frames; first += 65535) {
+        int n = n_frames - first < 65535 ? n_frames - first : 65535;
+        cudaError_t e = vaw::launch_synth_nv12(dst + (size_t)first * frame_stride, width, height, pitch,
+                                               frame_stride, first_index + first, n, seed, white_noise,
+                                               (cudaStream_t)stream);
+        if (e != cudaSuccess) return cuda_fail(nullptr, e, "synth launch");
+    }
+    return VAW_OK;
+}
+
+int vaw_selftest_math(int device, uint32_t seed, uint64_t n_per_thread, uint64_t mismatches[4])
+{
+    if (!mismatches) return VAW_ERR_INVALID;
+    DeviceGuard dg(device);
+    unsigned long long* d = nullptr;
+    VAW_CUDA(nullptr, cudaMalloc(&d, 4 * sizeof(unsigned long long)));
+    cudaMemset(d, 0, 4 * sizeof(unsigned long long));
+    cudaError_t e = vaw::launch_selftest_math(seed, n_per_thread, d, nullptr);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    unsigned long long h[4] = {0, 0, 0, 0};
+    if (e == cudaSuccess) e = cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return cuda_fail(nullptr, e, "selftest");
+    for (int i = 0; i < 4; ++i) mismatches[i] = h[i];
+    return VAW_OK;
+}
+
+}  // extern "C"

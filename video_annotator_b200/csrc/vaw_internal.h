@@ -1,0 +1,39 @@
+// vaw_internal.h -- launchers shared between the kernels and the C-ABI layer.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "vaw_coords.cuh"
+
+namespace vaw {
+
+struct FrameBatch {
+    const uint8_t* src;
+    uint8_t* dst;
+    size_t src_frame_stride, dst_frame_stride;
+    const float* rots;  // device, 9 floats per frame, or nullptr -> rot0 for every frame
+    Rot rot0;
+    int n_frames;
+};
+
+// xtab[u] = (u - mcx)/mfx for u < n_x, ytab[v] = (v - mcy)/mfy for v < n_y (createMap.cl:16-17)
+cudaError_t launch_ray_tables(float* xtab, int n_x, float* ytab, int n_y, float mcx, float mfx,
+                              float mcy, float mfy, cudaStream_t st);
+
+// Fused map + remap, NV12 luma and chroma in one launch (variant GATHER).
+cudaError_t launch_warp_nv12_gather(const Geom& g, const FrameBatch& b, cudaStream_t st);
+// Fused map + remap for interleaved 1- or 3-channel frames (GRAY8 / BGR24).
+cudaError_t launch_warp_packed_gather(const Geom& g, const FrameBatch& b, int channels,
+                                      cudaStream_t st);
+// The map createMap.cl would write; plane 0 luma, plane 1 NV12 chroma.
+cudaError_t launch_dump_coords(const Geom& g, const Rot& rot, int plane, float* map_x, float* map_y,
+                               int map_pitch, cudaStream_t st);
+// Integer synthetic content (mirror of oracle/synth_ref.c).
+cudaError_t launch_synth_nv12(uint8_t* dst, int w, int h, int pitch, size_t frame_stride,
+                              int first_index, int n_frames, uint32_t seed, int white,
+                              cudaStream_t st);
+// Device self-test of the Fast-mode primitives against the IEEE intrinsics.
+cudaError_t launch_selftest_math(uint32_t seed, unsigned long long n_per_thread,
+                                 unsigned long long* mismatches /* device, 4 counters */,
+                                 cudaStream_t st);
+
+}  // namespace vaw

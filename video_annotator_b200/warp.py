@@ -1,0 +1,217 @@
+"""Python mirror of the reference's warp interface, over the C-ABI.
+
+Mirrors /root/reference/opencv/FrameSourceWarp.hpp:14-34 (CameraPreset, Camera) and the
+private FrameSourceWarp::warp_frame (FrameSourceWarp.cpp:272-314) as WarpContext.warp*.
+Device buffers are torch uint8 CUDA tensors (plumbing only); the arithmetic is all in
+libvaw.so.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+FORMAT_NV12, FORMAT_BGR24, FORMAT_GRAY8 = 0, 1, 2
+INTER_LINEAR = 1
+
+# CameraPreset, FrameSourceWarp.hpp:14-21
+GOPRO_H4B_WIDE43_PUBLISHED = 0
+GOPRO_H4B_WIDE43_MEASURED = 1
+GOPRO_H4B_WIDE43_MEASURED_STABILISATION = 2
+GOPRO_H4B_WIDE169_PUBLISHED = 3
+GOPRO_H4B_WIDE169_MEASURED = 4
+GOPRO_H4B_WIDE169_MEASURED_STABILISATION = 5
+
+
+class VawError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"vaw error {code}: {msg}")
+        self.code = code
+
+
+class Camera:
+    """Camera (FrameSourceWarp.hpp:28-34): model, 3x3 matrix, distortion, size."""
+
+    def __init__(self, c):
+        self._c = c
+
+    @property
+    def K(self):
+        return np.array(self._c.matrix[:], np.float64).reshape(3, 3)
+
+    @property
+    def size(self):
+        return self._c.width, self._c.height
+
+    @property
+    def model(self):
+        return self._c.model
+
+    @staticmethod
+    def from_matrix(K, width, height, model=0):
+        c = _lib.VawCamera()
+        c.model, c.width, c.height = model, width, height
+        for i, v in enumerate(np.asarray(K, np.float64).reshape(9)):
+            c.matrix[i] = v
+        return Camera(c)
+
+
+def _check(rc, ctx=None):
+    if rc != 0:
+        msg = _lib.load().vaw_last_error(ctx)
+        raise VawError(rc, (msg or b"").decode() or _lib.load().vaw_strerror(rc).decode())
+
+
+def get_preset_camera(preset, width, height):
+    """get_preset_camera, FrameSourceWarp.cpp:27-86."""
+    c = _lib.VawCamera()
+    _check(_lib.load().vaw_get_preset_camera(preset, width, height, C.byref(c)))
+    return Camera(c)
+
+
+def get_output_camera(cam, scale=1.0, crop_borders=False, zoom=1.0):
+    """get_output_camera, FrameSourceWarp.cpp:88-165."""
+    c = _lib.VawCamera()
+    _check(_lib.load().vaw_get_output_camera(C.byref(cam._c), scale, int(crop_borders), zoom, C.byref(c)))
+    return Camera(c)
+
+
+def _rot_arg(rot):
+    r = np.ascontiguousarray(np.asarray(rot, np.float64).reshape(-1))
+    return r, r.ctypes.data_as(_lib.f64p)
+
+
+def _stream_handle(stream):
+    if stream is None:
+        import torch
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(int(stream))
+
+
+class WarpContext:
+    """Owns a vaw_ctx: the state FrameSourceWarp's constructor builds (FrameSourceWarp.cpp:199-226)."""
+
+    def __init__(self, input_camera, output_camera, fmt=FORMAT_NV12, border=(0, 128, 128, 0),
+                 device=0, variant=0, out_size=None, interpolation=INTER_LINEAR):
+        lib = _lib.load()
+        p = _lib.VawParams()
+        _check(lib.vaw_params_from_cameras(C.byref(input_camera._c), C.byref(output_camera._c), fmt, C.byref(p)))
+        if out_size is not None:
+            p.out_width, p.out_height = out_size
+        p.interpolation = interpolation
+        p.variant = variant
+        b = list(border) + [0] * (4 - len(border))
+        for i in range(4):
+            p.border[i] = int(b[i])
+        self.params = p
+        self.fmt = fmt
+        self.device = device
+        self.channels = 3 if fmt == FORMAT_BGR24 else 1
+        h = C.c_void_p()
+        _check(lib.vaw_create(C.byref(p), device, C.byref(h)))
+        self._h = h
+        self._lib = lib
+
+    # sizes ---------------------------------------------------------------------------
+    @property
+    def src_size(self):
+        return self.params.src_width, self.params.src_height
+
+    @property
+    def out_size(self):
+        return self.params.out_width, self.params.out_height
+
+    def frame_bytes(self, which):
+        w, h = self.src_size if which == "src" else self.out_size
+        return self._lib.vaw_frame_bytes(self.fmt, w, h, w * self.channels)
+
+    def frame_shape(self, which):
+        w, h = self.src_size if which == "src" else self.out_size
+        if self.fmt == FORMAT_NV12:
+            return (h * 3 // 2, w)
+        return (h, w, 3) if self.fmt == FORMAT_BGR24 else (h, w)
+
+    @property
+    def launch_count(self):
+        return int(self._lib.vaw_launch_count(self._h))
+
+    def set_option(self, name, value):
+        _check(self._lib.vaw_set_option(self._h, name.encode(), int(value)), self._h)
+
+    # the warp ------------------------------------------------------------------------
+    def warp(self, src, dst, rotation, stream=None, src_pitch=None, dst_pitch=None):
+        """warp_frame(input, rotation), FrameSourceWarp.cpp:272-314.  src/dst: CUDA uint8 tensors."""
+        _, rp = _rot_arg(rotation)
+        sp = src_pitch or self.src_size[0] * self.channels
+        dp = dst_pitch or self.out_size[0] * self.channels
+        _check(self._lib.vaw_warp(self._h, src.data_ptr(), sp, dst.data_ptr(), dp, rp,
+                                  _stream_handle(stream)), self._h)
+        return dst
+
+    def upload_rotations(self, rotations, out, stream=None):
+        """rotations: (n, 3, 3) float64 host -> out: CUDA float32 tensor (n*9)."""
+        r, rp = _rot_arg(rotations)
+        _check(self._lib.vaw_upload_rotations(self._h, rp, r.size // 9, out.data_ptr(),
+                                              _stream_handle(stream)), self._h)
+        return out
+
+    def warp_batch(self, src, dst, rotations_dev, n_frames, stream=None, src_pitch=None,
+                   dst_pitch=None, src_stride=None, dst_stride=None):
+        sp = src_pitch or self.src_size[0] * self.channels
+        dp = dst_pitch or self.out_size[0] * self.channels
+        ss = src_stride if src_stride is not None else self.frame_bytes("src")
+        ds = dst_stride if dst_stride is not None else self.frame_bytes("dst")
+        _check(self._lib.vaw_warp_batch(self._h, src.data_ptr(), sp, ss, dst.data_ptr(), dp, ds,
+                                        rotations_dev.data_ptr(), n_frames, _stream_handle(stream)), self._h)
+        return dst
+
+    def warp_batch_host(self, src_host, dst_host, rotations):
+        """Host buffers (numpy arrays or pinned torch CPU tensors), tightly packed frames."""
+        r, rp = _rot_arg(rotations)
+        n = r.size // 9
+
+        def ptr(a):
+            return a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data
+        _check(self._lib.vaw_warp_batch_host(self._h, ptr(src_host), ptr(dst_host), rp, n), self._h)
+        return dst_host
+
+    def dump_coords(self, rotation, plane=0, stream=None):
+        """The map createMap.cl would write (createMap.cl:42-49); returns two CUDA float32 tensors."""
+        import torch
+        w, h = self.out_size
+        if plane == 1:
+            w, h = w // 2, h // 2
+        dev = torch.device("cuda", self.device)
+        mx = torch.empty((h, w), dtype=torch.float32, device=dev)
+        my = torch.empty((h, w), dtype=torch.float32, device=dev)
+        _, rp = _rot_arg(rotation)
+        _check(self._lib.vaw_dump_coords(self._h, rp, plane, mx.data_ptr(), my.data_ptr(), w,
+                                         _stream_handle(stream)), self._h)
+        return mx, my
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.vaw_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def synth_nv12(dst, width, height, n_frames, first_index=0, seed=20260001, white_noise=False,
+               device=0, stream=None):
+    """Fill a CUDA uint8 tensor with n_frames tightly packed synthetic NV12 frames."""
+    lib = _lib.load()
+    fb = width * height * 3 // 2
+    _check(lib.vaw_synth_nv12(dst.data_ptr(), width, height, width, fb, first_index, n_frames,
+                              seed, int(white_noise), device, _stream_handle(stream)))
+    return dst
+
+
+def selftest_math(device=0, seed=1, n_per_thread=1000):
+    out = (C.c_uint64 * 4)()
+    _check(_lib.load().vaw_selftest_math(device, seed, n_per_thread, out))
+    return dict(zip(("rcp", "div", "sqrt", "k"), [int(v) for v in out]))
