@@ -162,6 +162,15 @@ int vaw_warp_batch_host(vaw_ctx *ctx, const uint8_t *src_host, uint8_t *dst_host
 int vaw_dump_coords(vaw_ctx *ctx, const double rotation[9], int plane, float *map_x,
                     float *map_y, int map_pitch, void *stream);
 
+/* The reference's second pass on its own: cv::remap(src, dst, map_x, map_y, INTER_LINEAR,
+ * BORDER_CONSTANT, border) as called at opencv/FrameSourceWarp.cpp:306-312, for 8-bit
+ * images of 1..3 interleaved channels and CV_32FC1 maps (map pitch in floats), all in
+ * DEVICE memory.  Same integer filter as the fused kernels; exists so that callers holding
+ * a map can use it and so that the filter is pinned against cv::remap golden vectors. */
+int vaw_remap_u8(const uint8_t *src, int src_width, int src_height, int src_pitch, int channels,
+                 const float *map_x, const float *map_y, int rows, int cols, int map_pitch,
+                 uint8_t *dst, int dst_pitch, const uint8_t border[4], int device, void *stream);
+
 /* ---- synthetic frames (decode is out of scope; BASELINE.json north_star) ------------
  * Fill n_frames NV12 frames in device memory with the integer test pattern
  * (frame index first_index + i). */

@@ -1,0 +1,117 @@
+"""The C-ABI library (include/vaw.h -> video_annotator_b200/libvaw.so) on a CPU-only host:
+it builds, loads, exports every declared symbol, its host-only entry points work, and the
+compute entry points fail loudly (no CPU fallback) when there is no CUDA device."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from tests.conftest import GOLDEN, ROOT
+
+
+def _declared_symbols():
+    names = set()
+    for fn in os.listdir(os.path.join(ROOT, "include")):
+        if fn.endswith(".h"):
+            text = open(os.path.join(ROOT, "include", fn)).read()
+            text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+            names |= set(re.findall(r"\b(vaw_[a-z0-9_]+)\s*\(", text))
+    return names
+
+
+def test_library_exports_every_declared_symbol():
+    from video_annotator_b200 import _lib
+    lib = _lib.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 17
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/*.h but not exported"
+    # the ctypes mirror binds exactly the declared surface
+    assert set(_lib.SIGNATURES) == declared
+
+
+def test_params_struct_layout_matches_header():
+    from video_annotator_b200 import _lib
+    # 8 doubles + 6 int32 + 4 bytes + int32 + 7 int32 = 124, padded to the 8-byte alignment;
+    # vaw_api.cu static_asserts the same numbers on the C side
+    assert C.sizeof(_lib.VawParams) == 128
+    assert C.sizeof(_lib.VawCamera) == 4 * 4 + 9 * 8 + 4 * 8 == 120
+
+
+def test_strerror_and_frame_bytes():
+    from video_annotator_b200 import _lib
+    lib = _lib.load()
+    assert lib.vaw_strerror(0) == b"ok"
+    assert b"CUDA" in lib.vaw_strerror(-3)
+    assert lib.vaw_frame_bytes(0, 3840, 2160, 3840) == 3840 * 2160 * 3 // 2  # NV12
+    assert lib.vaw_frame_bytes(1, 1759, 998, 1759 * 3) == 1759 * 998 * 3
+    assert lib.vaw_frame_bytes(2, 100, 50, 128) == 128 * 50
+
+
+def test_camera_producers_match_golden_table_and_oracle(oracle):
+    """vaw_get_preset_camera / vaw_get_output_camera (FrameSourceWarp.cpp:27-165)."""
+    import video_annotator_b200 as V
+    t = np.load(os.path.join(GOLDEN, "camera_table.npz"))["table"]
+    for row in t:
+        preset, w, h, scale, crop, zoom, f, cx, cy, ow, oh = row
+        cam = V.get_preset_camera(int(preset), int(w), int(h))
+        ocam = oracle.get_preset_camera(int(preset), int(w), int(h))
+        assert np.array_equal(cam.K, ocam.K)
+        out = V.get_output_camera(cam, scale, bool(crop), zoom)
+        assert out.K[0, 0] == pytest.approx(f, rel=1e-12)
+        assert out.K[0, 2] == pytest.approx(cx, rel=1e-10)
+        assert out.K[1, 2] == pytest.approx(cy, rel=1e-10)
+        assert out.size == (int(ow), int(oh))
+        oout = oracle.get_output_camera(ocam, scale, bool(crop), zoom)
+        assert np.allclose(out.K, oout.K, rtol=1e-13, atol=0)
+        assert out.size == (oout.width, oout.height)
+
+
+def test_camera_producers_reject_bad_arguments():
+    from video_annotator_b200 import _lib
+    lib = _lib.load()
+    cam = _lib.VawCamera()
+    assert lib.vaw_get_preset_camera(99, 1920, 1080, C.byref(cam)) == -2
+    assert lib.vaw_get_preset_camera(0, 0, 1080, C.byref(cam)) == -2
+
+
+def test_create_validates_before_touching_cuda():
+    import video_annotator_b200 as V
+    cam = V.get_preset_camera(4, 1920, 1080)
+    out = V.get_output_camera(cam)
+    with pytest.raises(V.VawError) as e:  # only INTER_LINEAR exists (FrameSourceWarp.hpp:90)
+        V.WarpContext(cam, out, interpolation=2)
+    assert e.value.code == -4
+    with pytest.raises(V.VawError) as e:  # NV12 needs even sizes
+        V.WarpContext(cam, out, out_size=(1759, 998))
+    assert e.value.code == -2
+    with pytest.raises(V.VawError) as e:  # `short` indices (createMap.cl:10-11)
+        V.WarpContext(cam, out, out_size=(40000, 998))
+    assert e.value.code == -2
+
+
+def test_no_cpu_fallback_without_device():
+    """The product path must fail loudly when there is no GPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    import video_annotator_b200 as V
+    cam = V.get_preset_camera(4, 1920, 1080)
+    out = V.get_output_camera(cam)
+    with pytest.raises(V.VawError) as e:
+        V.WarpContext(cam, out)
+    assert e.value.code == -3
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing in the package or include/ may reference it."""
+    pkg = os.path.join(ROOT, "video_annotator_b200")
+    for base, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                text = open(os.path.join(base, fn)).read()
+                assert "import oracle" not in text and "from oracle" not in text, fn
+                assert "liboracle" not in text and "vaw_oracle_" not in text, fn

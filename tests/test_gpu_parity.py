@@ -1,0 +1,409 @@
+"""Parity of the CUDA warp path (libvaw.so, through the C-ABI) against the CPU oracle.
+
+Bars (BASELINE.json north_star):
+  A. source coordinates within 1e-3 px of the createMap.cl transcription (oracle/create_map_ref.c)
+     -- and, stronger, BIT-EXACT against the host restatement of the device function
+     (tests/helpers/devatan_map.c: same IEEE operations, same atan polynomial);
+  B. output pixels 0 LSB from cv::remap's integer filter (oracle/remap_ref.c, pinned to
+     cv2.remap) evaluated on the SAME map;
+  C. output pixels against the oracle's whole path (libm-atanf map): mismatch histogram
+     and PSNR reported; the only source of difference is 1/32-px bucket flips where the
+     two atan implementations differ in the last bits.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests import gpu_util as G
+from tests.conftest import GOLDEN, ROOT, rotation_xyz
+
+pytestmark = pytest.mark.gpu
+
+NCPU = os.cpu_count() or 1
+
+
+@pytest.fixture(scope="module")
+def V():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import video_annotator_b200 as V
+    return V
+
+
+def _record(name, obj):
+    d = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(d, exist_ok=True)
+    path = os.path.join(d, "parity.json")
+    data = {}
+    if os.path.exists(path):
+        try:
+            data = json.load(open(path))
+        except Exception:
+            data = {}
+    data[name] = obj
+    json.dump(data, open(path, "w"), indent=1)
+
+
+def _warp_one(V, ctx, src_np, rot):
+    import torch
+    src = G.to_dev(src_np)
+    dst = torch.empty(ctx.frame_shape("dst"), dtype=torch.uint8, device="cuda")
+    ctx.warp(src, dst, rot)
+    torch.cuda.synchronize()
+    return dst.cpu().numpy()
+
+
+def _oracle_on_map(oracle, src, sw, sh, mx, my, cx, cy, border):
+    y = oracle.remap_u8(src[:sh], mx, my, border=(border[0],), threads=NCPU)
+    uv = oracle.remap_u8(src[sh:].reshape(sh // 2, sw // 2, 2), cx, cy, border=border[1:3], threads=NCPU)
+    return np.concatenate([y, uv.reshape(y.shape[0] // 2, y.shape[1])], axis=0)
+
+
+def _small_cams(V):
+    g = np.load(os.path.join(GOLDEN, "nv12_small.npz"))
+    cin = V.Camera.from_matrix(g["K_in"], 96, 64, model=1)
+    cout = V.Camera.from_matrix(g["K_out"], 80, 48)
+    return g, cin, cout
+
+
+# ---- the certified fast division / sqrt / atan sequences -----------------------------------
+def test_fast_math_sequences_equal_ieee_intrinsics(V):
+    m = V.selftest_math(seed=12345, n_per_thread=2000)
+    assert m == {"rcp": 0, "div": 0, "sqrt": 0, "k": 0}, m
+
+
+# ---- A. coordinates ---------------------------------------------------------------------------
+@pytest.mark.parametrize("name,rot", [("C1", (0, 0, 0)), ("C1", (2.0, -3.0, 1.5)), ("C2", (-1.0, 2.5, 0.7)),
+                                      ("C3", (2.0, -3.0, 1.5)), ("C5", (6.0, -8.0, 4.0))])
+def test_coordinates(V, oracle, name, rot):
+    from video_annotator_b200 import configs
+    w = configs.workload(name)
+    R = rotation_xyz(*rot)
+    ctx = V.WarpContext(w.input_camera, w.output_camera, out_size=w.out_size)
+    ow, oh = w.out_size
+    k = G.oracle_k(oracle, (w.input_camera, w.output_camera))
+    mx, my = [t.cpu().numpy() for t in ctx.dump_coords(R, 0)]
+    cx, cy = [t.cpu().numpy() for t in ctx.dump_coords(R, 1)]
+    # bit-exact against the host restatement of the device function
+    hx, hy = G.host_device_map(k, R, oh, ow)
+    assert G.bits_equal(mx, hx) and G.bits_equal(my, hy)
+    ocx, ocy = oracle.chroma_map(hx, hy, threads=NCPU)
+    assert G.bits_equal(cx, ocx) and G.bits_equal(cy, ocy)
+    # within 1e-3 px of the createMap.cl transcription (libm atanf)
+    ox, oy = oracle.create_map(k, R, oh, ow, threads=NCPU)
+    assert np.array_equal(np.isnan(ox), np.isnan(mx))
+    ex, ey = float(np.nanmax(np.abs(mx - ox))), float(np.nanmax(np.abs(my - oy)))
+    ulp = np.spacing(np.maximum(np.abs(ox), np.float32(1.0)))
+    _record(f"coords_{name}_{rot}", {"max_err_px": [ex, ey],
+                                      "max_err_ulp": float(np.nanmax(np.abs(mx - ox) / ulp)),
+                                      "frac_bit_identical": float(np.mean(mx.view(np.uint32) == ox.view(np.uint32)))})
+    assert ex < 1e-3 and ey < 1e-3
+    # the exact (library div/sqrt) mode produces the same bits as the certified fast mode
+    ctx.set_option("force_exact", 1)
+    mx2, my2 = [t.cpu().numpy() for t in ctx.dump_coords(R, 0)]
+    assert G.bits_equal(mx, mx2) and G.bits_equal(my, my2)
+    ctx.close()
+
+
+def test_coordinates_degenerate_geometry(V, oracle):
+    """r = 0 -> NaN (createMap.cl:38-39); q.z <= 0 after a large rotation is not guarded (:32-35)."""
+    cin = V.Camera.from_matrix([[50.0, 0, 100.0], [0, 50.0, 80.0], [0, 0, 1]], 200, 160, model=1)
+    cout = V.Camera.from_matrix([[25.0, 0, 8.0], [0, 25.0, 6.0], [0, 0, 1]], 16, 12)
+    ctx = V.WarpContext(cin, cout)
+    k = G.oracle_k(oracle, (cin, cout))
+    mx, my = [t.cpu().numpy() for t in ctx.dump_coords(np.eye(3), 0)]
+    assert np.isnan(mx[6, 8]) and np.isnan(my[6, 8]) and np.isnan(mx).sum() == 1
+    hx, hy = G.host_device_map(k, np.eye(3), 12, 16)
+    assert G.bits_equal(mx, hx) and G.bits_equal(my, hy)
+    for rot in [(0, 100.0, 0), (170.0, 0, 0), (0, 89.9, 30.0), (0, 0, 180.0)]:
+        R = rotation_xyz(*rot)
+        mx, my = [t.cpu().numpy() for t in ctx.dump_coords(R, 0)]
+        hx, hy = G.host_device_map(k, R, 12, 16)
+        assert G.bits_equal(mx, hx) and G.bits_equal(my, hy), rot
+    ctx.close()
+
+
+# ---- the integer filter against cv::remap's golden vectors -----------------------------------
+def test_remap_filter_against_cv2_golden(V):
+    """tests/golden/remap_cases.npz are outputs of cv2.remap itself (NaN, inf, +-1e9, edge walks,
+    ties at odd multiples of 1/64; 1-3 channels; three border values)."""
+    g = np.load(os.path.join(GOLDEN, "remap_cases.npz"))
+    mx, my = G.to_dev(g["map_x"]), G.to_dev(g["map_y"])
+    for cn in (1, 2, 3):
+        src = G.to_dev(g[f"src{cn}"])
+        for bi, border in enumerate(g["borders"]):
+            got = V.remap_u8(src, mx, my, border=tuple(int(b) for b in border)).cpu().numpy()
+            assert np.array_equal(got, g[f"dst{cn}_b{bi}"]), (cn, bi)
+
+
+# ---- B. pixels, strict: 0 LSB on the same map ------------------------------------------------
+@pytest.mark.parametrize("name,rot,white", [("C1", (0, 0, 0), True), ("C1", (1.0, -2.0, 0.5), True),
+                                            ("C2", (-1.0, 2.5, 0.7), False), ("C3", (2.0, -3.0, 1.5), True),
+                                            ("C5", (3.0, -4.0, 2.0), True)])
+def test_pixels_bit_exact_on_same_map(V, oracle, name, rot, white):
+    from video_annotator_b200 import configs
+    w = configs.workload(name)
+    R = rotation_xyz(*rot)
+    sw, sh = w.src_size
+    border = (16, 128, 128)
+    ctx = V.WarpContext(w.input_camera, w.output_camera, out_size=w.out_size, border=border)
+    src = oracle.synth_nv12(sw, sh, 7, white_noise=white)
+    got = _warp_one(V, ctx, src, R)
+    mx, my = [t.cpu().numpy() for t in ctx.dump_coords(R, 0)]
+    cx, cy = [t.cpu().numpy() for t in ctx.dump_coords(R, 1)]
+    ref = _oracle_on_map(oracle, src, sw, sh, mx, my, cx, cy, border)
+    st = G.diff_stats(got, ref)
+    _record(f"pixels_same_map_{name}_{rot}", st)
+    assert st["max"] == 0, st
+    # C. against the oracle's own whole path (libm-atanf map): report, bound the bucket flips
+    k = G.oracle_k(oracle, (w.input_camera, w.output_camera))
+    full = oracle.warp_nv12(src, sw, sh, w.out_size[0], w.out_size[1], k, R, border=border, threads=NCPU)
+    st = G.diff_stats(got, full)
+    _record(f"pixels_vs_oracle_path_{name}_{rot}_{'white' if white else 'smooth'}", st)
+    if white:
+        assert st["differ"] < 0.01 and st["max"] <= 9, st     # 1 ulp -> 0.29 % flips, max 8
+    else:
+        assert st["gt1"] < 1e-4 and st["psnr"] > 60, st
+    ctx.close()
+
+
+def test_small_golden_cv2(V, oracle):
+    """tests/golden/nv12_small.npz: cv2.remap on the oracle map, three border settings."""
+    g, cin, cout = _small_cams(V)
+    for bi, border in enumerate(g["borders"]):
+        b = tuple(int(v) for v in border)
+        ctx = V.WarpContext(cin, cout, border=b)
+        got = _warp_one(V, ctx, g["src"], g["rot"])
+        mx, my = [t.cpu().numpy() for t in ctx.dump_coords(g["rot"], 0)]
+        cx, cy = [t.cpu().numpy() for t in ctx.dump_coords(g["rot"], 1)]
+        ref = _oracle_on_map(oracle, g["src"], 96, 64, mx, my, cx, cy, b)
+        assert np.array_equal(got, ref)
+        st = G.diff_stats(got, g[f"dst_b{bi}"])       # golden used the libm map: only bucket flips differ
+        assert st["differ"] < 0.02, st
+        ctx.close()
+
+
+# ---- batching, pitches, host path -----------------------------------------------------------------
+def test_batch_equals_per_frame_and_is_deterministic(V, oracle):
+    import torch
+    from video_annotator_b200 import configs
+    w = configs.workload("C1")
+    n = 6
+    rots = configs.make_rotations(40, 0.6)[30:30 + n]
+    ctx = V.WarpContext(w.input_camera, w.output_camera, out_size=w.out_size)
+    sw, sh = w.src_size
+    src = torch.empty((n,) + ctx.frame_shape("src"), dtype=torch.uint8, device="cuda")
+    V.synth_nv12(src, sw, sh, n, first_index=3)
+    torch.cuda.synchronize()
+    # device generator == host generator (so the oracle sees the same frames)
+    for i in (0, n - 1):
+        assert np.array_equal(src[i].cpu().numpy(), oracle.synth_nv12(sw, sh, 3 + i))
+    rdev = torch.empty(n * 9, dtype=torch.float32, device="cuda")
+    ctx.upload_rotations(rots, rdev)
+    assert np.array_equal(rdev.cpu().numpy(), rots.reshape(-1).astype(np.float32))  # the (cl_float) cast
+    dst = torch.zeros((n,) + ctx.frame_shape("dst"), dtype=torch.uint8, device="cuda")
+    before = ctx.launch_count
+    ctx.warp_batch(src, dst, rdev, n)
+    torch.cuda.synchronize()
+    assert ctx.launch_count == before + 1          # one launch for the whole batch
+    dst2 = torch.zeros_like(dst)
+    ctx.warp_batch(src, dst2, rdev, n)
+    single = torch.zeros_like(dst[0])
+    for i in range(n):
+        ctx.warp(src[i], single, rots[i])
+        assert torch.equal(single, dst[i]), i
+    assert torch.equal(dst, dst2)
+    # each frame against the oracle on the same map
+    k = G.oracle_k(oracle, (w.input_camera, w.output_camera))
+    hx, hy = G.host_device_map(k, rots[2], w.out_size[1], w.out_size[0])
+    cx, cy = oracle.chroma_map(hx, hy)
+    ref = _oracle_on_map(oracle, src[2].cpu().numpy(), sw, sh, hx, hy, cx, cy, (0, 128, 128))
+    assert np.array_equal(dst[2].cpu().numpy(), ref)
+    ctx.close()
+
+
+def test_pitched_buffers_and_untouched_padding(V, oracle):
+    import torch
+    g, cin, cout = _small_cams(V)
+    ctx = V.WarpContext(cin, cout)
+    sp, dp = 128, 96                                   # row pitches larger than the widths (96, 80)
+    src = torch.full((96, sp), 255, dtype=torch.uint8, device="cuda")
+    src[:, :96] = G.to_dev(g["src"])
+    dst = torch.full((72, dp), 0xAB, dtype=torch.uint8, device="cuda")
+    ctx.warp(src, dst, g["rot"], src_pitch=sp, dst_pitch=dp)
+    torch.cuda.synchronize()
+    ref = _warp_one(V, ctx, g["src"], g["rot"])
+    out = dst.cpu().numpy()
+    assert np.array_equal(out[:, :80], ref)
+    assert (out[:, 80:] == 0xAB).all()
+    ctx.close()
+
+
+@pytest.mark.parametrize("out_size", [(2, 2), (6, 4), (130, 18), (254, 34), (258, 30)])
+def test_ragged_output_sizes(V, oracle, out_size):
+    """Output sizes that do not fill a warp row / CTA tile; guard bytes after the frame stay intact."""
+    import torch
+    g, cin, _ = _small_cams(V)
+    ow, oh = out_size
+    cout = V.Camera.from_matrix([[30.0, 0, (ow - 1) / 2], [0, 30.0, (oh - 1) / 2], [0, 0, 1]], ow, oh)
+    ctx = V.WarpContext(cin, cout, border=(9, 99, 199))
+    src = G.to_dev(g["src"])
+    n_out = ow * oh * 3 // 2
+    buf = torch.full((n_out + 64,), 0xCD, dtype=torch.uint8, device="cuda")
+    ctx.warp(src, buf, g["rot"])
+    torch.cuda.synchronize()
+    out = buf.cpu().numpy()
+    assert (out[n_out:] == 0xCD).all()
+    k = G.oracle_k(oracle, (cin, cout))
+    hx, hy = G.host_device_map(k, g["rot"], oh, ow)
+    cx, cy = oracle.chroma_map(hx, hy)
+    ref = _oracle_on_map(oracle, g["src"], 96, 64, hx, hy, cx, cy, (9, 99, 199))
+    assert np.array_equal(out[:n_out].reshape(oh * 3 // 2, ow), ref)
+    ctx.close()
+
+
+def test_degenerate_rotations_pixels(V, oracle):
+    """Rays behind the camera (q.z <= 0), the NaN at the optical axis, everything out of frame."""
+    g, cin, cout = _small_cams(V)
+    cout = V.Camera.from_matrix([[30.0, 0, 40.0], [0, 30.0, 24.0], [0, 0, 1]], 80, 48)  # integer centre
+    ctx = V.WarpContext(cin, cout, border=(77, 10, 240))
+    k = G.oracle_k(oracle, (cin, cout))
+    for rot in [(0, 0, 0), (0, 100.0, 0), (170.0, 0, 0), (0, 60.0, 45.0), (0, 0, 90.0)]:
+        R = rotation_xyz(*rot)
+        got = _warp_one(V, ctx, g["src"], R)
+        hx, hy = G.host_device_map(k, R, 48, 80)
+        cx, cy = oracle.chroma_map(hx, hy)
+        ref = _oracle_on_map(oracle, g["src"], 96, 64, hx, hy, cx, cy, (77, 10, 240))
+        assert np.array_equal(got, ref), rot
+    ctx.close()
+
+
+def test_host_buffer_path_equals_device_path(V, oracle):
+    """vaw_warp_batch_host: pageable numpy buffers and pinned torch buffers, chunked pipeline."""
+    import torch
+    from video_annotator_b200 import configs
+    w = configs.workload("C2")
+    n = 37                                              # > 2 chunks, ragged last chunk
+    rots = w.rotations(n, first=40)
+    ctx = V.WarpContext(w.input_camera, w.output_camera, out_size=w.out_size)
+    sw, sh = w.src_size
+    src = torch.empty((n,) + ctx.frame_shape("src"), dtype=torch.uint8, device="cuda")
+    V.synth_nv12(src, sw, sh, n)
+    rdev = torch.empty(n * 9, dtype=torch.float32, device="cuda")
+    ctx.upload_rotations(rots, rdev)
+    dst = torch.empty((n,) + ctx.frame_shape("dst"), dtype=torch.uint8, device="cuda")
+    ctx.warp_batch(src, dst, rdev, n)
+    torch.cuda.synchronize()
+    want = dst.cpu().numpy()
+    src_np = src.cpu().numpy()
+    out_np = np.zeros_like(want)
+    ctx.warp_batch_host(src_np, out_np, rots)
+    assert np.array_equal(out_np, want)
+    src_pin = torch.from_numpy(src_np).pin_memory()
+    out_pin = torch.zeros(want.shape, dtype=torch.uint8).pin_memory()
+    ctx.warp_batch_host(src_pin, out_pin, rots)
+    assert np.array_equal(out_pin.numpy(), want)
+    ctx.close()
+
+
+# ---- the reference's literal behaviour: one remap of a BGR 8UC3 frame ---------------------------------
+def test_bgr_literal_reference_case(V, oracle):
+    """C1-ref: 1920x1080 BGR -> 1759x998 (odd width), identity rotation, border 0
+    (FrameSourceWarp.cpp:306-312, :401, :445)."""
+    import torch
+    cam = V.get_preset_camera(V.warp.GOPRO_H4B_WIDE169_MEASURED, 1920, 1080)
+    out = V.get_output_camera(cam)
+    assert out.size == (1759, 998)
+    rng = np.random.default_rng(11)
+    src = rng.integers(0, 256, (1080, 1920, 3), dtype=np.uint8)
+    k = G.oracle_k(oracle, (cam, out))
+    for rot in [(0, 0, 0), (1.0, -2.0, 0.5)]:
+        R = rotation_xyz(*rot)
+        ctx = V.WarpContext(cam, out, fmt=V.FORMAT_BGR24, border=(0, 0, 0))
+        dst = torch.empty(ctx.frame_shape("dst"), dtype=torch.uint8, device="cuda")
+        ctx.warp(G.to_dev(src), dst, R)
+        mx, my = [t.cpu().numpy() for t in ctx.dump_coords(R, 0)]
+        hx, hy = G.host_device_map(k, R, 998, 1759)
+        assert G.bits_equal(mx, hx) and G.bits_equal(my, hy)
+        ref = oracle.remap_u8(src, mx, my, border=(0, 0, 0), threads=NCPU)
+        assert np.array_equal(dst.cpu().numpy(), ref)
+        full = oracle.warp_bgr(src, 1759, 998, k, R, threads=NCPU)
+        st = G.diff_stats(dst.cpu().numpy(), full)
+        _record(f"bgr_vs_oracle_path_{rot}", st)
+        assert st["differ"] < 0.01
+        ctx.close()
+
+
+def test_gray8(V, oracle):
+    import torch
+    g, cin, cout = _small_cams(V)
+    cout = V.Camera.from_matrix(g["K_out"], 79, 47)      # odd sizes are legal for packed formats
+    ctx = V.WarpContext(cin, cout, fmt=V.FORMAT_GRAY8, border=(200,))
+    src = g["src"][:64]
+    dst = torch.empty((47, 79), dtype=torch.uint8, device="cuda")
+    ctx.warp(G.to_dev(src), dst, g["rot"])
+    mx, my = [t.cpu().numpy() for t in ctx.dump_coords(g["rot"], 0)]
+    assert np.array_equal(dst.cpu().numpy(), oracle.remap_u8(src, mx, my, border=(200,)))
+    ctx.close()
+
+
+# ---- full-size clips through size-independent properties ----------------------------------------------
+def test_full_size_clip_properties(V, oracle):
+    """C3 at BASELINE size, 24 frames in one launch: spot frames against the oracle, a constant
+    clip stays constant where it is sampled inside, and re-running is bit-identical."""
+    import torch
+    from video_annotator_b200 import configs
+    w = configs.workload("C3")
+    n = 24
+    rots = w.rotations(n, first=100)
+    border = (0, 128, 128)
+    ctx = V.WarpContext(w.input_camera, w.output_camera, out_size=w.out_size, border=border)
+    sw, sh = w.src_size
+    ow, oh = w.out_size
+    src = torch.empty((n,) + ctx.frame_shape("src"), dtype=torch.uint8, device="cuda")
+    V.synth_nv12(src, sw, sh, n, white_noise=True)
+    rdev = torch.empty(n * 9, dtype=torch.float32, device="cuda")
+    ctx.upload_rotations(rots, rdev)
+    dst = torch.empty((n,) + ctx.frame_shape("dst"), dtype=torch.uint8, device="cuda")
+    ctx.warp_batch(src, dst, rdev, n)
+    torch.cuda.synchronize()
+    k = G.oracle_k(oracle, (w.input_camera, w.output_camera))
+    for i in (0, 11, n - 1):
+        hx, hy = G.host_device_map(k, rots[i], oh, ow)
+        cx, cy = oracle.chroma_map(hx, hy, threads=NCPU)
+        ref = _oracle_on_map(oracle, src[i].cpu().numpy(), sw, sh, hx, hy, cx, cy, border)
+        assert np.array_equal(dst[i].cpu().numpy(), ref), i
+    chk = dst.to(torch.int64).sum().item()
+    dst.zero_()
+    ctx.warp_batch(src, dst, rdev, n)
+    assert dst.to(torch.int64).sum().item() == chk
+    # constant content: every output sample is 200 (all four taps inside), the border value,
+    # or a blend of the two along the frame edge -- never anything outside [border, 200]
+    src.fill_(200)
+    ctx.warp_batch(src, dst, rdev, n)
+    y = dst[:, :oh]
+    assert int(y.max()) == 200 and int((y == 200).sum()) > 0.55 * y.numel()
+    uv = dst[:, oh:]
+    assert int(uv.max()) == 200 and int(uv.min()) == 128
+    ctx.close()
+
+
+# ---- error convention ----------------------------------------------------------------------------
+def test_error_codes(V):
+    import torch
+    g, cin, cout = _small_cams(V)
+    ctx = V.WarpContext(cin, cout)
+    src = G.to_dev(g["src"])
+    dst = torch.empty(ctx.frame_shape("dst"), dtype=torch.uint8, device="cuda")
+    with pytest.raises(V.VawError) as e:
+        ctx.warp(src, dst, g["rot"], src_pitch=50)     # pitch smaller than a row
+    assert e.value.code == -2 and "pitch" in str(e.value)
+    with pytest.raises(V.VawError) as e:
+        ctx.set_option("no_such_option", 1)
+    assert e.value.code == -2
+    with pytest.raises(V.VawError) as e:
+        V.WarpContext(cin, cout, device=99)
+    assert e.value.code == -2
+    ctx.close()

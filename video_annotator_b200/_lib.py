@@ -49,6 +49,8 @@ SIGNATURES = {
     "vaw_upload_rotations": (C.c_int, [C.c_void_p, f64p, C.c_int, C.c_void_p, C.c_void_p]),
     "vaw_warp_batch_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, f64p, C.c_int]),
     "vaw_dump_coords": (C.c_int, [C.c_void_p, f64p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "vaw_remap_u8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                               C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, u8p, C.c_int, C.c_void_p]),
     "vaw_synth_nv12": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int,
                                  C.c_uint32, C.c_int, C.c_int, C.c_void_p]),
     "vaw_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),

@@ -15,6 +15,8 @@
 #include "../../include/vaw.h"
 #include "vaw_internal.h"
 
+static_assert(sizeof(vaw_params) == 128 && sizeof(vaw_camera) == 120, "C-ABI struct layout");
+
 namespace {
 
 constexpr int kStages = 3;                      // host-path pipeline depth
@@ -379,6 +381,27 @@ int vaw_dump_coords(vaw_ctx* ctx, const double rotation[9], int plane, float* ma
                                             map_pitch, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "dump_coords launch");
     ctx->launches++;
+    return VAW_OK;
+}
+
+int vaw_remap_u8(const uint8_t* src, int src_width, int src_height, int src_pitch, int channels,
+                 const float* map_x, const float* map_y, int rows, int cols, int map_pitch,
+                 uint8_t* dst, int dst_pitch, const uint8_t border[4], int device, void* stream)
+{
+    if (!src || !map_x || !map_y || !dst || !border) return fail(nullptr, VAW_ERR_INVALID, "null argument");
+    if (channels < 1 || channels > 3) return fail(nullptr, VAW_ERR_UNSUPPORTED, "1 to 3 channels");
+    if (src_width < 1 || src_height < 1 || src_width > 32766 || src_height > 32766 || rows < 0 || cols < 0 ||
+        src_pitch < src_width * channels || dst_pitch < cols * channels || map_pitch < cols)
+        return fail(nullptr, VAW_ERR_INVALID, "bad remap geometry");
+    if (channels == 2 && ((src_pitch & 1) || (reinterpret_cast<uintptr_t>(src) & 1)))
+        return fail(nullptr, VAW_ERR_INVALID, "2-channel source base and pitch must be even");
+    if (rows == 0 || cols == 0) return VAW_OK;
+    if (rows > 65535) return fail(nullptr, VAW_ERR_INVALID, "too many rows");
+    DeviceGuard dg(device);
+    const unsigned b = (unsigned)border[0] | ((unsigned)border[1] << 8) | ((unsigned)border[2] << 16);
+    cudaError_t e = vaw::launch_remap(src, src_width, src_height, src_pitch, channels, map_x, map_y, rows,
+                                      cols, map_pitch, dst, dst_pitch, b, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(nullptr, e, "remap launch");
     return VAW_OK;
 }
 

@@ -27,6 +27,10 @@ cudaError_t launch_warp_packed_gather(const Geom& g, const FrameBatch& b, int ch
 // The map createMap.cl would write; plane 0 luma, plane 1 NV12 chroma.
 cudaError_t launch_dump_coords(const Geom& g, const Rot& rot, int plane, float* map_x, float* map_y,
                                int map_pitch, cudaStream_t st);
+// cv::remap(INTER_LINEAR, BORDER_CONSTANT) with an explicit map, cn = 1..3.
+cudaError_t launch_remap(const uint8_t* src, int src_w, int src_h, int src_pitch, int cn,
+                         const float* map_x, const float* map_y, int rows, int cols, int map_pitch,
+                         uint8_t* dst, int dst_pitch, unsigned border, cudaStream_t st);
 // Integer synthetic content (mirror of oracle/synth_ref.c).
 cudaError_t launch_synth_nv12(uint8_t* dst, int w, int h, int pitch, size_t frame_stride,
                               int first_index, int n_frames, uint32_t seed, int white,

@@ -225,6 +225,50 @@ cudaError_t launch_dump_coords(const Geom& g, const Rot& rot, int plane, float* 
     return cudaGetLastError();
 }
 
+// ---- unfused sampler: cv::remap with an explicit map -------------------------------------
+// The reference's second pass (cv::remap at FrameSourceWarp.cpp:306-312) on its own, for
+// callers that already hold a map and for pinning the integer filter against cv::remap's
+// golden vectors (NaN / inf / edge coordinates that a camera geometry rarely produces).
+template <int kCn>
+__global__ void __launch_bounds__(256)
+remap_kernel(const uint8_t* __restrict__ src, int src_w, int src_h, int src_pitch,
+             const float* __restrict__ map_x, const float* __restrict__ map_y, int rows, int cols,
+             int map_pitch, uint8_t* __restrict__ dst, int dst_pitch, unsigned border)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= cols || y >= rows) return;
+    const float mx = __ldg(map_x + (size_t)y * map_pitch + x);
+    const float my = __ldg(map_y + (size_t)y * map_pitch + x);
+    uint8_t* o = dst + (size_t)y * dst_pitch + (size_t)x * kCn;
+    if (kCn == 1) {
+        o[0] = (uint8_t)sample_c1(src, src_pitch, src_w, src_h, mx, my, border & 255);
+    } else if (kCn == 2) {
+        unsigned v = sample_c2(src, src_pitch, src_w, src_h, mx, my, border & 0xffffu);
+        o[0] = (uint8_t)v;
+        o[1] = (uint8_t)(v >> 8);
+    } else {
+        unsigned v = sample_c3(src, src_pitch, src_w, src_h, mx, my, border & 0xffffffu);
+        o[0] = (uint8_t)v;
+        o[1] = (uint8_t)(v >> 8);
+        o[2] = (uint8_t)(v >> 16);
+    }
+}
+
+cudaError_t launch_remap(const uint8_t* src, int src_w, int src_h, int src_pitch, int cn,
+                         const float* map_x, const float* map_y, int rows, int cols, int map_pitch,
+                         uint8_t* dst, int dst_pitch, unsigned border, cudaStream_t st)
+{
+    dim3 block(256), grid((cols + 255) / 256, rows);
+    if (cn == 1)
+        remap_kernel<1><<<grid, block, 0, st>>>(src, src_w, src_h, src_pitch, map_x, map_y, rows, cols, map_pitch, dst, dst_pitch, border);
+    else if (cn == 2)
+        remap_kernel<2><<<grid, block, 0, st>>>(src, src_w, src_h, src_pitch, map_x, map_y, rows, cols, map_pitch, dst, dst_pitch, border);
+    else
+        remap_kernel<3><<<grid, block, 0, st>>>(src, src_w, src_h, src_pitch, map_x, map_y, rows, cols, map_pitch, dst, dst_pitch, border);
+    return cudaGetLastError();
+}
+
 // ---- ray tables ----------------------------------------------------------------------
 __global__ void ray_tables_kernel(float* xtab, int n_x, float* ytab, int n_y, float mcx, float mfx,
                                   float mcy, float mfy)

@@ -211,6 +211,21 @@ def synth_nv12(dst, width, height, n_frames, first_index=0, seed=20260001, white
     return dst
 
 
+def remap_u8(src, map_x, map_y, border=(0, 0, 0), stream=None):
+    """cv::remap(INTER_LINEAR, BORDER_CONSTANT) as called at FrameSourceWarp.cpp:306-312.
+    src: CUDA uint8 (H, W) or (H, W, cn<=3); map_x/map_y: CUDA float32 (rows, cols)."""
+    import torch
+    cn = 1 if src.dim() == 2 else src.shape[2]
+    h, w = src.shape[:2]
+    rows, cols = map_x.shape
+    dst = torch.empty((rows, cols) if src.dim() == 2 else (rows, cols, cn), dtype=torch.uint8, device=src.device)
+    b = (C.c_uint8 * 4)(*([int(v) for v in border] + [0] * (4 - len(border))))
+    _check(_lib.load().vaw_remap_u8(src.data_ptr(), w, h, src.stride(0), cn, map_x.data_ptr(), map_y.data_ptr(),
+                                    rows, cols, map_x.stride(0), dst.data_ptr(), dst.stride(0), b,
+                                    src.device.index or 0, _stream_handle(stream)))
+    return dst
+
+
 def selftest_math(device=0, seed=1, n_per_thread=1000):
     out = (C.c_uint64 * 4)()
     _check(_lib.load().vaw_selftest_math(device, seed, n_per_thread, out))
