@@ -52,12 +52,19 @@ enum { VAW_FORMAT_NV12 = 0, VAW_FORMAT_BGR24 = 1, VAW_FORMAT_GRAY8 = 2 };
 /* cv::InterpolationFlags values (opencv/FrameSourceWarp.hpp:90); only LINEAR exists. */
 enum { VAW_INTER_NEAREST = 0, VAW_INTER_LINEAR = 1, VAW_INTER_CUBIC = 2 };
 
-/* Kernel variants (all bit-identical in output; for A/B measurement). */
+/* Kernel variants.  Every variant applies cv::remap's integer filter exactly to its own
+ * map (vaw_dump_coords returns that map); they differ in how the map is evaluated:
+ *   GATHER  per pixel, op for op as createMap.cl:15-49 (3 divides, sqrt, atan): the
+ *           reference-order evaluation, ~50 instructions per pixel for the coordinates;
+ *   POLY    once per 128x32-pixel piece in double precision on a sparse anchor grid, then a
+ *           certified tensor polynomial inside the piece (within 3e-5 px of the exact
+ *           projection, i.e. the correctly rounded fp32 map up to rare last-bit
+ *           differences); pieces that cannot be certified use the GATHER evaluation.
+ * AUTO = POLY for NV12, GATHER for the packed formats. */
 enum {
     VAW_VARIANT_AUTO = 0,
-    VAW_VARIANT_GATHER = 1, /* per-tap loads through L1/L2                         */
-    VAW_VARIANT_TEX = 2,    /* texture-unit 2x2 gather (tld4) + integer blend      */
-    VAW_VARIANT_TILED = 3   /* persistent CTAs, source tiles staged in shared mem  */
+    VAW_VARIANT_GATHER = 1,
+    VAW_VARIANT_POLY = 2
 };
 
 /* ---- parameters -------------------------------------------------------------------
@@ -186,6 +193,10 @@ int vaw_synth_nv12(uint8_t *dst, int width, int height, int pitch, size_t frame_
  * __fdiv_rn / __fsqrt_rn / the k = atan(r)/r step on random operands in the certified
  * ranges; mismatches[4] = {rcp, div, sqrt, k}. */
 int vaw_set_option(vaw_ctx *ctx, const char *name, int value);
+/* Variant POLY: how the 128x32-pixel pieces of the output classify for `rotation`:
+ * counts = {pieces, with a certified polynomial, of those fully inside the source (sampler
+ * without border tests), of those fully outside (pure border fill)}.  All zero for GATHER. */
+int vaw_piece_stats(vaw_ctx *ctx, const double rotation[9], uint32_t counts[4], void *stream);
 int vaw_selftest_math(int device, uint32_t seed, uint64_t n_per_thread, uint64_t mismatches[4]);
 
 #ifdef __cplusplus

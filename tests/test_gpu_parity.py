@@ -75,18 +75,36 @@ def test_fast_math_sequences_equal_ieee_intrinsics(V):
 
 
 # ---- A. coordinates ---------------------------------------------------------------------------
-@pytest.mark.parametrize("name,rot", [("C1", (0, 0, 0)), ("C1", (2.0, -3.0, 1.5)), ("C2", (-1.0, 2.5, 0.7)),
-                                      ("C3", (2.0, -3.0, 1.5)), ("C5", (6.0, -8.0, 4.0))])
-def test_coordinates(V, oracle, name, rot):
+GATHER, POLY = 1, 2
+COORD_CASES = [("C1", (0, 0, 0)), ("C1", (2.0, -3.0, 1.5)), ("C2", (-1.0, 2.5, 0.7)),
+               ("C3", (2.0, -3.0, 1.5)), ("C5", (6.0, -8.0, 4.0))]
+
+
+def _exact_map_f64(k, R, rows, cols):
+    """The projection of createMap.cl:15-49 in float64 on the fp32-cast parameters."""
+    r = np.asarray(R, np.float64).reshape(9).astype(np.float32).astype(np.float64).reshape(3, 3)
+    u, v = np.meshgrid(np.arange(cols, dtype=np.float64), np.arange(rows, dtype=np.float64))
+    x = (u - k.map_center_x) / k.map_focal_x
+    y = (v - k.map_center_y) / k.map_focal_y
+    q = [r[i, 0] * x + r[i, 1] * y + r[i, 2] for i in range(3)]
+    c0, c1 = q[0] / q[2], q[1] / q[2]
+    rad = np.sqrt(c0 * c0 + c1 * c1)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        kk = np.arctan(rad) / rad
+    return k.src_center_x + c0 * kk * k.src_focal_x, k.src_center_y + c1 * kk * k.src_focal_y
+
+
+@pytest.mark.parametrize("name,rot", COORD_CASES)
+def test_coordinates_gather_variant(V, oracle, name, rot):
+    """Variant GATHER evaluates createMap.cl op for op: bit-exact against the host restatement."""
     from video_annotator_b200 import configs
     w = configs.workload(name)
     R = rotation_xyz(*rot)
-    ctx = V.WarpContext(w.input_camera, w.output_camera, out_size=w.out_size)
+    ctx = V.WarpContext(w.input_camera, w.output_camera, out_size=w.out_size, variant=GATHER)
     ow, oh = w.out_size
     k = G.oracle_k(oracle, (w.input_camera, w.output_camera))
     mx, my = [t.cpu().numpy() for t in ctx.dump_coords(R, 0)]
     cx, cy = [t.cpu().numpy() for t in ctx.dump_coords(R, 1)]
-    # bit-exact against the host restatement of the device function
     hx, hy = G.host_device_map(k, R, oh, ow)
     assert G.bits_equal(mx, hx) and G.bits_equal(my, hy)
     ocx, ocy = oracle.chroma_map(hx, hy, threads=NCPU)
@@ -95,10 +113,8 @@ def test_coordinates(V, oracle, name, rot):
     ox, oy = oracle.create_map(k, R, oh, ow, threads=NCPU)
     assert np.array_equal(np.isnan(ox), np.isnan(mx))
     ex, ey = float(np.nanmax(np.abs(mx - ox))), float(np.nanmax(np.abs(my - oy)))
-    ulp = np.spacing(np.maximum(np.abs(ox), np.float32(1.0)))
-    _record(f"coords_{name}_{rot}", {"max_err_px": [ex, ey],
-                                      "max_err_ulp": float(np.nanmax(np.abs(mx - ox) / ulp)),
-                                      "frac_bit_identical": float(np.mean(mx.view(np.uint32) == ox.view(np.uint32)))})
+    _record(f"coords_gather_{name}_{rot}", {"max_err_px": [ex, ey],
+                                             "frac_bit_identical": float(np.mean(mx.view(np.uint32) == ox.view(np.uint32)))})
     assert ex < 1e-3 and ey < 1e-3
     # the exact (library div/sqrt) mode produces the same bits as the certified fast mode
     ctx.set_option("force_exact", 1)
@@ -107,12 +123,53 @@ def test_coordinates(V, oracle, name, rot):
     ctx.close()
 
 
+@pytest.mark.parametrize("name,rot", COORD_CASES)
+def test_coordinates_poly_variant(V, oracle, name, rot):
+    """Variant POLY (the default for NV12): per-piece polynomials from double-precision anchors.
+    Bars: <= 1e-3 px from the createMap.cl transcription; and within half an fp32 ulp + 5e-5 px of
+    the exact (float64) projection, i.e. the correctly rounded fp32 map up to rare last-bit flips.
+    Above x = 4096 (C5) one fp32 ulp is 4.9e-4 px and the transcription itself is up to 2 ulp
+    (9.8e-4 px) from the exact value, so there the bound against it is 3 ulp of the coordinate."""
+    from video_annotator_b200 import configs
+    w = configs.workload(name)
+    R = rotation_xyz(*rot)
+    ctx = V.WarpContext(w.input_camera, w.output_camera, out_size=w.out_size, variant=POLY)
+    ow, oh = w.out_size
+    k = G.oracle_k(oracle, (w.input_camera, w.output_camera))
+    mx, my = [t.cpu().numpy() for t in ctx.dump_coords(R, 0)]
+    cx, cy = [t.cpu().numpy() for t in ctx.dump_coords(R, 1)]
+    # chroma map = the oracle's definition applied to the kernel's own luma map, bit for bit
+    ocx, ocy = oracle.chroma_map(mx, my, threads=NCPU)
+    assert G.bits_equal(cx, ocx) and G.bits_equal(cy, ocy)
+    ox, oy = oracle.create_map(k, R, oh, ow, threads=NCPU)
+    assert np.array_equal(np.isnan(ox), np.isnan(mx)) and np.array_equal(np.isnan(oy), np.isnan(my))
+    ex, ey = _exact_map_f64(k, R, oh, ow)
+    ulp_x = np.spacing(np.abs(mx).astype(np.float32)).astype(np.float64)
+    ulp_y = np.spacing(np.abs(my).astype(np.float32)).astype(np.float64)
+    dx, dy = np.abs(mx - ex), np.abs(my - ey)
+    slack_x, slack_y = float(np.nanmax(dx - 0.5 * ulp_x)), float(np.nanmax(dy - 0.5 * ulp_y))
+    err_o = max(float(np.nanmax(np.abs(mx - ox))), float(np.nanmax(np.abs(my - oy))))
+    big = max(w.src_size) > 4096
+    _record(f"coords_poly_{name}_{rot}", {
+        "max_err_vs_oracle_px": err_o, "max_err_vs_exact_px": [float(np.nanmax(dx)), float(np.nanmax(dy))],
+        "max_excess_over_half_ulp_px": [slack_x, slack_y],
+        "frac_equal_to_rounded_exact": float(np.mean(mx == ex.astype(np.float32))),
+        "frac_bit_identical_to_oracle": float(np.mean(mx.view(np.uint32) == ox.view(np.uint32)))})
+    assert slack_x < 5e-5 and slack_y < 5e-5
+    assert err_o < (3 * 4.8828125e-4 + 1e-6 if big else 1e-3)
+    ctx.close()
+
+
 def test_coordinates_degenerate_geometry(V, oracle):
     """r = 0 -> NaN (createMap.cl:38-39); q.z <= 0 after a large rotation is not guarded (:32-35)."""
     cin = V.Camera.from_matrix([[50.0, 0, 100.0], [0, 50.0, 80.0], [0, 0, 1]], 200, 160, model=1)
     cout = V.Camera.from_matrix([[25.0, 0, 8.0], [0, 25.0, 6.0], [0, 0, 1]], 16, 12)
-    ctx = V.WarpContext(cin, cout)
     k = G.oracle_k(oracle, (cin, cout))
+    pctx = V.WarpContext(cin, cout, variant=POLY)   # the piece holding the axis must go per-pixel
+    px, py = [t.cpu().numpy() for t in pctx.dump_coords(np.eye(3), 0)]
+    assert np.isnan(px[6, 8]) and np.isnan(py[6, 8]) and np.isnan(px).sum() == 1
+    pctx.close()
+    ctx = V.WarpContext(cin, cout, variant=GATHER)
     mx, my = [t.cpu().numpy() for t in ctx.dump_coords(np.eye(3), 0)]
     assert np.isnan(mx[6, 8]) and np.isnan(my[6, 8]) and np.isnan(mx).sum() == 1
     hx, hy = G.host_device_map(k, np.eye(3), 12, 16)
@@ -142,26 +199,27 @@ def test_remap_filter_against_cv2_golden(V):
 @pytest.mark.parametrize("name,rot,white", [("C1", (0, 0, 0), True), ("C1", (1.0, -2.0, 0.5), True),
                                             ("C2", (-1.0, 2.5, 0.7), False), ("C3", (2.0, -3.0, 1.5), True),
                                             ("C5", (3.0, -4.0, 2.0), True)])
-def test_pixels_bit_exact_on_same_map(V, oracle, name, rot, white):
+@pytest.mark.parametrize("variant", [GATHER, POLY])
+def test_pixels_bit_exact_on_same_map(V, oracle, name, rot, white, variant):
     from video_annotator_b200 import configs
     w = configs.workload(name)
     R = rotation_xyz(*rot)
     sw, sh = w.src_size
     border = (16, 128, 128)
-    ctx = V.WarpContext(w.input_camera, w.output_camera, out_size=w.out_size, border=border)
+    ctx = V.WarpContext(w.input_camera, w.output_camera, out_size=w.out_size, border=border, variant=variant)
     src = oracle.synth_nv12(sw, sh, 7, white_noise=white)
     got = _warp_one(V, ctx, src, R)
     mx, my = [t.cpu().numpy() for t in ctx.dump_coords(R, 0)]
     cx, cy = [t.cpu().numpy() for t in ctx.dump_coords(R, 1)]
     ref = _oracle_on_map(oracle, src, sw, sh, mx, my, cx, cy, border)
     st = G.diff_stats(got, ref)
-    _record(f"pixels_same_map_{name}_{rot}", st)
+    _record(f"pixels_same_map_v{variant}_{name}_{rot}", st)
     assert st["max"] == 0, st
     # C. against the oracle's own whole path (libm-atanf map): report, bound the bucket flips
     k = G.oracle_k(oracle, (w.input_camera, w.output_camera))
     full = oracle.warp_nv12(src, sw, sh, w.out_size[0], w.out_size[1], k, R, border=border, threads=NCPU)
     st = G.diff_stats(got, full)
-    _record(f"pixels_vs_oracle_path_{name}_{rot}_{'white' if white else 'smooth'}", st)
+    _record(f"pixels_vs_oracle_path_v{variant}_{name}_{rot}_{'white' if white else 'smooth'}", st)
     if white:
         assert st["differ"] < 0.01 and st["max"] <= 9, st     # 1 ulp -> 0.29 % flips, max 8
     else:
@@ -216,8 +274,7 @@ def test_batch_equals_per_frame_and_is_deterministic(V, oracle):
         assert torch.equal(single, dst[i]), i
     assert torch.equal(dst, dst2)
     # each frame against the oracle on the same map
-    k = G.oracle_k(oracle, (w.input_camera, w.output_camera))
-    hx, hy = G.host_device_map(k, rots[2], w.out_size[1], w.out_size[0])
+    hx, hy = [t.cpu().numpy() for t in ctx.dump_coords(rots[2], 0)]
     cx, cy = oracle.chroma_map(hx, hy)
     ref = _oracle_on_map(oracle, src[2].cpu().numpy(), sw, sh, hx, hy, cx, cy, (0, 128, 128))
     assert np.array_equal(dst[2].cpu().numpy(), ref)
@@ -256,11 +313,66 @@ def test_ragged_output_sizes(V, oracle, out_size):
     torch.cuda.synchronize()
     out = buf.cpu().numpy()
     assert (out[n_out:] == 0xCD).all()
-    k = G.oracle_k(oracle, (cin, cout))
-    hx, hy = G.host_device_map(k, g["rot"], oh, ow)
+    hx, hy = [t.cpu().numpy() for t in ctx.dump_coords(g["rot"], 0)]
+    assert hx.shape == (oh, ow)
     cx, cy = oracle.chroma_map(hx, hy)
     ref = _oracle_on_map(oracle, g["src"], 96, 64, hx, hy, cx, cy, (9, 99, 199))
     assert np.array_equal(out[:n_out].reshape(oh * 3 // 2, ow), ref)
+    ctx.close()
+
+
+@pytest.mark.parametrize("out_size,centre", [((258, 34), (129.0, 17.0)), ((130, 66), (600.3, 300.7)),
+                                             ((386, 98), (1700.2, 900.4)), ((254, 30), (5000.0, 17.0)),
+                                             ((1758, 998), (896.27, 485.84))])
+def test_poly_paths_on_windows(V, oracle, out_size, centre):
+    """Windows of the C1 geometry that land on the optical axis (per-pixel piece), inside the
+    frame (certified interior pieces), across its edge (checked sampler) and fully outside
+    (border fill); ragged sizes; guard bytes after the frame stay intact."""
+    import torch
+    from video_annotator_b200 import configs
+    w = configs.workload("C1")
+    sw, sh = w.src_size
+    ow, oh = out_size
+    f = w.output_camera.K[0, 0]
+    cout = V.Camera.from_matrix([[f, 0, centre[0]], [0, f, centre[1]], [0, 0, 1]], ow, oh)
+    border = (7, 90, 200)
+    ctx = V.WarpContext(w.input_camera, cout, border=border, variant=POLY)
+    R = rotation_xyz(1.5, -2.0, 0.8)
+    stats = ctx.piece_stats(R)
+    _record(f"piece_stats_window_{out_size}_{centre}", stats)
+    src = oracle.synth_nv12(sw, sh, 2, white_noise=True)
+    n_out = ow * oh * 3 // 2
+    buf = torch.full((n_out + 64,), 0xCD, dtype=torch.uint8, device="cuda")
+    ctx.warp(G.to_dev(src), buf, R)
+    torch.cuda.synchronize()
+    out = buf.cpu().numpy()
+    assert (out[n_out:] == 0xCD).all()
+    mx, my = [t.cpu().numpy() for t in ctx.dump_coords(R, 0)]
+    cx, cy = oracle.chroma_map(mx, my)
+    ref = _oracle_on_map(oracle, src, sw, sh, mx, my, cx, cy, border)
+    assert np.array_equal(out[:n_out].reshape(oh * 3 // 2, ow), ref)
+    k = G.oracle_k(oracle, (w.input_camera, cout))
+    ox, oy = oracle.create_map(k, R, oh, ow)
+    assert max(float(np.nanmax(np.abs(mx - ox))), float(np.nanmax(np.abs(my - oy)))) < 1e-3
+    if centre[0] == 5000.0:
+        assert stats["outside"] == stats["pieces"] and (out[:ow * oh] == 7).all()
+    if centre == (600.3, 300.7):
+        assert stats["interior"] == stats["pieces"]
+    if centre == (129.0, 17.0):
+        assert stats["poly"] < stats["pieces"]     # the piece holding the axis is evaluated per pixel
+    ctx.close()
+
+
+def test_piece_classification_c3(V):
+    """The C3 geometry: most pieces certify; ~36 % of the output is outside the source."""
+    from video_annotator_b200 import configs
+    w = configs.workload("C3")
+    ctx = V.WarpContext(w.input_camera, w.output_camera, out_size=w.out_size)
+    st = ctx.piece_stats(w.rotations(1, first=130)[0])
+    _record("piece_stats_C3", st)
+    assert st["pieces"] == 30 * 68
+    assert st["poly"] >= st["pieces"] - 4
+    assert st["interior"] > 0.5 * st["pieces"] and st["outside"] > 0.2 * st["pieces"]
     ctx.close()
 
 
@@ -273,7 +385,9 @@ def test_degenerate_rotations_pixels(V, oracle):
     for rot in [(0, 0, 0), (0, 100.0, 0), (170.0, 0, 0), (0, 60.0, 45.0), (0, 0, 90.0)]:
         R = rotation_xyz(*rot)
         got = _warp_one(V, ctx, g["src"], R)
-        hx, hy = G.host_device_map(k, R, 48, 80)
+        hx, hy = [t.cpu().numpy() for t in ctx.dump_coords(R, 0)]
+        gx, gy = G.host_device_map(k, R, 48, 80)   # f = 30 px: no piece certifies, all per-pixel
+        assert G.bits_equal(hx, gx) and G.bits_equal(hy, gy)
         cx, cy = oracle.chroma_map(hx, hy)
         ref = _oracle_on_map(oracle, g["src"], 96, 64, hx, hy, cx, cy, (77, 10, 240))
         assert np.array_equal(got, ref), rot
@@ -369,9 +483,8 @@ def test_full_size_clip_properties(V, oracle):
     dst = torch.empty((n,) + ctx.frame_shape("dst"), dtype=torch.uint8, device="cuda")
     ctx.warp_batch(src, dst, rdev, n)
     torch.cuda.synchronize()
-    k = G.oracle_k(oracle, (w.input_camera, w.output_camera))
     for i in (0, 11, n - 1):
-        hx, hy = G.host_device_map(k, rots[i], oh, ow)
+        hx, hy = [t.cpu().numpy() for t in ctx.dump_coords(rots[i], 0)]
         cx, cy = oracle.chroma_map(hx, hy, threads=NCPU)
         ref = _oracle_on_map(oracle, src[i].cpu().numpy(), sw, sh, hx, hy, cx, cy, border)
         assert np.array_equal(dst[i].cpu().numpy(), ref), i

@@ -53,6 +53,7 @@ SIGNATURES = {
                                C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, u8p, C.c_int, C.c_void_p]),
     "vaw_synth_nv12": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int,
                                  C.c_uint32, C.c_int, C.c_int, C.c_void_p]),
+    "vaw_piece_stats": (C.c_int, [C.c_void_p, f64p, C.POINTER(C.c_uint32), C.c_void_p]),
     "vaw_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "vaw_selftest_math": (C.c_int, [C.c_int, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint64)]),
 }

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <utility>
 #include "../../include/vaw.h"
 #include "vaw_internal.h"
 
@@ -27,6 +28,7 @@ struct Stage {
     cudaStream_t stream = nullptr;
     uint8_t *dev_in = nullptr, *dev_out = nullptr, *pin_in = nullptr, *pin_out = nullptr;
     float *dev_rot = nullptr, *pin_rot = nullptr;
+    vaw::PieceRec* pieces = nullptr;  // this stage's polynomial table (chunk_frames frames)
     // pending output of the chunk in flight on this stage
     uint8_t* host_dst = nullptr;
     size_t out_bytes = 0;
@@ -44,6 +46,17 @@ struct vaw_ctx {
     size_t src_frame_bytes = 0, dst_frame_bytes = 0;  // tightly packed
     uint64_t launches = 0;
     std::string err;
+    // variant POLY: per-piece polynomial tables (vaw_pieces.cuh)
+    int variant = VAW_VARIANT_GATHER;  // resolved (never AUTO)
+    vaw::GeomD gd{};
+    vaw::PieceBasis basis{};
+    size_t pieces_per_frame = 0;
+    vaw::PieceRec* table = nullptr;    // for vaw_warp / vaw_warp_batch
+    size_t table_frames = 0;
+    cudaEvent_t table_free = nullptr;  // recorded after the last kernel that read `table`
+    cudaStream_t table_stream = nullptr;
+    bool table_used = false;
+    vaw::PieceRec* dump_table = nullptr;
     // host path
     Stage stage[kStages];
     int chunk_frames = 0;
@@ -97,9 +110,66 @@ int check_buffers(vaw_ctx* ctx, const void* src, int src_pitch, void* dst, int d
     return VAW_OK;
 }
 
+// Inverse of the Vandermonde matrix of `n` nodes: monomial coefficient i = sum_a inv[i][a] f(node a).
+template <int N>
+void invert_vandermonde(const long double (&node)[N], double (&inv)[N][N])
+{
+    long double a[N][2 * N];
+    for (int r = 0; r < N; ++r) {
+        long double p = 1.0L;
+        for (int c = 0; c < N; ++c) { a[r][c] = p; p *= node[r]; }
+        for (int c = 0; c < N; ++c) a[r][N + c] = (r == c) ? 1.0L : 0.0L;
+    }
+    for (int col = 0; col < N; ++col) {
+        int piv = col;
+        for (int r = col + 1; r < N; ++r)
+            if (fabsl(a[r][col]) > fabsl(a[piv][col])) piv = r;
+        for (int c = 0; c < 2 * N; ++c) std::swap(a[col][c], a[piv][c]);
+        const long double d = a[col][col];
+        for (int c = 0; c < 2 * N; ++c) a[col][c] /= d;
+        for (int r = 0; r < N; ++r)
+            if (r != col) {
+                const long double f = a[r][col];
+                for (int c = 0; c < 2 * N; ++c) a[r][c] -= f * a[col][c];
+            }
+    }
+    // a[:, N:] = V^-1 with V[r][c] = node_r^c, i.e. coef = V^-1 f
+    for (int i = 0; i < N; ++i)
+        for (int r = 0; r < N; ++r) inv[i][r] = (double)a[i][N + r];
+}
+
+void make_basis(vaw::PieceBasis& b)
+{
+    long double su[vaw::kNu], sv[vaw::kNv];
+    for (int a = 0; a < vaw::kNu; ++a) su[a] = ((128.0L * a) / vaw::kDegU - 63.5L) / 64.0L;
+    for (int a = 0; a < vaw::kNv; ++a) sv[a] = ((32.0L * a) / vaw::kDegV - 15.5L) / 16.0L;
+    invert_vandermonde<vaw::kNu>(su, b.mu);
+    invert_vandermonde<vaw::kNv>(sv, b.mv);
+}
+
+// Make ctx->table hold `n_frames` frames and safe to overwrite from stream `st`.
+int acquire_table(vaw_ctx* ctx, int n_frames, cudaStream_t st)
+{
+    if ((size_t)n_frames > ctx->table_frames) {
+        if (ctx->table) {
+            VAW_CUDA(ctx, cudaDeviceSynchronize());
+            cudaFree(ctx->table);
+            ctx->table = nullptr;
+            ctx->table_frames = 0;
+        }
+        size_t want = (size_t)n_frames < 8 ? 8 : (size_t)n_frames;
+        VAW_CUDA(ctx, cudaMalloc(&ctx->table, want * ctx->pieces_per_frame * sizeof(vaw::PieceRec)));
+        ctx->table_frames = want;
+        ctx->table_used = false;
+    }
+    // the table is rebuilt by every call: order it after the previous reader when streams differ
+    if (ctx->table_used && ctx->table_stream != st) VAW_CUDA(ctx, cudaStreamWaitEvent(st, ctx->table_free, 0));
+    return VAW_OK;
+}
+
 int launch(vaw_ctx* ctx, const uint8_t* src, int src_pitch, size_t src_stride, uint8_t* dst,
            int dst_pitch, size_t dst_stride, const float* rots, const vaw::Rot* rot0, int n_frames,
-           cudaStream_t st)
+           cudaStream_t st, vaw::PieceRec* table_override = nullptr)
 {
     vaw::Geom g = ctx->g;
     g.src_pitch = src_pitch;
@@ -111,6 +181,7 @@ int launch(vaw_ctx* ctx, const uint8_t* src, int src_pitch, size_t src_stride, u
     b.dst_frame_stride = dst_stride;
     b.rots = rots;
     if (rot0) b.rot0 = *rot0;
+    const bool poly = ctx->p.format == VAW_FORMAT_NV12 && ctx->variant == VAW_VARIANT_POLY;
     // grid.z is limited to 65535 frames per launch
     for (int first = 0; first < n_frames; first += 65535) {
         vaw::FrameBatch bb = b;
@@ -119,6 +190,26 @@ int launch(vaw_ctx* ctx, const uint8_t* src, int src_pitch, size_t src_stride, u
         bb.dst = dst + (size_t)first * dst_stride;
         if (rots) bb.rots = rots + (size_t)first * 9;
         cudaError_t e;
+        if (poly) {
+            vaw::PieceRec* tab = table_override;
+            if (!tab) {
+                int rc = acquire_table(ctx, bb.n_frames, st);
+                if (rc) return rc;
+                tab = ctx->table;
+            }
+            e = vaw::launch_build_pieces(ctx->gd, ctx->basis, bb.rots, rot0 ? rot0->r : nullptr, bb.n_frames, tab, st);
+            if (e != cudaSuccess) return cuda_fail(ctx, e, "piece table launch");
+            ctx->launches++;
+            e = vaw::launch_warp_nv12_poly(g, bb, tab, st);
+            if (e == cudaSuccess && !table_override) {
+                ctx->table_used = true;
+                ctx->table_stream = st;
+                e = cudaEventRecord(ctx->table_free, st);
+            }
+            if (e != cudaSuccess) return cuda_fail(ctx, e, "warp kernel launch");
+            ctx->launches++;
+            continue;
+        }
         switch (ctx->p.format) {
         case VAW_FORMAT_NV12: e = vaw::launch_warp_nv12_gather(g, bb, st); break;
         case VAW_FORMAT_BGR24: e = vaw::launch_warp_packed_gather(g, bb, 3, st); break;
@@ -134,7 +225,7 @@ void free_host_path(vaw_ctx* ctx)
 {
     for (Stage& s : ctx->stage) {
         if (s.stream) cudaStreamSynchronize(s.stream);
-        cudaFree(s.dev_in); cudaFree(s.dev_out); cudaFree(s.dev_rot);
+        cudaFree(s.dev_in); cudaFree(s.dev_out); cudaFree(s.dev_rot); cudaFree(s.pieces);
         cudaFreeHost(s.pin_in); cudaFreeHost(s.pin_out); cudaFreeHost(s.pin_rot);
         if (s.stream) cudaStreamDestroy(s.stream);
         s = Stage{};
@@ -154,6 +245,8 @@ int init_host_path(vaw_ctx* ctx)
         VAW_CUDA(ctx, cudaMalloc(&s.dev_out, ctx->dst_frame_bytes * ctx->chunk_frames));
         VAW_CUDA(ctx, cudaMalloc(&s.dev_rot, sizeof(float) * 9 * ctx->chunk_frames));
         VAW_CUDA(ctx, cudaMallocHost(&s.pin_rot, sizeof(float) * 9 * ctx->chunk_frames));
+        if (ctx->variant == VAW_VARIANT_POLY)
+            VAW_CUDA(ctx, cudaMalloc(&s.pieces, sizeof(vaw::PieceRec) * ctx->pieces_per_frame * ctx->chunk_frames));
     }
     ctx->host_ready = true;
     return VAW_OK;
@@ -202,8 +295,10 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
         return fail(nullptr, VAW_ERR_UNSUPPORTED, "only INTER_LINEAR is implemented");
     if (p.format != VAW_FORMAT_NV12 && p.format != VAW_FORMAT_BGR24 && p.format != VAW_FORMAT_GRAY8)
         return fail(nullptr, VAW_ERR_INVALID, "unknown pixel format");
-    if (p.variant != VAW_VARIANT_AUTO && p.variant != VAW_VARIANT_GATHER)
+    if (p.variant != VAW_VARIANT_AUTO && p.variant != VAW_VARIANT_GATHER && p.variant != VAW_VARIANT_POLY)
         return fail(nullptr, VAW_ERR_UNSUPPORTED, "kernel variant not available in this build");
+    if (p.variant == VAW_VARIANT_POLY && p.format != VAW_FORMAT_NV12)
+        return fail(nullptr, VAW_ERR_UNSUPPORTED, "variant POLY exists for NV12 only");
     // `short` indices in createMap.cl:10-11 and int16 taps in cv::remap cap both sizes
     if (p.src_width < 2 || p.src_height < 2 || p.out_width < 1 || p.out_height < 1 ||
         p.src_width > 32766 || p.src_height > 32766 || p.out_width > 32766 || p.out_height > 32766)
@@ -249,6 +344,24 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
         delete ctx;
         return rc;
     }
+    ctx->variant = p.variant != VAW_VARIANT_AUTO ? p.variant
+                   : (p.format == VAW_FORMAT_NV12 ? VAW_VARIANT_POLY : VAW_VARIANT_GATHER);
+    if (ctx->variant == VAW_VARIANT_POLY) {
+        vaw::GeomD& d = ctx->gd;
+        d.scx = g.scx; d.scy = g.scy; d.sfx = g.sfx; d.sfy = g.sfy;  // the fp32 scalars, widened
+        d.mcx = g.mcx; d.mcy = g.mcy; d.mfx = g.mfx; d.mfy = g.mfy;
+        d.src_w = g.src_w; d.src_h = g.src_h; d.out_w = g.out_w; d.out_h = g.out_h;
+        make_basis(ctx->basis);
+        ctx->pieces_per_frame = (size_t)vaw::pieces_x(g.out_w) * vaw::pieces_y(g.out_h);
+        e = cudaEventCreateWithFlags(&ctx->table_free, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaMalloc(&ctx->dump_table, ctx->pieces_per_frame * sizeof(vaw::PieceRec));
+        if (e != cudaSuccess) {
+            int rc = cuda_fail(nullptr, e, "vaw_create (piece tables)");
+            cudaFree(ctx->xtab); cudaFree(ctx->ytab);
+            delete ctx;
+            return rc;
+        }
+    }
     ctx->launches = 1;
     g.xtab = ctx->xtab;
     g.ytab = ctx->ytab;
@@ -261,6 +374,10 @@ void vaw_destroy(vaw_ctx* ctx)
     if (!ctx) return;
     DeviceGuard dg(ctx->device);
     free_host_path(ctx);
+    cudaDeviceSynchronize();
+    cudaFree(ctx->table);
+    cudaFree(ctx->dump_table);
+    if (ctx->table_free) cudaEventDestroy(ctx->table_free);
     cudaFree(ctx->xtab);
     cudaFree(ctx->ytab);
     delete ctx;
@@ -352,7 +469,7 @@ int vaw_warp_batch_host(vaw_ctx* ctx, const uint8_t* src_host, uint8_t* dst_host
             hsrc = s.pin_in;
         }
         VAW_CUDA(ctx, cudaMemcpyAsync(s.dev_in, hsrc, sfb * n, cudaMemcpyHostToDevice, s.stream));
-        rc = launch(ctx, s.dev_in, src_pitch, sfb, s.dev_out, dst_pitch, dfb, s.dev_rot, nullptr, n, s.stream);
+        rc = launch(ctx, s.dev_in, src_pitch, sfb, s.dev_out, dst_pitch, dfb, s.dev_rot, nullptr, n, s.stream, s.pieces);
         if (rc) return rc;
         s.out_staged = !dst_pinned;
         if (s.out_staged && !s.pin_out) VAW_CUDA(ctx, cudaMallocHost(&s.pin_out, dfb * ctx->chunk_frames));
@@ -377,10 +494,43 @@ int vaw_dump_coords(vaw_ctx* ctx, const double rotation[9], int plane, float* ma
     const int need = plane ? ctx->p.out_width / 2 : ctx->p.out_width;
     if (map_pitch < need) return fail(ctx, VAW_ERR_INVALID, "map pitch smaller than a row");
     DeviceGuard dg(ctx->device);
-    cudaError_t e = vaw::launch_dump_coords(ctx->g, rot_from_double(rotation), plane, map_x, map_y,
-                                            map_pitch, (cudaStream_t)stream);
+    const vaw::Rot R = rot_from_double(rotation);
+    cudaError_t e;
+    if (ctx->variant == VAW_VARIANT_POLY) {
+        e = vaw::launch_build_pieces(ctx->gd, ctx->basis, nullptr, R.r, 1, ctx->dump_table, (cudaStream_t)stream);
+        if (e == cudaSuccess)
+            e = vaw::launch_dump_coords_poly(ctx->g, R, ctx->dump_table, plane, map_x, map_y, map_pitch,
+                                             (cudaStream_t)stream);
+        ctx->launches++;
+    } else {
+        e = vaw::launch_dump_coords(ctx->g, R, plane, map_x, map_y, map_pitch, (cudaStream_t)stream);
+    }
     if (e != cudaSuccess) return cuda_fail(ctx, e, "dump_coords launch");
     ctx->launches++;
+    return VAW_OK;
+}
+
+int vaw_piece_stats(vaw_ctx* ctx, const double rotation[9], uint32_t counts[4], void* stream)
+{
+    if (!ctx) return VAW_ERR_INVALID;
+    if (!rotation || !counts) return fail(ctx, VAW_ERR_INVALID, "null argument");
+    counts[0] = counts[1] = counts[2] = counts[3] = 0;
+    if (ctx->variant != VAW_VARIANT_POLY) return VAW_OK;
+    DeviceGuard dg(ctx->device);
+    const vaw::Rot R = rot_from_double(rotation);
+    cudaError_t e = vaw::launch_build_pieces(ctx->gd, ctx->basis, nullptr, R.r, 1, ctx->dump_table, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "piece table launch");
+    ctx->launches++;
+    std::string host(ctx->pieces_per_frame * sizeof(vaw::PieceRec), '\0');
+    VAW_CUDA(ctx, cudaMemcpyAsync(&host[0], ctx->dump_table, host.size(), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    VAW_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+    const vaw::PieceRec* rec = reinterpret_cast<const vaw::PieceRec*>(host.data());
+    for (size_t i = 0; i < ctx->pieces_per_frame; ++i) {
+        counts[0]++;
+        if (rec[i].flags & vaw::kPiecePoly) counts[1]++;
+        if (rec[i].flags & vaw::kPieceInterior) counts[2]++;
+        if (rec[i].flags & vaw::kPieceOutside) counts[3]++;
+    }
     return VAW_OK;
 }
 

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "vaw_coords.cuh"
+#include "vaw_pieces.cuh"
 
 namespace vaw {
 
@@ -24,6 +25,11 @@ cudaError_t launch_warp_nv12_gather(const Geom& g, const FrameBatch& b, cudaStre
 // Fused map + remap for interleaved 1- or 3-channel frames (GRAY8 / BGR24).
 cudaError_t launch_warp_packed_gather(const Geom& g, const FrameBatch& b, int channels,
                                       cudaStream_t st);
+// Fused map + remap, NV12, coordinates from the per-piece polynomial table (variant POLY).
+cudaError_t launch_warp_nv12_poly(const Geom& g, const FrameBatch& b, const PieceRec* table, cudaStream_t st);
+// The map the POLY kernel samples with (table built for `rot`, one frame).
+cudaError_t launch_dump_coords_poly(const Geom& g, const Rot& rot, const PieceRec* table, int plane,
+                                    float* map_x, float* map_y, int map_pitch, cudaStream_t st);
 // The map createMap.cl would write; plane 0 luma, plane 1 NV12 chroma.
 cudaError_t launch_dump_coords(const Geom& g, const Rot& rot, int plane, float* map_x, float* map_y,
                                int map_pitch, cudaStream_t st);

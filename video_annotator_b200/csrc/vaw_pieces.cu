@@ -1,0 +1,208 @@
+// vaw_pieces.cu -- builds the per-piece polynomial tables of the map (see vaw_pieces.cuh).
+//
+// One CTA handles up to 32 horizontally adjacent pieces of one piece-row of one frame:
+//   1. anchors: the projection of /root/reference/opencv/createMap.cl:15-49 evaluated in
+//      double precision on the shared node grid (6 x 4 nodes per piece, edges shared);
+//   2. Lagrange -> monomial along u, then along v (double);
+//   3. base = nearest integer of the centre coefficient; offsets stored as fp32;
+//   4. certificates: regularity (q.z range, optical axis not inside), accuracy against the
+//      exact projection at three interior check points, and the coordinate range
+//      (|offset| <= L1 norm of the non-constant coefficients) that classifies the piece as
+//      interior / outside / mixed with respect to the source frame.
+// This is a few hundred double-precision instructions per 4096 output pixels.
+#include <math.h>
+#include "vaw_pieces.cuh"
+
+namespace vaw {
+
+namespace {
+
+constexpr int kChunk = 32;                       // pieces per CTA along u
+constexpr int kNodesU = kChunk * kDegU + 1;      // 161 shared nodes
+constexpr int kThreads = 256;
+
+struct RotD { double r[9]; };
+struct RotF { float r[9]; };
+
+struct Ray { double mx, my, q0, q1, q2; };
+
+// createMap.cl:15-49 in double precision, for a (possibly fractional) output position.
+__device__ __forceinline__ Ray project(const GeomD& g, const RotD& R, double u, double v)
+{
+    const double x = (u - g.mcx) / g.mfx, y = (v - g.mcy) / g.mfy;
+    Ray o;
+    o.q0 = R.r[0] * x + R.r[1] * y + R.r[2];
+    o.q1 = R.r[3] * x + R.r[4] * y + R.r[5];
+    o.q2 = R.r[6] * x + R.r[7] * y + R.r[8];
+    const double c0 = o.q0 / o.q2, c1 = o.q1 / o.q2;
+    const double r2 = c0 * c0 + c1 * c1;
+    const double r = sqrt(r2);
+    // atan(r)/r is analytic in r^2; the series avoids 0/0 (the reference's NaN at r == 0 is
+    // reproduced by sending the piece that contains the axis to the per-pixel path)
+    const double k = r > 1e-4 ? atan(r) / r : 1.0 - r2 * (1.0 / 3.0 - r2 * 0.2);
+    o.mx = g.scx + c0 * k * g.sfx;
+    o.my = g.scy + c1 * k * g.sfy;
+    return o;
+}
+
+__device__ __forceinline__ double node_u(int ig) { return 128.0 * (ig / kDegU) + (128.0 * (ig % kDegU)) / kDegU; }
+__device__ __forceinline__ double node_v(int jg) { return 32.0 * (jg / kDegV) + (32.0 * (jg % kDegV)) / kDegV; }
+
+__device__ __forceinline__ double poly_eval(const float (&c)[kNu][kNv], double base, double s, double t)
+{
+    double acc = 0.0;
+#pragma unroll
+    for (int i = kDegU; i >= 0; --i) {
+        double a = 0.0;
+#pragma unroll
+        for (int j = kDegV; j >= 0; --j) a = a * t + (double)c[i][j];
+        acc = acc * s + a;
+    }
+    return base + acc;
+}
+
+__global__ void __launch_bounds__(kThreads)
+build_pieces_kernel(const GeomD g, const PieceBasis basis, const float* __restrict__ rots, const RotF rot0,
+                    PieceRec* __restrict__ table)
+{
+    __shared__ double anchors[kNv][kNodesU][2];
+    __shared__ double ucoef[kChunk][2][kNv][kNu];
+    __shared__ PieceRec recs[kChunk];
+    __shared__ int bad[kChunk];
+
+    const int npx = pieces_x(g.out_w), npy = pieces_y(g.out_h);
+    const int p0 = blockIdx.x * kChunk, py = blockIdx.y, frame = blockIdx.z;
+    const int np = min(kChunk, npx - p0);
+    const int tid = threadIdx.x;
+
+    RotD R;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R.r[i] = (double)(rots ? __ldg(rots + (size_t)frame * 9 + i) : rot0.r[i]);
+
+    if (tid < kChunk) bad[tid] = 0;
+    __syncthreads();
+
+    // 1. anchors on the shared node grid
+    const int nodes = np * kDegU + 1;
+    for (int idx = tid; idx < nodes * kNv; idx += kThreads) {
+        const int b = idx / nodes, ig = idx - b * nodes;
+        const Ray a = project(g, R, node_u(p0 * kDegU + ig), node_v(py * kDegV + b));
+        anchors[b][ig][0] = a.mx;
+        anchors[b][ig][1] = a.my;
+        if (!(isfinite(a.mx) && isfinite(a.my))) {
+            if (ig / kDegU < np) bad[ig / kDegU] = 1;
+            if (ig % kDegU == 0 && ig > 0) bad[ig / kDegU - 1] = 1;
+        }
+    }
+    __syncthreads();
+
+    // 2a. along u: (piece, coordinate, v-node) -> 6 monomial coefficients in s
+    for (int task = tid; task < np * 2 * kNv; task += kThreads) {
+        const int p = task / (2 * kNv), c = (task / kNv) & 1, b = task % kNv;
+        double f[kNu];
+#pragma unroll
+        for (int a = 0; a < kNu; ++a) f[a] = anchors[b][p * kDegU + a][c];
+#pragma unroll
+        for (int i = 0; i < kNu; ++i) {
+            double acc = 0.0;
+#pragma unroll
+            for (int a = 0; a < kNu; ++a) acc += basis.mu[i][a] * f[a];
+            ucoef[p][c][b][i] = acc;
+        }
+    }
+    __syncthreads();
+
+    // 2b. along v: (piece, coordinate, power of s) -> 4 monomial coefficients in t; 3. base
+    for (int task = tid; task < np * 2 * kNu; task += kThreads) {
+        const int p = task / (2 * kNu), c = (task / kNu) & 1, i = task % kNu;
+        double co[kNv];
+#pragma unroll
+        for (int j = 0; j < kNv; ++j) {
+            double acc = 0.0;
+#pragma unroll
+            for (int b = 0; b < kNv; ++b) acc += basis.mv[j][b] * ucoef[p][c][b][i];
+            co[j] = acc;
+        }
+        float (&dst)[kNu][kNv] = c ? recs[p].cy : recs[p].cx;
+        if (i == 0) {
+            const double base = nearbyint(co[0]);
+            (c ? recs[p].base_y : recs[p].base_x) = (float)base;
+            co[0] -= base;
+        }
+#pragma unroll
+        for (int j = 0; j < kNv; ++j) dst[i][j] = (float)co[j];
+    }
+    __syncthreads();
+
+    // 4a. accuracy: exact projection against the fp32 polynomial at interior check points
+    for (int task = tid; task < np * 3; task += kThreads) {
+        const int p = task / 3, which = task % 3;
+        const double du = which == 0 ? 38.4 : (which == 1 ? 115.2 : 64.0);
+        const double dv = which == 0 ? 5.3 : (which == 1 ? 26.7 : 16.0);
+        const Ray e = project(g, R, 128.0 * (p0 + p) + du, 32.0 * py + dv);
+        const double s = (du - 63.5) / 64.0, t = (dv - 15.5) / 16.0;
+        const double ex = poly_eval(recs[p].cx, (double)recs[p].base_x, s, t) - e.mx;
+        const double ey = poly_eval(recs[p].cy, (double)recs[p].base_y, s, t) - e.my;
+        if (!(fabs(ex) <= 3e-5 && fabs(ey) <= 3e-5)) bad[p] = 1;
+    }
+    __syncthreads();
+
+    // 4b. regularity, coordinate range, flags; write the records
+    if (tid < np) {
+        const int p = tid;
+        bool ok = !bad[p];
+        bool pos0 = true, neg0 = true, pos1 = true, neg1 = true;
+#pragma unroll
+        for (int corner = 0; corner < 4; ++corner) {
+            const Ray a = project(g, R, 128.0 * (p0 + p) + ((corner & 1) ? 128.0 : 0.0),
+                                  32.0 * py + ((corner & 2) ? 32.0 : 0.0));
+            ok = ok && a.q2 >= 0.015625 && a.q2 <= 64.0 && fabs(a.q0) <= 64.0 && fabs(a.q1) <= 64.0;
+            const double eps = 9.5367431640625e-07;  // 2^-20
+            pos0 = pos0 && a.q0 >= eps; neg0 = neg0 && a.q0 <= -eps;
+            pos1 = pos1 && a.q1 >= eps; neg1 = neg1 && a.q1 <= -eps;
+        }
+        ok = ok && (pos0 || neg0 || pos1 || neg1);  // optical axis not inside (NaN pixel, createMap.cl:38-39)
+        PieceRec& rec = recs[p];
+        double rx = 0.0, ry = 0.0;
+#pragma unroll
+        for (int i = 0; i < kNu; ++i)
+#pragma unroll
+            for (int j = 0; j < kNv; ++j)
+                if (i | j) { rx += fabs((double)rec.cx[i][j]); ry += fabs((double)rec.cy[i][j]); }
+        const double cxm = (double)rec.base_x + (double)rec.cx[0][0], cym = (double)rec.base_y + (double)rec.cy[0][0];
+        const double lo_x = cxm - rx - 0.01, hi_x = cxm + rx + 0.01, lo_y = cym - ry - 0.01, hi_y = cym + ry + 0.01;
+        ok = ok && fabs(lo_x) < 60000.0 && fabs(hi_x) < 60000.0 && fabs(lo_y) < 60000.0 && fabs(hi_y) < 60000.0;
+        uint32_t flags = 0;
+        if (ok) {
+            flags |= kPiecePoly;
+            const double W = g.src_w, H = g.src_h;
+            // luma taps ix, ix+1 in [0, W-1]  <=>  0 <= m < W-1;  chroma: 0.5 <= mean < W-1.5
+            if (lo_x >= 0.55 && hi_x <= W - 1.55 && lo_y >= 0.55 && hi_y <= H - 1.55) flags |= kPieceInterior;
+            // every luma and chroma tap outside in x, or in y
+            if (hi_x < -1.6 || lo_x > W + 0.55 || hi_y < -1.6 || lo_y > H + 0.55) flags |= kPieceOutside;
+        }
+        rec.flags = flags;
+        rec.pad = 0;
+    }
+    __syncthreads();
+    // coalesced copy of the records (208 bytes each) to the table
+    PieceRec* out = table + ((size_t)frame * npy + py) * npx + p0;
+    const uint32_t* s32 = reinterpret_cast<const uint32_t*>(recs);
+    uint32_t* d32 = reinterpret_cast<uint32_t*>(out);
+    for (int i = tid; i < np * (int)(sizeof(PieceRec) / 4); i += kThreads) d32[i] = s32[i];
+}
+
+}  // namespace
+
+cudaError_t launch_build_pieces(const GeomD& g, const PieceBasis& basis, const float* rots,
+                                const float* rot0, int n_frames, PieceRec* table, cudaStream_t st)
+{
+    RotF r0{};
+    if (rot0)
+        for (int i = 0; i < 9; ++i) r0.r[i] = rot0[i];
+    dim3 grid((pieces_x(g.out_w) + kChunk - 1) / kChunk, pieces_y(g.out_h), n_frames);
+    build_pieces_kernel<<<grid, kThreads, 0, st>>>(g, basis, rots, r0, table);
+    return cudaGetLastError();
+}
+
+}  // namespace vaw

@@ -189,6 +189,13 @@ class WarpContext:
                                          _stream_handle(stream)), self._h)
         return mx, my
 
+    def piece_stats(self, rotation, stream=None):
+        """Variant POLY: {'pieces', 'poly', 'interior', 'outside'} counts for this rotation."""
+        out = (C.c_uint32 * 4)()
+        _, rp = _rot_arg(rotation)
+        _check(self._lib.vaw_piece_stats(self._h, rp, out, _stream_handle(stream)), self._h)
+        return dict(zip(("pieces", "poly", "interior", "outside"), [int(v) for v in out]))
+
     def close(self):
         if getattr(self, "_h", None):
             self._lib.vaw_destroy(self._h)
