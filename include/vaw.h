@@ -60,11 +60,15 @@ enum { VAW_INTER_NEAREST = 0, VAW_INTER_LINEAR = 1, VAW_INTER_CUBIC = 2 };
  *           certified tensor polynomial inside the piece (within 3e-5 px of the exact
  *           projection, i.e. the correctly rounded fp32 map up to rare last-bit
  *           differences); pieces that cannot be certified use the GATHER evaluation.
- * AUTO = POLY for NV12, GATHER for the packed formats. */
+ *   TILED   POLY's coordinates; the source rectangle of every 8-row band is first copied into
+ *           shared memory by the TMA engine and the taps are read from there (needs a 16-byte
+ *           aligned source base / pitch / frame stride, else it gathers like POLY).
+ * POLY and TILED produce identical bytes.  AUTO = TILED for NV12, GATHER for the packed formats. */
 enum {
     VAW_VARIANT_AUTO = 0,
     VAW_VARIANT_GATHER = 1,
-    VAW_VARIANT_POLY = 2
+    VAW_VARIANT_POLY = 2,
+    VAW_VARIANT_TILED = 3
 };
 
 /* ---- parameters -------------------------------------------------------------------

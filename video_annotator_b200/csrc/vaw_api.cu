@@ -138,11 +138,11 @@ void invert_vandermonde(const long double (&node)[N], double (&inv)[N][N])
         for (int r = 0; r < N; ++r) inv[i][r] = (double)a[i][N + r];
 }
 
-void make_basis(vaw::PieceBasis& b)
+void make_basis(vaw::PieceBasis& b, int ph)
 {
     long double su[vaw::kNu], sv[vaw::kNv];
     for (int a = 0; a < vaw::kNu; ++a) su[a] = ((128.0L * a) / vaw::kDegU - 63.5L) / 64.0L;
-    for (int a = 0; a < vaw::kNv; ++a) sv[a] = ((32.0L * a) / vaw::kDegV - 15.5L) / 16.0L;
+    for (int a = 0; a < vaw::kNv; ++a) sv[a] = (((long double)ph * a) / vaw::kDegV - 0.5L * (ph - 1)) * (2.0L / ph);
     invert_vandermonde<vaw::kNu>(su, b.mu);
     invert_vandermonde<vaw::kNv>(sv, b.mv);
 }
@@ -181,7 +181,10 @@ int launch(vaw_ctx* ctx, const uint8_t* src, int src_pitch, size_t src_stride, u
     b.dst_frame_stride = dst_stride;
     b.rots = rots;
     if (rot0) b.rot0 = *rot0;
-    const bool poly = ctx->p.format == VAW_FORMAT_NV12 && ctx->variant == VAW_VARIANT_POLY;
+    const bool poly = ctx->p.format == VAW_FORMAT_NV12 && ctx->variant != VAW_VARIANT_GATHER;
+    // the TMA engine copies 16-byte aligned row segments: other layouts gather from global memory
+    const bool staged = ctx->variant == VAW_VARIANT_TILED && (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
+                        (src_pitch & 15) == 0 && (src_stride & 15) == 0;
     // grid.z is limited to 65535 frames per launch
     for (int first = 0; first < n_frames; first += 65535) {
         vaw::FrameBatch bb = b;
@@ -200,7 +203,7 @@ int launch(vaw_ctx* ctx, const uint8_t* src, int src_pitch, size_t src_stride, u
             e = vaw::launch_build_pieces(ctx->gd, ctx->basis, bb.rots, rot0 ? rot0->r : nullptr, bb.n_frames, tab, st);
             if (e != cudaSuccess) return cuda_fail(ctx, e, "piece table launch");
             ctx->launches++;
-            e = vaw::launch_warp_nv12_poly(g, bb, tab, st);
+            e = vaw::launch_warp_nv12_poly(g, bb, tab, staged, st);
             if (e == cudaSuccess && !table_override) {
                 ctx->table_used = true;
                 ctx->table_stream = st;
@@ -245,7 +248,7 @@ int init_host_path(vaw_ctx* ctx)
         VAW_CUDA(ctx, cudaMalloc(&s.dev_out, ctx->dst_frame_bytes * ctx->chunk_frames));
         VAW_CUDA(ctx, cudaMalloc(&s.dev_rot, sizeof(float) * 9 * ctx->chunk_frames));
         VAW_CUDA(ctx, cudaMallocHost(&s.pin_rot, sizeof(float) * 9 * ctx->chunk_frames));
-        if (ctx->variant == VAW_VARIANT_POLY)
+        if (ctx->variant != VAW_VARIANT_GATHER)
             VAW_CUDA(ctx, cudaMalloc(&s.pieces, sizeof(vaw::PieceRec) * ctx->pieces_per_frame * ctx->chunk_frames));
     }
     ctx->host_ready = true;
@@ -295,10 +298,10 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
         return fail(nullptr, VAW_ERR_UNSUPPORTED, "only INTER_LINEAR is implemented");
     if (p.format != VAW_FORMAT_NV12 && p.format != VAW_FORMAT_BGR24 && p.format != VAW_FORMAT_GRAY8)
         return fail(nullptr, VAW_ERR_INVALID, "unknown pixel format");
-    if (p.variant != VAW_VARIANT_AUTO && p.variant != VAW_VARIANT_GATHER && p.variant != VAW_VARIANT_POLY)
+    if (p.variant < VAW_VARIANT_AUTO || p.variant > VAW_VARIANT_TILED)
         return fail(nullptr, VAW_ERR_UNSUPPORTED, "kernel variant not available in this build");
-    if (p.variant == VAW_VARIANT_POLY && p.format != VAW_FORMAT_NV12)
-        return fail(nullptr, VAW_ERR_UNSUPPORTED, "variant POLY exists for NV12 only");
+    if ((p.variant == VAW_VARIANT_POLY || p.variant == VAW_VARIANT_TILED) && p.format != VAW_FORMAT_NV12)
+        return fail(nullptr, VAW_ERR_UNSUPPORTED, "variants POLY and TILED exist for NV12 only");
     // `short` indices in createMap.cl:10-11 and int16 taps in cv::remap cap both sizes
     if (p.src_width < 2 || p.src_height < 2 || p.out_width < 1 || p.out_height < 1 ||
         p.src_width > 32766 || p.src_height > 32766 || p.out_width > 32766 || p.out_height > 32766)
@@ -345,14 +348,24 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
         return rc;
     }
     ctx->variant = p.variant != VAW_VARIANT_AUTO ? p.variant
-                   : (p.format == VAW_FORMAT_NV12 ? VAW_VARIANT_POLY : VAW_VARIANT_GATHER);
-    if (ctx->variant == VAW_VARIANT_POLY) {
+                   : (p.format == VAW_FORMAT_NV12 ? VAW_VARIANT_TILED : VAW_VARIANT_GATHER);
+    if (ctx->variant != VAW_VARIANT_GATHER) {
+        // rows per piece: keep the cubic-in-v truncation error ~ 2.4e-3 * f_in * (PH / f_out)^4 px
+        // (measured on the BASELINE geometries) below 2e-5 px
+        const double fin = std::fmax(std::fabs(p.src_focal_x), std::fabs(p.src_focal_y));
+        const double fout = std::fmin(std::fabs(p.map_focal_x), std::fabs(p.map_focal_y));
+        int ph = 32;
+        while (ph > 8 && 2.4e-3 * fin * std::pow(ph / fout, 4.0) > 2e-5) ph >>= 1;
+        g.piece_h = ph;
+        g.t_off = 0.5f * (float)(ph - 1);
+        g.t_scale = 2.0f / (float)ph;
         vaw::GeomD& d = ctx->gd;
         d.scx = g.scx; d.scy = g.scy; d.sfx = g.sfx; d.sfy = g.sfy;  // the fp32 scalars, widened
         d.mcx = g.mcx; d.mcy = g.mcy; d.mfx = g.mfx; d.mfy = g.mfy;
         d.src_w = g.src_w; d.src_h = g.src_h; d.out_w = g.out_w; d.out_h = g.out_h;
-        make_basis(ctx->basis);
-        ctx->pieces_per_frame = (size_t)vaw::pieces_x(g.out_w) * vaw::pieces_y(g.out_h);
+        d.piece_h = ph;
+        make_basis(ctx->basis, ph);
+        ctx->pieces_per_frame = (size_t)vaw::pieces_x(g.out_w) * vaw::pieces_y(g.out_h, ph);
         e = cudaEventCreateWithFlags(&ctx->table_free, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaMalloc(&ctx->dump_table, ctx->pieces_per_frame * sizeof(vaw::PieceRec));
         if (e != cudaSuccess) {
@@ -496,7 +509,7 @@ int vaw_dump_coords(vaw_ctx* ctx, const double rotation[9], int plane, float* ma
     DeviceGuard dg(ctx->device);
     const vaw::Rot R = rot_from_double(rotation);
     cudaError_t e;
-    if (ctx->variant == VAW_VARIANT_POLY) {
+    if (ctx->variant != VAW_VARIANT_GATHER) {
         e = vaw::launch_build_pieces(ctx->gd, ctx->basis, nullptr, R.r, 1, ctx->dump_table, (cudaStream_t)stream);
         if (e == cudaSuccess)
             e = vaw::launch_dump_coords_poly(ctx->g, R, ctx->dump_table, plane, map_x, map_y, map_pitch,
@@ -515,7 +528,7 @@ int vaw_piece_stats(vaw_ctx* ctx, const double rotation[9], uint32_t counts[4], 
     if (!ctx) return VAW_ERR_INVALID;
     if (!rotation || !counts) return fail(ctx, VAW_ERR_INVALID, "null argument");
     counts[0] = counts[1] = counts[2] = counts[3] = 0;
-    if (ctx->variant != VAW_VARIANT_POLY) return VAW_OK;
+    if (ctx->variant == VAW_VARIANT_GATHER) return VAW_OK;
     DeviceGuard dg(ctx->device);
     const vaw::Rot R = rot_from_double(rotation);
     cudaError_t e = vaw::launch_build_pieces(ctx->gd, ctx->basis, nullptr, R.r, 1, ctx->dump_table, (cudaStream_t)stream);

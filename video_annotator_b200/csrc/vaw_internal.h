@@ -26,7 +26,10 @@ cudaError_t launch_warp_nv12_gather(const Geom& g, const FrameBatch& b, cudaStre
 cudaError_t launch_warp_packed_gather(const Geom& g, const FrameBatch& b, int channels,
                                       cudaStream_t st);
 // Fused map + remap, NV12, coordinates from the per-piece polynomial table (variant POLY).
-cudaError_t launch_warp_nv12_poly(const Geom& g, const FrameBatch& b, const PieceRec* table, cudaStream_t st);
+// `staged`: variant TILED (source bands copied to shared memory by the TMA engine); needs a
+// 16-byte aligned source base, pitch and frame stride.
+cudaError_t launch_warp_nv12_poly(const Geom& g, const FrameBatch& b, const PieceRec* table, bool staged,
+                                  cudaStream_t st);
 // The map the POLY kernel samples with (table built for `rot`, one frame).
 cudaError_t launch_dump_coords_poly(const Geom& g, const Rot& rot, const PieceRec* table, int plane,
                                     float* map_x, float* map_y, int map_pitch, cudaStream_t st);

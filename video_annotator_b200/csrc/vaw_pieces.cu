@@ -45,8 +45,20 @@ __device__ __forceinline__ Ray project(const GeomD& g, const RotD& R, double u, 
     return o;
 }
 
+// only the rotated ray (createMap.cl:22-30): enough for the regularity certificate
+__device__ __forceinline__ Ray ray_only(const GeomD& g, const RotD& R, double u, double v)
+{
+    const double x = (u - g.mcx) / g.mfx, y = (v - g.mcy) / g.mfy;
+    Ray o;
+    o.q0 = R.r[0] * x + R.r[1] * y + R.r[2];
+    o.q1 = R.r[3] * x + R.r[4] * y + R.r[5];
+    o.q2 = R.r[6] * x + R.r[7] * y + R.r[8];
+    o.mx = o.my = 0.0;
+    return o;
+}
+
 __device__ __forceinline__ double node_u(int ig) { return 128.0 * (ig / kDegU) + (128.0 * (ig % kDegU)) / kDegU; }
-__device__ __forceinline__ double node_v(int jg) { return 32.0 * (jg / kDegV) + (32.0 * (jg % kDegV)) / kDegV; }
+__device__ __forceinline__ double node_v(int jg, int ph) { return (double)ph * (jg / kDegV) + ((double)ph * (jg % kDegV)) / kDegV; }
 
 __device__ __forceinline__ double poly_eval(const float (&c)[kNu][kNv], double base, double s, double t)
 {
@@ -70,7 +82,8 @@ build_pieces_kernel(const GeomD g, const PieceBasis basis, const float* __restri
     __shared__ PieceRec recs[kChunk];
     __shared__ int bad[kChunk];
 
-    const int npx = pieces_x(g.out_w), npy = pieces_y(g.out_h);
+    const int ph = g.piece_h;
+    const int npx = pieces_x(g.out_w), npy = pieces_y(g.out_h, ph);
     const int p0 = blockIdx.x * kChunk, py = blockIdx.y, frame = blockIdx.z;
     const int np = min(kChunk, npx - p0);
     const int tid = threadIdx.x;
@@ -86,7 +99,7 @@ build_pieces_kernel(const GeomD g, const PieceBasis basis, const float* __restri
     const int nodes = np * kDegU + 1;
     for (int idx = tid; idx < nodes * kNv; idx += kThreads) {
         const int b = idx / nodes, ig = idx - b * nodes;
-        const Ray a = project(g, R, node_u(p0 * kDegU + ig), node_v(py * kDegV + b));
+        const Ray a = project(g, R, node_u(p0 * kDegU + ig), node_v(py * kDegV + b, ph));
         anchors[b][ig][0] = a.mx;
         anchors[b][ig][1] = a.my;
         if (!(isfinite(a.mx) && isfinite(a.my))) {
@@ -134,16 +147,17 @@ build_pieces_kernel(const GeomD g, const PieceBasis basis, const float* __restri
     }
     __syncthreads();
 
-    // 4a. accuracy: exact projection against the fp32 polynomial at interior check points
+    // 4a. accuracy: exact projection against the fp32 polynomial where the interpolation error
+    // of equispaced nodes peaks (inside the first / last node intervals)
     for (int task = tid; task < np * 3; task += kThreads) {
         const int p = task / 3, which = task % 3;
-        const double du = which == 0 ? 38.4 : (which == 1 ? 115.2 : 64.0);
-        const double dv = which == 0 ? 5.3 : (which == 1 ? 26.7 : 16.0);
-        const Ray e = project(g, R, 128.0 * (p0 + p) + du, 32.0 * py + dv);
-        const double s = (du - 63.5) / 64.0, t = (dv - 15.5) / 16.0;
+        const double du = which == 0 ? 9.0 : (which == 1 ? 119.0 : 70.0);
+        const double dv = (which == 1 ? 0.894 : 0.106) * ph;
+        const Ray e = project(g, R, 128.0 * (p0 + p) + du, (double)ph * py + dv);
+        const double s = (du - 63.5) / 64.0, t = (dv - 0.5 * (ph - 1)) * (2.0 / ph);
         const double ex = poly_eval(recs[p].cx, (double)recs[p].base_x, s, t) - e.mx;
         const double ey = poly_eval(recs[p].cy, (double)recs[p].base_y, s, t) - e.my;
-        if (!(fabs(ex) <= 3e-5 && fabs(ey) <= 3e-5)) bad[p] = 1;
+        if (!(fabs(ex) <= 5e-5 && fabs(ey) <= 5e-5)) bad[p] = 1;
     }
     __syncthreads();
 
@@ -154,8 +168,8 @@ build_pieces_kernel(const GeomD g, const PieceBasis basis, const float* __restri
         bool pos0 = true, neg0 = true, pos1 = true, neg1 = true;
 #pragma unroll
         for (int corner = 0; corner < 4; ++corner) {
-            const Ray a = project(g, R, 128.0 * (p0 + p) + ((corner & 1) ? 128.0 : 0.0),
-                                  32.0 * py + ((corner & 2) ? 32.0 : 0.0));
+            const Ray a = ray_only(g, R, 128.0 * (p0 + p) + ((corner & 1) ? 128.0 : 0.0),
+                                  (double)ph * py + ((corner & 2) ? (double)ph : 0.0));
             ok = ok && a.q2 >= 0.015625 && a.q2 <= 64.0 && fabs(a.q0) <= 64.0 && fabs(a.q1) <= 64.0;
             const double eps = 9.5367431640625e-07;  // 2^-20
             pos0 = pos0 && a.q0 >= eps; neg0 = neg0 && a.q0 <= -eps;
@@ -185,6 +199,45 @@ build_pieces_kernel(const GeomD g, const PieceBasis basis, const float* __restri
         rec.pad = 0;
     }
     __syncthreads();
+
+    // 5. source rectangle of every 8-row band of the interior pieces (for the smem staging):
+    // re-centre the polynomial on the band (t = tc + h*tau) and bound it by the L1 norm.
+    for (int task = tid; task < np * kMaxBands; task += kThreads) {
+        const int p = task / kMaxBands, bnd = task % kMaxBands;
+        PieceRec& rec = recs[p];
+        BandBox box = {0, -1, 0, -1, 0, -1, 0, -1};
+        if ((rec.flags & kPieceInterior) && bnd * kBandH < ph) {
+            const double tscale = 2.0 / ph;
+            const double tc = (bnd * kBandH + 0.5 * (kBandH - 1) - 0.5 * (ph - 1)) * tscale;
+            const double h = 0.5 * (kBandH - 1) * tscale;
+            double lo[2], hi[2];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const float (&co)[kNu][kNv] = c ? rec.cy : rec.cx;
+                double centre = 0.0, rad = 0.0;
+#pragma unroll
+                for (int i = 0; i < kNu; ++i) {
+                    const double c0 = co[i][0], c1 = co[i][1], c2 = co[i][2], c3 = co[i][3];
+                    const double b0 = ((c3 * tc + c2) * tc + c1) * tc + c0;
+                    const double b1 = h * ((3.0 * c3 * tc + 2.0 * c2) * tc + c1);
+                    const double b2 = h * h * (3.0 * c3 * tc + c2);
+                    const double b3 = h * h * h * c3;
+                    if (i == 0) centre = b0; else rad += fabs(b0);
+                    rad += fabs(b1) + fabs(b2) + fabs(b3);
+                }
+                centre += (double)(c ? rec.base_y : rec.base_x);
+                lo[c] = centre - rad - 0.02;
+                hi[c] = centre + rad + 0.02;
+            }
+            // luma taps floor(m), floor(m)+1; chroma coordinate = (mean - 0.5) / 2
+            box.x0 = (int16_t)floor(lo[0]); box.x1 = (int16_t)(floor(hi[0]) + 1.0);
+            box.y0 = (int16_t)floor(lo[1]); box.y1 = (int16_t)(floor(hi[1]) + 1.0);
+            box.cx0 = (int16_t)floor((lo[0] - 0.5) * 0.5 - 0.01); box.cx1 = (int16_t)(floor((hi[0] - 0.5) * 0.5 + 0.01) + 1.0);
+            box.cy0 = (int16_t)floor((lo[1] - 0.5) * 0.5 - 0.01); box.cy1 = (int16_t)(floor((hi[1] - 0.5) * 0.5 + 0.01) + 1.0);
+        }
+        rec.band[bnd] = box;
+    }
+    __syncthreads();
     // coalesced copy of the records (208 bytes each) to the table
     PieceRec* out = table + ((size_t)frame * npy + py) * npx + p0;
     const uint32_t* s32 = reinterpret_cast<const uint32_t*>(recs);
@@ -200,7 +253,7 @@ cudaError_t launch_build_pieces(const GeomD& g, const PieceBasis& basis, const f
     RotF r0{};
     if (rot0)
         for (int i = 0; i < 9; ++i) r0.r[i] = rot0[i];
-    dim3 grid((pieces_x(g.out_w) + kChunk - 1) / kChunk, pieces_y(g.out_h), n_frames);
+    dim3 grid((pieces_x(g.out_w) + kChunk - 1) / kChunk, pieces_y(g.out_h, g.piece_h), n_frames);
     build_pieces_kernel<<<grid, kThreads, 0, st>>>(g, basis, rots, r0, table);
     return cudaGetLastError();
 }

@@ -3,15 +3,17 @@
 // Why it exists: on a B200 the fused warp is not bound by HBM but by instruction issue.
 // At 70 % of the measured copy bandwidth there are ~24 issue slots per output pixel, and
 // the op-for-op evaluation of /root/reference/opencv/createMap.cl:15-49 (3 divides, sqrt,
-// atan) costs ~50 of them.  The map is smooth, so it is evaluated ONCE per 128x32-pixel
-// piece on a sparse anchor grid in double precision and interpolated inside the piece by a
-// tensor polynomial (degree 5 along u, 3 along v; truncation error < 1e-5 px for the
-// BASELINE geometries).  Per pixel that leaves 3 FMAs per coordinate.
+// atan) costs ~50 of them.  The map is smooth, so it is evaluated ONCE per piece of
+// 128 x PH output pixels (PH = 32, 16 or 8 rows, chosen from the focal lengths so that the
+// truncation error stays below ~1e-5 px) on a sparse anchor grid in double precision and
+// interpolated inside the piece by a tensor polynomial (degree 5 along u, 3 along v).
+// Per pixel that leaves 3 FMAs per coordinate.
 //
 // Accuracy contract (tests/test_gpu_parity.py): a piece takes the polynomial path only
 // if (a) the projection is regular over it (q.z bounded away from 0, optical axis not
 // inside -- the reference yields NaN at r == 0, createMap.cl:38-39), and (b) the
-// polynomial agrees with the exact projection at interior check points to 2e-5 px.
+// polynomial agrees with the exact projection at interior check points to 5e-5 px
+// (3e-6 .. 4e-5 px in practice: it is the interpolation error of the end intervals).
 // Everything else is evaluated per pixel with the op-for-op sequence (vaw_coords.cuh).
 // The coordinate the sampler uses is always the fp32 value base + offset, rounded once;
 // vaw_dump_coords returns exactly those values, so "cv::remap on the same map" is
@@ -22,10 +24,12 @@
 
 namespace vaw {
 
-constexpr int kPieceW = 128;  // output pixels per piece along u (= one warp row: 32 lanes x 4)
-constexpr int kPieceH = 32;   // rows per piece
-constexpr int kDegU = 5;      // polynomial degree along u  (6 anchors, spacing 25.6 px)
-constexpr int kDegV = 3;      // polynomial degree along v  (4 anchors, spacing 10.67 px)
+constexpr int kPieceW = 128;   // output pixels per piece along u (= one warp row: 32 lanes x 4)
+constexpr int kPieceHMax = 32; // rows per piece: 32, 16 or 8
+constexpr int kBandH = 8;      // rows per staging band (variant TILED)
+constexpr int kMaxBands = kPieceHMax / kBandH;
+constexpr int kDegU = 5;       // polynomial degree along u  (6 anchors, spacing 25.6 px)
+constexpr int kDegV = 3;       // polynomial degree along v  (4 anchors, spacing PH/3 rows)
 constexpr int kNu = kDegU + 1, kNv = kDegV + 1;
 
 enum : uint32_t {
@@ -34,17 +38,24 @@ enum : uint32_t {
     kPieceOutside = 4u    // every tap of every pixel lies outside: the piece is pure border
 };
 
-// One record per (frame, piece): 52 floats = 208 bytes, 16-byte aligned.
+// Source rectangle (inclusive, in samples of the plane) that the taps of one 8-row band touch.
+struct BandBox {
+    int16_t x0, x1, y0, y1;      // luma
+    int16_t cx0, cx1, cy0, cy1;  // chroma (U,V pairs)
+};
+
+// One record per (frame, piece): 272 bytes, 16-byte aligned.
 // coordinate = base + sum_{i<=5, j<=3} c[i][j] * s^i * t^j,
-//   s = (du - 63.5) / 64, t = (dv - 15.5) / 16, (du, dv) = pixel offset inside the piece.
+//   s = (du - 63.5) / 64, t = (dv - (PH-1)/2) * 2/PH, (du, dv) = pixel offset inside the piece.
 struct PieceRec {
     float cx[kNu][kNv];
     float cy[kNu][kNv];
     float base_x, base_y;  // integers: base + offset rounds once to the fp32 coordinate
     uint32_t flags;
     uint32_t pad;
+    BandBox band[kMaxBands];  // valid for interior pieces
 };
-static_assert(sizeof(PieceRec) == 208, "piece record layout");
+static_assert(sizeof(PieceRec) == 272, "piece record layout");
 
 // Lagrange -> monomial conversion matrices for the anchor nodes (computed on the host in
 // double precision, passed by value to the builder kernel).
@@ -56,10 +67,11 @@ struct PieceBasis {
 struct GeomD {  // the 8 fp32 scalars of FrameSourceWarp.cpp:283-290, widened exactly
     double scx, scy, sfx, sfy, mcx, mcy, mfx, mfy;
     int src_w, src_h, out_w, out_h;
+    int piece_h;
 };
 
 inline __host__ __device__ int pieces_x(int out_w) { return (out_w + kPieceW - 1) / kPieceW; }
-inline __host__ __device__ int pieces_y(int out_h) { return (out_h + kPieceH - 1) / kPieceH; }
+inline __host__ __device__ int pieces_y(int out_h, int ph) { return (out_h + ph - 1) / ph; }
 
 cudaError_t launch_build_pieces(const GeomD& g, const PieceBasis& basis, const float* rots,
                                 const float* rot0, int n_frames, PieceRec* table, cudaStream_t st);

@@ -1,0 +1,266 @@
+// vaw_poly.cuh -- device pieces shared by the polynomial-coordinate kernels (vaw_poly.cu):
+// collapsing a piece polynomial onto a lane's columns, per-row coordinates, the unchecked
+// integer samplers (global memory and shared memory), packing and stores.
+//
+// Everything here implements cv::remap's INTER_LINEAR fixed-point filter as called at
+// /root/reference/opencv/FrameSourceWarp.cpp:306-312 (see vaw_sample.cuh) on the map of
+// vaw_pieces.cuh; the NV12 chroma rule is oracle/nv12_warp_ref.c's.
+#pragma once
+#include <stdint.h>
+#include "vaw_coords.cuh"
+#include "vaw_pieces.cuh"
+#include "vaw_sample.cuh"
+
+namespace vaw {
+
+constexpr float kMagic = 12582912.0f;  // 1.5 * 2^23: float add -> round-half-even integer in the mantissa
+constexpr int kMagicBits = 0x4B400000;
+constexpr unsigned kMagicShift = (unsigned)(kMagicBits >> 5);  // bias left in (bits >> 5)
+
+struct ColPoly {
+    float a[2][4][kNv];  // [coordinate][column][power of t]
+    float bx, by;
+};
+
+// Collapse the piece polynomial onto this lane's four columns (160 FMAs per piece).
+__device__ __forceinline__ void derive(const PieceRec* __restrict__ rec, int lane, ColPoly& cp)
+{
+    const float4* r4 = reinterpret_cast<const float4*>(rec);
+    float c[2][kNu][kNv];
+#pragma unroll
+    for (int q = 0; q < 12; ++q) {
+        const float4 v = __ldg(r4 + q);
+        float* dst = &c[0][0][0] + 4 * q;
+        dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+    }
+    const float4 tail = __ldg(r4 + 12);
+    cp.bx = tail.x;
+    cp.by = tail.y;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float s = ((float)(4 * lane + j) - 63.5f) * 0.015625f;  // exact
+#pragma unroll
+        for (int co = 0; co < 2; ++co)
+#pragma unroll
+            for (int k = 0; k < kNv; ++k) {
+                float acc = c[co][kDegU][k];
+#pragma unroll
+                for (int i = kDegU - 1; i >= 0; --i) acc = __fmaf_rn(acc, s, c[co][i][k]);
+                cp.a[co][j][k] = acc;
+            }
+    }
+}
+
+// fp32 coordinates of the lane's 4 columns on one row; t = (dv - t_off) * t_scale (exact).
+__device__ __forceinline__ void row_coords(const ColPoly& cp, float t, float (&mx)[4], float (&my)[4])
+{
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float px = __fmaf_rn(cp.a[0][j][3], t, cp.a[0][j][2]);
+        px = __fmaf_rn(px, t, cp.a[0][j][1]);
+        px = __fmaf_rn(px, t, cp.a[0][j][0]);
+        mx[j] = __fadd_rn(cp.bx, px);  // the map value: rounded once to fp32
+        float py = __fmaf_rn(cp.a[1][j][3], t, cp.a[1][j][2]);
+        py = __fmaf_rn(py, t, cp.a[1][j][1]);
+        py = __fmaf_rn(py, t, cp.a[1][j][0]);
+        my[j] = __fadd_rn(cp.by, py);
+    }
+}
+
+__device__ __forceinline__ float row_t(const Geom& g, int dv) { return __fmul_rn(__fsub_rn((float)dv, g.t_off), g.t_scale); }
+
+// Twice the NV12 chroma coordinate of a luma quad: chroma_coord() = ((sum * 0.25) - 0.5) * 0.5 where
+// the two multiplications are exact, so z = fma(sum, 0.25, -0.5) carries the single rounding and
+// rint(32 * coordinate) = rint(16 * z).
+__device__ __forceinline__ float chroma_z(float m00, float m01, float m10, float m11)
+{
+    return __fmaf_rn(__fadd_rn(__fadd_rn(m00, m01), __fadd_rn(m10, m11)), 0.25f, -0.5f);
+}
+
+// ---- the integer blend --------------------------------------------------------------------
+// returns 1024 * result + fraction (+512 already added); the caller shifts by 10
+__device__ __forceinline__ int blend_y(int t00, int t01, int t10, int t11, int ax, int ay)
+{
+    const int wx = 32 - ax, wy = 32 - ay;
+    const int top = t00 * wx + t01 * ax, bot = t10 * wx + t11 * ax;
+    return top * wy + bot * ay + 512;
+}
+
+// taps are (U | V << 8) pairs; the horizontal blend runs on U (bits 0..15) and V (16..31) at once
+__device__ __forceinline__ unsigned blend_uv(unsigned t00, unsigned t01, unsigned t10, unsigned t11,
+                                             unsigned ax, unsigned ay)
+{
+    const unsigned wx = 32u - ax, wy = 32u - ay;
+    const unsigned s00 = __byte_perm(t00, 0, 0x4140), s01 = __byte_perm(t01, 0, 0x4140);
+    const unsigned s10 = __byte_perm(t10, 0, 0x4140), s11 = __byte_perm(t11, 0, 0x4140);
+    const unsigned top = s00 * wx + s01 * ax, bot = s10 * wx + s11 * ax;  // <= 8160 per half
+    const unsigned u = ((top & 0xffffu) * wy + (bot & 0xffffu) * ay + 512u) >> 10;
+    const unsigned v = ((top >> 16) * wy + (bot >> 16) * ay + 512u) >> 10;
+    return u | (v << 8);
+}
+
+// ---- samplers without border tests, taps from global memory ---------------------------------
+// rint(32 m) sits in the mantissa of fma(m, 32, 1.5*2^23); >> 5 keeps a constant bias that is
+// folded into `bias` (all offset arithmetic is modulo 2^32 and the true offset fits).
+__device__ __forceinline__ int luma_gmem(const uint8_t* __restrict__ plane, unsigned pitch, unsigned bias,
+                                         float mx, float my)
+{
+    const int bx = __float_as_int(__fmaf_rn(mx, 32.0f, kMagic));
+    const int by = __float_as_int(__fmaf_rn(my, 32.0f, kMagic));
+    const unsigned off = (unsigned)(by >> 5) * pitch + ((unsigned)(bx >> 5) + bias);
+    const uint8_t* p = plane + off;
+    const uint8_t* q = p + pitch;
+    return blend_y(__ldg(p), __ldg(p + 1), __ldg(q), __ldg(q + 1), bx & 31, by & 31);
+}
+
+__device__ __forceinline__ unsigned chroma_gmem(const uint8_t* __restrict__ plane, unsigned pitch, unsigned bias,
+                                                float zx, float zy)
+{
+    const int bx = __float_as_int(__fmaf_rn(zx, 16.0f, kMagic));
+    const int by = __float_as_int(__fmaf_rn(zy, 16.0f, kMagic));
+    const unsigned off = (unsigned)(by >> 5) * pitch + (((unsigned)(bx >> 5) + bias) << 1);
+    const uint8_t* p = plane + off;
+    const uint8_t* q = p + pitch;
+    return blend_uv(__ldg(reinterpret_cast<const uint16_t*>(p)), __ldg(reinterpret_cast<const uint16_t*>(p + 2)),
+                    __ldg(reinterpret_cast<const uint16_t*>(q)), __ldg(reinterpret_cast<const uint16_t*>(q + 2)),
+                    bx & 31, by & 31);
+}
+
+// ---- the same, taps from a staged tile in shared memory (row pitch PL bytes) ---------------
+template <int IMM>
+__device__ __forceinline__ unsigned lds_u8(unsigned addr)
+{
+    unsigned v;
+    asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(IMM));
+    return v;
+}
+template <int IMM>
+__device__ __forceinline__ unsigned lds_u16(unsigned addr)
+{
+    unsigned v;
+    asm volatile("ld.shared.u16 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(IMM));
+    return v;
+}
+
+template <int PL>
+__device__ __forceinline__ int luma_smem(unsigned lconst, float mx, float my)
+{
+    const int bx = __float_as_int(__fmaf_rn(mx, 32.0f, kMagic));
+    const int by = __float_as_int(__fmaf_rn(my, 32.0f, kMagic));
+    const unsigned a = (unsigned)(by >> 5) * (unsigned)PL + ((unsigned)(bx >> 5) + lconst);
+    return blend_y(lds_u8<0>(a), lds_u8<1>(a), lds_u8<PL>(a), lds_u8<PL + 1>(a), bx & 31, by & 31);
+}
+
+template <int PL>
+__device__ __forceinline__ unsigned chroma_smem(unsigned cconst, float zx, float zy)
+{
+    const int bx = __float_as_int(__fmaf_rn(zx, 16.0f, kMagic));
+    const int by = __float_as_int(__fmaf_rn(zy, 16.0f, kMagic));
+    const unsigned a = (unsigned)(by >> 5) * (unsigned)PL + (((unsigned)(bx >> 5) + cconst) << 1);
+    return blend_uv(lds_u16<0>(a), lds_u16<2>(a), lds_u16<PL>(a), lds_u16<PL + 2>(a), bx & 31, by & 31);
+}
+
+// ---- packing and stores ------------------------------------------------------------------------
+__device__ __forceinline__ unsigned pack4(int a0, int a1, int a2, int a3)
+{
+    // each a_i = 1024 * result + fraction, result <= 255
+    const unsigned lo = __byte_perm((unsigned)a0 >> 10, (unsigned)a1 >> 10, 0x0040);
+    const unsigned hi = __byte_perm((unsigned)a2 >> 10, (unsigned)a3 >> 10, 0x0040);
+    return __byte_perm(lo, hi, 0x5410);
+}
+
+template <bool kRagged>
+__device__ __forceinline__ void store_word(uint8_t* p, unsigned word, int valid)
+{
+    if (!kRagged || (valid >= 4 && (reinterpret_cast<uintptr_t>(p) & 3) == 0)) {
+        *reinterpret_cast<unsigned*>(p) = word;
+    } else {
+        for (int i = 0; i < valid && i < 4; ++i) p[i] = (uint8_t)(word >> (8 * i));
+    }
+}
+
+struct PlaneRefs {
+    const uint8_t* y;   // luma plane of this frame
+    const uint8_t* uv;  // chroma plane of this frame
+    uint8_t* dst;       // output frame
+};
+
+// Checked sampling of one row pair from given coordinates (mixed pieces, per-pixel fallback).
+__device__ __forceinline__ void sample_rows_checked(const Geom& g, const PlaneRefs& f, int u0, int v0,
+                                                    const float (&mx)[2][4], const float (&my)[2][4])
+{
+    const int border_y = g.border & 255;
+    const unsigned border_uv = (g.border >> 8) & 0xffffu;
+    const int valid = g.out_w - u0;
+    unsigned yw[2] = {0u, 0u};
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            yw[r] |= (unsigned)sample_c1(f.y, g.src_pitch, g.src_w, g.src_h, mx[r][i], my[r][i], border_y) << (8 * i);
+    unsigned cw = 0u;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const float cx = chroma_coord(mx[0][2 * q], mx[0][2 * q + 1], mx[1][2 * q], mx[1][2 * q + 1]);
+        const float cy = chroma_coord(my[0][2 * q], my[0][2 * q + 1], my[1][2 * q], my[1][2 * q + 1]);
+        cw |= sample_c2(f.uv, g.src_pitch, g.src_w >> 1, g.src_h >> 1, cx, cy, border_uv) << (16 * q);
+    }
+    if (valid > 0) {
+        store_word<true>(f.dst + (size_t)v0 * g.dst_pitch + u0, yw[0], valid);
+        store_word<true>(f.dst + (size_t)(v0 + 1) * g.dst_pitch + u0, yw[1], valid);
+        store_word<true>(f.dst + (size_t)(g.out_h + (v0 >> 1)) * g.dst_pitch + u0, cw, valid);
+    }
+}
+
+// Per-pixel op-for-op coordinates of a row pair (pieces without a polynomial certificate).
+__device__ __forceinline__ void exact_rows(const Geom& g, const Rot& R, int u_lo, int u0, int v0,
+                                           float (&mx)[2][4], float (&my)[2][4])
+{
+    const float4 xs = __ldg(reinterpret_cast<const float4*>(g.xtab + u0));
+    const float2 ys = __ldg(reinterpret_cast<const float2*>(g.ytab + v0));
+    const ColTerms c[4] = {col_terms(xs.x, R), col_terms(xs.y, R), col_terms(xs.z, R), col_terms(xs.w, R)};
+    const RowTerms w[2] = {row_terms(ys.x, R), row_terms(ys.y, R)};
+    const int u_hi = min(u_lo + kPieceW, g.out_w) - 1;
+    const int v_hi = min(v0 + 1, g.out_h - 1);
+    if (fast_path_ok(u_lo, u_hi, v0, v_hi, R, g)) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) map_eval<true>(c[i], w[r], R, g, mx[r][i], my[r][i]);
+    } else {
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) map_eval<false>(c[i], w[r], R, g, mx[r][i], my[r][i]);
+    }
+}
+
+// ---- mbarrier / bulk-copy primitives (TMA engine, non-tensor form) --------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned mbar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity)
+{
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+    } while (!ok);
+}
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completion on mbar
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned mbar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+
+}  // namespace vaw
