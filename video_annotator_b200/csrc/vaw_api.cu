@@ -6,6 +6,7 @@
 // cl_float (:283-299), the per-column/per-row ray tables, and -- for the host-buffer
 // entry point -- a small ring of device staging buffers and streams.  No map buffers.
 // There is no CPU fallback anywhere in this file.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cmath>
 #include <cstdio>
@@ -57,6 +58,10 @@ struct vaw_ctx {
     cudaStream_t table_stream = nullptr;
     bool table_used = false;
     vaw::PieceRec* dump_table = nullptr;
+    // variant TILED: tensor maps, cached per source layout (encoding 11 maps costs ~10 us)
+    struct MapEntry { const void* src = nullptr; int pitch = 0; size_t stride = 0; int frames = 0; vaw::TileMaps maps{}; };
+    MapEntry map_cache[4];
+    int map_next = 0;
     // host path
     Stage stage[kStages];
     int chunk_frames = 0;
@@ -167,6 +172,57 @@ int acquire_table(vaw_ctx* ctx, int n_frames, cudaStream_t st)
     return VAW_OK;
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// Tensor maps for a clip of `frames` NV12 frames at `src` (vaw_tile.cu).  The TMA engine needs a
+// 16-byte aligned base, pitch and frame stride; other layouts get maps.enabled = 0.
+const vaw::TileMaps& tile_maps(vaw_ctx* ctx, const uint8_t* src, int pitch, size_t stride, int frames)
+{
+    for (vaw_ctx::MapEntry& e : ctx->map_cache)
+        if (e.src == src && e.pitch == pitch && e.stride == stride && e.frames == frames) return e.maps;
+    vaw_ctx::MapEntry& e = ctx->map_cache[ctx->map_next];
+    ctx->map_next = (ctx->map_next + 1) % 4;
+    e.src = src; e.pitch = pitch; e.stride = stride; e.frames = frames;
+    e.maps.enabled = 0;
+    const int rows_total = ctx->p.src_height + ctx->p.src_height / 2;
+    EncodeTiledFn enc = encode_tiled();
+    const bool ok = enc && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (pitch & 15) == 0 && (stride & 15) == 0 &&
+                    pitch / 4 >= vaw::kTileMaxPitch / 4 && rows_total >= 8 && (frames == 1 || stride >= (size_t)pitch);
+    if (!ok) return e.maps;
+    const cuuint64_t dims[3] = {(cuuint64_t)(pitch / 4), (cuuint64_t)rows_total, (cuuint64_t)frames};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch,
+                                   (cuuint64_t)(stride ? stride : (size_t)pitch * (size_t)rows_total)};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    for (int i = 0; i < vaw::kTileWidths; ++i) {
+        const cuuint32_t box[3] = {(cuuint32_t)((vaw::kTileMinPitch + i * vaw::kTilePitchStep) / 4), 8, 1};
+        CUresult r = enc(&e.maps.m[i], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint8_t*>(src), dims, strides,
+                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return e.maps;
+    }
+    e.maps.enabled = 1;
+    return e.maps;
+}
+
 int launch(vaw_ctx* ctx, const uint8_t* src, int src_pitch, size_t src_stride, uint8_t* dst,
            int dst_pitch, size_t dst_stride, const float* rots, const vaw::Rot* rot0, int n_frames,
            cudaStream_t st, vaw::PieceRec* table_override = nullptr)
@@ -182,9 +238,7 @@ int launch(vaw_ctx* ctx, const uint8_t* src, int src_pitch, size_t src_stride, u
     b.rots = rots;
     if (rot0) b.rot0 = *rot0;
     const bool poly = ctx->p.format == VAW_FORMAT_NV12 && ctx->variant != VAW_VARIANT_GATHER;
-    // the TMA engine copies 16-byte aligned row segments: other layouts gather from global memory
-    const bool staged = ctx->variant == VAW_VARIANT_TILED && (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
-                        (src_pitch & 15) == 0 && (src_stride & 15) == 0;
+    const bool tiled = ctx->variant == VAW_VARIANT_TILED && ctx->g.piece_h == vaw::kPieceHMax;
     // grid.z is limited to 65535 frames per launch
     for (int first = 0; first < n_frames; first += 65535) {
         vaw::FrameBatch bb = b;
@@ -203,7 +257,10 @@ int launch(vaw_ctx* ctx, const uint8_t* src, int src_pitch, size_t src_stride, u
             e = vaw::launch_build_pieces(ctx->gd, ctx->basis, bb.rots, rot0 ? rot0->r : nullptr, bb.n_frames, tab, st);
             if (e != cudaSuccess) return cuda_fail(ctx, e, "piece table launch");
             ctx->launches++;
-            e = vaw::launch_warp_nv12_poly(g, bb, tab, staged, st);
+            if (tiled)
+                e = vaw::launch_warp_nv12_tile(g, bb, tab, tile_maps(ctx, bb.src, src_pitch, src_stride, bb.n_frames), st);
+            else
+                e = vaw::launch_warp_nv12_poly(g, bb, tab, st);
             if (e == cudaSuccess && !table_override) {
                 ctx->table_used = true;
                 ctx->table_stream = st;

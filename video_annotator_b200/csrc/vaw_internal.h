@@ -1,5 +1,6 @@
 // vaw_internal.h -- launchers shared between the kernels and the C-ABI layer.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "vaw_coords.cuh"
@@ -26,9 +27,19 @@ cudaError_t launch_warp_nv12_gather(const Geom& g, const FrameBatch& b, cudaStre
 cudaError_t launch_warp_packed_gather(const Geom& g, const FrameBatch& b, int channels,
                                       cudaStream_t st);
 // Fused map + remap, NV12, coordinates from the per-piece polynomial table (variant POLY).
-// `staged`: variant TILED (source bands copied to shared memory by the TMA engine); needs a
-// 16-byte aligned source base, pitch and frame stride.
-cudaError_t launch_warp_nv12_poly(const Geom& g, const FrameBatch& b, const PieceRec* table, bool staged,
+cudaError_t launch_warp_nv12_poly(const Geom& g, const FrameBatch& b, const PieceRec* table, cudaStream_t st);
+
+// Variant TILED (vaw_tile.cu): tensor maps over the NV12 clip, viewed as a 3-D tensor of 4-byte
+// elements (pitch/4 x 3H/2 rows x frames), one per tile row pitch (box = pitch/4 x 8 rows).
+constexpr int kTileMinPitch = 128, kTileMaxPitch = 448, kTilePitchStep = 32;
+constexpr int kTileWidths = (kTileMaxPitch - kTileMinPitch) / kTilePitchStep + 1;
+struct alignas(64) TileMaps {
+    CUtensorMap m[kTileWidths];
+    int enabled;  // 0: no maps (layout not TMA-compatible) -> every piece gathers from global memory
+    int pad[15];
+};
+// Needs piece_h == 32.
+cudaError_t launch_warp_nv12_tile(const Geom& g, const FrameBatch& b, const PieceRec* table, const TileMaps& maps,
                                   cudaStream_t st);
 // The map the POLY kernel samples with (table built for `rot`, one frame).
 cudaError_t launch_dump_coords_poly(const Geom& g, const Rot& rot, const PieceRec* table, int plane,

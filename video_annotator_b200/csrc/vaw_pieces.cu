@@ -200,34 +200,25 @@ build_pieces_kernel(const GeomD g, const PieceBasis basis, const float* __restri
     }
     __syncthreads();
 
-    // 5. source rectangle of every 8-row band of the interior pieces (for the smem staging):
-    // re-centre the polynomial on the band (t = tc + h*tau) and bound it by the L1 norm.
-    for (int task = tid; task < np * kMaxBands; task += kThreads) {
-        const int p = task / kMaxBands, bnd = task % kMaxBands;
-        PieceRec& rec = recs[p];
-        BandBox box = {0, -1, 0, -1, 0, -1, 0, -1};
-        if ((rec.flags & kPieceInterior) && bnd * kBandH < ph) {
-            const double tscale = 2.0 / ph;
-            const double tc = (bnd * kBandH + 0.5 * (kBandH - 1) - 0.5 * (ph - 1)) * tscale;
-            const double h = 0.5 * (kBandH - 1) * tscale;
+    // 5. source rectangle of the piece's taps (for the shared-memory staging), from the same
+    // L1-norm range; clamped to int16 (a piece that far outside is classified kPieceOutside)
+    if (tid < np) {
+        PieceRec& rec = recs[tid];
+        PieceBox box = {0, -1, 0, -1, 0, -1, 0, -1};
+        if ((rec.flags & kPiecePoly) && !(rec.flags & kPieceOutside)) {
             double lo[2], hi[2];
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 const float (&co)[kNu][kNv] = c ? rec.cy : rec.cx;
-                double centre = 0.0, rad = 0.0;
+                double rad = 0.0;
 #pragma unroll
-                for (int i = 0; i < kNu; ++i) {
-                    const double c0 = co[i][0], c1 = co[i][1], c2 = co[i][2], c3 = co[i][3];
-                    const double b0 = ((c3 * tc + c2) * tc + c1) * tc + c0;
-                    const double b1 = h * ((3.0 * c3 * tc + 2.0 * c2) * tc + c1);
-                    const double b2 = h * h * (3.0 * c3 * tc + c2);
-                    const double b3 = h * h * h * c3;
-                    if (i == 0) centre = b0; else rad += fabs(b0);
-                    rad += fabs(b1) + fabs(b2) + fabs(b3);
-                }
-                centre += (double)(c ? rec.base_y : rec.base_x);
-                lo[c] = centre - rad - 0.02;
-                hi[c] = centre + rad + 0.02;
+                for (int i = 0; i < kNu; ++i)
+#pragma unroll
+                    for (int j = 0; j < kNv; ++j)
+                        if (i | j) rad += fabs((double)co[i][j]);
+                const double centre = (double)(c ? rec.base_y : rec.base_x) + (double)co[0][0];
+                lo[c] = fmax(centre - rad - 0.02, -30000.0);
+                hi[c] = fmin(centre + rad + 0.02, 30000.0);
             }
             // luma taps floor(m), floor(m)+1; chroma coordinate = (mean - 0.5) / 2
             box.x0 = (int16_t)floor(lo[0]); box.x1 = (int16_t)(floor(hi[0]) + 1.0);
@@ -235,7 +226,7 @@ build_pieces_kernel(const GeomD g, const PieceBasis basis, const float* __restri
             box.cx0 = (int16_t)floor((lo[0] - 0.5) * 0.5 - 0.01); box.cx1 = (int16_t)(floor((hi[0] - 0.5) * 0.5 + 0.01) + 1.0);
             box.cy0 = (int16_t)floor((lo[1] - 0.5) * 0.5 - 0.01); box.cy1 = (int16_t)(floor((hi[1] - 0.5) * 0.5 + 0.01) + 1.0);
         }
-        rec.band[bnd] = box;
+        rec.box = box;
     }
     __syncthreads();
     // coalesced copy of the records (208 bytes each) to the table

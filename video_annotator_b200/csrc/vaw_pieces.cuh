@@ -26,8 +26,6 @@ namespace vaw {
 
 constexpr int kPieceW = 128;   // output pixels per piece along u (= one warp row: 32 lanes x 4)
 constexpr int kPieceHMax = 32; // rows per piece: 32, 16 or 8
-constexpr int kBandH = 8;      // rows per staging band (variant TILED)
-constexpr int kMaxBands = kPieceHMax / kBandH;
 constexpr int kDegU = 5;       // polynomial degree along u  (6 anchors, spacing 25.6 px)
 constexpr int kDegV = 3;       // polynomial degree along v  (4 anchors, spacing PH/3 rows)
 constexpr int kNu = kDegU + 1, kNv = kDegV + 1;
@@ -38,13 +36,14 @@ enum : uint32_t {
     kPieceOutside = 4u    // every tap of every pixel lies outside: the piece is pure border
 };
 
-// Source rectangle (inclusive, in samples of the plane) that the taps of one 8-row band touch.
-struct BandBox {
+// Source rectangle (inclusive, in samples of the plane) that the taps of one piece touch; it may
+// reach outside the frame for pieces that straddle the border.
+struct PieceBox {
     int16_t x0, x1, y0, y1;      // luma
     int16_t cx0, cx1, cy0, cy1;  // chroma (U,V pairs)
 };
 
-// One record per (frame, piece): 272 bytes, 16-byte aligned.
+// One record per (frame, piece): 224 bytes, 16-byte aligned.
 // coordinate = base + sum_{i<=5, j<=3} c[i][j] * s^i * t^j,
 //   s = (du - 63.5) / 64, t = (dv - (PH-1)/2) * 2/PH, (du, dv) = pixel offset inside the piece.
 struct PieceRec {
@@ -53,9 +52,9 @@ struct PieceRec {
     float base_x, base_y;  // integers: base + offset rounds once to the fp32 coordinate
     uint32_t flags;
     uint32_t pad;
-    BandBox band[kMaxBands];  // valid for interior pieces
+    PieceBox box;  // valid for certified pieces that are not pure border
 };
-static_assert(sizeof(PieceRec) == 272, "piece record layout");
+static_assert(sizeof(PieceRec) == 224, "piece record layout");
 
 // Lagrange -> monomial conversion matrices for the anchor nodes (computed on the host in
 // double precision, passed by value to the builder kernel).

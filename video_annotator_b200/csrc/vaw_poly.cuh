@@ -10,6 +10,7 @@
 #include "vaw_coords.cuh"
 #include "vaw_pieces.cuh"
 #include "vaw_sample.cuh"
+#include "vaw_internal.h"
 
 namespace vaw {
 
@@ -235,7 +236,58 @@ __device__ __forceinline__ void exact_rows(const Geom& g, const Rot& R, int u_lo
     }
 }
 
-// ---- mbarrier / bulk-copy primitives (TMA engine, non-tensor form) --------------------------
+// ---- per-warp row walk with taps from global memory ---------------------------------------------
+__device__ __forceinline__ Rot load_rot(const FrameBatch& b, int frame)
+{
+    if (b.rots == nullptr) return b.rot0;
+    Rot R;
+    const float* p = b.rots + (size_t)frame * 9;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R.r[i] = __ldg(p + i);
+    return R;
+}
+
+struct RowPtrs {  // output pointers of the lane's 4-pixel group for the current row pair
+    uint8_t *y0, *y1, *c;
+    size_t step_y, step_c;  // advance per row pair
+};
+
+// nrows (even) rows starting at piece row dv0, taps from global memory, no border tests.
+template <bool kRagged>
+__device__ __forceinline__ void band_gmem(const Geom& g, const ColPoly& cp, const PlaneRefs& f, int dv0, int nrows,
+                                          RowPtrs& o, int valid)
+{
+    const unsigned pitch = (unsigned)g.src_pitch;
+    const unsigned bias_y = 0u - kMagicShift * pitch - kMagicShift;         // offset = iy*pitch + ix
+    const unsigned bias_c = 0u - kMagicShift * (pitch >> 1) - kMagicShift;  // offset = iy*pitch + 2*(ix + bias)
+#pragma unroll 1
+    for (int dv = dv0; dv < dv0 + nrows; dv += 2) {
+        float mx[2][4], my[2][4];
+        row_coords(cp, row_t(g, dv), mx[0], my[0]);
+        row_coords(cp, row_t(g, dv + 1), mx[1], my[1]);
+        int acc[2][4];
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[r][i] = luma_gmem(f.y, pitch, bias_y, mx[r][i], my[r][i]);
+        unsigned cw = 0u;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const float zx = chroma_z(mx[0][2 * q], mx[0][2 * q + 1], mx[1][2 * q], mx[1][2 * q + 1]);
+            const float zy = chroma_z(my[0][2 * q], my[0][2 * q + 1], my[1][2 * q], my[1][2 * q + 1]);
+            cw |= chroma_gmem(f.uv, pitch, bias_c, zx, zy) << (16 * q);
+        }
+        if (!kRagged || valid > 0) {
+            store_word<kRagged>(o.y0, pack4(acc[0][0], acc[0][1], acc[0][2], acc[0][3]), valid);
+            store_word<kRagged>(o.y1, pack4(acc[1][0], acc[1][1], acc[1][2], acc[1][3]), valid);
+            store_word<kRagged>(o.c, cw, valid);
+        }
+        o.y0 += o.step_y; o.y1 += o.step_y; o.c += o.step_c;
+    }
+}
+
+
+// ---- mbarrier / TMA primitives -----------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count)

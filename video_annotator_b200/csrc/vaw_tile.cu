@@ -1,0 +1,299 @@
+// vaw_tile.cu -- fused map + remap for NV12, source tiles staged in shared memory by TMA
+// (variant TILED).
+//
+// Replaces FrameSourceWarp::warp_frame's two passes
+// (/root/reference/opencv/FrameSourceWarp.cpp:272-314).  Same arithmetic as vaw_poly.cu
+// (coordinates from the per-piece polynomials of vaw_pieces.cuh, cv::remap's integer
+// filter); what changes is where the taps come from.
+//
+// Why shared memory when L1 already hits 94 %: instructions and latency, not bytes.  A tap
+// address in global memory is 64-bit (5 extra integer instructions per pixel), the LSU takes
+// one global load per ~1.8 cycles per SM, and an L1 miss stalls a warp for an L2 round trip.
+// From shared memory the four taps are LDS [a], [a+1], [a+PL], [a+PL+1] off one 32-bit IMAD,
+// and the staging costs no issue slots because the TMA engine does it.
+//
+// One CTA (4 warps) owns one 128x32-pixel piece:
+//   - thread 0 arms an mbarrier and issues cp.async.bulk.tensor loads (3-D tensor map over
+//     the NV12 clip: bytes/4 x rows x frames, boxes of PL/4 x 8 rows) for the source
+//     rectangle the piece's taps touch -- luma rows, then the chroma rows of the same map;
+//   - meanwhile warp w collapses the piece polynomial onto column j = w of every lane and
+//     the four warps exchange the results through shared memory (the collapse is amortised
+//     over the whole piece, not repeated per warp);
+//   - pieces that straddle the frame border get the out-of-frame cells of the tile
+//     overwritten with the border value, so the sampler needs no border tests at all
+//     (cv::remap's BORDER_CONSTANT replaces each out-of-image tap by the border value, which
+//     is exactly what reading a border-filled cell does);
+//   - warp w then walks rows 8w..8w+7 two at a time.
+// Pieces whose rectangle does not fit the tile budget, pieces without a polynomial
+// certificate and pure-border pieces take the paths of vaw_poly.cu.
+#include <cuda.h>
+#include <stdint.h>
+#include "vaw_internal.h"
+#include "vaw_poly.cuh"
+
+namespace vaw {
+
+namespace {
+
+constexpr int kWarps = 4;
+constexpr int kRowsPerWarp = kPieceHMax / kWarps;  // 8
+constexpr int kTileCap = 36864;                    // bytes of luma + chroma tile per CTA
+constexpr int kCoefBytes = 8 * 32 * 16;            // column polynomials exchanged between the warps
+constexpr int kSmemBytes = kTileCap + kCoefBytes + 16;
+
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* map, int x, int y, int z, unsigned mbar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(z), "r"(mbar)
+        : "memory");
+}
+
+__device__ __forceinline__ int luma_tile(unsigned lconst, unsigned pl, float mx, float my)
+{
+    const int bx = __float_as_int(__fmaf_rn(mx, 32.0f, kMagic));
+    const int by = __float_as_int(__fmaf_rn(my, 32.0f, kMagic));
+    const unsigned a0 = (unsigned)(by >> 5) * pl + ((unsigned)(bx >> 5) + lconst);
+    const unsigned a1 = a0 + pl;
+    return blend_y(lds_u8<0>(a0), lds_u8<1>(a0), lds_u8<0>(a1), lds_u8<1>(a1), bx & 31, by & 31);
+}
+
+__device__ __forceinline__ unsigned chroma_tile(unsigned cconst, unsigned pl, float zx, float zy)
+{
+    const int bx = __float_as_int(__fmaf_rn(zx, 16.0f, kMagic));
+    const int by = __float_as_int(__fmaf_rn(zy, 16.0f, kMagic));
+    const unsigned a0 = (unsigned)(by >> 5) * pl + (((unsigned)(bx >> 5) + cconst) << 1);
+    const unsigned a1 = a0 + pl;
+    return blend_uv(lds_u16<0>(a0), lds_u16<2>(a0), lds_u16<0>(a1), lds_u16<2>(a1), bx & 31, by & 31);
+}
+
+// nrows (even) rows starting at piece row dv0, taps from the staged tile.
+template <bool kRagged>
+__device__ __forceinline__ void rows_tile(const Geom& g, const ColPoly& cp, unsigned lconst, unsigned cconst,
+                                          unsigned pl, int dv0, int nrows, RowPtrs& o, int valid)
+{
+#pragma unroll 1
+    for (int dv = dv0; dv < dv0 + nrows; dv += 2) {
+        float mx[2][4], my[2][4];
+        row_coords(cp, row_t(g, dv), mx[0], my[0]);
+        row_coords(cp, row_t(g, dv + 1), mx[1], my[1]);
+        int acc[2][4];
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[r][i] = luma_tile(lconst, pl, mx[r][i], my[r][i]);
+        unsigned cw = 0u;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const float zx = chroma_z(mx[0][2 * q], mx[0][2 * q + 1], mx[1][2 * q], mx[1][2 * q + 1]);
+            const float zy = chroma_z(my[0][2 * q], my[0][2 * q + 1], my[1][2 * q], my[1][2 * q + 1]);
+            cw |= chroma_tile(cconst, pl, zx, zy) << (16 * q);
+        }
+        if (!kRagged || valid > 0) {
+            store_word<kRagged>(o.y0, pack4(acc[0][0], acc[0][1], acc[0][2], acc[0][3]), valid);
+            store_word<kRagged>(o.y1, pack4(acc[1][0], acc[1][1], acc[1][2], acc[1][3]), valid);
+            store_word<kRagged>(o.c, cw, valid);
+        }
+        o.y0 += o.step_y; o.y1 += o.step_y; o.c += o.step_c;
+    }
+}
+
+// Overwrite the cells of a staged plane that lie outside the source with the border value.
+// Tile row r <-> source row y0 + r (valid in [0, n_rows)); tile byte c <-> source byte x0 + c
+// (valid in [0, n_bytes)); `pattern` = the border replicated over 4 bytes (x0 is a multiple of 4).
+__device__ __forceinline__ void fill_border(uint8_t* tile, int pl, int tile_rows, int y0, int n_rows, int x0,
+                                            int n_bytes, unsigned pattern, int tid)
+{
+    const int wpr = pl >> 2;  // words per tile row
+    for (int idx = tid; idx < tile_rows * wpr; idx += 32 * kWarps) {
+        const int r = idx / wpr, c = (idx - r * wpr) << 2;
+        const int y = y0 + r, x = x0 + c;
+        unsigned* w = reinterpret_cast<unsigned*>(tile + r * pl + c);
+        if ((unsigned)y >= (unsigned)n_rows || x + 3 < 0 || x >= n_bytes) {
+            *w = pattern;
+        } else if (x < 0 || x + 3 >= n_bytes) {
+            unsigned v = *w;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if ((unsigned)(x + k) >= (unsigned)n_bytes) v = (v & ~(0xffu << (8 * k))) | (pattern & (0xffu << (8 * k)));
+            *w = v;
+        }
+    }
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(32 * kWarps, 5)
+warp_nv12_tile_kernel(const Geom g, const FrameBatch b, const PieceRec* __restrict__ table,
+                      const __grid_constant__ TileMaps maps)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int lane = threadIdx.x, w = threadIdx.y, tid = w * 32 + lane;
+    const int px = blockIdx.x, py = blockIdx.y, frame = blockIdx.z;
+    const int npx = pieces_x(g.out_w), npy = pieces_y(g.out_h, kPieceHMax);
+    const PieceRec* rec = table + ((size_t)frame * npy + py) * npx + px;
+    const unsigned flags = __ldg(&rec->flags);
+    const int u_lo = px * kPieceW, u0 = u_lo + 4 * lane, v_base = py * kPieceHMax;
+    const int rows = min(kPieceHMax, g.out_h - v_base);  // even for NV12
+    const int dv0 = w * kRowsPerWarp;
+    const int my_rows = max(0, min(kRowsPerWarp, rows - dv0));
+    const int valid = g.out_w - u0;
+
+    PlaneRefs f;
+    f.y = b.src + (size_t)frame * b.src_frame_stride;
+    f.uv = f.y + (size_t)g.src_pitch * g.src_h;
+    f.dst = b.dst + (size_t)frame * b.dst_frame_stride;
+
+    RowPtrs o;
+    o.y0 = f.dst + (size_t)(v_base + dv0) * g.dst_pitch + u0;
+    o.y1 = o.y0 + g.dst_pitch;
+    o.c = f.dst + (size_t)(g.out_h + ((v_base + dv0) >> 1)) * g.dst_pitch + u0;
+    o.step_y = 2 * (size_t)g.dst_pitch;
+    o.step_c = (size_t)g.dst_pitch;
+    const bool word_ok = ((reinterpret_cast<uintptr_t>(f.dst) | (uintptr_t)g.dst_pitch) & 3) == 0 &&
+                         u_lo + kPieceW <= g.out_w;
+
+    if (flags & kPieceOutside) {  // pure border: nothing to compute
+        const unsigned yw = (g.border & 255u) * 0x01010101u;
+        const unsigned cw = ((g.border >> 8) & 0xffffu) * 0x00010001u;
+        if (valid > 0)
+            for (int dv = 0; dv < my_rows; dv += 2) {
+                store_word<true>(o.y0, yw, valid);
+                store_word<true>(o.y1, yw, valid);
+                store_word<true>(o.c, cw, valid);
+                o.y0 += o.step_y; o.y1 += o.step_y; o.c += o.step_c;
+            }
+        return;
+    }
+
+    if (!(flags & kPiecePoly)) {  // op-for-op per pixel
+        const Rot R = load_rot(b, frame);
+        for (int dv = dv0; dv < dv0 + my_rows; dv += 2) {
+            float mx[2][4], my[2][4];
+            exact_rows(g, R, u_lo, u0, v_base + dv, mx, my);
+            sample_rows_checked(g, f, u0, v_base + dv, mx, my);
+        }
+        return;
+    }
+
+    // ---- the source rectangle of this piece's taps (block-uniform) ---------------------------
+    const int4 raw = __ldg(reinterpret_cast<const int4*>(&rec->box));
+    const int bx0 = (int16_t)(raw.x & 0xffff), bx1 = (int16_t)(raw.x >> 16);
+    const int by0 = (int16_t)(raw.y & 0xffff), by1 = (int16_t)(raw.y >> 16);
+    const int cx0 = (int16_t)(raw.z & 0xffff), cx1 = (int16_t)(raw.z >> 16);
+    const int cy0 = (int16_t)(raw.w & 0xffff), cy1 = (int16_t)(raw.w >> 16);
+    const int lx0 = bx0 & ~15, wb = (bx1 - lx0 + 16) & ~15;
+    const int cbx0 = (2 * cx0) & ~15, cwb = (2 * cx1 + 2 - cbx0 + 15) & ~15;
+    const int nr8 = (by1 - by0 + 8) & ~7, cnr8 = (cy1 - cy0 + 8) & ~7;  // rows, rounded up to whole boxes
+    const int pl = max(kTileMinPitch, (max(wb, cwb) + 31) & ~31);
+    const bool fits = maps.enabled && pl <= kTileMaxPitch && nr8 > 0 && cnr8 > 0 && pl * (nr8 + cnr8) <= kTileCap;
+
+    if (!fits) {  // gather from global memory like variant POLY (each warp collapses for itself)
+        if (my_rows <= 0) return;
+        ColPoly cp;
+        derive(rec, lane, cp);
+        if (flags & kPieceInterior) {
+            if (word_ok) band_gmem<false>(g, cp, f, dv0, my_rows, o, valid);
+            else band_gmem<true>(g, cp, f, dv0, my_rows, o, valid);
+        } else {
+            for (int dv = dv0; dv < dv0 + my_rows; dv += 2) {
+                float mx[2][4], my[2][4];
+                row_coords(cp, row_t(g, dv), mx[0], my[0]);
+                row_coords(cp, row_t(g, dv + 1), mx[1], my[1]);
+                sample_rows_checked(g, f, u0, v_base + dv, mx, my);
+            }
+        }
+        return;
+    }
+
+    uint8_t* ltile = smem;
+    uint8_t* ctile = smem + nr8 * pl;
+    float4* coefs = reinterpret_cast<float4*>(smem + kTileCap);
+    const unsigned mbar = smem_u32(smem + kTileCap + kCoefBytes);
+
+    // ---- thread 0: arm the barrier, launch the tile loads ---------------------------------------
+    if (tid == 0) {
+        mbar_init(mbar, 1);
+        mbar_expect_tx(mbar, (unsigned)(pl * (nr8 + cnr8)));
+        const CUtensorMap* map = &maps.m[(pl - kTileMinPitch) / kTilePitchStep];
+        const unsigned l0 = smem_u32(ltile), c0 = smem_u32(ctile);
+        for (int k = 0; k < nr8; k += 8) tma_load_3d(l0 + (unsigned)(k * pl), map, lx0 >> 2, by0 + k, frame, mbar);
+        for (int k = 0; k < cnr8; k += 8)
+            tma_load_3d(c0 + (unsigned)(k * pl), map, cbx0 >> 2, g.src_h + cy0 + k, frame, mbar);
+    }
+
+    // ---- collapse the polynomial: warp w does column j = w for every lane -------------------------
+    {
+        const float4* r4 = reinterpret_cast<const float4*>(rec);
+        float c[2][kNu][kNv];
+#pragma unroll
+        for (int q = 0; q < 12; ++q) {
+            const float4 v = __ldg(r4 + q);
+            float* dst = &c[0][0][0] + 4 * q;
+            dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+        }
+        const float s = ((float)(4 * lane + w) - 63.5f) * 0.015625f;  // exact
+#pragma unroll
+        for (int co = 0; co < 2; ++co) {
+            float a[kNv];
+#pragma unroll
+            for (int k = 0; k < kNv; ++k) {
+                float acc = c[co][kDegU][k];
+#pragma unroll
+                for (int i = kDegU - 1; i >= 0; --i) acc = __fmaf_rn(acc, s, c[co][i][k]);
+                a[k] = acc;
+            }
+            coefs[(2 * w + co) * 32 + lane] = make_float4(a[0], a[1], a[2], a[3]);
+        }
+    }
+    __syncthreads();  // column polynomials exchanged; the barrier init is visible to every thread
+    ColPoly cp;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int co = 0; co < 2; ++co) {
+            const float4 v = coefs[(2 * j + co) * 32 + lane];
+            cp.a[co][j][0] = v.x; cp.a[co][j][1] = v.y; cp.a[co][j][2] = v.z; cp.a[co][j][3] = v.w;
+        }
+    {
+        const float4 tail = __ldg(reinterpret_cast<const float4*>(rec) + 12);
+        cp.bx = tail.x;
+        cp.by = tail.y;
+    }
+
+    mbar_wait(mbar, 0);  // the tile has landed
+
+    if (!(flags & kPieceInterior)) {  // straddles the frame border: paint the outside cells
+        const unsigned by_ = g.border & 255u, bu = (g.border >> 8) & 255u, bv = (g.border >> 16) & 255u;
+        fill_border(ltile, pl, nr8, by0, g.src_h, lx0, g.src_w, by_ * 0x01010101u, tid);
+        fill_border(ctile, pl, cnr8, cy0, g.src_h >> 1, cbx0, g.src_w, (bu | (bv << 8)) * 0x00010001u, tid);
+        __syncthreads();
+    }
+
+    if (my_rows <= 0) return;
+    // tap address = (iy - y0) * pl + (ix - x0) + tile, with the >>5 bias of the magic constant folded in
+    const unsigned upl = (unsigned)pl;
+    const unsigned lconst = smem_u32(ltile) - (unsigned)by0 * upl - (unsigned)lx0 - kMagicShift * upl - kMagicShift;
+    const unsigned cconst = ((smem_u32(ctile) - (unsigned)cy0 * upl - (unsigned)cbx0 - kMagicShift * upl) >> 1) - kMagicShift;
+    if (word_ok) rows_tile<false>(g, cp, lconst, cconst, upl, dv0, my_rows, o, valid);
+    else rows_tile<true>(g, cp, lconst, cconst, upl, dv0, my_rows, o, valid);
+}
+
+cudaError_t launch_warp_nv12_tile(const Geom& g, const FrameBatch& b, const PieceRec* table, const TileMaps& maps,
+                                  cudaStream_t st)
+{
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(warp_nv12_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
+    dim3 block(32, kWarps);
+    dim3 grid(pieces_x(g.out_w), pieces_y(g.out_h, kPieceHMax), b.n_frames);
+    warp_nv12_tile_kernel<<<grid, block, kSmemBytes, st>>>(g, b, table, maps);
+    return cudaGetLastError();
+}
+
+}  // namespace vaw
