@@ -47,6 +47,8 @@ def build(force=False, verbose=False):
     # use the system host compiler regardless of CC/CXX wrappers
     cmd = [nvcc(), *NVCC_FLAGS, "-ccbin", shutil.which("g++") or "g++", "-o", LIB,
            *[os.path.join(CSRC, s) for s in SOURCES]]
+    for macro in os.environ.get("VAW_DEFINES", "").split():
+        cmd.insert(1, "-D" + macro)
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

@@ -419,6 +419,7 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
         vaw::GeomD& d = ctx->gd;
         d.scx = g.scx; d.scy = g.scy; d.sfx = g.sfx; d.sfy = g.sfy;  // the fp32 scalars, widened
         d.mcx = g.mcx; d.mcy = g.mcy; d.mfx = g.mfx; d.mfy = g.mfy;
+        d.inv_mfx = 1.0 / d.mfx; d.inv_mfy = 1.0 / d.mfy;
         d.src_w = g.src_w; d.src_h = g.src_h; d.out_w = g.out_w; d.out_h = g.out_h;
         d.piece_h = ph;
         make_basis(ctx->basis, ph);

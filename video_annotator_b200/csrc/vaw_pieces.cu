@@ -29,17 +29,20 @@ struct Ray { double mx, my, q0, q1, q2; };
 // createMap.cl:15-49 in double precision, for a (possibly fractional) output position.
 __device__ __forceinline__ Ray project(const GeomD& g, const RotD& R, double u, double v)
 {
-    const double x = (u - g.mcx) / g.mfx, y = (v - g.mcy) / g.mfy;
+    // one reciprocal per divisor (1e-16 relative error; the anchors need ~1e-10)
+    const double x = (u - g.mcx) * g.inv_mfx, y = (v - g.mcy) * g.inv_mfy;
     Ray o;
     o.q0 = R.r[0] * x + R.r[1] * y + R.r[2];
     o.q1 = R.r[3] * x + R.r[4] * y + R.r[5];
     o.q2 = R.r[6] * x + R.r[7] * y + R.r[8];
-    const double c0 = o.q0 / o.q2, c1 = o.q1 / o.q2;
+    const double iq = 1.0 / o.q2;
+    const double c0 = o.q0 * iq, c1 = o.q1 * iq;
     const double r2 = c0 * c0 + c1 * c1;
-    const double r = sqrt(r2);
+    const double ir = rsqrt(r2);
+    const double r = r2 * ir;
     // atan(r)/r is analytic in r^2; the series avoids 0/0 (the reference's NaN at r == 0 is
     // reproduced by sending the piece that contains the axis to the per-pixel path)
-    const double k = r > 1e-4 ? atan(r) / r : 1.0 - r2 * (1.0 / 3.0 - r2 * 0.2);
+    const double k = r > 1e-4 ? atan(r) * ir : 1.0 - r2 * (1.0 / 3.0 - r2 * 0.2);
     o.mx = g.scx + c0 * k * g.sfx;
     o.my = g.scy + c1 * k * g.sfy;
     return o;
@@ -48,7 +51,7 @@ __device__ __forceinline__ Ray project(const GeomD& g, const RotD& R, double u, 
 // only the rotated ray (createMap.cl:22-30): enough for the regularity certificate
 __device__ __forceinline__ Ray ray_only(const GeomD& g, const RotD& R, double u, double v)
 {
-    const double x = (u - g.mcx) / g.mfx, y = (v - g.mcy) / g.mfy;
+    const double x = (u - g.mcx) * g.inv_mfx, y = (v - g.mcy) * g.inv_mfy;
     Ray o;
     o.q0 = R.r[0] * x + R.r[1] * y + R.r[2];
     o.q1 = R.r[3] * x + R.r[4] * y + R.r[5];
@@ -60,17 +63,20 @@ __device__ __forceinline__ Ray ray_only(const GeomD& g, const RotD& R, double u,
 __device__ __forceinline__ double node_u(int ig) { return 128.0 * (ig / kDegU) + (128.0 * (ig % kDegU)) / kDegU; }
 __device__ __forceinline__ double node_v(int jg, int ph) { return (double)ph * (jg / kDegV) + ((double)ph * (jg % kDegV)) / kDegV; }
 
-__device__ __forceinline__ double poly_eval(const float (&c)[kNu][kNv], double base, double s, double t)
+__device__ __forceinline__ float coef(const PieceRec& r, int c, int i, int j) { return c ? r.c[i][j].y : r.c[i][j].x; }
+__device__ __forceinline__ float base_of(const PieceRec& r, int c) { return c ? r.base.y : r.base.x; }
+
+__device__ __forceinline__ double poly_eval(const PieceRec& r, int c, double s, double t)
 {
     double acc = 0.0;
 #pragma unroll
     for (int i = kDegU; i >= 0; --i) {
         double a = 0.0;
 #pragma unroll
-        for (int j = kDegV; j >= 0; --j) a = a * t + (double)c[i][j];
+        for (int j = kDegV; j >= 0; --j) a = a * t + (double)coef(r, c, i, j);
         acc = acc * s + a;
     }
-    return base + acc;
+    return (double)base_of(r, c) + acc;
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -136,14 +142,13 @@ build_pieces_kernel(const GeomD g, const PieceBasis basis, const float* __restri
             for (int b = 0; b < kNv; ++b) acc += basis.mv[j][b] * ucoef[p][c][b][i];
             co[j] = acc;
         }
-        float (&dst)[kNu][kNv] = c ? recs[p].cy : recs[p].cx;
         if (i == 0) {
             const double base = nearbyint(co[0]);
-            (c ? recs[p].base_y : recs[p].base_x) = (float)base;
+            (c ? recs[p].base.y : recs[p].base.x) = (float)base;
             co[0] -= base;
         }
 #pragma unroll
-        for (int j = 0; j < kNv; ++j) dst[i][j] = (float)co[j];
+        for (int j = 0; j < kNv; ++j) (c ? recs[p].c[i][j].y : recs[p].c[i][j].x) = (float)co[j];
     }
     __syncthreads();
 
@@ -155,8 +160,8 @@ build_pieces_kernel(const GeomD g, const PieceBasis basis, const float* __restri
         const double dv = (which == 1 ? 0.894 : 0.106) * ph;
         const Ray e = project(g, R, 128.0 * (p0 + p) + du, (double)ph * py + dv);
         const double s = (du - 63.5) / 64.0, t = (dv - 0.5 * (ph - 1)) * (2.0 / ph);
-        const double ex = poly_eval(recs[p].cx, (double)recs[p].base_x, s, t) - e.mx;
-        const double ey = poly_eval(recs[p].cy, (double)recs[p].base_y, s, t) - e.my;
+        const double ex = poly_eval(recs[p], 0, s, t) - e.mx;
+        const double ey = poly_eval(recs[p], 1, s, t) - e.my;
         if (!(fabs(ex) <= 5e-5 && fabs(ey) <= 5e-5)) bad[p] = 1;
     }
     __syncthreads();
@@ -182,8 +187,8 @@ build_pieces_kernel(const GeomD g, const PieceBasis basis, const float* __restri
         for (int i = 0; i < kNu; ++i)
 #pragma unroll
             for (int j = 0; j < kNv; ++j)
-                if (i | j) { rx += fabs((double)rec.cx[i][j]); ry += fabs((double)rec.cy[i][j]); }
-        const double cxm = (double)rec.base_x + (double)rec.cx[0][0], cym = (double)rec.base_y + (double)rec.cy[0][0];
+                if (i | j) { rx += fabs((double)rec.c[i][j].x); ry += fabs((double)rec.c[i][j].y); }
+        const double cxm = (double)rec.base.x + (double)rec.c[0][0].x, cym = (double)rec.base.y + (double)rec.c[0][0].y;
         const double lo_x = cxm - rx - 0.01, hi_x = cxm + rx + 0.01, lo_y = cym - ry - 0.01, hi_y = cym + ry + 0.01;
         ok = ok && fabs(lo_x) < 60000.0 && fabs(hi_x) < 60000.0 && fabs(lo_y) < 60000.0 && fabs(hi_y) < 60000.0;
         uint32_t flags = 0;
@@ -209,14 +214,13 @@ build_pieces_kernel(const GeomD g, const PieceBasis basis, const float* __restri
             double lo[2], hi[2];
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
-                const float (&co)[kNu][kNv] = c ? rec.cy : rec.cx;
                 double rad = 0.0;
 #pragma unroll
                 for (int i = 0; i < kNu; ++i)
 #pragma unroll
                     for (int j = 0; j < kNv; ++j)
-                        if (i | j) rad += fabs((double)co[i][j]);
-                const double centre = (double)(c ? rec.base_y : rec.base_x) + (double)co[0][0];
+                        if (i | j) rad += fabs((double)coef(rec, c, i, j));
+                const double centre = (double)base_of(rec, c) + (double)coef(rec, c, 0, 0);
                 lo[c] = fmax(centre - rad - 0.02, -30000.0);
                 hi[c] = fmin(centre + rad + 0.02, 30000.0);
             }

@@ -46,10 +46,11 @@ struct PieceBox {
 // One record per (frame, piece): 224 bytes, 16-byte aligned.
 // coordinate = base + sum_{i<=5, j<=3} c[i][j] * s^i * t^j,
 //   s = (du - 63.5) / 64, t = (dv - (PH-1)/2) * 2/PH, (du, dv) = pixel offset inside the piece.
+// x and y coefficients are interleaved so that both coordinates run through the packed
+// FFMA2 / FADD2 instructions of sm_100 (one issue slot for two fp32 operations).
 struct PieceRec {
-    float cx[kNu][kNv];
-    float cy[kNu][kNv];
-    float base_x, base_y;  // integers: base + offset rounds once to the fp32 coordinate
+    float2 c[kNu][kNv];    // (x, y) coefficient of s^i t^j
+    float2 base;           // integers: base + offset rounds once to the fp32 coordinate
     uint32_t flags;
     uint32_t pad;
     PieceBox box;  // valid for certified pieces that are not pure border
@@ -65,6 +66,7 @@ struct PieceBasis {
 
 struct GeomD {  // the 8 fp32 scalars of FrameSourceWarp.cpp:283-290, widened exactly
     double scx, scy, sfx, sfy, mcx, mcy, mfx, mfy;
+    double inv_mfx, inv_mfy;
     int src_w, src_h, out_w, out_h;
     int piece_h;
 };

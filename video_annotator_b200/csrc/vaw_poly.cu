@@ -65,9 +65,9 @@ warp_nv12_poly_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
     if (!(flags & kPiecePoly)) {  // op-for-op per pixel
         const Rot R = load_rot(b, frame);
         for (int dv = 0; dv < rows; dv += 2) {
-            float mx[2][4], my[2][4];
-            exact_rows(g, R, u_lo, u0, v_base + dv, mx, my);
-            sample_rows_checked(g, f, u0, v_base + dv, mx, my);
+            float2 m[2][4];
+            exact_rows(g, R, u_lo, u0, v_base + dv, m);
+            sample_rows_checked(g, f, u0, v_base + dv, m);
         }
         return;
     }
@@ -77,10 +77,10 @@ warp_nv12_poly_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
 
     if (!(flags & kPieceInterior)) {  // polynomial coordinates, checked sampler
         for (int dv = 0; dv < rows; dv += 2) {
-            float mx[2][4], my[2][4];
-            row_coords(cp, row_t(g, dv), mx[0], my[0]);
-            row_coords(cp, row_t(g, dv + 1), mx[1], my[1]);
-            sample_rows_checked(g, f, u0, v_base + dv, mx, my);
+            float2 m[2][4];
+            row_coords(cp, row_t(g, dv), m[0]);
+            row_coords(cp, row_t(g, dv + 1), m[1]);
+            sample_rows_checked(g, f, u0, v_base + dv, m);
         }
         return;
     }
@@ -110,27 +110,27 @@ dump_coords_poly_kernel(const Geom g, const Rot R, const PieceRec* __restrict__ 
     ColPoly cp;
     if (flags & kPiecePoly) derive(rec, lane, cp);
     for (int dv = 0; dv < rows; dv += 2) {
-        float mx[2][4], my[2][4];
+        float2 m[2][4];
         const int v0 = v_base + dv;
         if (flags & kPiecePoly) {
-            row_coords(cp, row_t(g, dv), mx[0], my[0]);
-            row_coords(cp, row_t(g, dv + 1), mx[1], my[1]);
+            row_coords(cp, row_t(g, dv), m[0]);
+            row_coords(cp, row_t(g, dv + 1), m[1]);
         } else {
-            exact_rows(g, R, u_lo, u0, v0, mx, my);
+            exact_rows(g, R, u_lo, u0, v0, m);
         }
         if (plane == 0) {
             for (int r = 0; r < 2; ++r)
                 for (int i = 0; i < 4; ++i)
                     if (u0 + i < g.out_w && v0 + r < g.out_h) {
-                        map_x[(size_t)(v0 + r) * map_pitch + u0 + i] = mx[r][i];
-                        map_y[(size_t)(v0 + r) * map_pitch + u0 + i] = my[r][i];
+                        map_x[(size_t)(v0 + r) * map_pitch + u0 + i] = m[r][i].x;
+                        map_y[(size_t)(v0 + r) * map_pitch + u0 + i] = m[r][i].y;
                     }
         } else {
             for (int q = 0; q < 2; ++q)
                 if (u0 + 2 * q + 1 < g.out_w && v0 + 1 < g.out_h) {
                     const size_t o = (size_t)(v0 >> 1) * map_pitch + (u0 >> 1) + q;
-                    map_x[o] = chroma_coord(mx[0][2 * q], mx[0][2 * q + 1], mx[1][2 * q], mx[1][2 * q + 1]);
-                    map_y[o] = chroma_coord(my[0][2 * q], my[0][2 * q + 1], my[1][2 * q], my[1][2 * q + 1]);
+                    map_x[o] = chroma_coord(m[0][2 * q].x, m[0][2 * q + 1].x, m[1][2 * q].x, m[1][2 * q + 1].x);
+                    map_y[o] = chroma_coord(m[0][2 * q].y, m[0][2 * q + 1].y, m[1][2 * q].y, m[1][2 * q + 1].y);
                 }
         }
     }

@@ -18,53 +18,67 @@ constexpr float kMagic = 12582912.0f;  // 1.5 * 2^23: float add -> round-half-ev
 constexpr int kMagicBits = 0x4B400000;
 constexpr unsigned kMagicShift = (unsigned)(kMagicBits >> 5);  // bias left in (bits >> 5)
 
+// (x, y) pairs throughout: FFMA2 / FADD2 (sm_100) do both coordinates in one issue slot and are
+// two ordinary IEEE fp32 operations, so nothing changes numerically.
 struct ColPoly {
-    float a[2][4][kNv];  // [coordinate][column][power of t]
-    float bx, by;
+    float2 a[4][kNv];  // [column][power of t]
+    float2 base;
 };
 
-// Collapse the piece polynomial onto this lane's four columns (160 FMAs per piece).
-__device__ __forceinline__ void derive(const PieceRec* __restrict__ rec, int lane, ColPoly& cp)
+__device__ __forceinline__ float2 pair(float v) { return make_float2(v, v); }
+
+// Horner in s for one column: coefficients (x, y) of t^k, k = 0..3
+__device__ __forceinline__ void collapse_column(const float2 (&c)[kNu][kNv], float s, float2 (&out)[kNv])
 {
-    const float4* r4 = reinterpret_cast<const float4*>(rec);
-    float c[2][kNu][kNv];
+    const float2 ss = pair(s);
 #pragma unroll
-    for (int q = 0; q < 12; ++q) {
-        const float4 v = __ldg(r4 + q);
-        float* dst = &c[0][0][0] + 4 * q;
-        dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
-    }
-    const float4 tail = __ldg(r4 + 12);
-    cp.bx = tail.x;
-    cp.by = tail.y;
+    for (int k = 0; k < kNv; ++k) {
+        float2 acc = c[kDegU][k];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float s = ((float)(4 * lane + j) - 63.5f) * 0.015625f;  // exact
-#pragma unroll
-        for (int co = 0; co < 2; ++co)
-#pragma unroll
-            for (int k = 0; k < kNv; ++k) {
-                float acc = c[co][kDegU][k];
-#pragma unroll
-                for (int i = kDegU - 1; i >= 0; --i) acc = __fmaf_rn(acc, s, c[co][i][k]);
-                cp.a[co][j][k] = acc;
-            }
+        for (int i = kDegU - 1; i >= 0; --i) acc = __ffma2_rn(acc, ss, c[i][k]);
+        out[k] = acc;
     }
 }
 
-// fp32 coordinates of the lane's 4 columns on one row; t = (dv - t_off) * t_scale (exact).
-__device__ __forceinline__ void row_coords(const ColPoly& cp, float t, float (&mx)[4], float (&my)[4])
+__device__ __forceinline__ void load_coeffs(const PieceRec* __restrict__ rec, float2 (&c)[kNu][kNv])
 {
+    const float4* r4 = reinterpret_cast<const float4*>(rec);
+#pragma unroll
+    for (int q = 0; q < 12; ++q) {
+        const float4 v = __ldg(r4 + q);
+        float2* dst = &c[0][0] + 2 * q;
+        dst[0] = make_float2(v.x, v.y);
+        dst[1] = make_float2(v.z, v.w);
+    }
+}
+
+__device__ __forceinline__ float2 load_base(const PieceRec* __restrict__ rec)
+{
+    const float4 tail = __ldg(reinterpret_cast<const float4*>(rec) + 12);
+    return make_float2(tail.x, tail.y);
+}
+
+// Collapse the piece polynomial onto this lane's four columns (80 FFMA2 per piece).
+__device__ __forceinline__ void derive(const PieceRec* __restrict__ rec, int lane, ColPoly& cp)
+{
+    float2 c[kNu][kNv];
+    load_coeffs(rec, c);
+    cp.base = load_base(rec);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        collapse_column(c, ((float)(4 * lane + j) - 63.5f) * 0.015625f, cp.a[j]);  // s is exact
+}
+
+// fp32 coordinates (x, y) of the lane's 4 columns on one row; t = (dv - t_off) * t_scale (exact).
+__device__ __forceinline__ void row_coords(const ColPoly& cp, float t, float2 (&m)[4])
+{
+    const float2 tt = pair(t);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        float px = __fmaf_rn(cp.a[0][j][3], t, cp.a[0][j][2]);
-        px = __fmaf_rn(px, t, cp.a[0][j][1]);
-        px = __fmaf_rn(px, t, cp.a[0][j][0]);
-        mx[j] = __fadd_rn(cp.bx, px);  // the map value: rounded once to fp32
-        float py = __fmaf_rn(cp.a[1][j][3], t, cp.a[1][j][2]);
-        py = __fmaf_rn(py, t, cp.a[1][j][1]);
-        py = __fmaf_rn(py, t, cp.a[1][j][0]);
-        my[j] = __fadd_rn(cp.by, py);
+        float2 p = __ffma2_rn(cp.a[j][3], tt, cp.a[j][2]);
+        p = __ffma2_rn(p, tt, cp.a[j][1]);
+        p = __ffma2_rn(p, tt, cp.a[j][0]);
+        m[j] = __fadd2_rn(cp.base, p);  // the map value: rounded once to fp32
     }
 }
 
@@ -73,9 +87,15 @@ __device__ __forceinline__ float row_t(const Geom& g, int dv) { return __fmul_rn
 // Twice the NV12 chroma coordinate of a luma quad: chroma_coord() = ((sum * 0.25) - 0.5) * 0.5 where
 // the two multiplications are exact, so z = fma(sum, 0.25, -0.5) carries the single rounding and
 // rint(32 * coordinate) = rint(16 * z).
-__device__ __forceinline__ float chroma_z(float m00, float m01, float m10, float m11)
+__device__ __forceinline__ float2 chroma_z(float2 m00, float2 m01, float2 m10, float2 m11)
 {
-    return __fmaf_rn(__fadd_rn(__fadd_rn(m00, m01), __fadd_rn(m10, m11)), 0.25f, -0.5f);
+    return __ffma2_rn(__fadd2_rn(__fadd2_rn(m00, m01), __fadd2_rn(m10, m11)), pair(0.25f), pair(-0.5f));
+}
+// rint(32 m) in the mantissa: fma(m, 32, 1.5 * 2^23) for both coordinates (16 for chroma z)
+__device__ __forceinline__ int2 fix_bits(float2 m, float scale)
+{
+    const float2 s = __ffma2_rn(m, pair(scale), pair(kMagic));
+    return make_int2(__float_as_int(s.x), __float_as_int(s.y));
 }
 
 // ---- the integer blend --------------------------------------------------------------------
@@ -103,11 +123,10 @@ __device__ __forceinline__ unsigned blend_uv(unsigned t00, unsigned t01, unsigne
 // ---- samplers without border tests, taps from global memory ---------------------------------
 // rint(32 m) sits in the mantissa of fma(m, 32, 1.5*2^23); >> 5 keeps a constant bias that is
 // folded into `bias` (all offset arithmetic is modulo 2^32 and the true offset fits).
-__device__ __forceinline__ int luma_gmem(const uint8_t* __restrict__ plane, unsigned pitch, unsigned bias,
-                                         float mx, float my)
+__device__ __forceinline__ int luma_gmem(const uint8_t* __restrict__ plane, unsigned pitch, unsigned bias, float2 m)
 {
-    const int bx = __float_as_int(__fmaf_rn(mx, 32.0f, kMagic));
-    const int by = __float_as_int(__fmaf_rn(my, 32.0f, kMagic));
+    const int2 bb = fix_bits(m, 32.0f);
+    const int bx = bb.x, by = bb.y;
     const unsigned off = (unsigned)(by >> 5) * pitch + ((unsigned)(bx >> 5) + bias);
     const uint8_t* p = plane + off;
     const uint8_t* q = p + pitch;
@@ -115,10 +134,10 @@ __device__ __forceinline__ int luma_gmem(const uint8_t* __restrict__ plane, unsi
 }
 
 __device__ __forceinline__ unsigned chroma_gmem(const uint8_t* __restrict__ plane, unsigned pitch, unsigned bias,
-                                                float zx, float zy)
+                                                float2 z)
 {
-    const int bx = __float_as_int(__fmaf_rn(zx, 16.0f, kMagic));
-    const int by = __float_as_int(__fmaf_rn(zy, 16.0f, kMagic));
+    const int2 bb = fix_bits(z, 16.0f);
+    const int bx = bb.x, by = bb.y;
     const unsigned off = (unsigned)(by >> 5) * pitch + (((unsigned)(bx >> 5) + bias) << 1);
     const uint8_t* p = plane + off;
     const uint8_t* q = p + pitch;
@@ -141,24 +160,6 @@ __device__ __forceinline__ unsigned lds_u16(unsigned addr)
     unsigned v;
     asm volatile("ld.shared.u16 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(IMM));
     return v;
-}
-
-template <int PL>
-__device__ __forceinline__ int luma_smem(unsigned lconst, float mx, float my)
-{
-    const int bx = __float_as_int(__fmaf_rn(mx, 32.0f, kMagic));
-    const int by = __float_as_int(__fmaf_rn(my, 32.0f, kMagic));
-    const unsigned a = (unsigned)(by >> 5) * (unsigned)PL + ((unsigned)(bx >> 5) + lconst);
-    return blend_y(lds_u8<0>(a), lds_u8<1>(a), lds_u8<PL>(a), lds_u8<PL + 1>(a), bx & 31, by & 31);
-}
-
-template <int PL>
-__device__ __forceinline__ unsigned chroma_smem(unsigned cconst, float zx, float zy)
-{
-    const int bx = __float_as_int(__fmaf_rn(zx, 16.0f, kMagic));
-    const int by = __float_as_int(__fmaf_rn(zy, 16.0f, kMagic));
-    const unsigned a = (unsigned)(by >> 5) * (unsigned)PL + (((unsigned)(bx >> 5) + cconst) << 1);
-    return blend_uv(lds_u16<0>(a), lds_u16<2>(a), lds_u16<PL>(a), lds_u16<PL + 2>(a), bx & 31, by & 31);
 }
 
 // ---- packing and stores ------------------------------------------------------------------------
@@ -188,7 +189,7 @@ struct PlaneRefs {
 
 // Checked sampling of one row pair from given coordinates (mixed pieces, per-pixel fallback).
 __device__ __forceinline__ void sample_rows_checked(const Geom& g, const PlaneRefs& f, int u0, int v0,
-                                                    const float (&mx)[2][4], const float (&my)[2][4])
+                                                    const float2 (&m)[2][4])
 {
     const int border_y = g.border & 255;
     const unsigned border_uv = (g.border >> 8) & 0xffffu;
@@ -198,12 +199,12 @@ __device__ __forceinline__ void sample_rows_checked(const Geom& g, const PlaneRe
     for (int r = 0; r < 2; ++r)
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-            yw[r] |= (unsigned)sample_c1(f.y, g.src_pitch, g.src_w, g.src_h, mx[r][i], my[r][i], border_y) << (8 * i);
+            yw[r] |= (unsigned)sample_c1(f.y, g.src_pitch, g.src_w, g.src_h, m[r][i].x, m[r][i].y, border_y) << (8 * i);
     unsigned cw = 0u;
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
-        const float cx = chroma_coord(mx[0][2 * q], mx[0][2 * q + 1], mx[1][2 * q], mx[1][2 * q + 1]);
-        const float cy = chroma_coord(my[0][2 * q], my[0][2 * q + 1], my[1][2 * q], my[1][2 * q + 1]);
+        const float cx = chroma_coord(m[0][2 * q].x, m[0][2 * q + 1].x, m[1][2 * q].x, m[1][2 * q + 1].x);
+        const float cy = chroma_coord(m[0][2 * q].y, m[0][2 * q + 1].y, m[1][2 * q].y, m[1][2 * q + 1].y);
         cw |= sample_c2(f.uv, g.src_pitch, g.src_w >> 1, g.src_h >> 1, cx, cy, border_uv) << (16 * q);
     }
     if (valid > 0) {
@@ -214,8 +215,7 @@ __device__ __forceinline__ void sample_rows_checked(const Geom& g, const PlaneRe
 }
 
 // Per-pixel op-for-op coordinates of a row pair (pieces without a polynomial certificate).
-__device__ __forceinline__ void exact_rows(const Geom& g, const Rot& R, int u_lo, int u0, int v0,
-                                           float (&mx)[2][4], float (&my)[2][4])
+__device__ __forceinline__ void exact_rows(const Geom& g, const Rot& R, int u_lo, int u0, int v0, float2 (&m)[2][4])
 {
     const float4 xs = __ldg(reinterpret_cast<const float4*>(g.xtab + u0));
     const float2 ys = __ldg(reinterpret_cast<const float2*>(g.ytab + v0));
@@ -227,12 +227,12 @@ __device__ __forceinline__ void exact_rows(const Geom& g, const Rot& R, int u_lo
 #pragma unroll
         for (int r = 0; r < 2; ++r)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) map_eval<true>(c[i], w[r], R, g, mx[r][i], my[r][i]);
+            for (int i = 0; i < 4; ++i) map_eval<true>(c[i], w[r], R, g, m[r][i].x, m[r][i].y);
     } else {
 #pragma unroll
         for (int r = 0; r < 2; ++r)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) map_eval<false>(c[i], w[r], R, g, mx[r][i], my[r][i]);
+            for (int i = 0; i < 4; ++i) map_eval<false>(c[i], w[r], R, g, m[r][i].x, m[r][i].y);
     }
 }
 
@@ -262,21 +262,19 @@ __device__ __forceinline__ void band_gmem(const Geom& g, const ColPoly& cp, cons
     const unsigned bias_c = 0u - kMagicShift * (pitch >> 1) - kMagicShift;  // offset = iy*pitch + 2*(ix + bias)
 #pragma unroll 1
     for (int dv = dv0; dv < dv0 + nrows; dv += 2) {
-        float mx[2][4], my[2][4];
-        row_coords(cp, row_t(g, dv), mx[0], my[0]);
-        row_coords(cp, row_t(g, dv + 1), mx[1], my[1]);
+        float2 m[2][4];
+        row_coords(cp, row_t(g, dv), m[0]);
+        row_coords(cp, row_t(g, dv + 1), m[1]);
         int acc[2][4];
 #pragma unroll
         for (int r = 0; r < 2; ++r)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) acc[r][i] = luma_gmem(f.y, pitch, bias_y, mx[r][i], my[r][i]);
+            for (int i = 0; i < 4; ++i) acc[r][i] = luma_gmem(f.y, pitch, bias_y, m[r][i]);
         unsigned cw = 0u;
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const float zx = chroma_z(mx[0][2 * q], mx[0][2 * q + 1], mx[1][2 * q], mx[1][2 * q + 1]);
-            const float zy = chroma_z(my[0][2 * q], my[0][2 * q + 1], my[1][2 * q], my[1][2 * q + 1]);
-            cw |= chroma_gmem(f.uv, pitch, bias_c, zx, zy) << (16 * q);
-        }
+        for (int q = 0; q < 2; ++q)
+            cw |= chroma_gmem(f.uv, pitch, bias_c, chroma_z(m[0][2 * q], m[0][2 * q + 1], m[1][2 * q], m[1][2 * q + 1]))
+                  << (16 * q);
         if (!kRagged || valid > 0) {
             store_word<kRagged>(o.y0, pack4(acc[0][0], acc[0][1], acc[0][2], acc[0][3]), valid);
             store_word<kRagged>(o.y1, pack4(acc[1][0], acc[1][1], acc[1][2], acc[1][3]), valid);

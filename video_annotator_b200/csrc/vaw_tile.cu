@@ -37,7 +37,10 @@ namespace {
 
 constexpr int kWarps = 4;
 constexpr int kRowsPerWarp = kPieceHMax / kWarps;  // 8
-constexpr int kTileCap = 36864;                    // bytes of luma + chroma tile per CTA
+#ifndef VAW_TILE_CTAS
+#define VAW_TILE_CTAS 6  // resident CTAs per SM the kernel is sized for (registers and shared memory)
+#endif
+constexpr int kTileCap = VAW_TILE_CTAS >= 6 ? 32768 : 36864;  // bytes of luma + chroma tile per CTA
 constexpr int kCoefBytes = 8 * 32 * 16;            // column polynomials exchanged between the warps
 constexpr int kSmemBytes = kTileCap + kCoefBytes + 16;
 
@@ -49,19 +52,19 @@ __device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* map
         : "memory");
 }
 
-__device__ __forceinline__ int luma_tile(unsigned lconst, unsigned pl, float mx, float my)
+__device__ __forceinline__ int luma_tile(unsigned lconst, unsigned pl, float2 m)
 {
-    const int bx = __float_as_int(__fmaf_rn(mx, 32.0f, kMagic));
-    const int by = __float_as_int(__fmaf_rn(my, 32.0f, kMagic));
+    const int2 bb = fix_bits(m, 32.0f);
+    const int bx = bb.x, by = bb.y;
     const unsigned a0 = (unsigned)(by >> 5) * pl + ((unsigned)(bx >> 5) + lconst);
     const unsigned a1 = a0 + pl;
     return blend_y(lds_u8<0>(a0), lds_u8<1>(a0), lds_u8<0>(a1), lds_u8<1>(a1), bx & 31, by & 31);
 }
 
-__device__ __forceinline__ unsigned chroma_tile(unsigned cconst, unsigned pl, float zx, float zy)
+__device__ __forceinline__ unsigned chroma_tile(unsigned cconst, unsigned pl, float2 z)
 {
-    const int bx = __float_as_int(__fmaf_rn(zx, 16.0f, kMagic));
-    const int by = __float_as_int(__fmaf_rn(zy, 16.0f, kMagic));
+    const int2 bb = fix_bits(z, 16.0f);
+    const int bx = bb.x, by = bb.y;
     const unsigned a0 = (unsigned)(by >> 5) * pl + (((unsigned)(bx >> 5) + cconst) << 1);
     const unsigned a1 = a0 + pl;
     return blend_uv(lds_u16<0>(a0), lds_u16<2>(a0), lds_u16<0>(a1), lds_u16<2>(a1), bx & 31, by & 31);
@@ -74,21 +77,18 @@ __device__ __forceinline__ void rows_tile(const Geom& g, const ColPoly& cp, unsi
 {
 #pragma unroll 1
     for (int dv = dv0; dv < dv0 + nrows; dv += 2) {
-        float mx[2][4], my[2][4];
-        row_coords(cp, row_t(g, dv), mx[0], my[0]);
-        row_coords(cp, row_t(g, dv + 1), mx[1], my[1]);
+        float2 m[2][4];
+        row_coords(cp, row_t(g, dv), m[0]);
+        row_coords(cp, row_t(g, dv + 1), m[1]);
         int acc[2][4];
 #pragma unroll
         for (int r = 0; r < 2; ++r)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) acc[r][i] = luma_tile(lconst, pl, mx[r][i], my[r][i]);
+            for (int i = 0; i < 4; ++i) acc[r][i] = luma_tile(lconst, pl, m[r][i]);
         unsigned cw = 0u;
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const float zx = chroma_z(mx[0][2 * q], mx[0][2 * q + 1], mx[1][2 * q], mx[1][2 * q + 1]);
-            const float zy = chroma_z(my[0][2 * q], my[0][2 * q + 1], my[1][2 * q], my[1][2 * q + 1]);
-            cw |= chroma_tile(cconst, pl, zx, zy) << (16 * q);
-        }
+        for (int q = 0; q < 2; ++q)
+            cw |= chroma_tile(cconst, pl, chroma_z(m[0][2 * q], m[0][2 * q + 1], m[1][2 * q], m[1][2 * q + 1])) << (16 * q);
         if (!kRagged || valid > 0) {
             store_word<kRagged>(o.y0, pack4(acc[0][0], acc[0][1], acc[0][2], acc[0][3]), valid);
             store_word<kRagged>(o.y1, pack4(acc[1][0], acc[1][1], acc[1][2], acc[1][3]), valid);
@@ -101,29 +101,33 @@ __device__ __forceinline__ void rows_tile(const Geom& g, const ColPoly& cp, unsi
 // Overwrite the cells of a staged plane that lie outside the source with the border value.
 // Tile row r <-> source row y0 + r (valid in [0, n_rows)); tile byte c <-> source byte x0 + c
 // (valid in [0, n_bytes)); `pattern` = the border replicated over 4 bytes (x0 is a multiple of 4).
+// Only the outside rows and the outside column strips are visited.
 __device__ __forceinline__ void fill_border(uint8_t* tile, int pl, int tile_rows, int y0, int n_rows, int x0,
                                             int n_bytes, unsigned pattern, int tid)
 {
-    const int wpr = pl >> 2;  // words per tile row
-    for (int idx = tid; idx < tile_rows * wpr; idx += 32 * kWarps) {
-        const int r = idx / wpr, c = (idx - r * wpr) << 2;
-        const int y = y0 + r, x = x0 + c;
-        unsigned* w = reinterpret_cast<unsigned*>(tile + r * pl + c);
-        if ((unsigned)y >= (unsigned)n_rows || x + 3 < 0 || x >= n_bytes) {
-            *w = pattern;
-        } else if (x < 0 || x + 3 >= n_bytes) {
-            unsigned v = *w;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if ((unsigned)(x + k) >= (unsigned)n_bytes) v = (v & ~(0xffu << (8 * k))) | (pattern & (0xffu << (8 * k)));
-            *w = v;
+    const int nthr = 32 * kWarps;
+    const int wpr = pl >> 2;                                  // words per tile row
+    const int r_lo = min(max(-y0, 0), tile_rows);             // rows [0, r_lo) are above the plane
+    const int r_hi = min(max(n_rows - y0, r_lo), tile_rows);  // rows [r_hi, tile_rows) are below it
+    unsigned* w = reinterpret_cast<unsigned*>(tile);
+    for (int idx = tid; idx < r_lo * wpr; idx += nthr) w[idx] = pattern;
+    for (int idx = r_hi * wpr + tid; idx < tile_rows * wpr; idx += nthr) w[idx] = pattern;
+    const int c_lo = min(max(-x0, 0), pl);                    // bytes [0, c_lo) are left of the plane
+    const int c_hi = min(max(n_bytes - x0, c_lo), pl);        // bytes [c_hi, pl) are right of it
+    const int strip = c_lo + (pl - c_hi);                     // outside bytes per inside row
+    if (strip > 0) {
+        const int total = (r_hi - r_lo) * strip;
+        for (int idx = tid; idx < total; idx += nthr) {
+            const int r = idx / strip, k = idx - r * strip;
+            const int c = k < c_lo ? k : c_hi + (k - c_lo);
+            tile[(r_lo + r) * pl + c] = (uint8_t)(pattern >> (8 * (c & 3)));
         }
     }
 }
 
 }  // namespace
 
-__global__ void __launch_bounds__(32 * kWarps, 5)
+__global__ void __launch_bounds__(32 * kWarps, VAW_TILE_CTAS)
 warp_nv12_tile_kernel(const Geom g, const FrameBatch b, const PieceRec* __restrict__ table,
                       const __grid_constant__ TileMaps maps)
 {
@@ -169,9 +173,9 @@ warp_nv12_tile_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
     if (!(flags & kPiecePoly)) {  // op-for-op per pixel
         const Rot R = load_rot(b, frame);
         for (int dv = dv0; dv < dv0 + my_rows; dv += 2) {
-            float mx[2][4], my[2][4];
-            exact_rows(g, R, u_lo, u0, v_base + dv, mx, my);
-            sample_rows_checked(g, f, u0, v_base + dv, mx, my);
+            float2 m[2][4];
+            exact_rows(g, R, u_lo, u0, v_base + dv, m);
+            sample_rows_checked(g, f, u0, v_base + dv, m);
         }
         return;
     }
@@ -197,10 +201,10 @@ warp_nv12_tile_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
             else band_gmem<true>(g, cp, f, dv0, my_rows, o, valid);
         } else {
             for (int dv = dv0; dv < dv0 + my_rows; dv += 2) {
-                float mx[2][4], my[2][4];
-                row_coords(cp, row_t(g, dv), mx[0], my[0]);
-                row_coords(cp, row_t(g, dv + 1), mx[1], my[1]);
-                sample_rows_checked(g, f, u0, v_base + dv, mx, my);
+                float2 m[2][4];
+                row_coords(cp, row_t(g, dv), m[0]);
+                row_coords(cp, row_t(g, dv + 1), m[1]);
+                sample_rows_checked(g, f, u0, v_base + dv, m);
             }
         }
         return;
@@ -224,42 +228,21 @@ warp_nv12_tile_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
 
     // ---- collapse the polynomial: warp w does column j = w for every lane -------------------------
     {
-        const float4* r4 = reinterpret_cast<const float4*>(rec);
-        float c[2][kNu][kNv];
-#pragma unroll
-        for (int q = 0; q < 12; ++q) {
-            const float4 v = __ldg(r4 + q);
-            float* dst = &c[0][0][0] + 4 * q;
-            dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
-        }
-        const float s = ((float)(4 * lane + w) - 63.5f) * 0.015625f;  // exact
-#pragma unroll
-        for (int co = 0; co < 2; ++co) {
-            float a[kNv];
-#pragma unroll
-            for (int k = 0; k < kNv; ++k) {
-                float acc = c[co][kDegU][k];
-#pragma unroll
-                for (int i = kDegU - 1; i >= 0; --i) acc = __fmaf_rn(acc, s, c[co][i][k]);
-                a[k] = acc;
-            }
-            coefs[(2 * w + co) * 32 + lane] = make_float4(a[0], a[1], a[2], a[3]);
-        }
+        float2 c[kNu][kNv], a[kNv];
+        load_coeffs(rec, c);
+        collapse_column(c, ((float)(4 * lane + w) - 63.5f) * 0.015625f, a);  // s is exact
+        coefs[(2 * w) * 32 + lane] = make_float4(a[0].x, a[0].y, a[1].x, a[1].y);
+        coefs[(2 * w + 1) * 32 + lane] = make_float4(a[2].x, a[2].y, a[3].x, a[3].y);
     }
     __syncthreads();  // column polynomials exchanged; the barrier init is visible to every thread
     ColPoly cp;
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int co = 0; co < 2; ++co) {
-            const float4 v = coefs[(2 * j + co) * 32 + lane];
-            cp.a[co][j][0] = v.x; cp.a[co][j][1] = v.y; cp.a[co][j][2] = v.z; cp.a[co][j][3] = v.w;
-        }
-    {
-        const float4 tail = __ldg(reinterpret_cast<const float4*>(rec) + 12);
-        cp.bx = tail.x;
-        cp.by = tail.y;
+    for (int j = 0; j < 4; ++j) {
+        const float4 lo = coefs[(2 * j) * 32 + lane], hi = coefs[(2 * j + 1) * 32 + lane];
+        cp.a[j][0] = make_float2(lo.x, lo.y); cp.a[j][1] = make_float2(lo.z, lo.w);
+        cp.a[j][2] = make_float2(hi.x, hi.y); cp.a[j][3] = make_float2(hi.z, hi.w);
     }
+    cp.base = load_base(rec);
 
     mbar_wait(mbar, 0);  // the tile has landed
 
