@@ -182,6 +182,32 @@ int vaw_remap_u8(const uint8_t *src, int src_width, int src_height, int src_pitc
                  const float *map_x, const float *map_y, int rows, int cols, int map_pitch,
                  uint8_t *dst, int dst_pitch, const uint8_t border[4], int device, void *stream);
 
+/* ---- device memory for hosts that do not link the CUDA runtime -----------------------------
+ * The reference hands cv::UMat frames around (opencv/FrameSource.hpp:16,22); a host-language
+ * binding (the C++ shim under video_annotator_b200/host, cgo, JNI ...) owns device frames
+ * through these instead.  vaw_memcpy and vaw_sync block until the stream has drained. */
+int vaw_malloc(int device, size_t bytes, void **out);
+int vaw_free(int device, void *ptr);
+int vaw_memcpy(int device, void *dst, const void *src, size_t bytes, int to_device, void *stream);
+int vaw_sync(int device, void *stream);
+
+/* ---- frame-parallel sharding ---------------------------------------------------------
+ * The reference is single device, single thread; once every frame has its rotation the
+ * frames are independent (warp_frame reads only its frame, its rotation and constant
+ * intrinsics: opencv/FrameSourceWarp.cpp:272-314), so a clip shards into contiguous frame
+ * ranges with no exchange between devices.
+ * vaw_shard_range: the range [first, first + count) of part `part` of `n_parts`.
+ * vaw_clip_*: one context, one host thread and one set of streams per device; every device
+ * warps its own range of a host-resident clip through the pinned-staging pipeline of
+ * vaw_warp_batch_host.  `devices` = CUDA ordinals (NULL: 0 .. n_devices-1). */
+int vaw_shard_range(int n_frames, int n_parts, int part, int *first, int *count);
+typedef struct vaw_clip vaw_clip;
+int vaw_clip_create(const vaw_params *params, int n_devices, const int *devices, vaw_clip **out);
+void vaw_clip_destroy(vaw_clip *clip);
+int vaw_clip_warp_host(vaw_clip *clip, const uint8_t *src_host, uint8_t *dst_host,
+                       const double *rotations_host, int n_frames);
+const char *vaw_clip_last_error(const vaw_clip *clip);
+
 /* ---- synthetic frames (decode is out of scope; BASELINE.json north_star) ------------
  * Fill n_frames NV12 frames in device memory with the integer test pattern
  * (frame index first_index + i). */
@@ -197,6 +223,12 @@ int vaw_synth_nv12(uint8_t *dst, int width, int height, int pitch, size_t frame_
  * __fdiv_rn / __fsqrt_rn / the k = atan(r)/r step on random operands in the certified
  * ranges; mismatches[4] = {rcp, div, sqrt, k}. */
 int vaw_set_option(vaw_ctx *ctx, const char *name, int value);
+/* vaw_set_option(ctx, "time_kernels", 1) makes every NV12 launch record CUDA events on its
+ * stream around the piece-table builder and the warp kernel (a ring of the last 512 launches);
+ * vaw_kernel_times returns the most recent launches' durations in milliseconds, oldest first
+ * (it waits for them).  This is what bench.py's roofline line is computed from. */
+int vaw_kernel_times(vaw_ctx *ctx, int max_launches, float *builder_ms, float *warp_ms, int *n_out);
+
 /* Variant POLY: how the 128x32-pixel pieces of the output classify for `rotation`:
  * counts = {pieces, with a certified polynomial, of those fully inside the source (sampler
  * without border tests), of those fully outside (pure border fill)}.  All zero for GATHER. */

@@ -1,0 +1,125 @@
+// CPU test of the FrameSourceWarp state machine (video_annotator_b200/host), no GPU needed:
+// warp_frame is overridden with a pass-through that records the rotation it was given.
+// Behaviours checked are the reference's (opencv/FrameSourceWarp.cpp:397-480).
+#include <cmath>
+#include <cstdio>
+#include <vector>
+
+#include "../../include/vaw.h"
+#include "../../video_annotator_b200/host/FrameSourceWarp.hpp"
+
+static int g_checks = 0, g_failed = 0;
+#define CHECK(cond)                                                        \
+    do {                                                                   \
+        ++g_checks;                                                        \
+        if (!(cond)) { ++g_failed; std::printf("FAILED %s:%d %s\n", __FILE__, __LINE__, #cond); } \
+    } while (0)
+
+struct FakeSource : FrameSource {
+    int n, pulls = 0;
+    explicit FakeSource(int n_) : n(n_) {}
+    Frame make(long i)
+    {
+        if (i >= n) throw EOF;
+        auto f = std::make_shared<DeviceFrame>();
+        f->width = 1920; f->height = 1080; f->pitch = 1920; f->format = VAW_FORMAT_NV12; f->index = i;
+        return f;
+    }
+    Frame pull_frame() override { return make(pulls++); }
+    Frame peek_frame() override { return make(pulls); }
+};
+
+struct SpinSource : RotationSource {  // constant angular rate about z
+    double step;
+    explicit SpinSource(double deg) : step(deg * 3.14159265358979323846 / 180.0) {}
+    bool rotation_since_last_frame(long, Mat33& out) override
+    {
+        out = Mat33{{std::cos(step), -std::sin(step), 0, std::sin(step), std::cos(step), 0, 0, 0, 1}};
+        return true;
+    }
+};
+
+struct RecordingWarp : FrameSourceWarp {
+    using FrameSourceWarp::FrameSourceWarp;
+    std::vector<Mat33> rotations;
+    std::vector<long> indices;
+  protected:
+    Frame warp_frame(Frame input, const Mat33& rotation) override
+    {
+        rotations.push_back(rotation);
+        indices.push_back(input->index);
+        return input;
+    }
+};
+
+static double dist_to_identity(const Mat33& r)
+{
+    const Mat33 e = Mat33::eye();
+    double d = 0;
+    for (int i = 0; i < 9; ++i) d = std::fmax(d, std::fabs(r.m[i] - e.m[i]));
+    return d;
+}
+
+int main()
+{
+    {  // algebra
+        const Mat33 a{{2, 1, 0, 0, 3, 1, 1, 0, 4}};
+        CHECK(dist_to_identity(a * a.inv()) < 1e-14);
+        RotationFilter f(30);
+        const Mat33 r{{0, -1, 0, 1, 0, 0, 0, 0, 1}};
+        f.add(r);
+        const Mat33 s = f.filter();
+        CHECK(dist_to_identity(s * r.t()) < 1e-12);      // a constant sequence is its own smoothing
+        CHECK(dist_to_identity(s * s.t()) < 1e-12);      // result is orthonormal
+    }
+    {  // no rotation: frame 0 dropped, order kept, look-ahead latency, EOF drain
+        const int n = 10, radius = 3;
+        auto src = std::make_shared<FakeSource>(n);
+        RecordingWarp w(src, GOPRO_H4B_WIDE169_MEASURED, 1, false, 1, radius, INTER_LINEAR, nullptr, false);
+        CHECK(w.output_camera().width == 1759 && w.output_camera().height == 998);
+        CHECK(w.output_width() == 1758 && w.output_height() == 998);                 // NV12: even
+        Frame first = w.pull_frame();
+        CHECK(first->index == 1);                       // frame 0 is never emitted (:403-406)
+        CHECK(src->pulls == radius + 2);                // frame 0 + radius+1 buffered frames (:453)
+        int emitted = 1;
+        bool eof = false;
+        for (int i = 0; i < 50 && !eof; ++i) {
+            try { Frame f = w.pull_frame(); CHECK(f->index == 1 + emitted); ++emitted; }
+            catch (int err) { CHECK(err == EOF); eof = true; }
+        }
+        CHECK(eof && emitted == n - 1);
+        for (const Mat33& r : w.rotations) CHECK(dist_to_identity(r) < 1e-12);
+        bool again = false;
+        try { w.pull_frame(); } catch (int err) { again = err == EOF; }
+        CHECK(again);                                   // stays at EOF
+    }
+    {  // steady spin: the smoothed path equals the measured one mid-stream -> correction ~ identity
+        const int n = 40, radius = 5;
+        auto src = std::make_shared<FakeSource>(n);
+        RecordingWarp w(src, GOPRO_H4B_WIDE169_MEASURED, 1, false, 1, radius, INTER_LINEAR,
+                        std::make_shared<SpinSource>(1.0), false);
+        try { while (true) w.pull_frame(); } catch (int err) { CHECK(err == EOF); }
+        CHECK((int)w.rotations.size() == n - 1);
+        for (size_t i = 2 * radius; i + radius + 1 < w.rotations.size(); ++i) CHECK(dist_to_identity(w.rotations[i]) < 2e-4);
+        // at the start the filter still sees the "camera was still" padding: a real correction
+        CHECK(dist_to_identity(w.rotations[0]) > 1e-3);
+        for (const Mat33& r : w.rotations) CHECK(std::fabs((r * r.t()).m[0] - 1.0) < 1e-9);
+    }
+    {  // peek_frame advances like pull_frame (:478-480)
+        auto src = std::make_shared<FakeSource>(6);
+        RecordingWarp w(src, GOPRO_H4B_WIDE169_MEASURED, 1, false, 1, 1, INTER_LINEAR, nullptr, false);
+        CHECK(w.peek_frame()->index == 1);
+        CHECK(w.pull_frame()->index == 2);
+    }
+    {  // camera producers agree with the C-ABI
+        const Camera c = get_preset_camera(GOPRO_H4B_WIDE43_MEASURED, 1920, 1440);
+        const Camera o = get_output_camera(c, 0.5, false, 1);          // the DisplayImage.cpp:55 setting
+        CHECK(o.width == 988 && o.height == 744);
+        CHECK(std::fabs(o.matrix.m[0] - 187.299) < 1e-3);
+        bool threw = false;
+        try { get_preset_camera((CameraPreset)42, 10, 10); } catch (int err) { threw = err == VAW_ERR_INVALID; }
+        CHECK(threw);
+    }
+    std::printf("%s: %d checks, %d failed\n", g_failed ? "FAILED" : "OK", g_checks, g_failed);
+    return g_failed ? 1 : 0;
+}

@@ -11,14 +11,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvaw.so")
 
-SOURCES = ["vaw_kernels.cu", "vaw_pieces.cu", "vaw_poly.cu", "vaw_tile.cu", "vaw_api.cu", "vaw_camera.cpp"]
+SOURCES = ["vaw_kernels.cu", "vaw_pieces.cu", "vaw_poly.cu", "vaw_tile.cu", "vaw_api.cu", "vaw_camera.cpp", "vaw_clip.cpp"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
     # the coordinate code is written with explicit _rn intrinsics; this is belt and braces
     "-fmad=false",
-    "-Xcompiler", "-fPIC,-O2,-Wall",
+    "-Xcompiler", "-fPIC,-O2,-Wall,-pthread",
     "--shared", "-cudart", "static",
 ]
 
@@ -54,6 +54,22 @@ def build(force=False, verbose=False):
         cmd.insert(2, "-v")
     subprocess.check_call(cmd, env=env)
     return LIB
+
+
+HOST = os.path.join(HERE, "host")
+DEMO = os.path.join(HOST, "vaw_demo")
+
+
+def build_host_shim(force=False):
+    """g++ build of the C++ FrameSource / FrameSourceWarp shim + demo (pure C++ over the C-ABI:
+    no CUDA headers, links libvaw.so only).  -Werror like the reference's meson.build:11."""
+    srcs = [os.path.join(HOST, "vaw_demo.cpp"), os.path.join(HOST, "FrameSourceWarp.cpp")]
+    deps = srcs + [os.path.join(HOST, "FrameSourceWarp.hpp"), os.path.join(HOST, "FrameSource.hpp"), LIB]
+    if not force and os.path.exists(DEMO) and all(os.path.getmtime(d) <= os.path.getmtime(DEMO) for d in deps):
+        return DEMO
+    subprocess.check_call([shutil.which("g++") or "g++", "-std=c++14", "-O2", "-Wall", "-Werror", "-o", DEMO, *srcs,
+                           "-L" + HERE, "-l:libvaw.so", "-Wl,-rpath," + HERE, "-pthread"])
+    return DEMO
 
 
 if __name__ == "__main__":

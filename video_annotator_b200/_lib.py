@@ -53,6 +53,16 @@ SIGNATURES = {
                                C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, u8p, C.c_int, C.c_void_p]),
     "vaw_synth_nv12": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int,
                                  C.c_uint32, C.c_int, C.c_int, C.c_void_p]),
+    "vaw_malloc": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "vaw_free": (C.c_int, [C.c_int, C.c_void_p]),
+    "vaw_memcpy": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "vaw_sync": (C.c_int, [C.c_int, C.c_void_p]),
+    "vaw_kernel_times": (C.c_int, [C.c_void_p, C.c_int, f32p, f32p, C.POINTER(C.c_int)]),
+    "vaw_shard_range": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "vaw_clip_create": (C.c_int, [C.POINTER(VawParams), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p)]),
+    "vaw_clip_destroy": (None, [C.c_void_p]),
+    "vaw_clip_warp_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, f64p, C.c_int]),
+    "vaw_clip_last_error": (C.c_char_p, [C.c_void_p]),
     "vaw_piece_stats": (C.c_int, [C.c_void_p, f64p, C.POINTER(C.c_uint32), C.c_void_p]),
     "vaw_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "vaw_selftest_math": (C.c_int, [C.c_int, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint64)]),

@@ -43,9 +43,13 @@ class Workload:
         + output bytes + the 36-byte rotation.  No map bytes: the map is never materialised."""
         return self.src_frame_bytes + self.out_frame_bytes + 36
 
-    def rotations(self, n=None, first=0):
+    def rotations(self, n=None, first=0, total=None):
+        """Warp rotations of frames [first, first + n) of a clip of `total` frames (default: the clip
+        ends at first + n).  A rank's slice of a longer clip must pass the clip's `total`, so that
+        the smoothing window near the end of its range sees the following frames."""
         n = self.n_frames if n is None else n
-        return make_rotations(first + n, self.sigma_deg)[first:]
+        total = first + n if total is None else total
+        return make_rotations(total, self.sigma_deg)[first:first + n]
 
 
 def _rodrigues(v):

@@ -62,6 +62,11 @@ struct vaw_ctx {
     struct MapEntry { const void* src = nullptr; int pitch = 0; size_t stride = 0; int frames = 0; vaw::TileMaps maps{}; };
     MapEntry map_cache[4];
     int map_next = 0;
+    // option "time_kernels": CUDA-event stamps around the kernels of every launch (bench.py's roofline)
+    static constexpr int kTimeRing = 512;
+    bool time_kernels = false;
+    cudaEvent_t* tev = nullptr;  // 3 per launch: start, after the table builder, after the warp kernel
+    uint64_t timed_launches = 0;
     // host path
     Stage stage[kStages];
     int chunk_frames = 0;
@@ -254,9 +259,12 @@ int launch(vaw_ctx* ctx, const uint8_t* src, int src_pitch, size_t src_stride, u
                 if (rc) return rc;
                 tab = ctx->table;
             }
+            cudaEvent_t* tev = ctx->time_kernels ? ctx->tev + 3 * (ctx->timed_launches % vaw_ctx::kTimeRing) : nullptr;
+            if (tev) cudaEventRecord(tev[0], st);
             e = vaw::launch_build_pieces(ctx->gd, ctx->basis, bb.rots, rot0 ? rot0->r : nullptr, bb.n_frames, tab, st);
             if (e != cudaSuccess) return cuda_fail(ctx, e, "piece table launch");
             ctx->launches++;
+            if (tev) cudaEventRecord(tev[1], st);
             if (tiled)
                 e = vaw::launch_warp_nv12_tile(g, bb, tab, tile_maps(ctx, bb.src, src_pitch, src_stride, bb.n_frames), st);
             else
@@ -268,6 +276,7 @@ int launch(vaw_ctx* ctx, const uint8_t* src, int src_pitch, size_t src_stride, u
             }
             if (e != cudaSuccess) return cuda_fail(ctx, e, "warp kernel launch");
             ctx->launches++;
+            if (tev) { cudaEventRecord(tev[2], st); ctx->timed_launches++; }
             continue;
         }
         switch (ctx->p.format) {
@@ -449,6 +458,10 @@ void vaw_destroy(vaw_ctx* ctx)
     cudaFree(ctx->table);
     cudaFree(ctx->dump_table);
     if (ctx->table_free) cudaEventDestroy(ctx->table_free);
+    if (ctx->tev) {
+        for (int i = 0; i < 3 * vaw_ctx::kTimeRing; ++i) cudaEventDestroy(ctx->tev[i]);
+        delete[] ctx->tev;
+    }
     cudaFree(ctx->xtab);
     cudaFree(ctx->ytab);
     delete ctx;
@@ -458,6 +471,17 @@ int vaw_set_option(vaw_ctx* ctx, const char* name, int value)
 {
     if (!ctx || !name) return VAW_ERR_INVALID;
     if (!std::strcmp(name, "force_exact")) { ctx->g.force_exact = value ? 1 : 0; return VAW_OK; }
+    if (!std::strcmp(name, "time_kernels")) {
+        DeviceGuard dg(ctx->device);
+        if (value && !ctx->tev) {
+            ctx->tev = new (std::nothrow) cudaEvent_t[3 * vaw_ctx::kTimeRing];
+            if (!ctx->tev) return fail(ctx, VAW_ERR_NOMEM, "out of host memory");
+            for (int i = 0; i < 3 * vaw_ctx::kTimeRing; ++i) VAW_CUDA(ctx, cudaEventCreate(&ctx->tev[i]));
+        }
+        ctx->time_kernels = value != 0;
+        ctx->timed_launches = 0;
+        return VAW_OK;
+    }
     return fail(ctx, VAW_ERR_INVALID, std::string("unknown option ") + name);
 }
 
@@ -578,6 +602,69 @@ int vaw_dump_coords(vaw_ctx* ctx, const double rotation[9], int plane, float* ma
     }
     if (e != cudaSuccess) return cuda_fail(ctx, e, "dump_coords launch");
     ctx->launches++;
+    return VAW_OK;
+}
+
+int vaw_malloc(int device, size_t bytes, void** out)
+{
+    if (!out) return VAW_ERR_INVALID;
+    *out = nullptr;
+    DeviceGuard dg(device);
+    cudaError_t e = cudaMalloc(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) return cuda_fail(nullptr, e, "vaw_malloc");
+    return VAW_OK;
+}
+
+int vaw_free(int device, void* ptr)
+{
+    DeviceGuard dg(device);
+    cudaError_t e = cudaFree(ptr);
+    return e == cudaSuccess ? VAW_OK : cuda_fail(nullptr, e, "vaw_free");
+}
+
+int vaw_memcpy(int device, void* dst, const void* src, size_t bytes, int to_device, void* stream)
+{
+    if (!dst || !src) return VAW_ERR_INVALID;
+    DeviceGuard dg(device);
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost,
+                                    (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    return e == cudaSuccess ? VAW_OK : cuda_fail(nullptr, e, "vaw_memcpy");
+}
+
+int vaw_sync(int device, void* stream)
+{
+    DeviceGuard dg(device);
+    cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+    return e == cudaSuccess ? VAW_OK : cuda_fail(nullptr, e, "vaw_sync");
+}
+
+int vaw_kernel_times(vaw_ctx* ctx, int max_launches, float* builder_ms, float* warp_ms, int* n_out)
+{
+    if (!ctx) return VAW_ERR_INVALID;
+    if (!builder_ms || !warp_ms || !n_out || max_launches < 0) return fail(ctx, VAW_ERR_INVALID, "null argument");
+    *n_out = 0;
+    if (!ctx->tev) return VAW_OK;
+    DeviceGuard dg(ctx->device);
+    const uint64_t have = ctx->timed_launches < (uint64_t)vaw_ctx::kTimeRing ? ctx->timed_launches : vaw_ctx::kTimeRing;
+    const uint64_t n = have < (uint64_t)max_launches ? have : (uint64_t)max_launches;
+    for (uint64_t i = 0; i < n; ++i) {  // the most recent n launches, oldest first
+        const cudaEvent_t* e = ctx->tev + 3 * ((ctx->timed_launches - n + i) % vaw_ctx::kTimeRing);
+        VAW_CUDA(ctx, cudaEventSynchronize(e[2]));
+        VAW_CUDA(ctx, cudaEventElapsedTime(&builder_ms[i], e[0], e[1]));
+        VAW_CUDA(ctx, cudaEventElapsedTime(&warp_ms[i], e[1], e[2]));
+    }
+    *n_out = (int)n;
+    return VAW_OK;
+}
+
+int vaw_shard_range(int n_frames, int n_parts, int part, int* first, int* count)
+{
+    if (n_frames < 0 || n_parts < 1 || part < 0 || part >= n_parts || !first || !count) return VAW_ERR_INVALID;
+    // contiguous ranges, sizes differing by at most one, earlier parts take the remainder
+    const int base = n_frames / n_parts, rem = n_frames % n_parts;
+    *first = part * base + (part < rem ? part : rem);
+    *count = base + (part < rem ? 1 : 0);
     return VAW_OK;
 }
 

@@ -1,0 +1,139 @@
+// FrameSourceWarp.hpp -- drop-in for the reference's stabilise-and-reproject stage.
+//
+// Mirrors /root/reference/opencv/FrameSourceWarp.hpp:14-94: CameraPreset, CameraModel,
+// Camera, and class FrameSourceWarp with the same constructor parameter list and the same
+// pull_frame / peek_frame behaviour, quirks included (frame 0 is never emitted,
+// FrameSourceWarp.cpp:403-406; look-ahead of smooth_radius frames, :453; EOF padding and
+// draining, :456-467; peek_frame advances like pull_frame, :478-480).
+//
+// What is replaced: warp_frame (:272-314) -- the createMap OpenCL kernel plus cv::remap --
+// is ONE call into libvaw.so (vaw_warp), hand-written CUDA for sm_100a; no map buffers exist.
+// What is out of scope: the optical-flow measurement of the inter-frame rotation
+// (:228-270, :316-375).  Its result enters through the RotationSource interface
+// instead, and everything downstream of the measurement (accumulation :441-442, the
+// Savitzky-Golay look-ahead filter :212/:444/:471, the correction :472-475) is kept.
+#ifndef VAW_FRAME_SOURCE_WARP_HPP_
+#define VAW_FRAME_SOURCE_WARP_HPP_
+
+#include <deque>
+#include <memory>
+#include <queue>
+#include <vector>
+
+#include "FrameSource.hpp"
+
+enum CameraPreset {
+    GOPRO_H4B_WIDE43_PUBLISHED,
+    GOPRO_H4B_WIDE43_MEASURED,
+    GOPRO_H4B_WIDE43_MEASURED_STABILISATION,
+    GOPRO_H4B_WIDE169_PUBLISHED,
+    GOPRO_H4B_WIDE169_MEASURED,
+    GOPRO_H4B_WIDE169_MEASURED_STABILISATION
+};
+
+enum CameraModel { RECTILINEAR, FISHEYE };
+
+enum InterpolationFlags { INTER_NEAREST = 0, INTER_LINEAR = 1, INTER_CUBIC = 2 };  // cv::InterpolationFlags values
+
+struct Mat33 {  // stands in for cv::Mat 3x3 CV_64F / cv::Matx33d, row-major
+    double m[9];
+    static Mat33 eye();
+    Mat33 operator*(const Mat33& o) const;
+    Mat33 t() const;    // transpose
+    Mat33 inv() const;  // general 3x3 inverse (the reference calls cv::Mat::inv, :472, :475)
+};
+
+class Camera {
+  public:
+    CameraModel model;
+    Mat33 matrix;
+    double distortion_coefficients[4];
+    int width, height;  // cv::Size size
+};
+
+Camera get_preset_camera(CameraPreset preset, int width, int height);                     // :27-86
+Camera get_output_camera(const Camera& input, double scale, bool crop_borders, double zoom);  // :88-165
+
+/**
+ * The measured rotation of the camera between the previous frame and this one -- what
+ * guess_camera_rotation (:316-375) returns and consume_frame left-multiplies (:441-442).
+ * One call per consumed frame after the first; return false to reuse the previous
+ * inter-frame rotation (the reference does that with fewer than 40 RANSAC inliers, :431-438).
+ */
+class RotationSource {
+  public:
+    virtual bool rotation_since_last_frame(long frame_index, Mat33& out) = 0;
+    virtual ~RotationSource() = default;
+};
+
+/**
+ * Savitzky-Golay smoothing of a rotation sequence, evaluated at the centre of a window of
+ * 2*radius+1 samples (the reference builds gram_sg::RotationFilter from
+ * SavitzkyGolayFilterConfig(radius, 0, 2, 0), :212): weights applied element-wise to the
+ * matrices, result projected back to SO(3).  The library is not vendored in the reference
+ * (meson.build:37, no version pin): parity of this stage is unpinned.
+ */
+class RotationFilter {
+    int m_radius;
+    std::vector<double> m_weights;
+    std::deque<Mat33> m_window;
+  public:
+    explicit RotationFilter(int radius);
+    void add(const Mat33& rotation);
+    Mat33 filter() const;
+};
+
+/**
+ * FrameSourceWarp is a video processor that accepts a stream of input video frames
+ * and metadata and applies reprojection and stabilisation on them
+ */
+class FrameSourceWarp : public FrameSource {
+    std::shared_ptr<FrameSource> m_source;
+    std::shared_ptr<RotationSource> m_rotation_source;
+
+    Camera m_input_camera;
+    Camera m_output_camera;
+    struct vaw_ctx* m_ctx = nullptr;  // replaces m_map_x, m_map_y, m_remap_kernel (:47-49)
+    int m_device = 0, m_format = 0;
+
+    long m_frame_index = 0;
+    Mat33 m_measured_rotation;
+    Mat33 m_last_frame_rotation;
+
+    unsigned int m_smooth_radius;
+    InterpolationFlags m_interpolation;
+
+    RotationFilter m_rotation_filter;
+    std::queue<Frame> m_buffered_frames;
+    std::queue<Mat33> m_buffered_rotations;
+
+    void consume_frame(Frame input_frame);
+
+  protected:
+    // warp_frame(input, rotation), :272-314.  Virtual so that the state machine can be tested
+    // without a GPU; the real one calls vaw_warp and synchronises before returning.
+    virtual Frame warp_frame(Frame input, const Mat33& rotation);
+
+  public:
+    FrameSourceWarp(
+      std::shared_ptr<FrameSource> source,
+      CameraPreset input_camera,
+      double scale = 1,
+      bool crop_borders = false,
+      double zoom = 1,
+      int smooth_radius = 30,
+      InterpolationFlags interpolation = INTER_LINEAR,
+      std::shared_ptr<RotationSource> rotation_source = nullptr,  // nullptr: the camera does not rotate
+      bool create_device_context = true                           // false: CPU-only tests of the state machine
+    );
+    ~FrameSourceWarp() override;
+    Frame pull_frame() override;
+    Frame peek_frame() override;
+
+    const Camera& input_camera() const { return m_input_camera; }
+    const Camera& output_camera() const { return m_output_camera; }
+    int output_width() const;   // even for NV12
+    int output_height() const;
+};
+
+#endif  // VAW_FRAME_SOURCE_WARP_HPP_

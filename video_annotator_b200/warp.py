@@ -189,6 +189,15 @@ class WarpContext:
                                          _stream_handle(stream)), self._h)
         return mx, my
 
+    def kernel_times(self, max_launches=512):
+        """(builder_ms, warp_ms) numpy arrays of the most recent launches (option time_kernels)."""
+        b = np.zeros(max_launches, np.float32)
+        w = np.zeros(max_launches, np.float32)
+        n = C.c_int(0)
+        _check(self._lib.vaw_kernel_times(self._h, max_launches, b.ctypes.data_as(_lib.f32p),
+                                          w.ctypes.data_as(_lib.f32p), C.byref(n)), self._h)
+        return b[:n.value], w[:n.value]
+
     def piece_stats(self, rotation, stream=None):
         """Variant POLY: {'pieces', 'poly', 'interior', 'outside'} counts for this rotation."""
         out = (C.c_uint32 * 4)()
@@ -199,6 +208,47 @@ class WarpContext:
     def close(self):
         if getattr(self, "_h", None):
             self._lib.vaw_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def shard_range(n_frames, n_parts, part):
+    """Contiguous frame range (first, count) of one rank / device (vaw_shard_range)."""
+    first, count = C.c_int(0), C.c_int(0)
+    _check(_lib.load().vaw_shard_range(n_frames, n_parts, part, C.byref(first), C.byref(count)))
+    return first.value, count.value
+
+
+class ClipWarper:
+    """Frame-parallel warp of a host-resident clip over several GPUs of one box (vaw_clip_*)."""
+
+    def __init__(self, ctx_params, devices):
+        lib = _lib.load()
+        h = C.c_void_p()
+        arr = (C.c_int * len(devices))(*devices)
+        rc = lib.vaw_clip_create(C.byref(ctx_params), len(devices), arr, C.byref(h))
+        if rc != 0:
+            raise VawError(rc, (lib.vaw_clip_last_error(None) or b"").decode())
+        self._h, self._lib = h, lib
+
+    def warp_host(self, src_host, dst_host, rotations):
+        r, rp = _rot_arg(rotations)
+
+        def ptr(a):
+            return a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data
+        rc = self._lib.vaw_clip_warp_host(self._h, ptr(src_host), ptr(dst_host), rp, r.size // 9)
+        if rc != 0:
+            raise VawError(rc, (self._lib.vaw_clip_last_error(self._h) or b"").decode())
+        return dst_host
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.vaw_clip_destroy(self._h)
             self._h = None
 
     def __del__(self):
