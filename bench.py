@@ -256,6 +256,7 @@ def run_ours(args):
     rdev = torch.empty(n * 9, dtype=torch.float32, device=dev)
     ctx.upload_rotations(rots, rdev)
     torch.cuda.synchronize()
+    pieces = ctx.piece_stats(rots[n // 2])
 
     def barrier():
         torch.cuda.synchronize()
@@ -335,7 +336,7 @@ def run_ours(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                 "config": config_dict(wl, args, world, {
                     "l2": f"inputs {n * wl.src_frame_bytes >> 20} MiB per step > {L2_BYTES >> 20} MiB L2 (no flush needed)",
-                    "variant": args.variant}),
+                    "variant": args.variant, "pieces_128x32": pieces}),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": recorded_traffic(wl.name, n),
                              "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,

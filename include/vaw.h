@@ -230,9 +230,11 @@ int vaw_set_option(vaw_ctx *ctx, const char *name, int value);
 int vaw_kernel_times(vaw_ctx *ctx, int max_launches, float *builder_ms, float *warp_ms, int *n_out);
 
 /* Variant POLY: how the 128x32-pixel pieces of the output classify for `rotation`:
- * counts = {pieces, with a certified polynomial, of those fully inside the source (sampler
- * without border tests), of those fully outside (pure border fill)}.  All zero for GATHER. */
-int vaw_piece_stats(vaw_ctx *ctx, const double rotation[9], uint32_t counts[4], void *stream);
+ * counts = {pieces, with a certified polynomial, of those fully inside the source, of those
+ * fully outside (pure border fill), largest shared-memory tile a piece needs (bytes), the
+ * context's tile capacity (bytes), pieces that exceed it (they gather from global memory), 0}.
+ * All zero for GATHER. */
+int vaw_piece_stats(vaw_ctx *ctx, const double rotation[9], uint32_t counts[8], void *stream);
 int vaw_selftest_math(int device, uint32_t seed, uint64_t n_per_thread, uint64_t mismatches[4]);
 
 #ifdef __cplusplus

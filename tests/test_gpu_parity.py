@@ -374,6 +374,13 @@ def test_piece_classification_c3(V):
     assert st["pieces"] == 30 * 68
     assert st["poly"] >= st["pieces"] - 4
     assert st["interior"] > 0.5 * st["pieces"] and st["outside"] > 0.2 * st["pieces"]
+    assert st["over_cap"] == 0 and st["max_tile_bytes"] <= st["tile_cap"]   # every piece is staged by TMA
+    ctx.close()
+    w = configs.workload("C5")                                              # 2.55x magnification: bigger tiles
+    ctx = V.WarpContext(w.input_camera, w.output_camera, out_size=w.out_size)
+    st = ctx.piece_stats(w.rotations(1, first=130)[0])
+    _record("piece_stats_C5", st)
+    assert st["over_cap"] <= 0.02 * st["pieces"]
     ctx.close()
 
 
@@ -420,6 +427,31 @@ def test_host_buffer_path_equals_device_path(V, oracle):
     out_pin = torch.zeros(want.shape, dtype=torch.uint8).pin_memory()
     ctx.warp_batch_host(src_pin, out_pin, rots)
     assert np.array_equal(out_pin.numpy(), want)
+    ctx.close()
+
+
+def test_clip_scheduler_frame_parallel(V, oracle):
+    """vaw_clip_*: contiguous frame ranges on several contexts / host threads (two contexts on
+    the one GPU here, two GPUs under `gpurun --gpus 2`) equal the single-context result."""
+    import torch
+    from video_annotator_b200 import configs
+    w = configs.workload("C1")
+    n = 11
+    rots = w.rotations(n, first=20, total=60) if w.sigma_deg else configs.make_rotations(60, 0.5)[20:20 + n]
+    ctx = V.WarpContext(w.input_camera, w.output_camera, out_size=w.out_size)
+    sw, sh = w.src_size
+    src = torch.empty((n,) + ctx.frame_shape("src"), dtype=torch.uint8, device="cuda")
+    V.synth_nv12(src, sw, sh, n, white_noise=True)
+    src_np = src.cpu().numpy()
+    want = np.zeros((n,) + ctx.frame_shape("dst"), np.uint8)
+    ctx.warp_batch_host(src_np, want, rots)
+    ndev = torch.cuda.device_count()
+    devices = [0, 1 % ndev, 0]                       # three shards: 4 + 4 + 3 frames
+    clip = V.ClipWarper(ctx.params, devices)
+    got = np.zeros_like(want)
+    clip.warp_host(src_np, got, rots)
+    assert np.array_equal(got, want)
+    clip.close()
     ctx.close()
 
 

@@ -62,6 +62,7 @@ struct vaw_ctx {
     struct MapEntry { const void* src = nullptr; int pitch = 0; size_t stride = 0; int frames = 0; vaw::TileMaps maps{}; };
     MapEntry map_cache[4];
     int map_next = 0;
+    int tile_cap = 32 << 10;  // chosen at creation from the pieces' source boxes
     // option "time_kernels": CUDA-event stamps around the kernels of every launch (bench.py's roofline)
     static constexpr int kTimeRing = 512;
     bool time_kernels = false;
@@ -208,6 +209,7 @@ const vaw::TileMaps& tile_maps(vaw_ctx* ctx, const uint8_t* src, int pitch, size
     ctx->map_next = (ctx->map_next + 1) % 4;
     e.src = src; e.pitch = pitch; e.stride = stride; e.frames = frames;
     e.maps.enabled = 0;
+    e.maps.tile_cap = ctx->tile_cap;
     const int rows_total = ctx->p.src_height + ctx->p.src_height / 2;
     EncodeTiledFn enc = encode_tiled();
     const bool ok = enc && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (pitch & 15) == 0 && (stride & 15) == 0 &&
@@ -435,6 +437,29 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
         ctx->pieces_per_frame = (size_t)vaw::pieces_x(g.out_w) * vaw::pieces_y(g.out_h, ph);
         e = cudaEventCreateWithFlags(&ctx->table_free, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaMalloc(&ctx->dump_table, ctx->pieces_per_frame * sizeof(vaw::PieceRec));
+        if (e == cudaSuccess && ctx->variant == VAW_VARIANT_TILED && ph == vaw::kPieceHMax) {
+            // size the per-CTA tile from the source boxes of the unrotated geometry, +20 % for the
+            // tilt a few degrees of rotation add; more shared memory per CTA = fewer resident CTAs
+            const float eye[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+            e = vaw::launch_build_pieces(ctx->gd, ctx->basis, nullptr, eye, 1, ctx->dump_table, nullptr);
+            std::string host(ctx->pieces_per_frame * sizeof(vaw::PieceRec), '\0');
+            if (e == cudaSuccess) e = cudaMemcpy(&host[0], ctx->dump_table, host.size(), cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess) {
+                const vaw::PieceRec* rec = reinterpret_cast<const vaw::PieceRec*>(host.data());
+                long long need = 0;
+                for (size_t i = 0; i < ctx->pieces_per_frame; ++i) {
+                    const int nb = vaw::tile_need_bytes(rec[i]);
+                    if (nb != 0x7fffffff && nb > need) need = nb;
+                }
+                long long cap = (need * 12 / 10 + 1023) & ~1023LL;
+                // 6 CTAs per SM fit when tile + bookkeeping <= 227 KB / 6: do not give that up for the margin
+                const long long six = ((227 << 10) / 6 - vaw::tile_smem_bytes(0) - 1024) & ~1023LL;
+                if (need <= six && cap > six) cap = six;
+                if (cap < vaw::kTileCapMin) cap = vaw::kTileCapMin;
+                if (cap > vaw::kTileCapMax) cap = vaw::kTileCapMax;
+                ctx->tile_cap = (int)cap;
+            }
+        }
         if (e != cudaSuccess) {
             int rc = cuda_fail(nullptr, e, "vaw_create (piece tables)");
             cudaFree(ctx->xtab); cudaFree(ctx->ytab);
@@ -668,11 +693,11 @@ int vaw_shard_range(int n_frames, int n_parts, int part, int* first, int* count)
     return VAW_OK;
 }
 
-int vaw_piece_stats(vaw_ctx* ctx, const double rotation[9], uint32_t counts[4], void* stream)
+int vaw_piece_stats(vaw_ctx* ctx, const double rotation[9], uint32_t counts[8], void* stream)
 {
     if (!ctx) return VAW_ERR_INVALID;
     if (!rotation || !counts) return fail(ctx, VAW_ERR_INVALID, "null argument");
-    counts[0] = counts[1] = counts[2] = counts[3] = 0;
+    for (int i = 0; i < 8; ++i) counts[i] = 0;
     if (ctx->variant == VAW_VARIANT_GATHER) return VAW_OK;
     DeviceGuard dg(ctx->device);
     const vaw::Rot R = rot_from_double(rotation);
@@ -688,7 +713,11 @@ int vaw_piece_stats(vaw_ctx* ctx, const double rotation[9], uint32_t counts[4], 
         if (rec[i].flags & vaw::kPiecePoly) counts[1]++;
         if (rec[i].flags & vaw::kPieceInterior) counts[2]++;
         if (rec[i].flags & vaw::kPieceOutside) counts[3]++;
+        const int nb = vaw::tile_need_bytes(rec[i]);
+        if (nb > 0 && (nb > ctx->tile_cap)) counts[6]++;
+        if (nb != 0x7fffffff && (uint32_t)nb > counts[4]) counts[4] = (uint32_t)nb;
     }
+    counts[5] = (uint32_t)ctx->tile_cap;
     return VAW_OK;
 }
 

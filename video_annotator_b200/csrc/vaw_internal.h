@@ -32,12 +32,18 @@ cudaError_t launch_warp_nv12_poly(const Geom& g, const FrameBatch& b, const Piec
 // Variant TILED (vaw_tile.cu): tensor maps over the NV12 clip, viewed as a 3-D tensor of 4-byte
 // elements (pitch/4 x 3H/2 rows x frames), one per tile row pitch (box = pitch/4 x 8 rows).
 constexpr int kTileMinPitch = 128, kTileMaxPitch = 448, kTilePitchStep = 32;
+constexpr int kTileCapMin = 16 << 10, kTileCapMax = 160 << 10;  // per-CTA tile bytes (chosen per geometry)
 constexpr int kTileWidths = (kTileMaxPitch - kTileMinPitch) / kTilePitchStep + 1;
 struct alignas(64) TileMaps {
     CUtensorMap m[kTileWidths];
-    int enabled;  // 0: no maps (layout not TMA-compatible) -> every piece gathers from global memory
-    int pad[15];
+    int enabled;   // 0: no maps (layout not TMA-compatible) -> every piece gathers from global memory
+    int tile_cap;  // bytes of shared memory for the luma + chroma tile of one CTA
+    int pad[14];
 };
+// bytes of tile a piece needs for its source box (what the kernel computes), 0 if it has none
+int tile_need_bytes(const PieceRec& rec);
+// dynamic shared memory of the tile kernel for a given tile capacity
+int tile_smem_bytes(int tile_cap);
 // Needs piece_h == 32.
 cudaError_t launch_warp_nv12_tile(const Geom& g, const FrameBatch& b, const PieceRec* table, const TileMaps& maps,
                                   cudaStream_t st);

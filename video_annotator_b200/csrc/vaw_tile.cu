@@ -28,6 +28,7 @@
 // certificate and pure-border pieces take the paths of vaw_poly.cu.
 #include <cuda.h>
 #include <stdint.h>
+#include <algorithm>
 #include "vaw_internal.h"
 #include "vaw_poly.cuh"
 
@@ -40,9 +41,9 @@ constexpr int kRowsPerWarp = kPieceHMax / kWarps;  // 8
 #ifndef VAW_TILE_CTAS
 #define VAW_TILE_CTAS 6  // resident CTAs per SM the kernel is sized for (registers and shared memory)
 #endif
-constexpr int kTileCap = VAW_TILE_CTAS >= 6 ? 32768 : 36864;  // bytes of luma + chroma tile per CTA
-constexpr int kCoefBytes = 8 * 32 * 16;            // column polynomials exchanged between the warps
-constexpr int kSmemBytes = kTileCap + kCoefBytes + 16;
+// shared memory: [column polynomials exchanged between the warps | mbarrier | tile (TMA: 128-byte aligned)]
+constexpr int kCoefBytes = 8 * 32 * 16;
+constexpr int kTileOffset = kCoefBytes + 128;
 
 __device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* map, int x, int y, int z, unsigned mbar)
 {
@@ -190,7 +191,7 @@ warp_nv12_tile_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
     const int cbx0 = (2 * cx0) & ~15, cwb = (2 * cx1 + 2 - cbx0 + 15) & ~15;
     const int nr8 = (by1 - by0 + 8) & ~7, cnr8 = (cy1 - cy0 + 8) & ~7;  // rows, rounded up to whole boxes
     const int pl = max(kTileMinPitch, (max(wb, cwb) + 31) & ~31);
-    const bool fits = maps.enabled && pl <= kTileMaxPitch && nr8 > 0 && cnr8 > 0 && pl * (nr8 + cnr8) <= kTileCap;
+    const bool fits = maps.enabled && pl <= kTileMaxPitch && nr8 > 0 && cnr8 > 0 && pl * (nr8 + cnr8) <= maps.tile_cap;
 
     if (!fits) {  // gather from global memory like variant POLY (each warp collapses for itself)
         if (my_rows <= 0) return;
@@ -210,10 +211,10 @@ warp_nv12_tile_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
         return;
     }
 
-    uint8_t* ltile = smem;
-    uint8_t* ctile = smem + nr8 * pl;
-    float4* coefs = reinterpret_cast<float4*>(smem + kTileCap);
-    const unsigned mbar = smem_u32(smem + kTileCap + kCoefBytes);
+    uint8_t* ltile = smem + kTileOffset;
+    uint8_t* ctile = ltile + nr8 * pl;
+    float4* coefs = reinterpret_cast<float4*>(smem);
+    const unsigned mbar = smem_u32(smem + kCoefBytes);
 
     // ---- thread 0: arm the barrier, launch the tile loads ---------------------------------------
     if (tid == 0) {
@@ -262,6 +263,21 @@ warp_nv12_tile_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
     else rows_tile<true>(g, cp, lconst, cconst, upl, dv0, my_rows, o, valid);
 }
 
+int tile_smem_bytes(int tile_cap) { return kTileOffset + tile_cap; }
+
+// Host mirror of the kernel's tile sizing (same integer arithmetic).
+int tile_need_bytes(const PieceRec& rec)
+{
+    if (!(rec.flags & kPiecePoly) || (rec.flags & kPieceOutside)) return 0;
+    const PieceBox& b = rec.box;
+    const int lx0 = b.x0 & ~15, wb = (b.x1 - lx0 + 16) & ~15;
+    const int cbx0 = (2 * b.cx0) & ~15, cwb = (2 * b.cx1 + 2 - cbx0 + 15) & ~15;
+    const int nr8 = (b.y1 - b.y0 + 8) & ~7, cnr8 = (b.cy1 - b.cy0 + 8) & ~7;
+    const int pl = std::max(kTileMinPitch, (std::max(wb, cwb) + 31) & ~31);
+    if (pl > kTileMaxPitch || nr8 <= 0 || cnr8 <= 0) return 0x7fffffff;
+    return pl * (nr8 + cnr8);
+}
+
 cudaError_t launch_warp_nv12_tile(const Geom& g, const FrameBatch& b, const PieceRec* table, const TileMaps& maps,
                                   cudaStream_t st)
 {
@@ -269,13 +285,14 @@ cudaError_t launch_warp_nv12_tile(const Geom& g, const FrameBatch& b, const Piec
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(warp_nv12_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(warp_nv12_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             tile_smem_bytes(kTileCapMax));
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
     dim3 block(32, kWarps);
     dim3 grid(pieces_x(g.out_w), pieces_y(g.out_h, kPieceHMax), b.n_frames);
-    warp_nv12_tile_kernel<<<grid, block, kSmemBytes, st>>>(g, b, table, maps);
+    warp_nv12_tile_kernel<<<grid, block, tile_smem_bytes(maps.tile_cap), st>>>(g, b, table, maps);
     return cudaGetLastError();
 }
 

@@ -199,11 +199,12 @@ class WarpContext:
         return b[:n.value], w[:n.value]
 
     def piece_stats(self, rotation, stream=None):
-        """Variant POLY: {'pieces', 'poly', 'interior', 'outside'} counts for this rotation."""
-        out = (C.c_uint32 * 4)()
+        """Piece classification and tile sizing for this rotation (vaw_piece_stats)."""
+        out = (C.c_uint32 * 8)()
         _, rp = _rot_arg(rotation)
         _check(self._lib.vaw_piece_stats(self._h, rp, out, _stream_handle(stream)), self._h)
-        return dict(zip(("pieces", "poly", "interior", "outside"), [int(v) for v in out]))
+        return dict(zip(("pieces", "poly", "interior", "outside", "max_tile_bytes", "tile_cap", "over_cap"),
+                        [int(v) for v in out]))
 
     def close(self):
         if getattr(self, "_h", None):
