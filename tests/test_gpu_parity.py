@@ -299,6 +299,31 @@ def test_pitched_buffers_and_untouched_padding(V, oracle):
     ctx.close()
 
 
+@pytest.mark.parametrize("src_pitch,dst_pitch", [(3904, 3968), (3842, 3846), (3840, 3844)])
+def test_pitched_4k_frames(V, oracle, src_pitch, dst_pitch):
+    """Row pitches larger than the width at BASELINE size: a 16-byte-multiple source pitch keeps the
+    TMA staging (tensor map over the pitched clip); any other pitch gathers from global memory; an
+    output pitch that is not a multiple of 4 takes the byte-store path.  Same bytes either way."""
+    import torch
+    from video_annotator_b200 import configs
+    w = configs.workload("C3")
+    sw, sh = w.src_size
+    ow, oh = w.out_size
+    rot = w.rotations(1, first=140)[0]
+    ctx = V.WarpContext(w.input_camera, w.output_camera, out_size=w.out_size)
+    frame = oracle.synth_nv12(sw, sh, 4, white_noise=True)
+    want = _warp_one(V, ctx, frame, rot)
+    src = torch.full((sh * 3 // 2, src_pitch), 0x5A, dtype=torch.uint8, device="cuda")
+    src[:, :sw] = G.to_dev(frame)
+    dst = torch.full((oh * 3 // 2, dst_pitch), 0xA5, dtype=torch.uint8, device="cuda")
+    ctx.warp(src, dst, rot, src_pitch=src_pitch, dst_pitch=dst_pitch)
+    torch.cuda.synchronize()
+    out = dst.cpu().numpy()
+    assert np.array_equal(out[:, :ow], want)
+    assert (out[:, ow:] == 0xA5).all()
+    ctx.close()
+
+
 @pytest.mark.parametrize("out_size", [(2, 2), (6, 4), (130, 18), (254, 34), (258, 30)])
 def test_ragged_output_sizes(V, oracle, out_size):
     """Output sizes that do not fill a warp row / CTA tile; guard bytes after the frame stay intact."""

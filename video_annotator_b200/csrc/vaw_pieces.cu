@@ -19,7 +19,10 @@ namespace {
 
 constexpr int kChunk = 32;                       // pieces per CTA along u
 constexpr int kNodesU = kChunk * kDegU + 1;      // 161 shared nodes
-constexpr int kThreads = 256;
+#ifndef VAW_BUILDER_THREADS
+#define VAW_BUILDER_THREADS 192  // small CTAs: the kernel is latency-bound (measured 76 us vs 80 at 256, 96 at 320)
+#endif
+constexpr int kThreads = VAW_BUILDER_THREADS;
 
 struct RotD { double r[9]; };
 struct RotF { float r[9]; };
@@ -152,29 +155,29 @@ build_pieces_kernel(const GeomD g, const PieceBasis basis, const float* __restri
     }
     __syncthreads();
 
-    // 4a. accuracy: exact projection against the fp32 polynomial where the interpolation error
-    // of equispaced nodes peaks (inside the first / last node intervals)
-    for (int task = tid; task < np * 3; task += kThreads) {
-        const int p = task / 3, which = task % 3;
-        const double du = which == 0 ? 9.0 : (which == 1 ? 119.0 : 70.0);
-        const double dv = (which == 1 ? 0.894 : 0.106) * ph;
-        const Ray e = project(g, R, 128.0 * (p0 + p) + du, (double)ph * py + dv);
-        const double s = (du - 63.5) / 64.0, t = (dv - 0.5 * (ph - 1)) * (2.0 / ph);
-        const double ex = poly_eval(recs[p], 0, s, t) - e.mx;
-        const double ey = poly_eval(recs[p], 1, s, t) - e.my;
-        if (!(fabs(ex) <= 5e-5 && fabs(ey) <= 5e-5)) bad[p] = 1;
-    }
-    __syncthreads();
-
-    // 4b. regularity, coordinate range, flags; write the records
-    if (tid < np) {
-        const int p = tid;
-        bool ok = !bad[p];
+    // 4. certificates, all in one phase on disjoint thread ranges:
+    //    tasks [0, 3 np): accuracy -- exact projection against the fp32 polynomial where the
+    //    interpolation error of equispaced nodes peaks (inside the first / last node intervals);
+    //    tasks [3 np, 4 np): regularity, coordinate range -> flags and the source box.
+    for (int task = tid; task < np * 4; task += kThreads) {
+        if (task < np * 3) {
+            const int p = task / 3, which = task % 3;
+            const double du = which == 0 ? 9.0 : (which == 1 ? 119.0 : 70.0);
+            const double dv = (which == 1 ? 0.894 : 0.106) * ph;
+            const Ray e = project(g, R, 128.0 * (p0 + p) + du, (double)ph * py + dv);
+            const double s = (du - 63.5) / 64.0, t = (dv - 0.5 * (ph - 1)) * (2.0 / ph);
+            const double ex = poly_eval(recs[p], 0, s, t) - e.mx;
+            const double ey = poly_eval(recs[p], 1, s, t) - e.my;
+            if (!(fabs(ex) <= 5e-5 && fabs(ey) <= 5e-5)) bad[p] = 1;
+            continue;
+        }
+        const int p = task - np * 3;
+        bool ok = true;
         bool pos0 = true, neg0 = true, pos1 = true, neg1 = true;
 #pragma unroll
         for (int corner = 0; corner < 4; ++corner) {
             const Ray a = ray_only(g, R, 128.0 * (p0 + p) + ((corner & 1) ? 128.0 : 0.0),
-                                  (double)ph * py + ((corner & 2) ? (double)ph : 0.0));
+                                   (double)ph * py + ((corner & 2) ? (double)ph : 0.0));
             ok = ok && a.q2 >= 0.015625 && a.q2 <= 64.0 && fabs(a.q0) <= 64.0 && fabs(a.q1) <= 64.0;
             const double eps = 9.5367431640625e-07;  // 2^-20
             pos0 = pos0 && a.q0 >= eps; neg0 = neg0 && a.q0 <= -eps;
@@ -182,55 +185,47 @@ build_pieces_kernel(const GeomD g, const PieceBasis basis, const float* __restri
         }
         ok = ok && (pos0 || neg0 || pos1 || neg1);  // optical axis not inside (NaN pixel, createMap.cl:38-39)
         PieceRec& rec = recs[p];
-        double rx = 0.0, ry = 0.0;
+        // coordinate range: |offset| <= L1 norm of the non-constant coefficients (|s|, |t| <= 1)
+        double lo[2], hi[2];
 #pragma unroll
-        for (int i = 0; i < kNu; ++i)
+        for (int c = 0; c < 2; ++c) {
+            double rad = 0.0;
 #pragma unroll
-            for (int j = 0; j < kNv; ++j)
-                if (i | j) { rx += fabs((double)rec.c[i][j].x); ry += fabs((double)rec.c[i][j].y); }
-        const double cxm = (double)rec.base.x + (double)rec.c[0][0].x, cym = (double)rec.base.y + (double)rec.c[0][0].y;
-        const double lo_x = cxm - rx - 0.01, hi_x = cxm + rx + 0.01, lo_y = cym - ry - 0.01, hi_y = cym + ry + 0.01;
-        ok = ok && fabs(lo_x) < 60000.0 && fabs(hi_x) < 60000.0 && fabs(lo_y) < 60000.0 && fabs(hi_y) < 60000.0;
+            for (int i = 0; i < kNu; ++i)
+#pragma unroll
+                for (int j = 0; j < kNv; ++j)
+                    if (i | j) rad += fabs((double)coef(rec, c, i, j));
+            const double centre = (double)base_of(rec, c) + (double)coef(rec, c, 0, 0);
+            lo[c] = centre - rad - 0.01;
+            hi[c] = centre + rad + 0.01;
+        }
+        ok = ok && fabs(lo[0]) < 30000.0 && fabs(hi[0]) < 30000.0 && fabs(lo[1]) < 30000.0 && fabs(hi[1]) < 30000.0;
         uint32_t flags = 0;
+        PieceBox box = {0, -1, 0, -1, 0, -1, 0, -1};
         if (ok) {
             flags |= kPiecePoly;
             const double W = g.src_w, H = g.src_h;
             // luma taps ix, ix+1 in [0, W-1]  <=>  0 <= m < W-1;  chroma: 0.5 <= mean < W-1.5
-            if (lo_x >= 0.55 && hi_x <= W - 1.55 && lo_y >= 0.55 && hi_y <= H - 1.55) flags |= kPieceInterior;
+            if (lo[0] >= 0.55 && hi[0] <= W - 1.55 && lo[1] >= 0.55 && hi[1] <= H - 1.55) flags |= kPieceInterior;
             // every luma and chroma tap outside in x, or in y
-            if (hi_x < -1.6 || lo_x > W + 0.55 || hi_y < -1.6 || lo_y > H + 0.55) flags |= kPieceOutside;
+            if (hi[0] < -1.6 || lo[0] > W + 0.55 || hi[1] < -1.6 || lo[1] > H + 0.55) flags |= kPieceOutside;
+            if (!(flags & kPieceOutside)) {
+                // source rectangle of the taps (for the shared-memory staging): luma taps floor(m),
+                // floor(m)+1; chroma coordinate = (mean - 0.5) / 2
+                box.x0 = (int16_t)floor(lo[0] - 0.01); box.x1 = (int16_t)(floor(hi[0] + 0.01) + 1.0);
+                box.y0 = (int16_t)floor(lo[1] - 0.01); box.y1 = (int16_t)(floor(hi[1] + 0.01) + 1.0);
+                box.cx0 = (int16_t)floor((lo[0] - 0.5) * 0.5 - 0.01); box.cx1 = (int16_t)(floor((hi[0] - 0.5) * 0.5 + 0.01) + 1.0);
+                box.cy0 = (int16_t)floor((lo[1] - 0.5) * 0.5 - 0.01); box.cy1 = (int16_t)(floor((hi[1] - 0.5) * 0.5 + 0.01) + 1.0);
+            }
         }
         rec.flags = flags;
         rec.pad = 0;
+        rec.box = box;
     }
     __syncthreads();
-
-    // 5. source rectangle of the piece's taps (for the shared-memory staging), from the same
-    // L1-norm range; clamped to int16 (a piece that far outside is classified kPieceOutside)
-    if (tid < np) {
-        PieceRec& rec = recs[tid];
-        PieceBox box = {0, -1, 0, -1, 0, -1, 0, -1};
-        if ((rec.flags & kPiecePoly) && !(rec.flags & kPieceOutside)) {
-            double lo[2], hi[2];
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                double rad = 0.0;
-#pragma unroll
-                for (int i = 0; i < kNu; ++i)
-#pragma unroll
-                    for (int j = 0; j < kNv; ++j)
-                        if (i | j) rad += fabs((double)coef(rec, c, i, j));
-                const double centre = (double)base_of(rec, c) + (double)coef(rec, c, 0, 0);
-                lo[c] = fmax(centre - rad - 0.02, -30000.0);
-                hi[c] = fmin(centre + rad + 0.02, 30000.0);
-            }
-            // luma taps floor(m), floor(m)+1; chroma coordinate = (mean - 0.5) / 2
-            box.x0 = (int16_t)floor(lo[0]); box.x1 = (int16_t)(floor(hi[0]) + 1.0);
-            box.y0 = (int16_t)floor(lo[1]); box.y1 = (int16_t)(floor(hi[1]) + 1.0);
-            box.cx0 = (int16_t)floor((lo[0] - 0.5) * 0.5 - 0.01); box.cx1 = (int16_t)(floor((hi[0] - 0.5) * 0.5 + 0.01) + 1.0);
-            box.cy0 = (int16_t)floor((lo[1] - 0.5) * 0.5 - 0.01); box.cy1 = (int16_t)(floor((hi[1] - 0.5) * 0.5 + 0.01) + 1.0);
-        }
-        rec.box = box;
+    if (tid < np && bad[tid]) {  // failed the accuracy certificate: per-pixel evaluation
+        recs[tid].flags = 0;
+        recs[tid].box = PieceBox{0, -1, 0, -1, 0, -1, 0, -1};
     }
     __syncthreads();
     // coalesced copy of the records (208 bytes each) to the table
