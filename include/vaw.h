@@ -208,6 +208,16 @@ int vaw_clip_warp_host(vaw_clip *clip, const uint8_t *src_host, uint8_t *dst_hos
                        const double *rotations_host, int n_frames);
 const char *vaw_clip_last_error(const vaw_clip *clip);
 
+/* ---- the step before the warp ------------------------------------------------------------
+ * cv::cvtColor(frame, output, COLOR_YUV2BGR_NV12) as the reference runs it on every frame before
+ * buffering and warping it (opencv/FrameSourceWarp.cpp:399-401): NV12 (width x 3*height/2 bytes,
+ * even sizes) -> interleaved BGR 8UC3, bit-exact with OpenCV's fixed-point BT.601.  DEVICE
+ * pointers, n_frames frames at constant strides, asynchronous on `stream`.  Feeding its output
+ * to a VAW_FORMAT_BGR24 context reproduces the reference's literal pipeline. */
+int vaw_nv12_to_bgr(const uint8_t *src, int width, int height, int src_pitch, size_t src_frame_stride,
+                    uint8_t *dst, int dst_pitch, size_t dst_frame_stride, int n_frames, int device,
+                    void *stream);
+
 /* ---- synthetic frames (decode is out of scope; BASELINE.json north_star) ------------
  * Fill n_frames NV12 frames in device memory with the integer test pattern
  * (frame index first_index + i). */

@@ -75,6 +75,8 @@ def lib():
         L.vaw_oracle_get_output_camera.argtypes = [C.POINTER(Camera), C.c_double, C.c_int, C.c_double,
                                                    C.POINTER(Camera)]
         L.vaw_oracle_get_output_camera.restype = None
+        L.vaw_oracle_nv12_to_bgr.argtypes = [u8, C.c_int, C.c_int, C.c_int, u8, C.c_int, C.c_int]
+        L.vaw_oracle_nv12_to_bgr.restype = None
         L.vaw_oracle_synth_nv12.argtypes = [u8, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int]
         L.vaw_oracle_synth_nv12.restype = None
         _lib = L
@@ -157,6 +159,14 @@ def warp_bgr(src, out_w, out_h, k, rot, border=(0, 0, 0), threads=1):
     b = np.asarray(border, dtype=np.uint8)
     lib().vaw_oracle_warp_bgr(_u8(src), w, h, src.strides[0], _u8(dst), out_w, out_h,
                               dst.strides[0], C.byref(k), _fp(r), _u8(b), threads)
+    return dst
+
+
+def nv12_to_bgr(src, w, h, threads=1):
+    """cv::cvtColor(COLOR_YUV2BGR_NV12): (3h/2, w) uint8 -> (h, w, 3)."""
+    src = np.ascontiguousarray(src)
+    dst = np.empty((h, w, 3), np.uint8)
+    lib().vaw_oracle_nv12_to_bgr(_u8(src), w, h, src.strides[0], _u8(dst), dst.strides[0], threads)
     return dst
 
 

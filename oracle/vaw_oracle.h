@@ -14,6 +14,8 @@
  *     (third-party: OpenCV imgproc, not vendored in the reference; the image
  *     carries opencv-python-headless 4.13.0, the reference pins >= 4.5 in
  *     opencv/meson.build:33)
+ *   - cv::cvtColor(COLOR_YUV2BGR_NV12), called at
+ *     opencv/FrameSourceWarp.cpp:399-401   -> vaw_oracle_nv12_to_bgr()  (PINNED to cv2.cvtColor)
  *   - opencv/FrameSourceWarp.cpp:27-86     -> vaw_oracle_get_preset_camera()
  *   - opencv/FrameSourceWarp.cpp:88-165    -> vaw_oracle_get_output_camera()
  *
@@ -81,6 +83,11 @@ void vaw_oracle_warp_bgr(const uint8_t *src, int src_w, int src_h, int src_pitch
                          uint8_t *dst, int out_w, int out_h, int dst_pitch,
                          const vaw_oracle_intrinsics *k, const float rot[9],
                          const uint8_t border[3], int n_threads);
+
+/* cv::cvtColor(COLOR_YUV2BGR_NV12), FrameSourceWarp.cpp:399-401.  src: NV12 buffer (h*3/2 rows of
+ * src_pitch bytes), dst: h x w x 3. */
+void vaw_oracle_nv12_to_bgr(const uint8_t *src, int w, int h, int src_pitch, uint8_t *dst, int dst_pitch,
+                            int n_threads);
 
 /* Count unique source bytes touched by the in-range taps. */
 int64_t vaw_oracle_touched_bytes(const float *map_x, const float *map_y, int rows, int cols,

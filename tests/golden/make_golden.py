@@ -14,6 +14,7 @@ What pins what:
                     vectors for createMap.cl (parity unpinned); this is the anchor.
   camera_table.npz  output cameras computed by a Python transcription of
                     FrameSourceWarp.cpp:27-165 using cv2.fisheye.undistortPoints.
+  cvt_nv12_bgr.npz  cv2.cvtColor(COLOR_YUV2BGR_NV12) on random + extreme samples.  PINS oracle/cvt_ref.c.
   nv12_small.npz    a small NV12 warp computed with cv2.remap on the oracle's luma
                     map and a numpy chroma map.  PINS oracle/nv12_warp_ref.c.
 """
@@ -137,7 +138,28 @@ def nv12_small():
                         borders=np.array([(0, 128, 128), (0, 0, 0), (33, 77, 201)], np.uint8), **out)
 
 
+def cvt_nv12_bgr():
+    """cv2.cvtColor(COLOR_YUV2BGR_NV12) -- the call at opencv/FrameSourceWarp.cpp:399-401 -- on random
+    NV12 plus the extreme (Y, U, V) combinations.  PINS oracle/cvt_ref.c."""
+    rng = np.random.default_rng(20260004)
+    w, h = 64, 48
+    nv = rng.integers(0, 256, (h * 3 // 2, w), dtype=np.uint8)
+    ext = np.array([0, 1, 15, 16, 17, 127, 128, 129, 234, 235, 236, 254, 255], np.uint8)
+    k = 0
+    for yv in ext:                       # first rows: extreme combinations
+        for uv in ext[::3]:
+            if k >= w * 8:
+                break
+            nv[(k // w), k % w] = yv
+            nv[h + (k // w) // 2, (k % w) & ~1] = uv
+            nv[h + (k // w) // 2, ((k % w) & ~1) + 1] = ext[(k * 7) % len(ext)]
+            k += 1
+    np.savez_compressed(os.path.join(HERE, "cvt_nv12_bgr.npz"), nv12=nv,
+                        bgr=cv2.cvtColor(nv, cv2.COLOR_YUV2BGR_NV12))
+
+
 if __name__ == "__main__":
+    cvt_nv12_bgr()
     remap_cases()
     fisheye_map()
     camera_table()

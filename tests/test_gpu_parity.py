@@ -508,6 +508,35 @@ def test_bgr_literal_reference_case(V, oracle):
         ctx.close()
 
 
+def test_nv12_to_bgr_and_the_literal_reference_pipeline(V, oracle):
+    """cvtColor(COLOR_YUV2BGR_NV12) then the BGR warp = FrameSourceWarp.cpp:399-401 + :272-314:
+    the conversion is bit-exact against cv2's golden output and the oracle, and the two stages
+    chained equal the oracle's chain."""
+    import torch
+    g = np.load(os.path.join(GOLDEN, "cvt_nv12_bgr.npz"))
+    got = V.nv12_to_bgr(G.to_dev(g["nv12"]), 64, 48)[0].cpu().numpy()
+    assert np.array_equal(got, g["bgr"])
+    w, h, n = 1920, 1080, 3
+    src = torch.empty((n, h * 3 // 2, w), dtype=torch.uint8, device="cuda")
+    V.synth_nv12(src, w, h, n, white_noise=True)
+    bgr = V.nv12_to_bgr(src, w, h, n)
+    torch.cuda.synchronize()
+    for i in range(n):
+        assert np.array_equal(bgr[i].cpu().numpy(), oracle.nv12_to_bgr(src[i].cpu().numpy(), w, h, threads=NCPU))
+    cam = V.get_preset_camera(V.warp.GOPRO_H4B_WIDE169_MEASURED, w, h)
+    out = V.get_output_camera(cam)
+    ctx = V.WarpContext(cam, out, fmt=V.FORMAT_BGR24, border=(0, 0, 0))
+    R = rotation_xyz(0.7, -1.1, 0.4)
+    dst = torch.empty(ctx.frame_shape("dst"), dtype=torch.uint8, device="cuda")
+    ctx.warp(bgr[1], dst, R)
+    mx, my = [t.cpu().numpy() for t in ctx.dump_coords(R, 0)]
+    assert np.array_equal(dst.cpu().numpy(), oracle.remap_u8(bgr[1].cpu().numpy(), mx, my, border=(0, 0, 0), threads=NCPU))
+    ctx.close()
+    # odd-multiple-of-2 width: the byte path
+    nv = oracle.synth_nv12(126, 34, 1, white_noise=True)
+    assert np.array_equal(V.nv12_to_bgr(G.to_dev(nv), 126, 34)[0].cpu().numpy(), oracle.nv12_to_bgr(nv, 126, 34))
+
+
 def test_gray8(V, oracle):
     import torch
     g, cin, cout = _small_cams(V)

@@ -7,4 +7,4 @@ and streams.  Nothing here falls back to the CPU.
 """
 from ._lib import VawCamera, VawParams, load  # noqa: F401
 from .warp import (FORMAT_BGR24, FORMAT_GRAY8, FORMAT_NV12, Camera, ClipWarper, VawError, WarpContext,  # noqa: F401
-                   get_output_camera, get_preset_camera, remap_u8, selftest_math, shard_range, synth_nv12)
+                   get_output_camera, get_preset_camera, nv12_to_bgr, remap_u8, selftest_math, shard_range, synth_nv12)

@@ -51,6 +51,8 @@ SIGNATURES = {
     "vaw_dump_coords": (C.c_int, [C.c_void_p, f64p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "vaw_remap_u8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, u8p, C.c_int, C.c_void_p]),
+    "vaw_nv12_to_bgr": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_size_t,
+                                  C.c_int, C.c_int, C.c_void_p]),
     "vaw_synth_nv12": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int,
                                  C.c_uint32, C.c_int, C.c_int, C.c_void_p]),
     "vaw_malloc": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(C.c_void_p)]),

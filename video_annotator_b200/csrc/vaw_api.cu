@@ -742,6 +742,23 @@ int vaw_remap_u8(const uint8_t* src, int src_width, int src_height, int src_pitc
     return VAW_OK;
 }
 
+int vaw_nv12_to_bgr(const uint8_t* src, int width, int height, int src_pitch, size_t src_frame_stride,
+                    uint8_t* dst, int dst_pitch, size_t dst_frame_stride, int n_frames, int device, void* stream)
+{
+    if (!src || !dst) return fail(nullptr, VAW_ERR_INVALID, "null frame pointer");
+    if (width < 2 || height < 2 || ((width | height) & 1) || src_pitch < width || dst_pitch < 3 * width || n_frames < 0)
+        return fail(nullptr, VAW_ERR_INVALID, "bad cvtColor geometry");
+    DeviceGuard dg(device);
+    for (int first = 0; first < n_frames; first += 65535) {
+        const int n = n_frames - first < 65535 ? n_frames - first : 65535;
+        cudaError_t e = vaw::launch_nv12_to_bgr(src + (size_t)first * src_frame_stride, width, height, src_pitch,
+                                                src_frame_stride, dst + (size_t)first * dst_frame_stride, dst_pitch,
+                                                dst_frame_stride, n, (cudaStream_t)stream);
+        if (e != cudaSuccess) return cuda_fail(nullptr, e, "nv12_to_bgr launch");
+    }
+    return VAW_OK;
+}
+
 int vaw_synth_nv12(uint8_t* dst, int width, int height, int pitch, size_t frame_stride,
                    int first_index, int n_frames, uint32_t seed, int white_noise, int device,
                    void* stream)

@@ -57,6 +57,9 @@ cudaError_t launch_dump_coords(const Geom& g, const Rot& rot, int plane, float* 
 cudaError_t launch_remap(const uint8_t* src, int src_w, int src_h, int src_pitch, int cn,
                          const float* map_x, const float* map_y, int rows, int cols, int map_pitch,
                          uint8_t* dst, int dst_pitch, unsigned border, cudaStream_t st);
+// cv::cvtColor(COLOR_YUV2BGR_NV12) for n_frames frames (FrameSourceWarp.cpp:399-401).
+cudaError_t launch_nv12_to_bgr(const uint8_t* src, int w, int h, int src_pitch, size_t src_stride, uint8_t* dst,
+                               int dst_pitch, size_t dst_stride, int n_frames, cudaStream_t st);
 // Integer synthetic content (mirror of oracle/synth_ref.c).
 cudaError_t launch_synth_nv12(uint8_t* dst, int w, int h, int pitch, size_t frame_stride,
                               int first_index, int n_frames, uint32_t seed, int white,

@@ -269,6 +269,77 @@ cudaError_t launch_remap(const uint8_t* src, int src_w, int src_h, int src_pitch
     return cudaGetLastError();
 }
 
+// ---- NV12 -> BGR: cv::cvtColor(COLOR_YUV2BGR_NV12) ------------------------------------------
+// The conversion the reference runs on every frame before buffering and warping it
+// (FrameSourceWarp.cpp:399-401).  OpenCV's 20-bit fixed-point BT.601 (oracle/cvt_ref.c).
+// A thread converts 4 x 2 luma samples (two UV pairs): two 4-byte luma loads, one 4-byte chroma
+// load, six 4-byte stores; a warp row is 128 pixels = 384 contiguous output bytes.  HBM-bound:
+// 1.5 bytes in, 3 bytes out per pixel.
+__device__ __forceinline__ unsigned sat8(int v) { return (unsigned)min(max(v, 0), 255); }
+
+__device__ __forceinline__ void yuv_pixel(int y, int u, int v, unsigned& b, unsigned& g, unsigned& r)
+{
+    const int yy = max(y - 16, 0) * 1220542 + (1 << 19);
+    b = sat8((yy + 2116026 * u) >> 20);
+    g = sat8((yy - 852492 * v - 409993 * u) >> 20);
+    r = sat8((yy + 1673527 * v) >> 20);
+}
+
+__global__ void __launch_bounds__(256)
+nv12_to_bgr_kernel(const uint8_t* __restrict__ src, int w, int h, int src_pitch, size_t src_stride,
+                   uint8_t* __restrict__ dst, int dst_pitch, size_t dst_stride, int aligned)
+{
+    const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const int y0 = (blockIdx.y * 8 + threadIdx.y) * 2;
+    if (x0 >= w || y0 >= h) return;
+    const uint8_t* s = src + (size_t)blockIdx.z * src_stride;
+    uint8_t* d = dst + (size_t)blockIdx.z * dst_stride;
+    const uint8_t* uvp = s + (size_t)(h + (y0 >> 1)) * src_pitch + x0;
+    unsigned yw[2], uvw;
+    const int n = min(4, w - x0);  // w is even: n is 2 or 4
+    if (aligned && n == 4) {
+        yw[0] = __ldg(reinterpret_cast<const unsigned*>(s + (size_t)y0 * src_pitch + x0));
+        yw[1] = __ldg(reinterpret_cast<const unsigned*>(s + (size_t)(y0 + 1) * src_pitch + x0));
+        uvw = __ldg(reinterpret_cast<const unsigned*>(uvp));
+    } else {
+        yw[0] = yw[1] = uvw = 0;
+        for (int i = 0; i < n; ++i) {
+            yw[0] |= (unsigned)__ldg(s + (size_t)y0 * src_pitch + x0 + i) << (8 * i);
+            yw[1] |= (unsigned)__ldg(s + (size_t)(y0 + 1) * src_pitch + x0 + i) << (8 * i);
+            uvw |= (unsigned)__ldg(uvp + i) << (8 * i);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        unsigned px[4][3];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int u = (int)((uvw >> (16 * (i >> 1))) & 255) - 128, v = (int)((uvw >> (16 * (i >> 1) + 8)) & 255) - 128;
+            yuv_pixel((int)((yw[r] >> (8 * i)) & 255), u, v, px[i][0], px[i][1], px[i][2]);
+        }
+        uint8_t* o = d + (size_t)(y0 + r) * dst_pitch + (size_t)x0 * 3;
+        if (aligned && n == 4) {
+            unsigned* o32 = reinterpret_cast<unsigned*>(o);
+            o32[0] = px[0][0] | (px[0][1] << 8) | (px[0][2] << 16) | (px[1][0] << 24);
+            o32[1] = px[1][1] | (px[1][2] << 8) | (px[2][0] << 16) | (px[2][1] << 24);
+            o32[2] = px[2][2] | (px[3][0] << 8) | (px[3][1] << 16) | (px[3][2] << 24);
+        } else {
+            for (int i = 0; i < n; ++i)
+                for (int c = 0; c < 3; ++c) o[3 * i + c] = (uint8_t)px[i][c];
+        }
+    }
+}
+
+cudaError_t launch_nv12_to_bgr(const uint8_t* src, int w, int h, int src_pitch, size_t src_stride, uint8_t* dst,
+                               int dst_pitch, size_t dst_stride, int n_frames, cudaStream_t st)
+{
+    const int aligned = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)src_pitch | (uintptr_t)src_stride |
+                          reinterpret_cast<uintptr_t>(dst) | (uintptr_t)dst_pitch | (uintptr_t)dst_stride) & 3) == 0;
+    dim3 block(32, 8), grid((w + 127) / 128, (h / 2 + 7) / 8, n_frames);
+    nv12_to_bgr_kernel<<<grid, block, 0, st>>>(src, w, h, src_pitch, src_stride, dst, dst_pitch, dst_stride, aligned);
+    return cudaGetLastError();
+}
+
 // ---- ray tables ----------------------------------------------------------------------
 __global__ void ray_tables_kernel(float* xtab, int n_x, float* ytab, int n_y, float mcx, float mfx,
                                   float mcy, float mfy)

@@ -284,6 +284,17 @@ def remap_u8(src, map_x, map_y, border=(0, 0, 0), stream=None):
     return dst
 
 
+def nv12_to_bgr(src, width, height, n_frames=1, stream=None):
+    """cv::cvtColor(COLOR_YUV2BGR_NV12), FrameSourceWarp.cpp:399-401.  src: CUDA uint8, n_frames tightly
+    packed NV12 frames; returns a CUDA uint8 tensor (n_frames, height, width, 3)."""
+    import torch
+    dst = torch.empty((n_frames, height, width, 3), dtype=torch.uint8, device=src.device)
+    _check(_lib.load().vaw_nv12_to_bgr(src.data_ptr(), width, height, width, width * height * 3 // 2, dst.data_ptr(),
+                                       width * 3, width * height * 3, n_frames, src.device.index or 0,
+                                       _stream_handle(stream)))
+    return dst
+
+
 def selftest_math(device=0, seed=1, n_per_thread=1000):
     out = (C.c_uint64 * 4)()
     _check(_lib.load().vaw_selftest_math(device, seed, n_per_thread, out))
