@@ -107,16 +107,19 @@ __device__ __forceinline__ int blend_y(int t00, int t01, int t10, int t11, int a
     return top * wy + bot * ay + 512;
 }
 
-// taps are (U | V << 8) pairs; the horizontal blend runs on U (bits 0..15) and V (16..31) at once
+// taps are (U | V << 8) pairs.  The four-weight sum is exact in integers, so the order of the two
+// blends is free: vertical first on U (bits 0..15) and V (bits 16..31) at once, then the horizontal
+// blend of each channel as one two-way dot product (IDP.2A) -- same value as blend_y's order.
 __device__ __forceinline__ unsigned blend_uv(unsigned t00, unsigned t01, unsigned t10, unsigned t11,
                                              unsigned ax, unsigned ay)
 {
-    const unsigned wx = 32u - ax, wy = 32u - ay;
+    const unsigned wy = 32u - ay;
     const unsigned s00 = __byte_perm(t00, 0, 0x4140), s01 = __byte_perm(t01, 0, 0x4140);
     const unsigned s10 = __byte_perm(t10, 0, 0x4140), s11 = __byte_perm(t11, 0, 0x4140);
-    const unsigned top = s00 * wx + s01 * ax, bot = s10 * wx + s11 * ax;  // <= 8160 per half
-    const unsigned u = ((top & 0xffffu) * wy + (bot & 0xffffu) * ay + 512u) >> 10;
-    const unsigned v = ((top >> 16) * wy + (bot >> 16) * ay + 512u) >> 10;
+    const unsigned left = s00 * wy + s10 * ay, right = s01 * wy + s11 * ay;  // <= 8160 per half
+    const unsigned wpair = 32u + 255u * ax;                                   // (32 - ax) | ax << 8
+    const unsigned u = __dp2a_lo(__byte_perm(left, right, 0x5410), wpair, 512u) >> 10;
+    const unsigned v = __dp2a_lo(__byte_perm(left, right, 0x7632), wpair, 512u) >> 10;
     return u | (v << 8);
 }
 
@@ -260,11 +263,15 @@ __device__ __forceinline__ void band_gmem(const Geom& g, const ColPoly& cp, cons
     const unsigned pitch = (unsigned)g.src_pitch;
     const unsigned bias_y = 0u - kMagicShift * pitch - kMagicShift;         // offset = iy*pitch + ix
     const unsigned bias_c = 0u - kMagicShift * (pitch >> 1) - kMagicShift;  // offset = iy*pitch + 2*(ix + bias)
+    // t = (dv - t_off) * t_scale is a small dyadic rational: stepping it by t_scale is exact
+    float t = row_t(g, dv0);
+    const float dt = g.t_scale, dt2 = __fadd_rn(g.t_scale, g.t_scale);
 #pragma unroll 1
     for (int dv = dv0; dv < dv0 + nrows; dv += 2) {
         float2 m[2][4];
-        row_coords(cp, row_t(g, dv), m[0]);
-        row_coords(cp, row_t(g, dv + 1), m[1]);
+        row_coords(cp, t, m[0]);
+        row_coords(cp, __fadd_rn(t, dt), m[1]);
+        t = __fadd_rn(t, dt2);
         int acc[2][4];
 #pragma unroll
         for (int r = 0; r < 2; ++r)

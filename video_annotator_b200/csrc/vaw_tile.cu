@@ -76,11 +76,15 @@ template <bool kRagged>
 __device__ __forceinline__ void rows_tile(const Geom& g, const ColPoly& cp, unsigned lconst, unsigned cconst,
                                           unsigned pl, int dv0, int nrows, RowPtrs& o, int valid)
 {
+    // t = (dv - t_off) * t_scale is a small dyadic rational: stepping it by t_scale is exact
+    float t = row_t(g, dv0);
+    const float dt = g.t_scale, dt2 = __fadd_rn(g.t_scale, g.t_scale);
 #pragma unroll 1
     for (int dv = dv0; dv < dv0 + nrows; dv += 2) {
         float2 m[2][4];
-        row_coords(cp, row_t(g, dv), m[0]);
-        row_coords(cp, row_t(g, dv + 1), m[1]);
+        row_coords(cp, t, m[0]);
+        row_coords(cp, __fadd_rn(t, dt), m[1]);
+        t = __fadd_rn(t, dt2);
         int acc[2][4];
 #pragma unroll
         for (int r = 0; r < 2; ++r)
