@@ -71,10 +71,31 @@ __device__ __forceinline__ unsigned chroma_tile(unsigned cconst, unsigned pl, fl
     return blend_uv(lds_u16<0>(a0), lds_u16<2>(a0), lds_u16<0>(a1), lds_u16<2>(a1), bx & 31, by & 31);
 }
 
-// nrows (even) rows starting at piece row dv0, taps from the staged tile.
+// Lane -> column mapping of the staged path: lane l owns luma columns 2l, 2l+1 and 64+2l, 64+2l+1
+// of the piece (slot j -> column 2l + (j & 1) + 64 (j >> 1)).  One LDS instruction then serves 32
+// pixels that are 2 columns apart: at the C3 centre (1.84 source px per output px) its addresses
+// span 118 bytes = 30 banks, i.e. one shared-memory wavefront.  With four consecutive columns per
+// lane the same instruction spans 236 bytes and needs two or more (measured 2.5 wavefronts per
+// LDS, shared-memory pipe 72 % busy).  Quads (j = 0,1 and j = 2,3) stay inside a lane, so the NV12
+// chroma rule needs no shuffles; stores become 2 bytes per lane (64 contiguous bytes per warp).
+__device__ __forceinline__ int pair_column(int lane, int j) { return 2 * lane + (j & 1) + 64 * (j >> 1); }
+
+template <bool kRagged>
+__device__ __forceinline__ void store_pair(uint8_t* p, unsigned lo, unsigned hi, bool inside)
+{
+    if (!kRagged) {
+        *reinterpret_cast<uint16_t*>(p) = (uint16_t)(lo | (hi << 8));
+    } else if (inside) {
+        p[0] = (uint8_t)lo;
+        p[1] = (uint8_t)hi;
+    }
+}
+
+// nrows (even) rows starting at piece row dv0, taps from the staged tile.  o.y0 / o.y1 / o.c point
+// at column 2*lane of the piece.
 template <bool kRagged>
 __device__ __forceinline__ void rows_tile(const Geom& g, const ColPoly& cp, unsigned lconst, unsigned cconst,
-                                          unsigned pl, int dv0, int nrows, RowPtrs& o, int valid)
+                                          unsigned pl, int dv0, int nrows, RowPtrs& o, bool in_a, bool in_b)
 {
     // t = (dv - t_off) * t_scale is a small dyadic rational: stepping it by t_scale is exact
     float t = row_t(g, dv0);
@@ -85,20 +106,21 @@ __device__ __forceinline__ void rows_tile(const Geom& g, const ColPoly& cp, unsi
         row_coords(cp, t, m[0]);
         row_coords(cp, __fadd_rn(t, dt), m[1]);
         t = __fadd_rn(t, dt2);
-        int acc[2][4];
+        unsigned y[2][4];
 #pragma unroll
         for (int r = 0; r < 2; ++r)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) acc[r][i] = luma_tile(lconst, pl, m[r][i]);
-        unsigned cw = 0u;
+            for (int i = 0; i < 4; ++i) y[r][i] = (unsigned)luma_tile(lconst, pl, m[r][i]) >> 10;
+        unsigned c[2];
 #pragma unroll
         for (int q = 0; q < 2; ++q)
-            cw |= chroma_tile(cconst, pl, chroma_z(m[0][2 * q], m[0][2 * q + 1], m[1][2 * q], m[1][2 * q + 1])) << (16 * q);
-        if (!kRagged || valid > 0) {
-            store_word<kRagged>(o.y0, pack4(acc[0][0], acc[0][1], acc[0][2], acc[0][3]), valid);
-            store_word<kRagged>(o.y1, pack4(acc[1][0], acc[1][1], acc[1][2], acc[1][3]), valid);
-            store_word<kRagged>(o.c, cw, valid);
-        }
+            c[q] = chroma_tile(cconst, pl, chroma_z(m[0][2 * q], m[0][2 * q + 1], m[1][2 * q], m[1][2 * q + 1]));
+        store_pair<kRagged>(o.y0, y[0][0], y[0][1], in_a);
+        store_pair<kRagged>(o.y0 + 64, y[0][2], y[0][3], in_b);
+        store_pair<kRagged>(o.y1, y[1][0], y[1][1], in_a);
+        store_pair<kRagged>(o.y1 + 64, y[1][2], y[1][3], in_b);
+        store_pair<kRagged>(o.c, c[0] & 255u, c[0] >> 8, in_a);
+        store_pair<kRagged>(o.c + 64, c[1] & 255u, c[1] >> 8, in_b);
         o.y0 += o.step_y; o.y1 += o.step_y; o.c += o.step_c;
     }
 }
@@ -194,7 +216,11 @@ warp_nv12_tile_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
     const int lx0 = bx0 & ~15, wb = (bx1 - lx0 + 16) & ~15;
     const int cbx0 = (2 * cx0) & ~15, cwb = (2 * cx1 + 2 - cbx0 + 15) & ~15;
     const int nr8 = (by1 - by0 + 8) & ~7, cnr8 = (cy1 - cy0 + 8) & ~7;  // rows, rounded up to whole boxes
-    const int pl = max(kTileMinPitch, (max(wb, cwb) + 31) & ~31);
+    // Tile row pitch: a multiple of 128 bytes (32 banks) when that fits -- the lanes of one LDS then
+    // keep distinct banks however many source rows they straddle -- else the tightest multiple of 32.
+    const int need = max(wb, cwb);
+    const int pl128 = (need + 127) & ~127, pl32 = max(kTileMinPitch, (need + 31) & ~31);
+    const int pl = (pl128 <= kTileMaxPitch && pl128 * (nr8 + cnr8) <= maps.tile_cap) ? pl128 : pl32;
     const bool fits = maps.enabled && pl <= kTileMaxPitch && nr8 > 0 && cnr8 > 0 && pl * (nr8 + cnr8) <= maps.tile_cap;
 
     if (!fits) {  // gather from global memory like variant POLY (each warp collapses for itself)
@@ -235,7 +261,7 @@ warp_nv12_tile_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
     {
         float2 c[kNu][kNv], a[kNv];
         load_coeffs(rec, c);
-        collapse_column(c, ((float)(4 * lane + w) - 63.5f) * 0.015625f, a);  // s is exact
+        collapse_column(c, ((float)pair_column(lane, w) - 63.5f) * 0.015625f, a);  // s is exact
         coefs[(2 * w) * 32 + lane] = make_float4(a[0].x, a[0].y, a[1].x, a[1].y);
         coefs[(2 * w + 1) * 32 + lane] = make_float4(a[2].x, a[2].y, a[3].x, a[3].y);
     }
@@ -263,8 +289,14 @@ warp_nv12_tile_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
     const unsigned upl = (unsigned)pl;
     const unsigned lconst = smem_u32(ltile) - (unsigned)by0 * upl - (unsigned)lx0 - kMagicShift * upl - kMagicShift;
     const unsigned cconst = ((smem_u32(ctile) - (unsigned)cy0 * upl - (unsigned)cbx0 - kMagicShift * upl) >> 1) - kMagicShift;
-    if (word_ok) rows_tile<false>(g, cp, lconst, cconst, upl, dv0, my_rows, o, valid);
-    else rows_tile<true>(g, cp, lconst, cconst, upl, dv0, my_rows, o, valid);
+    // the staged path uses the pair mapping: re-base the output pointers on column 2 * lane
+    const int shift = 2 * lane - 4 * lane;
+    o.y0 += shift; o.y1 += shift; o.c += shift;
+    const bool in_a = u_lo + 2 * lane < g.out_w, in_b = u_lo + 64 + 2 * lane < g.out_w;  // widths are even
+    const bool pair_ok = ((reinterpret_cast<uintptr_t>(f.dst) | (uintptr_t)g.dst_pitch) & 1) == 0 &&
+                         u_lo + kPieceW <= g.out_w;
+    if (pair_ok) rows_tile<false>(g, cp, lconst, cconst, upl, dv0, my_rows, o, in_a, in_b);
+    else rows_tile<true>(g, cp, lconst, cconst, upl, dv0, my_rows, o, in_a, in_b);
 }
 
 int tile_smem_bytes(int tile_cap) { return kTileOffset + tile_cap; }
