@@ -63,12 +63,16 @@ enum { VAW_INTER_NEAREST = 0, VAW_INTER_LINEAR = 1, VAW_INTER_CUBIC = 2 };
  *   TILED   POLY's coordinates; the source rectangle of every 8-row band is first copied into
  *           shared memory by the TMA engine and the taps are read from there (needs a 16-byte
  *           aligned source base / pitch / frame stride, else it gathers like POLY).
- * POLY and TILED produce identical bytes.  AUTO = TILED for NV12, GATHER for the packed formats. */
+ *   PIPE    TILED's tiles, scheduled as a persistent producer/consumer pipeline: a producer warp
+ *           per CTA pulls pieces from a global queue and issues the TMA loads two pieces ahead,
+ *           four consumer warps sample; the record and tile latencies disappear behind compute.
+ * POLY, TILED and PIPE produce identical bytes.  AUTO = TILED for NV12, GATHER for the packed formats. */
 enum {
     VAW_VARIANT_AUTO = 0,
     VAW_VARIANT_GATHER = 1,
     VAW_VARIANT_POLY = 2,
-    VAW_VARIANT_TILED = 3
+    VAW_VARIANT_TILED = 3,
+    VAW_VARIANT_PIPE = 4
 };
 
 /* ---- parameters -------------------------------------------------------------------

@@ -75,7 +75,7 @@ def test_fast_math_sequences_equal_ieee_intrinsics(V):
 
 
 # ---- A. coordinates ---------------------------------------------------------------------------
-GATHER, POLY, TILED = 1, 2, 3
+GATHER, POLY, TILED, PIPE = 1, 2, 3, 4
 COORD_CASES = [("C1", (0, 0, 0)), ("C1", (2.0, -3.0, 1.5)), ("C2", (-1.0, 2.5, 0.7)),
                ("C3", (2.0, -3.0, 1.5)), ("C5", (6.0, -8.0, 4.0))]
 
@@ -200,7 +200,7 @@ def test_remap_filter_against_cv2_golden(V):
 @pytest.mark.parametrize("name,rot,white", [("C1", (0, 0, 0), True), ("C1", (1.0, -2.0, 0.5), True),
                                             ("C2", (-1.0, 2.5, 0.7), False), ("C3", (2.0, -3.0, 1.5), True),
                                             ("C5", (3.0, -4.0, 2.0), True)])
-@pytest.mark.parametrize("variant", [GATHER, POLY, TILED])
+@pytest.mark.parametrize("variant", [GATHER, POLY, TILED, PIPE])
 def test_pixels_bit_exact_on_same_map(V, oracle, name, rot, white, variant):
     from video_annotator_b200 import configs
     w = configs.workload(name)
@@ -588,6 +588,31 @@ def test_full_size_clip_properties(V, oracle):
     uv = dst[:, oh:]
     assert int(uv.max()) == 200 and int(uv.min()) == 128
     ctx.close()
+
+
+@pytest.mark.parametrize("name,n", [("C3", 10), ("C5", 4), ("C2", 7)])
+def test_variants_produce_identical_batches(V, name, n):
+    """POLY (global gathers), TILED (one CTA per piece) and PIPE (persistent producer/consumer
+    pipeline, dynamic piece queue) share the map and the filter: identical bytes for a batch."""
+    import torch
+    from video_annotator_b200 import configs
+    w = configs.workload(name)
+    rots = w.rotations(n, first=50, total=200)
+    sw, sh = w.src_size
+    outs = []
+    for variant in (POLY, TILED, PIPE):
+        ctx = V.WarpContext(w.input_camera, w.output_camera, out_size=w.out_size, variant=variant, border=(3, 100, 200))
+        src = torch.empty((n,) + ctx.frame_shape("src"), dtype=torch.uint8, device="cuda")
+        V.synth_nv12(src, sw, sh, n, white_noise=True)
+        rdev = torch.empty(n * 9, dtype=torch.float32, device="cuda")
+        ctx.upload_rotations(rots, rdev)
+        dst = torch.full((n,) + ctx.frame_shape("dst"), 0xEE, dtype=torch.uint8, device="cuda")
+        for _ in range(2):                       # twice: the piece queue is reset per launch
+            ctx.warp_batch(src, dst, rdev, n)
+        torch.cuda.synchronize()
+        outs.append(dst.cpu())
+        ctx.close()
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
 
 
 # ---- error convention ----------------------------------------------------------------------------

@@ -30,6 +30,7 @@ struct Stage {
     uint8_t *dev_in = nullptr, *dev_out = nullptr, *pin_in = nullptr, *pin_out = nullptr;
     float *dev_rot = nullptr, *pin_rot = nullptr;
     vaw::PieceRec* pieces = nullptr;  // this stage's polynomial table (chunk_frames frames)
+    unsigned* counter = nullptr;      // this stage's piece queue (variant PIPE)
     // pending output of the chunk in flight on this stage
     uint8_t* host_dst = nullptr;
     size_t out_bytes = 0;
@@ -63,6 +64,7 @@ struct vaw_ctx {
     MapEntry map_cache[4];
     int map_next = 0;
     int tile_cap = 32 << 10;  // chosen at creation from the pieces' source boxes
+    unsigned* counter = nullptr;  // piece queue of variant PIPE (for ctx->table)
     // option "time_kernels": CUDA-event stamps around the kernels of every launch (bench.py's roofline)
     static constexpr int kTimeRing = 512;
     bool time_kernels = false;
@@ -232,7 +234,7 @@ const vaw::TileMaps& tile_maps(vaw_ctx* ctx, const uint8_t* src, int pitch, size
 
 int launch(vaw_ctx* ctx, const uint8_t* src, int src_pitch, size_t src_stride, uint8_t* dst,
            int dst_pitch, size_t dst_stride, const float* rots, const vaw::Rot* rot0, int n_frames,
-           cudaStream_t st, vaw::PieceRec* table_override = nullptr)
+           cudaStream_t st, vaw::PieceRec* table_override = nullptr, unsigned* counter_override = nullptr)
 {
     vaw::Geom g = ctx->g;
     g.src_pitch = src_pitch;
@@ -245,7 +247,10 @@ int launch(vaw_ctx* ctx, const uint8_t* src, int src_pitch, size_t src_stride, u
     b.rots = rots;
     if (rot0) b.rot0 = *rot0;
     const bool poly = ctx->p.format == VAW_FORMAT_NV12 && ctx->variant != VAW_VARIANT_GATHER;
-    const bool tiled = ctx->variant == VAW_VARIANT_TILED && ctx->g.piece_h == vaw::kPieceHMax;
+    const bool tiled = (ctx->variant == VAW_VARIANT_TILED || ctx->variant == VAW_VARIANT_PIPE) &&
+                       ctx->g.piece_h == vaw::kPieceHMax;
+    const bool piped = tiled && ctx->variant == VAW_VARIANT_PIPE &&
+                       vaw::pipe_smem_bytes(ctx->tile_cap) <= (227 << 10);
     // grid.z is limited to 65535 frames per launch
     for (int first = 0; first < n_frames; first += 65535) {
         vaw::FrameBatch bb = b;
@@ -267,7 +272,10 @@ int launch(vaw_ctx* ctx, const uint8_t* src, int src_pitch, size_t src_stride, u
             if (e != cudaSuccess) return cuda_fail(ctx, e, "piece table launch");
             ctx->launches++;
             if (tev) cudaEventRecord(tev[1], st);
-            if (tiled)
+            if (piped)
+                e = vaw::launch_warp_nv12_pipe(g, bb, tab, table_override ? counter_override : ctx->counter,
+                                               tile_maps(ctx, bb.src, src_pitch, src_stride, bb.n_frames), st);
+            else if (tiled)
                 e = vaw::launch_warp_nv12_tile(g, bb, tab, tile_maps(ctx, bb.src, src_pitch, src_stride, bb.n_frames), st);
             else
                 e = vaw::launch_warp_nv12_poly(g, bb, tab, st);
@@ -296,7 +304,7 @@ void free_host_path(vaw_ctx* ctx)
 {
     for (Stage& s : ctx->stage) {
         if (s.stream) cudaStreamSynchronize(s.stream);
-        cudaFree(s.dev_in); cudaFree(s.dev_out); cudaFree(s.dev_rot); cudaFree(s.pieces);
+        cudaFree(s.dev_in); cudaFree(s.dev_out); cudaFree(s.dev_rot); cudaFree(s.pieces); cudaFree(s.counter);
         cudaFreeHost(s.pin_in); cudaFreeHost(s.pin_out); cudaFreeHost(s.pin_rot);
         if (s.stream) cudaStreamDestroy(s.stream);
         s = Stage{};
@@ -317,7 +325,10 @@ int init_host_path(vaw_ctx* ctx)
         VAW_CUDA(ctx, cudaMalloc(&s.dev_rot, sizeof(float) * 9 * ctx->chunk_frames));
         VAW_CUDA(ctx, cudaMallocHost(&s.pin_rot, sizeof(float) * 9 * ctx->chunk_frames));
         if (ctx->variant != VAW_VARIANT_GATHER)
+        {
             VAW_CUDA(ctx, cudaMalloc(&s.pieces, sizeof(vaw::PieceRec) * ctx->pieces_per_frame * ctx->chunk_frames));
+            VAW_CUDA(ctx, cudaMalloc(&s.counter, 256));
+        }
     }
     ctx->host_ready = true;
     return VAW_OK;
@@ -366,10 +377,10 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
         return fail(nullptr, VAW_ERR_UNSUPPORTED, "only INTER_LINEAR is implemented");
     if (p.format != VAW_FORMAT_NV12 && p.format != VAW_FORMAT_BGR24 && p.format != VAW_FORMAT_GRAY8)
         return fail(nullptr, VAW_ERR_INVALID, "unknown pixel format");
-    if (p.variant < VAW_VARIANT_AUTO || p.variant > VAW_VARIANT_TILED)
+    if (p.variant < VAW_VARIANT_AUTO || p.variant > VAW_VARIANT_PIPE)
         return fail(nullptr, VAW_ERR_UNSUPPORTED, "kernel variant not available in this build");
-    if ((p.variant == VAW_VARIANT_POLY || p.variant == VAW_VARIANT_TILED) && p.format != VAW_FORMAT_NV12)
-        return fail(nullptr, VAW_ERR_UNSUPPORTED, "variants POLY and TILED exist for NV12 only");
+    if (p.variant >= VAW_VARIANT_POLY && p.format != VAW_FORMAT_NV12)
+        return fail(nullptr, VAW_ERR_UNSUPPORTED, "variants POLY, TILED and PIPE exist for NV12 only");
     // `short` indices in createMap.cl:10-11 and int16 taps in cv::remap cap both sizes
     if (p.src_width < 2 || p.src_height < 2 || p.out_width < 1 || p.out_height < 1 ||
         p.src_width > 32766 || p.src_height > 32766 || p.out_width > 32766 || p.out_height > 32766)
@@ -437,7 +448,8 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
         ctx->pieces_per_frame = (size_t)vaw::pieces_x(g.out_w) * vaw::pieces_y(g.out_h, ph);
         e = cudaEventCreateWithFlags(&ctx->table_free, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaMalloc(&ctx->dump_table, ctx->pieces_per_frame * sizeof(vaw::PieceRec));
-        if (e == cudaSuccess && ctx->variant == VAW_VARIANT_TILED && ph == vaw::kPieceHMax) {
+        if (e == cudaSuccess) e = cudaMalloc(&ctx->counter, 256);
+        if (e == cudaSuccess && (ctx->variant == VAW_VARIANT_TILED || ctx->variant == VAW_VARIANT_PIPE) && ph == vaw::kPieceHMax) {
             // size the per-CTA tile from the source boxes of the unrotated geometry, +20 % for the
             // tilt a few degrees of rotation add; more shared memory per CTA = fewer resident CTAs
             const float eye[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
@@ -482,6 +494,7 @@ void vaw_destroy(vaw_ctx* ctx)
     cudaDeviceSynchronize();
     cudaFree(ctx->table);
     cudaFree(ctx->dump_table);
+    cudaFree(ctx->counter);
     if (ctx->table_free) cudaEventDestroy(ctx->table_free);
     if (ctx->tev) {
         for (int i = 0; i < 3 * vaw_ctx::kTimeRing; ++i) cudaEventDestroy(ctx->tev[i]);
@@ -589,7 +602,7 @@ int vaw_warp_batch_host(vaw_ctx* ctx, const uint8_t* src_host, uint8_t* dst_host
             hsrc = s.pin_in;
         }
         VAW_CUDA(ctx, cudaMemcpyAsync(s.dev_in, hsrc, sfb * n, cudaMemcpyHostToDevice, s.stream));
-        rc = launch(ctx, s.dev_in, src_pitch, sfb, s.dev_out, dst_pitch, dfb, s.dev_rot, nullptr, n, s.stream, s.pieces);
+        rc = launch(ctx, s.dev_in, src_pitch, sfb, s.dev_out, dst_pitch, dfb, s.dev_rot, nullptr, n, s.stream, s.pieces, s.counter);
         if (rc) return rc;
         s.out_staged = !dst_pinned;
         if (s.out_staged && !s.pin_out) VAW_CUDA(ctx, cudaMallocHost(&s.pin_out, dfb * ctx->chunk_frames));

@@ -40,6 +40,11 @@ struct alignas(64) TileMaps {
     int tile_cap;  // bytes of shared memory for the luma + chroma tile of one CTA
     int pad[14];
 };
+// Variant PIPE (vaw_pipe.cu): persistent producer/consumer pipeline over the same tiles; `counter`
+// is one unsigned in device memory (the piece queue), reset by the launcher.
+cudaError_t launch_warp_nv12_pipe(const Geom& g, const FrameBatch& b, const PieceRec* table, unsigned* counter,
+                                  const TileMaps& maps, cudaStream_t st);
+int pipe_smem_bytes(int tile_cap);
 // bytes of tile a piece needs for its source box (what the kernel computes), 0 if it has none
 int tile_need_bytes(const PieceRec& rec);
 // dynamic shared memory of the tile kernel for a given tile capacity

@@ -1,0 +1,120 @@
+// vaw_tile.cuh -- device pieces shared by the shared-memory variants (vaw_tile.cu: one CTA per
+// piece; vaw_pipe.cu: persistent producer/consumer pipeline): the TMA tensor load, the samplers
+// that read taps from a staged tile, the pair lane mapping, the border fill.
+// Same arithmetic as vaw_poly.cuh: cv::remap's integer filter
+// (/root/reference/opencv/FrameSourceWarp.cpp:306-312) on the map of vaw_pieces.cuh.
+#pragma once
+#include <cuda.h>
+#include <stdint.h>
+#include "vaw_poly.cuh"
+
+namespace vaw {
+
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* map, int x, int y, int z, unsigned mbar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(z), "r"(mbar)
+        : "memory");
+}
+
+__device__ __forceinline__ int luma_tile(unsigned lconst, unsigned pl, float2 m)
+{
+    const int2 bb = fix_bits(m, 32.0f);
+    const int bx = bb.x, by = bb.y;
+    const unsigned a0 = (unsigned)(by >> 5) * pl + ((unsigned)(bx >> 5) + lconst);
+    const unsigned a1 = a0 + pl;
+    return blend_y(lds_u8<0>(a0), lds_u8<1>(a0), lds_u8<0>(a1), lds_u8<1>(a1), bx & 31, by & 31);
+}
+
+__device__ __forceinline__ unsigned chroma_tile(unsigned cconst, unsigned pl, float2 z)
+{
+    const int2 bb = fix_bits(z, 16.0f);
+    const int bx = bb.x, by = bb.y;
+    const unsigned a0 = (unsigned)(by >> 5) * pl + (((unsigned)(bx >> 5) + cconst) << 1);
+    const unsigned a1 = a0 + pl;
+    return blend_uv(lds_u16<0>(a0), lds_u16<2>(a0), lds_u16<0>(a1), lds_u16<2>(a1), bx & 31, by & 31);
+}
+
+// Lane -> column mapping of the staged path: lane l owns luma columns 2l, 2l+1 and 64+2l, 64+2l+1
+// of the piece (slot j -> column 2l + (j & 1) + 64 (j >> 1)).  One LDS instruction then serves 32
+// pixels that are 2 columns apart: at the C3 centre (1.84 source px per output px) its addresses
+// span 118 bytes = 30 banks, i.e. one shared-memory wavefront.  With four consecutive columns per
+// lane the same instruction spans 236 bytes and needs two or more (measured 2.5 wavefronts per
+// LDS, shared-memory pipe 72 % busy).  Quads (j = 0,1 and j = 2,3) stay inside a lane, so the NV12
+// chroma rule needs no shuffles; stores become 2 bytes per lane (64 contiguous bytes per warp).
+__device__ __forceinline__ int pair_column(int lane, int j) { return 2 * lane + (j & 1) + 64 * (j >> 1); }
+
+template <bool kRagged>
+__device__ __forceinline__ void store_pair(uint8_t* p, unsigned lo, unsigned hi, bool inside)
+{
+    if (!kRagged) {
+        *reinterpret_cast<uint16_t*>(p) = (uint16_t)(lo | (hi << 8));
+    } else if (inside) {
+        p[0] = (uint8_t)lo;
+        p[1] = (uint8_t)hi;
+    }
+}
+
+// nrows (even) rows starting at piece row dv0, taps from the staged tile.  o.y0 / o.y1 / o.c point
+// at column 2*lane of the piece.
+template <bool kRagged>
+__device__ __forceinline__ void rows_tile(const Geom& g, const ColPoly& cp, unsigned lconst, unsigned cconst,
+                                          unsigned pl, int dv0, int nrows, RowPtrs& o, bool in_a, bool in_b)
+{
+    // t = (dv - t_off) * t_scale is a small dyadic rational: stepping it by t_scale is exact
+    float t = row_t(g, dv0);
+    const float dt = g.t_scale, dt2 = __fadd_rn(g.t_scale, g.t_scale);
+#pragma unroll 1
+    for (int dv = dv0; dv < dv0 + nrows; dv += 2) {
+        float2 m[2][4];
+        row_coords(cp, t, m[0]);
+        row_coords(cp, __fadd_rn(t, dt), m[1]);
+        t = __fadd_rn(t, dt2);
+        unsigned y[2][4];
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) y[r][i] = (unsigned)luma_tile(lconst, pl, m[r][i]) >> 10;
+        unsigned c[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+            c[q] = chroma_tile(cconst, pl, chroma_z(m[0][2 * q], m[0][2 * q + 1], m[1][2 * q], m[1][2 * q + 1]));
+        store_pair<kRagged>(o.y0, y[0][0], y[0][1], in_a);
+        store_pair<kRagged>(o.y0 + 64, y[0][2], y[0][3], in_b);
+        store_pair<kRagged>(o.y1, y[1][0], y[1][1], in_a);
+        store_pair<kRagged>(o.y1 + 64, y[1][2], y[1][3], in_b);
+        store_pair<kRagged>(o.c, c[0] & 255u, c[0] >> 8, in_a);
+        store_pair<kRagged>(o.c + 64, c[1] & 255u, c[1] >> 8, in_b);
+        o.y0 += o.step_y; o.y1 += o.step_y; o.c += o.step_c;
+    }
+}
+
+// Overwrite the cells of a staged plane that lie outside the source with the border value.
+// Tile row r <-> source row y0 + r (valid in [0, n_rows)); tile byte c <-> source byte x0 + c
+// (valid in [0, n_bytes)); `pattern` = the border replicated over 4 bytes (x0 is a multiple of 4).
+// Only the outside rows and the outside column strips are visited.
+__device__ __forceinline__ void fill_border(uint8_t* tile, int pl, int tile_rows, int y0, int n_rows, int x0,
+                                            int n_bytes, unsigned pattern, int tid, int nthr)
+{
+    const int wpr = pl >> 2;                                  // words per tile row
+    const int r_lo = min(max(-y0, 0), tile_rows);             // rows [0, r_lo) are above the plane
+    const int r_hi = min(max(n_rows - y0, r_lo), tile_rows);  // rows [r_hi, tile_rows) are below it
+    unsigned* w = reinterpret_cast<unsigned*>(tile);
+    for (int idx = tid; idx < r_lo * wpr; idx += nthr) w[idx] = pattern;
+    for (int idx = r_hi * wpr + tid; idx < tile_rows * wpr; idx += nthr) w[idx] = pattern;
+    const int c_lo = min(max(-x0, 0), pl);                    // bytes [0, c_lo) are left of the plane
+    const int c_hi = min(max(n_bytes - x0, c_lo), pl);        // bytes [c_hi, pl) are right of it
+    const int strip = c_lo + (pl - c_hi);                     // outside bytes per inside row
+    if (strip > 0) {
+        const int total = (r_hi - r_lo) * strip;
+        for (int idx = tid; idx < total; idx += nthr) {
+            const int r = idx / strip, k = idx - r * strip;
+            const int c = k < c_lo ? k : c_hi + (k - c_lo);
+            tile[(r_lo + r) * pl + c] = (uint8_t)(pattern >> (8 * (c & 3)));
+        }
+    }
+}
+
+
+}  // namespace vaw
