@@ -247,9 +247,8 @@ int launch(vaw_ctx* ctx, const uint8_t* src, int src_pitch, size_t src_stride, u
     b.rots = rots;
     if (rot0) b.rot0 = *rot0;
     const bool poly = ctx->p.format == VAW_FORMAT_NV12 && ctx->variant != VAW_VARIANT_GATHER;
-    const bool tiled = (ctx->variant == VAW_VARIANT_TILED || ctx->variant == VAW_VARIANT_PIPE) &&
-                       ctx->g.piece_h == vaw::kPieceHMax;
-    const bool piped = tiled && ctx->variant == VAW_VARIANT_PIPE &&
+    const bool tiled = ctx->variant == VAW_VARIANT_TILED || ctx->variant == VAW_VARIANT_PIPE;
+    const bool piped = ctx->variant == VAW_VARIANT_PIPE && ctx->g.piece_h == vaw::kPieceHMax &&
                        vaw::pipe_smem_bytes(ctx->tile_cap) <= (227 << 10);
     // grid.z is limited to 65535 frames per launch
     for (int first = 0; first < n_frames; first += 65535) {
@@ -449,7 +448,7 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
         e = cudaEventCreateWithFlags(&ctx->table_free, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaMalloc(&ctx->dump_table, ctx->pieces_per_frame * sizeof(vaw::PieceRec));
         if (e == cudaSuccess) e = cudaMalloc(&ctx->counter, 256);
-        if (e == cudaSuccess && (ctx->variant == VAW_VARIANT_TILED || ctx->variant == VAW_VARIANT_PIPE) && ph == vaw::kPieceHMax) {
+        if (e == cudaSuccess && (ctx->variant == VAW_VARIANT_TILED || ctx->variant == VAW_VARIANT_PIPE)) {
             // size the per-CTA tile from the source boxes of the unrotated geometry, +20 % for the
             // tilt a few degrees of rotation add; more shared memory per CTA = fewer resident CTAs
             const float eye[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};

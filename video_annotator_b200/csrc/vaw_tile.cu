@@ -38,7 +38,6 @@ namespace vaw {
 namespace {
 
 constexpr int kWarps = 4;
-constexpr int kRowsPerWarp = kPieceHMax / kWarps;  // 8
 #ifndef VAW_TILE_CTAS
 #define VAW_TILE_CTAS 6  // resident CTAs per SM the kernel is sized for (registers and shared memory)
 #endif
@@ -55,13 +54,14 @@ warp_nv12_tile_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
     extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x, w = threadIdx.y, tid = w * 32 + lane;
     const int px = blockIdx.x, py = blockIdx.y, frame = blockIdx.z;
-    const int npx = pieces_x(g.out_w), npy = pieces_y(g.out_h, kPieceHMax);
+    const int ph = g.piece_h, rows_per_warp = ph / kWarps;  // 32 / 16 / 8 rows per piece -> 8 / 4 / 2 per warp
+    const int npx = pieces_x(g.out_w), npy = pieces_y(g.out_h, ph);
     const PieceRec* rec = table + ((size_t)frame * npy + py) * npx + px;
     const unsigned flags = __ldg(&rec->flags);
-    const int u_lo = px * kPieceW, u0 = u_lo + 4 * lane, v_base = py * kPieceHMax;
-    const int rows = min(kPieceHMax, g.out_h - v_base);  // even for NV12
-    const int dv0 = w * kRowsPerWarp;
-    const int my_rows = max(0, min(kRowsPerWarp, rows - dv0));
+    const int u_lo = px * kPieceW, u0 = u_lo + 4 * lane, v_base = py * ph;
+    const int rows = min(ph, g.out_h - v_base);  // even for NV12
+    const int dv0 = w * rows_per_warp;
+    const int my_rows = max(0, min(rows_per_warp, rows - dv0));
     const int valid = g.out_w - u0;
 
     PlaneRefs f;
@@ -221,7 +221,7 @@ cudaError_t launch_warp_nv12_tile(const Geom& g, const FrameBatch& b, const Piec
         configured[dev] = true;
     }
     dim3 block(32, kWarps);
-    dim3 grid(pieces_x(g.out_w), pieces_y(g.out_h, kPieceHMax), b.n_frames);
+    dim3 grid(pieces_x(g.out_w), pieces_y(g.out_h, g.piece_h), b.n_frames);
     warp_nv12_tile_kernel<<<grid, block, tile_smem_bytes(maps.tile_cap), st>>>(g, b, table, maps);
     return cudaGetLastError();
 }
