@@ -21,8 +21,8 @@ static_assert(sizeof(vaw_params) == 128 && sizeof(vaw_camera) == 120, "C-ABI str
 
 namespace {
 
-constexpr int kStages = 3;                      // host-path pipeline depth
-constexpr size_t kChunkBytes = 96u << 20;       // target bytes of source frames per chunk
+constexpr int kStages = 4;                      // host-path pipeline depth
+constexpr size_t kChunkBytes = 32u << 20;       // target bytes of source frames per chunk (small: short pipeline fill and drain)
 thread_local std::string g_create_error;
 
 struct Stage {
@@ -186,18 +186,17 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 EncodeTiledFn encode_tiled()
 {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    // function-local static: initialised once, thread-safe (several host threads create contexts
+    // concurrently in the clip scheduler)
+    static const EncodeTiledFn fn = []() -> EncodeTiledFn {
         void* p = nullptr;
         cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
             q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-        else
-            cudaGetLastError();
-    }
+            return reinterpret_cast<EncodeTiledFn>(p);
+        cudaGetLastError();
+        return nullptr;
+    }();
     return fn;
 }
 

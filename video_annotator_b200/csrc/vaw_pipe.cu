@@ -309,7 +309,7 @@ int pipe_smem_bytes(int tile_cap) { return kStageOffset + kStages * stage_bytes(
 cudaError_t launch_warp_nv12_pipe(const Geom& g, const FrameBatch& b, const PieceRec* table, unsigned* counter,
                                   const TileMaps& maps, cudaStream_t st)
 {
-    static bool configured[64] = {};
+    static bool configured[64] = {};  // per device; a benign race: the attribute call is idempotent
     static int sm_count[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);

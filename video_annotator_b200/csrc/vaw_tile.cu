@@ -211,7 +211,7 @@ int tile_need_bytes(const PieceRec& rec)
 cudaError_t launch_warp_nv12_tile(const Geom& g, const FrameBatch& b, const PieceRec* table, const TileMaps& maps,
                                   cudaStream_t st)
 {
-    static bool configured[64] = {};
+    static bool configured[64] = {};  // per device; a benign race: the attribute call is idempotent
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !configured[dev]) {
