@@ -615,6 +615,63 @@ def test_variants_produce_identical_batches(V, name, n):
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
 
 
+def test_many_buffers_and_two_streams_on_one_context(V, oracle):
+    """One context, six different source buffers (more than the tensor-map cache holds) and two CUDA
+    streams used alternately: the piece table is rebuilt per call and ordered across streams by an
+    event, so every call must produce what a fresh context produces."""
+    import torch
+    from video_annotator_b200 import configs
+    w = configs.workload("C3")
+    sw, sh = w.src_size
+    rots = w.rotations(6, first=60, total=200)
+    ctx = V.WarpContext(w.input_camera, w.output_camera, out_size=w.out_size)
+    srcs = [torch.empty(ctx.frame_shape("src"), dtype=torch.uint8, device="cuda") for _ in range(6)]
+    for i, s_ in enumerate(srcs):
+        V.synth_nv12(s_, sw, sh, 1, first_index=10 + i, white_noise=True)
+    torch.cuda.synchronize()
+    want = []
+    for i in range(6):
+        ref = V.WarpContext(w.input_camera, w.output_camera, out_size=w.out_size)
+        d = torch.empty(ctx.frame_shape("dst"), dtype=torch.uint8, device="cuda")
+        ref.warp(srcs[i], d, rots[i])
+        torch.cuda.synchronize()
+        want.append(d)
+        ref.close()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    outs = [torch.zeros(ctx.frame_shape("dst"), dtype=torch.uint8, device="cuda") for _ in range(6)]
+    for rep in range(3):
+        for i in range(6):
+            st = streams[(i + rep) & 1]
+            ctx.warp(srcs[i], outs[i], rots[i], stream=st.cuda_stream)
+    torch.cuda.synchronize()
+    for i in range(6):
+        assert torch.equal(outs[i], want[i]), i
+    ctx.close()
+
+
+def test_empty_batch_and_single_frame_batch(V):
+    import torch
+    from video_annotator_b200 import configs
+    w = configs.workload("C2")
+    ctx = V.WarpContext(w.input_camera, w.output_camera, out_size=w.out_size)
+    sw, sh = w.src_size
+    src = torch.empty((1,) + ctx.frame_shape("src"), dtype=torch.uint8, device="cuda")
+    V.synth_nv12(src, sw, sh, 1)
+    rdev = torch.empty(9, dtype=torch.float32, device="cuda")
+    rot = w.rotations(1, first=33, total=80)
+    ctx.upload_rotations(rot, rdev)
+    dst = torch.full((1,) + ctx.frame_shape("dst"), 0x77, dtype=torch.uint8, device="cuda")
+    ctx.warp_batch(src, dst, rdev, 0)                      # empty batch: nothing is touched
+    torch.cuda.synchronize()
+    assert int((dst != 0x77).sum()) == 0
+    ctx.warp_batch(src, dst, rdev, 1)
+    single = torch.empty(ctx.frame_shape("dst"), dtype=torch.uint8, device="cuda")
+    ctx.warp(src[0], single, rot[0])
+    torch.cuda.synchronize()
+    assert torch.equal(dst[0], single)
+    ctx.close()
+
+
 # ---- error convention ----------------------------------------------------------------------------
 def test_error_codes(V):
     import torch
