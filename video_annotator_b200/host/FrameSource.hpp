@@ -28,23 +28,14 @@ using Frame = std::shared_ptr<DeviceFrame>;  // stands in for cv::UMat (ref-coun
 
 Frame make_device_frame(int device, int format, int width, int height);  // throws int on failure
 
-/**
- * A source of frames
- */
+// One stage of the pull pipeline.  Contract as in the reference (FrameSource.hpp:9-24):
+//   pull_frame  hands out the next frame and moves on;
+//   peek_frame  hands out the next frame and stays where it is;
+// both throw when nothing can be delivered -- `throw EOF` (an int) at the end of the stream.
 class FrameSource {
   public:
-    /**
-     * Return the next frame and advance the current position
-     * Raises an exception if no frames are ready
-     */
     virtual Frame pull_frame() = 0;
-
-    /**
-     * Return the next frame but do not advance the current position
-     * Raises an exception if no frames are ready
-     */
     virtual Frame peek_frame() = 0;
-
     virtual ~FrameSource() = default;
 };
 

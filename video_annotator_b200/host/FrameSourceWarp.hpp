@@ -83,10 +83,9 @@ class RotationFilter {
     Mat33 filter() const;
 };
 
-/**
- * FrameSourceWarp is a video processor that accepts a stream of input video frames
- * and metadata and applies reprojection and stabilisation on them
- */
+// The stabilise-and-reproject stage: pulls frames from `source`, smooths the camera path over a
+// look-ahead window and hands out each frame re-projected (fisheye -> rectilinear) under the
+// rotation that cancels the shake.  Class and member names follow FrameSourceWarp.hpp:40-94.
 class FrameSourceWarp : public FrameSource {
     std::shared_ptr<FrameSource> m_source;
     std::shared_ptr<RotationSource> m_rotation_source;
