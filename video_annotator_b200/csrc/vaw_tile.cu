@@ -169,7 +169,9 @@ warp_nv12_tile_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
     }
     cp.base = load_base(rec);
 
+#ifndef VAW_ABL_NO_TMA_WAIT
     mbar_wait(mbar, 0);  // the tile has landed
+#endif
 
     if (!(flags & kPieceInterior)) {  // straddles the frame border: paint the outside cells
         const unsigned by_ = g.border & 255u, bu = (g.border >> 8) & 255u, bv = (g.border >> 16) & 255u;

@@ -24,7 +24,11 @@ __device__ __forceinline__ int luma_tile(unsigned lconst, unsigned pl, float2 m)
     const int bx = bb.x, by = bb.y;
     const unsigned a0 = (unsigned)(by >> 5) * pl + ((unsigned)(bx >> 5) + lconst);
     const unsigned a1 = a0 + pl;
+#ifdef VAW_ABL_NO_LDS  // analysis only: taps derived from the address instead of loaded
+    return blend_y(a0 & 255, (a0 >> 1) & 255, a1 & 255, (a1 >> 3) & 255, bx & 31, by & 31);
+#else
     return blend_y(lds_u8<0>(a0), lds_u8<1>(a0), lds_u8<0>(a1), lds_u8<1>(a1), bx & 31, by & 31);
+#endif
 }
 
 __device__ __forceinline__ unsigned chroma_tile(unsigned cconst, unsigned pl, float2 z)
@@ -33,7 +37,11 @@ __device__ __forceinline__ unsigned chroma_tile(unsigned cconst, unsigned pl, fl
     const int bx = bb.x, by = bb.y;
     const unsigned a0 = (unsigned)(by >> 5) * pl + (((unsigned)(bx >> 5) + cconst) << 1);
     const unsigned a1 = a0 + pl;
+#ifdef VAW_ABL_NO_LDS
+    return blend_uv(a0 & 0xffff, (a0 >> 1) & 0xffff, a1 & 0xffff, (a1 >> 3) & 0xffff, bx & 31, by & 31);
+#else
     return blend_uv(lds_u16<0>(a0), lds_u16<2>(a0), lds_u16<0>(a1), lds_u16<2>(a1), bx & 31, by & 31);
+#endif
 }
 
 // Lane -> column mapping of the staged path: lane l owns luma columns 2l, 2l+1 and 64+2l, 64+2l+1
@@ -79,13 +87,22 @@ __device__ __forceinline__ void rows_tile(const Geom& g, const ColPoly& cp, unsi
         unsigned c[2];
 #pragma unroll
         for (int q = 0; q < 2; ++q)
+#ifdef VAW_ABL_NO_CHROMA
+            c[q] = y[0][q] | (y[1][q] << 8);
+#else
             c[q] = chroma_tile(cconst, pl, chroma_z(m[0][2 * q], m[0][2 * q + 1], m[1][2 * q], m[1][2 * q + 1]));
+#endif
+#ifdef VAW_ABL_NO_STORE  // analysis only: results stay live, (almost) nothing is written
+        if ((y[0][0] ^ y[0][1] ^ y[0][2] ^ y[0][3] ^ y[1][0] ^ y[1][1] ^ y[1][2] ^ y[1][3] ^ c[0] ^ c[1]) == 0x12345u)
+#endif
+        {
         store_pair<kRagged>(o.y0, y[0][0], y[0][1], in_a);
         store_pair<kRagged>(o.y0 + 64, y[0][2], y[0][3], in_b);
         store_pair<kRagged>(o.y1, y[1][0], y[1][1], in_a);
         store_pair<kRagged>(o.y1 + 64, y[1][2], y[1][3], in_b);
         store_pair<kRagged>(o.c, c[0] & 255u, c[0] >> 8, in_a);
         store_pair<kRagged>(o.c + 64, c[1] & 255u, c[1] >> 8, in_b);
+        }
         o.y0 += o.step_y; o.y1 += o.step_y; o.c += o.step_c;
     }
 }
