@@ -70,15 +70,25 @@ __device__ __forceinline__ void derive(const PieceRec* __restrict__ rec, int lan
 }
 
 // fp32 coordinates (x, y) of the lane's 4 columns on one row; t = (dv - t_off) * t_scale (exact).
+#ifndef VAW_SCALAR_COLS
+#define VAW_SCALAR_COLS 0  // analysis: evaluate the last N column slots with scalar FFMA instead of FFMA2
+#endif
 __device__ __forceinline__ void row_coords(const ColPoly& cp, float t, float2 (&m)[4])
 {
     const float2 tt = pair(t);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        float2 p = __ffma2_rn(cp.a[j][3], tt, cp.a[j][2]);
-        p = __ffma2_rn(p, tt, cp.a[j][1]);
-        p = __ffma2_rn(p, tt, cp.a[j][0]);
-        m[j] = __fadd2_rn(cp.base, p);  // the map value: rounded once to fp32
+        if (j >= 4 - VAW_SCALAR_COLS) {
+            float px = __fmaf_rn(cp.a[j][3].x, t, cp.a[j][2].x), py = __fmaf_rn(cp.a[j][3].y, t, cp.a[j][2].y);
+            px = __fmaf_rn(px, t, cp.a[j][1].x); py = __fmaf_rn(py, t, cp.a[j][1].y);
+            px = __fmaf_rn(px, t, cp.a[j][0].x); py = __fmaf_rn(py, t, cp.a[j][0].y);
+            m[j] = make_float2(__fadd_rn(cp.base.x, px), __fadd_rn(cp.base.y, py));
+        } else {
+            float2 p = __ffma2_rn(cp.a[j][3], tt, cp.a[j][2]);
+            p = __ffma2_rn(p, tt, cp.a[j][1]);
+            p = __ffma2_rn(p, tt, cp.a[j][0]);
+            m[j] = __fadd2_rn(cp.base, p);  // the map value: rounded once to fp32
+        }
     }
 }
 
