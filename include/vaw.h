@@ -250,6 +250,9 @@ int vaw_kernel_times(vaw_ctx *ctx, int max_launches, float *builder_ms, float *w
  * All zero for GATHER. */
 int vaw_piece_stats(vaw_ctx *ctx, const double rotation[9], uint32_t counts[8], void *stream);
 int vaw_selftest_math(int device, uint32_t seed, uint64_t n_per_thread, uint64_t mismatches[4]);
+/* Instrumented builds only (-DVAW_BOUNDS_CHECK): number of shared-memory tap addresses of variant
+ * TILED that fell outside their staged tile since the library was loaded; -1 in a normal build. */
+long long vaw_debug_oob_count(int device);
 
 #ifdef __cplusplus
 }

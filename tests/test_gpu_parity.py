@@ -689,3 +689,12 @@ def test_error_codes(V):
         V.WarpContext(cin, cout, device=99)
     assert e.value.code == -2
     ctx.close()
+
+
+def test_zz_no_tap_left_its_tile(V):
+    """Runs last.  In the instrumented build (VAW_DEFINES=VAW_BOUNDS_CHECK=1, tools/gpu_boundscheck.sh)
+    every shared-memory tap address of every TILED launch of this test session was range-checked; in
+    the normal build the entry point reports -1 and there is nothing to assert."""
+    n = V.load().vaw_debug_oob_count(0)
+    assert n in (-1, 0), f"{n} taps outside their staged tile"
+    _record("oob_taps", {"count": int(n), "instrumented": n >= 0})

@@ -641,6 +641,12 @@ int vaw_dump_coords(vaw_ctx* ctx, const double rotation[9], int plane, float* ma
     return VAW_OK;
 }
 
+long long vaw_debug_oob_count(int device)
+{
+    DeviceGuard dg(device);
+    return vaw::tile_oob_count();
+}
+
 int vaw_malloc(int device, size_t bytes, void** out)
 {
     if (!out) return VAW_ERR_INVALID;

@@ -49,6 +49,8 @@ int pipe_smem_bytes(int tile_cap);
 int tile_need_bytes(const PieceRec& rec);
 // dynamic shared memory of the tile kernel for a given tile capacity
 int tile_smem_bytes(int tile_cap);
+// out-of-tile tap count of the instrumented build (-DVAW_BOUNDS_CHECK), -1 when not instrumented
+long long tile_oob_count();
 // Needs piece_h == 32.
 cudaError_t launch_warp_nv12_tile(const Geom& g, const FrameBatch& b, const PieceRec* table, const TileMaps& maps,
                                   cudaStream_t st);

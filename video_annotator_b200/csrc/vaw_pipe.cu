@@ -295,8 +295,10 @@ warp_nv12_pipe_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
                 const int shift = 2 * lane - 4 * lane;  // the staged path uses the pair mapping
                 o.y0 += shift; o.y1 += shift; o.c += shift;
                 const bool in_a = u_lo + 2 * lane < g.out_w, in_b = u_lo + 64 + 2 * lane < g.out_w;
-                if (even_ok && u_lo + kPieceW <= g.out_w) rows_tile<false>(g, cp, lconst, cconst, upl, dv0, my_rows, o, in_a, in_b);
-                else rows_tile<true>(g, cp, lconst, cconst, upl, dv0, my_rows, o, in_a, in_b);
+                const TileBounds tb = {smem_u32(ltile), smem_u32(ltile) + (unsigned)(head.nr8 * pl), smem_u32(ctile),
+                                       smem_u32(ctile) + (unsigned)(head.cnr8 * pl)};
+                if (even_ok && u_lo + kPieceW <= g.out_w) rows_tile<false>(g, cp, lconst, cconst, upl, dv0, my_rows, o, in_a, in_b, tb);
+                else rows_tile<true>(g, cp, lconst, cconst, upl, dv0, my_rows, o, in_a, in_b, tb);
             }
         }
         __syncwarp();

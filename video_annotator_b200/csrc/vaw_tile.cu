@@ -191,8 +191,21 @@ warp_nv12_tile_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
     const bool in_a = u_lo + 2 * lane < g.out_w, in_b = u_lo + 64 + 2 * lane < g.out_w;  // widths are even
     const bool pair_ok = ((reinterpret_cast<uintptr_t>(f.dst) | (uintptr_t)g.dst_pitch) & 1) == 0 &&
                          u_lo + kPieceW <= g.out_w;
-    if (pair_ok) rows_tile<false>(g, cp, lconst, cconst, upl, dv0, my_rows, o, in_a, in_b);
-    else rows_tile<true>(g, cp, lconst, cconst, upl, dv0, my_rows, o, in_a, in_b);
+    const TileBounds tb = {smem_u32(ltile), smem_u32(ltile) + (unsigned)(nr8 * pl), smem_u32(ctile),
+                           smem_u32(ctile) + (unsigned)(cnr8 * pl)};
+    if (pair_ok) rows_tile<false>(g, cp, lconst, cconst, upl, dv0, my_rows, o, in_a, in_b, tb);
+    else rows_tile<true>(g, cp, lconst, cconst, upl, dv0, my_rows, o, in_a, in_b, tb);
+}
+
+long long tile_oob_count()
+{
+#ifdef VAW_BOUNDS_CHECK
+    unsigned long long v = 0;
+    if (cudaMemcpyFromSymbol(&v, g_oob_taps, sizeof v) != cudaSuccess) return -2;
+    return (long long)v;
+#else
+    return -1;
+#endif
 }
 
 int tile_smem_bytes(int tile_cap) { return kTileOffset + tile_cap; }

@@ -18,12 +18,27 @@ __device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* map
         : "memory");
 }
 
-__device__ __forceinline__ int luma_tile(unsigned lconst, unsigned pl, float2 m)
+// Instrumented build (-DVAW_BOUNDS_CHECK, tests only: compute-sanitizer is not available on the GPU
+// pool): every tap address of the staged samplers is checked against the plane's tile and counted
+// when it falls outside; vaw_debug_oob_count() returns the count (-1 when not instrumented).
+struct TileBounds { unsigned l_lo, l_hi, c_lo, c_hi; };  // shared-memory byte ranges [lo, hi)
+#ifdef VAW_BOUNDS_CHECK
+static __device__ unsigned long long g_oob_taps;
+__device__ __forceinline__ void check_taps(unsigned a0, unsigned a1, unsigned width, unsigned lo, unsigned hi)
+{
+    if (a0 < lo || a0 + width > hi || a1 < lo || a1 + width > hi) atomicAdd(&g_oob_taps, 1ull);
+}
+#endif
+
+__device__ __forceinline__ int luma_tile(unsigned lconst, unsigned pl, float2 m, const TileBounds& tb)
 {
     const int2 bb = fix_bits(m, 32.0f);
     const int bx = bb.x, by = bb.y;
     const unsigned a0 = (unsigned)(by >> 5) * pl + ((unsigned)(bx >> 5) + lconst);
     const unsigned a1 = a0 + pl;
+#ifdef VAW_BOUNDS_CHECK
+    check_taps(a0, a1, 2u, tb.l_lo, tb.l_hi);
+#endif
 #ifdef VAW_ABL_NO_LDS  // analysis only: taps derived from the address instead of loaded
     return blend_y(a0 & 255, (a0 >> 1) & 255, a1 & 255, (a1 >> 3) & 255, bx & 31, by & 31);
 #else
@@ -31,12 +46,15 @@ __device__ __forceinline__ int luma_tile(unsigned lconst, unsigned pl, float2 m)
 #endif
 }
 
-__device__ __forceinline__ unsigned chroma_tile(unsigned cconst, unsigned pl, float2 z)
+__device__ __forceinline__ unsigned chroma_tile(unsigned cconst, unsigned pl, float2 z, const TileBounds& tb)
 {
     const int2 bb = fix_bits(z, 16.0f);
     const int bx = bb.x, by = bb.y;
     const unsigned a0 = (unsigned)(by >> 5) * pl + (((unsigned)(bx >> 5) + cconst) << 1);
     const unsigned a1 = a0 + pl;
+#ifdef VAW_BOUNDS_CHECK
+    check_taps(a0, a1, 4u, tb.c_lo, tb.c_hi);
+#endif
 #ifdef VAW_ABL_NO_LDS
     return blend_uv(a0 & 0xffff, (a0 >> 1) & 0xffff, a1 & 0xffff, (a1 >> 3) & 0xffff, bx & 31, by & 31);
 #else
@@ -68,7 +86,8 @@ __device__ __forceinline__ void store_pair(uint8_t* p, unsigned lo, unsigned hi,
 // at column 2*lane of the piece.
 template <bool kRagged>
 __device__ __forceinline__ void rows_tile(const Geom& g, const ColPoly& cp, unsigned lconst, unsigned cconst,
-                                          unsigned pl, int dv0, int nrows, RowPtrs& o, bool in_a, bool in_b)
+                                          unsigned pl, int dv0, int nrows, RowPtrs& o, bool in_a, bool in_b,
+                                          const TileBounds& tb)
 {
     // t = (dv - t_off) * t_scale is a small dyadic rational: stepping it by t_scale is exact
     float t = row_t(g, dv0);
@@ -83,14 +102,14 @@ __device__ __forceinline__ void rows_tile(const Geom& g, const ColPoly& cp, unsi
 #pragma unroll
         for (int r = 0; r < 2; ++r)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) y[r][i] = (unsigned)luma_tile(lconst, pl, m[r][i]) >> 10;
+            for (int i = 0; i < 4; ++i) y[r][i] = (unsigned)luma_tile(lconst, pl, m[r][i], tb) >> 10;
         unsigned c[2];
 #pragma unroll
         for (int q = 0; q < 2; ++q)
 #ifdef VAW_ABL_NO_CHROMA
             c[q] = y[0][q] | (y[1][q] << 8);
 #else
-            c[q] = chroma_tile(cconst, pl, chroma_z(m[0][2 * q], m[0][2 * q + 1], m[1][2 * q], m[1][2 * q + 1]));
+            c[q] = chroma_tile(cconst, pl, chroma_z(m[0][2 * q], m[0][2 * q + 1], m[1][2 * q], m[1][2 * q + 1]), tb);
 #endif
 #ifdef VAW_ABL_NO_STORE  // analysis only: results stay live, (almost) nothing is written
         if ((y[0][0] ^ y[0][1] ^ y[0][2] ^ y[0][3] ^ y[1][0] ^ y[1][1] ^ y[1][2] ^ y[1][3] ^ c[0] ^ c[1]) == 0x12345u)
