@@ -20,7 +20,7 @@ namespace {
 constexpr int kChunk = 32;                       // pieces per CTA along u
 constexpr int kNodesU = kChunk * kDegU + 1;      // 161 shared nodes
 #ifndef VAW_BUILDER_THREADS
-#define VAW_BUILDER_THREADS 192  // small CTAs: the kernel is latency-bound (measured 76 us vs 80 at 256, 96 at 320)
+#define VAW_BUILDER_THREADS 128  // small CTAs: the kernel is latency-bound (C3, 64 frames: 65 us at 128, 69 at 160, 76 at 192, 80 at 256 and at 64)
 #endif
 constexpr int kThreads = VAW_BUILDER_THREADS;
 
