@@ -17,7 +17,10 @@ namespace vaw {
 
 namespace {
 
-constexpr int kChunk = 32;                       // pieces per CTA along u
+#ifndef VAW_BUILDER_CHUNK
+#define VAW_BUILDER_CHUNK 32
+#endif
+constexpr int kChunk = VAW_BUILDER_CHUNK;        // pieces per CTA along u
 constexpr int kNodesU = kChunk * kDegU + 1;      // 161 shared nodes
 #ifndef VAW_BUILDER_THREADS
 #define VAW_BUILDER_THREADS 128  // small CTAs: the kernel is latency-bound (C3, 64 frames: 65 us at 128, 69 at 160, 76 at 192, 80 at 256 and at 64)
