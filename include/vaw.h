@@ -66,13 +66,20 @@ enum { VAW_INTER_NEAREST = 0, VAW_INTER_LINEAR = 1, VAW_INTER_CUBIC = 2 };
  *   PIPE    TILED's tiles, scheduled as a persistent producer/consumer pipeline: a producer warp
  *           per CTA pulls pieces from a global queue and issues the TMA loads two pieces ahead,
  *           four consumer warps sample; the record and tile latencies disappear behind compute.
+ *   TEX     TILED, except that pieces certified interior (every tap inside the source) are filtered
+ *           by the texture units: the coordinate is rounded to 1/32 px exactly as cv::remap rounds
+ *           it, the unit's 8-bit fractional weights represent k/32 exactly, and the filtered value
+ *           is rescaled and rounded half up like (sum + 512) >> 10.  Needs a texture-aligned source
+ *           base (512 bytes), a pitch that is a multiple of 32 and a frame stride that is a whole
+ *           number of rows; other layouts run as TILED.
  * POLY, TILED and PIPE produce identical bytes.  AUTO = TILED for NV12, GATHER for the packed formats. */
 enum {
     VAW_VARIANT_AUTO = 0,
     VAW_VARIANT_GATHER = 1,
     VAW_VARIANT_POLY = 2,
     VAW_VARIANT_TILED = 3,
-    VAW_VARIANT_PIPE = 4
+    VAW_VARIANT_PIPE = 4,
+    VAW_VARIANT_TEX = 5
 };
 
 /* ---- parameters -------------------------------------------------------------------
@@ -242,6 +249,8 @@ int vaw_set_option(vaw_ctx *ctx, const char *name, int value);
  * vaw_kernel_times returns the most recent launches' durations in milliseconds, oldest first
  * (it waits for them).  This is what bench.py's roofline line is computed from. */
 int vaw_kernel_times(vaw_ctx *ctx, int max_launches, float *builder_ms, float *warp_ms, int *n_out);
+/* The same launches' warp time split into the texture kernel (variant TEX, else ~0) and the tile kernel. */
+int vaw_kernel_times_split(vaw_ctx *ctx, int max_launches, float *tex_ms, float *tile_ms, int *n_out);
 
 /* Variant POLY: how the 128x32-pixel pieces of the output classify for `rotation`:
  * counts = {pieces, with a certified polynomial, of those fully inside the source, of those

@@ -60,6 +60,7 @@ SIGNATURES = {
     "vaw_memcpy": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "vaw_sync": (C.c_int, [C.c_int, C.c_void_p]),
     "vaw_kernel_times": (C.c_int, [C.c_void_p, C.c_int, f32p, f32p, C.POINTER(C.c_int)]),
+    "vaw_kernel_times_split": (C.c_int, [C.c_void_p, C.c_int, f32p, f32p, C.POINTER(C.c_int)]),
     "vaw_shard_range": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "vaw_clip_create": (C.c_int, [C.POINTER(VawParams), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p)]),
     "vaw_clip_destroy": (None, [C.c_void_p]),

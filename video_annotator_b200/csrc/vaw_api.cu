@@ -64,11 +64,18 @@ struct vaw_ctx {
     MapEntry map_cache[4];
     int map_next = 0;
     int tile_cap = 32 << 10;  // chosen at creation from the pieces' source boxes
+    // variant TEX: texture objects over the clip, cached per source layout
+    struct TexEntry { const void* src = nullptr; int pitch = 0; size_t stride = 0; int frames = 0; vaw::TexSet set{}; int n_groups = 0; };
+    static constexpr int kTexCache = 8;
+    TexEntry tex_cache[kTexCache];
+    int tex_next = 0;
+    int tex_align = 512, tex_pitch_align = 32;
     unsigned* counter = nullptr;  // piece queue of variant PIPE (for ctx->table)
     // option "time_kernels": CUDA-event stamps around the kernels of every launch (bench.py's roofline)
     static constexpr int kTimeRing = 512;
     bool time_kernels = false;
-    cudaEvent_t* tev = nullptr;  // 3 per launch: start, after the table builder, after the warp kernel
+    cudaEvent_t* tev = nullptr;  // 4 per launch: start, after the table builder, after the texture kernel, after the warp kernel
+    static constexpr int kTev = 4;
     uint64_t timed_launches = 0;
     // host path
     Stage stage[kStages];
@@ -231,6 +238,86 @@ const vaw::TileMaps& tile_maps(vaw_ctx* ctx, const uint8_t* src, int pitch, size
     return e.maps;
 }
 
+void destroy_tex_entry(vaw_ctx::TexEntry& e)
+{
+    for (int k = 0; k < e.n_groups; ++k) {
+        if (e.set.y[k]) cudaDestroyTextureObject((cudaTextureObject_t)e.set.y[k]);
+        if (e.set.uv[k]) cudaDestroyTextureObject((cudaTextureObject_t)e.set.uv[k]);
+    }
+    e = vaw_ctx::TexEntry{};
+}
+
+// Texture objects for a clip of `frames` NV12 frames at `src` (vaw_tex.cu): pitch-linear 2-D
+// textures over groups of whole frames.  Needs the texture base / pitch alignment of the device and
+// a frame stride that is a whole number of rows; other layouts get set.enabled = 0.  At most
+// kTexGroups * group_frames frames per launch (the caller splits longer clips).
+const vaw::TexSet& tex_set(vaw_ctx* ctx, const uint8_t* src, int pitch, size_t stride, int frames)
+{
+    for (vaw_ctx::TexEntry& e : ctx->tex_cache)
+        if (e.src == src && e.pitch == pitch && e.stride == stride && e.frames == frames) return e.set;
+    vaw_ctx::TexEntry& e = ctx->tex_cache[ctx->tex_next];
+    ctx->tex_next = (ctx->tex_next + 1) % vaw_ctx::kTexCache;
+    if (e.n_groups) {
+        cudaDeviceSynchronize();  // a kernel in flight may still read the evicted objects
+        destroy_tex_entry(e);
+    }
+    e.src = src; e.pitch = pitch; e.stride = stride; e.frames = frames;
+    e.set.enabled = 0;
+    const int rows_total = ctx->p.src_height + ctx->p.src_height / 2;
+    const size_t fstride = frames > 1 ? stride : (size_t)pitch * rows_total;
+    if (pitch <= 0 || (pitch % ctx->tex_pitch_align) || (reinterpret_cast<uintptr_t>(src) % ctx->tex_align) ||
+        fstride % (size_t)pitch || fstride / (size_t)pitch < (size_t)rows_total || fstride / (size_t)pitch > 65000)
+        return e.set;
+    const int frame_rows = (int)(fstride / (size_t)pitch);
+    // group bases must keep the texture alignment: group_frames a multiple of align / gcd(stride, align)
+    size_t gcd = fstride, al = (size_t)ctx->tex_align;
+    while (al) { size_t t = gcd % al; gcd = al; al = t; }
+    const int unit = (int)((size_t)ctx->tex_align / gcd);
+    int gf = (65000 / frame_rows) / unit * unit;
+    if (gf < 1) return e.set;
+    if (gf > frames) gf = frames;  // a single (possibly short) group
+    const int n_groups = (frames + gf - 1) / gf;
+    if (n_groups > vaw::kTexGroups) {
+        // longer clips are split by the caller into launches of kTexGroups * gf frames
+    }
+    const int groups_here = n_groups < vaw::kTexGroups ? n_groups : vaw::kTexGroups;
+    cudaTextureDesc td{};
+    td.addressMode[0] = td.addressMode[1] = cudaAddressModeBorder;
+    td.filterMode = cudaFilterModeLinear;
+    td.readMode = cudaReadModeNormalizedFloat;
+    td.normalizedCoords = 0;
+    for (int k = 0; k < groups_here; ++k) {
+        const int f0 = k * gf, nf = frames - f0 < gf ? frames - f0 : gf;
+        cudaResourceDesc rd{};
+        rd.resType = cudaResourceTypePitch2D;
+        rd.res.pitch2D.devPtr = const_cast<uint8_t*>(src) + (size_t)f0 * fstride;
+        rd.res.pitch2D.pitchInBytes = (size_t)pitch;
+        rd.res.pitch2D.height = (size_t)(nf - 1) * frame_rows + rows_total;
+        rd.res.pitch2D.width = (size_t)ctx->p.src_width;
+        rd.res.pitch2D.desc = cudaCreateChannelDesc<unsigned char>();
+        cudaTextureObject_t ty = 0, tc = 0;
+        cudaError_t err = cudaCreateTextureObject(&ty, &rd, &td, nullptr);
+        if (err == cudaSuccess) {
+            rd.res.pitch2D.width = (size_t)ctx->p.src_width / 2;
+            rd.res.pitch2D.desc = cudaCreateChannelDesc<uchar2>();
+            err = cudaCreateTextureObject(&tc, &rd, &td, nullptr);
+        }
+        e.set.y[k] = ty; e.set.uv[k] = tc;
+        e.n_groups = k + 1;
+        if (err != cudaSuccess) {
+            cudaGetLastError();
+            const void* s0 = e.src; const int p0 = e.pitch; const size_t st0 = e.stride; const int fr0 = e.frames;
+            destroy_tex_entry(e);
+            e.src = s0; e.pitch = p0; e.stride = st0; e.frames = fr0;
+            return e.set;
+        }
+    }
+    e.set.group_frames = gf;
+    e.set.frame_rows = frame_rows;
+    e.set.enabled = 1;
+    return e.set;
+}
+
 int launch(vaw_ctx* ctx, const uint8_t* src, int src_pitch, size_t src_stride, uint8_t* dst,
            int dst_pitch, size_t dst_stride, const float* rots, const vaw::Rot* rot0, int n_frames,
            cudaStream_t st, vaw::PieceRec* table_override = nullptr, unsigned* counter_override = nullptr)
@@ -246,13 +333,23 @@ int launch(vaw_ctx* ctx, const uint8_t* src, int src_pitch, size_t src_stride, u
     b.rots = rots;
     if (rot0) b.rot0 = *rot0;
     const bool poly = ctx->p.format == VAW_FORMAT_NV12 && ctx->variant != VAW_VARIANT_GATHER;
-    const bool tiled = ctx->variant == VAW_VARIANT_TILED || ctx->variant == VAW_VARIANT_PIPE;
+    const bool tiled = ctx->variant == VAW_VARIANT_TILED || ctx->variant == VAW_VARIANT_PIPE ||
+                       ctx->variant == VAW_VARIANT_TEX;
     const bool piped = ctx->variant == VAW_VARIANT_PIPE && ctx->g.piece_h == vaw::kPieceHMax &&
                        vaw::pipe_smem_bytes(ctx->tile_cap) <= (227 << 10);
-    // grid.z is limited to 65535 frames per launch
-    for (int first = 0; first < n_frames; first += 65535) {
+    // grid.z is limited to 65535 frames per launch; variant TEX to kTexGroups textures of <= 65000 rows
+    int per_launch = 65535;
+    if (ctx->variant == VAW_VARIANT_TEX) {
+        const int rows_total = ctx->p.src_height + ctx->p.src_height / 2;
+        const size_t fr = src_stride && src_pitch ? src_stride / (size_t)src_pitch : (size_t)rows_total;
+        const long long cap = (long long)vaw::kTexGroups * (65000 / (long long)(fr ? fr : 1));
+        // keep launches a multiple of 512 frames so that every launch's group bases stay aligned alike
+        if (cap >= 512 && cap < per_launch) per_launch = (int)(cap / 512 * 512);
+        else if (cap >= 1 && cap < per_launch) per_launch = (int)cap;
+    }
+    for (int first = 0; first < n_frames; first += per_launch) {
         vaw::FrameBatch bb = b;
-        bb.n_frames = n_frames - first < 65535 ? n_frames - first : 65535;
+        bb.n_frames = n_frames - first < per_launch ? n_frames - first : per_launch;
         bb.src = src + (size_t)first * src_stride;
         bb.dst = dst + (size_t)first * dst_stride;
         if (rots) bb.rots = rots + (size_t)first * 9;
@@ -264,12 +361,23 @@ int launch(vaw_ctx* ctx, const uint8_t* src, int src_pitch, size_t src_stride, u
                 if (rc) return rc;
                 tab = ctx->table;
             }
-            cudaEvent_t* tev = ctx->time_kernels ? ctx->tev + 3 * (ctx->timed_launches % vaw_ctx::kTimeRing) : nullptr;
+            cudaEvent_t* tev = ctx->time_kernels ? ctx->tev + vaw_ctx::kTev * (ctx->timed_launches % vaw_ctx::kTimeRing) : nullptr;
             if (tev) cudaEventRecord(tev[0], st);
             e = vaw::launch_build_pieces(ctx->gd, ctx->basis, bb.rots, rot0 ? rot0->r : nullptr, bb.n_frames, tab, st);
             if (e != cudaSuccess) return cuda_fail(ctx, e, "piece table launch");
             ctx->launches++;
             if (tev) cudaEventRecord(tev[1], st);
+            if (ctx->variant == VAW_VARIANT_TEX) {
+                // certified interior pieces through the texture units; the rest through the tile kernel
+                const vaw::TexSet& ts = tex_set(ctx, bb.src, src_pitch, src_stride, bb.n_frames);
+                if (ts.enabled && ts.group_frames * vaw::kTexGroups >= bb.n_frames) {
+                    e = vaw::launch_warp_nv12_tex(g, bb, tab, ts, st);
+                    if (e != cudaSuccess) return cuda_fail(ctx, e, "texture kernel launch");
+                    ctx->launches++;
+                    bb.skip_interior = 1;
+                }
+            }
+            if (tev) cudaEventRecord(tev[2], st);
             if (piped)
                 e = vaw::launch_warp_nv12_pipe(g, bb, tab, table_override ? counter_override : ctx->counter,
                                                tile_maps(ctx, bb.src, src_pitch, src_stride, bb.n_frames), st);
@@ -284,7 +392,7 @@ int launch(vaw_ctx* ctx, const uint8_t* src, int src_pitch, size_t src_stride, u
             }
             if (e != cudaSuccess) return cuda_fail(ctx, e, "warp kernel launch");
             ctx->launches++;
-            if (tev) { cudaEventRecord(tev[2], st); ctx->timed_launches++; }
+            if (tev) { cudaEventRecord(tev[3], st); ctx->timed_launches++; }
             continue;
         }
         switch (ctx->p.format) {
@@ -375,10 +483,10 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
         return fail(nullptr, VAW_ERR_UNSUPPORTED, "only INTER_LINEAR is implemented");
     if (p.format != VAW_FORMAT_NV12 && p.format != VAW_FORMAT_BGR24 && p.format != VAW_FORMAT_GRAY8)
         return fail(nullptr, VAW_ERR_INVALID, "unknown pixel format");
-    if (p.variant < VAW_VARIANT_AUTO || p.variant > VAW_VARIANT_PIPE)
+    if (p.variant < VAW_VARIANT_AUTO || p.variant > VAW_VARIANT_TEX)
         return fail(nullptr, VAW_ERR_UNSUPPORTED, "kernel variant not available in this build");
     if (p.variant >= VAW_VARIANT_POLY && p.format != VAW_FORMAT_NV12)
-        return fail(nullptr, VAW_ERR_UNSUPPORTED, "variants POLY, TILED and PIPE exist for NV12 only");
+        return fail(nullptr, VAW_ERR_UNSUPPORTED, "variants POLY, TILED, PIPE and TEX exist for NV12 only");
     // `short` indices in createMap.cl:10-11 and int16 taps in cv::remap cap both sizes
     if (p.src_width < 2 || p.src_height < 2 || p.out_width < 1 || p.out_height < 1 ||
         p.src_width > 32766 || p.src_height > 32766 || p.out_width > 32766 || p.out_height > 32766)
@@ -447,7 +555,16 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
         e = cudaEventCreateWithFlags(&ctx->table_free, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaMalloc(&ctx->dump_table, ctx->pieces_per_frame * sizeof(vaw::PieceRec));
         if (e == cudaSuccess) e = cudaMalloc(&ctx->counter, 256);
-        if (e == cudaSuccess && (ctx->variant == VAW_VARIANT_TILED || ctx->variant == VAW_VARIANT_PIPE)) {
+        if (e == cudaSuccess && ctx->variant == VAW_VARIANT_TEX) {
+            cudaDeviceProp prop{};
+            e = cudaGetDeviceProperties(&prop, device);
+            if (e == cudaSuccess) {
+                ctx->tex_align = prop.textureAlignment > 0 ? (int)prop.textureAlignment : 512;
+                ctx->tex_pitch_align = prop.texturePitchAlignment > 0 ? (int)prop.texturePitchAlignment : 32;
+            }
+        }
+        if (e == cudaSuccess && (ctx->variant == VAW_VARIANT_TILED || ctx->variant == VAW_VARIANT_PIPE ||
+                                 ctx->variant == VAW_VARIANT_TEX)) {
             // size the per-CTA tile from the source boxes of the unrotated geometry, +20 % for the
             // tilt a few degrees of rotation add; more shared memory per CTA = fewer resident CTAs
             const float eye[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
@@ -490,12 +607,13 @@ void vaw_destroy(vaw_ctx* ctx)
     DeviceGuard dg(ctx->device);
     free_host_path(ctx);
     cudaDeviceSynchronize();
+    for (vaw_ctx::TexEntry& te : ctx->tex_cache) destroy_tex_entry(te);
     cudaFree(ctx->table);
     cudaFree(ctx->dump_table);
     cudaFree(ctx->counter);
     if (ctx->table_free) cudaEventDestroy(ctx->table_free);
     if (ctx->tev) {
-        for (int i = 0; i < 3 * vaw_ctx::kTimeRing; ++i) cudaEventDestroy(ctx->tev[i]);
+        for (int i = 0; i < vaw_ctx::kTev * vaw_ctx::kTimeRing; ++i) cudaEventDestroy(ctx->tev[i]);
         delete[] ctx->tev;
     }
     cudaFree(ctx->xtab);
@@ -510,9 +628,9 @@ int vaw_set_option(vaw_ctx* ctx, const char* name, int value)
     if (!std::strcmp(name, "time_kernels")) {
         DeviceGuard dg(ctx->device);
         if (value && !ctx->tev) {
-            ctx->tev = new (std::nothrow) cudaEvent_t[3 * vaw_ctx::kTimeRing];
+            ctx->tev = new (std::nothrow) cudaEvent_t[vaw_ctx::kTev * vaw_ctx::kTimeRing];
             if (!ctx->tev) return fail(ctx, VAW_ERR_NOMEM, "out of host memory");
-            for (int i = 0; i < 3 * vaw_ctx::kTimeRing; ++i) VAW_CUDA(ctx, cudaEventCreate(&ctx->tev[i]));
+            for (int i = 0; i < vaw_ctx::kTev * vaw_ctx::kTimeRing; ++i) VAW_CUDA(ctx, cudaEventCreate(&ctx->tev[i]));
         }
         ctx->time_kernels = value != 0;
         ctx->timed_launches = 0;
@@ -691,10 +809,29 @@ int vaw_kernel_times(vaw_ctx* ctx, int max_launches, float* builder_ms, float* w
     const uint64_t have = ctx->timed_launches < (uint64_t)vaw_ctx::kTimeRing ? ctx->timed_launches : vaw_ctx::kTimeRing;
     const uint64_t n = have < (uint64_t)max_launches ? have : (uint64_t)max_launches;
     for (uint64_t i = 0; i < n; ++i) {  // the most recent n launches, oldest first
-        const cudaEvent_t* e = ctx->tev + 3 * ((ctx->timed_launches - n + i) % vaw_ctx::kTimeRing);
-        VAW_CUDA(ctx, cudaEventSynchronize(e[2]));
+        const cudaEvent_t* e = ctx->tev + vaw_ctx::kTev * ((ctx->timed_launches - n + i) % vaw_ctx::kTimeRing);
+        VAW_CUDA(ctx, cudaEventSynchronize(e[3]));
         VAW_CUDA(ctx, cudaEventElapsedTime(&builder_ms[i], e[0], e[1]));
-        VAW_CUDA(ctx, cudaEventElapsedTime(&warp_ms[i], e[1], e[2]));
+        VAW_CUDA(ctx, cudaEventElapsedTime(&warp_ms[i], e[1], e[3]));
+    }
+    *n_out = (int)n;
+    return VAW_OK;
+}
+
+int vaw_kernel_times_split(vaw_ctx* ctx, int max_launches, float* tex_ms, float* tile_ms, int* n_out)
+{
+    if (!ctx) return VAW_ERR_INVALID;
+    if (!tex_ms || !tile_ms || !n_out || max_launches < 0) return fail(ctx, VAW_ERR_INVALID, "null argument");
+    *n_out = 0;
+    if (!ctx->tev) return VAW_OK;
+    DeviceGuard dg(ctx->device);
+    const uint64_t have = ctx->timed_launches < (uint64_t)vaw_ctx::kTimeRing ? ctx->timed_launches : vaw_ctx::kTimeRing;
+    const uint64_t n = have < (uint64_t)max_launches ? have : (uint64_t)max_launches;
+    for (uint64_t i = 0; i < n; ++i) {
+        const cudaEvent_t* e = ctx->tev + vaw_ctx::kTev * ((ctx->timed_launches - n + i) % vaw_ctx::kTimeRing);
+        VAW_CUDA(ctx, cudaEventSynchronize(e[3]));
+        VAW_CUDA(ctx, cudaEventElapsedTime(&tex_ms[i], e[1], e[2]));
+        VAW_CUDA(ctx, cudaEventElapsedTime(&tile_ms[i], e[2], e[3]));
     }
     *n_out = (int)n;
     return VAW_OK;

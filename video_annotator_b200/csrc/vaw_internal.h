@@ -15,6 +15,7 @@ struct FrameBatch {
     const float* rots;  // device, 9 floats per frame, or nullptr -> rot0 for every frame
     Rot rot0;
     int n_frames;
+    int skip_interior;  // variant TEX: certified interior pieces are sampled by the texture kernel
 };
 
 // xtab[u] = (u - mcx)/mfx for u < n_x, ytab[v] = (v - mcy)/mfy for v < n_y (createMap.cl:16-17)
@@ -54,6 +55,22 @@ long long tile_oob_count();
 // Needs piece_h == 32.
 cudaError_t launch_warp_nv12_tile(const Geom& g, const FrameBatch& b, const PieceRec* table, const TileMaps& maps,
                                   cudaStream_t st);
+// Variant TEX (vaw_tex.cu): certified interior pieces are filtered by the texture units.  The clip
+// is viewed as pitch-linear 2-D textures over groups of `group_frames` whole frames (a texture is at
+// most 65000 rows high): y[k] = 8-bit luma view, uv[k] = 2 x 8-bit view of the same rows (chroma
+// texel x of global row r = bytes 2x, 2x+1 of that row).  Frame f sits at texture rows
+// (f % group_frames) * frame_rows ...; its chroma plane starts src_h rows further down.
+constexpr int kTexGroups = 32;
+struct alignas(64) TexSet {
+    unsigned long long y[kTexGroups], uv[kTexGroups];
+    int enabled;       // 0: layout not texturable -> every piece takes the TILED path
+    int group_frames;  // frames per texture
+    int frame_rows;    // texture rows from one frame to the next (frame stride / pitch)
+    int pad[13];
+};
+cudaError_t launch_warp_nv12_tex(const Geom& g, const FrameBatch& b, const PieceRec* table, const TexSet& ts,
+                                 cudaStream_t st);
+
 // The map the POLY kernel samples with (table built for `rot`, one frame).
 cudaError_t launch_dump_coords_poly(const Geom& g, const Rot& rot, const PieceRec* table, int plane,
                                     float* map_x, float* map_y, int map_pitch, cudaStream_t st);

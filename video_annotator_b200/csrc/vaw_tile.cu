@@ -78,6 +78,9 @@ warp_nv12_tile_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
     const bool word_ok = ((reinterpret_cast<uintptr_t>(f.dst) | (uintptr_t)g.dst_pitch) & 3) == 0 &&
                          u_lo + kPieceW <= g.out_w;
 
+    if (b.skip_interior && (flags & (kPiecePoly | kPieceInterior)) == (kPiecePoly | kPieceInterior))
+        return;  // variant TEX: this piece belongs to the texture kernel
+
     if (flags & kPieceOutside) {  // pure border: nothing to compute
         const unsigned yw = (g.border & 255u) * 0x01010101u;
         const unsigned cw = ((g.border >> 8) & 0xffffu) * 0x00010001u;

@@ -198,6 +198,15 @@ class WarpContext:
                                           w.ctypes.data_as(_lib.f32p), C.byref(n)), self._h)
         return b[:n.value], w[:n.value]
 
+    def kernel_times_split(self, max_launches=512):
+        """(tex_ms, tile_ms): the warp time of the same launches split by kernel (vaw_kernel_times_split)."""
+        a = np.zeros(max_launches, np.float32)
+        w = np.zeros(max_launches, np.float32)
+        n = C.c_int(0)
+        _check(self._lib.vaw_kernel_times_split(self._h, max_launches, a.ctypes.data_as(_lib.f32p),
+                                                w.ctypes.data_as(_lib.f32p), C.byref(n)), self._h)
+        return a[:n.value], w[:n.value]
+
     def piece_stats(self, rotation, stream=None):
         """Piece classification and tile sizing for this rotation (vaw_piece_stats)."""
         out = (C.c_uint32 * 8)()
