@@ -1,0 +1,11 @@
+#!/bin/bash
+# PIPE and TILED after a change: parity subset, then bench both.
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q -x -k "variants_produce or pixels_bit_exact or pitched or ragged" > gpurun_out/pytest_pipe.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pipe.log
+tail -2 gpurun_out/pytest_pipe.log
+for v in 3 4; do
+  timeout 300 python bench.py --no-cpu-baseline --no-e2e --steps 50 --variant $v > gpurun_out/pipe_v$v.json 2>> gpurun_out/pipe.err
+  python -c "
+import json; d=json.load(open('gpurun_out/pipe_v$v.json')); print('variant $v', round(d['value']), round(d['roofline']['frac'],4), d['roofline']['launch_ms'], d['roofline']['other_kernels_ms'])" | tee -a gpurun_out/pipe.log
+done
+tail -3 gpurun_out/pipe.err

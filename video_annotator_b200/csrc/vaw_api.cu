@@ -221,7 +221,7 @@ const vaw::TileMaps& tile_maps(vaw_ctx* ctx, const uint8_t* src, int pitch, size
     const int rows_total = ctx->p.src_height + ctx->p.src_height / 2;
     EncodeTiledFn enc = encode_tiled();
     const bool ok = enc && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (pitch & 15) == 0 && (stride & 15) == 0 &&
-                    pitch / 4 >= vaw::kTileMaxPitch / 4 && rows_total >= 8 && (frames == 1 || stride >= (size_t)pitch);
+                    pitch / 4 >= vaw::kTileMaxPitch / 4 && rows_total >= 32 && (frames == 1 || stride >= (size_t)pitch);
     if (!ok) return e.maps;
     const cuuint64_t dims[3] = {(cuuint64_t)(pitch / 4), (cuuint64_t)rows_total, (cuuint64_t)frames};
     const cuuint64_t strides[2] = {(cuuint64_t)pitch,
@@ -232,6 +232,11 @@ const vaw::TileMaps& tile_maps(vaw_ctx* ctx, const uint8_t* src, int pitch, size
         CUresult r = enc(&e.maps.m[i], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint8_t*>(src), dims, strides,
                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return e.maps;
+        const cuuint32_t box32[3] = {box[0], 32, 1};
+        r = enc(&e.maps.m32[i], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint8_t*>(src), dims, strides,
+                box32, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return e.maps;
     }
     e.maps.enabled = 1;

@@ -36,7 +36,8 @@ constexpr int kTileMinPitch = 128, kTileMaxPitch = 448, kTilePitchStep = 32;
 constexpr int kTileCapMin = 16 << 10, kTileCapMax = 160 << 10;  // per-CTA tile bytes (chosen per geometry)
 constexpr int kTileWidths = (kTileMaxPitch - kTileMinPitch) / kTilePitchStep + 1;
 struct alignas(64) TileMaps {
-    CUtensorMap m[kTileWidths];
+    CUtensorMap m[kTileWidths];    // boxes of 8 rows
+    CUtensorMap m32[kTileWidths];  // boxes of 32 rows: a tile is loaded as 32-row boxes, then 8-row boxes for the rest
     int enabled;   // 0: no maps (layout not TMA-compatible) -> every piece gathers from global memory
     int tile_cap;  // bytes of shared memory for the luma + chroma tile of one CTA
     int pad[14];

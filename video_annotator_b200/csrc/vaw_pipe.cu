@@ -1,4 +1,4 @@
-// vaw_pipe.cu -- fused map + remap for NV12 as a persistent producer/consumer pipeline
+// vaw_pipe.cu -- fused map + remap for NV12 as one persistent producer/consumer pipeline per SM
 // (variant PIPE).  Same arithmetic and same bytes as vaw_tile.cu (variant TILED); what changes
 // is the schedule.
 //
@@ -7,23 +7,33 @@
 //
 // Why: with one CTA per piece (vaw_tile.cu) every CTA starts with a serial chain -- load the
 // piece record from L2, issue the TMA loads, wait for the tile, exchange the column polynomials --
-// during which its four warps issue nothing; ncu attributes a quarter of all warp time to it
-// (long_scoreboard + barrier) and the issue ports stay at ~71 %.  Here each CTA is persistent:
-//   - one PRODUCER warp pulls the next piece index from a global counter (so all CTAs advance
-//     along one frontier and the L2 working set stays about one source frame), copies the
-//     piece record into the stage, and issues the cp.async.bulk.tensor loads of the source box
-//     into the stage's tile buffer (completion on the stage's `full` mbarrier);
-//   - four CONSUMER warps wait on `full`, collapse the polynomial onto their columns, sample
-//     the 32 rows of the piece from the staged tile and release the stage (`empty` mbarrier).
-// With two stages the loads of piece k+1 fly while piece k is being sampled, and the per-CTA set-up
-// is paid once per launch.
+// during which its four warps issue nothing; ncu attributes a quarter of all warp time to it and
+// the issue ports stay at ~71 %.  Pure-border pieces still cost a CTA launch each.  Here:
+//   - ONE CTA per SM: a PRODUCER warp, two ISSUER warps, a FILLER warp and kGroups CONSUMER GROUPS
+//     of four warps;
+//   - the FILLER warp writes the pure-border pieces (they need no source);
+//   - the PRODUCER pulls pieces from a global queue (eight per atomic, so all SMs advance along one
+//     frontier and the L2 working set stays about one source frame); lane i prepares piece i of the
+//     ticket (position, box, tile size) and the warp then hands out, in queue order, a stage
+//     descriptor and exactly the bytes the piece's source box needs from a RING in shared memory
+//     (~198 KB; space is reclaimed in stage order as the consumers release stages);
+//   - ISSUER j takes the described stages j, j+2, ...: expected bytes, a bulk copy of the piece
+//     record, the cp.async.bulk.tensor loads of the box (32-row boxes, then 8-row boxes), all
+//     completing on the stage's `full` mbarrier;
+//   - consumer group g takes stages g, g+kGroups, ...: waits on `full`, collapses the polynomial,
+//     samples the 32 rows from the staged tile, releases the stage (`empty` mbarrier).
 //
-// Measured (B200, C3, 64 frames): 0.86 ms against 0.74 ms for TILED, so TILED stays the default and
-// this variant is kept for A/B.  The reason is shared memory: a tile is 28-32 KB, so an SM holds
-// six of them either way; TILED spends them on six CTAs = 24 sampling warps whose start-up bubbles
-// overlap each other, PIPE on 3 CTAs x 2 stages = 12 sampling warps, and one piece of look-ahead
-// does not cover a tile load that mostly comes from HBM (the consumers still wait on `full` for
-// 23 % of their time, ncu).  A deeper ring needs smaller tiles (half-height pieces): round 2.
+// What the measurements say (B200, C3, 64 frames; TILED = 0.738 ms): shared memory is the currency.
+// A C3 tile is 28 KB and the ring holds seven.  Four groups (16 sampling warps, 96 registers, three
+// tiles of look-ahead): 0.732 ms -- TILED's speed with two thirds of its sampling warps.  Five groups
+// (80 registers, two tiles ahead): 0.836 ms; six groups (72 registers, one tile ahead): 0.854 ms, the
+// consumers then wait for their loads 30 % of the time.  Staging half pieces instead (13-16 KB
+// tiles, three pieces of look-ahead at six groups) needs per-half source boxes from the builder
+// (+50 % builder time) and more live state than 72 registers hold: 1.14 ms.  A single producer warp
+// doing everything (a ~230-instruction dependent chain per piece) was the limit before the issuer
+// warps existed: 0.95 ms.  Look-ahead and sampling warps trade one for one against the same 227 KB,
+// so the pipeline ends where TILED's six staggered CTAs already are; TILED stays the default because
+// it also handles the 16- and 8-row pieces.
 #include <cuda.h>
 #include <stdint.h>
 #include "vaw_internal.h"
@@ -34,241 +44,348 @@ namespace vaw {
 
 namespace {
 
-constexpr int kConsumers = 4;                       // consumer warps (8 rows of the piece each)
-constexpr int kRowsPerWarp = kPieceHMax / kConsumers;
-constexpr int kThreads = 32 * (kConsumers + 1);     // + 1 producer warp
-constexpr int kStages = 2;
-constexpr int kCoefBytes = 8 * 32 * 16;             // column polynomials exchanged between the consumer warps
+#ifndef VAW_PIPE_GROUPS
+#define VAW_PIPE_GROUPS 4
+#endif
+constexpr int kGroups = VAW_PIPE_GROUPS;            // consumer groups per CTA
+constexpr int kGroupWarps = 4;                      // warps per group
+constexpr int kRowsPerWarp = kPieceHMax / kGroupWarps;      // 8 rows of the piece per warp
+constexpr int kFillerWarp = 1 + kGroups * kGroupWarps;      // fills the pure-border pieces
+constexpr int kIssuers = 2;                                 // warps that issue the loads of the stages the producer described
+constexpr int kIssuerWarp0 = kFillerWarp + 1;
+constexpr int kThreads = 32 * (2 + kIssuers + kGroups * kGroupWarps);  // registers are granted per 4 warps: 20 warps -> 96 each, 24 -> 80, 28 -> 72
+constexpr int kSlots = 16;                          // stage descriptors (<= 32: one lane per slot in the producer)
+constexpr int kBatch = 8;                           // pieces per queue ticket
+constexpr int kCoefBytes = 8 * 32 * 16;             // column polynomials exchanged inside a group
+constexpr int kSlotBytes = 32 + (int)sizeof(PieceRec);
 
-// Stage header written by the producer next to the copied piece record.
-struct StageHead {
-    int idx;          // flattened piece index, -1 = no more work
-    int mode;         // kModeStaged, kModeDirect
-    int pl, nr8, cnr8, lx0, cbx0;
-    int pad;
+// Stage descriptor written by the producer; the piece record is copied next to it.
+struct SlotHead {
+    int idx;            // flattened piece index, -1 = no more work
+    int frame;
+    int pxy;            // piece column | piece row << 16
+    int plmode;         // tile row pitch | mode << 16
+    int rows;           // luma tile rows | chroma tile rows << 16
+    int lorg, corg;     // first source byte of the tile rows (int16) | first source row (int16) << 16, luma / chroma
+    unsigned tile_off;  // byte offset of the tile in the ring
 };
-enum { kModeDirect = 0, kModeStaged = 1 };
+static_assert(sizeof(SlotHead) == 32, "slot head layout");
+enum { kModeDirect = 0, kModeStaged = 1 };  // direct: no tile, the taps are gathered from global memory
 
-// shared memory layout (bytes):
-//   [0, 64)                     mbarriers: full[kStages], empty[kStages]
-//   [64, 64 + 2*kCoefBytes)     two exchange buffers for the column polynomials (alternating pieces)
-//   then per stage: StageHead (32) + PieceRec (224) = 256, then the tile (tile_cap, 128-byte aligned)
-constexpr int kBarOffset = 0;
-constexpr int kCoefOffset = 128;
-constexpr int kStageOffset = kCoefOffset + 2 * kCoefBytes;
-__host__ __device__ inline int stage_bytes(int tile_cap) { return 256 + tile_cap; }
+// shared memory layout (bytes)
+constexpr int kBarOffset = 0;                                  // full[kSlots], empty[kSlots], ready[kSlots]
+constexpr int kSlotOffset = 1024;                              // per slot: SlotHead (32) + PieceRec (256)
+constexpr int kCoefOffset = kSlotOffset + kSlots * kSlotBytes; // one exchange buffer per group
+constexpr int kRingOffset = (kCoefOffset + kGroups * kCoefBytes + 1023) & ~1023;
+constexpr int kSmemBytes = 227 << 10;
+constexpr int kRingBytes = kSmemBytes - kRingOffset;
+static_assert(24 * kSlots <= kSlotOffset, "mbarrier area");
+static_assert(kSlotBytes % 16 == 0 && kCoefOffset % 16 == 0, "alignment");
 
 __device__ __forceinline__ void mbar_arrive(unsigned mbar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
 }
-__device__ __forceinline__ void consumer_sync()  // the four consumer warps only
+__device__ __forceinline__ void group_sync(int g)  // the four warps of consumer group g
 {
-    asm volatile("bar.sync 1, %0;" ::"n"(32 * kConsumers) : "memory");
+    asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(32 * kGroupWarps) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// Tile geometry of one source box (same integer arithmetic as vaw_tile.cu): returns the bytes needed, 0 if it cannot be staged.
+__device__ __forceinline__ unsigned plan_tile(int4 raw, int tile_cap, int enabled, int& pl, int& nr8, int& cnr8, int& lorg, int& corg)
+{
+    const int bx0 = (int16_t)(raw.x & 0xffff), bx1 = (int16_t)(raw.x >> 16);
+    const int by0 = (int16_t)(raw.y & 0xffff), by1 = (int16_t)(raw.y >> 16);
+    const int cx0 = (int16_t)(raw.z & 0xffff), cx1 = (int16_t)(raw.z >> 16);
+    const int cy0 = (int16_t)(raw.w & 0xffff), cy1 = (int16_t)(raw.w >> 16);
+    const int lx0 = bx0 & ~15, wb = (bx1 - lx0 + 16) & ~15;
+    const int cbx0 = (2 * cx0) & ~15, cwb = (2 * cx1 + 2 - cbx0 + 15) & ~15;
+    nr8 = (by1 - by0 + 8) & ~7;
+    cnr8 = (cy1 - cy0 + 8) & ~7;
+    const int want = max(wb, cwb);
+    const int pl128 = (want + 127) & ~127, pl32 = max(kTileMinPitch, (want + 31) & ~31);
+    pl = (pl128 <= kTileMaxPitch && pl128 * (nr8 + cnr8) <= tile_cap) ? pl128 : pl32;
+    lorg = (lx0 & 0xffff) | (by0 << 16);
+    corg = (cbx0 & 0xffff) | (cy0 << 16);
+    if (!enabled || pl > kTileMaxPitch || nr8 <= 0 || cnr8 <= 0 || pl * (nr8 + cnr8) > kRingBytes / 2) return 0u;
+    return (unsigned)(pl * (nr8 + cnr8) + 127) & ~127u;
+}
+
+// A piece without a tile (no polynomial certificate, or a box the ring cannot hold): per-pixel
+// coordinates and/or taps gathered from global memory, as in vaw_poly.cu.
+// (Out of line it was slower: 0.771 ms against 0.732 ms at four groups.)
+__device__ __forceinline__ void direct_piece(const Geom& g, const FrameBatch& b, const PieceRec* __restrict__ table, int idx,
+                                          unsigned flags, int frame, int u_lo, int v_base, int dv0, int my_rows, int lane,
+                                          uint8_t* dst, bool word_base_ok)
+{
+    const int u0 = u_lo + 4 * lane, valid = g.out_w - u0;
+    PlaneRefs f;
+    f.y = b.src + (size_t)frame * b.src_frame_stride;
+    f.uv = f.y + (size_t)g.src_pitch * g.src_h;
+    f.dst = dst;
+    if (!(flags & kPiecePoly)) {  // op-for-op per pixel
+        const Rot R = load_rot(b, frame);
+        for (int dv = dv0; dv < dv0 + my_rows; dv += 2) {
+            float2 m[2][4];
+            exact_rows(g, R, u_lo, u0, v_base + dv, m);
+            sample_rows_checked(g, f, u0, v_base + dv, m);
+        }
+    } else if (my_rows > 0) {  // no tile (layout or size): gather from global memory
+        ColPoly cp;
+        derive(table + idx, lane, cp);
+        if (flags & kPieceInterior) {
+            RowPtrs o;
+            o.y0 = dst + (size_t)(v_base + dv0) * g.dst_pitch + u0;
+            o.y1 = o.y0 + g.dst_pitch;
+            o.c = dst + (size_t)(g.out_h + ((v_base + dv0) >> 1)) * g.dst_pitch + u0;
+            o.step_y = 2 * (size_t)g.dst_pitch;
+            o.step_c = (size_t)g.dst_pitch;
+            if (word_base_ok && u_lo + kPieceW <= g.out_w) band_gmem<false>(g, cp, f, dv0, my_rows, o, valid);
+            else band_gmem<true>(g, cp, f, dv0, my_rows, o, valid);
+        } else {
+            for (int dv = dv0; dv < dv0 + my_rows; dv += 2) {
+                float2 m[2][4];
+                row_coords(cp, row_t(g, dv), m[0]);
+                row_coords(cp, row_t(g, dv + 1), m[1]);
+                sample_rows_checked(g, f, u0, v_base + dv, m);
+            }
+        }
+    }
 }
 
 }  // namespace
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 1)
 warp_nv12_pipe_kernel(const Geom g, const FrameBatch b, const PieceRec* __restrict__ table,
                       unsigned* __restrict__ counter, const __grid_constant__ TileMaps maps)
 {
-    extern __shared__ __align__(128) uint8_t smem[];
+    extern __shared__ __align__(1024) uint8_t smem[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int npx = pieces_x(g.out_w), npy = pieces_y(g.out_h, kPieceHMax);
-    const int total = b.n_frames * npy * npx;
-    const int sbytes = stage_bytes(maps.tile_cap);
+    const int per_frame = npy * npx;
+    const int total = b.n_frames * per_frame;
     const unsigned bar0 = smem_u32(smem + kBarOffset);
     auto full_bar = [&](int s) { return bar0 + 8u * (unsigned)s; };
-    auto empty_bar = [&](int s) { return bar0 + 8u * (unsigned)(kStages + s); };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (unsigned)(kSlots + s); };
+    auto ready_bar = [&](int s) { return bar0 + 8u * (unsigned)(2 * kSlots + s); };
+    uint8_t* const ring = smem + kRingOffset;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) {
-            mbar_init(full_bar(s), 1);            // the producer's arrive (+ the TMA bytes)
-            mbar_init(empty_bar(s), kConsumers);  // one arrive per consumer warp
+        for (int s = 0; s < kSlots; ++s) {
+            mbar_init(full_bar(s), 1);             // the issuer's arrive (+ the TMA bytes)
+            mbar_init(empty_bar(s), kGroupWarps);  // one arrive per consumer warp of the group
+            mbar_init(ready_bar(s), 1);            // the producer's arrive: the stage is described
         }
     }
     __syncthreads();
 
-    if (w == kConsumers) {
+    if (w == 0) {
         // ================================ producer warp ==========================================
-        // Pieces are pulled from the global queue four at a time (one atomic per batch; lane i < 4
-        // prefetches the flags and box of piece i), so the queue and record latencies are paid once
-        // per batch.  Pure-border pieces never reach the consumers: the producer fills them itself.
-        constexpr int kBatch = 4;
-        const bool word_base_ok =
-            ((reinterpret_cast<uintptr_t>(b.dst) | (uintptr_t)g.dst_pitch | (uintptr_t)b.dst_frame_stride) & 3) == 0;
-        int k = 0;  // stages handed to the consumers so far
-        bool more = true;
-        while (more) {
-            int first = 0;
-            if (lane == 0) first = (int)atomicAdd(counter, (unsigned)kBatch);
-            first = __shfl_sync(0xffffffffu, first, 0);
-            unsigned my_flags = 0;
-            if (lane < kBatch && first + lane < total) my_flags = __ldg(&table[first + lane].flags);
-            for (int i = 0; i < kBatch; ++i) {
-                const int idx = first + i;
-                if (idx >= total) { more = false; break; }
-                const unsigned flags = __shfl_sync(0xffffffffu, my_flags, i);
-                const int frame = idx / (npy * npx);
-                if (flags & kPieceOutside) {  // pure border: fill it here (32 rows x 128 px + chroma)
-                    const int rem = idx - frame * npy * npx;
-                    const int py = rem / npx, px = rem - py * npx;
-                    const int u0 = px * kPieceW + 4 * lane, v_base = py * kPieceHMax;
-                    const int rows = min(kPieceHMax, g.out_h - v_base), valid = g.out_w - u0;
-                    uint8_t* dst = b.dst + (size_t)frame * b.dst_frame_stride;
-                    uint8_t* yrow = dst + (size_t)v_base * g.dst_pitch + u0;
-                    uint8_t* crow = dst + (size_t)(g.out_h + (v_base >> 1)) * g.dst_pitch + u0;
-                    const unsigned yw = (g.border & 255u) * 0x01010101u;
-                    const unsigned cw = ((g.border >> 8) & 0xffffu) * 0x00010001u;
-                    const bool fast = word_base_ok && valid >= 4;
-                    if (valid > 0) {
-                        for (int r = 0; r < rows; ++r, yrow += g.dst_pitch) {
-                            if (fast) *reinterpret_cast<unsigned*>(yrow) = yw; else store_word<true>(yrow, yw, valid);
-                        }
-                        for (int r = 0; r < rows / 2; ++r, crow += g.dst_pitch) {
-                            if (fast) *reinterpret_cast<unsigned*>(crow) = cw; else store_word<true>(crow, cw, valid);
-                        }
-                    }
-                    continue;
-                }
-                const int s = k % kStages;
-                const unsigned round = (unsigned)(k / kStages);
-                uint8_t* stage = smem + kStageOffset + s * sbytes;
-                // start the record load before waiting for the stage
-                float4 recpart = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (lane < 14) recpart = __ldg(reinterpret_cast<const float4*>(table + idx) + lane);
-                if (k >= kStages) mbar_wait(empty_bar(s), (round - 1u) & 1u);  // consumers released the stage
-                StageHead* head = reinterpret_cast<StageHead*>(stage);
-                if (lane < 14) reinterpret_cast<float4*>(stage + 32)[lane] = recpart;
-                __syncwarp();
-                const PieceRec* lrec = reinterpret_cast<const PieceRec*>(stage + 32);
-                const PieceBox box = lrec->box;
-                int mode = kModeDirect, pl = 0, nr8 = 0, cnr8 = 0, lx0 = 0, cbx0 = 0;
-                if (flags & kPiecePoly) {
-                    lx0 = box.x0 & ~15;
-                    const int wb = (box.x1 - lx0 + 16) & ~15;
-                    cbx0 = (2 * box.cx0) & ~15;
-                    const int cwb = (2 * box.cx1 + 2 - cbx0 + 15) & ~15;
-                    nr8 = (box.y1 - box.y0 + 8) & ~7;
-                    cnr8 = (box.cy1 - box.cy0 + 8) & ~7;
-                    const int need = max(wb, cwb);
-                    const int pl128 = (need + 127) & ~127, pl32 = max(kTileMinPitch, (need + 31) & ~31);
-                    pl = (pl128 <= kTileMaxPitch && pl128 * (nr8 + cnr8) <= maps.tile_cap) ? pl128 : pl32;
-                    if (maps.enabled && pl <= kTileMaxPitch && nr8 > 0 && cnr8 > 0 && pl * (nr8 + cnr8) <= maps.tile_cap)
-                        mode = kModeStaged;
-                }
-                if (lane == 0) {
-                    head->idx = idx; head->mode = mode; head->pl = pl; head->nr8 = nr8; head->cnr8 = cnr8;
-                    head->lx0 = lx0; head->cbx0 = cbx0;
+        int k = 0;        // stages handed out so far
+        int k_head = 0;   // oldest stage whose ring space is still accounted as in use
+        unsigned tail = 0, used = 0;
+        unsigned my_size = 0;  // lane s: bytes (tile + wrap padding) held by slot s
+        auto release_oldest = [&]() {
+            const int s = k_head % kSlots;
+            mbar_wait(empty_bar(s), (unsigned)(k_head / kSlots) & 1u);
+            used -= __shfl_sync(0xffffffffu, my_size, s);
+            ++k_head;
+        };
+        // metadata of a ticket's pieces: lane i < kBatch holds the flags and the source box of piece first + i
+        auto fetch = [&](int& first, unsigned& flags, int4& box) {
+            int f = 0;
+            if (lane == 0) f = (int)atomicAdd(counter, (unsigned)kBatch);
+            first = __shfl_sync(0xffffffffu, f, 0);
+            flags = kPieceOutside;  // lanes without a piece: nothing to stage
+            box = make_int4(0, 0, 0, 0);
+            if (lane < kBatch && first + lane < total) {
+                const int4* r4 = reinterpret_cast<const int4*>(table + first + lane);
+                flags = (unsigned)__ldg(r4 + 12).z;
+                box = __ldg(r4 + 13);
+            }
+        };
+        int first_n; unsigned flags_n; int4 box_n;
+        fetch(first_n, flags_n, box_n);
+        for (;;) {
+            const int first = first_n;
+            const unsigned flags_l = flags_n;
+            const int4 box = box_n;
+            if (first >= total) break;
+            fetch(first_n, flags_n, box_n);  // the next ticket's latency hides behind this one's work
+            // ---- lane i < kBatch prepares piece first + i: position and the tile of its source box ----
+            const int idx_l = first + lane;
+            const int frame_l = idx_l / per_frame, rem_l = idx_l - frame_l * per_frame;
+            const int py_l = rem_l / npx, px_l = rem_l - py_l * npx;
+            int pl_l = 0, rows_l = 0, lorg_l = 0, corg_l = 0, mode_l = kModeDirect;
+            unsigned need_l = 0u;
+            if ((flags_l & (kPiecePoly | kPieceOutside)) == kPiecePoly) {
+                int nr8, cnr8;
+                need_l = plan_tile(box, maps.tile_cap, maps.enabled, pl_l, nr8, cnr8, lorg_l, corg_l);
+                rows_l = nr8 | (cnr8 << 16);
+                if (need_l) mode_l = kModeStaged;
+            }
+            // pure-border pieces are the filler warp's; every other piece gets a stage, in queue order
+            unsigned todo = __ballot_sync(0xffffffffu, !(flags_l & kPieceOutside));
+            while (todo) {
+                const int i = __ffs((int)todo) - 1;
+                todo &= todo - 1;
+                const unsigned need = __shfl_sync(0xffffffffu, need_l, i);
+                // ---- a descriptor and ring space: reclaim released stages in order until both exist ----
+                if (used == 0) tail = 0;
+                const bool wrap = need && tail + need > (unsigned)kRingBytes;
+                const unsigned padding = wrap ? (unsigned)kRingBytes - tail : 0u;
+                while (k - k_head >= kSlots || used + padding + need > (unsigned)kRingBytes) release_oldest();
+                const int s = k % kSlots;
+                const unsigned off = wrap ? 0u : tail;
+                tail = off + need;
+                used += padding + need;
+                if (lane == s) my_size = padding + need;
+                if (lane == i) {  // the piece's own lane describes the stage; an issuer warp starts its loads
+                    int4* head = reinterpret_cast<int4*>(smem + kSlotOffset + s * kSlotBytes);
+                    head[0] = make_int4(idx_l, frame_l, px_l | (py_l << 16), pl_l | (mode_l << 16));
+                    head[1] = make_int4(rows_l, lorg_l, corg_l, (int)off);
+                    mbar_arrive(ready_bar(s));
                 }
                 __syncwarp();
-                if (mode == kModeStaged) {
-                    // lanes issue the 8-row boxes in parallel: lane r -> luma box r, then chroma boxes
-                    const unsigned l0 = smem_u32(stage + 256), c0 = l0 + (unsigned)(nr8 * pl);
-                    const CUtensorMap* map = &maps.m[(pl - kTileMinPitch) / kTilePitchStep];
-                    if (lane == 0) mbar_expect_tx(full_bar(s), (unsigned)(pl * (nr8 + cnr8)));  // arrive + expected bytes
-                    __syncwarp();
-                    const int nl = nr8 >> 3, nc = cnr8 >> 3;
-                    for (int q = lane; q < nl + nc; q += 32) {
-                        if (q < nl) tma_load_3d(l0 + (unsigned)(q * 8 * pl), map, lx0 >> 2, box.y0 + 8 * q, frame, full_bar(s));
-                        else tma_load_3d(c0 + (unsigned)((q - nl) * 8 * pl), map, cbx0 >> 2, g.src_h + box.cy0 + 8 * (q - nl), frame, full_bar(s));
-                    }
-                } else if (lane == 0) {
-                    mbar_arrive(full_bar(s));
-                }
                 ++k;
             }
         }
-        // tell the consumers there is no more work
-        {
-            const int s = k % kStages;
-            const unsigned round = (unsigned)(k / kStages);
-            if (k >= kStages) mbar_wait(empty_bar(s), (round - 1u) & 1u);
+        // one terminal stage per consumer group (idx -1), then one per issuer warp (idx -2)
+        for (int t = 0; t < kGroups + kIssuers; ++t, ++k) {
+            while (k - k_head >= kSlots) release_oldest();
+            const int s = k % kSlots;
+            if (lane == s) my_size = 0;
             if (lane == 0) {
-                reinterpret_cast<StageHead*>(smem + kStageOffset + s * sbytes)->idx = -1;
-                mbar_arrive(full_bar(s));
+                reinterpret_cast<SlotHead*>(smem + kSlotOffset + s * kSlotBytes)->idx = t < kGroups ? -1 : -2;
+                mbar_arrive(ready_bar(s));
+            }
+            __syncwarp();
+        }
+        return;
+    }
+
+    if (w >= kIssuerWarp0) {
+        // ================================ issuer warps ===========================================
+        // Issuer j starts the loads of stages j, j + kIssuers, ...: the record copy and the
+        // TMA boxes of the tile (whole 32-row boxes, then 8-row boxes for the rest; luma first, then chroma).
+        for (int k = w - kIssuerWarp0;; k += kIssuers) {
+            const int s = k % kSlots;
+            mbar_wait(ready_bar(s), (unsigned)(k / kSlots) & 1u);
+            const uint8_t* slot = smem + kSlotOffset + s * kSlotBytes;
+            const SlotHead head = *reinterpret_cast<const SlotHead*>(slot);
+            const unsigned fb = full_bar(s);
+            if (head.idx == -2) break;  // consecutive stages alternate between the issuers: one of these each
+            if (head.idx < 0) {         // a consumer group's terminal stage: pass it on
+                if (lane == 0) mbar_arrive(fb);
+                continue;
+            }
+            if (lane == 0) {
+                const int pl = head.plmode & 0xffff, mode = head.plmode >> 16;
+                const int nr8 = head.rows & 0xffff, cnr8 = head.rows >> 16;
+                {
+                    // arrive + expected bytes: the record copy and, when staged, the boxes
+                    mbar_expect_tx(fb, (unsigned)sizeof(PieceRec) + (mode == kModeStaged ? (unsigned)(pl * (nr8 + cnr8)) : 0u));
+                    bulk_g2s(smem_u32(slot + 32), table + head.idx, (unsigned)sizeof(PieceRec), fb);
+                    if (mode == kModeStaged) {
+                        const int lx0 = (int16_t)(head.lorg & 0xffff), by0 = head.lorg >> 16;
+                        const int cbx0 = (int16_t)(head.corg & 0xffff), cy0 = head.corg >> 16;
+                        const unsigned l0 = smem_u32(ring + head.tile_off), c0 = l0 + (unsigned)(nr8 * pl);
+                        const int mi = (pl - kTileMinPitch) / kTilePitchStep;
+                        const CUtensorMap *map = &maps.m[mi], *map32 = &maps.m32[mi];
+                        int r = 0;
+                        for (; r + 32 <= nr8; r += 32) tma_load_3d(l0 + (unsigned)(r * pl), map32, lx0 >> 2, by0 + r, head.frame, fb);
+                        for (; r < nr8; r += 8) tma_load_3d(l0 + (unsigned)(r * pl), map, lx0 >> 2, by0 + r, head.frame, fb);
+                        for (r = 0; r + 32 <= cnr8; r += 32)
+                            tma_load_3d(c0 + (unsigned)(r * pl), map32, cbx0 >> 2, g.src_h + cy0 + r, head.frame, fb);
+                        for (; r < cnr8; r += 8)
+                            tma_load_3d(c0 + (unsigned)(r * pl), map, cbx0 >> 2, g.src_h + cy0 + r, head.frame, fb);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        return;
+    }
+
+    if (w == kFillerWarp) {
+        // ================================ filler warp ============================================
+        // Pure-border pieces need no source: this warp writes them, 32 flags per load, independent of
+        // the queue (static stride over all pieces of the launch).
+        const bool vec_ok =
+            ((reinterpret_cast<uintptr_t>(b.dst) | (uintptr_t)g.dst_pitch | (uintptr_t)b.dst_frame_stride) & 15) == 0;
+        const unsigned yw = (g.border & 255u) * 0x01010101u;
+        const unsigned cw = ((g.border >> 8) & 0xffffu) * 0x00010001u;
+        for (int base = (int)blockIdx.x * 32; base < total; base += (int)gridDim.x * 32) {
+            unsigned fl = 0;
+            if (base + lane < total) fl = __ldg(&table[base + lane].flags);
+            unsigned todo = __ballot_sync(0xffffffffu, (fl & kPieceOutside) != 0);
+            while (todo) {
+                const int idx = base + __ffs((int)todo) - 1;
+                todo &= todo - 1;
+                const int frame = idx / per_frame, rem = idx - frame * per_frame;
+                const int py = rem / npx, px = rem - py * npx;
+                const int v_base = py * kPieceHMax;
+                const int rows = min(kPieceHMax, g.out_h - v_base);
+                uint8_t* dst = b.dst + (size_t)frame * b.dst_frame_stride;
+                if (vec_ok && px * kPieceW + kPieceW <= g.out_w) {
+                    // 16 bytes per lane: 8 lanes per row, 4 rows per store instruction
+                    const int sub = lane >> 3, col = (lane & 7) * 16;
+                    uint8_t* yrow = dst + (size_t)(v_base + sub) * g.dst_pitch + px * kPieceW + col;
+                    uint8_t* crow = dst + (size_t)(g.out_h + (v_base >> 1) + sub) * g.dst_pitch + px * kPieceW + col;
+                    const uint4 y4 = make_uint4(yw, yw, yw, yw), c4 = make_uint4(cw, cw, cw, cw);
+                    for (int r = sub; r < rows; r += 4, yrow += 4 * (size_t)g.dst_pitch) *reinterpret_cast<uint4*>(yrow) = y4;
+                    for (int r = sub; r < rows / 2; r += 4, crow += 4 * (size_t)g.dst_pitch) *reinterpret_cast<uint4*>(crow) = c4;
+                } else {
+                    const int u0 = px * kPieceW + 4 * lane, valid = g.out_w - u0;
+                    uint8_t* yrow = dst + (size_t)v_base * g.dst_pitch + u0;
+                    uint8_t* crow = dst + (size_t)(g.out_h + (v_base >> 1)) * g.dst_pitch + u0;
+                    if (valid > 0) {
+                        for (int r = 0; r < rows; ++r, yrow += g.dst_pitch) store_word<true>(yrow, yw, valid);
+                        for (int r = 0; r < rows / 2; ++r, crow += g.dst_pitch) store_word<true>(crow, cw, valid);
+                    }
+                }
             }
         }
         return;
     }
 
-    // ==================================== consumer warps =========================================
-    const int dv0 = w * kRowsPerWarp;
+    // ==================================== consumer groups ========================================
+    const int grp = (w - 1) / kGroupWarps, wg = (w - 1) % kGroupWarps, gtid = wg * 32 + lane;
     const bool even_ok = ((reinterpret_cast<uintptr_t>(b.dst) | (uintptr_t)g.dst_pitch | (uintptr_t)b.dst_frame_stride) & 1) == 0;
     const bool word_base_ok = ((reinterpret_cast<uintptr_t>(b.dst) | (uintptr_t)g.dst_pitch | (uintptr_t)b.dst_frame_stride) & 3) == 0;
-    for (int k = 0;; ++k) {
-        const int s = k % kStages;
-        const unsigned round = (unsigned)(k / kStages);
-        mbar_wait(full_bar(s), round & 1u);  // record copied, tile landed
-        uint8_t* stage = smem + kStageOffset + s * sbytes;
-        const StageHead head = *reinterpret_cast<const StageHead*>(stage);
+    float4* const coefs = reinterpret_cast<float4*>(smem + kCoefOffset + grp * kCoefBytes);
+    for (int k = grp;; k += kGroups) {
+        const int s = k % kSlots;
+        mbar_wait(full_bar(s), (unsigned)(k / kSlots) & 1u);  // record copied, tile landed
+        const uint8_t* slot = smem + kSlotOffset + s * kSlotBytes;
+        const SlotHead head = *reinterpret_cast<const SlotHead*>(slot);
         if (head.idx < 0) break;
-        const PieceRec* rec = reinterpret_cast<const PieceRec*>(stage + 32);  // in shared memory
+        const PieceRec* rec = reinterpret_cast<const PieceRec*>(slot + 32);  // in shared memory
         const unsigned flags = rec->flags;
-        const int frame = head.idx / (npy * npx);
-        const int rem = head.idx - frame * npy * npx;
-        const int py = rem / npx, px = rem - py * npx;
-        const int u_lo = px * kPieceW, u0 = u_lo + 4 * lane, v_base = py * kPieceHMax;
+        const int frame = head.frame;
+        const int py = head.pxy >> 16, px = head.pxy & 0xffff;
+        const int u_lo = px * kPieceW, v_base = py * kPieceHMax;
         const int rows = min(kPieceHMax, g.out_h - v_base);  // even for NV12
+        const int dv0 = wg * kRowsPerWarp;
         const int my_rows = max(0, min(kRowsPerWarp, rows - dv0));
-        const int valid = g.out_w - u0;
+        uint8_t* const dst = b.dst + (size_t)frame * b.dst_frame_stride;
+        bool wrote_tile = false;
 
-        PlaneRefs f;
-        f.y = b.src + (size_t)frame * b.src_frame_stride;
-        f.uv = f.y + (size_t)g.src_pitch * g.src_h;
-        f.dst = b.dst + (size_t)frame * b.dst_frame_stride;
-        RowPtrs o;
-        o.y0 = f.dst + (size_t)(v_base + dv0) * g.dst_pitch + u0;
-        o.y1 = o.y0 + g.dst_pitch;
-        o.c = f.dst + (size_t)(g.out_h + ((v_base + dv0) >> 1)) * g.dst_pitch + u0;
-        o.step_y = 2 * (size_t)g.dst_pitch;
-        o.step_c = (size_t)g.dst_pitch;
-        const bool word_ok = word_base_ok && u_lo + kPieceW <= g.out_w;
-
-        if (flags & kPieceOutside) {  // pure border: nothing to compute
-            const unsigned yw = (g.border & 255u) * 0x01010101u;
-            const unsigned cw = ((g.border >> 8) & 0xffffu) * 0x00010001u;
-            if (valid > 0)
-                for (int dv = 0; dv < my_rows; dv += 2) {
-                    store_word<true>(o.y0, yw, valid);
-                    store_word<true>(o.y1, yw, valid);
-                    store_word<true>(o.c, cw, valid);
-                    o.y0 += o.step_y; o.y1 += o.step_y; o.c += o.step_c;
-                }
-        } else if (!(flags & kPiecePoly)) {  // op-for-op per pixel
-            const Rot R = load_rot(b, frame);
-            for (int dv = dv0; dv < dv0 + my_rows; dv += 2) {
-                float2 m[2][4];
-                exact_rows(g, R, u_lo, u0, v_base + dv, m);
-                sample_rows_checked(g, f, u0, v_base + dv, m);
-            }
-        } else if (head.mode != kModeStaged) {  // does not fit a tile: gather from global memory
-            if (my_rows > 0) {
-                ColPoly cp;
-                derive(table + head.idx, lane, cp);
-                if (flags & kPieceInterior) {
-                    if (word_ok) band_gmem<false>(g, cp, f, dv0, my_rows, o, valid);
-                    else band_gmem<true>(g, cp, f, dv0, my_rows, o, valid);
-                } else {
-                    for (int dv = dv0; dv < dv0 + my_rows; dv += 2) {
-                        float2 m[2][4];
-                        row_coords(cp, row_t(g, dv), m[0]);
-                        row_coords(cp, row_t(g, dv + 1), m[1]);
-                        sample_rows_checked(g, f, u0, v_base + dv, m);
-                    }
-                }
-            }
+        if ((head.plmode >> 16) != kModeStaged) {
+            direct_piece(g, b, table, head.idx, flags, frame, u_lo, v_base, dv0, my_rows, lane, dst, word_base_ok);
         } else {
-            // ---- staged: collapse (warp w does column slot j = w), exchange, sample ---------------
-            float4* coefs = reinterpret_cast<float4*>(smem + kCoefOffset + (k & 1) * kCoefBytes);
+            // ---- staged: collapse (warp wg does column slot j = wg), exchange, sample -------------
             {
                 float2 a[kNv];
-                collapse_column(rec->c, ((float)pair_column(lane, w) - 63.5f) * 0.015625f, a);  // s is exact
-                coefs[(2 * w) * 32 + lane] = make_float4(a[0].x, a[0].y, a[1].x, a[1].y);
-                coefs[(2 * w + 1) * 32 + lane] = make_float4(a[2].x, a[2].y, a[3].x, a[3].y);
+                collapse_column(rec->c, ((float)pair_column(lane, wg) - 63.5f) * 0.015625f, a);  // s is exact
+                coefs[(2 * wg) * 32 + lane] = make_float4(a[0].x, a[0].y, a[1].x, a[1].y);
+                coefs[(2 * wg + 1) * 32 + lane] = make_float4(a[2].x, a[2].y, a[3].x, a[3].y);
             }
-            consumer_sync();
+            group_sync(grp);
             ColPoly cp;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -277,36 +394,44 @@ warp_nv12_pipe_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
                 cp.a[j][2] = make_float2(hi.x, hi.y); cp.a[j][3] = make_float2(hi.z, hi.w);
             }
             cp.base = rec->base;
-            const PieceBox box = rec->box;
-            const int pl = head.pl;
-            uint8_t* ltile = stage + 256;
-            uint8_t* ctile = ltile + head.nr8 * pl;
+            const int pl = head.plmode & 0xffff;
+            const int nr8 = head.rows & 0xffff, cnr8 = head.rows >> 16;
+            const int lx0 = (int16_t)(head.lorg & 0xffff), by0 = head.lorg >> 16;
+            const int cbx0 = (int16_t)(head.corg & 0xffff), cy0 = head.corg >> 16;
+            uint8_t* ltile = ring + head.tile_off;
+            uint8_t* ctile = ltile + nr8 * pl;
             if (!(flags & kPieceInterior)) {  // straddles the frame border: paint the outside cells
                 const unsigned by_ = g.border & 255u, bu = (g.border >> 8) & 255u, bv = (g.border >> 16) & 255u;
-                fill_border(ltile, pl, head.nr8, box.y0, g.src_h, head.lx0, g.src_w, by_ * 0x01010101u, threadIdx.x, 32 * kConsumers);
-                fill_border(ctile, pl, head.cnr8, box.cy0, g.src_h >> 1, head.cbx0, g.src_w, (bu | (bv << 8)) * 0x00010001u,
-                            threadIdx.x, 32 * kConsumers);
-                consumer_sync();
+                fill_border(ltile, pl, nr8, by0, g.src_h, lx0, g.src_w, by_ * 0x01010101u, gtid, 32 * kGroupWarps);
+                fill_border(ctile, pl, cnr8, cy0, g.src_h >> 1, cbx0, g.src_w, (bu | (bv << 8)) * 0x00010001u,
+                            gtid, 32 * kGroupWarps);
+                wrote_tile = true;
             }
+            group_sync(grp);  // the exchange buffer is free again; the painted cells are visible
             if (my_rows > 0) {
+                RowPtrs o;  // the staged path uses the pair mapping: column 2 * lane of the piece
+                o.y0 = dst + (size_t)(v_base + dv0) * g.dst_pitch + u_lo + 2 * lane;
+                o.y1 = o.y0 + g.dst_pitch;
+                o.c = dst + (size_t)(g.out_h + ((v_base + dv0) >> 1)) * g.dst_pitch + u_lo + 2 * lane;
+                o.step_y = 2 * (size_t)g.dst_pitch;
+                o.step_c = (size_t)g.dst_pitch;
                 const unsigned upl = (unsigned)pl;
-                const unsigned lconst = smem_u32(ltile) - (unsigned)box.y0 * upl - (unsigned)head.lx0 - kMagicShift * upl - kMagicShift;
-                const unsigned cconst = ((smem_u32(ctile) - (unsigned)box.cy0 * upl - (unsigned)head.cbx0 - kMagicShift * upl) >> 1) - kMagicShift;
-                const int shift = 2 * lane - 4 * lane;  // the staged path uses the pair mapping
-                o.y0 += shift; o.y1 += shift; o.c += shift;
+                const unsigned lconst = smem_u32(ltile) - (unsigned)by0 * upl - (unsigned)lx0 - kMagicShift * upl - kMagicShift;
+                const unsigned cconst = ((smem_u32(ctile) - (unsigned)cy0 * upl - (unsigned)cbx0 - kMagicShift * upl) >> 1) - kMagicShift;
                 const bool in_a = u_lo + 2 * lane < g.out_w, in_b = u_lo + 64 + 2 * lane < g.out_w;
-                const TileBounds tb = {smem_u32(ltile), smem_u32(ltile) + (unsigned)(head.nr8 * pl), smem_u32(ctile),
-                                       smem_u32(ctile) + (unsigned)(head.cnr8 * pl)};
+                const TileBounds tb = {smem_u32(ltile), smem_u32(ltile) + (unsigned)(nr8 * pl), smem_u32(ctile),
+                                       smem_u32(ctile) + (unsigned)(cnr8 * pl)};
                 if (even_ok && u_lo + kPieceW <= g.out_w) rows_tile<false>(g, cp, lconst, cconst, upl, dv0, my_rows, o, in_a, in_b, tb);
                 else rows_tile<true>(g, cp, lconst, cconst, upl, dv0, my_rows, o, in_a, in_b, tb);
             }
         }
+        if (wrote_tile) fence_async_smem();  // generic-proxy writes before the TMA reuses the bytes
         __syncwarp();
         if (lane == 0) mbar_arrive(empty_bar(s));  // this warp is done with the stage
     }
 }
 
-int pipe_smem_bytes(int tile_cap) { return kStageOffset + kStages * stage_bytes(tile_cap); }
+int pipe_smem_bytes(int tile_cap) { (void)tile_cap; return kSmemBytes; }
 
 cudaError_t launch_warp_nv12_pipe(const Geom& g, const FrameBatch& b, const PieceRec* table, unsigned* counter,
                                   const TileMaps& maps, cudaStream_t st)
@@ -317,24 +442,18 @@ cudaError_t launch_warp_nv12_pipe(const Geom& g, const FrameBatch& b, const Piec
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) dev = 0;
     if (!configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(warp_nv12_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 << 10);
+        cudaError_t e = cudaFuncSetAttribute(warp_nv12_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
-    const int smem = pipe_smem_bytes(maps.tile_cap);
-    if (smem > (227 << 10)) return cudaErrorInvalidValue;
-    int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, warp_nv12_pipe_kernel, kThreads, smem);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
     const long long total = (long long)pieces_x(g.out_w) * pieces_y(g.out_h, kPieceHMax) * b.n_frames;
-    long long ctas = (long long)sm_count[dev] * per_sm;
-    if (ctas > total) ctas = total;
+    long long ctas = sm_count[dev];
+    if (ctas > (total + kBatch - 1) / kBatch) ctas = (total + kBatch - 1) / kBatch;
     if (ctas < 1) ctas = 1;
-    e = cudaMemsetAsync(counter, 0, sizeof(unsigned), st);
+    cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned), st);
     if (e != cudaSuccess) return e;
-    warp_nv12_pipe_kernel<<<(unsigned)ctas, kThreads, smem, st>>>(g, b, table, counter, maps);
+    warp_nv12_pipe_kernel<<<(unsigned)ctas, kThreads, kSmemBytes, st>>>(g, b, table, counter, maps);
     return cudaGetLastError();
 }
 

@@ -38,6 +38,9 @@ namespace vaw {
 namespace {
 
 constexpr int kWarps = 4;
+#ifndef VAW_TILE_HOIST
+#define VAW_TILE_HOIST 0  // 1: also request the coefficients at CTA entry (measured slower: 0.763 ms against 0.738 ms)
+#endif
 #ifndef VAW_TILE_CTAS
 #define VAW_TILE_CTAS 6  // resident CTAs per SM the kernel is sized for (registers and shared memory)
 #endif
@@ -57,7 +60,14 @@ warp_nv12_tile_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
     const int ph = g.piece_h, rows_per_warp = ph / kWarps;  // 32 / 16 / 8 rows per piece -> 8 / 4 / 2 per warp
     const int npx = pieces_x(g.out_w), npy = pieces_y(g.out_h, ph);
     const PieceRec* rec = table + ((size_t)frame * npy + py) * npx + px;
-    const unsigned flags = __ldg(&rec->flags);
+    // flags and box are requested together (one L2 round trip instead of two dependent ones: 0.745 -> 0.738 ms)
+    const float4 rec_tail = __ldg(reinterpret_cast<const float4*>(rec) + 12);  // base.x, base.y, flags, pad
+    const int4 raw = __ldg(reinterpret_cast<const int4*>(rec) + 13);          // the source box
+    float2 c[kNu][kNv];
+#if VAW_TILE_HOIST
+    load_coeffs(rec, c);
+#endif
+    const unsigned flags = __float_as_uint(rec_tail.z);
     const int u_lo = px * kPieceW, u0 = u_lo + 4 * lane, v_base = py * ph;
     const int rows = min(ph, g.out_h - v_base);  // even for NV12
     const int dv0 = w * rows_per_warp;
@@ -105,7 +115,6 @@ warp_nv12_tile_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
     }
 
     // ---- the source rectangle of this piece's taps (block-uniform) ---------------------------
-    const int4 raw = __ldg(reinterpret_cast<const int4*>(&rec->box));
     const int bx0 = (int16_t)(raw.x & 0xffff), bx1 = (int16_t)(raw.x >> 16);
     const int by0 = (int16_t)(raw.y & 0xffff), by1 = (int16_t)(raw.y >> 16);
     const int cx0 = (int16_t)(raw.z & 0xffff), cx1 = (int16_t)(raw.z >> 16);
@@ -147,17 +156,24 @@ warp_nv12_tile_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
     if (tid == 0) {
         mbar_init(mbar, 1);
         mbar_expect_tx(mbar, (unsigned)(pl * (nr8 + cnr8)));
-        const CUtensorMap* map = &maps.m[(pl - kTileMinPitch) / kTilePitchStep];
+        const int mi = (pl - kTileMinPitch) / kTilePitchStep;
+        const CUtensorMap *map = &maps.m[mi], *map32 = &maps.m32[mi];
         const unsigned l0 = smem_u32(ltile), c0 = smem_u32(ctile);
-        for (int k = 0; k < nr8; k += 8) tma_load_3d(l0 + (unsigned)(k * pl), map, lx0 >> 2, by0 + k, frame, mbar);
-        for (int k = 0; k < cnr8; k += 8)
+        int k = 0;
+        for (; k + 32 <= nr8; k += 32) tma_load_3d(l0 + (unsigned)(k * pl), map32, lx0 >> 2, by0 + k, frame, mbar);
+        for (; k < nr8; k += 8) tma_load_3d(l0 + (unsigned)(k * pl), map, lx0 >> 2, by0 + k, frame, mbar);
+        for (k = 0; k + 32 <= cnr8; k += 32)
+            tma_load_3d(c0 + (unsigned)(k * pl), map32, cbx0 >> 2, g.src_h + cy0 + k, frame, mbar);
+        for (; k < cnr8; k += 8)
             tma_load_3d(c0 + (unsigned)(k * pl), map, cbx0 >> 2, g.src_h + cy0 + k, frame, mbar);
     }
 
     // ---- collapse the polynomial: warp w does column j = w for every lane -------------------------
     {
-        float2 c[kNu][kNv], a[kNv];
+        float2 a[kNv];
+#if !VAW_TILE_HOIST
         load_coeffs(rec, c);
+#endif
         collapse_column(c, ((float)pair_column(lane, w) - 63.5f) * 0.015625f, a);  // s is exact
         coefs[(2 * w) * 32 + lane] = make_float4(a[0].x, a[0].y, a[1].x, a[1].y);
         coefs[(2 * w + 1) * 32 + lane] = make_float4(a[2].x, a[2].y, a[3].x, a[3].y);
@@ -170,7 +186,7 @@ warp_nv12_tile_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
         cp.a[j][0] = make_float2(lo.x, lo.y); cp.a[j][1] = make_float2(lo.z, lo.w);
         cp.a[j][2] = make_float2(hi.x, hi.y); cp.a[j][3] = make_float2(hi.z, hi.w);
     }
-    cp.base = load_base(rec);
+    cp.base = make_float2(rec_tail.x, rec_tail.y);
 
 #ifndef VAW_ABL_NO_TMA_WAIT
     mbar_wait(mbar, 0);  // the tile has landed
