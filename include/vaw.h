@@ -99,7 +99,13 @@ typedef struct vaw_params {
                                           borderValue; OpenCV default is 0; the NV12
                                           neutral chroma is 128)                     */
     int32_t variant;                   /* VAW_VARIANT_*                              */
-    int32_t reserved[7];
+    float src_distortion[4];           /* extension: k1..k4 of the input camera's cv::fisheye
+                                          distortion, theta_d = theta (1 + k1 theta^2 + ... + k4 theta^8)
+                                          (Camera::distortion_coefficients, FrameSourceWarp.hpp:31; the
+                                          presets set zeros, FrameSourceWarp.cpp:35, and createMap.cl
+                                          ignores the field).  All zero = the reference's map, bit for
+                                          bit; float like every scalar the reference hands its kernel   */
+    int32_t reserved[3];
 } vaw_params;
 
 /* Camera description (opencv/FrameSourceWarp.hpp:14-34). */

@@ -40,7 +40,14 @@ void vaw_oracle_create_map_point(int gid_x, int gid_y, const vaw_oracle_intrinsi
 
     /* createMap.cl:38-39 -- length() fixed as sqrt(x*x + y*y); NaN at radius 0 */
     float radius_identity = sqrtf(c0 * c0 + c1 * c1);
-    float fisheye_correction = atanf(radius_identity) / radius_identity;
+    float theta = atanf(radius_identity);
+    if (k->dist[0] != 0.0f || k->dist[1] != 0.0f || k->dist[2] != 0.0f || k->dist[3] != 0.0f) {
+        /* extension, not in createMap.cl: the cv::fisheye distortion polynomial (Horner, no FMA) */
+        float t2 = theta * theta;
+        float poly = 1.0f + t2 * (k->dist[0] + t2 * (k->dist[1] + t2 * (k->dist[2] + t2 * k->dist[3])));
+        theta = theta * poly;
+    }
+    float fisheye_correction = theta / radius_identity;
 
     /* createMap.cl:48-49 -- center + ((c * k) * focal) */
     *out_x = k->src_center_x + c0 * fisheye_correction * k->src_focal_x;

@@ -27,10 +27,10 @@ def build(force=False):
 
 
 class Intrinsics(C.Structure):
-    """The 8 floats of FrameSourceWarp.cpp:283-290."""
+    """The 8 floats of FrameSourceWarp.cpp:283-290 (+ the fisheye distortion extension, zeros = createMap.cl)."""
     _fields_ = [(n, C.c_float) for n in (
         "src_center_x", "src_center_y", "src_focal_x", "src_focal_y",
-        "map_center_x", "map_center_y", "map_focal_x", "map_focal_y")]
+        "map_center_x", "map_center_y", "map_focal_x", "map_focal_y")] + [("dist", C.c_float * 4)]
 
 
 class Camera(C.Structure):
@@ -91,13 +91,18 @@ def _u8(a):
     return a.ctypes.data_as(C.POINTER(C.c_uint8))
 
 
-def intrinsics(K_in, K_out):
-    """double -> float cast exactly where the reference does it (FrameSourceWarp.cpp:283-290)."""
+def intrinsics(K_in, K_out, dist=None):
+    """double -> float cast exactly where the reference does it (FrameSourceWarp.cpp:283-290).
+    dist: optional k1..k4 of the input camera's cv::fisheye distortion (extension; None = createMap.cl)."""
     K_in = np.asarray(K_in, dtype=np.float64)
     K_out = np.asarray(K_out, dtype=np.float64)
-    return Intrinsics(np.float32(K_in[0, 2]), np.float32(K_in[1, 2]), np.float32(K_in[0, 0]),
-                      np.float32(K_in[1, 1]), np.float32(K_out[0, 2]), np.float32(K_out[1, 2]),
-                      np.float32(K_out[0, 0]), np.float32(K_out[1, 1]))
+    k = Intrinsics(np.float32(K_in[0, 2]), np.float32(K_in[1, 2]), np.float32(K_in[0, 0]),
+                   np.float32(K_in[1, 1]), np.float32(K_out[0, 2]), np.float32(K_out[1, 2]),
+                   np.float32(K_out[0, 0]), np.float32(K_out[1, 1]))
+    if dist is not None:
+        for i in range(4):
+            k.dist[i] = np.float32(dist[i])
+    return k
 
 
 def rot32(rot):

@@ -48,6 +48,12 @@ extern "C" {
 typedef struct vaw_oracle_intrinsics {
     float src_center_x, src_center_y, src_focal_x, src_focal_y; /* input camera  */
     float map_center_x, map_center_y, map_focal_x, map_focal_y; /* output camera */
+    /* Extension: k1..k4 of the input camera's cv::fisheye distortion,
+     * theta_d = theta (1 + k1 theta^2 + k2 theta^4 + k3 theta^6 + k4 theta^8)
+     * (Camera::distortion_coefficients, FrameSourceWarp.hpp:31).  The reference's presets set
+     * zeros (FrameSourceWarp.cpp:35) and createMap.cl ignores the field: all zero reproduces
+     * createMap.cl bit for bit.  Pinned against cv2.fisheye.initUndistortRectifyMap. */
+    float dist[4];
 } vaw_oracle_intrinsics;
 
 /* createMap.cl:1-51.  map_x/map_y: rows x cols fp32, row stride `step` floats.

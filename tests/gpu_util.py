@@ -31,7 +31,7 @@ def devatan_lib():
 
 def host_device_map(k, rot, rows, cols):
     """Luma map as the DEVICE computes it, evaluated on the host (k: oracle Intrinsics)."""
-    kk = np.array([getattr(k, f[0]) for f in k._fields_], np.float32)
+    kk = np.array([getattr(k, f[0]) for f in k._fields_[:8]] + list(k.dist[:]), np.float32)
     r = np.ascontiguousarray(np.asarray(rot, np.float64).reshape(9).astype(np.float32))
     mx = np.empty((rows, cols), np.float32)
     my = np.empty((rows, cols), np.float32)

@@ -21,7 +21,7 @@ static float dev_atanf_pos(float r)
     return p;
 }
 
-/* k[8] = scx, scy, sfx, sfy, mcx, mcy, mfx, mfy */
+/* k[12] = scx, scy, sfx, sfy, mcx, mcy, mfx, mfy, k1..k4 (cv::fisheye distortion extension; zeros = createMap.cl) */
 void devatan_create_map(float *map_x, float *map_y, int rows, int cols, const float *k, const float *rot)
 {
     for (int v = 0; v < rows; ++v)
@@ -33,7 +33,12 @@ void devatan_create_map(float *map_x, float *map_y, int rows, int cols, const fl
             float q2 = (rot[6] * x + rot[7] * y) + rot[8];
             float c0 = q0 / q2, c1 = q1 / q2;
             float rad = sqrtf(c0 * c0 + c1 * c1);
-            float kk = dev_atanf_pos(rad) / rad;
+            float theta = dev_atanf_pos(rad);
+            if (k[8] != 0.0f || k[9] != 0.0f || k[10] != 0.0f || k[11] != 0.0f) {
+                float t2 = theta * theta;
+                theta = theta * (1.0f + t2 * (k[8] + t2 * (k[9] + t2 * (k[10] + t2 * k[11]))));
+            }
+            float kk = theta / rad;
             map_x[(long)v * cols + u] = k[0] + c0 * kk * k[2];
             map_y[(long)v * cols + u] = k[1] + c1 * kk * k[3];
         }

@@ -75,7 +75,7 @@ def test_fast_math_sequences_equal_ieee_intrinsics(V):
 
 
 # ---- A. coordinates ---------------------------------------------------------------------------
-GATHER, POLY, TILED, PIPE = 1, 2, 3, 4
+GATHER, POLY, TILED, PIPE, TEX = 1, 2, 3, 4, 5
 COORD_CASES = [("C1", (0, 0, 0)), ("C1", (2.0, -3.0, 1.5)), ("C2", (-1.0, 2.5, 0.7)),
                ("C3", (2.0, -3.0, 1.5)), ("C5", (6.0, -8.0, 4.0))]
 
@@ -701,3 +701,80 @@ def test_zz_no_tap_left_its_tile(V):
     n = V.load().vaw_debug_oob_count(0)
     assert n in (-1, 0), f"{n} taps outside their staged tile"
     _record("oob_taps", {"count": int(n), "instrumented": n >= 0})
+
+
+@pytest.mark.parametrize("name,n,white", [("C1", 3, 1), ("C3", 3, 1), ("C3", 3, 0), ("C2", 3, 1)])
+def test_texture_variant_within_one_lsb(V, name, n, white):
+    """Variant TEX filters certified interior pieces with the texture units.  The unit's arithmetic is
+    not cv::remap's fixed-point filter bit for bit, so this variant is held to BASELINE.json's
+    tolerance (<= 1 LSB per sample against the same map, here = TILED's bytes) instead of 0, and the
+    mismatch histogram is recorded.  It is not the default variant."""
+    import torch
+    from video_annotator_b200 import configs
+    w = configs.workload(name)
+    rots = w.rotations(n, first=57, total=57 + n) if w.sigma_deg else np.tile(np.eye(3), (n, 1, 1))
+    src = V.synth_nv12(torch.empty((n, w.src_size[1] * 3 // 2, w.src_size[0]), dtype=torch.uint8, device="cuda"),
+                       w.src_size[0], w.src_size[1], n, first_index=5, white_noise=bool(white))
+    outs = {}
+    for variant in (TILED, TEX):
+        ctx = V.WarpContext(w.input_camera, w.output_camera, out_size=w.out_size, variant=variant, border=(3, 100, 200))
+        dst = torch.full((n, w.out_size[1] * 3 // 2, w.out_size[0]), 77, dtype=torch.uint8, device="cuda")
+        rdev = torch.empty(n * 9, dtype=torch.float32, device="cuda")
+        ctx.upload_rotations(rots, rdev)
+        ctx.warp_batch(src, dst, rdev, n)
+        torch.cuda.synchronize()
+        outs[variant] = dst.cpu().numpy().astype(np.int16)
+        ctx.close()
+    d = outs[TEX] - outs[TILED]
+    hist = {int(k): int(v) for k, v in zip(*np.unique(d, return_counts=True))}
+    mse = float(np.mean(d.astype(np.float64) ** 2))
+    _record(f"texture_variant_{name}_{'white' if white else 'smooth'}",
+            {"hist_tex_minus_tiled": hist, "samples": int(d.size),
+             "psnr_db": float(10 * np.log10(255.0 ** 2 / mse)) if mse > 0 else float("inf")})
+    assert np.abs(d).max() <= 1
+    assert hist.get(0, 0) > 0.8 * d.size
+
+
+# ---- extension (SURVEY 8 f3): fisheye distortion k1..k4 of the input camera ----------------------
+DIST = (0.02, -0.015, 0.006, -0.001)
+
+
+def _distorted_c1(V):
+    from video_annotator_b200 import configs
+    w = configs.workload("C1")
+    cin = V.Camera.from_matrix(w.input_camera.K, w.src_size[0], w.src_size[1], model=1, distortion=DIST)
+    return w, cin
+
+
+@pytest.mark.parametrize("variant", [GATHER, POLY, TILED])
+def test_fisheye_distortion_coordinates_and_pixels(V, oracle, variant):
+    """Camera::distortion_coefficients (FrameSourceWarp.hpp:31) is carried by the reference but ignored
+    by createMap.cl; here k1..k4 of the cv::fisheye model enter the map.  Pins: the oracle
+    transcription with the distortion step (itself within 1e-3 px of cv2.fisheye.initUndistortRectifyMap,
+    tests/test_oracle_map.py) for the coordinates; the integer filter on the kernel's own map, 0 LSB,
+    for the pixels.  GATHER additionally equals the host restatement of the device sequence bit for bit."""
+    w, cin = _distorted_c1(V)
+    R = rotation_xyz(1.5, -2.0, 0.8)
+    sw, sh = w.src_size
+    ow, oh = w.out_size
+    border = (16, 128, 128)
+    ctx = V.WarpContext(cin, w.output_camera, out_size=w.out_size, border=border, variant=variant)
+    k = oracle.intrinsics(cin.K, w.output_camera.K, dist=DIST)
+    mx, my = [t.cpu().numpy() for t in ctx.dump_coords(R, 0)]
+    cx, cy = [t.cpu().numpy() for t in ctx.dump_coords(R, 1)]
+    ox, oy = oracle.create_map(k, R, oh, ow, threads=NCPU)
+    o0x, _ = oracle.create_map(oracle.intrinsics(cin.K, w.output_camera.K), R, oh, ow, threads=NCPU)
+    assert float(np.nanmax(np.abs(ox - o0x))) > 1.0           # the distortion is not a no-op
+    err = max(float(np.nanmax(np.abs(mx - ox))), float(np.nanmax(np.abs(my - oy))))
+    _record(f"coords_distortion_v{variant}", {"max_err_vs_oracle_px": err})
+    assert err < 1e-3
+    if variant == GATHER:
+        hx, hy = G.host_device_map(k, R, oh, ow)
+        assert G.bits_equal(mx, hx) and G.bits_equal(my, hy)
+    src = oracle.synth_nv12(sw, sh, 3, white_noise=True)
+    got = _warp_one(V, ctx, src, R)
+    ref = _oracle_on_map(oracle, src, sw, sh, mx, my, cx, cy, border)
+    st = G.diff_stats(got, ref)
+    _record(f"pixels_distortion_v{variant}", st)
+    assert st["max"] == 0, st
+    ctx.close()

@@ -81,6 +81,28 @@ def test_map_live_cv_fisheye_full_frame(oracle):
     assert np.nanmax(np.abs(my - cvy)) < 1e-3
 
 
+@pytest.mark.parametrize("dist", [(0.02, -0.015, 0.006, -0.001), (-0.05, 0.01, 0.0, 0.0)])
+def test_map_with_fisheye_distortion_vs_cv_fisheye(oracle, dist):
+    """Extension: k1..k4 of the input camera.  cv2.fisheye.initUndistortRectifyMap is
+    the pin: same model (theta_d = theta (1 + k1 theta^2 + ...)), evaluated in double by OpenCV."""
+    cv2 = pytest.importorskip("cv2")
+    cam = oracle.get_preset_camera(4, 1920, 1080)
+    outc = oracle.get_output_camera(cam, 1.0, False, 1.0)
+    rot = rotation_xyz(1.5, -2.0, 0.8)
+    k = oracle.intrinsics(cam.K, outc.K, dist=dist)
+    mx, my = oracle.create_map(k, rot, outc.height, outc.width, threads=4)
+    r32 = oracle.rot32(rot).astype(np.float64).reshape(3, 3)
+    Kin = np.array([[k.src_focal_x, 0, k.src_center_x], [0, k.src_focal_y, k.src_center_y], [0, 0, 1]], np.float64)
+    Kout = np.array([[k.map_focal_x, 0, k.map_center_x], [0, k.map_focal_y, k.map_center_y], [0, 0, 1]], np.float64)
+    D = np.array([np.float32(d) for d in dist], np.float64)
+    cvx, cvy = cv2.fisheye.initUndistortRectifyMap(Kin, D, r32.T, Kout, (outc.width, outc.height), cv2.CV_32FC1)
+    assert np.nanmax(np.abs(mx - cvx)) < 1e-3
+    assert np.nanmax(np.abs(my - cvy)) < 1e-3
+    # and it is not a no-op
+    m0x, _ = oracle.create_map(oracle.intrinsics(cam.K, outc.K), rot, outc.height, outc.width, threads=4)
+    assert np.nanmax(np.abs(mx - m0x)) > 1.0
+
+
 def test_chroma_map_definition(oracle):
     rng = np.random.default_rng(5)
     mx = rng.uniform(0, 4000, (10, 12)).astype(np.float32)

@@ -522,6 +522,12 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
     g.border = (unsigned)p.border[0] | ((unsigned)p.border[1] << 8) | ((unsigned)p.border[2] << 16) |
                ((unsigned)p.border[3] << 24);
     g.force_exact = (!centre_ok(g.scx) || !centre_ok(g.scy)) ? 1 : 0;
+    g.has_dist = 0;
+    for (int i = 0; i < 4; ++i) {
+        g.kd[i] = p.src_distortion[i];
+        if (!(std::fabs(g.kd[i]) <= 1e6f)) { delete ctx; return fail(nullptr, VAW_ERR_INVALID, "distortion coefficient out of range"); }
+        if (g.kd[i] != 0.0f) g.has_dist = 1;
+    }
     ctx->src_frame_bytes = vaw_frame_bytes(p.format, p.src_width, p.src_height, p.src_width * ctx->channels);
     ctx->dst_frame_bytes = vaw_frame_bytes(p.format, p.out_width, p.out_height, p.out_width * ctx->channels);
 
@@ -553,6 +559,7 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
         d.scx = g.scx; d.scy = g.scy; d.sfx = g.sfx; d.sfy = g.sfy;  // the fp32 scalars, widened
         d.mcx = g.mcx; d.mcy = g.mcy; d.mfx = g.mfx; d.mfy = g.mfy;
         d.inv_mfx = 1.0 / d.mfx; d.inv_mfy = 1.0 / d.mfy;
+        for (int i = 0; i < 4; ++i) d.kd[i] = g.kd[i];  // the fp32 coefficients, widened
         d.src_w = g.src_w; d.src_h = g.src_h; d.out_w = g.out_w; d.out_h = g.out_h;
         d.piece_h = ph;
         make_basis(ctx->basis, ph);

@@ -124,5 +124,6 @@ extern "C" int vaw_params_from_cameras(const vaw_camera* input, const vaw_camera
         p->out_height &= ~1;
     }
     p->format = format;
+    for (int i = 0; i < 4; ++i) p->src_distortion[i] = (float)input->distortion[i];  // zeros for the presets (:35)
     return VAW_OK;
 }

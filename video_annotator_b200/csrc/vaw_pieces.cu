@@ -48,7 +48,11 @@ __device__ __forceinline__ Ray project(const GeomD& g, const RotD& R, double u, 
     const double r = r2 * ir;
     // atan(r)/r is analytic in r^2; the series avoids 0/0 (the reference's NaN at r == 0 is
     // reproduced by sending the piece that contains the axis to the per-pixel path)
-    const double k = r > 1e-4 ? atan(r) * ir : 1.0 - r2 * (1.0 / 3.0 - r2 * 0.2);
+    double k = r > 1e-4 ? atan(r) * ir : 1.0 - r2 * (1.0 / 3.0 - r2 * 0.2);  // theta / r
+    {   // extension: cv::fisheye distortion, theta_d / r = (theta / r) (1 + k1 theta^2 + ... + k4 theta^8)
+        const double th2 = k * k * r2;
+        k *= 1.0 + th2 * (g.kd[0] + th2 * (g.kd[1] + th2 * (g.kd[2] + th2 * g.kd[3])));
+    }
     o.mx = g.scx + c0 * k * g.sfx;
     o.my = g.scy + c1 * k * g.sfy;
     return o;
@@ -109,6 +113,11 @@ build_pieces_kernel(const GeomD g, const PieceBasis basis, const float* __restri
 
     // 1. anchors on the shared node grid
     const int nodes = np * kDegU + 1;
+#ifndef VAW_BUILDER_UNROLL
+#define VAW_BUILDER_UNROLL 1  // anchors per thread evaluated side by side (instruction-level parallelism of the fp64 chains)
+#endif
+    constexpr int kAnchorUnroll = VAW_BUILDER_UNROLL;
+#pragma unroll kAnchorUnroll
     for (int idx = tid; idx < nodes * kNv; idx += kThreads) {
         const int b = idx / nodes, ig = idx - b * nodes;
         const Ray a = project(g, R, node_u(p0 * kDegU + ig), node_v(py * kDegV + b, ph));

@@ -67,6 +67,7 @@ struct PieceBasis {
 struct GeomD {  // the 8 fp32 scalars of FrameSourceWarp.cpp:283-290, widened exactly
     double scx, scy, sfx, sfy, mcx, mcy, mfx, mfy;
     double inv_mfx, inv_mfy;
+    double kd[4];  // cv::fisheye distortion k1..k4 of the input camera (extension; zeros = createMap.cl)
     int src_w, src_h, out_w, out_h;
     int piece_h;
 };

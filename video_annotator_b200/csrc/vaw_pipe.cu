@@ -50,9 +50,16 @@ namespace {
 constexpr int kGroups = VAW_PIPE_GROUPS;            // consumer groups per CTA
 constexpr int kGroupWarps = 4;                      // warps per group
 constexpr int kRowsPerWarp = kPieceHMax / kGroupWarps;      // 8 rows of the piece per warp
-constexpr int kFillerWarp = 1 + kGroups * kGroupWarps;      // fills the pure-border pieces
 constexpr int kIssuers = 2;                                 // warps that issue the loads of the stages the producer described
-constexpr int kIssuerWarp0 = kFillerWarp + 1;
+constexpr int kIssuerWarp0 = 1;                             // warps 0..3 (one warpgroup): producer, two issuers, filler
+constexpr int kFillerWarp = 3;                              // fills the pure-border pieces
+constexpr int kFirstConsumer = 4;
+#ifndef VAW_PIPE_AUX_REGS
+#define VAW_PIPE_AUX_REGS 40       // registers the four auxiliary warps keep (setmaxnreg.dec)
+#endif
+#ifndef VAW_PIPE_CONSUMER_REGS
+#define VAW_PIPE_CONSUMER_REGS 0   // registers the consumer warps grow to (setmaxnreg.inc); 0 = leave the launch allocation
+#endif
 constexpr int kThreads = 32 * (2 + kIssuers + kGroups * kGroupWarps);  // registers are granted per 4 warps: 20 warps -> 96 each, 24 -> 80, 28 -> 72
 constexpr int kSlots = 16;                          // stage descriptors (<= 32: one lane per slot in the producer)
 constexpr int kBatch = 8;                           // pieces per queue ticket
@@ -185,6 +192,9 @@ warp_nv12_pipe_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
 
     if (w == 0) {
         // ================================ producer warp ==========================================
+#if VAW_PIPE_CONSUMER_REGS
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(VAW_PIPE_AUX_REGS));  // hand registers to the consumers
+#endif
         int k = 0;        // stages handed out so far
         int k_head = 0;   // oldest stage whose ring space is still accounted as in use
         unsigned tail = 0, used = 0;
@@ -268,8 +278,11 @@ warp_nv12_pipe_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
         return;
     }
 
-    if (w >= kIssuerWarp0) {
+    if (w >= kIssuerWarp0 && w < kIssuerWarp0 + kIssuers) {
         // ================================ issuer warps ===========================================
+#if VAW_PIPE_CONSUMER_REGS
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(VAW_PIPE_AUX_REGS));  // hand registers to the consumers
+#endif
         // Issuer j starts the loads of stages j, j + kIssuers, ...: the record copy and the
         // TMA boxes of the tile (whole 32-row boxes, then 8-row boxes for the rest; luma first, then chroma).
         for (int k = w - kIssuerWarp0;; k += kIssuers) {
@@ -313,6 +326,9 @@ warp_nv12_pipe_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
 
     if (w == kFillerWarp) {
         // ================================ filler warp ============================================
+#if VAW_PIPE_CONSUMER_REGS
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(VAW_PIPE_AUX_REGS));  // hand registers to the consumers
+#endif
         // Pure-border pieces need no source: this warp writes them, 32 flags per load, independent of
         // the queue (static stride over all pieces of the launch).
         const bool vec_ok =
@@ -354,7 +370,10 @@ warp_nv12_pipe_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
     }
 
     // ==================================== consumer groups ========================================
-    const int grp = (w - 1) / kGroupWarps, wg = (w - 1) % kGroupWarps, gtid = wg * 32 + lane;
+#if VAW_PIPE_CONSUMER_REGS
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(VAW_PIPE_CONSUMER_REGS));  // from the auxiliary warpgroup
+#endif
+    const int grp = (w - kFirstConsumer) / kGroupWarps, wg = (w - kFirstConsumer) % kGroupWarps, gtid = wg * 32 + lane;
     const bool even_ok = ((reinterpret_cast<uintptr_t>(b.dst) | (uintptr_t)g.dst_pitch | (uintptr_t)b.dst_frame_stride) & 1) == 0;
     const bool word_base_ok = ((reinterpret_cast<uintptr_t>(b.dst) | (uintptr_t)g.dst_pitch | (uintptr_t)b.dst_frame_stride) & 3) == 0;
     float4* const coefs = reinterpret_cast<float4*>(smem + kCoefOffset + grp * kCoefBytes);

@@ -47,12 +47,19 @@ class Camera:
     def model(self):
         return self._c.model
 
+    @property
+    def distortion(self):
+        return np.array(self._c.distortion[:], np.float64)
+
     @staticmethod
-    def from_matrix(K, width, height, model=0):
+    def from_matrix(K, width, height, model=0, distortion=None):
         c = _lib.VawCamera()
         c.model, c.width, c.height = model, width, height
         for i, v in enumerate(np.asarray(K, np.float64).reshape(9)):
             c.matrix[i] = v
+        if distortion is not None:
+            for i in range(4):
+                c.distortion[i] = float(distortion[i])
         return Camera(c)
 
 
