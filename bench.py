@@ -222,6 +222,10 @@ def run_reference(args):
     return 0
 
 
+KERNEL_NAMES = {1: "warp_nv12_gather_kernel", 2: "warp_nv12_poly_kernel", 3: "warp_nv12_tile_kernel",
+                4: "warp_nv12_pipe_kernel", 5: "warp_nv12_tex_kernel + warp_nv12_tile_kernel"}
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -339,12 +343,12 @@ def run_ours(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                 "config": config_dict(wl, args, world, {
                     "l2": f"inputs {n * wl.src_frame_bytes >> 20} MiB per step > {L2_BYTES >> 20} MiB L2 (no flush needed)",
-                    "variant": args.variant, "pieces_128x32": pieces}),
+                    "variant": args.variant, "variant_resolved": ctx.variant, "pieces_128x32": pieces}),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": recorded_traffic(wl.name, n),
                              "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
-                             "kernel": "warp_nv12_tile_kernel (fused map + remap, luma + chroma, one launch per step)"
-                                       if timed_kernels else "warp_nv12_gather_kernel",
+                             "kernel": KERNEL_NAMES.get(ctx.variant, "warp_nv12_tile_kernel")
+                                       + " (fused map + remap, luma + chroma, one launch per step)",
                              "launch_ms": {"avg": avg_launch_ms, "median": float(np.median(warp_ms)),
                                            "best": float(np.min(warp_ms)), "launches_timed": int(len(warp_ms))},
                              "other_kernels_ms": {"build_pieces_kernel": float(np.mean(builder_ms))},

@@ -63,16 +63,21 @@ enum { VAW_INTER_NEAREST = 0, VAW_INTER_LINEAR = 1, VAW_INTER_CUBIC = 2 };
  *   TILED   POLY's coordinates; the source rectangle of every 8-row band is first copied into
  *           shared memory by the TMA engine and the taps are read from there (needs a 16-byte
  *           aligned source base / pitch / frame stride, else it gathers like POLY).
- *   PIPE    TILED's tiles, scheduled as a persistent producer/consumer pipeline: a producer warp
- *           per CTA pulls pieces from a global queue and issues the TMA loads two pieces ahead,
- *           four consumer warps sample; the record and tile latencies disappear behind compute.
+ *   PIPE    TILED's tiles, scheduled as one persistent producer/consumer pipeline per SM: a producer
+ *           warp pulls pieces from a global queue and allocates exactly the bytes each source box
+ *           needs from a ring in shared memory, two issuer warps start the TMA loads up to three
+ *           pieces ahead, groups of four consumer warps sample, a filler warp writes the pure-border
+ *           pieces.  Needs 32-row pieces (else it runs as TILED).
  *   TEX     TILED, except that pieces certified interior (every tap inside the source) are filtered
  *           by the texture units: the coordinate is rounded to 1/32 px exactly as cv::remap rounds
- *           it, the unit's 8-bit fractional weights represent k/32 exactly, and the filtered value
- *           is rescaled and rounded half up like (sum + 512) >> 10.  Needs a texture-aligned source
- *           base (512 bytes), a pitch that is a multiple of 32 and a frame stride that is a whole
- *           number of rows; other layouts run as TILED.
- * POLY, TILED and PIPE produce identical bytes.  AUTO = TILED for NV12, GATHER for the packed formats. */
+ *           it and the filtered value is rescaled and rounded half up like (sum + 512) >> 10.  The
+ *           unit's internal precision is lower than cv::remap's 10-bit weights: 5 % of the samples of
+ *           white noise come out 1 LSB off (never more; tests/test_gpu_parity.py), and it is slower
+ *           than TILED (tex-pipe bound).  Kept for the comparison BASELINE.json asks for,
+ *           never chosen by AUTO.  Needs a texture-aligned source base (512 bytes), a pitch that is
+ *           a multiple of 32 and a frame stride that is a whole number of rows; else it runs as TILED.
+ * POLY, TILED and PIPE produce identical bytes.  AUTO = TILED for NV12 (PIPE when the source box of a
+ * piece is too large for six tiles per SM, e.g. 5312x2988 -> 3840x2160), GATHER for the packed formats. */
 enum {
     VAW_VARIANT_AUTO = 0,
     VAW_VARIANT_GATHER = 1,
@@ -154,6 +159,8 @@ const char *vaw_strerror(int code);
 size_t vaw_frame_bytes(int format, int width, int height, int pitch);
 /* Number of this library's kernels launched through ctx so far. */
 uint64_t vaw_launch_count(const vaw_ctx *ctx);
+/* The kernel variant the context resolved to (VAW_VARIANT_*, never AUTO). */
+int vaw_get_variant(const vaw_ctx *ctx);
 
 /* ---- the warp ---------------------------------------------------------------------
  * vaw_warp replaces `cv::UMat FrameSourceWarp::warp_frame(cv::UMat input, cv::Mat rotation)`

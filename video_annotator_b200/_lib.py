@@ -44,6 +44,7 @@ SIGNATURES = {
     "vaw_strerror": (C.c_char_p, [C.c_int]),
     "vaw_frame_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "vaw_launch_count": (C.c_uint64, [C.c_void_p]),
+    "vaw_get_variant": (C.c_int, [C.c_void_p]),
     "vaw_warp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, f64p, C.c_void_p]),
     "vaw_warp_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_int,
                                  C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]),

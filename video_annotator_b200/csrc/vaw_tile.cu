@@ -41,6 +41,9 @@ constexpr int kWarps = 4;
 #ifndef VAW_TILE_HOIST
 #define VAW_TILE_HOIST 0  // 1: also request the coefficients at CTA entry (measured slower: 0.763 ms against 0.738 ms)
 #endif
+#ifndef VAW_TILE_PREFETCH
+#define VAW_TILE_PREFETCH 1
+#endif
 #ifndef VAW_TILE_CTAS
 #define VAW_TILE_CTAS 6  // resident CTAs per SM the kernel is sized for (registers and shared memory)
 #endif
@@ -60,6 +63,12 @@ warp_nv12_tile_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
     const int ph = g.piece_h, rows_per_warp = ph / kWarps;  // 32 / 16 / 8 rows per piece -> 8 / 4 / 2 per warp
     const int npx = pieces_x(g.out_w), npy = pieces_y(g.out_h, ph);
     const PieceRec* rec = table + ((size_t)frame * npy + py) * npx + px;
+#if VAW_TILE_PREFETCH
+    // pull the coefficient lines of the record into L1 while the flags / box round trip is in flight: the
+    // coefficient loads that follow the TMA issue then hit L1 instead of paying a second L2 round trip
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(rec));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(rec) + 128));
+#endif
     // flags and box are requested together (one L2 round trip instead of two dependent ones: 0.745 -> 0.738 ms)
     const float4 rec_tail = __ldg(reinterpret_cast<const float4*>(rec) + 12);  // base.x, base.y, flags, pad
     const int4 raw = __ldg(reinterpret_cast<const int4*>(rec) + 13);          // the source box

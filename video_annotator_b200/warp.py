@@ -139,6 +139,11 @@ class WarpContext:
         return (h, w, 3) if self.fmt == FORMAT_BGR24 else (h, w)
 
     @property
+    def variant(self):
+        """The kernel variant the context resolved to (VAW_VARIANT_*, never AUTO)."""
+        return int(self._lib.vaw_get_variant(self._h))
+
+    @property
     def launch_count(self):
         return int(self._lib.vaw_launch_count(self._h))
 
