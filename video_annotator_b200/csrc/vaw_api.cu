@@ -562,6 +562,7 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
         d.mcx = g.mcx; d.mcy = g.mcy; d.mfx = g.mfx; d.mfy = g.mfy;
         d.inv_mfx = 1.0 / d.mfx; d.inv_mfy = 1.0 / d.mfy;
         for (int i = 0; i < 4; ++i) d.kd[i] = g.kd[i];  // the fp32 coefficients, widened
+        d.has_dist = g.has_dist;
         d.src_w = g.src_w; d.src_h = g.src_h; d.out_w = g.out_w; d.out_h = g.out_h;
         d.piece_h = ph;
         make_basis(ctx->basis, ph);

@@ -49,7 +49,7 @@ __device__ __forceinline__ Ray project(const GeomD& g, const RotD& R, double u, 
     // atan(r)/r is analytic in r^2; the series avoids 0/0 (the reference's NaN at r == 0 is
     // reproduced by sending the piece that contains the axis to the per-pixel path)
     double k = r > 1e-4 ? atan(r) * ir : 1.0 - r2 * (1.0 / 3.0 - r2 * 0.2);  // theta / r
-    {   // extension: cv::fisheye distortion, theta_d / r = (theta / r) (1 + k1 theta^2 + ... + k4 theta^8)
+    if (g.has_dist) {  // extension: cv::fisheye distortion, theta_d / r = (theta / r) (1 + k1 theta^2 + ... + k4 theta^8)
         const double th2 = k * k * r2;
         k *= 1.0 + th2 * (g.kd[0] + th2 * (g.kd[1] + th2 * (g.kd[2] + th2 * g.kd[3])));
     }

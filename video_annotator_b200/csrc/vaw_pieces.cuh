@@ -70,6 +70,7 @@ struct GeomD {  // the 8 fp32 scalars of FrameSourceWarp.cpp:283-290, widened ex
     double kd[4];  // cv::fisheye distortion k1..k4 of the input camera (extension; zeros = createMap.cl)
     int src_w, src_h, out_w, out_h;
     int piece_h;
+    int has_dist;  // any kd != 0
 };
 
 inline __host__ __device__ int pieces_x(int out_w) { return (out_w + kPieceW - 1) / kPieceW; }

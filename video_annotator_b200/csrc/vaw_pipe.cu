@@ -333,6 +333,8 @@ warp_nv12_pipe_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
         // the queue (static stride over all pieces of the launch).
         const bool vec_ok =
             ((reinterpret_cast<uintptr_t>(b.dst) | (uintptr_t)g.dst_pitch | (uintptr_t)b.dst_frame_stride) & 15) == 0;
+        const bool pair_ok =
+            ((reinterpret_cast<uintptr_t>(b.dst) | (uintptr_t)g.dst_pitch | (uintptr_t)b.dst_frame_stride) & 1) == 0;
         const unsigned yw = (g.border & 255u) * 0x01010101u;
         const unsigned cw = ((g.border >> 8) & 0xffffu) * 0x00010001u;
         for (int base = (int)blockIdx.x * 32; base < total; base += (int)gridDim.x * 32) {
@@ -355,6 +357,18 @@ warp_nv12_pipe_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
                     const uint4 y4 = make_uint4(yw, yw, yw, yw), c4 = make_uint4(cw, cw, cw, cw);
                     for (int r = sub; r < rows; r += 4, yrow += 4 * (size_t)g.dst_pitch) *reinterpret_cast<uint4*>(yrow) = y4;
                     for (int r = sub; r < rows / 2; r += 4, crow += 4 * (size_t)g.dst_pitch) *reinterpret_cast<uint4*>(crow) = c4;
+                } else if (pair_ok && px * kPieceW + kPieceW <= g.out_w) {
+                    // even base / pitch only (e.g. a 2482-byte pitch): 2 bytes per lane, two stores per row
+                    uint8_t* yrow = dst + (size_t)v_base * g.dst_pitch + px * kPieceW + 2 * lane;
+                    uint8_t* crow = dst + (size_t)(g.out_h + (v_base >> 1)) * g.dst_pitch + px * kPieceW + 2 * lane;
+                    for (int r = 0; r < rows; ++r, yrow += g.dst_pitch) {
+                        *reinterpret_cast<uint16_t*>(yrow) = (uint16_t)yw;
+                        *reinterpret_cast<uint16_t*>(yrow + 64) = (uint16_t)yw;
+                    }
+                    for (int r = 0; r < rows / 2; ++r, crow += g.dst_pitch) {
+                        *reinterpret_cast<uint16_t*>(crow) = (uint16_t)cw;
+                        *reinterpret_cast<uint16_t*>(crow + 64) = (uint16_t)cw;
+                    }
                 } else {
                     const int u0 = px * kPieceW + 4 * lane, valid = g.out_w - u0;
                     uint8_t* yrow = dst + (size_t)v_base * g.dst_pitch + u0;

@@ -108,7 +108,7 @@ warp_nv12_tex_kernel(const Geom g, const FrameBatch b, const PieceRec* __restric
     const int lane = threadIdx.x, w = threadIdx.y;
     const int px = blockIdx.x, py = blockIdx.y, frame = blockIdx.z;
     const int ph = g.piece_h, rows_per_warp = ph / kWarps;
-    const int npx = pieces_x(g.out_w), npy = pieces_y(g.out_h, ph);
+    const int npx = (int)gridDim.x, npy = (int)gridDim.y;  // = pieces_x(out_w), pieces_y(out_h, ph): the launch grid, no division
     const PieceRec* rec = table + ((size_t)frame * npy + py) * npx + px;
     const unsigned flags = __ldg(&rec->flags);
     if ((flags & (kPiecePoly | kPieceInterior)) != (kPiecePoly | kPieceInterior)) return;  // vaw_tile.cu's

@@ -61,7 +61,7 @@ warp_nv12_tile_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
     const int lane = threadIdx.x, w = threadIdx.y, tid = w * 32 + lane;
     const int px = blockIdx.x, py = blockIdx.y, frame = blockIdx.z;
     const int ph = g.piece_h, rows_per_warp = ph / kWarps;  // 32 / 16 / 8 rows per piece -> 8 / 4 / 2 per warp
-    const int npx = pieces_x(g.out_w), npy = pieces_y(g.out_h, ph);
+    const int npx = (int)gridDim.x, npy = (int)gridDim.y;  // = pieces_x(out_w), pieces_y(out_h, ph): the launch grid, no division
     const PieceRec* rec = table + ((size_t)frame * npy + py) * npx + px;
 #if VAW_TILE_PREFETCH
     // pull the coefficient lines of the record into L1 while the flags / box round trip is in flight: the
