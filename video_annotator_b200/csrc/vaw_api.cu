@@ -600,6 +600,7 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
                 if (cap < vaw::kTileCapMin) cap = vaw::kTileCapMin;
                 if (cap > vaw::kTileCapMax) cap = vaw::kTileCapMax;
                 ctx->tile_cap = (int)cap;
+                ctx->gd.tile_cap = ctx->tile_cap;  // the builder picks the tile pitch of every piece against it
                 // AUTO: one CTA per piece keeps six tiles per SM in flight only while a tile fits 227 KB / 6;
                 // for larger source boxes (C5: 50 KB) the ring pipeline, which allocates exactly what each
                 // piece needs, is faster (C5: 60.3 k against 56.3 k frames/s)

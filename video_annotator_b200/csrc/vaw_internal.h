@@ -32,7 +32,7 @@ cudaError_t launch_warp_nv12_poly(const Geom& g, const FrameBatch& b, const Piec
 
 // Variant TILED (vaw_tile.cu): tensor maps over the NV12 clip, viewed as a 3-D tensor of 4-byte
 // elements (pitch/4 x 3H/2 rows x frames), one per tile row pitch (box = pitch/4 x 8 rows).
-constexpr int kTileMinPitch = 128, kTileMaxPitch = 448, kTilePitchStep = 32;
+constexpr int kTileMinPitch = kStageMinPitch, kTileMaxPitch = kStageMaxPitch, kTilePitchStep = 32;
 constexpr int kTileCapMin = 16 << 10, kTileCapMax = 160 << 10;  // per-CTA tile bytes (chosen per geometry)
 constexpr int kTileWidths = (kTileMaxPitch - kTileMinPitch) / kTilePitchStep + 1;
 struct alignas(64) TileMaps {

@@ -233,14 +233,29 @@ build_pieces_kernel(const GeomD g, const PieceBasis basis, const float* __restri
         rec.flags = flags;
         rec.pad = 0;
         rec.box = box;
+        PieceStage st = {0, 0, 0, 0, 0, 0, 0, 0};
+        if ((flags & kPiecePoly) && !(flags & kPieceOutside)) {
+            const int lx0 = box.x0 & ~15, wb = (box.x1 - lx0 + 16) & ~15;
+            const int cbx0 = (2 * box.cx0) & ~15, cwb = (2 * box.cx1 + 2 - cbx0 + 15) & ~15;
+            const int nr8 = (box.y1 - box.y0 + 8) & ~7, cnr8 = (box.cy1 - box.cy0 + 8) & ~7;  // rows, rounded up to whole boxes
+            const int want = max(wb, cwb);
+            const int pl128 = (want + 127) & ~127, pl32 = max(kStageMinPitch, (want + 31) & ~31);
+            const int pl = (pl128 <= kStageMaxPitch && pl128 * (nr8 + cnr8) <= g.tile_cap) ? pl128 : pl32;
+            if (pl <= kStageMaxPitch && nr8 > 0 && cnr8 > 0 && nr8 < 65536 && cnr8 < 65536) {
+                st.lx0 = (int16_t)lx0; st.by0 = box.y0; st.cbx0 = (int16_t)cbx0; st.cy0 = box.cy0;
+                st.pl = (uint16_t)pl; st.nr8 = (uint16_t)nr8; st.cnr8 = (uint16_t)cnr8;
+            }
+        }
+        rec.stage = st;
     }
     __syncthreads();
     if (tid < np && bad[tid]) {  // failed the accuracy certificate: per-pixel evaluation
         recs[tid].flags = 0;
         recs[tid].box = PieceBox{0, -1, 0, -1, 0, -1, 0, -1};
+        recs[tid].stage = PieceStage{0, 0, 0, 0, 0, 0, 0, 0};
     }
     __syncthreads();
-    // coalesced copy of the records (208 bytes each) to the table
+    // coalesced copy of the records (240 bytes each) to the table
     PieceRec* out = table + ((size_t)frame * npy + py) * npx + p0;
     const uint32_t* s32 = reinterpret_cast<const uint32_t*>(recs);
     uint32_t* d32 = reinterpret_cast<uint32_t*>(out);

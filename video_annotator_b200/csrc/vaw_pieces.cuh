@@ -29,6 +29,7 @@ constexpr int kPieceHMax = 32; // rows per piece: 32, 16 or 8
 constexpr int kDegU = 5;       // polynomial degree along u  (6 anchors, spacing 25.6 px)
 constexpr int kDegV = 3;       // polynomial degree along v  (4 anchors, spacing PH/3 rows)
 constexpr int kNu = kDegU + 1, kNv = kDegV + 1;
+constexpr int kStageMinPitch = 128, kStageMaxPitch = 448;  // tile row pitches (= kTileMinPitch / kTileMaxPitch, vaw_internal.h)
 
 enum : uint32_t {
     kPiecePoly = 1u,      // polynomial coordinates certified for this piece
@@ -43,7 +44,19 @@ struct PieceBox {
     int16_t cx0, cx1, cy0, cy1;  // chroma (U,V pairs)
 };
 
-// One record per (frame, piece): 224 bytes, 16-byte aligned.
+// How the samplers stage the piece's source box in shared memory (same integer arithmetic for every
+// variant, done once here instead of by every thread of the sampler): tile rows are `pl` bytes apart,
+// start at source byte lx0 / cbx0 (multiples of 16) and row by0 / cy0, and come in whole 8-row boxes.
+// The pitch is a multiple of 128 bytes (32 banks) when that fits the tile capacity -- the lanes of one
+// LDS then keep distinct banks however many source rows they straddle -- else the tightest multiple of 32.
+struct PieceStage {
+    int16_t lx0, by0, cbx0, cy0;
+    uint16_t pl;          // 0: the box cannot be staged (wider than the largest tile pitch)
+    uint16_t nr8, cnr8;   // luma / chroma tile rows
+    uint16_t pad;
+};
+
+// One record per (frame, piece): 240 bytes, 16-byte aligned.
 // coordinate = base + sum_{i<=5, j<=3} c[i][j] * s^i * t^j,
 //   s = (du - 63.5) / 64, t = (dv - (PH-1)/2) * 2/PH, (du, dv) = pixel offset inside the piece.
 // x and y coefficients are interleaved so that both coordinates run through the packed
@@ -53,9 +66,10 @@ struct PieceRec {
     float2 base;           // integers: base + offset rounds once to the fp32 coordinate
     uint32_t flags;
     uint32_t pad;
-    PieceBox box;  // valid for certified pieces that are not pure border
+    PieceBox box;      // valid for certified pieces that are not pure border
+    PieceStage stage;  // derived from `box`
 };
-static_assert(sizeof(PieceRec) == 224, "piece record layout");
+static_assert(sizeof(PieceRec) == 240, "piece record layout");
 
 // Lagrange -> monomial conversion matrices for the anchor nodes (computed on the host in
 // double precision, passed by value to the builder kernel).
@@ -71,6 +85,7 @@ struct GeomD {  // the 8 fp32 scalars of FrameSourceWarp.cpp:283-290, widened ex
     int src_w, src_h, out_w, out_h;
     int piece_h;
     int has_dist;  // any kd != 0
+    int tile_cap;  // bytes of shared memory a tile may take with a 128-byte-multiple pitch (0: always the tightest pitch)
 };
 
 inline __host__ __device__ int pieces_x(int out_w) { return (out_w + kPieceW - 1) / kPieceW; }

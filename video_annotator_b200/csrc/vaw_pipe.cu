@@ -102,23 +102,15 @@ __device__ __forceinline__ void fence_async_smem()
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-// Tile geometry of one source box (same integer arithmetic as vaw_tile.cu): returns the bytes needed, 0 if it cannot be staged.
-__device__ __forceinline__ unsigned plan_tile(int4 raw, int tile_cap, int enabled, int& pl, int& nr8, int& cnr8, int& lorg, int& corg)
+// The tile of one piece as the builder laid it out (PieceStage): returns the bytes needed, 0 if it cannot be staged.
+__device__ __forceinline__ unsigned plan_tile(int4 raw, int enabled, int& pl, int& rows, int& lorg, int& corg)
 {
-    const int bx0 = (int16_t)(raw.x & 0xffff), bx1 = (int16_t)(raw.x >> 16);
-    const int by0 = (int16_t)(raw.y & 0xffff), by1 = (int16_t)(raw.y >> 16);
-    const int cx0 = (int16_t)(raw.z & 0xffff), cx1 = (int16_t)(raw.z >> 16);
-    const int cy0 = (int16_t)(raw.w & 0xffff), cy1 = (int16_t)(raw.w >> 16);
-    const int lx0 = bx0 & ~15, wb = (bx1 - lx0 + 16) & ~15;
-    const int cbx0 = (2 * cx0) & ~15, cwb = (2 * cx1 + 2 - cbx0 + 15) & ~15;
-    nr8 = (by1 - by0 + 8) & ~7;
-    cnr8 = (cy1 - cy0 + 8) & ~7;
-    const int want = max(wb, cwb);
-    const int pl128 = (want + 127) & ~127, pl32 = max(kTileMinPitch, (want + 31) & ~31);
-    pl = (pl128 <= kTileMaxPitch && pl128 * (nr8 + cnr8) <= tile_cap) ? pl128 : pl32;
-    lorg = (lx0 & 0xffff) | (by0 << 16);
-    corg = (cbx0 & 0xffff) | (cy0 << 16);
-    if (!enabled || pl > kTileMaxPitch || nr8 <= 0 || cnr8 <= 0 || pl * (nr8 + cnr8) > kRingBytes / 2) return 0u;
+    lorg = raw.x;                      // lx0 | by0 << 16
+    corg = raw.y;                      // cbx0 | cy0 << 16
+    pl = raw.z & 0xffff;
+    const int nr8 = (raw.z >> 16) & 0xffff, cnr8 = raw.w & 0xffff;
+    rows = nr8 | (cnr8 << 16);
+    if (!enabled || pl == 0 || pl * (nr8 + cnr8) > kRingBytes / 2) return 0u;
     return (unsigned)(pl * (nr8 + cnr8) + 127) & ~127u;
 }
 
@@ -205,7 +197,7 @@ warp_nv12_pipe_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
             used -= __shfl_sync(0xffffffffu, my_size, s);
             ++k_head;
         };
-        // metadata of a ticket's pieces: lane i < kBatch holds the flags and the source box of piece first + i
+        // metadata of a ticket's pieces: lane i < kBatch holds the flags and the stage descriptor of piece first + i
         auto fetch = [&](int& first, unsigned& flags, int4& box) {
             int f = 0;
             if (lane == 0) f = (int)atomicAdd(counter, (unsigned)kBatch);
@@ -215,7 +207,7 @@ warp_nv12_pipe_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
             if (lane < kBatch && first + lane < total) {
                 const int4* r4 = reinterpret_cast<const int4*>(table + first + lane);
                 flags = (unsigned)__ldg(r4 + 12).z;
-                box = __ldg(r4 + 13);
+                box = __ldg(r4 + 14);  // PieceStage
             }
         };
         int first_n; unsigned flags_n; int4 box_n;
@@ -233,9 +225,7 @@ warp_nv12_pipe_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
             int pl_l = 0, rows_l = 0, lorg_l = 0, corg_l = 0, mode_l = kModeDirect;
             unsigned need_l = 0u;
             if ((flags_l & (kPiecePoly | kPieceOutside)) == kPiecePoly) {
-                int nr8, cnr8;
-                need_l = plan_tile(box, maps.tile_cap, maps.enabled, pl_l, nr8, cnr8, lorg_l, corg_l);
-                rows_l = nr8 | (cnr8 << 16);
+                need_l = plan_tile(box, maps.enabled, pl_l, rows_l, lorg_l, corg_l);
                 if (need_l) mode_l = kModeStaged;
             }
             // pure-border pieces are the filler warp's; every other piece gets a stage, in queue order

@@ -71,7 +71,7 @@ warp_nv12_tile_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
 #endif
     // flags and box are requested together (one L2 round trip instead of two dependent ones: 0.745 -> 0.738 ms)
     const float4 rec_tail = __ldg(reinterpret_cast<const float4*>(rec) + 12);  // base.x, base.y, flags, pad
-    const int4 raw = __ldg(reinterpret_cast<const int4*>(rec) + 13);          // the source box
+    const int4 raw = __ldg(reinterpret_cast<const int4*>(rec) + 14);          // how to stage the source box (PieceStage)
     float2 c[kNu][kNv];
 #if VAW_TILE_HOIST
     load_coeffs(rec, c);
@@ -103,6 +103,16 @@ warp_nv12_tile_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
     if (flags & kPieceOutside) {  // pure border: nothing to compute
         const unsigned yw = (g.border & 255u) * 0x01010101u;
         const unsigned cw = ((g.border >> 8) & 0xffffu) * 0x00010001u;
+        if (((reinterpret_cast<uintptr_t>(f.dst) | (uintptr_t)g.dst_pitch) & 15) == 0 && u_lo + kPieceW <= g.out_w) {
+            // 16 bytes per lane: 8 lanes per row, 4 rows per store instruction
+            const int sub = lane >> 3, col = (lane & 7) * 16;
+            uint8_t* yrow = f.dst + (size_t)(v_base + dv0 + sub) * g.dst_pitch + u_lo + col;
+            uint8_t* crow = f.dst + (size_t)(g.out_h + ((v_base + dv0) >> 1) + sub) * g.dst_pitch + u_lo + col;
+            const uint4 y4 = make_uint4(yw, yw, yw, yw), c4 = make_uint4(cw, cw, cw, cw);
+            for (int r = sub; r < my_rows; r += 4, yrow += 4 * (size_t)g.dst_pitch) *reinterpret_cast<uint4*>(yrow) = y4;
+            for (int r = sub; r < my_rows / 2; r += 4, crow += 4 * (size_t)g.dst_pitch) *reinterpret_cast<uint4*>(crow) = c4;
+            return;
+        }
         if (valid > 0)
             for (int dv = 0; dv < my_rows; dv += 2) {
                 store_word<true>(o.y0, yw, valid);
@@ -123,20 +133,11 @@ warp_nv12_tile_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
         return;
     }
 
-    // ---- the source rectangle of this piece's taps (block-uniform) ---------------------------
-    const int bx0 = (int16_t)(raw.x & 0xffff), bx1 = (int16_t)(raw.x >> 16);
-    const int by0 = (int16_t)(raw.y & 0xffff), by1 = (int16_t)(raw.y >> 16);
-    const int cx0 = (int16_t)(raw.z & 0xffff), cx1 = (int16_t)(raw.z >> 16);
-    const int cy0 = (int16_t)(raw.w & 0xffff), cy1 = (int16_t)(raw.w >> 16);
-    const int lx0 = bx0 & ~15, wb = (bx1 - lx0 + 16) & ~15;
-    const int cbx0 = (2 * cx0) & ~15, cwb = (2 * cx1 + 2 - cbx0 + 15) & ~15;
-    const int nr8 = (by1 - by0 + 8) & ~7, cnr8 = (cy1 - cy0 + 8) & ~7;  // rows, rounded up to whole boxes
-    // Tile row pitch: a multiple of 128 bytes (32 banks) when that fits -- the lanes of one LDS then
-    // keep distinct banks however many source rows they straddle -- else the tightest multiple of 32.
-    const int need = max(wb, cwb);
-    const int pl128 = (need + 127) & ~127, pl32 = max(kTileMinPitch, (need + 31) & ~31);
-    const int pl = (pl128 <= kTileMaxPitch && pl128 * (nr8 + cnr8) <= maps.tile_cap) ? pl128 : pl32;
-    const bool fits = maps.enabled && pl <= kTileMaxPitch && nr8 > 0 && cnr8 > 0 && pl * (nr8 + cnr8) <= maps.tile_cap;
+    // ---- the tile of this piece's source rectangle, as the builder laid it out (block-uniform) ------
+    const int lx0 = (int16_t)(raw.x & 0xffff), by0 = raw.x >> 16;
+    const int cbx0 = (int16_t)(raw.y & 0xffff), cy0 = raw.y >> 16;
+    const int pl = raw.z & 0xffff, nr8 = (raw.z >> 16) & 0xffff, cnr8 = raw.w & 0xffff;
+    const bool fits = maps.enabled && pl != 0 && pl * (nr8 + cnr8) <= maps.tile_cap;
 
     if (!fits) {  // gather from global memory like variant POLY (each warp collapses for itself)
         if (my_rows <= 0) return;

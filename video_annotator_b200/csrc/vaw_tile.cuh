@@ -139,16 +139,30 @@ __device__ __forceinline__ void fill_border(uint8_t* tile, int pl, int tile_rows
     unsigned* w = reinterpret_cast<unsigned*>(tile);
     for (int idx = tid; idx < r_lo * wpr; idx += nthr) w[idx] = pattern;
     for (int idx = r_hi * wpr + tid; idx < tile_rows * wpr; idx += nthr) w[idx] = pattern;
-    const int c_lo = min(max(-x0, 0), pl);                    // bytes [0, c_lo) are left of the plane
+    const int c_lo = min(max(-x0, 0), pl);                    // bytes [0, c_lo) are left of the plane (a multiple of 4)
     const int c_hi = min(max(n_bytes - x0, c_lo), pl);        // bytes [c_hi, pl) are right of it
-    const int strip = c_lo + (pl - c_hi);                     // outside bytes per inside row
-    if (strip > 0) {
-        const int total = (r_hi - r_lo) * strip;
-        for (int idx = tid; idx < total; idx += nthr) {
-            const int r = idx / strip, k = idx - r * strip;
-            const int c = k < c_lo ? k : c_hi + (k - c_lo);
-            tile[(r_lo + r) * pl + c] = (uint8_t)(pattern >> (8 * (c & 3)));
+    if (c_lo == 0 && c_hi == pl) return;
+    // whole outside words of an inside row: [0, w_lo) and [w_hi, wpr); then the bytes [c_hi, 4 w_hi) of a
+    // plane whose width is not a multiple of 4.  No division: lanes run along the words, warps along the
+    // rows -- or one row per thread when the strips are only a few words wide.
+    const int w_lo = c_lo >> 2, w_hi = min((c_hi + 3) >> 2, wpr);
+    const int nw = w_lo + (wpr - w_hi);
+    if (nw > 8) {
+        const int sub = tid & 31, nwarp = nthr >> 5;
+        for (int r = r_lo + (tid >> 5); r < r_hi; r += nwarp) {
+            unsigned* row = w + r * wpr;
+            for (int j = sub; j < nw; j += 32) row[j < w_lo ? j : w_hi + (j - w_lo)] = pattern;
         }
+    } else if (nw > 0) {
+        for (int r = r_lo + tid; r < r_hi; r += nthr) {
+            unsigned* row = w + r * wpr;
+            for (int j = 0; j < nw; ++j) row[j < w_lo ? j : w_hi + (j - w_lo)] = pattern;
+        }
+    }
+    if (c_hi & 3) {
+        const int end = min(4 * w_hi, pl);
+        for (int r = r_lo + tid; r < r_hi; r += nthr)
+            for (int c = c_hi; c < end; ++c) tile[r * pl + c] = (uint8_t)(pattern >> (8 * (c & 3)));
     }
 }
 
