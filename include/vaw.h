@@ -76,8 +76,9 @@ enum { VAW_INTER_NEAREST = 0, VAW_INTER_LINEAR = 1, VAW_INTER_CUBIC = 2 };
  *           than TILED (tex-pipe bound).  Kept for the comparison BASELINE.json asks for,
  *           never chosen by AUTO.  Needs a texture-aligned source base (512 bytes), a pitch that is
  *           a multiple of 32 and a frame stride that is a whole number of rows; else it runs as TILED.
- * POLY, TILED and PIPE produce identical bytes.  AUTO = TILED for NV12 (PIPE when the source box of a
- * piece is too large for six tiles per SM, e.g. 5312x2988 -> 3840x2160), GATHER for the packed formats. */
+ * POLY, TILED and PIPE produce identical bytes.  AUTO for NV12 = TILED, or PIPE where it measured faster:
+ * when the source box of a piece is too large for six tiles per SM (5312x2988 -> 3840x2160) or small
+ * enough for the ring to run four pieces ahead (2704x1520); GATHER for the packed formats. */
 enum {
     VAW_VARIANT_AUTO = 0,
     VAW_VARIANT_GATHER = 1,

@@ -601,10 +601,14 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
                 if (cap > vaw::kTileCapMax) cap = vaw::kTileCapMax;
                 ctx->tile_cap = (int)cap;
                 ctx->gd.tile_cap = ctx->tile_cap;  // the builder picks the tile pitch of every piece against it
-                // AUTO: one CTA per piece keeps six tiles per SM in flight only while a tile fits 227 KB / 6;
-                // for larger source boxes (C5: 50 KB) the ring pipeline, which allocates exactly what each
-                // piece needs, is faster (C5: 60.3 k against 56.3 k frames/s)
-                if (p.variant == VAW_VARIANT_AUTO && need > six && ph == vaw::kPieceHMax) ctx->variant = VAW_VARIANT_PIPE;
+                // AUTO: one CTA per piece (TILED) keeps six tiles per SM in flight, without look-ahead.  The ring
+                // pipeline (PIPE) allocates exactly what each piece needs: it wins when tiles are too large for
+                // six per SM (C5, 50 KB: 63.0 k against 57.3 k frames/s) and when they are small enough for
+                // the ring to run four or more pieces ahead of its four consumer groups (C2, 16 KB: 137 k
+                // against 131 k); in between (C3, 28 KB, seven per ring) TILED's 24 sampling warps are faster.
+                if (p.variant == VAW_VARIANT_AUTO && ph == vaw::kPieceHMax && need > 0 &&
+                    (need > six || (long long)ctx->tile_cap * 8 <= (vaw::pipe_smem_bytes(0) - (30 << 10))))
+                    ctx->variant = VAW_VARIANT_PIPE;
             }
         }
         if (e != cudaSuccess) {
