@@ -83,6 +83,35 @@ warp_nv12_tile_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
     const int my_rows = max(0, min(rows_per_warp, rows - dv0));
     const int valid = g.out_w - u0;
 
+    if (b.skip_interior && (flags & (kPiecePoly | kPieceInterior)) == (kPiecePoly | kPieceInterior))
+        return;  // variant TEX: this piece belongs to the texture kernel
+
+    if (flags & kPieceOutside) {  // pure border: nothing to compute (before any of the sampling paths' pointer set-up)
+        uint8_t* const dst = b.dst + (size_t)frame * b.dst_frame_stride;
+        const unsigned yw = (g.border & 255u) * 0x01010101u;
+        const unsigned cw = ((g.border >> 8) & 0xffffu) * 0x00010001u;
+        if (((reinterpret_cast<uintptr_t>(dst) | (uintptr_t)g.dst_pitch) & 15) == 0 && u_lo + kPieceW <= g.out_w) {
+            // 16 bytes per lane: 8 lanes per row, 4 rows per store instruction
+            const int sub = lane >> 3, col = (lane & 7) * 16;
+            uint8_t* yrow = dst + (size_t)(v_base + dv0 + sub) * g.dst_pitch + u_lo + col;
+            uint8_t* crow = dst + (size_t)(g.out_h + ((v_base + dv0) >> 1) + sub) * g.dst_pitch + u_lo + col;
+            const uint4 y4 = make_uint4(yw, yw, yw, yw), c4 = make_uint4(cw, cw, cw, cw);
+            for (int r = sub; r < my_rows; r += 4, yrow += 4 * (size_t)g.dst_pitch) *reinterpret_cast<uint4*>(yrow) = y4;
+            for (int r = sub; r < my_rows / 2; r += 4, crow += 4 * (size_t)g.dst_pitch) *reinterpret_cast<uint4*>(crow) = c4;
+            return;
+        }
+        uint8_t* y0 = dst + (size_t)(v_base + dv0) * g.dst_pitch + u0;
+        uint8_t* cc = dst + (size_t)(g.out_h + ((v_base + dv0) >> 1)) * g.dst_pitch + u0;
+        if (valid > 0)
+            for (int dv = 0; dv < my_rows; dv += 2) {
+                store_word<true>(y0, yw, valid);
+                store_word<true>(y0 + g.dst_pitch, yw, valid);
+                store_word<true>(cc, cw, valid);
+                y0 += 2 * (size_t)g.dst_pitch; cc += g.dst_pitch;
+            }
+        return;
+    }
+
     PlaneRefs f;
     f.y = b.src + (size_t)frame * b.src_frame_stride;
     f.uv = f.y + (size_t)g.src_pitch * g.src_h;
@@ -96,32 +125,6 @@ warp_nv12_tile_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
     o.step_c = (size_t)g.dst_pitch;
     const bool word_ok = ((reinterpret_cast<uintptr_t>(f.dst) | (uintptr_t)g.dst_pitch) & 3) == 0 &&
                          u_lo + kPieceW <= g.out_w;
-
-    if (b.skip_interior && (flags & (kPiecePoly | kPieceInterior)) == (kPiecePoly | kPieceInterior))
-        return;  // variant TEX: this piece belongs to the texture kernel
-
-    if (flags & kPieceOutside) {  // pure border: nothing to compute
-        const unsigned yw = (g.border & 255u) * 0x01010101u;
-        const unsigned cw = ((g.border >> 8) & 0xffffu) * 0x00010001u;
-        if (((reinterpret_cast<uintptr_t>(f.dst) | (uintptr_t)g.dst_pitch) & 15) == 0 && u_lo + kPieceW <= g.out_w) {
-            // 16 bytes per lane: 8 lanes per row, 4 rows per store instruction
-            const int sub = lane >> 3, col = (lane & 7) * 16;
-            uint8_t* yrow = f.dst + (size_t)(v_base + dv0 + sub) * g.dst_pitch + u_lo + col;
-            uint8_t* crow = f.dst + (size_t)(g.out_h + ((v_base + dv0) >> 1) + sub) * g.dst_pitch + u_lo + col;
-            const uint4 y4 = make_uint4(yw, yw, yw, yw), c4 = make_uint4(cw, cw, cw, cw);
-            for (int r = sub; r < my_rows; r += 4, yrow += 4 * (size_t)g.dst_pitch) *reinterpret_cast<uint4*>(yrow) = y4;
-            for (int r = sub; r < my_rows / 2; r += 4, crow += 4 * (size_t)g.dst_pitch) *reinterpret_cast<uint4*>(crow) = c4;
-            return;
-        }
-        if (valid > 0)
-            for (int dv = 0; dv < my_rows; dv += 2) {
-                store_word<true>(o.y0, yw, valid);
-                store_word<true>(o.y1, yw, valid);
-                store_word<true>(o.c, cw, valid);
-                o.y0 += o.step_y; o.y1 += o.step_y; o.c += o.step_c;
-            }
-        return;
-    }
 
     if (!(flags & kPiecePoly)) {  // op-for-op per pixel
         const Rot R = load_rot(b, frame);
