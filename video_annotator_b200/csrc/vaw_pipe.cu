@@ -54,6 +54,9 @@ constexpr int kIssuers = 2;                                 // warps that issue 
 constexpr int kIssuerWarp0 = 1;                             // warps 0..3 (one warpgroup): producer, two issuers, filler
 constexpr int kFillerWarp = 3;                              // fills the pure-border pieces
 constexpr int kFirstConsumer = 4;
+#ifndef VAW_PIPE_PARK_NS
+#define VAW_PIPE_PARK_NS 2000      // suspend-time hint of the pipeline's mbarrier waits (0: plain try_wait spin)
+#endif
 #ifndef VAW_PIPE_AUX_REGS
 #define VAW_PIPE_AUX_REGS 40       // registers the four auxiliary warps keep (setmaxnreg.dec)
 #endif
@@ -89,6 +92,14 @@ constexpr int kRingBytes = kSmemBytes - kRingOffset;
 static_assert(24 * kSlots <= kSlotOffset, "mbarrier area");
 static_assert(kSlotBytes % 16 == 0 && kCoefOffset % 16 == 0, "alignment");
 
+__device__ __forceinline__ void pipe_wait(unsigned mbar, unsigned parity)
+{
+#if VAW_PIPE_PARK_NS
+    mbar_wait_parked(mbar, parity, VAW_PIPE_PARK_NS);
+#else
+    mbar_wait(mbar, parity);
+#endif
+}
 __device__ __forceinline__ void mbar_arrive(unsigned mbar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
@@ -193,7 +204,7 @@ warp_nv12_pipe_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
         unsigned my_size = 0;  // lane s: bytes (tile + wrap padding) held by slot s
         auto release_oldest = [&]() {
             const int s = k_head % kSlots;
-            mbar_wait(empty_bar(s), (unsigned)(k_head / kSlots) & 1u);
+            pipe_wait(empty_bar(s), (unsigned)(k_head / kSlots) & 1u);
             used -= __shfl_sync(0xffffffffu, my_size, s);
             ++k_head;
         };
@@ -277,7 +288,7 @@ warp_nv12_pipe_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
         // TMA boxes of the tile (whole 32-row boxes, then 8-row boxes for the rest; luma first, then chroma).
         for (int k = w - kIssuerWarp0;; k += kIssuers) {
             const int s = k % kSlots;
-            mbar_wait(ready_bar(s), (unsigned)(k / kSlots) & 1u);
+            pipe_wait(ready_bar(s), (unsigned)(k / kSlots) & 1u);
             const uint8_t* slot = smem + kSlotOffset + s * kSlotBytes;
             const SlotHead head = *reinterpret_cast<const SlotHead*>(slot);
             const unsigned fb = full_bar(s);
@@ -383,7 +394,7 @@ warp_nv12_pipe_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
     float4* const coefs = reinterpret_cast<float4*>(smem + kCoefOffset + grp * kCoefBytes);
     for (int k = grp;; k += kGroups) {
         const int s = k % kSlots;
-        mbar_wait(full_bar(s), (unsigned)(k / kSlots) & 1u);  // record copied, tile landed
+        pipe_wait(full_bar(s), (unsigned)(k / kSlots) & 1u);  // record copied, tile landed
         const uint8_t* slot = smem + kSlotOffset + s * kSlotBytes;
         const SlotHead head = *reinterpret_cast<const SlotHead*>(slot);
         if (head.idx < 0) break;

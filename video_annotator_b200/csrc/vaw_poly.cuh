@@ -323,6 +323,17 @@ __device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity)
             : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
     } while (!ok);
 }
+// The same with a suspend-time hint (nanoseconds): the waiting warp is parked by the hardware for up to that
+// long per try instead of spinning through the issue slots of the warps that work.
+__device__ __forceinline__ void mbar_wait_parked(unsigned mbar, unsigned parity, unsigned hint_ns)
+{
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok) : "r"(mbar), "r"(parity), "r"(hint_ns) : "memory");
+    } while (!ok);
+}
 // global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completion on mbar
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned mbar)
 {
