@@ -820,3 +820,31 @@ def test_windows_of_the_4k_geometry(V, oracle, out_size, centre, variant):
     else:
         assert np.array_equal(got, ref)
     ctx.close()
+
+
+@pytest.mark.parametrize("focal_scale,rows", [(0.78, 16), (0.4, 8)])
+def test_shorter_pieces_for_short_focal_lengths(V, oracle, focal_scale, rows):
+    """The rows-per-piece rule (vaw_create): a shorter output focal length makes the cubic-in-v
+    truncation estimate exceed the certificate, so pieces get 16 or 8 rows (4 or 2 per warp).  Same
+    bars: coordinates within 1e-3 px of the transcription, pixels 0 LSB on the kernel's own map."""
+    from video_annotator_b200 import configs
+    w = configs.workload("C1")
+    sw, sh = w.src_size
+    ow, oh = 642, 362
+    f = w.output_camera.K[0, 0] * focal_scale
+    cout = V.Camera.from_matrix([[f, 0, (ow - 1) / 2.0], [0, f, (oh - 1) / 2.0], [0, 0, 1]], ow, oh)
+    border = (5, 60, 190)
+    ctx = V.WarpContext(w.input_camera, cout, border=border, variant=TILED)
+    R = rotation_xyz(-1.0, 2.0, 0.6)
+    stats = ctx.piece_stats(R)
+    assert stats["pieces"] == ((ow + 127) // 128) * ((oh + rows - 1) // rows), stats   # i.e. `rows` rows per piece
+    src = oracle.synth_nv12(sw, sh, 9, white_noise=True)
+    got = _warp_one(V, ctx, src, R)
+    mx, my = [t.cpu().numpy() for t in ctx.dump_coords(R, 0)]
+    cx, cy = oracle.chroma_map(mx, my)
+    ref = _oracle_on_map(oracle, src, sw, sh, mx, my, cx, cy, border)
+    assert np.array_equal(got, ref)
+    k = G.oracle_k(oracle, (w.input_camera, cout))
+    ox, oy = oracle.create_map(k, R, oh, ow)
+    assert max(float(np.nanmax(np.abs(mx - ox))), float(np.nanmax(np.abs(my - oy)))) < 1e-3
+    ctx.close()
