@@ -32,6 +32,43 @@ struct RotF { float r[9]; };
 
 struct Ray { double mx, my, q0, q1, q2; };
 
+// atan(t) / t on t in [0, 1] as a polynomial in s = t^2 (tools/fit_atan64.py, degree 13: relative error
+// 1.8e-12, i.e. < 1e-8 px at 4K; the anchors need ~1e-10).  The library atan() costs a double-precision
+// division subroutine per call; together with 1 / q2 those calls were 16 % of the builder's instructions.
+__device__ __forceinline__ double atan_over_t(double s)
+{
+    const double c[14] = {
+9.99999999998195555e-01,
+    -3.33333332624654421e-01,
+    1.99999953399910668e-01,
+    -1.42855923902450388e-01,
+    1.11094283515041928e-01,
+    -9.07679894442711965e-02,
+    7.61425097816378765e-02,
+    -6.36609554917869219e-02,
+    5.04556591859826667e-02,
+    -3.52678487665738852e-02,
+    1.99375722877763104e-02,
+    -8.24198211827211098e-03,
+    2.16282427498169566e-03,
+    -2.66606699012429877e-04
+    };
+    double p = c[13];
+#pragma unroll
+    for (int i = 12; i >= 0; --i) p = fma(p, s, c[i]);
+    return p;
+}
+
+// 1 / x for x in the certified range [2^-6, 2^6]: single-precision seed, two Newton steps (relative error
+// 2^-23 -> 2^-46 -> double rounding).  Outside that range the piece is not certified anyway.
+__device__ __forceinline__ double rcp_newton64(double x)
+{
+    double y = (double)__frcp_rn((float)x);
+    y = fma(y, fma(-x, y, 1.0), y);
+    y = fma(y, fma(-x, y, 1.0), y);
+    return y;
+}
+
 // createMap.cl:15-49 in double precision, for a (possibly fractional) output position.
 __device__ __forceinline__ Ray project(const GeomD& g, const RotD& R, double u, double v)
 {
@@ -41,14 +78,24 @@ __device__ __forceinline__ Ray project(const GeomD& g, const RotD& R, double u, 
     o.q0 = R.r[0] * x + R.r[1] * y + R.r[2];
     o.q1 = R.r[3] * x + R.r[4] * y + R.r[5];
     o.q2 = R.r[6] * x + R.r[7] * y + R.r[8];
-    const double iq = 1.0 / o.q2;
+    const double iq = rcp_newton64(o.q2);
     const double c0 = o.q0 * iq, c1 = o.q1 * iq;
     const double r2 = c0 * c0 + c1 * c1;
     const double ir = rsqrt(r2);
     const double r = r2 * ir;
     // atan(r)/r is analytic in r^2; the series avoids 0/0 (the reference's NaN at r == 0 is
     // reproduced by sending the piece that contains the axis to the per-pixel path)
-    double k = r > 1e-4 ? atan(r) * ir : 1.0 - r2 * (1.0 / 3.0 - r2 * 0.2);  // theta / r
+    // theta / r: atan(r) / r for r <= 1, (pi/2 - atan(1/r)) / r beyond; the series near the axis avoids 0 * inf
+    // (the reference's NaN at r == 0 is reproduced by sending the piece that contains the axis to the per-pixel path)
+    double k;
+    if (r > 1.0) {
+        const double t2 = ir * ir;
+        k = (1.5707963267948966 - ir * atan_over_t(t2)) * ir;
+    } else if (r > 1e-4) {
+        k = atan_over_t(r2);
+    } else {
+        k = 1.0 - r2 * (1.0 / 3.0 - r2 * 0.2);
+    }
     if (g.has_dist) {  // extension: cv::fisheye distortion, theta_d / r = (theta / r) (1 + k1 theta^2 + ... + k4 theta^8)
         const double th2 = k * k * r2;
         k *= 1.0 + th2 * (g.kd[0] + th2 * (g.kd[1] + th2 * (g.kd[2] + th2 * g.kd[3])));
@@ -70,8 +117,24 @@ __device__ __forceinline__ Ray ray_only(const GeomD& g, const RotD& R, double u,
     return o;
 }
 
-__device__ __forceinline__ double node_u(int ig) { return 128.0 * (ig / kDegU) + (128.0 * (ig % kDegU)) / kDegU; }
-__device__ __forceinline__ double node_v(int jg, int ph) { return (double)ph * (jg / kDegV) + ((double)ph * (jg % kDegV)) / kDegV; }
+// Anchor node positions: 128 (ig / 5) + 128 (ig % 5) / 5 and ph (jg / 3) + ph (jg % 3) / 3.  The quotients are
+// written as correctly rounded constants (ph is a power of two, so scaling commutes with the rounding): the
+// same doubles the divisions produce, without a double-precision division subroutine per anchor (a zero
+// numerator sent every fifth / third one down its slow path; with 1 / q2 and atan() that was 16 % of the
+// builder's instructions).
+__device__ __forceinline__ double node_u(int ig)
+{
+    const int m = ig % kDegU;
+    const double f = m == 0 ? 0.0 : (m == 1 ? 128.0 / 5 : (m == 2 ? 256.0 / 5 : (m == 3 ? 384.0 / 5 : 512.0 / 5)));
+    return 128.0 * (ig / kDegU) + f;
+}
+__device__ __forceinline__ double node_v(int jg, int ph)
+{
+    const int m = jg % kDegV;
+    const double f = m == 0 ? 0.0 : (m == 1 ? 1.0 / 3 : 2.0 / 3);
+    return (double)ph * (jg / kDegV) + (double)ph * f;
+}
+static_assert(kDegU == 5 && kDegV == 3, "node_u / node_v spell out the fifths and thirds");
 
 __device__ __forceinline__ float coef(const PieceRec& r, int c, int i, int j) { return c ? r.c[i][j].y : r.c[i][j].x; }
 __device__ __forceinline__ float base_of(const PieceRec& r, int c) { return c ? r.base.y : r.base.x; }
@@ -117,9 +180,10 @@ build_pieces_kernel(const GeomD g, const PieceBasis basis, const float* __restri
 #define VAW_BUILDER_UNROLL 1  // anchors per thread evaluated side by side (instruction-level parallelism of the fp64 chains)
 #endif
     constexpr int kAnchorUnroll = VAW_BUILDER_UNROLL;
+    int b = 0, ig = tid;  // node (row b, column ig) of flat index idx = b * nodes + ig, kept without a division per anchor
+    while (ig >= nodes) { ig -= nodes; ++b; }
 #pragma unroll kAnchorUnroll
     for (int idx = tid; idx < nodes * kNv; idx += kThreads) {
-        const int b = idx / nodes, ig = idx - b * nodes;
         const Ray a = project(g, R, node_u(p0 * kDegU + ig), node_v(py * kDegV + b, ph));
         anchors[b][ig][0] = a.mx;
         anchors[b][ig][1] = a.my;
@@ -127,6 +191,8 @@ build_pieces_kernel(const GeomD g, const PieceBasis basis, const float* __restri
             if (ig / kDegU < np) bad[ig / kDegU] = 1;
             if (ig % kDegU == 0 && ig > 0) bad[ig / kDegU - 1] = 1;
         }
+        ig += kThreads;
+        while (ig >= nodes) { ig -= nodes; ++b; }
     }
     __syncthreads();
 
