@@ -218,7 +218,7 @@ def run_reference(args):
             "cpu_baseline": base,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -241,9 +241,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # rank 0's stdout carries exactly one JSON line: keep NCCL's version banner off it
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # (NCCL prints its version banner on stdout at init: main() has moved fd 1 to stderr, see emit())
         dist.init_process_group("nccl", device_id=dev)
 
     import video_annotator_b200 as V
@@ -359,7 +357,7 @@ def run_ours(args):
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(wl, args.cpu_seconds)
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     if world > 1:
         dist.barrier()
@@ -367,6 +365,23 @@ def run_ours(args):
     return 0
 
 
+_RESULT_FD = None
+
+
+def emit(line):
+    """The one JSON line of the contract, on the process's ORIGINAL stdout.  Everything else any library
+    writes to fd 1 (NCCL's version banner, torchrun notices) goes to stderr: fd 1 is redirected at start-up."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 if __name__ == "__main__":
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)   # from here on fd 1 is stderr, for C libraries as well as for print()
     a = parse_args()
     sys.exit(run_reference(a) if a.impl == "reference" else run_ours(a))
