@@ -36,7 +36,7 @@ enum {
     VAW_OK = 0,
     VAW_ERR_INVALID = -2,     /* bad argument / unsupported parameter               */
     VAW_ERR_CUDA = -3,        /* CUDA runtime or driver error, or no device          */
-    VAW_ERR_UNSUPPORTED = -4, /* e.g. interpolation other than INTER_LINEAR          */
+    VAW_ERR_UNSUPPORTED = -4, /* e.g. INTER_CUBIC                                    */
     VAW_ERR_NOMEM = -5
 };
 
@@ -100,7 +100,8 @@ typedef struct vaw_params {
     int32_t src_width, src_height;     /* input image size (luma), <= 32766          */
     int32_t out_width, out_height;     /* m_output_camera.size, <= 32766             */
     int32_t format;                    /* VAW_FORMAT_*                               */
-    int32_t interpolation;             /* VAW_INTER_LINEAR                           */
+    int32_t interpolation;             /* VAW_INTER_LINEAR; VAW_INTER_NEAREST (cv::remap's
+                                          cvRound of the map, variant GATHER)        */
     uint8_t border[4];                 /* NV12: Y,U,V  BGR24: B,G,R  (cv::remap's
                                           borderValue; OpenCV default is 0; the NV12
                                           neutral chroma is 128)                     */

@@ -848,3 +848,45 @@ def test_shorter_pieces_for_short_focal_lengths(V, oracle, focal_scale, rows):
     ox, oy = oracle.create_map(k, R, oh, ow)
     assert max(float(np.nanmax(np.abs(mx - ox))), float(np.nanmax(np.abs(my - oy)))) < 1e-3
     ctx.close()
+
+
+@pytest.mark.parametrize("fmt", ["nv12", "bgr"])
+def test_inter_nearest(V, oracle, fmt):
+    """FrameSourceWarp's `interpolation` parameter (FrameSourceWarp.hpp:90) with cv::INTER_NEAREST:
+    cv::remap's cvRound of the map, implemented as the integer filter on whole-pixel coordinates
+    (tests/test_oracle_remap.py pins that identity on the real cv2.remap).  0 LSB."""
+    import torch
+    from video_annotator_b200 import configs
+    w = configs.workload("C1")
+    sw, sh = w.src_size
+    R = rotation_xyz(1.0, -2.0, 0.5)
+    if fmt == "nv12":
+        border = (16, 128, 128)
+        ctx = V.WarpContext(w.input_camera, w.output_camera, out_size=w.out_size, border=border,
+                            interpolation=V.INTER_NEAREST)
+        assert ctx.variant == GATHER
+        src = oracle.synth_nv12(sw, sh, 4, white_noise=True)
+        got = _warp_one(V, ctx, src, R)
+        mx, my = [t.cpu().numpy() for t in ctx.dump_coords(R, 0)]
+        cx, cy = [t.cpu().numpy() for t in ctx.dump_coords(R, 1)]
+        ref = _oracle_on_map(oracle, src, sw, sh, np.rint(mx), np.rint(my), np.rint(cx), np.rint(cy), border)
+        assert np.array_equal(got, ref)
+        lin = V.WarpContext(w.input_camera, w.output_camera, out_size=w.out_size, border=border, variant=GATHER)
+        assert not np.array_equal(_warp_one(V, lin, src, R), got)      # it is not the linear filter
+        lin.close()
+    else:
+        ow, oh = w.output_camera.size
+        border = (10, 20, 30)
+        ctx = V.WarpContext(w.input_camera, w.output_camera, fmt=V.FORMAT_BGR24, border=border,
+                            interpolation=V.INTER_NEAREST)
+        rng = np.random.default_rng(3)
+        src = rng.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+        dst = torch.empty((oh, ow, 3), dtype=torch.uint8, device="cuda")
+        ctx.warp(G.to_dev(src), dst, R)
+        torch.cuda.synchronize()
+        mx, my = [t.cpu().numpy() for t in ctx.dump_coords(R, 0)]
+        ref = oracle.remap_u8(src, np.rint(mx), np.rint(my), border=border, threads=NCPU)
+        assert np.array_equal(dst.cpu().numpy(), ref.reshape(oh, ow, 3))
+    ctx.close()
+    with pytest.raises(V.VawError):
+        V.WarpContext(w.input_camera, w.output_camera, out_size=w.out_size, interpolation=V.INTER_NEAREST, variant=TILED)

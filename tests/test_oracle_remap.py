@@ -69,3 +69,25 @@ def test_remap_threads_agree(oracle):
     mx = rng.uniform(-2, 66, (33, 47)).astype(np.float32)
     my = rng.uniform(-2, 66, (33, 47)).astype(np.float32)
     assert np.array_equal(oracle.remap_u8(src, mx, my, threads=1), oracle.remap_u8(src, mx, my, threads=5))
+
+
+@pytest.mark.parametrize("cn", [1, 2, 3])
+def test_nearest_is_the_linear_filter_on_the_rounded_map(oracle, cn):
+    """cv::remap(INTER_NEAREST) samples at (cvRound(x), cvRound(y)) -- saturate_cast<short> of the map,
+    round-half-even -- and takes the border value outside.  The library implements it as the integer
+    bilinear filter on a map rounded to whole pixels (all the weight on tap 00); this pins that
+    identity on the real cv2.remap: random, half-integer, out-of-range and non-finite coordinates."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(11 + cn)
+    h, w = 37, 53
+    src = rng.integers(0, 256, (h, w) if cn == 1 else (h, w, cn), dtype=np.uint8)
+    mx = rng.uniform(-3, w + 3, (64, 80)).astype(np.float32)
+    my = rng.uniform(-3, h + 3, (64, 80)).astype(np.float32)
+    mx[0, :40] = np.arange(40, dtype=np.float32) - 2.5          # exact .5 ties, both parities
+    my[0, :40] = 5.5
+    mx[1, :6] = [np.nan, np.inf, -np.inf, 1e9, -1e9, w - 0.5]
+    my[1, :6] = [3.0, 3.0, 3.0, 3.0, 3.0, h - 0.5]
+    border = (7, 130, 250)[:cn]
+    want = cv2.remap(src, mx, my, cv2.INTER_NEAREST, borderMode=cv2.BORDER_CONSTANT, borderValue=border)
+    got = oracle.remap_u8(src, np.rint(mx), np.rint(my), border=border)
+    assert np.array_equal(got.reshape(want.shape), want)

@@ -486,8 +486,10 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
     if (!params || !out) return fail(nullptr, VAW_ERR_INVALID, "null argument");
     *out = nullptr;
     const vaw_params& p = *params;
-    if (p.interpolation != VAW_INTER_LINEAR)
-        return fail(nullptr, VAW_ERR_UNSUPPORTED, "only INTER_LINEAR is implemented");
+    if (p.interpolation != VAW_INTER_LINEAR && p.interpolation != VAW_INTER_NEAREST)
+        return fail(nullptr, VAW_ERR_UNSUPPORTED, "only INTER_LINEAR and INTER_NEAREST are implemented");
+    if (p.interpolation == VAW_INTER_NEAREST && p.variant != VAW_VARIANT_AUTO && p.variant != VAW_VARIANT_GATHER)
+        return fail(nullptr, VAW_ERR_UNSUPPORTED, "INTER_NEAREST runs on variant GATHER (or AUTO)");
     if (p.format != VAW_FORMAT_NV12 && p.format != VAW_FORMAT_BGR24 && p.format != VAW_FORMAT_GRAY8)
         return fail(nullptr, VAW_ERR_INVALID, "unknown pixel format");
     if (p.variant < VAW_VARIANT_AUTO || p.variant > VAW_VARIANT_TEX)
@@ -524,6 +526,7 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
     g.border = (unsigned)p.border[0] | ((unsigned)p.border[1] << 8) | ((unsigned)p.border[2] << 16) |
                ((unsigned)p.border[3] << 24);
     g.force_exact = (!centre_ok(g.scx) || !centre_ok(g.scy)) ? 1 : 0;
+    g.nearest = p.interpolation == VAW_INTER_NEAREST ? 1 : 0;
     g.has_dist = 0;
     for (int i = 0; i < 4; ++i) {
         g.kd[i] = p.src_distortion[i];
@@ -546,7 +549,7 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
         return rc;
     }
     ctx->variant = p.variant != VAW_VARIANT_AUTO ? p.variant
-                   : (p.format == VAW_FORMAT_NV12 ? VAW_VARIANT_TILED : VAW_VARIANT_GATHER);
+                   : (p.format == VAW_FORMAT_NV12 && !g.nearest ? VAW_VARIANT_TILED : VAW_VARIANT_GATHER);
     if (ctx->variant != VAW_VARIANT_GATHER) {
         // rows per piece: keep the cubic-in-v truncation error ~ 2.4e-3 * f_in * (PH / f_out)^4 px
         // (measured on the BASELINE geometries) below the certificate's 5e-5 px

@@ -25,6 +25,12 @@ __device__ __forceinline__ int fix5(float m)
     return (fabsf(t) < 2147483648.0f) ? s : (int)0x80000000;
 }
 
+// cv::remap(INTER_NEAREST) takes the sample at (cvRound(x), cvRound(y)) (saturate_cast<short> of the map
+// value: round-half-even), border value when that falls outside.  That is the integer filter above on a
+// coordinate rounded to a whole pixel first: ax = ay = 0, all the weight on tap 00.  rintf keeps NaN / inf,
+// which fix5 then sends far outside.
+__device__ __forceinline__ float nearest_coord(float m) { return rintf(m); }
+
 // Two-stage form of the 4-weight blend (algebraically identical integer arithmetic).
 __device__ __forceinline__ int blend(int t00, int t01, int t10, int t11, int ax, int ay)
 {

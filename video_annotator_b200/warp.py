@@ -12,6 +12,7 @@ import numpy as np
 from . import _lib
 
 FORMAT_NV12, FORMAT_BGR24, FORMAT_GRAY8 = 0, 1, 2
+INTER_NEAREST = 0
 INTER_LINEAR = 1
 
 # CameraPreset, FrameSourceWarp.hpp:14-21
