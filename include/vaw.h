@@ -36,7 +36,7 @@ enum {
     VAW_OK = 0,
     VAW_ERR_INVALID = -2,     /* bad argument / unsupported parameter               */
     VAW_ERR_CUDA = -3,        /* CUDA runtime or driver error, or no device          */
-    VAW_ERR_UNSUPPORTED = -4, /* e.g. INTER_CUBIC                                    */
+    VAW_ERR_UNSUPPORTED = -4, /* e.g. an interpolation flag other than the three below */
     VAW_ERR_NOMEM = -5
 };
 
@@ -101,7 +101,8 @@ typedef struct vaw_params {
     int32_t out_width, out_height;     /* m_output_camera.size, <= 32766             */
     int32_t format;                    /* VAW_FORMAT_*                               */
     int32_t interpolation;             /* VAW_INTER_LINEAR; VAW_INTER_NEAREST (cv::remap's
-                                          cvRound of the map, variant GATHER)        */
+                                          cvRound of the map) and VAW_INTER_CUBIC (its
+                                          4x4 fixed-point filter) run on variant GATHER */
     uint8_t border[4];                 /* NV12: Y,U,V  BGR24: B,G,R  (cv::remap's
                                           borderValue; OpenCV default is 0; the NV12
                                           neutral chroma is 128)                     */
@@ -163,6 +164,9 @@ size_t vaw_frame_bytes(int format, int width, int height, int pitch);
 uint64_t vaw_launch_count(const vaw_ctx *ctx);
 /* The kernel variant the context resolved to (VAW_VARIANT_*, never AUTO). */
 int vaw_get_variant(const vaw_ctx *ctx);
+/* Host only: the 32 x 32 x 16 fixed-point weights of cv::remap(INTER_CUBIC) as this library builds them
+ * ([fraction y][fraction x][tap row][tap column], scaled by 2^15; each block of 16 sums to 2^15). */
+int vaw_cubic_table(int16_t out[16384]);
 
 /* ---- the warp ---------------------------------------------------------------------
  * vaw_warp replaces `cv::UMat FrameSourceWarp::warp_frame(cv::UMat input, cv::Mat rotation)`

@@ -77,6 +77,13 @@ void vaw_oracle_remap_u8(const uint8_t *src, int src_w, int src_h, int src_pitch
                          const float *map_x, const float *map_y, int rows, int cols, int map_step,
                          uint8_t *dst, int dst_pitch, const uint8_t *border, int n_threads);
 
+/* cv::remap(INTER_CUBIC, BORDER_CONSTANT), same arguments (remap_cubic_ref.c); the 32 x 32 x 16
+ * fixed-point weight table it uses (weights scaled by 2^15, each block sums to 2^15). */
+void vaw_oracle_remap_cubic_u8(const uint8_t *src, int src_w, int src_h, int src_pitch, int cn,
+                               const float *map_x, const float *map_y, int rows, int cols, int map_step,
+                               uint8_t *dst, int dst_pitch, const uint8_t *border, int n_threads);
+const short *vaw_oracle_cubic_table(void);
+
 /* Full NV12 path: luma map -> chroma map -> remap of both planes.
  * src: (src_h*3/2) rows of src_pitch bytes; dst likewise with out_h. */
 void vaw_oracle_warp_nv12(const uint8_t *src, int src_w, int src_h, int src_pitch,

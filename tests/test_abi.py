@@ -81,8 +81,11 @@ def test_create_validates_before_touching_cuda():
     import video_annotator_b200 as V
     cam = V.get_preset_camera(4, 1920, 1080)
     out = V.get_output_camera(cam)
-    with pytest.raises(V.VawError) as e:  # only INTER_LINEAR exists (FrameSourceWarp.hpp:90)
-        V.WarpContext(cam, out, interpolation=2)
+    with pytest.raises(V.VawError) as e:  # cv::INTER_LANCZOS4 (FrameSourceWarp.hpp:90): not implemented
+        V.WarpContext(cam, out, interpolation=4)
+    assert e.value.code == -4
+    with pytest.raises(V.VawError) as e:  # nearest / cubic run on variant GATHER only
+        V.WarpContext(cam, out, interpolation=V.INTER_CUBIC, variant=3)
     assert e.value.code == -4
     with pytest.raises(V.VawError) as e:  # NV12 needs even sizes
         V.WarpContext(cam, out, out_size=(1759, 998))
@@ -90,6 +93,15 @@ def test_create_validates_before_touching_cuda():
     with pytest.raises(V.VawError) as e:  # `short` indices (createMap.cl:10-11)
         V.WarpContext(cam, out, out_size=(40000, 998))
     assert e.value.code == -2
+
+
+def test_cubic_table_equals_the_oracles(oracle):
+    """The library builds cv::remap's INTER_CUBIC weight table itself (csrc/vaw_cubic.cuh, host code); it
+    must equal the oracle's restatement (pinned on cv2.remap) entry for entry."""
+    from video_annotator_b200 import _lib
+    tab = np.zeros(32 * 32 * 16, np.int16)
+    assert _lib.load().vaw_cubic_table(tab.ctypes.data_as(C.POINTER(C.c_int16))) == 0
+    assert np.array_equal(tab.reshape(32, 32, 4, 4), oracle.cubic_table())
 
 
 def test_no_cpu_fallback_without_device():

@@ -91,3 +91,43 @@ def test_nearest_is_the_linear_filter_on_the_rounded_map(oracle, cn):
     want = cv2.remap(src, mx, my, cv2.INTER_NEAREST, borderMode=cv2.BORDER_CONSTANT, borderValue=border)
     got = oracle.remap_u8(src, np.rint(mx), np.rint(my), border=border)
     assert np.array_equal(got.reshape(want.shape), want)
+
+
+@pytest.mark.parametrize("cn", [1, 2, 3])
+def test_cubic_vs_live_cv2(oracle, cn):
+    """oracle/remap_cubic_ref.c against the real cv2.remap(INTER_CUBIC, BORDER_CONSTANT): random maps
+    that straddle the border, grid-aligned and non-finite coordinates, overshoot on a checkerboard."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(21 + cn)
+    h, w = 41, 57
+    src = rng.integers(0, 256, (h, w) if cn == 1 else (h, w, cn), dtype=np.uint8)
+    src[::2, ::2] = 255
+    src[1::2, 1::2] = 0
+    mx = rng.uniform(-4, w + 4, (96, 120)).astype(np.float32)
+    my = rng.uniform(-4, h + 4, (96, 120)).astype(np.float32)
+    xs = np.array([-2.0, -1.5, -1.0, -0.5, 0.0, 0.25, 0.5, 1.0, w - 2.0, w - 1.5, w - 1.0, w - 0.5, w, w + 1.5,
+                   np.nan, np.inf, -np.inf, 1e9, -1e9, 3.03125, 3.96875, 4.015625], np.float32)
+    mx[0, :22] = xs
+    my[0, :22] = 7.0
+    mx[1, :22] = 9.0
+    my[1, :22] = np.where(np.isfinite(xs), np.minimum(xs, h + 1.5), xs)
+    for border in ((0, 0, 0), (77, 130, 255)):
+        want = cv2.remap(src, mx, my, cv2.INTER_CUBIC, borderMode=cv2.BORDER_CONSTANT, borderValue=border[:cn])
+        got = oracle.remap_u8(src, mx, my, border=border[:cn], cubic=True, threads=2)
+        assert np.array_equal(got.reshape(want.shape), want)
+    tab = oracle.cubic_table()
+    assert (tab.reshape(1024, 16).astype(np.int64).sum(1) == 32768).all()
+
+
+def test_cubic_and_nearest_golden_vectors(oracle):
+    """Committed cv2.remap(INTER_CUBIC / INTER_NEAREST) outputs (tests/golden/make_golden.py)."""
+    g = np.load(os.path.join(GOLDEN, "remap_cases.npz"))
+    c = np.load(os.path.join(GOLDEN, "remap_cubic.npz"))
+    mx, my = g["map_x"], g["map_y"]
+    for cn in (1, 2, 3):
+        src = g[f"src{cn}"]
+        for bi, border in enumerate(g["borders"]):
+            got = oracle.remap_u8(src, mx, my, border=border[:cn], cubic=True)
+            assert np.array_equal(got, c[f"cubic{cn}_b{bi}"].reshape(got.shape)), ("cubic", cn, bi)
+            got = oracle.remap_u8(src, np.rint(mx), np.rint(my), border=border[:cn])
+            assert np.array_equal(got, c[f"nearest{cn}_b{bi}"].reshape(got.shape)), ("nearest", cn, bi)

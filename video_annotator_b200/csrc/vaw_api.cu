@@ -16,6 +16,7 @@
 #include <utility>
 #include "../../include/vaw.h"
 #include "vaw_internal.h"
+#include "vaw_cubic.cuh"
 
 static_assert(sizeof(vaw_params) == 128 && sizeof(vaw_camera) == 120, "C-ABI struct layout");
 
@@ -44,6 +45,7 @@ struct vaw_ctx {
     int device = 0;
     vaw::Geom g{};
     float *xtab = nullptr, *ytab = nullptr;
+    int16_t* cubic_tab = nullptr;  // INTER_CUBIC weights (device)
     int channels = 1;
     size_t src_frame_bytes = 0, dst_frame_bytes = 0;  // tightly packed
     uint64_t launches = 0;
@@ -481,15 +483,22 @@ uint64_t vaw_launch_count(const vaw_ctx* ctx) { return ctx ? ctx->launches : 0; 
 
 int vaw_get_variant(const vaw_ctx* ctx) { return ctx ? ctx->variant : VAW_ERR_INVALID; }
 
+int vaw_cubic_table(int16_t* out)
+{
+    if (!out) return VAW_ERR_INVALID;
+    vaw::build_cubic_table(out);
+    return VAW_OK;
+}
+
 int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
 {
     if (!params || !out) return fail(nullptr, VAW_ERR_INVALID, "null argument");
     *out = nullptr;
     const vaw_params& p = *params;
-    if (p.interpolation != VAW_INTER_LINEAR && p.interpolation != VAW_INTER_NEAREST)
-        return fail(nullptr, VAW_ERR_UNSUPPORTED, "only INTER_LINEAR and INTER_NEAREST are implemented");
-    if (p.interpolation == VAW_INTER_NEAREST && p.variant != VAW_VARIANT_AUTO && p.variant != VAW_VARIANT_GATHER)
-        return fail(nullptr, VAW_ERR_UNSUPPORTED, "INTER_NEAREST runs on variant GATHER (or AUTO)");
+    if (p.interpolation != VAW_INTER_LINEAR && p.interpolation != VAW_INTER_NEAREST && p.interpolation != VAW_INTER_CUBIC)
+        return fail(nullptr, VAW_ERR_UNSUPPORTED, "only INTER_NEAREST, INTER_LINEAR and INTER_CUBIC are implemented");
+    if (p.interpolation != VAW_INTER_LINEAR && p.variant != VAW_VARIANT_AUTO && p.variant != VAW_VARIANT_GATHER)
+        return fail(nullptr, VAW_ERR_UNSUPPORTED, "INTER_NEAREST and INTER_CUBIC run on variant GATHER (or AUTO)");
     if (p.format != VAW_FORMAT_NV12 && p.format != VAW_FORMAT_BGR24 && p.format != VAW_FORMAT_GRAY8)
         return fail(nullptr, VAW_ERR_INVALID, "unknown pixel format");
     if (p.variant < VAW_VARIANT_AUTO || p.variant > VAW_VARIANT_TEX)
@@ -541,6 +550,13 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
     cudaError_t e = cudaMalloc(&ctx->xtab, sizeof(float) * n_x);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->ytab, sizeof(float) * n_y);
     if (e == cudaSuccess) e = vaw::launch_ray_tables(ctx->xtab, n_x, ctx->ytab, n_y, g.mcx, g.mfx, g.mcy, g.mfy, nullptr);
+    if (e == cudaSuccess && p.interpolation == VAW_INTER_CUBIC) {
+        std::string tab(sizeof(int16_t) * vaw::kCubicTabEntries, '\0');
+        vaw::build_cubic_table(reinterpret_cast<int16_t*>(&tab[0]));
+        e = cudaMalloc(&ctx->cubic_tab, tab.size());
+        if (e == cudaSuccess) e = cudaMemcpy(ctx->cubic_tab, tab.data(), tab.size(), cudaMemcpyHostToDevice);
+        g.cubic_tab = ctx->cubic_tab;
+    }
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         int rc = cuda_fail(nullptr, e, "vaw_create");
@@ -549,7 +565,7 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
         return rc;
     }
     ctx->variant = p.variant != VAW_VARIANT_AUTO ? p.variant
-                   : (p.format == VAW_FORMAT_NV12 && !g.nearest ? VAW_VARIANT_TILED : VAW_VARIANT_GATHER);
+                   : (p.format == VAW_FORMAT_NV12 && p.interpolation == VAW_INTER_LINEAR ? VAW_VARIANT_TILED : VAW_VARIANT_GATHER);
     if (ctx->variant != VAW_VARIANT_GATHER) {
         // rows per piece: keep the cubic-in-v truncation error ~ 2.4e-3 * f_in * (PH / f_out)^4 px
         // (measured on the BASELINE geometries) below the certificate's 5e-5 px
@@ -648,6 +664,7 @@ void vaw_destroy(vaw_ctx* ctx)
     }
     cudaFree(ctx->xtab);
     cudaFree(ctx->ytab);
+    cudaFree(ctx->cubic_tab);
     delete ctx;
 }
 

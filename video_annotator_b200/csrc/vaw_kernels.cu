@@ -18,6 +18,7 @@
 #include <stdint.h>
 #include "vaw_internal.h"
 #include "vaw_sample.cuh"
+#include "vaw_cubic.cuh"
 #include "vaw_synth.cuh"
 
 namespace vaw {
@@ -78,16 +79,20 @@ __device__ __forceinline__ void warp_nv12_body(const Geom& g, const Rot& R, cons
     for (int r = 0; r < 2; ++r)
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-            yw[r] |= (unsigned)sample_c1(src, g.src_pitch, g.src_w, g.src_h, g.nearest ? nearest_coord(mx[r][i]) : mx[r][i],
-                                         g.nearest ? nearest_coord(my[r][i]) : my[r][i],
-                                         border_y) << (8 * i);
+            yw[r] |= (g.cubic_tab ? sample_cubic<1>(src, g.src_pitch, g.src_w, g.src_h, mx[r][i], my[r][i], (unsigned)border_y, g.cubic_tab)
+                                  : (unsigned)sample_c1(src, g.src_pitch, g.src_w, g.src_h,
+                                                        g.nearest ? nearest_coord(mx[r][i]) : mx[r][i],
+                                                        g.nearest ? nearest_coord(my[r][i]) : my[r][i], border_y))
+                     << (8 * i);
     unsigned cw = 0u;
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
         float cx = chroma_coord(mx[0][2 * q], mx[0][2 * q + 1], mx[1][2 * q], mx[1][2 * q + 1]);
         float cy = chroma_coord(my[0][2 * q], my[0][2 * q + 1], my[1][2 * q], my[1][2 * q + 1]);
         if (g.nearest) { cx = nearest_coord(cx); cy = nearest_coord(cy); }
-        cw |= sample_c2(src_uv, g.src_pitch, g.src_w >> 1, g.src_h >> 1, cx, cy, border_uv) << (16 * q);
+        cw |= (g.cubic_tab ? sample_cubic<2>(src_uv, g.src_pitch, g.src_w >> 1, g.src_h >> 1, cx, cy, border_uv, g.cubic_tab)
+                           : sample_c2(src_uv, g.src_pitch, g.src_w >> 1, g.src_h >> 1, cx, cy, border_uv))
+              << (16 * q);
     }
     if (valid > 0) {
         store4(dst + (size_t)v0 * g.dst_pitch + u0, yw[0], valid);
@@ -139,16 +144,19 @@ __device__ __forceinline__ void warp_packed_body(const Geom& g, const Rot& R, co
             unsigned wv = 0u;
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-                wv |= (unsigned)sample_c1(src, g.src_pitch, g.src_w, g.src_h, g.nearest ? nearest_coord(mx[r][i]) : mx[r][i],
-                                          g.nearest ? nearest_coord(my[r][i]) : my[r][i],
-                                          g.border & 255) << (8 * i);
+                wv |= (g.cubic_tab ? sample_cubic<1>(src, g.src_pitch, g.src_w, g.src_h, mx[r][i], my[r][i], g.border & 255u, g.cubic_tab)
+                                   : (unsigned)sample_c1(src, g.src_pitch, g.src_w, g.src_h,
+                                                         g.nearest ? nearest_coord(mx[r][i]) : mx[r][i],
+                                                         g.nearest ? nearest_coord(my[r][i]) : my[r][i], g.border & 255))
+                      << (8 * i);
             if (valid > 0) store4(row, wv, valid);
         } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                unsigned px = sample_c3(src, g.src_pitch, g.src_w, g.src_h, g.nearest ? nearest_coord(mx[r][i]) : mx[r][i],
-                                        g.nearest ? nearest_coord(my[r][i]) : my[r][i],
-                                        g.border & 0xffffffu);
+                unsigned px = g.cubic_tab
+                                  ? sample_cubic<3>(src, g.src_pitch, g.src_w, g.src_h, mx[r][i], my[r][i], g.border & 0xffffffu, g.cubic_tab)
+                                  : sample_c3(src, g.src_pitch, g.src_w, g.src_h, g.nearest ? nearest_coord(mx[r][i]) : mx[r][i],
+                                              g.nearest ? nearest_coord(my[r][i]) : my[r][i], g.border & 0xffffffu);
                 if (i < valid) {
                     row[3 * i] = (uint8_t)px;
                     row[3 * i + 1] = (uint8_t)(px >> 8);

@@ -148,7 +148,7 @@ FrameSourceWarp::FrameSourceWarp(std::shared_ptr<FrameSource> source, CameraPres
     vaw_params p{};
     int rc = vaw_params_from_cameras(&in, &out, m_format, &p);
     if (rc != VAW_OK) throw rc;
-    p.interpolation = (int)m_interpolation;  // INTER_LINEAR or INTER_NEAREST; anything else -> VAW_ERR_UNSUPPORTED
+    p.interpolation = (int)m_interpolation;  // INTER_NEAREST, INTER_LINEAR or INTER_CUBIC; anything else -> VAW_ERR_UNSUPPORTED
     p.border[0] = 0; p.border[1] = 128; p.border[2] = 128;  // NV12: Y 0 (cv::remap's default, :306-312), neutral chroma
     if (m_format == VAW_FORMAT_BGR24) p.border[1] = p.border[2] = 0;
     rc = vaw_create(&p, m_device, &m_ctx);
