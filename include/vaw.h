@@ -50,7 +50,7 @@ enum {
 enum { VAW_FORMAT_NV12 = 0, VAW_FORMAT_BGR24 = 1, VAW_FORMAT_GRAY8 = 2 };
 
 /* cv::InterpolationFlags values (opencv/FrameSourceWarp.hpp:90); only LINEAR exists. */
-enum { VAW_INTER_NEAREST = 0, VAW_INTER_LINEAR = 1, VAW_INTER_CUBIC = 2 };
+enum { VAW_INTER_NEAREST = 0, VAW_INTER_LINEAR = 1, VAW_INTER_CUBIC = 2, VAW_INTER_LANCZOS4 = 4 };  /* cv::InterpolationFlags values */
 
 /* Kernel variants.  Every variant applies cv::remap's integer filter exactly to its own
  * map (vaw_dump_coords returns that map); they differ in how the map is evaluated:
@@ -101,8 +101,9 @@ typedef struct vaw_params {
     int32_t out_width, out_height;     /* m_output_camera.size, <= 32766             */
     int32_t format;                    /* VAW_FORMAT_*                               */
     int32_t interpolation;             /* VAW_INTER_LINEAR; VAW_INTER_NEAREST (cv::remap's
-                                          cvRound of the map) and VAW_INTER_CUBIC (its
-                                          4x4 fixed-point filter) run on variant GATHER */
+                                          cvRound of the map), VAW_INTER_CUBIC and
+                                          VAW_INTER_LANCZOS4 (its 4x4 / 8x8 fixed-point
+                                          filters) run on variant GATHER              */
     uint8_t border[4];                 /* NV12: Y,U,V  BGR24: B,G,R  (cv::remap's
                                           borderValue; OpenCV default is 0; the NV12
                                           neutral chroma is 128)                     */
@@ -167,6 +168,8 @@ int vaw_get_variant(const vaw_ctx *ctx);
 /* Host only: the 32 x 32 x 16 fixed-point weights of cv::remap(INTER_CUBIC) as this library builds them
  * ([fraction y][fraction x][tap row][tap column], scaled by 2^15; each block of 16 sums to 2^15). */
 int vaw_cubic_table(int16_t out[16384]);
+/* The same for INTER_LANCZOS4: 32 x 32 x 64 weights. */
+int vaw_lanczos4_table(int16_t out[65536]);
 
 /* ---- the warp ---------------------------------------------------------------------
  * vaw_warp replaces `cv::UMat FrameSourceWarp::warp_frame(cv::UMat input, cv::Mat rotation)`

@@ -66,6 +66,10 @@ def lib():
         L.vaw_oracle_remap_cubic_u8.restype = None
         L.vaw_oracle_cubic_table.argtypes = []
         L.vaw_oracle_cubic_table.restype = C.POINTER(C.c_short)
+        L.vaw_oracle_remap_lanczos4_u8.argtypes = L.vaw_oracle_remap_u8.argtypes
+        L.vaw_oracle_remap_lanczos4_u8.restype = None
+        L.vaw_oracle_lanczos4_table.argtypes = []
+        L.vaw_oracle_lanczos4_table.restype = C.POINTER(C.c_short)
         L.vaw_oracle_warp_nv12.argtypes = [u8, C.c_int, C.c_int, C.c_int, u8, C.c_int, C.c_int,
                                            C.c_int, ip, fp, C.c_int, C.c_int, C.c_int, C.c_int]
         L.vaw_oracle_warp_nv12.restype = None
@@ -137,8 +141,15 @@ def cubic_table():
     return np.ctypeslib.as_array(p, shape=(32 * 32 * 16,)).reshape(32, 32, 4, 4).copy()
 
 
-def remap_u8(src, mx, my, border=None, threads=1, cubic=False):
-    """src: (H, W) or (H, W, cn) uint8; returns (rows, cols[, cn]).  cubic: INTER_CUBIC instead of INTER_LINEAR."""
+def lanczos4_table():
+    """cv::remap's INTER_LANCZOS4 weights: (32, 32, 8, 8) int16."""
+    p = lib().vaw_oracle_lanczos4_table()
+    return np.ctypeslib.as_array(p, shape=(32 * 32 * 64,)).reshape(32, 32, 8, 8).copy()
+
+
+def remap_u8(src, mx, my, border=None, threads=1, cubic=False, lanczos4=False):
+    """src: (H, W) or (H, W, cn) uint8; returns (rows, cols[, cn]).  cubic / lanczos4: INTER_CUBIC / INTER_LANCZOS4
+    instead of INTER_LINEAR."""
     src = np.ascontiguousarray(src)
     cn = 1 if src.ndim == 2 else src.shape[2]
     h, w = src.shape[:2]
@@ -149,7 +160,7 @@ def remap_u8(src, mx, my, border=None, threads=1, cubic=False):
     b = np.zeros(4, np.uint8)
     if border is not None:
         b[:cn] = np.asarray(border, dtype=np.uint8).reshape(-1)[:cn]
-    fn = lib().vaw_oracle_remap_cubic_u8 if cubic else lib().vaw_oracle_remap_u8
+    fn = lib().vaw_oracle_remap_lanczos4_u8 if lanczos4 else (lib().vaw_oracle_remap_cubic_u8 if cubic else lib().vaw_oracle_remap_u8)
     fn(_u8(src), w, h, src.strides[0], cn, _fp(mx), _fp(my), rows, cols,
        cols, _u8(dst), dst.strides[0], _u8(b), threads)
     return dst

@@ -83,6 +83,11 @@ void vaw_oracle_remap_cubic_u8(const uint8_t *src, int src_w, int src_h, int src
                                const float *map_x, const float *map_y, int rows, int cols, int map_step,
                                uint8_t *dst, int dst_pitch, const uint8_t *border, int n_threads);
 const short *vaw_oracle_cubic_table(void);
+/* cv::remap(INTER_LANCZOS4, BORDER_CONSTANT): 8 x 8 taps, table 32 x 32 x 64. */
+void vaw_oracle_remap_lanczos4_u8(const uint8_t *src, int src_w, int src_h, int src_pitch, int cn,
+                                  const float *map_x, const float *map_y, int rows, int cols, int map_step,
+                                  uint8_t *dst, int dst_pitch, const uint8_t *border, int n_threads);
+const short *vaw_oracle_lanczos4_table(void);
 
 /* Full NV12 path: luma map -> chroma map -> remap of both planes.
  * src: (src_h*3/2) rows of src_pitch bytes; dst likewise with out_h. */

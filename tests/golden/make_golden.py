@@ -7,7 +7,7 @@ What pins what:
   remap_cases.npz   outputs of cv2.remap (the real cv::remap the reference calls at
                     opencv/FrameSourceWarp.cpp:306-312) on random + adversarial maps.
                     PINS oracle/remap_ref.c.
-  remap_cubic.npz   cv2.remap(INTER_CUBIC / INTER_NEAREST) on the maps and sources of remap_cases.npz.
+  remap_cubic.npz   cv2.remap(INTER_CUBIC / INTER_LANCZOS4 / INTER_NEAREST) on the maps and sources of remap_cases.npz.
                     PINS oracle/remap_cubic_ref.c and the nearest = linear-on-rounded-map identity.
   fisheye_map.npz   cv2.fisheye.initUndistortRectifyMap(K_in, D=0, R=rot^T, P=K_out)
                     -- an independent implementation of createMap.cl's projection
@@ -168,7 +168,7 @@ def remap_cubic():
         src = g[f"src{cn}"]
         for bi, border in enumerate(g["borders"]):
             bv = tuple(float(b) for b in border[:cn])
-            for name, flag in (("cubic", cv2.INTER_CUBIC), ("nearest", cv2.INTER_NEAREST)):
+            for name, flag in (("cubic", cv2.INTER_CUBIC), ("nearest", cv2.INTER_NEAREST), ("lanczos", cv2.INTER_LANCZOS4)):
                 out[f"{name}{cn}_b{bi}"] = cv2.remap(src, g["map_x"], g["map_y"], flag, borderMode=cv2.BORDER_CONSTANT,
                                                      borderValue=bv if cn > 1 else bv[0])
     np.savez_compressed(os.path.join(HERE, "remap_cubic.npz"), **out)

@@ -81,8 +81,8 @@ def test_create_validates_before_touching_cuda():
     import video_annotator_b200 as V
     cam = V.get_preset_camera(4, 1920, 1080)
     out = V.get_output_camera(cam)
-    with pytest.raises(V.VawError) as e:  # cv::INTER_LANCZOS4 (FrameSourceWarp.hpp:90): not implemented
-        V.WarpContext(cam, out, interpolation=4)
+    with pytest.raises(V.VawError) as e:  # cv::INTER_AREA (FrameSourceWarp.hpp:90): not a remap filter, not implemented
+        V.WarpContext(cam, out, interpolation=3)
     assert e.value.code == -4
     with pytest.raises(V.VawError) as e:  # nearest / cubic run on variant GATHER only
         V.WarpContext(cam, out, interpolation=V.INTER_CUBIC, variant=3)
@@ -102,6 +102,9 @@ def test_cubic_table_equals_the_oracles(oracle):
     tab = np.zeros(32 * 32 * 16, np.int16)
     assert _lib.load().vaw_cubic_table(tab.ctypes.data_as(C.POINTER(C.c_int16))) == 0
     assert np.array_equal(tab.reshape(32, 32, 4, 4), oracle.cubic_table())
+    tab8 = np.zeros(32 * 32 * 64, np.int16)
+    assert _lib.load().vaw_lanczos4_table(tab8.ctypes.data_as(C.POINTER(C.c_int16))) == 0
+    assert np.array_equal(tab8.reshape(32, 32, 8, 8), oracle.lanczos4_table())
 
 
 def test_no_cpu_fallback_without_device():

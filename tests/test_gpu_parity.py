@@ -892,40 +892,42 @@ def test_inter_nearest(V, oracle, fmt):
         V.WarpContext(w.input_camera, w.output_camera, out_size=w.out_size, interpolation=V.INTER_NEAREST, variant=TILED)
 
 
+@pytest.mark.parametrize("interp", ["cubic", "lanczos4"])
 @pytest.mark.parametrize("fmt", ["nv12", "bgr"])
-def test_inter_cubic(V, oracle, fmt):
-    """cv::INTER_CUBIC for FrameSourceWarp's `interpolation` parameter (FrameSourceWarp.hpp:90): cv::remap's
-    4 x 4 fixed-point filter (oracle/remap_cubic_ref.c, pinned on the real cv2.remap) on the kernel's own map.
-    0 LSB, white noise (overshoot and saturation included), border-straddling pixels included."""
+def test_inter_cubic(V, oracle, fmt, interp):
+    """cv::INTER_CUBIC / cv::INTER_LANCZOS4 for FrameSourceWarp's `interpolation` parameter (FrameSourceWarp.hpp:90):
+    cv::remap's 4 x 4 / 8 x 8 fixed-point filters (oracle/remap_cubic_ref.c, pinned on the real cv2.remap) on the
+    kernel's own map.  0 LSB, white noise (overshoot and saturation included), border-straddling pixels included."""
     import torch
     from video_annotator_b200 import configs
     w = configs.workload("C1")
     sw, sh = w.src_size
     R = rotation_xyz(1.0, -2.0, 0.5)
+    flag, kw = (V.INTER_CUBIC, {"cubic": True}) if interp == "cubic" else (V.INTER_LANCZOS4, {"lanczos4": True})
     if fmt == "nv12":
         border = (16, 128, 128)
         ctx = V.WarpContext(w.input_camera, w.output_camera, out_size=w.out_size, border=border,
-                            interpolation=V.INTER_CUBIC)
+                            interpolation=flag)
         assert ctx.variant == GATHER
         src = oracle.synth_nv12(sw, sh, 4, white_noise=True)
         got = _warp_one(V, ctx, src, R)
         mx, my = [t.cpu().numpy() for t in ctx.dump_coords(R, 0)]
         cx, cy = [t.cpu().numpy() for t in ctx.dump_coords(R, 1)]
-        y = oracle.remap_u8(src[:sh], mx, my, border=border[:1], cubic=True, threads=NCPU)
-        uv = oracle.remap_u8(src[sh:].reshape(sh // 2, sw // 2, 2), cx, cy, border=border[1:3], cubic=True, threads=NCPU)
+        y = oracle.remap_u8(src[:sh], mx, my, border=border[:1], threads=NCPU, **kw)
+        uv = oracle.remap_u8(src[sh:].reshape(sh // 2, sw // 2, 2), cx, cy, border=border[1:3], threads=NCPU, **kw)
         ref = np.concatenate([y, uv.reshape(y.shape[0] // 2, y.shape[1])], axis=0)
         assert np.array_equal(got, ref)
     else:
         ow, oh = w.output_camera.size
         border = (10, 20, 30)
         ctx = V.WarpContext(w.input_camera, w.output_camera, fmt=V.FORMAT_BGR24, border=border,
-                            interpolation=V.INTER_CUBIC)
+                            interpolation=flag)
         rng = np.random.default_rng(3)
         src = rng.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
         dst = torch.empty((oh, ow, 3), dtype=torch.uint8, device="cuda")
         ctx.warp(G.to_dev(src), dst, R)
         torch.cuda.synchronize()
         mx, my = [t.cpu().numpy() for t in ctx.dump_coords(R, 0)]
-        ref = oracle.remap_u8(src, mx, my, border=border, cubic=True, threads=NCPU)
+        ref = oracle.remap_u8(src, mx, my, border=border, threads=NCPU, **kw)
         assert np.array_equal(dst.cpu().numpy(), ref.reshape(oh, ow, 3))
     ctx.close()

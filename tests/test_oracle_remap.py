@@ -95,7 +95,7 @@ def test_nearest_is_the_linear_filter_on_the_rounded_map(oracle, cn):
 
 @pytest.mark.parametrize("cn", [1, 2, 3])
 def test_cubic_vs_live_cv2(oracle, cn):
-    """oracle/remap_cubic_ref.c against the real cv2.remap(INTER_CUBIC, BORDER_CONSTANT): random maps
+    """oracle/remap_cubic_ref.c against the real cv2.remap(INTER_CUBIC and INTER_LANCZOS4, BORDER_CONSTANT): random maps
     that straddle the border, grid-aligned and non-finite coordinates, overshoot on a checkerboard."""
     cv2 = pytest.importorskip("cv2")
     rng = np.random.default_rng(21 + cn)
@@ -115,6 +115,9 @@ def test_cubic_vs_live_cv2(oracle, cn):
         want = cv2.remap(src, mx, my, cv2.INTER_CUBIC, borderMode=cv2.BORDER_CONSTANT, borderValue=border[:cn])
         got = oracle.remap_u8(src, mx, my, border=border[:cn], cubic=True, threads=2)
         assert np.array_equal(got.reshape(want.shape), want)
+        want = cv2.remap(src, mx, my, cv2.INTER_LANCZOS4, borderMode=cv2.BORDER_CONSTANT, borderValue=border[:cn])
+        got = oracle.remap_u8(src, mx, my, border=border[:cn], lanczos4=True, threads=2)
+        assert np.array_equal(got.reshape(want.shape), want)
     tab = oracle.cubic_table()
     assert (tab.reshape(1024, 16).astype(np.int64).sum(1) == 32768).all()
 
@@ -131,3 +134,5 @@ def test_cubic_and_nearest_golden_vectors(oracle):
             assert np.array_equal(got, c[f"cubic{cn}_b{bi}"].reshape(got.shape)), ("cubic", cn, bi)
             got = oracle.remap_u8(src, np.rint(mx), np.rint(my), border=border[:cn])
             assert np.array_equal(got, c[f"nearest{cn}_b{bi}"].reshape(got.shape)), ("nearest", cn, bi)
+            got = oracle.remap_u8(src, mx, my, border=border[:cn], lanczos4=True)
+            assert np.array_equal(got, c[f"lanczos{cn}_b{bi}"].reshape(got.shape)), ("lanczos", cn, bi)

@@ -46,6 +46,7 @@ SIGNATURES = {
     "vaw_launch_count": (C.c_uint64, [C.c_void_p]),
     "vaw_get_variant": (C.c_int, [C.c_void_p]),
     "vaw_cubic_table": (C.c_int, [C.POINTER(C.c_int16)]),
+    "vaw_lanczos4_table": (C.c_int, [C.POINTER(C.c_int16)]),
     "vaw_warp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, f64p, C.c_void_p]),
     "vaw_warp_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_int,
                                  C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]),

@@ -490,15 +490,23 @@ int vaw_cubic_table(int16_t* out)
     return VAW_OK;
 }
 
+int vaw_lanczos4_table(int16_t* out)
+{
+    if (!out) return VAW_ERR_INVALID;
+    vaw::build_lanczos4_table(out);
+    return VAW_OK;
+}
+
 int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
 {
     if (!params || !out) return fail(nullptr, VAW_ERR_INVALID, "null argument");
     *out = nullptr;
     const vaw_params& p = *params;
-    if (p.interpolation != VAW_INTER_LINEAR && p.interpolation != VAW_INTER_NEAREST && p.interpolation != VAW_INTER_CUBIC)
-        return fail(nullptr, VAW_ERR_UNSUPPORTED, "only INTER_NEAREST, INTER_LINEAR and INTER_CUBIC are implemented");
+    if (p.interpolation != VAW_INTER_LINEAR && p.interpolation != VAW_INTER_NEAREST && p.interpolation != VAW_INTER_CUBIC &&
+        p.interpolation != VAW_INTER_LANCZOS4)
+        return fail(nullptr, VAW_ERR_UNSUPPORTED, "only INTER_NEAREST, INTER_LINEAR, INTER_CUBIC and INTER_LANCZOS4 are implemented");
     if (p.interpolation != VAW_INTER_LINEAR && p.variant != VAW_VARIANT_AUTO && p.variant != VAW_VARIANT_GATHER)
-        return fail(nullptr, VAW_ERR_UNSUPPORTED, "INTER_NEAREST and INTER_CUBIC run on variant GATHER (or AUTO)");
+        return fail(nullptr, VAW_ERR_UNSUPPORTED, "INTER_NEAREST, INTER_CUBIC and INTER_LANCZOS4 run on variant GATHER (or AUTO)");
     if (p.format != VAW_FORMAT_NV12 && p.format != VAW_FORMAT_BGR24 && p.format != VAW_FORMAT_GRAY8)
         return fail(nullptr, VAW_ERR_INVALID, "unknown pixel format");
     if (p.variant < VAW_VARIANT_AUTO || p.variant > VAW_VARIANT_TEX)
@@ -550,9 +558,12 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
     cudaError_t e = cudaMalloc(&ctx->xtab, sizeof(float) * n_x);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->ytab, sizeof(float) * n_y);
     if (e == cudaSuccess) e = vaw::launch_ray_tables(ctx->xtab, n_x, ctx->ytab, n_y, g.mcx, g.mfx, g.mcy, g.mfy, nullptr);
-    if (e == cudaSuccess && p.interpolation == VAW_INTER_CUBIC) {
-        std::string tab(sizeof(int16_t) * vaw::kCubicTabEntries, '\0');
-        vaw::build_cubic_table(reinterpret_cast<int16_t*>(&tab[0]));
+    if (e == cudaSuccess && (p.interpolation == VAW_INTER_CUBIC || p.interpolation == VAW_INTER_LANCZOS4)) {
+        const bool cubic = p.interpolation == VAW_INTER_CUBIC;
+        std::string tab(sizeof(int16_t) * (cubic ? vaw::kCubicTabEntries : vaw::kLanczosTabEntries), '\0');
+        if (cubic) vaw::build_cubic_table(reinterpret_cast<int16_t*>(&tab[0]));
+        else vaw::build_lanczos4_table(reinterpret_cast<int16_t*>(&tab[0]));
+        g.tab_ks = cubic ? 4 : 8;
         e = cudaMalloc(&ctx->cubic_tab, tab.size());
         if (e == cudaSuccess) e = cudaMemcpy(ctx->cubic_tab, tab.data(), tab.size(), cudaMemcpyHostToDevice);
         g.cubic_tab = ctx->cubic_tab;

@@ -79,7 +79,7 @@ __device__ __forceinline__ void warp_nv12_body(const Geom& g, const Rot& R, cons
     for (int r = 0; r < 2; ++r)
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-            yw[r] |= (g.cubic_tab ? sample_cubic<1>(src, g.src_pitch, g.src_w, g.src_h, mx[r][i], my[r][i], (unsigned)border_y, g.cubic_tab)
+            yw[r] |= (g.cubic_tab ? sample_hi<1>(src, g.src_pitch, g.src_w, g.src_h, mx[r][i], my[r][i], (unsigned)border_y, g.cubic_tab, g.tab_ks)
                                   : (unsigned)sample_c1(src, g.src_pitch, g.src_w, g.src_h,
                                                         g.nearest ? nearest_coord(mx[r][i]) : mx[r][i],
                                                         g.nearest ? nearest_coord(my[r][i]) : my[r][i], border_y))
@@ -90,7 +90,7 @@ __device__ __forceinline__ void warp_nv12_body(const Geom& g, const Rot& R, cons
         float cx = chroma_coord(mx[0][2 * q], mx[0][2 * q + 1], mx[1][2 * q], mx[1][2 * q + 1]);
         float cy = chroma_coord(my[0][2 * q], my[0][2 * q + 1], my[1][2 * q], my[1][2 * q + 1]);
         if (g.nearest) { cx = nearest_coord(cx); cy = nearest_coord(cy); }
-        cw |= (g.cubic_tab ? sample_cubic<2>(src_uv, g.src_pitch, g.src_w >> 1, g.src_h >> 1, cx, cy, border_uv, g.cubic_tab)
+        cw |= (g.cubic_tab ? sample_hi<2>(src_uv, g.src_pitch, g.src_w >> 1, g.src_h >> 1, cx, cy, border_uv, g.cubic_tab, g.tab_ks)
                            : sample_c2(src_uv, g.src_pitch, g.src_w >> 1, g.src_h >> 1, cx, cy, border_uv))
               << (16 * q);
     }
@@ -144,7 +144,7 @@ __device__ __forceinline__ void warp_packed_body(const Geom& g, const Rot& R, co
             unsigned wv = 0u;
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-                wv |= (g.cubic_tab ? sample_cubic<1>(src, g.src_pitch, g.src_w, g.src_h, mx[r][i], my[r][i], g.border & 255u, g.cubic_tab)
+                wv |= (g.cubic_tab ? sample_hi<1>(src, g.src_pitch, g.src_w, g.src_h, mx[r][i], my[r][i], g.border & 255u, g.cubic_tab, g.tab_ks)
                                    : (unsigned)sample_c1(src, g.src_pitch, g.src_w, g.src_h,
                                                          g.nearest ? nearest_coord(mx[r][i]) : mx[r][i],
                                                          g.nearest ? nearest_coord(my[r][i]) : my[r][i], g.border & 255))
@@ -154,7 +154,7 @@ __device__ __forceinline__ void warp_packed_body(const Geom& g, const Rot& R, co
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 unsigned px = g.cubic_tab
-                                  ? sample_cubic<3>(src, g.src_pitch, g.src_w, g.src_h, mx[r][i], my[r][i], g.border & 0xffffffu, g.cubic_tab)
+                                  ? sample_hi<3>(src, g.src_pitch, g.src_w, g.src_h, mx[r][i], my[r][i], g.border & 0xffffffu, g.cubic_tab, g.tab_ks)
                                   : sample_c3(src, g.src_pitch, g.src_w, g.src_h, g.nearest ? nearest_coord(mx[r][i]) : mx[r][i],
                                               g.nearest ? nearest_coord(my[r][i]) : my[r][i], g.border & 0xffffffu);
                 if (i < valid) {

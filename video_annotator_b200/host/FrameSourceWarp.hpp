@@ -33,7 +33,7 @@ enum CameraPreset {
 
 enum CameraModel { RECTILINEAR, FISHEYE };
 
-enum InterpolationFlags { INTER_NEAREST = 0, INTER_LINEAR = 1, INTER_CUBIC = 2 };  // cv::InterpolationFlags values
+enum InterpolationFlags { INTER_NEAREST = 0, INTER_LINEAR = 1, INTER_CUBIC = 2, INTER_LANCZOS4 = 4 };  // cv::InterpolationFlags values
 
 struct Mat33 {  // stands in for cv::Mat 3x3 CV_64F / cv::Matx33d, row-major
     double m[9];

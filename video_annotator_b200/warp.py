@@ -15,6 +15,7 @@ FORMAT_NV12, FORMAT_BGR24, FORMAT_GRAY8 = 0, 1, 2
 INTER_NEAREST = 0
 INTER_LINEAR = 1
 INTER_CUBIC = 2
+INTER_LANCZOS4 = 4
 
 # CameraPreset, FrameSourceWarp.hpp:14-21
 GOPRO_H4B_WIDE43_PUBLISHED = 0
