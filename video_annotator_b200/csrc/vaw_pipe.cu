@@ -90,6 +90,8 @@ constexpr int kRingOffset = (kCoefOffset + kGroups * kCoefBytes + 1023) & ~1023;
 constexpr int kSmemBytes = 227 << 10;
 constexpr int kRingBytes = kSmemBytes - kRingOffset;
 static_assert(24 * kSlots <= kSlotOffset, "mbarrier area");
+static_assert(kSlots <= 32 && kBatch <= 32, "the producer keeps one slot / one piece of a ticket per lane");
+static_assert(kGroups >= 1 && kGroups <= 15, "one named barrier per consumer group (ids 1..15)");
 static_assert(kSlotBytes % 16 == 0 && kCoefOffset % 16 == 0, "alignment");
 
 __device__ __forceinline__ void pipe_wait(unsigned mbar, unsigned parity)
