@@ -23,17 +23,17 @@
 //   - consumer group g takes stages g, g+kGroups, ...: waits on `full`, collapses the polynomial,
 //     samples the 32 rows from the staged tile, releases the stage (`empty` mbarrier).
 //
-// What the measurements say (B200, C3, 64 frames; TILED = 0.738 ms): shared memory is the currency.
-// A C3 tile is 28 KB and the ring holds seven.  Four groups (16 sampling warps, 96 registers, three
-// tiles of look-ahead): 0.732 ms -- TILED's speed with two thirds of its sampling warps.  Five groups
-// (80 registers, two tiles ahead): 0.836 ms; six groups (72 registers, one tile ahead): 0.854 ms, the
-// consumers then wait for their loads 30 % of the time.  Staging half pieces instead (13-16 KB
-// tiles, three pieces of look-ahead at six groups) needs per-half source boxes from the builder
-// (+50 % builder time) and more live state than 72 registers hold: 1.14 ms.  A single producer warp
-// doing everything (a ~230-instruction dependent chain per piece) was the limit before the issuer
-// warps existed: 0.95 ms.  Look-ahead and sampling warps trade one for one against the same 227 KB,
-// so the pipeline ends where TILED's six staggered CTAs already are; TILED stays the default because
-// it also handles the 16- and 8-row pieces.
+// What the measurements say (B200, C3, 64 frames, against TILED measured in the same runs; DESIGN.md has the
+// table): shared memory is the currency.  A C3 tile is 28 KB and the ring holds seven.  Four groups (16
+// sampling warps, 96 registers, three tiles of look-ahead) run at TILED's speed with two thirds of its
+// sampling warps (0.726 ms against 0.699 ms); five groups (two tiles ahead) 0.759 ms and six groups (one
+// tile ahead) 0.827 ms even with their registers raised by setmaxnreg -- the consumers then wait for their
+// loads up to 30 % of the time.  Staging half pieces instead (13-16 KB tiles) needs per-half source boxes
+// from the builder (+50 % builder time) and more live state than 72 registers hold: 1.14 ms.  A single
+// producer warp doing everything (a ~230-instruction dependent chain per piece) was the limit before the
+// issuer warps existed: 0.95 ms.  Where tiles are too large for TILED's six per SM (C5, 50 KB: 0.464 ms
+// against 0.505 ms) or small enough for the ring to run four pieces ahead (C2, 16 KB: 0.204 against
+// 0.212 ms) the pipeline is the faster variant, and AUTO selects it there (vaw_create).
 #include <cuda.h>
 #include <stdint.h>
 #include "vaw_internal.h"
