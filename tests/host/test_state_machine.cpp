@@ -120,6 +120,24 @@ int main()
         try { get_preset_camera((CameraPreset)42, 10, 10); } catch (int err) { threw = err == VAW_ERR_INVALID; }
         CHECK(threw);
     }
+    {  // the overload with explicit cameras: same state machine, cameras taken as given
+        auto src = std::make_shared<FakeSource>(6);
+        Camera in = get_preset_camera(GOPRO_H4B_WIDE169_MEASURED, 1920, 1080);
+        in.distortion_coefficients[0] = 0.02;
+        Camera out = get_output_camera(in, 1, false, 1);
+        out.width = 1280; out.height = 720;
+        out.matrix.m[0] = out.matrix.m[4] = 400.0; out.matrix.m[2] = 639.5; out.matrix.m[5] = 359.5;
+        RecordingWarp w(src, in, out, 1, INTER_CUBIC, nullptr, false);
+        CHECK(w.output_width() == 1280 && w.output_height() == 720);
+        CHECK(w.input_camera().distortion_coefficients[0] == 0.02);
+        CHECK(w.pull_frame()->index == 1);
+        Camera wrong = in;
+        wrong.width = 1280;
+        bool threw = false;
+        try { RecordingWarp bad(std::make_shared<FakeSource>(6), wrong, out, 1, INTER_LINEAR, nullptr, false); }
+        catch (int err) { threw = err == VAW_ERR_INVALID; }
+        CHECK(threw);                                   // the input camera must describe the frames of the source
+    }
     std::printf("%s: %d checks, %d failed\n", g_failed ? "FAILED" : "OK", g_checks, g_failed);
     return g_failed ? 1 : 0;
 }

@@ -143,12 +143,32 @@ FrameSourceWarp::FrameSourceWarp(std::shared_ptr<FrameSource> source, CameraPres
     m_format = first_frame->format;
     m_input_camera = get_preset_camera(input_camera, first_frame->width, first_frame->height);
     m_output_camera = get_output_camera(m_input_camera, scale, crop_borders, zoom);
-    if (!create_device_context) return;
+    if (create_device_context) create_context();
+}
+
+FrameSourceWarp::FrameSourceWarp(std::shared_ptr<FrameSource> source, const Camera& input_camera, const Camera& output_camera,
+                                 int smooth_radius, InterpolationFlags interpolation,
+                                 std::shared_ptr<RotationSource> rotation_source, bool create_device_context)
+    : m_source(source), m_rotation_source(rotation_source), m_measured_rotation(Mat33::eye()),
+      m_last_frame_rotation(Mat33::eye()), m_smooth_radius((unsigned)smooth_radius), m_interpolation(interpolation),
+      m_rotation_filter(smooth_radius)
+{
+    Frame first_frame = m_source->peek_frame();  // :214-219: device and pixel format come from the first frame
+    m_device = first_frame->device;
+    m_format = first_frame->format;
+    if (first_frame->width != input_camera.width || first_frame->height != input_camera.height) throw (int)VAW_ERR_INVALID;
+    m_input_camera = input_camera;
+    m_output_camera = output_camera;
+    if (create_device_context) create_context();
+}
+
+void FrameSourceWarp::create_context()
+{
     vaw_camera in = camera_to(m_input_camera), out = camera_to(m_output_camera);
     vaw_params p{};
     int rc = vaw_params_from_cameras(&in, &out, m_format, &p);
     if (rc != VAW_OK) throw rc;
-    p.interpolation = (int)m_interpolation;  // INTER_NEAREST, INTER_LINEAR or INTER_CUBIC; anything else -> VAW_ERR_UNSUPPORTED
+    p.interpolation = (int)m_interpolation;  // NEAREST / LINEAR / CUBIC / LANCZOS4; anything else -> VAW_ERR_UNSUPPORTED
     p.border[0] = 0; p.border[1] = 128; p.border[2] = 128;  // NV12: Y 0 (cv::remap's default, :306-312), neutral chroma
     if (m_format == VAW_FORMAT_BGR24) p.border[1] = p.border[2] = 0;
     rc = vaw_create(&p, m_device, &m_ctx);

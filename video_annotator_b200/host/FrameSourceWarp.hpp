@@ -107,6 +107,7 @@ class FrameSourceWarp : public FrameSource {
     std::queue<Mat33> m_buffered_rotations;
 
     void consume_frame(Frame input_frame);
+    void create_context();  // vaw_create from m_input_camera / m_output_camera / m_format / m_interpolation
 
   protected:
     // warp_frame(input, rotation), :272-314.  Virtual so that the state machine can be tested
@@ -124,6 +125,18 @@ class FrameSourceWarp : public FrameSource {
       InterpolationFlags interpolation = INTER_LINEAR,
       std::shared_ptr<RotationSource> rotation_source = nullptr,  // nullptr: the camera does not rotate
       bool create_device_context = true                           // false: CPU-only tests of the state machine
+    );
+    // Overload with explicit cameras: an output camera that get_output_camera cannot express
+    // (BASELINE config 5: 5312x2988 -> 3840x2160 with its own focal length; the out_w / out_h / out_fx /
+    // out_fy options of the wider toolchain, src/render.ts:678-681), or an input camera with distortion.
+    FrameSourceWarp(
+      std::shared_ptr<FrameSource> source,
+      const Camera& input_camera,
+      const Camera& output_camera,
+      int smooth_radius = 30,
+      InterpolationFlags interpolation = INTER_LINEAR,
+      std::shared_ptr<RotationSource> rotation_source = nullptr,
+      bool create_device_context = true
     );
     ~FrameSourceWarp() override;
     Frame pull_frame() override;
