@@ -4,10 +4,15 @@
  *
  * Follows /root/reference/opencv/createMap.cl:10-50 statement by statement,
  * with the argument order of /root/reference/opencv/FrameSourceWarp.cpp:280-300.
- * The reference is OpenCL C; it cannot run here (no OpenCL runtime in the image),
- * so the coordinate stage is PARITY UNPINNED by the reference itself (it has no
- * tests or golden vectors).  It is cross-checked against
- * cv2.fisheye.initUndistortRectifyMap in tests/test_oracle_map.py.
+ * PARITY PINNED: the reference has no tests or golden vectors, but its kernel source
+ * compiles unmodified with gcc behind a shim header (oracle/ref_build -> oracle/_ref,
+ * built from /root/reference/opencv/createMap.cl where it lies).  This transcription
+ * equals that library bit for bit on whole C1/C2/C3/C5 maps (identity to 80 degree
+ * rotations, the NaN pixel at r == 0 included) -- tests/test_oracle_ref.py, live and
+ * through the committed fixture tests/golden/createmap_ref.npz -- and is additionally
+ * cross-checked against cv2.fisheye.initUndistortRectifyMap (tests/test_oracle_map.py).
+ * It exists because /root/reference does not travel to the GPU box and because the
+ * fisheye-distortion extension below is not in the reference kernel.
  *
  * Build with -O2 -ffp-contract=off (no FMA contraction, no x87): every
  * operation below rounds once to fp32, in the order written.  Where OpenCL leaves

@@ -95,6 +95,52 @@ def _fp(a):
     return a.ctypes.data_as(C.POINTER(C.c_float))
 
 
+# ---- oracle/_ref: the reference's own createMap.cl, compiled unmodified by oracle/ref_build ------
+_REF_DIR = os.path.join(_HERE, "_ref")
+_REF_SO = os.path.join(_REF_DIR, "libcreatemap_ref.so")
+_REF_BUILD = os.path.join(_HERE, "ref_build")
+REF_SOURCE = "/root/reference/opencv/createMap.cl"
+_ref_lib = None
+
+
+def build_ref(force=False):
+    """gcc -x c -include cl_shim.h /root/reference/opencv/createMap.cl -> oracle/_ref/libcreatemap_ref.so.
+    Only where the reference tree is mounted (the authoring container); the GPU box uses the prebuilt
+    file that travels with the snapshot.  Returns the path, or None when neither exists."""
+    if os.path.exists(REF_SOURCE):
+        deps = [REF_SOURCE] + [os.path.join(_REF_BUILD, f) for f in ("cl_shim.h", "createmap_driver.c", "Makefile")]
+        if force or not os.path.exists(_REF_SO) or os.path.getmtime(_REF_SO) < max(os.path.getmtime(d) for d in deps):
+            subprocess.check_call(["make", "-C", _REF_BUILD, "-s"])
+    return _REF_SO if os.path.exists(_REF_SO) else None
+
+
+def ref_available():
+    return build_ref() is not None
+
+
+def ref_create_map(k, rot, rows, cols, threads=1):
+    """The map createMap.cl writes (the reference's own kernel source, run on the host over the
+    NDRange {cols, rows} with the argument binding of FrameSourceWarp.cpp:275-300).  Ignores k.dist:
+    the reference kernel has no distortion term."""
+    global _ref_lib
+    if _ref_lib is None:
+        so = build_ref()
+        if so is None:
+            raise RuntimeError("oracle/_ref is not built and /root/reference is not mounted")
+        L = C.CDLL(so)
+        fp = C.POINTER(C.c_float)
+        L.vaw_ref_create_map.argtypes = [fp, fp, C.c_int, C.c_int, C.c_int, fp, fp, C.c_int]
+        L.vaw_ref_create_map.restype = None
+        _ref_lib = L
+    mx = np.full((rows, cols), -12345.0, np.float32)
+    my = np.full((rows, cols), -12345.0, np.float32)
+    kk = np.array([k.src_center_x, k.src_center_y, k.src_focal_x, k.src_focal_y,
+                   k.map_center_x, k.map_center_y, k.map_focal_x, k.map_focal_y], np.float32)
+    r = rot32(rot)
+    _ref_lib.vaw_ref_create_map(_fp(mx), _fp(my), rows, cols, cols * 4, _fp(kk), _fp(r), threads)
+    return mx, my
+
+
 def _u8(a):
     return a.ctypes.data_as(C.POINTER(C.c_uint8))
 
@@ -220,3 +266,15 @@ def synth_nv12(w, h, frame_index=0, seed=20260001, white_noise=False):
     dst = np.empty((h * 3 // 2, w), np.uint8)
     lib().vaw_oracle_synth_nv12(_u8(dst), w, h, w, frame_index, seed, int(white_noise))
     return dst
+
+
+def reference_create_map(k, rot, rows, cols, threads=1):
+    """The coordinate oracle the parity tests check against: the reference's own kernel
+    (oracle/_ref, compiled from createMap.cl) when it is built -- else, or when the fisheye
+    distortion extension is in use (createMap.cl has no such term), the transcription, which
+    tests/test_oracle_ref.py pins to oracle/_ref bit for bit.  Returns (map_x, map_y, kind)."""
+    if not any(k.dist[:]) and ref_available():
+        mx, my = ref_create_map(k, rot, rows, cols, threads)
+        return mx, my, "reference (oracle/_ref: createMap.cl compiled unmodified)"
+    mx, my = create_map(k, rot, rows, cols, threads)
+    return mx, my, "port (oracle/create_map_ref.c)"

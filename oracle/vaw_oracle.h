@@ -23,12 +23,14 @@
  *   - pixel stage: PINNED.  vaw_oracle_remap_u8 is checked bit-for-bit against
  *     cv2.remap (the real cv::remap) in tests/test_oracle_remap.py and against
  *     the committed fixtures tests/golden/remap_*.npz produced by it.
- *   - coordinate stage: PARITY UNPINNED by the reference.  The reference has no
- *     tests, golden vectors or fixtures and createMap.cl cannot run here (no
- *     OpenCL runtime).  The transcription is cross-checked against an
- *     independent implementation of the same projection from the reference's
- *     own dependency, cv2.fisheye.initUndistortRectifyMap (fp32 rounding
- *     level agreement), and frozen as tests/golden/create_map_*.npz.
+ *   - coordinate stage: PINNED to the reference's own kernel.  The reference has
+ *     no tests or golden vectors and there is no OpenCL runtime here, but
+ *     createMap.cl compiles unmodified with gcc behind a shim header
+ *     (oracle/ref_build -> oracle/_ref/libcreatemap_ref.so).  The transcription
+ *     equals that library bit for bit (tests/test_oracle_ref.py: live, and via
+ *     the fixture tests/golden/createmap_ref.npz generated from it); it is also
+ *     cross-checked against cv2.fisheye.initUndistortRectifyMap (fp32 rounding
+ *     level agreement).
  *   - camera stage: cross-checked against cv2.fisheye.undistortPoints.
  *
  * NV12-plane semantics (no reference behaviour exists: the reference warps BGR,

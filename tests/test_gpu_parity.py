@@ -1,7 +1,10 @@
 """Parity of the CUDA warp path (libvaw.so, through the C-ABI) against the CPU oracle.
 
 Bars (BASELINE.json north_star):
-  A. source coordinates within 1e-3 px of the createMap.cl transcription (oracle/create_map_ref.c)
+  A. source coordinates within 1e-3 px of createMap.cl itself: oracle/_ref (the reference's kernel
+     source compiled unmodified, oracle/ref_build) when that library is present -- it travels to the
+     GPU box with the snapshot -- else the transcription oracle/create_map_ref.c, which
+     tests/test_oracle_ref.py pins to _ref bit for bit
      -- and, stronger, BIT-EXACT against the host restatement of the device function
      (tests/helpers/devatan_map.c: same IEEE operations, same atan polynomial);
   B. output pixels 0 LSB from cv::remap's integer filter (oracle/remap_ref.c, pinned to
@@ -110,7 +113,7 @@ def test_coordinates_gather_variant(V, oracle, name, rot):
     ocx, ocy = oracle.chroma_map(hx, hy, threads=NCPU)
     assert G.bits_equal(cx, ocx) and G.bits_equal(cy, ocy)
     # within 1e-3 px of the createMap.cl transcription (libm atanf)
-    ox, oy = oracle.create_map(k, R, oh, ow, threads=NCPU)
+    ox, oy, _ = oracle.reference_create_map(k, R, oh, ow, threads=NCPU)
     assert np.array_equal(np.isnan(ox), np.isnan(mx))
     ex, ey = float(np.nanmax(np.abs(mx - ox))), float(np.nanmax(np.abs(my - oy)))
     _record(f"coords_gather_{name}_{rot}", {"max_err_px": [ex, ey],
@@ -142,7 +145,7 @@ def test_coordinates_poly_variant(V, oracle, name, rot):
     # chroma map = the oracle's definition applied to the kernel's own luma map, bit for bit
     ocx, ocy = oracle.chroma_map(mx, my, threads=NCPU)
     assert G.bits_equal(cx, ocx) and G.bits_equal(cy, ocy)
-    ox, oy = oracle.create_map(k, R, oh, ow, threads=NCPU)
+    ox, oy, _ = oracle.reference_create_map(k, R, oh, ow, threads=NCPU)
     assert np.array_equal(np.isnan(ox), np.isnan(mx)) and np.array_equal(np.isnan(oy), np.isnan(my))
     ex, ey = _exact_map_f64(k, R, oh, ow)
     ulp_x = np.spacing(np.abs(mx).astype(np.float32)).astype(np.float64)
@@ -387,7 +390,7 @@ def test_poly_paths_on_windows(V, oracle, out_size, centre):
     ref = _oracle_on_map(oracle, src, sw, sh, mx, my, cx, cy, border)
     assert np.array_equal(out[:n_out].reshape(oh * 3 // 2, ow), ref)
     k = G.oracle_k(oracle, (w.input_camera, cout))
-    ox, oy = oracle.create_map(k, R, oh, ow)
+    ox, oy, _ = oracle.reference_create_map(k, R, oh, ow, threads=NCPU)
     assert max(float(np.nanmax(np.abs(mx - ox))), float(np.nanmax(np.abs(my - oy)))) < 1e-3
     if centre[0] == 5000.0:
         assert stats["outside"] == stats["pieces"] and (out[:ow * oh] == 7).all()
@@ -768,7 +771,7 @@ def test_fisheye_distortion_coordinates_and_pixels(V, oracle, variant):
     k = oracle.intrinsics(cin.K, w.output_camera.K, dist=DIST)
     mx, my = [t.cpu().numpy() for t in ctx.dump_coords(R, 0)]
     cx, cy = [t.cpu().numpy() for t in ctx.dump_coords(R, 1)]
-    ox, oy = oracle.create_map(k, R, oh, ow, threads=NCPU)
+    ox, oy, _ = oracle.reference_create_map(k, R, oh, ow, threads=NCPU)
     o0x, _ = oracle.create_map(oracle.intrinsics(cin.K, w.output_camera.K), R, oh, ow, threads=NCPU)
     assert float(np.nanmax(np.abs(ox - o0x))) > 1.0           # the distortion is not a no-op
     err = max(float(np.nanmax(np.abs(mx - ox))), float(np.nanmax(np.abs(my - oy))))
@@ -845,7 +848,7 @@ def test_shorter_pieces_for_short_focal_lengths(V, oracle, focal_scale, rows):
     ref = _oracle_on_map(oracle, src, sw, sh, mx, my, cx, cy, border)
     assert np.array_equal(got, ref)
     k = G.oracle_k(oracle, (w.input_camera, cout))
-    ox, oy = oracle.create_map(k, R, oh, ow)
+    ox, oy, _ = oracle.reference_create_map(k, R, oh, ow, threads=NCPU)
     assert max(float(np.nanmax(np.abs(mx - ox))), float(np.nanmax(np.abs(my - oy)))) < 1e-3
     ctx.close()
 

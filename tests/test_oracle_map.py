@@ -1,7 +1,7 @@
 """Coordinate oracle (oracle/create_map_ref.c, restating opencv/createMap.cl:10-50).
 
-The reference has no golden vectors for this stage (parity unpinned); anchors are
-an independent implementation from the reference's own dependency
+Pinned to the reference's own kernel in tests/test_oracle_ref.py (oracle/_ref); here the
+additional anchors: an independent implementation from the reference's own dependency
 (cv2.fisheye.initUndistortRectifyMap) and frozen bit patterns."""
 import os
 
