@@ -49,8 +49,9 @@ enum {
  * VAW_FORMAT_GRAY8: single 8-bit plane. */
 enum { VAW_FORMAT_NV12 = 0, VAW_FORMAT_BGR24 = 1, VAW_FORMAT_GRAY8 = 2 };
 
-/* cv::InterpolationFlags values (opencv/FrameSourceWarp.hpp:90); only LINEAR exists. */
-enum { VAW_INTER_NEAREST = 0, VAW_INTER_LINEAR = 1, VAW_INTER_CUBIC = 2, VAW_INTER_LANCZOS4 = 4 };  /* cv::InterpolationFlags values */
+/* cv::InterpolationFlags values accepted for the constructor's `interpolation` parameter
+ * (opencv/FrameSourceWarp.hpp:90).  All four are cv::remap's 8-bit fixed-point filters, bit for bit. */
+enum { VAW_INTER_NEAREST = 0, VAW_INTER_LINEAR = 1, VAW_INTER_CUBIC = 2, VAW_INTER_LANCZOS4 = 4 };
 
 /* Kernel variants.  Every variant applies cv::remap's integer filter exactly to its own
  * map (vaw_dump_coords returns that map); they differ in how the map is evaluated:
@@ -145,8 +146,13 @@ typedef struct vaw_ctx vaw_ctx;
 int vaw_get_preset_camera(int preset, int width, int height, vaw_camera *out);
 int vaw_get_output_camera(const vaw_camera *input, double scale, int crop_borders, double zoom,
                           vaw_camera *out);
-/* Fill the 8 scalars + sizes of `p` from two cameras (FrameSourceWarp.cpp:283-290);
- * for NV12 the output size is rounded down to even. Other fields are left untouched. */
+/* Fill the 8 scalars + sizes + distortion of `p` from two cameras (FrameSourceWarp.cpp:283-290);
+ * for NV12 the output size is rounded down to even; interpolation = VAW_INTER_LINEAR (the
+ * constructor's default, FrameSourceWarp.hpp:90) and variant = VAW_VARIANT_AUTO; border and
+ * reserved fields are left untouched.  The kernels implement createMap.cl's projection pair:
+ * a FISHEYE input camera and a RECTILINEAR output camera; other models -> VAW_ERR_UNSUPPORTED
+ * (vaw_get_output_camera likewise for a non-fisheye input).  vaw_get_output_camera honours
+ * input->distortion the way cv::fisheye::undistortPoints does (FrameSourceWarp.cpp:93-110). */
 int vaw_params_from_cameras(const vaw_camera *input, const vaw_camera *output, int format,
                             vaw_params *p);
 

@@ -130,3 +130,59 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(base, fn)).read()
                 assert "import oracle" not in text and "from oracle" not in text, fn
                 assert "liboracle" not in text and "vaw_oracle_" not in text, fn
+
+
+def test_output_camera_honours_distortion_like_cv_fisheye():
+    """get_output_camera passes distortion_coefficients to fisheye::undistortPoints
+    (FrameSourceWarp.cpp:93-110); the library's Newton inversion must agree with the real
+    cv2.fisheye.undistortPoints on the 8 probe points, through the derived intrinsics."""
+    cv2 = pytest.importorskip("cv2")
+    import video_annotator_b200 as V
+    dist = np.array([0.05, -0.02, 0.01, -0.003])
+    cam0 = V.get_preset_camera(1, 1920, 1440)
+    cam = V.Camera.from_matrix(cam0.K, 1920, 1440, model=1, distortion=dist)
+    K = cam0.K
+    w1, h1 = 1919.0, 1439.0
+    probes = np.array([[0, 0], [0, h1], [w1, 0], [w1, h1], [K[0, 2], 0], [w1, K[1, 2]], [K[0, 2], h1], [0, K[1, 2]]],
+                      np.float64).reshape(-1, 1, 2)
+    e = cv2.fisheye.undistortPoints(probes, K, dist).reshape(-1, 2)
+    for crop in (False, True):
+        pts = e[4:] if crop else e
+        mn, mx = pts.min(0), pts.max(0)
+        od = np.rint(e[3] - e[0])
+        f = 0.5 * np.hypot(np.rint(w1), np.rint(h1)) / np.hypot(od[0], od[1])
+        out = V.get_output_camera(cam, 0.5, crop, 1.0)
+        assert out.K[0, 0] == pytest.approx(f, rel=1e-12)
+        assert out.K[0, 2] == pytest.approx(f * -mn[0], rel=1e-9)
+        assert out.K[1, 2] == pytest.approx(f * -mn[1], rel=1e-9)
+        assert out.size == (int(f * (mx[0] - mn[0])), int(f * (mx[1] - mn[1])))
+    # and it differs from the zero-distortion camera (the coefficients are not ignored)
+    assert V.get_output_camera(cam, 0.5).size != V.get_output_camera(cam0, 0.5).size
+
+
+def test_camera_models_other_than_fisheye_in_rectilinear_out_are_refused():
+    """createMap.cl implements one projection pair; a RECTILINEAR input camera must not be warped as fisheye."""
+    import video_annotator_b200 as V
+    from video_annotator_b200 import _lib
+    lib = _lib.load()
+    cam = V.get_preset_camera(4, 1920, 1080)
+    rect_in = V.Camera.from_matrix(cam.K, 1920, 1080, model=0)
+    out = _lib.VawCamera()
+    assert lib.vaw_get_output_camera(C.byref(rect_in._c), 1.0, 0, 1.0, C.byref(out)) == -4
+    good_out = V.get_output_camera(cam)
+    p = _lib.VawParams()
+    assert lib.vaw_params_from_cameras(C.byref(rect_in._c), C.byref(good_out._c), 0, C.byref(p)) == -4
+    fish_out = V.Camera.from_matrix(good_out.K, 1758, 998, model=1)
+    assert lib.vaw_params_from_cameras(C.byref(cam._c), C.byref(fish_out._c), 0, C.byref(p)) == -4
+
+
+def test_params_from_cameras_sets_the_reference_defaults():
+    """A zero-initialised vaw_params must come back with INTER_LINEAR (FrameSourceWarp.hpp:90), not 0 = NEAREST."""
+    import video_annotator_b200 as V
+    from video_annotator_b200 import _lib
+    cam = V.get_preset_camera(4, 1920, 1080)
+    out = V.get_output_camera(cam)
+    p = _lib.VawParams()
+    assert _lib.load().vaw_params_from_cameras(C.byref(cam._c), C.byref(out._c), 0, C.byref(p)) == 0
+    assert p.interpolation == V.INTER_LINEAR and p.variant == 0
+    assert (p.out_width, p.out_height) == (1758, 998)

@@ -425,9 +425,23 @@ void free_host_path(vaw_ctx* ctx)
     ctx->host_ready = false;
 }
 
+int init_host_path_impl(vaw_ctx* ctx);
+
 int init_host_path(vaw_ctx* ctx)
 {
     if (ctx->host_ready) return VAW_OK;
+    const int rc = init_host_path_impl(ctx);
+    if (rc != VAW_OK) {  // no half-allocated ring: a retry starts from scratch
+        const std::string msg = ctx->err;
+        free_host_path(ctx);
+        cudaGetLastError();
+        ctx->err = msg;
+    }
+    return rc;
+}
+
+int init_host_path_impl(vaw_ctx* ctx)
+{
     size_t per = ctx->src_frame_bytes;
     int cf = (int)(kChunkBytes / per);
     ctx->chunk_frames = cf < 1 ? 1 : (cf > 64 ? 64 : cf);
@@ -547,7 +561,9 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
     g.has_dist = 0;
     for (int i = 0; i < 4; ++i) {
         g.kd[i] = p.src_distortion[i];
-        if (!(std::fabs(g.kd[i]) <= 1e6f)) { delete ctx; return fail(nullptr, VAW_ERR_INVALID, "distortion coefficient out of range"); }
+        // |k| <= 10 keeps theta_d = theta (1 + k1 theta^2 + ...) far inside the fp32 range the per-pixel
+        // path's shared-reciprocal sequences are certified for (real lenses: |k| < 1)
+        if (!(std::fabs(g.kd[i]) <= 10.0f)) { delete ctx; return fail(nullptr, VAW_ERR_INVALID, "distortion coefficient out of range (|k| <= 10)"); }
         if (g.kd[i] != 0.0f) g.has_dist = 1;
     }
     ctx->src_frame_bytes = vaw_frame_bytes(p.format, p.src_width, p.src_height, p.src_width * ctx->channels);
@@ -571,8 +587,8 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         int rc = cuda_fail(nullptr, e, "vaw_create");
-        cudaFree(ctx->xtab); cudaFree(ctx->ytab);
-        delete ctx;
+        vaw_destroy(ctx);  // frees whatever was allocated so far
+        cudaGetLastError();
         return rc;
     }
     ctx->variant = p.variant != VAW_VARIANT_AUTO ? p.variant
@@ -646,8 +662,8 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
         }
         if (e != cudaSuccess) {
             int rc = cuda_fail(nullptr, e, "vaw_create (piece tables)");
-            cudaFree(ctx->xtab); cudaFree(ctx->ytab);
-            delete ctx;
+            vaw_destroy(ctx);
+            cudaGetLastError();
             return rc;
         }
     }
@@ -718,6 +734,18 @@ int vaw_warp_batch(vaw_ctx* ctx, const uint8_t* src, int src_pitch, size_t src_f
     if (n_frames == 0) return VAW_OK;
     if (ctx->p.format == VAW_FORMAT_NV12 && (src_frame_stride & 1))
         return fail(ctx, VAW_ERR_INVALID, "NV12 frame stride must be even");
+    if (n_frames > 1) {
+        // output frames must not overlap (a zero or short stride would make frames overwrite each other);
+        // source frames may repeat (stride 0 = the same frame under n rotations) but not interleave
+        const size_t out_rows = ctx->p.format == VAW_FORMAT_NV12 ? (size_t)ctx->p.out_height * 3 / 2 : (size_t)ctx->p.out_height;
+        const size_t src_rows = ctx->p.format == VAW_FORMAT_NV12 ? (size_t)ctx->p.src_height * 3 / 2 : (size_t)ctx->p.src_height;
+        const size_t dst_need = (out_rows - 1) * (size_t)dst_pitch + (size_t)ctx->p.out_width * ctx->channels;
+        const size_t src_need = (src_rows - 1) * (size_t)src_pitch + (size_t)ctx->p.src_width * ctx->channels;
+        if (dst_frame_stride < dst_need)
+            return fail(ctx, VAW_ERR_INVALID, "dst_frame_stride smaller than one output frame");
+        if (src_frame_stride != 0 && src_frame_stride < src_need)
+            return fail(ctx, VAW_ERR_INVALID, "src_frame_stride smaller than one source frame (0 = repeat the frame)");
+    }
     DeviceGuard dg(ctx->device);
     return launch(ctx, src, src_pitch, src_frame_stride, dst, dst_pitch, dst_frame_stride, rotations,
                   nullptr, n_frames, (cudaStream_t)stream);
@@ -761,11 +789,21 @@ int vaw_warp_batch_host(vaw_ctx* ctx, const uint8_t* src_host, uint8_t* dst_host
         return VAW_OK;
     };
 
-    int k = 0;
-    for (int first = 0; first < n_frames; first += ctx->chunk_frames, ++k) {
-        Stage& s = ctx->stage[k % kStages];
-        if ((rc = drain(s))) return rc;
-        const int n = n_frames - first < ctx->chunk_frames ? n_frames - first : ctx->chunk_frames;
+    // On any error: wait for every stage still in flight (its DMA may be reading src_host or writing
+    // dst_host / the pinned staging), forget the staged outputs and only then return, so that the
+    // caller may free or reuse its buffers.  The message of the first error is kept.
+    auto abort_all = [&](int code) -> int {
+        const std::string msg = ctx->err;
+        for (Stage& s : ctx->stage) {
+            if (s.stream) cudaStreamSynchronize(s.stream);
+            s.busy = false;
+            s.out_staged = false;
+        }
+        cudaGetLastError();
+        ctx->err = msg;
+        return code;
+    };
+    auto submit = [&](Stage& s, int first, int n) -> int {
         const uint8_t* hsrc = src_host + (size_t)first * sfb;
         uint8_t* hdst = dst_host + (size_t)first * dfb;
         for (int i = 0; i < n * 9; ++i) s.pin_rot[i] = (float)rotations_host[(size_t)first * 9 + i];
@@ -776,18 +814,28 @@ int vaw_warp_batch_host(vaw_ctx* ctx, const uint8_t* src_host, uint8_t* dst_host
             hsrc = s.pin_in;
         }
         VAW_CUDA(ctx, cudaMemcpyAsync(s.dev_in, hsrc, sfb * n, cudaMemcpyHostToDevice, s.stream));
-        rc = launch(ctx, s.dev_in, src_pitch, sfb, s.dev_out, dst_pitch, dfb, s.dev_rot, nullptr, n, s.stream, s.pieces, s.counter);
-        if (rc) return rc;
+        s.busy = true;  // from here on the stage has work in flight that touches the caller's buffers
+        int rc2 = launch(ctx, s.dev_in, src_pitch, sfb, s.dev_out, dst_pitch, dfb, s.dev_rot, nullptr, n, s.stream, s.pieces, s.counter);
+        if (rc2) return rc2;
         s.out_staged = !dst_pinned;
         if (s.out_staged && !s.pin_out) VAW_CUDA(ctx, cudaMallocHost(&s.pin_out, dfb * ctx->chunk_frames));
         VAW_CUDA(ctx, cudaMemcpyAsync(s.out_staged ? s.pin_out : hdst, s.dev_out, dfb * n, cudaMemcpyDeviceToHost, s.stream));
         s.host_dst = hdst;
         s.out_bytes = dfb * n;
-        s.busy = true;
+        return VAW_OK;
+    };
+
+    int k = 0;
+    for (int first = 0; first < n_frames; first += ctx->chunk_frames, ++k) {
+        Stage& s = ctx->stage[k % kStages];
+        if ((rc = drain(s))) return abort_all(rc);
+        const int n = n_frames - first < ctx->chunk_frames ? n_frames - first : ctx->chunk_frames;
+        s.out_staged = false;
+        if ((rc = submit(s, first, n))) return abort_all(rc);
     }
     // drain in submission order
     for (int i = 0; i < kStages; ++i)
-        if ((rc = drain(ctx->stage[(k + i) % kStages]))) return rc;
+        if ((rc = drain(ctx->stage[(k + i) % kStages]))) return abort_all(rc);
     return VAW_OK;
 }
 

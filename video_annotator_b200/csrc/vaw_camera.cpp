@@ -8,9 +8,11 @@
 //   - the "MEASURED" presets scale cx by width but fx, fy AND cy by height (:50-77);
 //   - both diagonals of the scale estimate pass through integer cv::Point (:142-150);
 //   - the output size is truncated, not rounded (:163).
-// cv::fisheye::undistortPoints (OpenCV calib3d) is only ever called with zero
-// distortion and identity R/P here (:35, :93-110), which reduces to
-// p * tan(theta)/theta with theta = |p| clamped to pi/2.
+// cv::fisheye::undistortPoints (OpenCV calib3d) is called with the camera's
+// distortion_coefficients and identity R/P (:93-110).  The presets carry zeros (:35), which
+// reduces to p * tan(theta)/theta with theta = |p| clamped to pi/2; non-zero k1..k4 (the
+// explicit-camera constructor) go through the same Newton inversion OpenCV runs (10 iterations,
+// epsilon 1e-8), checked against cv2.fisheye.undistortPoints in tests/test_oracle_camera.py.
 #include <cmath>
 #include <cstring>
 #include "../../include/vaw.h"
@@ -21,13 +23,32 @@ constexpr double kPi = 3.1415926535897932384626433832795;
 
 struct Pt { double x, y; };
 
-Pt undistort_ideal_fisheye(Pt d, const double K[9])
+// cv::fisheye::undistortPoints for one point, R = P = identity: theta_d = |p| (clamped to the
+// model's 180-degree field), theta from theta_d = theta (1 + k1 theta^2 + ... + k4 theta^8) by
+// Newton's method started at theta_d, result p * tan(theta) / theta_d.  Points whose iteration
+// does not converge or changes sign come back as (-1e6, -1e6), as in OpenCV.
+Pt undistort_fisheye(Pt d, const double K[9], const double kd[4])
 {
     Pt pw{(d.x - K[2]) / K[0], (d.y - K[5]) / K[4]};
     double theta_d = std::sqrt(pw.x * pw.x + pw.y * pw.y);
     theta_d = std::fmin(std::fmax(-kPi / 2, theta_d), kPi / 2);
-    double scale = theta_d > 1e-8 ? std::tan(theta_d) / theta_d : 1.0;
-    return {pw.x * scale, pw.y * scale};
+    double theta = theta_d, scale = 0.0;
+    bool converged = false;
+    if (std::fabs(theta_d) > 1e-8) {
+        for (int j = 0; j < 10; ++j) {
+            const double t2 = theta * theta, t4 = t2 * t2, t6 = t4 * t2, t8 = t6 * t2;
+            const double k0 = kd[0] * t2, k1 = kd[1] * t4, k2 = kd[2] * t6, k3 = kd[3] * t8;
+            const double fix = (theta * (1 + k0 + k1 + k2 + k3) - theta_d) / (1 + 3 * k0 + 5 * k1 + 7 * k2 + 9 * k3);
+            theta -= fix;
+            if (std::fabs(fix) < 1e-8) { converged = true; break; }
+        }
+        scale = std::tan(theta) / theta_d;
+    } else {
+        converged = true;
+    }
+    const bool flipped = (theta_d < 0 && theta > 0) || (theta_d > 0 && theta < 0);
+    if (converged && !flipped) return {pw.x * scale, pw.y * scale};
+    return {-1000000.0, -1000000.0};
 }
 
 inline int round_half_even(double v) { return (int)std::lrint(v); }  // cv::saturate_cast<int>(double)
@@ -75,12 +96,16 @@ extern "C" int vaw_get_output_camera(const vaw_camera* input, double scale, int 
                                      double zoom, vaw_camera* out)
 {
     if (!input || !out || zoom == 0) return VAW_ERR_INVALID;
+    // get_output_camera always runs fisheye::undistortPoints (:93-110), whatever Camera::model says;
+    // this library's kernels implement the fisheye input model only, so anything else is refused
+    // here instead of being warped with the wrong projection
+    if (input->model != 1) return VAW_ERR_UNSUPPORTED;
     const double* K = input->matrix;
     const double w1 = input->width - 1, h1 = input->height - 1;
     // four corners, then the four edge midpoints through the principal point
     const Pt probes[8] = {{0, 0}, {0, h1}, {w1, 0}, {w1, h1}, {K[2], 0}, {w1, K[5]}, {K[2], h1}, {0, K[5]}};
     Pt e[8];
-    for (int i = 0; i < 8; ++i) e[i] = undistort_ideal_fisheye(probes[i], K);
+    for (int i = 0; i < 8; ++i) e[i] = undistort_fisheye(probes[i], K, input->distortion);
 
     const int first = crop_borders ? 4 : 0;
     double min_x = e[first].x, max_x = e[first].x, min_y = e[first].y, max_y = e[first].y;
@@ -107,6 +132,7 @@ extern "C" int vaw_params_from_cameras(const vaw_camera* input, const vaw_camera
                                        vaw_params* p)
 {
     if (!input || !output || !p) return VAW_ERR_INVALID;
+    if (input->model != 1 || output->model != 0) return VAW_ERR_UNSUPPORTED;  // fisheye in, rectilinear out (createMap.cl)
     p->src_center_x = input->matrix[2];
     p->src_center_y = input->matrix[5];
     p->src_focal_x = input->matrix[0];
@@ -124,6 +150,8 @@ extern "C" int vaw_params_from_cameras(const vaw_camera* input, const vaw_camera
         p->out_height &= ~1;
     }
     p->format = format;
+    p->interpolation = VAW_INTER_LINEAR;  // the constructor's default (FrameSourceWarp.hpp:90)
+    p->variant = VAW_VARIANT_AUTO;
     for (int i = 0; i < 4; ++i) p->src_distortion[i] = (float)input->distortion[i];  // zeros for the presets (:35)
     return VAW_OK;
 }

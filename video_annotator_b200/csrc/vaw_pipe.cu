@@ -35,6 +35,7 @@
 // against 0.505 ms) or small enough for the ring to run four pieces ahead (C2, 16 KB: 0.204 against
 // 0.212 ms) the pipeline is the faster variant, and AUTO selects it there (vaw_create).
 #include <cuda.h>
+#include <atomic>
 #include <stdint.h>
 #include "vaw_internal.h"
 #include "vaw_poly.cuh"
@@ -472,19 +473,22 @@ int pipe_smem_bytes(int tile_cap) { (void)tile_cap; return kSmemBytes; }
 cudaError_t launch_warp_nv12_pipe(const Geom& g, const FrameBatch& b, const PieceRec* table, unsigned* counter,
                                   const TileMaps& maps, cudaStream_t st)
 {
-    static bool configured[64] = {};  // per device; a benign race: the attribute call is idempotent
-    static int sm_count[64] = {};
+    // once per device: the SM count is published before the flag (one host thread per device launches
+    // concurrently in the clip scheduler); ordinals beyond the table query and set on every launch
+    static std::atomic<int> sm_count[64];
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64) dev = 0;
-    if (!configured[dev]) {
+    const bool tracked = dev >= 0 && dev < 64;
+    int sms = tracked ? sm_count[dev].load(std::memory_order_acquire) : 0;
+    if (sms == 0) {
         cudaError_t e = cudaFuncSetAttribute(warp_nv12_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return e;
-        configured[dev] = true;
+        if (sms < 1) sms = 1;
+        if (tracked) sm_count[dev].store(sms, std::memory_order_release);
     }
     const long long total = (long long)pieces_x(g.out_w) * pieces_y(g.out_h, kPieceHMax) * b.n_frames;
-    long long ctas = sm_count[dev];
+    long long ctas = sms;
     if (ctas > (total + kBatch - 1) / kBatch) ctas = (total + kBatch - 1) / kBatch;
     if (ctas < 1) ctas = 1;
     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned), st);

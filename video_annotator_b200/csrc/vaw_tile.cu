@@ -29,6 +29,7 @@
 #include <cuda.h>
 #include <stdint.h>
 #include <algorithm>
+#include <atomic>
 #include "vaw_internal.h"
 #include "vaw_poly.cuh"
 #include "vaw_tile.cuh"
@@ -258,14 +259,17 @@ int tile_need_bytes(const PieceRec& rec)
 cudaError_t launch_warp_nv12_tile(const Geom& g, const FrameBatch& b, const PieceRec* table, const TileMaps& maps,
                                   cudaStream_t st)
 {
-    static bool configured[64] = {};  // per device; a benign race: the attribute call is idempotent
+    // once per device (the clip scheduler launches from one host thread per device); ordinals
+    // beyond the table simply set the attribute on every launch
+    static std::atomic<bool> configured[64];
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !configured[dev]) {
+    const bool tracked = dev >= 0 && dev < 64;
+    if (!tracked || !configured[dev].load(std::memory_order_acquire)) {
         cudaError_t e = cudaFuncSetAttribute(warp_nv12_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              tile_smem_bytes(kTileCapMax));
         if (e != cudaSuccess) return e;
-        configured[dev] = true;
+        if (tracked) configured[dev].store(true, std::memory_order_release);
     }
     dim3 block(32, kWarps);
     dim3 grid(pieces_x(g.out_w), pieces_y(g.out_h, g.piece_h), b.n_frames);
