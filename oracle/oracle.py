@@ -118,7 +118,7 @@ def ref_available():
     return build_ref() is not None
 
 
-def ref_create_map(k, rot, rows, cols, threads=1):
+def ref_create_map(k, rot, rows, cols, threads=1, sentinel=None):
     """The map createMap.cl writes (the reference's own kernel source, run on the host over the
     NDRange {cols, rows} with the argument binding of FrameSourceWarp.cpp:275-300).  Ignores k.dist:
     the reference kernel has no distortion term."""
@@ -132,8 +132,12 @@ def ref_create_map(k, rot, rows, cols, threads=1):
         L.vaw_ref_create_map.argtypes = [fp, fp, C.c_int, C.c_int, C.c_int, fp, fp, C.c_int]
         L.vaw_ref_create_map.restype = None
         _ref_lib = L
-    mx = np.full((rows, cols), -12345.0, np.float32)
-    my = np.full((rows, cols), -12345.0, np.float32)
+    if sentinel is None:
+        mx = np.empty((rows, cols), np.float32)
+        my = np.empty((rows, cols), np.float32)
+    else:  # tests: pre-fill so that a work-item that never ran is visible
+        mx = np.full((rows, cols), sentinel, np.float32)
+        my = np.full((rows, cols), sentinel, np.float32)
     kk = np.array([k.src_center_x, k.src_center_y, k.src_focal_x, k.src_focal_y,
                    k.map_center_x, k.map_center_y, k.map_focal_x, k.map_focal_y], np.float32)
     r = rot32(rot)

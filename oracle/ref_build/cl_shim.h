@@ -1,7 +1,7 @@
 /*
  * cl_shim.h -- the handful of OpenCL C built-ins /root/reference/opencv/createMap.cl uses,
  * spelled for gcc, so that the reference's kernel source compiles UNMODIFIED as plain C
- * (gcc -x c -include cl_shim.h /root/reference/opencv/createMap.cl).  TEST INFRASTRUCTURE ONLY.
+ * (createmap_driver.c: #include "cl_shim.h", then #include of the .cl file).  TEST INFRASTRUCTURE ONLY.
  *
  * What is fixed here because OpenCL C leaves it to the implementation:
  *   - dot(float3, float3): ((a0*b0 + a1*b1) + a2*b2), every operation rounded once to fp32
@@ -18,7 +18,7 @@
 #include <math.h>
 #include <stddef.h>
 
-#define __kernel
+#define __kernel static inline
 #define __global
 
 typedef float float2 __attribute__((vector_size(8)));

@@ -19,13 +19,12 @@
 
 __thread size_t vaw_cl_global_id[3];
 
-/* the reference kernel, compiled from its own source file */
-void createMap(float *out_map_x, int map_x_step, int map_x_offset, int map_rows, int map_cols,
-               float *out_map_y, int map_y_step, int map_y_offset,
-               float src_center_x, float src_center_y, float src_focal_x, float src_focal_y,
-               float map_center_x, float map_center_y, float map_focal_x, float map_focal_y,
-               float rot00, float rot01, float rot02, float rot10, float rot11, float rot12,
-               float rot20, float rot21, float rot22);
+/* The reference kernel: its own source file, included from where it lies under /root/reference
+ * (VAW_REF_CL is that path, set by the Makefile), so that gcc can inline the work-item function
+ * into the NDRange loop below -- the CPU baseline then does not pay a 25-argument call per pixel.
+ * The text of the kernel is not touched; with -ffp-contract=off and no fast-math, inlining cannot
+ * change a single rounding (tests/test_oracle_ref.py compares whole maps bit for bit). */
+#include VAW_REF_CL
 
 typedef struct {
     float *map_x, *map_y;

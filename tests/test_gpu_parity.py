@@ -227,10 +227,12 @@ def test_pixels_bit_exact_on_same_map(V, oracle, name, rot, white, variant):
     full = oracle.warp_nv12(src, sw, sh, w.out_size[0], w.out_size[1], k, R, border=border, threads=NCPU)
     st = G.diff_stats(got, full)
     _record(f"pixels_vs_oracle_path_v{variant}_{name}_{rot}_{'white' if white else 'smooth'}", st)
+    # bounds = the measured tails (profiles/r01_parity.json) with ~40 % head-room, so that a map regression
+    # shows: white noise worst case C5 0.21 % differ / 0.145 % > 1 LSB / max 9; band-limited 3e-6 > 1 LSB
     if white:
-        assert st["differ"] < 0.01 and st["max"] <= 10, st    # 1 ulp -> 0.29 % flips, max 8
+        assert st["differ"] < 3e-3 and st["gt1"] < 2e-3 and st["max"] <= 9 and st["psnr"] > 64, st
     else:
-        assert st["gt1"] < 1e-4 and st["psnr"] > 60, st
+        assert st["gt1"] < 1e-5 and st["max"] <= 6 and st["psnr"] > 80, st
     ctx.close()
 
 

@@ -55,7 +55,7 @@ def test_transcription_equals_reference_kernel_live(oracle, geom):
     (ow, oh) = w.out_size
     for R in (np.eye(3), rotation_xyz(2.0, -3.0, 1.5), rotation_xyz(10.0, -15.0, 20.0), rotation_xyz(-75.0, 40.0, 3.0)):
         ax, ay = oracle.create_map(k, R, oh, ow, threads=NCPU)
-        bx, by = oracle.ref_create_map(k, R, oh, ow, threads=NCPU)
+        bx, by = oracle.ref_create_map(k, R, oh, ow, threads=NCPU, sentinel=-12345.0)
         assert bits_equal(ax, bx) and bits_equal(ay, by)
         assert not np.any(bx == -12345.0)  # the NDRange covered every pixel
 

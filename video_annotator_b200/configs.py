@@ -14,7 +14,6 @@ import numpy as np
 
 from . import warp as W
 
-ROT_SEED = 20260002
 CONTENT_SEED = 20260001
 
 
@@ -52,46 +51,7 @@ class Workload:
         return make_rotations(total, self.sigma_deg)[first:first + n]
 
 
-def _rodrigues(v):
-    th = np.linalg.norm(v)
-    if th < 1e-15:
-        return np.eye(3)
-    k = v / th
-    K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
-    return np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * (K @ K)
-
-
-def sg_weights(m):
-    """Savitzky-Golay smoothing weights, window 2m+1, polynomial order 2 (centre point)."""
-    i = np.arange(-m, m + 1, dtype=np.float64)
-    return 3.0 * (3 * m * m + 3 * m - 1 - 5 * i * i) / ((2 * m + 3) * (2 * m + 1) * (2 * m - 1))
-
-
-def make_rotations(n, sigma_deg, radius=30, seed=ROT_SEED):
-    """(n, 3, 3) float64 warp rotations for a seeded gyro random walk (identity if sigma = 0)."""
-    if sigma_deg == 0 or n == 0:
-        return np.tile(np.eye(3), (n, 1, 1))
-    rng = np.random.default_rng(seed)
-    inc = rng.normal(0.0, np.deg2rad(sigma_deg), (n, 3))
-    measured = np.empty((n, 3, 3))
-    acc = np.eye(3)
-    for i in range(n):
-        acc = _rodrigues(inc[i]) @ acc          # FrameSourceWarp.cpp:441-442
-        measured[i] = acc
-    w = sg_weights(radius)
-    pad = np.concatenate([np.repeat(measured[:1], radius, 0), measured,
-                          np.repeat(measured[-1:], radius, 0)])  # :456-461 pads with the last rotation
-    out = np.empty_like(measured)
-    for i in range(n):
-        m = np.tensordot(w, pad[i:i + 2 * radius + 1], axes=(0, 0))
-        u, _, vt = np.linalg.svd(m)              # back to SO(3)
-        s = u @ vt
-        if np.linalg.det(s) < 0:
-            u[:, -1] *= -1
-            s = u @ vt
-        correction = s @ measured[i].T           # :472
-        out[i] = correction.T                    # :475 (inverse of a rotation)
-    return out
+from .rotations import ROT_SEED, make_rotations, sg_weights  # noqa: E402,F401  (pure numpy, also loaded stand-alone by bench.py's reference arm)
 
 
 def _centred(f, size):

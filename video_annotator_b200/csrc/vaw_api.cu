@@ -23,6 +23,7 @@ static_assert(sizeof(vaw_params) == 128 && sizeof(vaw_camera) == 120, "C-ABI str
 namespace {
 
 constexpr int kStages = 4;                      // host-path pipeline depth
+constexpr int kHeadFrames = 8;                  // frames whose table is built in line; the rest overlaps their sampling
 constexpr size_t kChunkBytes = 32u << 20;       // target bytes of source frames per chunk (small: short pipeline fill and drain)
 thread_local std::string g_create_error;
 
@@ -73,6 +74,12 @@ struct vaw_ctx {
     int tex_next = 0;
     int tex_align = 512, tex_pitch_align = 32;
     unsigned* counter = nullptr;  // piece queue of variant PIPE (for ctx->table)
+    unsigned* counter2 = nullptr; // ... of the second sampler launch of a split batch
+    // builder off the critical path: the table of all but the first kHeadFrames frames of a batch is
+    // built on a high-priority side stream while the sampler already works on the head frames
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool split_builder = true;
     // option "time_kernels": CUDA-event stamps around the kernels of every launch (bench.py's roofline)
     static constexpr int kTimeRing = 512;
     bool time_kernels = false;
@@ -370,7 +377,23 @@ int launch(vaw_ctx* ctx, const uint8_t* src, int src_pitch, size_t src_stride, u
             }
             cudaEvent_t* tev = ctx->time_kernels ? ctx->tev + vaw_ctx::kTev * (ctx->timed_launches % vaw_ctx::kTimeRing) : nullptr;
             if (tev) cudaEventRecord(tev[0], st);
-            e = vaw::launch_build_pieces(ctx->gd, ctx->basis, bb.rots, rot0 ? rot0->r : nullptr, bb.n_frames, tab, st);
+            // Split: [builder(head) -> sampler(head)] on `st`, builder(rest) meanwhile on the side stream,
+            // then sampler(rest) on `st`.  The side stream starts after everything already queued on `st`
+            // (the rotations may come from there) and is ordered before the second sampler by an event.
+            const bool split = ctx->split_builder && ctx->side && !table_override && ctx->variant != VAW_VARIANT_TEX &&
+                               bb.n_frames >= 4 * kHeadFrames;
+            const int head = split ? kHeadFrames : bb.n_frames;
+            if (split) {
+                VAW_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
+                VAW_CUDA(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+                e = vaw::launch_build_pieces(ctx->gd, ctx->basis, bb.rots ? bb.rots + (size_t)head * 9 : nullptr,
+                                             rot0 ? rot0->r : nullptr, bb.n_frames - head,
+                                             tab + (size_t)head * ctx->pieces_per_frame, ctx->side);
+                if (e != cudaSuccess) return cuda_fail(ctx, e, "piece table launch (side stream)");
+                ctx->launches++;
+                VAW_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side));
+            }
+            e = vaw::launch_build_pieces(ctx->gd, ctx->basis, bb.rots, rot0 ? rot0->r : nullptr, head, tab, st);
             if (e != cudaSuccess) return cuda_fail(ctx, e, "piece table launch");
             ctx->launches++;
             if (tev) cudaEventRecord(tev[1], st);
@@ -385,20 +408,37 @@ int launch(vaw_ctx* ctx, const uint8_t* src, int src_pitch, size_t src_stride, u
                 }
             }
             if (tev) cudaEventRecord(tev[2], st);
-            if (piped)
-                e = vaw::launch_warp_nv12_pipe(g, bb, tab, table_override ? counter_override : ctx->counter,
-                                               tile_maps(ctx, bb.src, src_pitch, src_stride, bb.n_frames), st);
-            else if (tiled)
-                e = vaw::launch_warp_nv12_tile(g, bb, tab, tile_maps(ctx, bb.src, src_pitch, src_stride, bb.n_frames), st);
-            else
-                e = vaw::launch_warp_nv12_poly(g, bb, tab, st);
-            if (e == cudaSuccess && !table_override) {
+            const vaw::TileMaps* tm = (piped || tiled) ? &tile_maps(ctx, bb.src, src_pitch, src_stride, bb.n_frames) : nullptr;
+            for (int part = 0; part < (split ? 2 : 1); ++part) {
+                vaw::FrameBatch pb = bb;
+                const vaw::PieceRec* ptab = tab;
+                unsigned* cnt = table_override ? counter_override : ctx->counter;
+                if (split) {
+                    pb.n_frames = part ? bb.n_frames - head : head;
+                    if (part) {
+                        // everything is re-based on the first frame of the part, except the tensor maps,
+                        // which stay encoded over the whole clip (frame coordinate offset by tma_frame0)
+                        pb.src = bb.src + (size_t)head * src_stride;
+                        pb.dst = bb.dst + (size_t)head * dst_stride;
+                        if (bb.rots) pb.rots = bb.rots + (size_t)head * 9;
+                        pb.tma_frame0 = head;
+                        ptab = tab + (size_t)head * ctx->pieces_per_frame;
+                        cnt = ctx->counter2;
+                        VAW_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
+                    }
+                }
+                if (piped) e = vaw::launch_warp_nv12_pipe(g, pb, ptab, cnt, *tm, st);
+                else if (tiled) e = vaw::launch_warp_nv12_tile(g, pb, ptab, *tm, st);
+                else e = vaw::launch_warp_nv12_poly(g, pb, ptab, st);
+                if (e != cudaSuccess) return cuda_fail(ctx, e, "warp kernel launch");
+                ctx->launches++;
+            }
+            if (!table_override) {
                 ctx->table_used = true;
                 ctx->table_stream = st;
                 e = cudaEventRecord(ctx->table_free, st);
+                if (e != cudaSuccess) return cuda_fail(ctx, e, "warp kernel launch");
             }
-            if (e != cudaSuccess) return cuda_fail(ctx, e, "warp kernel launch");
-            ctx->launches++;
             if (tev) { cudaEventRecord(tev[3], st); ctx->timed_launches++; }
             continue;
         }
@@ -619,6 +659,14 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
         e = cudaEventCreateWithFlags(&ctx->table_free, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaMalloc(&ctx->dump_table, ctx->pieces_per_frame * sizeof(vaw::PieceRec));
         if (e == cudaSuccess) e = cudaMalloc(&ctx->counter, 256);
+        if (e == cudaSuccess) e = cudaMalloc(&ctx->counter2, 256);
+        if (e == cudaSuccess) {
+            int lo = 0, hi = 0;  // "greatest" priority is the numerically lowest
+            e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+            if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, hi);
+        }
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
         if (e == cudaSuccess && ctx->variant == VAW_VARIANT_TEX) {
             cudaDeviceProp prop{};
             e = cudaGetDeviceProperties(&prop, device);
@@ -684,6 +732,10 @@ void vaw_destroy(vaw_ctx* ctx)
     cudaFree(ctx->table);
     cudaFree(ctx->dump_table);
     cudaFree(ctx->counter);
+    cudaFree(ctx->counter2);
+    if (ctx->side) cudaStreamDestroy(ctx->side);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->table_free) cudaEventDestroy(ctx->table_free);
     if (ctx->tev) {
         for (int i = 0; i < vaw_ctx::kTev * vaw_ctx::kTimeRing; ++i) cudaEventDestroy(ctx->tev[i]);
@@ -699,6 +751,7 @@ int vaw_set_option(vaw_ctx* ctx, const char* name, int value)
 {
     if (!ctx || !name) return VAW_ERR_INVALID;
     if (!std::strcmp(name, "force_exact")) { ctx->g.force_exact = value ? 1 : 0; return VAW_OK; }
+    if (!std::strcmp(name, "split_builder")) { ctx->split_builder = value != 0; return VAW_OK; }
     if (!std::strcmp(name, "time_kernels")) {
         DeviceGuard dg(ctx->device);
         if (value && !ctx->tev) {

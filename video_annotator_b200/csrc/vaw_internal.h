@@ -16,6 +16,7 @@ struct FrameBatch {
     Rot rot0;
     int n_frames;
     int skip_interior;  // variant TEX: certified interior pieces are sampled by the texture kernel
+    int tma_frame0;     // frame index of src within the clip the tensor maps were encoded for (split batches)
 };
 
 // xtab[u] = (u - mcx)/mfx for u < n_x, ytab[v] = (v - mcy)/mfy for v < n_y (createMap.cl:16-17)

@@ -314,12 +314,12 @@ warp_nv12_pipe_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
                         const int mi = (pl - kTileMinPitch) / kTilePitchStep;
                         const CUtensorMap *map = &maps.m[mi], *map32 = &maps.m32[mi];
                         int r = 0;
-                        for (; r + 32 <= nr8; r += 32) tma_load_3d(l0 + (unsigned)(r * pl), map32, lx0 >> 2, by0 + r, head.frame, fb);
-                        for (; r < nr8; r += 8) tma_load_3d(l0 + (unsigned)(r * pl), map, lx0 >> 2, by0 + r, head.frame, fb);
+                        for (; r + 32 <= nr8; r += 32) tma_load_3d(l0 + (unsigned)(r * pl), map32, lx0 >> 2, by0 + r, head.frame + b.tma_frame0, fb);
+                        for (; r < nr8; r += 8) tma_load_3d(l0 + (unsigned)(r * pl), map, lx0 >> 2, by0 + r, head.frame + b.tma_frame0, fb);
                         for (r = 0; r + 32 <= cnr8; r += 32)
-                            tma_load_3d(c0 + (unsigned)(r * pl), map32, cbx0 >> 2, g.src_h + cy0 + r, head.frame, fb);
+                            tma_load_3d(c0 + (unsigned)(r * pl), map32, cbx0 >> 2, g.src_h + cy0 + r, head.frame + b.tma_frame0, fb);
                         for (; r < cnr8; r += 8)
-                            tma_load_3d(c0 + (unsigned)(r * pl), map, cbx0 >> 2, g.src_h + cy0 + r, head.frame, fb);
+                            tma_load_3d(c0 + (unsigned)(r * pl), map, cbx0 >> 2, g.src_h + cy0 + r, head.frame + b.tma_frame0, fb);
                     }
                 }
             }

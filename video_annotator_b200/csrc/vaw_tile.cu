@@ -174,12 +174,12 @@ warp_nv12_tile_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
         const CUtensorMap *map = &maps.m[mi], *map32 = &maps.m32[mi];
         const unsigned l0 = smem_u32(ltile), c0 = smem_u32(ctile);
         int k = 0;
-        for (; k + 32 <= nr8; k += 32) tma_load_3d(l0 + (unsigned)(k * pl), map32, lx0 >> 2, by0 + k, frame, mbar);
-        for (; k < nr8; k += 8) tma_load_3d(l0 + (unsigned)(k * pl), map, lx0 >> 2, by0 + k, frame, mbar);
+        for (; k + 32 <= nr8; k += 32) tma_load_3d(l0 + (unsigned)(k * pl), map32, lx0 >> 2, by0 + k, frame + b.tma_frame0, mbar);
+        for (; k < nr8; k += 8) tma_load_3d(l0 + (unsigned)(k * pl), map, lx0 >> 2, by0 + k, frame + b.tma_frame0, mbar);
         for (k = 0; k + 32 <= cnr8; k += 32)
-            tma_load_3d(c0 + (unsigned)(k * pl), map32, cbx0 >> 2, g.src_h + cy0 + k, frame, mbar);
+            tma_load_3d(c0 + (unsigned)(k * pl), map32, cbx0 >> 2, g.src_h + cy0 + k, frame + b.tma_frame0, mbar);
         for (; k < cnr8; k += 8)
-            tma_load_3d(c0 + (unsigned)(k * pl), map, cbx0 >> 2, g.src_h + cy0 + k, frame, mbar);
+            tma_load_3d(c0 + (unsigned)(k * pl), map, cbx0 >> 2, g.src_h + cy0 + k, frame + b.tma_frame0, mbar);
     }
 
     // ---- collapse the polynomial: warp w does column j = w for every lane -------------------------
