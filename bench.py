@@ -79,6 +79,7 @@ def parse_args():
     ap.add_argument("--no-shim", action="store_true")
     ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to its GPU's NUMA node")
     ap.add_argument("--no-split-builder", action="store_true")
+    ap.add_argument("--tile-kernel", type=int, default=0, help="A/B: 1 = the round-1 tile kernel, 2 = the quadrant kernel (default)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample budget")
     return ap.parse_args()
 
@@ -428,7 +429,7 @@ def shim_bench():
         return {"error": repr(exc)[:200]}
 
 
-KERNEL_NAMES = {1: "warp_nv12_gather_kernel", 2: "warp_nv12_poly_kernel", 3: "warp_nv12_tile_kernel",
+KERNEL_NAMES = {1: "warp_nv12_gather_kernel", 2: "warp_nv12_poly_kernel", 3: "warp_nv12_quad_kernel",
                 4: "warp_nv12_pipe_kernel", 5: "warp_nv12_tex_kernel + warp_nv12_tile_kernel"}
 
 
@@ -461,6 +462,8 @@ def run_ours(args):
                         device=local, variant=args.variant)
     if args.no_split_builder:
         ctx.set_option("split_builder", 0)
+    if args.tile_kernel:
+        ctx.set_option("tile_kernel", args.tile_kernel)
     # this rank's contiguous frame range of the clip, with its rotations
     rots = wl.rotations(n, first=100 + first, total=100 + clip_total)
     src = torch.empty((n,) + ctx.frame_shape("src"), dtype=torch.uint8, device=dev)
@@ -583,7 +586,7 @@ def run_ours(args):
                 "launches_per_step": inner, "frames_per_step": frames_all * inner,
                 "details": {"out": list(wl.out_size), "variant": args.variant, "variant_resolved": ctx.variant,
                             "pieces_128x32": pieces, "frames_this_rank": n, "numa": numa,
-                            "split_builder": not args.no_split_builder},
+                            "split_builder": not args.no_split_builder, "tile_kernel": args.tile_kernel or 2},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": recorded_traffic(wl.name, n),
                              "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,

@@ -252,7 +252,81 @@ def test_small_golden_cv2(V, oracle):
         ctx.close()
 
 
+@pytest.mark.parametrize("name,n", [("C1", 3), ("C3", 2), ("C5", 2)])
+def test_round1_tile_kernel_equals_quadrant_kernel(V, name, n):
+    """The round-1 tile kernel (4 columns per lane, kept for A/B) and the quadrant kernel (the default)
+    sample the same map with the same filter: identical bytes, white noise, rotations incl. a large one."""
+    import torch
+    from video_annotator_b200 import configs
+    w = configs.workload(name)
+    rots = np.stack([rotation_xyz(0.7, -1.1, 0.4), rotation_xyz(9.0, -14.0, 19.0), np.eye(3)][:n])
+    sw, sh = w.src_size
+    out = []
+    for kern in (2, 1):
+        ctx = V.WarpContext(w.input_camera, w.output_camera, out_size=w.out_size, variant=TILED, border=(7, 100, 200))
+        ctx.set_option("tile_kernel", kern)
+        src = torch.empty((n,) + ctx.frame_shape("src"), dtype=torch.uint8, device="cuda")
+        V.synth_nv12(src, sw, sh, n, first_index=5, white_noise=True)
+        rdev = torch.empty(n * 9, dtype=torch.float32, device="cuda")
+        ctx.upload_rotations(rots, rdev)
+        dst = torch.zeros((n,) + ctx.frame_shape("dst"), dtype=torch.uint8, device="cuda")
+        ctx.warp_batch(src, dst, rdev, n)
+        torch.cuda.synchronize()
+        out.append(dst)
+        ctx.close()
+    assert torch.equal(out[0], out[1])
+
+
 # ---- batching, pitches, host path -----------------------------------------------------------------
+@pytest.mark.parametrize("variant", [POLY, TILED, PIPE])
+def test_split_batches_equal_unsplit(V, variant):
+    """Batches of >= 32 frames build the table of all but the first 8 frames on a side stream while the
+    sampler already runs (two sampler launches): same bytes as the single-launch path, on the default
+    stream and on a user stream, call after call (the table is reused)."""
+    import torch
+    from video_annotator_b200 import configs
+    w = configs.workload("C1")
+    n = 37
+    rots = configs.make_rotations(80, 0.8)[20:20 + n]
+    ctx = V.WarpContext(w.input_camera, w.output_camera, out_size=w.out_size, variant=variant)
+    sw, sh = w.src_size
+    src = torch.empty((n,) + ctx.frame_shape("src"), dtype=torch.uint8, device="cuda")
+    V.synth_nv12(src, sw, sh, n, first_index=11, white_noise=True)
+    rdev = torch.empty(n * 9, dtype=torch.float32, device="cuda")
+    ctx.upload_rotations(rots, rdev)
+    ctx.set_option("split_builder", 0)
+    ref = torch.zeros((n,) + ctx.frame_shape("dst"), dtype=torch.uint8, device="cuda")
+    before = ctx.launch_count
+    ctx.warp_batch(src, ref, rdev, n)
+    torch.cuda.synchronize()
+    assert ctx.launch_count == before + 2
+    ctx.set_option("split_builder", 1)
+    side = torch.cuda.Stream()
+    for rep in range(3):
+        out = torch.zeros_like(ref)
+        before = ctx.launch_count
+        if rep == 1:
+            side.wait_stream(torch.cuda.current_stream())
+            ctx.warp_batch(src, out, rdev, n, stream=side.cuda_stream)
+            side.synchronize()
+        else:
+            ctx.warp_batch(src, out, rdev, n)
+            torch.cuda.synchronize()
+        assert ctx.launch_count == before + 4      # two table builders + two sampler launches
+        assert torch.equal(out, ref), rep
+    # reversed rotations through the same context: the second half of the table must be rebuilt, not reused
+    rdev2 = torch.empty_like(rdev)
+    ctx.upload_rotations(rots[::-1].copy(), rdev2)
+    out = torch.zeros_like(ref)
+    ctx.warp_batch(src, out, rdev2, n)
+    ctx.set_option("split_builder", 0)
+    out2 = torch.zeros_like(ref)
+    ctx.warp_batch(src, out2, rdev2, n)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2) and not torch.equal(out, ref)
+    ctx.close()
+
+
 def test_batch_equals_per_frame_and_is_deterministic(V, oracle):
     import torch
     from video_annotator_b200 import configs

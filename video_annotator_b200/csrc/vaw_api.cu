@@ -67,6 +67,8 @@ struct vaw_ctx {
     MapEntry map_cache[4];
     int map_next = 0;
     int tile_cap = 32 << 10;  // chosen at creation from the pieces' source boxes
+    int tile_kernel = 2;      // 2: quadrant kernel (default), 1: the round-1 kernel (A/B only; option "tile_kernel")
+    long long tile_need = 0;  // largest tile a piece of the unrotated geometry needs (bytes)
     // variant TEX: texture objects over the clip, cached per source layout
     struct TexEntry { const void* src = nullptr; int pitch = 0; size_t stride = 0; int frames = 0; vaw::TexSet set{}; int n_groups = 0; };
     static constexpr int kTexCache = 8;
@@ -227,6 +229,7 @@ const vaw::TileMaps& tile_maps(vaw_ctx* ctx, const uint8_t* src, int pitch, size
     e.src = src; e.pitch = pitch; e.stride = stride; e.frames = frames;
     e.maps.enabled = 0;
     e.maps.tile_cap = ctx->tile_cap;
+    e.maps.kernel = ctx->tile_kernel;
     const int rows_total = ctx->p.src_height + ctx->p.src_height / 2;
     EncodeTiledFn enc = encode_tiled();
     const bool ok = enc && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (pitch & 15) == 0 && (stride & 15) == 0 &&
@@ -245,6 +248,11 @@ const vaw::TileMaps& tile_maps(vaw_ctx* ctx, const uint8_t* src, int pitch, size
         const cuuint32_t box32[3] = {box[0], 32, 1};
         r = enc(&e.maps.m32[i], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint8_t*>(src), dims, strides,
                 box32, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return e.maps;
+        const cuuint32_t box4[3] = {box[0], 4, 1};
+        r = enc(&e.maps.m4[i], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint8_t*>(src), dims, strides,
+                box4, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return e.maps;
     }
@@ -501,6 +509,24 @@ int init_host_path_impl(vaw_ctx* ctx)
     return VAW_OK;
 }
 
+// Tile capacity = the shared memory that the largest CTA count still fitting the biggest tile of the
+// unrotated geometry (+6 % for the tilt a few degrees of rotation add) leaves each CTA: the rest of that
+// budget is free head-room for larger rotations.  Returns the CTA count.
+int choose_tile_cap(vaw_ctx* ctx)
+{
+    const int book = vaw::tile_smem_bytes(0, ctx->tile_kernel);
+    const int max_ctas = ctx->tile_kernel == 1 ? 6 : 8;  // register limit of the two kernels (80 / 64 registers)
+    int ctas = max_ctas;
+    while (ctas > 1 && ctx->tile_need * 106 / 100 > vaw::tile_cap_for_ctas(ctas, book)) --ctas;
+    long long cap = vaw::tile_cap_for_ctas(ctas, book);
+    if (cap < vaw::kTileCapMin) cap = vaw::kTileCapMin;
+    if (cap > vaw::kTileCapMax) cap = vaw::kTileCapMax;
+    ctx->tile_cap = (int)cap;
+    ctx->gd.tile_cap = ctx->tile_cap;  // the builder picks the tile pitch of every piece against it
+    for (vaw_ctx::MapEntry& e : ctx->map_cache) e = vaw_ctx::MapEntry{};
+    return ctas;
+}
+
 bool is_pinned(const void* p)
 {
     cudaPointerAttributes a{};
@@ -690,21 +716,12 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
                     const int nb = vaw::tile_need_bytes(rec[i]);
                     if (nb != 0x7fffffff && nb > need) need = nb;
                 }
-                long long cap = (need * 12 / 10 + 1023) & ~1023LL;
-                // 6 CTAs per SM fit when tile + bookkeeping <= 227 KB / 6: do not give that up for the margin
-                const long long six = ((227 << 10) / 6 - vaw::tile_smem_bytes(0) - 1024) & ~1023LL;
-                if (need <= six && cap > six) cap = six;
-                if (cap < vaw::kTileCapMin) cap = vaw::kTileCapMin;
-                if (cap > vaw::kTileCapMax) cap = vaw::kTileCapMax;
-                ctx->tile_cap = (int)cap;
-                ctx->gd.tile_cap = ctx->tile_cap;  // the builder picks the tile pitch of every piece against it
-                // AUTO: one CTA per piece (TILED) keeps six tiles per SM in flight, without look-ahead.  The ring
-                // pipeline (PIPE) allocates exactly what each piece needs: it wins when tiles are too large for
-                // six per SM (C5, 50 KB: 63.0 k against 57.3 k frames/s) and when they are small enough for
-                // the ring to run four or more pieces ahead of its four consumer groups (C2, 16 KB: 137 k
-                // against 131 k); in between (C3, 28 KB, seven per ring) TILED's 24 sampling warps are faster.
-                if (p.variant == VAW_VARIANT_AUTO && ph == vaw::kPieceHMax && need > 0 &&
-                    (need > six || (long long)ctx->tile_cap * 8 <= (vaw::pipe_smem_bytes(0) - (30 << 10))))
+                ctx->tile_need = need;
+                const int ctas = choose_tile_cap(ctx);
+                // AUTO: one CTA per piece (TILED) unless the tiles are so large that fewer than four CTAs fit an
+                // SM; then the ring pipeline (PIPE), which allocates exactly what each piece needs, keeps more
+                // tiles in flight
+                if (p.variant == VAW_VARIANT_AUTO && ph == vaw::kPieceHMax && need > 0 && ctas < 4)
                     ctx->variant = VAW_VARIANT_PIPE;
             }
         }
@@ -752,6 +769,14 @@ int vaw_set_option(vaw_ctx* ctx, const char* name, int value)
     if (!ctx || !name) return VAW_ERR_INVALID;
     if (!std::strcmp(name, "force_exact")) { ctx->g.force_exact = value ? 1 : 0; return VAW_OK; }
     if (!std::strcmp(name, "split_builder")) { ctx->split_builder = value != 0; return VAW_OK; }
+    if (!std::strcmp(name, "tile_kernel")) {  // A/B of the two tile kernels (analysis only)
+        if (value != 1 && value != 2) return fail(ctx, VAW_ERR_INVALID, "tile_kernel is 1 or 2");
+        DeviceGuard dg(ctx->device);
+        VAW_CUDA(ctx, cudaDeviceSynchronize());
+        ctx->tile_kernel = value;
+        choose_tile_cap(ctx);
+        return VAW_OK;
+    }
     if (!std::strcmp(name, "time_kernels")) {
         DeviceGuard dg(ctx->device);
         if (value && !ctx->tev) {

@@ -303,13 +303,13 @@ build_pieces_kernel(const GeomD g, const PieceBasis basis, const float* __restri
         if ((flags & kPiecePoly) && !(flags & kPieceOutside)) {
             const int lx0 = box.x0 & ~15, wb = (box.x1 - lx0 + 16) & ~15;
             const int cbx0 = (2 * box.cx0) & ~15, cwb = (2 * box.cx1 + 2 - cbx0 + 15) & ~15;
-            const int nr8 = (box.y1 - box.y0 + 8) & ~7, cnr8 = (box.cy1 - box.cy0 + 8) & ~7;  // rows, rounded up to whole boxes
+            const int nrows = (box.y1 - box.y0 + 4) & ~3, cnrows = (box.cy1 - box.cy0 + 4) & ~3;  // rows, rounded up to whole 4-row boxes
             const int want = max(wb, cwb);
             const int pl128 = (want + 127) & ~127, pl32 = max(kStageMinPitch, (want + 31) & ~31);
-            const int pl = (pl128 <= kStageMaxPitch && pl128 * (nr8 + cnr8) <= g.tile_cap) ? pl128 : pl32;
-            if (pl <= kStageMaxPitch && nr8 > 0 && cnr8 > 0 && nr8 < 65536 && cnr8 < 65536) {
+            const int pl = (pl128 <= kStageMaxPitch && pl128 * (nrows + cnrows) <= g.tile_cap) ? pl128 : pl32;
+            if (pl <= kStageMaxPitch && nrows > 0 && cnrows > 0 && nrows < 65536 && cnrows < 65536) {
                 st.lx0 = (int16_t)lx0; st.by0 = box.y0; st.cbx0 = (int16_t)cbx0; st.cy0 = box.cy0;
-                st.pl = (uint16_t)pl; st.nr8 = (uint16_t)nr8; st.cnr8 = (uint16_t)cnr8;
+                st.pl = (uint16_t)pl; st.nrows = (uint16_t)nrows; st.cnrows = (uint16_t)cnrows;
             }
         }
         rec.stage = st;

@@ -46,13 +46,14 @@ struct PieceBox {
 
 // How the samplers stage the piece's source box in shared memory (same integer arithmetic for every
 // variant, done once here instead of by every thread of the sampler): tile rows are `pl` bytes apart,
-// start at source byte lx0 / cbx0 (multiples of 16) and row by0 / cy0, and come in whole 8-row boxes.
+// start at source byte lx0 / cbx0 (multiples of 16) and row by0 / cy0, and come in whole 4-row boxes
+// (loaded as 32-row, then 8-row, then 4-row TMA boxes).
 // The pitch is a multiple of 128 bytes (32 banks) when that fits the tile capacity -- the lanes of one
 // LDS then keep distinct banks however many source rows they straddle -- else the tightest multiple of 32.
 struct PieceStage {
     int16_t lx0, by0, cbx0, cy0;
     uint16_t pl;          // 0: the box cannot be staged (wider than the largest tile pitch)
-    uint16_t nr8, cnr8;   // luma / chroma tile rows
+    uint16_t nrows, cnrows;   // luma / chroma tile rows
     uint16_t pad;
 };
 

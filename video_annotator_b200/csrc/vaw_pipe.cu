@@ -122,10 +122,10 @@ __device__ __forceinline__ unsigned plan_tile(int4 raw, int enabled, int& pl, in
     lorg = raw.x;                      // lx0 | by0 << 16
     corg = raw.y;                      // cbx0 | cy0 << 16
     pl = raw.z & 0xffff;
-    const int nr8 = (raw.z >> 16) & 0xffff, cnr8 = raw.w & 0xffff;
-    rows = nr8 | (cnr8 << 16);
-    if (!enabled || pl == 0 || pl * (nr8 + cnr8) > kRingBytes / 2) return 0u;
-    return (unsigned)(pl * (nr8 + cnr8) + 127) & ~127u;
+    const int nrows = (raw.z >> 16) & 0xffff, cnrows = raw.w & 0xffff;
+    rows = nrows | (cnrows << 16);
+    if (!enabled || pl == 0 || pl * (nrows + cnrows) > kRingBytes / 2) return 0u;
+    return (unsigned)(pl * (nrows + cnrows) + 127) & ~127u;
 }
 
 // A piece without a tile (no polynomial certificate, or a box the ring cannot hold): per-pixel
@@ -302,24 +302,26 @@ warp_nv12_pipe_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
             }
             if (lane == 0) {
                 const int pl = head.plmode & 0xffff, mode = head.plmode >> 16;
-                const int nr8 = head.rows & 0xffff, cnr8 = head.rows >> 16;
+                const int nrows = head.rows & 0xffff, cnrows = head.rows >> 16;
                 {
                     // arrive + expected bytes: the record copy and, when staged, the boxes
-                    mbar_expect_tx(fb, (unsigned)sizeof(PieceRec) + (mode == kModeStaged ? (unsigned)(pl * (nr8 + cnr8)) : 0u));
+                    mbar_expect_tx(fb, (unsigned)sizeof(PieceRec) + (mode == kModeStaged ? (unsigned)(pl * (nrows + cnrows)) : 0u));
                     bulk_g2s(smem_u32(slot + 32), table + head.idx, (unsigned)sizeof(PieceRec), fb);
                     if (mode == kModeStaged) {
                         const int lx0 = (int16_t)(head.lorg & 0xffff), by0 = head.lorg >> 16;
                         const int cbx0 = (int16_t)(head.corg & 0xffff), cy0 = head.corg >> 16;
-                        const unsigned l0 = smem_u32(ring + head.tile_off), c0 = l0 + (unsigned)(nr8 * pl);
+                        const unsigned l0 = smem_u32(ring + head.tile_off), c0 = l0 + (unsigned)(nrows * pl);
                         const int mi = (pl - kTileMinPitch) / kTilePitchStep;
-                        const CUtensorMap *map = &maps.m[mi], *map32 = &maps.m32[mi];
+                        const CUtensorMap *map = &maps.m[mi], *map32 = &maps.m32[mi], *map4 = &maps.m4[mi];
                         int r = 0;
-                        for (; r + 32 <= nr8; r += 32) tma_load_3d(l0 + (unsigned)(r * pl), map32, lx0 >> 2, by0 + r, head.frame + b.tma_frame0, fb);
-                        for (; r < nr8; r += 8) tma_load_3d(l0 + (unsigned)(r * pl), map, lx0 >> 2, by0 + r, head.frame + b.tma_frame0, fb);
-                        for (r = 0; r + 32 <= cnr8; r += 32)
+                        for (; r + 32 <= nrows; r += 32) tma_load_3d(l0 + (unsigned)(r * pl), map32, lx0 >> 2, by0 + r, head.frame + b.tma_frame0, fb);
+                        for (; r + 8 <= nrows; r += 8) tma_load_3d(l0 + (unsigned)(r * pl), map, lx0 >> 2, by0 + r, head.frame + b.tma_frame0, fb);
+                        if (r < nrows) tma_load_3d(l0 + (unsigned)(r * pl), map4, lx0 >> 2, by0 + r, head.frame + b.tma_frame0, fb);
+                        for (r = 0; r + 32 <= cnrows; r += 32)
                             tma_load_3d(c0 + (unsigned)(r * pl), map32, cbx0 >> 2, g.src_h + cy0 + r, head.frame + b.tma_frame0, fb);
-                        for (; r < cnr8; r += 8)
+                        for (; r + 8 <= cnrows; r += 8)
                             tma_load_3d(c0 + (unsigned)(r * pl), map, cbx0 >> 2, g.src_h + cy0 + r, head.frame + b.tma_frame0, fb);
+                        if (r < cnrows) tma_load_3d(c0 + (unsigned)(r * pl), map4, cbx0 >> 2, g.src_h + cy0 + r, head.frame + b.tma_frame0, fb);
                     }
                 }
             }
@@ -432,15 +434,15 @@ warp_nv12_pipe_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
             }
             cp.base = rec->base;
             const int pl = head.plmode & 0xffff;
-            const int nr8 = head.rows & 0xffff, cnr8 = head.rows >> 16;
+            const int nrows = head.rows & 0xffff, cnrows = head.rows >> 16;
             const int lx0 = (int16_t)(head.lorg & 0xffff), by0 = head.lorg >> 16;
             const int cbx0 = (int16_t)(head.corg & 0xffff), cy0 = head.corg >> 16;
             uint8_t* ltile = ring + head.tile_off;
-            uint8_t* ctile = ltile + nr8 * pl;
+            uint8_t* ctile = ltile + nrows * pl;
             if (!(flags & kPieceInterior)) {  // straddles the frame border: paint the outside cells
                 const unsigned by_ = g.border & 255u, bu = (g.border >> 8) & 255u, bv = (g.border >> 16) & 255u;
-                fill_border(ltile, pl, nr8, by0, g.src_h, lx0, g.src_w, by_ * 0x01010101u, gtid, 32 * kGroupWarps);
-                fill_border(ctile, pl, cnr8, cy0, g.src_h >> 1, cbx0, g.src_w, (bu | (bv << 8)) * 0x00010001u,
+                fill_border(ltile, pl, nrows, by0, g.src_h, lx0, g.src_w, by_ * 0x01010101u, gtid, 32 * kGroupWarps);
+                fill_border(ctile, pl, cnrows, cy0, g.src_h >> 1, cbx0, g.src_w, (bu | (bv << 8)) * 0x00010001u,
                             gtid, 32 * kGroupWarps);
                 wrote_tile = true;
             }
@@ -456,8 +458,8 @@ warp_nv12_pipe_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
                 const unsigned lconst = smem_u32(ltile) - (unsigned)by0 * upl - (unsigned)lx0 - kMagicShift * upl - kMagicShift;
                 const unsigned cconst = ((smem_u32(ctile) - (unsigned)cy0 * upl - (unsigned)cbx0 - kMagicShift * upl) >> 1) - kMagicShift;
                 const bool in_a = u_lo + 2 * lane < g.out_w, in_b = u_lo + 64 + 2 * lane < g.out_w;
-                const TileBounds tb = {smem_u32(ltile), smem_u32(ltile) + (unsigned)(nr8 * pl), smem_u32(ctile),
-                                       smem_u32(ctile) + (unsigned)(cnr8 * pl)};
+                const TileBounds tb = {smem_u32(ltile), smem_u32(ltile) + (unsigned)(nrows * pl), smem_u32(ctile),
+                                       smem_u32(ctile) + (unsigned)(cnrows * pl)};
                 if (even_ok && u_lo + kPieceW <= g.out_w) rows_tile<false>(g, cp, lconst, cconst, upl, dv0, my_rows, o, in_a, in_b, tb);
                 else rows_tile<true>(g, cp, lconst, cconst, upl, dv0, my_rows, o, in_a, in_b, tb);
             }

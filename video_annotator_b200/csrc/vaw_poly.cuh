@@ -126,11 +126,13 @@ __device__ __forceinline__ unsigned blend_uv(unsigned t00, unsigned t01, unsigne
     const unsigned wy = 32u - ay;
     const unsigned s00 = __byte_perm(t00, 0, 0x4140), s01 = __byte_perm(t01, 0, 0x4140);
     const unsigned s10 = __byte_perm(t10, 0, 0x4140), s11 = __byte_perm(t11, 0, 0x4140);
-    const unsigned left = s00 * wy + s10 * ay, right = s01 * wy + s11 * ay;  // <= 8160 per half
+    // the rounding constant rides along as +16 in every 16-bit half: the horizontal weights sum to 32, so
+    // the dot products below come out as sum + 512 without a register for the accumulator (<= 8176 per half)
+    const unsigned left = s00 * wy + (s10 * ay + 0x00100010u), right = s01 * wy + (s11 * ay + 0x00100010u);
     const unsigned wpair = 32u + 255u * ax;                                   // (32 - ax) | ax << 8
-    const unsigned u = __dp2a_lo(__byte_perm(left, right, 0x5410), wpair, 512u) >> 10;
-    const unsigned v = __dp2a_lo(__byte_perm(left, right, 0x7632), wpair, 512u) >> 10;
-    return u | (v << 8);
+    const unsigned u = __dp2a_lo(__byte_perm(left, right, 0x5410), wpair, 0u) >> 10;
+    const unsigned v = __dp2a_lo(__byte_perm(left, right, 0x7632), wpair, 0u) >> 2;
+    return u | (v & 0xff00u);
 }
 
 // ---- samplers without border tests, taps from global memory ---------------------------------

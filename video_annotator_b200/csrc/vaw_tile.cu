@@ -140,8 +140,8 @@ warp_nv12_tile_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
     // ---- the tile of this piece's source rectangle, as the builder laid it out (block-uniform) ------
     const int lx0 = (int16_t)(raw.x & 0xffff), by0 = raw.x >> 16;
     const int cbx0 = (int16_t)(raw.y & 0xffff), cy0 = raw.y >> 16;
-    const int pl = raw.z & 0xffff, nr8 = (raw.z >> 16) & 0xffff, cnr8 = raw.w & 0xffff;
-    const bool fits = maps.enabled && pl != 0 && pl * (nr8 + cnr8) <= maps.tile_cap;
+    const int pl = raw.z & 0xffff, nrows = (raw.z >> 16) & 0xffff, cnrows = raw.w & 0xffff;
+    const bool fits = maps.enabled && pl != 0 && pl * (nrows + cnrows) <= maps.tile_cap;
 
     if (!fits) {  // gather from global memory like variant POLY (each warp collapses for itself)
         if (my_rows <= 0) return;
@@ -162,24 +162,26 @@ warp_nv12_tile_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
     }
 
     uint8_t* ltile = smem + kTileOffset;
-    uint8_t* ctile = ltile + nr8 * pl;
+    uint8_t* ctile = ltile + nrows * pl;
     float4* coefs = reinterpret_cast<float4*>(smem);
     const unsigned mbar = smem_u32(smem + kCoefBytes);
 
     // ---- thread 0: arm the barrier, launch the tile loads ---------------------------------------
     if (tid == 0) {
         mbar_init(mbar, 1);
-        mbar_expect_tx(mbar, (unsigned)(pl * (nr8 + cnr8)));
+        mbar_expect_tx(mbar, (unsigned)(pl * (nrows + cnrows)));
         const int mi = (pl - kTileMinPitch) / kTilePitchStep;
-        const CUtensorMap *map = &maps.m[mi], *map32 = &maps.m32[mi];
+        const CUtensorMap *map = &maps.m[mi], *map32 = &maps.m32[mi], *map4 = &maps.m4[mi];
         const unsigned l0 = smem_u32(ltile), c0 = smem_u32(ctile);
         int k = 0;
-        for (; k + 32 <= nr8; k += 32) tma_load_3d(l0 + (unsigned)(k * pl), map32, lx0 >> 2, by0 + k, frame + b.tma_frame0, mbar);
-        for (; k < nr8; k += 8) tma_load_3d(l0 + (unsigned)(k * pl), map, lx0 >> 2, by0 + k, frame + b.tma_frame0, mbar);
-        for (k = 0; k + 32 <= cnr8; k += 32)
+        for (; k + 32 <= nrows; k += 32) tma_load_3d(l0 + (unsigned)(k * pl), map32, lx0 >> 2, by0 + k, frame + b.tma_frame0, mbar);
+        for (; k + 8 <= nrows; k += 8) tma_load_3d(l0 + (unsigned)(k * pl), map, lx0 >> 2, by0 + k, frame + b.tma_frame0, mbar);
+        if (k < nrows) tma_load_3d(l0 + (unsigned)(k * pl), map4, lx0 >> 2, by0 + k, frame + b.tma_frame0, mbar);
+        for (k = 0; k + 32 <= cnrows; k += 32)
             tma_load_3d(c0 + (unsigned)(k * pl), map32, cbx0 >> 2, g.src_h + cy0 + k, frame + b.tma_frame0, mbar);
-        for (; k < cnr8; k += 8)
+        for (; k + 8 <= cnrows; k += 8)
             tma_load_3d(c0 + (unsigned)(k * pl), map, cbx0 >> 2, g.src_h + cy0 + k, frame + b.tma_frame0, mbar);
+        if (k < cnrows) tma_load_3d(c0 + (unsigned)(k * pl), map4, cbx0 >> 2, g.src_h + cy0 + k, frame + b.tma_frame0, mbar);
     }
 
     // ---- collapse the polynomial: warp w does column j = w for every lane -------------------------
@@ -208,8 +210,8 @@ warp_nv12_tile_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
 
     if (!(flags & kPieceInterior)) {  // straddles the frame border: paint the outside cells
         const unsigned by_ = g.border & 255u, bu = (g.border >> 8) & 255u, bv = (g.border >> 16) & 255u;
-        fill_border(ltile, pl, nr8, by0, g.src_h, lx0, g.src_w, by_ * 0x01010101u, tid, 32 * kWarps);
-        fill_border(ctile, pl, cnr8, cy0, g.src_h >> 1, cbx0, g.src_w, (bu | (bv << 8)) * 0x00010001u, tid, 32 * kWarps);
+        fill_border(ltile, pl, nrows, by0, g.src_h, lx0, g.src_w, by_ * 0x01010101u, tid, 32 * kWarps);
+        fill_border(ctile, pl, cnrows, cy0, g.src_h >> 1, cbx0, g.src_w, (bu | (bv << 8)) * 0x00010001u, tid, 32 * kWarps);
         __syncthreads();
     }
 
@@ -224,10 +226,281 @@ warp_nv12_tile_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
     const bool in_a = u_lo + 2 * lane < g.out_w, in_b = u_lo + 64 + 2 * lane < g.out_w;  // widths are even
     const bool pair_ok = ((reinterpret_cast<uintptr_t>(f.dst) | (uintptr_t)g.dst_pitch) & 1) == 0 &&
                          u_lo + kPieceW <= g.out_w;
-    const TileBounds tb = {smem_u32(ltile), smem_u32(ltile) + (unsigned)(nr8 * pl), smem_u32(ctile),
-                           smem_u32(ctile) + (unsigned)(cnr8 * pl)};
+    const TileBounds tb = {smem_u32(ltile), smem_u32(ltile) + (unsigned)(nrows * pl), smem_u32(ctile),
+                           smem_u32(ctile) + (unsigned)(cnrows * pl)};
     if (pair_ok) rows_tile<false>(g, cp, lconst, cconst, upl, dv0, my_rows, o, in_a, in_b, tb);
     else rows_tile<true>(g, cp, lconst, cconst, upl, dv0, my_rows, o, in_a, in_b, tb);
+}
+
+// ================================================================================================
+// Quadrant kernel (the default): the same piece, tile and arithmetic, re-cut for occupancy.
+//
+// What round 1's profile said (profiles/r01_ncu_summary.txt): the sampler is issue- and latency-bound,
+// issue slots 71 % busy with 24 resident warps per SM, and both limits on the warp count -- 80
+// registers and 37 KB of shared memory per CTA -- came from the lane mapping: four columns per lane
+// = 32 registers of column polynomials, and a 4 KB exchange buffer + barrier to share the collapse
+// between the warps.  Here warp w owns a QUADRANT of the piece (64 columns x PH/2 rows), lane l the
+// two adjacent columns 2l, 2l+1 of it:
+//   - 16 registers of column polynomials -> the kernel fits 64 registers, 8 CTAs (32 warps) per SM;
+//   - each warp collapses its own two columns (40 FFMA2, coefficients straight from L1): no exchange
+//     buffer, no barrier between the collapse and the sampling, shared memory = 128 bytes + tile;
+//   - tile rows come in multiples of 4 (32/8/4-row TMA boxes), so the C3 tiles fit 8 per SM;
+//   - per row pair a lane makes 2 x 2 luma samples and the one chroma sample of that quad; a warp
+//     store writes 64 contiguous bytes, the LDS of a warp stay within one 128-byte window per row
+//     exactly as with the round-1 pair mapping (2 columns per lane).
+constexpr int kQuadCtas = 8;          // resident CTAs per SM the kernel is compiled for (64 registers)
+constexpr int kQuadTileOffset = 128;  // [mbarrier | tile (TMA: 128-byte aligned)]
+
+struct ColPoly2 {
+    float2 a[2][kNv];  // [column][power of t]
+    float2 base;
+};
+
+// Collapse the piece polynomial onto the lane's two columns: per power of t one Horner chain in s per
+// column -- the operation order of collapse_column(), so the coefficients equal derive()'s bit for bit
+// (vaw_dump_coords runs derive()).  Coefficients are read per power of t (6 x 8-byte broadcast loads
+// from L1) so that at most 12 of the record's 48 coefficient registers are live at a time.
+__device__ __forceinline__ void derive2(const PieceRec* __restrict__ rec, int col0, ColPoly2& cp)
+{
+    const float2* c2 = reinterpret_cast<const float2*>(rec);  // c[i][k] at index i * kNv + k
+    const float2 s0 = pair(((float)col0 - 63.5f) * 0.015625f), s1 = pair(((float)(col0 + 1) - 63.5f) * 0.015625f);
+#pragma unroll
+    for (int k = 0; k < kNv; ++k) {
+        float2 ci[kNu];
+#pragma unroll
+        for (int i = 0; i < kNu; ++i) ci[i] = __ldg(c2 + i * kNv + k);
+        float2 a0 = ci[kDegU], a1 = ci[kDegU];
+#pragma unroll
+        for (int i = kDegU - 1; i >= 0; --i) {
+            a0 = __ffma2_rn(a0, s0, ci[i]);
+            a1 = __ffma2_rn(a1, s1, ci[i]);
+        }
+        cp.a[0][k] = a0;
+        cp.a[1][k] = a1;
+    }
+}
+
+__device__ __forceinline__ float2 col_coord(const float2 (&a)[kNv], float2 base, float2 tt)
+{
+    float2 p = __ffma2_rn(a[3], tt, a[2]);
+    p = __ffma2_rn(p, tt, a[1]);
+    p = __ffma2_rn(p, tt, a[0]);
+    return __fadd2_rn(base, p);  // the map value: rounded once to fp32
+}
+
+// base + index * pitch as ONE 64-bit multiply-add (IMAD.WIDE): the compiler's strength-reduced running
+// pointers cost four instructions per store here (add, add-with-carry and two moves to re-pair registers).
+__device__ __forceinline__ unsigned long long row_ptr(unsigned long long base, unsigned index, unsigned pitch)
+{
+    unsigned long long a;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(a) : "r"(index), "r"(pitch), "l"(base));
+    return a;
+}
+__device__ __forceinline__ void stg_u16(unsigned long long gaddr, unsigned v)
+{
+    asm volatile("st.global.u16 [%0], %1;" ::"l"(gaddr), "h"((unsigned short)v) : "memory");
+}
+__device__ __forceinline__ void stg_u8(unsigned long long gaddr, unsigned v)
+{
+    asm volatile("st.global.u8 [%0], %1;" ::"l"(gaddr), "h"((unsigned short)(v & 255u)) : "memory");
+}
+// A zero the compiler cannot see through: a loop counter started from it stays in a vector register, so
+// that counter * pitch + pointer is one IMAD.WIDE per store instead of uniform-datapath arithmetic plus
+// a two-instruction 64-bit vector add.
+__device__ __forceinline__ unsigned opaque_zero()
+{
+    unsigned z;
+    asm volatile("mov.u32 %0, 0;" : "=r"(z));
+    return z;
+}
+
+// nrows (even) rows starting at piece row dv0 for the lane's two columns; taps from the staged tile.
+// py / pc: the lane's column pair in the first luma row / chroma row of the band.
+template <bool kRagged>
+__device__ __forceinline__ void rows_quad(const Geom& g, const ColPoly2& cp, unsigned lconst, unsigned cconst, unsigned pl,
+                                          int dv0, int nrows, uint8_t* __restrict__ py, uint8_t* __restrict__ pc,
+                                          bool inside, const TileBounds& tb)
+{
+    float t = row_t(g, dv0);
+    const float dt = g.t_scale, dt2 = __fadd_rn(g.t_scale, g.t_scale);  // stepping the dyadic t is exact
+    const unsigned dpitch = (unsigned)g.dst_pitch;
+    const unsigned long long gy0 = (unsigned long long)__cvta_generic_to_global(py), gy1 = gy0 + dpitch;
+    const unsigned long long gc = (unsigned long long)__cvta_generic_to_global(pc);
+#pragma unroll 1
+    for (unsigned j2 = opaque_zero(); j2 < (unsigned)nrows; j2 += 2) {  // rows j2, j2 + 1 of the band
+        const float2 t0 = pair(t), t1 = pair(__fadd_rn(t, dt));
+        t = __fadd_rn(t, dt2);
+        const float2 m00 = col_coord(cp.a[0], cp.base, t0), m01 = col_coord(cp.a[1], cp.base, t0);
+        const float2 m10 = col_coord(cp.a[0], cp.base, t1), m11 = col_coord(cp.a[1], cp.base, t1);
+        const unsigned y00 = (unsigned)luma_tile(lconst, pl, m00, tb) >> 10, y01 = (unsigned)luma_tile(lconst, pl, m01, tb) >> 10;
+        const unsigned y10 = (unsigned)luma_tile(lconst, pl, m10, tb) >> 10, y11 = (unsigned)luma_tile(lconst, pl, m11, tb) >> 10;
+        const unsigned c = chroma_tile(cconst, pl, chroma_z(m00, m01, m10, m11), tb);  // U | V << 8
+        const unsigned long long r0 = row_ptr(gy0, j2, dpitch), r1 = row_ptr(gy1, j2, dpitch);
+        const unsigned long long rc = row_ptr(gc, j2 >> 1, dpitch);
+        if (!kRagged) {
+            stg_u16(r0, y00 | (y01 << 8));
+            stg_u16(r1, y10 | (y11 << 8));
+            stg_u16(rc, c);
+        } else if (inside) {
+            stg_u8(r0, y00); stg_u8(r0 + 1, y01);
+            stg_u8(r1, y10); stg_u8(r1 + 1, y11);
+            stg_u8(rc, c); stg_u8(rc + 1, c >> 8);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(32 * kWarps, kQuadCtas)
+warp_nv12_quad_kernel(const Geom g, const FrameBatch b, const PieceRec* __restrict__ table,
+                      const __grid_constant__ TileMaps maps)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int lane = threadIdx.x, w = threadIdx.y, tid = w * 32 + lane;
+    const int px = blockIdx.x, py = blockIdx.y, frame = blockIdx.z;
+    const int ph = g.piece_h;
+    const int npx = (int)gridDim.x, npy = (int)gridDim.y;
+    const PieceRec* rec = table + ((size_t)frame * npy + py) * npx + px;
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(rec));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(rec) + 128));
+    const float4 rec_tail = __ldg(reinterpret_cast<const float4*>(rec) + 12);  // base.x, base.y, flags, pad
+    const int4 raw = __ldg(reinterpret_cast<const int4*>(rec) + 14);          // PieceStage
+    const unsigned mbar = smem_u32(smem);
+    if (tid == 0) mbar_init(mbar, 1);
+    __syncthreads();  // the barrier is initialised for every warp (nothing has been waited for yet)
+
+    const unsigned flags = __float_as_uint(rec_tail.z);
+    const int u_lo = px * kPieceW, v_base = py * ph;
+    const int rows = min(ph, g.out_h - v_base);  // even for NV12
+    uint8_t* const dst = b.dst + (size_t)frame * b.dst_frame_stride;
+
+    if (flags & kPieceOutside) {  // pure border: 128 threads fill the piece
+        const unsigned yw = (g.border & 255u) * 0x01010101u;
+        const unsigned cw = ((g.border >> 8) & 0xffffu) * 0x00010001u;
+        if (((reinterpret_cast<uintptr_t>(dst) | (uintptr_t)g.dst_pitch) & 15) == 0 && u_lo + kPieceW <= g.out_w) {
+            // 16 bytes per lane: 8 lanes per row, 16 rows per pass of the CTA
+            const int sub = tid >> 3, col = (tid & 7) * 16;
+            const uint4 y4 = make_uint4(yw, yw, yw, yw), c4 = make_uint4(cw, cw, cw, cw);
+            uint8_t* yrow = dst + (size_t)(v_base + sub) * g.dst_pitch + u_lo + col;
+            for (int r = sub; r < rows; r += 16, yrow += 16 * (size_t)g.dst_pitch) *reinterpret_cast<uint4*>(yrow) = y4;
+            uint8_t* crow = dst + (size_t)(g.out_h + (v_base >> 1) + sub) * g.dst_pitch + u_lo + col;
+            if (sub < rows / 2) *reinterpret_cast<uint4*>(crow) = c4;
+            return;
+        }
+        // ragged / unaligned: 4 columns per lane, rows split over the warps like the round-1 kernel
+        const int u0 = u_lo + 4 * lane, valid = g.out_w - u0, rpw = ph / kWarps;
+        const int dv0 = w * rpw, my = max(0, min(rpw, rows - dv0));
+        uint8_t* y0 = dst + (size_t)(v_base + dv0) * g.dst_pitch + u0;
+        uint8_t* cc = dst + (size_t)(g.out_h + ((v_base + dv0) >> 1)) * g.dst_pitch + u0;
+        if (valid > 0)
+            for (int dv = 0; dv < my; dv += 2) {
+                store_word<true>(y0, yw, valid);
+                store_word<true>(y0 + g.dst_pitch, yw, valid);
+                store_word<true>(cc, cw, valid);
+                y0 += 2 * (size_t)g.dst_pitch; cc += g.dst_pitch;
+            }
+        return;
+    }
+
+    // ---- the tile of this piece's source rectangle, as the builder laid it out (block-uniform) ------
+    const int lx0 = (int16_t)(raw.x & 0xffff), by0 = raw.x >> 16;
+    const int cbx0 = (int16_t)(raw.y & 0xffff), cy0 = raw.y >> 16;
+    const int pl = raw.z & 0xffff, nrows = (raw.z >> 16) & 0xffff, cnrows = raw.w & 0xffff;
+    const bool staged = (flags & kPiecePoly) && maps.enabled && pl != 0 && pl * (nrows + cnrows) <= maps.tile_cap;
+
+    if (!staged) {
+        // pieces without a polynomial certificate or whose box does not fit the tile: the gather paths of
+        // variant POLY with the 4-columns-per-lane mapping (warp w walks rows [w PH/4, (w+1) PH/4))
+        const int rpw = ph / kWarps, dv0 = w * rpw, my_rows = max(0, min(rpw, rows - dv0));
+        const int u0 = u_lo + 4 * lane, valid = g.out_w - u0;
+        if (my_rows <= 0) return;
+        PlaneRefs f;
+        f.y = b.src + (size_t)frame * b.src_frame_stride;
+        f.uv = f.y + (size_t)g.src_pitch * g.src_h;
+        f.dst = dst;
+        if (!(flags & kPiecePoly)) {  // op-for-op per pixel
+            const Rot R = load_rot(b, frame);
+            for (int dv = dv0; dv < dv0 + my_rows; dv += 2) {
+                float2 m[2][4];
+                exact_rows(g, R, u_lo, u0, v_base + dv, m);
+                sample_rows_checked(g, f, u0, v_base + dv, m);
+            }
+            return;
+        }
+        ColPoly cp;
+        derive(rec, lane, cp);
+        if (flags & kPieceInterior) {
+            RowPtrs o;
+            o.y0 = dst + (size_t)(v_base + dv0) * g.dst_pitch + u0;
+            o.y1 = o.y0 + g.dst_pitch;
+            o.c = dst + (size_t)(g.out_h + ((v_base + dv0) >> 1)) * g.dst_pitch + u0;
+            o.step_y = 2 * (size_t)g.dst_pitch;
+            o.step_c = (size_t)g.dst_pitch;
+            const bool word_ok = ((reinterpret_cast<uintptr_t>(dst) | (uintptr_t)g.dst_pitch) & 3) == 0 &&
+                                 u_lo + kPieceW <= g.out_w;
+            if (word_ok) band_gmem<false>(g, cp, f, dv0, my_rows, o, valid);
+            else band_gmem<true>(g, cp, f, dv0, my_rows, o, valid);
+        } else {
+            for (int dv = dv0; dv < dv0 + my_rows; dv += 2) {
+                float2 m[2][4];
+                row_coords(cp, row_t(g, dv), m[0]);
+                row_coords(cp, row_t(g, dv + 1), m[1]);
+                sample_rows_checked(g, f, u0, v_base + dv, m);
+            }
+        }
+        return;
+    }
+
+    uint8_t* ltile = smem + kQuadTileOffset;
+    uint8_t* ctile = ltile + nrows * pl;
+
+    // ---- thread 0: launch the tile loads ------------------------------------------------------------
+    if (tid == 0) {
+        mbar_expect_tx(mbar, (unsigned)(pl * (nrows + cnrows)));
+        const int mi = (pl - kTileMinPitch) / kTilePitchStep;
+        const CUtensorMap *map = &maps.m[mi], *map32 = &maps.m32[mi], *map4 = &maps.m4[mi];
+        const unsigned l0 = smem_u32(ltile), c0 = smem_u32(ctile);
+        const int z = frame + b.tma_frame0;
+        int k = 0;
+        for (; k + 32 <= nrows; k += 32) tma_load_3d(l0 + (unsigned)(k * pl), map32, lx0 >> 2, by0 + k, z, mbar);
+        for (; k + 8 <= nrows; k += 8) tma_load_3d(l0 + (unsigned)(k * pl), map, lx0 >> 2, by0 + k, z, mbar);
+        if (k < nrows) tma_load_3d(l0 + (unsigned)(k * pl), map4, lx0 >> 2, by0 + k, z, mbar);
+        for (k = 0; k + 32 <= cnrows; k += 32) tma_load_3d(c0 + (unsigned)(k * pl), map32, cbx0 >> 2, g.src_h + cy0 + k, z, mbar);
+        for (; k + 8 <= cnrows; k += 8) tma_load_3d(c0 + (unsigned)(k * pl), map, cbx0 >> 2, g.src_h + cy0 + k, z, mbar);
+        if (k < cnrows) tma_load_3d(c0 + (unsigned)(k * pl), map4, cbx0 >> 2, g.src_h + cy0 + k, z, mbar);
+    }
+
+    // ---- this warp's quadrant; every lane collapses the polynomial onto its two columns ---------------
+    const int wx = w & 1, wy = w >> 1, hrows = ph >> 1;
+    const int col0 = 64 * wx + 2 * lane;  // within the piece
+    ColPoly2 cp;
+    derive2(rec, col0, cp);
+    cp.base = make_float2(rec_tail.x, rec_tail.y);
+
+    mbar_wait(mbar, 0);  // the tile has landed
+
+    if (!(flags & kPieceInterior)) {  // straddles the frame border: paint the outside cells
+        const unsigned by_ = g.border & 255u, bu = (g.border >> 8) & 255u, bv = (g.border >> 16) & 255u;
+        fill_border(ltile, pl, nrows, by0, g.src_h, lx0, g.src_w, by_ * 0x01010101u, tid, 32 * kWarps);
+        fill_border(ctile, pl, cnrows, cy0, g.src_h >> 1, cbx0, g.src_w, (bu | (bv << 8)) * 0x00010001u, tid, 32 * kWarps);
+        __syncthreads();
+    }
+
+    const int dv0 = wy * hrows;
+    const int my_rows = max(0, min(hrows, rows - dv0));
+    if (my_rows <= 0) return;
+    // tap address = (iy - y0) * pl + (ix - x0) + tile, with the >>5 bias of the magic constant folded in
+    const unsigned upl = (unsigned)pl;
+    const unsigned lconst = smem_u32(ltile) - (unsigned)by0 * upl - (unsigned)lx0 - kMagicShift * upl - kMagicShift;
+    const unsigned cconst = ((smem_u32(ctile) - (unsigned)cy0 * upl - (unsigned)cbx0 - kMagicShift * upl) >> 1) - kMagicShift;
+    const int u0 = u_lo + col0;
+    const bool inside = u0 < g.out_w;  // widths are even: the pair is inside or outside together
+    const bool pair_ok = ((reinterpret_cast<uintptr_t>(dst) | (uintptr_t)g.dst_pitch) & 1) == 0 &&
+                         u_lo + kPieceW <= g.out_w;
+    const TileBounds tb = {smem_u32(ltile), smem_u32(ltile) + (unsigned)(nrows * pl), smem_u32(ctile),
+                           smem_u32(ctile) + (unsigned)(cnrows * pl)};
+    uint8_t* const oy = dst + (size_t)(v_base + dv0) * g.dst_pitch + u0;
+    uint8_t* const oc = dst + (size_t)(g.out_h + ((v_base + dv0) >> 1)) * g.dst_pitch + u0;
+    if (pair_ok) rows_quad<false>(g, cp, lconst, cconst, upl, dv0, my_rows, oy, oc, inside, tb);
+    else rows_quad<true>(g, cp, lconst, cconst, upl, dv0, my_rows, oy, oc, inside, tb);
 }
 
 long long tile_oob_count()
@@ -241,7 +514,7 @@ long long tile_oob_count()
 #endif
 }
 
-int tile_smem_bytes(int tile_cap) { return kTileOffset + tile_cap; }
+int tile_smem_bytes(int tile_cap, int kernel) { return (kernel == 1 ? kTileOffset : kQuadTileOffset) + tile_cap; }
 
 // Host mirror of the kernel's tile sizing (same integer arithmetic).
 int tile_need_bytes(const PieceRec& rec)
@@ -250,10 +523,10 @@ int tile_need_bytes(const PieceRec& rec)
     const PieceBox& b = rec.box;
     const int lx0 = b.x0 & ~15, wb = (b.x1 - lx0 + 16) & ~15;
     const int cbx0 = (2 * b.cx0) & ~15, cwb = (2 * b.cx1 + 2 - cbx0 + 15) & ~15;
-    const int nr8 = (b.y1 - b.y0 + 8) & ~7, cnr8 = (b.cy1 - b.cy0 + 8) & ~7;
+    const int nrows = (b.y1 - b.y0 + 4) & ~3, cnrows = (b.cy1 - b.cy0 + 4) & ~3;
     const int pl = std::max(kTileMinPitch, (std::max(wb, cwb) + 31) & ~31);
-    if (pl > kTileMaxPitch || nr8 <= 0 || cnr8 <= 0) return 0x7fffffff;
-    return pl * (nr8 + cnr8);
+    if (pl > kTileMaxPitch || nrows <= 0 || cnrows <= 0) return 0x7fffffff;
+    return pl * (nrows + cnrows);
 }
 
 cudaError_t launch_warp_nv12_tile(const Geom& g, const FrameBatch& b, const PieceRec* table, const TileMaps& maps,
@@ -267,13 +540,21 @@ cudaError_t launch_warp_nv12_tile(const Geom& g, const FrameBatch& b, const Piec
     const bool tracked = dev >= 0 && dev < 64;
     if (!tracked || !configured[dev].load(std::memory_order_acquire)) {
         cudaError_t e = cudaFuncSetAttribute(warp_nv12_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             tile_smem_bytes(kTileCapMax));
+                                             tile_smem_bytes(kTileCapMax, 1));
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(warp_nv12_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     tile_smem_bytes(kTileCapMax, 2));
+        if (e == cudaSuccess)  // all of the SM's shared memory for tiles: the taps never go through L1
+            e = cudaFuncSetAttribute(warp_nv12_quad_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         if (e != cudaSuccess) return e;
         if (tracked) configured[dev].store(true, std::memory_order_release);
     }
     dim3 block(32, kWarps);
     dim3 grid(pieces_x(g.out_w), pieces_y(g.out_h, g.piece_h), b.n_frames);
-    warp_nv12_tile_kernel<<<grid, block, tile_smem_bytes(maps.tile_cap), st>>>(g, b, table, maps);
+    if (maps.kernel == 1)
+        warp_nv12_tile_kernel<<<grid, block, tile_smem_bytes(maps.tile_cap, 1), st>>>(g, b, table, maps);
+    else
+        warp_nv12_quad_kernel<<<grid, block, tile_smem_bytes(maps.tile_cap, 2), st>>>(g, b, table, maps);
     return cudaGetLastError();
 }
 
