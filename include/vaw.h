@@ -194,6 +194,13 @@ int vaw_warp_batch(vaw_ctx *ctx, const uint8_t *src, int src_pitch, size_t src_f
                    uint8_t *dst, int dst_pitch, size_t dst_frame_stride,
                    const float *rotations, int n_frames, void *stream);
 
+/* Optional hint for callers whose source frames live in ONE slab of n_slots equally spaced frames
+ * (a frame pool / decoder surface ring; the C++ shim's FramePool): vaw_warp / vaw_warp_batch calls
+ * whose source lies inside the slab then share the slab's TMA tensor maps (encoded once) instead of
+ * encoding maps per distinct source pointer.  base = NULL unbinds.  Purely a launch-cost matter:
+ * results are identical with and without it. */
+int vaw_bind_clip(vaw_ctx *ctx, const uint8_t *base, int pitch, size_t frame_stride, int n_slots);
+
 /* double[9*n] (host) -> float[9*n] (device), the (cl_float) cast of FrameSourceWarp.cpp:291-299.
  * Synchronous with respect to the host buffer. */
 int vaw_upload_rotations(vaw_ctx *ctx, const double *rotations_host, int n_frames,
@@ -272,9 +279,14 @@ int vaw_synth_nv12(uint8_t *dst, int width, int height, int pitch, size_t frame_
  * __fdiv_rn / __fsqrt_rn / the k = atan(r)/r step on random operands in the certified
  * ranges; mismatches[4] = {rcp, div, sqrt, k}. */
 int vaw_set_option(vaw_ctx *ctx, const char *name, int value);
+/* Other options: "split_builder" (default 1): batches of >= 32 frames build the piece table of all but the
+ * first 8 frames on a high-priority side stream while the sampler already works on those 8, so that the
+ * builder is off the critical path (two sampler launches per batch; same bytes).  "tile_kernel" 1 | 2:
+ * A/B of the round-1 tile kernel against the quadrant kernel (analysis only; identical bytes). */
 /* vaw_set_option(ctx, "time_kernels", 1) makes every NV12 launch record CUDA events on its
  * stream around the piece-table builder and the warp kernel (a ring of the last 512 launches);
- * vaw_kernel_times returns the most recent launches' durations in milliseconds, oldest first
+ * (builder_ms covers the head frames' table, the rest of the table is built on a side stream under the
+ * sampler, see "split_builder").  vaw_kernel_times returns the most recent launches' durations in milliseconds, oldest first
  * (it waits for them).  This is what bench.py's roofline line is computed from. */
 int vaw_kernel_times(vaw_ctx *ctx, int max_launches, float *builder_ms, float *warp_ms, int *n_out);
 /* The same launches' warp time split into the texture kernel (variant TEX, else ~0) and the tile kernel. */

@@ -3,6 +3,7 @@
 // Behaviours checked are the reference's (opencv/FrameSourceWarp.cpp:397-480).
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/vaw.h"
@@ -137,6 +138,100 @@ int main()
         try { RecordingWarp bad(std::make_shared<FakeSource>(6), wrong, out, 1, INTER_LINEAR, nullptr, false); }
         catch (int err) { threw = err == VAW_ERR_INVALID; }
         CHECK(threw);                                   // the input camera must describe the frames of the source
+    }
+    {  // batched look-ahead warping: same frames, same order, same rotations as one warp per call
+        const int n = 41, radius = 4;
+        std::vector<Mat33> ref_rot;
+        std::vector<long> ref_idx;
+        for (int batch : {1, 5, 64}) {
+            auto src = std::make_shared<FakeSource>(n);
+            RecordingWarp w(src, GOPRO_H4B_WIDE169_MEASURED, 1, false, 1, radius, INTER_LINEAR,
+                            std::make_shared<SpinSource>(0.7), false);
+            w.set_warp_batch(batch);
+            std::vector<long> out_idx;
+            if (batch == 5) {  // latency: batch - 1 more upstream pulls before the first frame comes out
+                out_idx.push_back(w.pull_frame()->index);
+                CHECK(src->pulls == radius + 2 + (batch - 1));
+            }
+            try { while (true) out_idx.push_back(w.pull_frame()->index); } catch (int err) { CHECK(err == EOF); }
+            CHECK((int)out_idx.size() == n - 1);
+            for (size_t i = 0; i < out_idx.size(); ++i) CHECK(out_idx[i] == (long)i + 1);
+            if (batch == 1) { ref_rot = w.rotations; ref_idx = w.indices; continue; }
+            CHECK(w.indices == ref_idx);
+            CHECK(w.rotations.size() == ref_rot.size());
+            for (size_t i = 0; i < ref_rot.size() && i < w.rotations.size(); ++i)
+                for (int k = 0; k < 9; ++k) CHECK(w.rotations[i].m[k] == ref_rot[i].m[k]);  // bit for bit
+            bool again = false;
+            try { w.pull_frame(); } catch (int err) { again = err == EOF; }
+            CHECK(again);
+        }
+    }
+    {  // an upstream failure surfaces after the frames that precede it, also when batching
+        struct FailingSource : FakeSource {
+            using FakeSource::FakeSource;
+            Frame pull_frame() override { if (pulls == 9) { ++pulls; throw -7; } return FakeSource::pull_frame(); }
+        };
+        for (int batch : {1, 4}) {
+            auto src = std::make_shared<FailingSource>(30);
+            RecordingWarp w(src, GOPRO_H4B_WIDE169_MEASURED, 1, false, 1, 2, INTER_LINEAR, nullptr, false);
+            w.set_warp_batch(batch);
+            int got = 0, err_code = 0;
+            try { while (true) { w.pull_frame(); ++got; } } catch (int err) { err_code = err; }
+            CHECK(err_code == -7);
+            CHECK(got == 6);  // frames 1..8 buffered; emitting frame k needs frame k + radius: 1..6 come out, then the error
+        }
+    }
+    {  // frame pool bookkeeping (over caller-owned memory: no device needed)
+        static uint8_t slab[8 * 256];
+        FramePool pool(0, slab, 256, 8);
+        uint8_t* a = pool.acquire();
+        uint8_t* b = pool.acquire();
+        uint8_t* c = pool.acquire();
+        CHECK(a == slab && b == slab + 256 && c == slab + 512 && pool.used() == 3);  // ring order: neighbours
+        pool.release(b);
+        CHECK(pool.acquire() == slab + 768);       // the cursor moves on, the hole is reused only after a lap
+        for (int i = 0; i < 4; ++i) CHECK(pool.acquire() != nullptr);
+        CHECK(pool.used() == 7 && pool.acquire() == slab + 256 && pool.acquire() == nullptr);
+        pool.release(slab + 5 * 256 + 1);          // not a slot start of a busy slot: slot 5 is released (address inside it)
+        pool.release(nullptr);                      // ignored
+        CHECK(pool.used() == 7);
+    }
+    if (std::getenv("VAW_ROT_INCREMENTS")) {  // rotation chain against video_annotator_b200/rotations.py (tests/test_host_shim.py)
+        // file: n lines of axis-angle increments; prints the warp rotation of every emitted frame
+        struct Replay : RotationSource {
+            std::vector<Mat33> inc;
+            bool rotation_since_last_frame(long frame_index, Mat33& out) override
+            {
+                if (frame_index < 1 || (size_t)frame_index > inc.size()) return false;
+                out = inc[(size_t)frame_index - 1];
+                return true;
+            }
+        };
+        auto replay = std::make_shared<Replay>();
+        FILE* f = std::fopen(std::getenv("VAW_ROT_INCREMENTS"), "r");
+        double vx, vy, vz;
+        while (f && std::fscanf(f, "%lf %lf %lf", &vx, &vy, &vz) == 3) {
+            const double th = std::sqrt(vx * vx + vy * vy + vz * vz);
+            Mat33 r = Mat33::eye();
+            if (th >= 1e-15) {
+                const double kx = vx / th, ky = vy / th, kz = vz / th, s = std::sin(th), c1 = 1 - std::cos(th);
+                const Mat33 K{{0, -kz, ky, kz, 0, -kx, -ky, kx, 0}};
+                const Mat33 K2 = K * K;
+                for (int i = 0; i < 9; ++i) r.m[i] += s * K.m[i] + c1 * K2.m[i];
+            }
+            replay->inc.push_back(r);
+        }
+        if (f) std::fclose(f);
+        const int n = (int)replay->inc.size() + 1, radius = std::atoi(std::getenv("VAW_ROT_RADIUS") ? std::getenv("VAW_ROT_RADIUS") : "30");
+        auto src = std::make_shared<FakeSource>(n);
+        RecordingWarp w(src, GOPRO_H4B_WIDE169_MEASURED, 1, false, 1, radius, INTER_LINEAR, replay, false);
+        w.set_warp_batch(7);
+        try { while (true) w.pull_frame(); } catch (int err) { CHECK(err == EOF); }
+        for (const Mat33& r : w.rotations) {
+            std::printf("ROT");
+            for (double v : r.m) std::printf(" %.17g", v);
+            std::printf("\n");
+        }
     }
     std::printf("%s: %d checks, %d failed\n", g_failed ? "FAILED" : "OK", g_checks, g_failed);
     return g_failed ? 1 : 0;

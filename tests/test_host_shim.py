@@ -32,6 +32,26 @@ def test_state_machine_on_cpu():
     assert out.stdout.strip().startswith("OK:")
 
 
+def test_shim_rotation_chain_equals_the_python_workload_generator(tmp_path):
+    """The two restatements of FrameSourceWarp.cpp:441-475 -- the C++ shim's accumulate / Savitzky-Golay /
+    SO(3)-projection / inverse chain (batched look-ahead on) and video_annotator_b200/rotations.py, which
+    generates the benchmark's rotations -- agree on the same gyro increments to 1e-12."""
+    from video_annotator_b200 import rotations as R
+    _build_state_machine_test()
+    rng = np.random.default_rng(7)
+    for n, radius in ((75, 30), (12, 3)):
+        inc = rng.normal(0.0, np.deg2rad(0.6), (n, 3))
+        path = tmp_path / f"inc_{n}.txt"
+        np.savetxt(path, inc, fmt="%.17g")
+        env = dict(os.environ, VAW_ROT_INCREMENTS=str(path), VAW_ROT_RADIUS=str(radius))
+        out = subprocess.run([HOST_TEST], capture_output=True, text=True, timeout=120, env=env)
+        assert out.returncode == 0, out.stdout + out.stderr
+        got = np.array([[float(v) for v in ln.split()[1:]] for ln in out.stdout.splitlines() if ln.startswith("ROT")])
+        want = R.rotations_from_increments(inc, radius).reshape(n, 9)
+        assert got.shape == want.shape
+        assert np.abs(got - want).max() < 1e-12
+
+
 def test_shim_and_demo_build_with_werror():
     from video_annotator_b200 import _build
     demo = _build.build_host_shim(force=True)
@@ -43,7 +63,8 @@ def test_shim_and_demo_build_with_werror():
 
 
 @pytest.mark.gpu
-def test_demo_chain_on_gpu(oracle):
+@pytest.mark.parametrize("warp_batch", [1, 5])
+def test_demo_chain_on_gpu(oracle, warp_batch):
     """DisplayImage.cpp's loop over the shim: every emitted frame equals the Python API's warp of
     the same synthetic frame with the rotation the shim reports, and the frames come out in order
     with frame 0 dropped."""
@@ -52,7 +73,10 @@ def test_demo_chain_on_gpu(oracle):
     from video_annotator_b200 import _build
     demo = _build.build_host_shim()
     w, h, n, radius = 1920, 1080, 12, 3
-    out = subprocess.run([demo, str(w), str(h), str(n), str(radius), "0.5"], capture_output=True, text=True, timeout=300)
+    # warp_batch 5: look-ahead frames are warped five per launch from the pooled slab (vaw_warp_batch +
+    # vaw_bind_clip); frames, order, rotations and bytes must not change
+    out = subprocess.run([demo, str(w), str(h), str(n), str(radius), "0.5", str(warp_batch)], capture_output=True,
+                         text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     lines = out.stdout.strip().splitlines()
     ow, oh = [int(v) for v in lines[0].split()[1:]]
@@ -73,3 +97,16 @@ def test_demo_chain_on_gpu(oracle):
         assert zlib.crc32(dst.cpu().numpy().tobytes()) == crc, idx
     assert re.search(r"\d+ frames", out.stderr)
     ctx.close()
+
+
+@pytest.mark.gpu
+def test_demo_bench_mode_reports_both_pull_patterns():
+    from video_annotator_b200 import _build
+    demo = _build.build_host_shim()
+    out = subprocess.run([demo, "--bench", "300", "16", "1920", "1080"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    import json
+    d = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][0])
+    assert d["frames"] == 299 and d["warp_batch"] == 16
+    assert d["fps_batched"] > 0 and d["fps_one_warp_per_call"] > 0
+    assert d["batched_launches"] <= 299 // 16 + 8   # frames really went through batched launches (a few runs split at the slab's wrap)

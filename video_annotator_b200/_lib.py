@@ -50,6 +50,7 @@ SIGNATURES = {
     "vaw_warp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, f64p, C.c_void_p]),
     "vaw_warp_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_int,
                                  C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]),
+    "vaw_bind_clip": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_int]),
     "vaw_upload_rotations": (C.c_int, [C.c_void_p, f64p, C.c_int, C.c_void_p, C.c_void_p]),
     "vaw_warp_batch_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, f64p, C.c_int]),
     "vaw_dump_coords": (C.c_int, [C.c_void_p, f64p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),

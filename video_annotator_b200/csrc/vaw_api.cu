@@ -67,6 +67,10 @@ struct vaw_ctx {
     MapEntry map_cache[4];
     int map_next = 0;
     int tile_cap = 32 << 10;  // chosen at creation from the pieces' source boxes
+    // vaw_bind_clip: a slab of equally spaced source frames; launches inside it share its tensor maps
+    const uint8_t* clip_base = nullptr;
+    int clip_pitch = 0, clip_slots = 0;
+    size_t clip_stride = 0;
     int tile_kernel = 2;      // 2: quadrant kernel (default), 1: the round-1 kernel (A/B only; option "tile_kernel")
     long long tile_need = 0;  // largest tile a piece of the unrotated geometry needs (bytes)
     // variant TEX: texture objects over the clip, cached per source layout
@@ -416,7 +420,19 @@ int launch(vaw_ctx* ctx, const uint8_t* src, int src_pitch, size_t src_stride, u
                 }
             }
             if (tev) cudaEventRecord(tev[2], st);
-            const vaw::TileMaps* tm = (piped || tiled) ? &tile_maps(ctx, bb.src, src_pitch, src_stride, bb.n_frames) : nullptr;
+            // source inside the bound slab: its tensor maps (encoded once) + the slot index of the first frame
+            int clip_frame0 = -1;
+            if (ctx->clip_base && bb.src >= ctx->clip_base && src_pitch == ctx->clip_pitch &&
+                (bb.n_frames == 1 || src_stride == ctx->clip_stride)) {
+                const size_t off = (size_t)(bb.src - ctx->clip_base);
+                if (off % ctx->clip_stride == 0 && off / ctx->clip_stride + (size_t)bb.n_frames <= (size_t)ctx->clip_slots)
+                    clip_frame0 = (int)(off / ctx->clip_stride);
+            }
+            const vaw::TileMaps* tm = nullptr;
+            if (piped || tiled)
+                tm = clip_frame0 >= 0 ? &tile_maps(ctx, ctx->clip_base, ctx->clip_pitch, ctx->clip_stride, ctx->clip_slots)
+                                      : &tile_maps(ctx, bb.src, src_pitch, src_stride, bb.n_frames);
+            if (clip_frame0 >= 0) bb.tma_frame0 = clip_frame0;
             for (int part = 0; part < (split ? 2 : 1); ++part) {
                 vaw::FrameBatch pb = bb;
                 const vaw::PieceRec* ptab = tab;
@@ -429,7 +445,7 @@ int launch(vaw_ctx* ctx, const uint8_t* src, int src_pitch, size_t src_stride, u
                         pb.src = bb.src + (size_t)head * src_stride;
                         pb.dst = bb.dst + (size_t)head * dst_stride;
                         if (bb.rots) pb.rots = bb.rots + (size_t)head * 9;
-                        pb.tma_frame0 = head;
+                        pb.tma_frame0 = bb.tma_frame0 + head;
                         ptab = tab + (size_t)head * ctx->pieces_per_frame;
                         cnt = ctx->counter2;
                         VAW_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
@@ -827,6 +843,20 @@ int vaw_warp_batch(vaw_ctx* ctx, const uint8_t* src, int src_pitch, size_t src_f
     DeviceGuard dg(ctx->device);
     return launch(ctx, src, src_pitch, src_frame_stride, dst, dst_pitch, dst_frame_stride, rotations,
                   nullptr, n_frames, (cudaStream_t)stream);
+}
+
+int vaw_bind_clip(vaw_ctx* ctx, const uint8_t* base, int pitch, size_t frame_stride, int n_slots)
+{
+    if (!ctx) return VAW_ERR_INVALID;
+    if (!base) {  // unbind
+        ctx->clip_base = nullptr; ctx->clip_pitch = 0; ctx->clip_stride = 0; ctx->clip_slots = 0;
+        return VAW_OK;
+    }
+    if (n_slots < 1 || pitch < ctx->p.src_width * ctx->channels ||
+        frame_stride < vaw_frame_bytes(ctx->p.format, ctx->p.src_width, ctx->p.src_height, pitch))
+        return fail(ctx, VAW_ERR_INVALID, "bad clip layout");
+    ctx->clip_base = base; ctx->clip_pitch = pitch; ctx->clip_stride = frame_stride; ctx->clip_slots = n_slots;
+    return VAW_OK;
 }
 
 int vaw_upload_rotations(vaw_ctx* ctx, const double* rotations_host, int n_frames,

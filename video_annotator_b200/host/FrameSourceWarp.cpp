@@ -5,6 +5,9 @@
 
 #include <cmath>
 #include <cstdio>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "../../include/vaw.h"
 
@@ -33,9 +36,77 @@ Mat33 Mat33::inv() const
 }
 
 // ---- device frames ---------------------------------------------------------------------------
+FramePool::FramePool(int device, size_t frame_bytes, int slots)
+    : m_device(device), m_stride((frame_bytes + 255) & ~(size_t)255), m_slots(slots < 1 ? 1 : slots), m_busy(new bool[slots < 1 ? 1 : slots]())
+{
+    void* p = nullptr;
+    const int rc = vaw_malloc(device, m_stride * (size_t)m_slots, &p);
+    if (rc != VAW_OK) throw rc;
+    m_base = static_cast<uint8_t*>(p);
+}
+
+FramePool::FramePool(int device, uint8_t* base, size_t stride, int slots)
+    : m_device(device), m_stride(stride), m_slots(slots < 1 ? 1 : slots), m_base(base), m_owns(false), m_busy(new bool[slots < 1 ? 1 : slots]())
+{
+}
+
+FramePool::~FramePool()
+{
+    if (m_base && m_owns) vaw_free(m_device, m_base);
+}
+
+uint8_t* FramePool::acquire()
+{
+    if (m_used == m_slots) return nullptr;
+    // ring order: frames acquired back to back are neighbours in the slab (until the cursor wraps)
+    for (int k = 0; k < m_slots; ++k) {
+        const int i = (m_cursor + k) % m_slots;
+        if (!m_busy[i]) {
+            m_busy[i] = true;
+            ++m_used;
+            m_cursor = (i + 1) % m_slots;
+            return m_base + (size_t)i * m_stride;
+        }
+    }
+    return nullptr;
+}
+
+void FramePool::release(uint8_t* slot)
+{
+    const size_t i = (size_t)(slot - m_base) / m_stride;
+    if (slot < m_base || i >= (size_t)m_slots || !m_busy[i]) return;
+    m_busy[i] = false;
+    --m_used;
+}
+
+namespace {
+std::mutex g_pool_mutex;
+std::map<std::pair<int, size_t>, std::shared_ptr<FramePool>> g_pools;
+}  // namespace
+
+std::shared_ptr<FramePool> frame_pool(int device, size_t bytes)
+{
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    std::shared_ptr<FramePool>& p = g_pools[std::make_pair(device, bytes)];
+    if (!p) p = std::make_shared<FramePool>(device, bytes, kDefaultPoolSlots);
+    return p;
+}
+
+void frame_pool_trim()
+{
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    g_pools.clear();
+}
+
 DeviceFrame::~DeviceFrame()
 {
-    if (data) vaw_free(device, data);
+    if (!data || alias_of) return;
+    if (pool) {
+        std::lock_guard<std::mutex> lock(g_pool_mutex);
+        pool->release(data);
+    } else {
+        vaw_free(device, data);
+    }
 }
 
 Frame make_device_frame(int device, int format, int width, int height)
@@ -44,7 +115,16 @@ Frame make_device_frame(int device, int format, int width, int height)
     const int channels = format == VAW_FORMAT_BGR24 ? 3 : 1;
     f->width = width; f->height = height; f->pitch = width * channels; f->format = format; f->device = device;
     f->bytes = vaw_frame_bytes(format, width, height, f->pitch);
-    void* p = nullptr;
+    std::shared_ptr<FramePool> pool = frame_pool(device, f->bytes);
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mutex);
+        f->data = pool->acquire();
+    }
+    if (f->data) {
+        f->pool = pool;
+        return f;
+    }
+    void* p = nullptr;  // more frames in flight than the pool holds: a plain allocation
     const int rc = vaw_malloc(device, f->bytes, &p);
     if (rc != VAW_OK) throw rc;
     f->data = static_cast<uint8_t*>(p);
@@ -180,11 +260,14 @@ void FrameSourceWarp::create_context()
 
 FrameSourceWarp::~FrameSourceWarp()
 {
+    if (m_rot_dev) vaw_free(m_device, m_rot_dev);
     if (m_ctx) vaw_destroy(m_ctx);
 }
 
 int FrameSourceWarp::output_width() const { return m_format == VAW_FORMAT_NV12 ? m_output_camera.width & ~1 : m_output_camera.width; }
 int FrameSourceWarp::output_height() const { return m_format == VAW_FORMAT_NV12 ? m_output_camera.height & ~1 : m_output_camera.height; }
+
+void FrameSourceWarp::set_warp_batch(int frames) { m_warp_batch = frames < 1 ? 1 : (frames > kMaxWarpBatch ? kMaxWarpBatch : frames); }
 
 Frame FrameSourceWarp::warp_frame(Frame input, const Mat33& rotation)
 {
@@ -194,6 +277,65 @@ Frame FrameSourceWarp::warp_frame(Frame input, const Mat33& rotation)
     if (rc == VAW_OK) rc = vaw_sync(m_device, nullptr);  // the reference's launch is blocking, :301
     if (rc != VAW_OK) throw -1;                           // :301-304
     return output;
+}
+
+// Several frames whose rotations are already known: runs of frames that sit at a constant stride (the
+// usual case with pooled frames) go through ONE vaw_warp_batch each, with a single synchronisation at the
+// end -- a 4K frame is ~12 us of GPU work, less than a launch + sync round trip.
+std::vector<Frame> FrameSourceWarp::warp_frames(const std::vector<Frame>& inputs, const std::vector<Mat33>& rotations)
+{
+    std::vector<Frame> outputs;
+    outputs.reserve(inputs.size());
+    if (!m_ctx || inputs.size() == 1) {  // no device context (CPU tests) or nothing to batch
+        for (size_t i = 0; i < inputs.size(); ++i) outputs.push_back(warp_frame(inputs[i], rotations[i]));
+        return outputs;
+    }
+    const size_t n = inputs.size();
+    for (size_t i = 0; i < n; ++i) {
+        outputs.push_back(make_device_frame(m_device, m_format, output_width(), output_height()));
+        outputs.back()->index = inputs[i]->index;
+    }
+    if (!m_rot_dev) {
+        void* p = nullptr;
+        if (vaw_malloc(m_device, sizeof(float) * 9 * kMaxWarpBatch, &p) != VAW_OK) throw -1;
+        m_rot_dev = static_cast<float*>(p);
+    }
+    std::vector<double> rots(9 * n);
+    for (size_t i = 0; i < n; ++i)
+        for (int k = 0; k < 9; ++k) rots[9 * i + k] = rotations[i].m[k];
+    if (vaw_upload_rotations(m_ctx, rots.data(), (int)n, m_rot_dev, nullptr) != VAW_OK) throw -1;
+    // the source slab's tensor maps are encoded once (a hint; any other layout still works)
+    const std::shared_ptr<FramePool>& pool = inputs[0]->pool;
+    if (pool && pool->base() != m_bound_base) {
+        if (vaw_bind_clip(m_ctx, pool->base(), inputs[0]->pitch, pool->stride(), pool->slots()) == VAW_OK) m_bound_base = pool->base();
+    }
+    size_t first = 0;
+    while (first < n) {
+        // longest run [first, last) with constant source and output strides
+        size_t last = first + 1;
+        ptrdiff_t ss = 0, ds = 0;
+        if (last < n) {
+            ss = inputs[last]->data - inputs[first]->data;
+            ds = outputs[last]->data - outputs[first]->data;
+            const bool ok = ss > 0 && ds > 0 && (size_t)ss >= inputs[first]->bytes && (size_t)ds >= outputs[first]->bytes &&
+                            inputs[last]->pitch == inputs[first]->pitch;
+            if (ok) {
+                ++last;
+                while (last < n && inputs[last]->data - inputs[last - 1]->data == ss &&
+                       outputs[last]->data - outputs[last - 1]->data == ds && inputs[last]->pitch == inputs[first]->pitch)
+                    ++last;
+            }
+        }
+        const int count = (int)(last - first);
+        const int rc = vaw_warp_batch(m_ctx, inputs[first]->data, inputs[first]->pitch, count > 1 ? (size_t)ss : inputs[first]->bytes,
+                                      outputs[first]->data, outputs[first]->pitch, count > 1 ? (size_t)ds : outputs[first]->bytes,
+                                      m_rot_dev + 9 * first, count, nullptr);
+        if (rc != VAW_OK) throw -1;
+        ++m_batch_launches;
+        first = last;
+    }
+    if (vaw_sync(m_device, nullptr) != VAW_OK) throw -1;
+    return outputs;
 }
 
 void FrameSourceWarp::consume_frame(Frame input_frame)
@@ -219,29 +361,69 @@ void FrameSourceWarp::consume_frame(Frame input_frame)
     ++m_frame_index;
 }
 
-Frame FrameSourceWarp::pull_frame()
+// One turn of the reference's pull_frame (:452-476) up to, not including, warp_frame: top up the
+// look-ahead queue, then take the oldest frame with the rotation that undoes its shake.
+bool FrameSourceWarp::next_frame_and_rotation(Frame& frame, Mat33& rotation)
 {
     while (m_buffered_frames.size() <= m_smooth_radius) {
         try {
             consume_frame(m_source->pull_frame());
         } catch (int err) {
             if (err == EOF) {
-                // Pretend the camera kept moving the same way after the last frame (:458-460)
+                // upstream has ended: the filter window is topped up with the final camera pose (:458-460)
                 m_rotation_filter.add(m_measured_rotation);
                 break;
             }
             throw;
         }
     }
-    if (m_buffered_frames.size() == 0) throw EOF;
-    // Stabilise by applying the inverse of the accumulated camera rotation (:468-475)
-    Frame frame = m_buffered_frames.front();
+    if (m_buffered_frames.size() == 0) return false;
+    // rotation that takes the measured camera pose onto the smoothed path, inverted for the map (:468-475)
+    frame = m_buffered_frames.front();
     const Mat33 measured_rotation = m_buffered_rotations.front();
     const Mat33 corrected_rotation = m_rotation_filter.filter();
     const Mat33 rotation_correction = corrected_rotation * measured_rotation.inv();
     m_buffered_frames.pop();
     m_buffered_rotations.pop();
-    return warp_frame(frame, rotation_correction.inv());
+    rotation = rotation_correction.inv();
+    return true;
+}
+
+Frame FrameSourceWarp::pull_frame()
+{
+    if (m_warp_batch <= 1) {  // the reference's pull pattern exactly: one upstream pull, one warp per call
+        Frame frame;
+        Mat33 rotation;
+        if (!next_frame_and_rotation(frame, rotation)) throw EOF;
+        return warp_frame(frame, rotation);
+    }
+    // Batched: the same turns, run up to m_warp_batch times ahead -- every frame gets exactly the rotation
+    // the one-at-a-time loop gives it (same filter state, same order) -- then ONE batched warp; the
+    // results are handed out over the following calls.  Only the latency (frames pulled from upstream
+    // before the first one comes out) grows, by m_warp_batch - 1.
+    if (m_ready.empty()) {
+        if (m_deferred_error_set) { m_deferred_error_set = false; throw m_deferred_error; }
+        std::vector<Frame> frames;
+        std::vector<Mat33> rotations;
+        try {
+            while ((int)frames.size() < m_warp_batch) {
+                Frame frame;
+                Mat33 rotation;
+                if (!next_frame_and_rotation(frame, rotation)) break;
+                frames.push_back(frame);
+                rotations.push_back(rotation);
+            }
+        } catch (int err) {
+            if (frames.empty()) throw;
+            m_deferred_error = err;  // surfaces after the frames that precede it, as it would one at a time
+            m_deferred_error_set = true;
+        }
+        if (frames.empty()) throw EOF;
+        for (Frame& f : warp_frames(frames, rotations)) m_ready.push_back(f);
+    }
+    Frame out = m_ready.front();
+    m_ready.pop_front();
+    return out;
 }
 
 Frame FrameSourceWarp::peek_frame()

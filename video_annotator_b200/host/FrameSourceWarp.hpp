@@ -106,13 +106,28 @@ class FrameSourceWarp : public FrameSource {
     std::queue<Frame> m_buffered_frames;
     std::queue<Mat33> m_buffered_rotations;
 
+    // batched warping of look-ahead frames (set_warp_batch): outputs ready to hand out, device rotations,
+    // an upstream error that surfaces after the frames that precede it
+    static constexpr int kMaxWarpBatch = 64;
+    int m_warp_batch = 1;
+    std::deque<Frame> m_ready;
+    float* m_rot_dev = nullptr;
+    const uint8_t* m_bound_base = nullptr;
+    long m_batch_launches = 0;
+    int m_deferred_error = 0;
+    bool m_deferred_error_set = false;
+
     void consume_frame(Frame input_frame);
+    bool next_frame_and_rotation(Frame& frame, Mat33& rotation);  // pull_frame (:452-476) up to warp_frame
     void create_context();  // vaw_create from m_input_camera / m_output_camera / m_format / m_interpolation
 
   protected:
     // warp_frame(input, rotation), :272-314.  Virtual so that the state machine can be tested
     // without a GPU; the real one calls vaw_warp and synchronises before returning.
     virtual Frame warp_frame(Frame input, const Mat33& rotation);
+    // The same for several frames whose rotations are known: one vaw_warp_batch per run of equally spaced
+    // frames, one synchronisation.  Without a device context it calls warp_frame per frame.
+    virtual std::vector<Frame> warp_frames(const std::vector<Frame>& inputs, const std::vector<Mat33>& rotations);
 
   public:
     FrameSourceWarp(
@@ -146,6 +161,11 @@ class FrameSourceWarp : public FrameSource {
     const Camera& output_camera() const { return m_output_camera; }
     int output_width() const;   // even for NV12
     int output_height() const;
+    // Warp up to `frames` look-ahead frames per launch (default 1 = the reference's pull pattern: one
+    // upstream pull and one warp per call).  Frames, order and rotations are unchanged; only the number of
+    // frames pulled from upstream before the first output grows by frames - 1.
+    void set_warp_batch(int frames);
+    long batch_launches() const { return m_batch_launches; }
 };
 
 #endif  // VAW_FRAME_SOURCE_WARP_HPP_

@@ -6,12 +6,17 @@
 // interop and imshow are out of scope (BASELINE.json north_star): frames are synthesised in
 // device memory and every output frame is read back and check-summed instead of displayed.
 //
-//   vaw_demo <width> <height> <frames> <smooth_radius> [sigma_deg]
+//   vaw_demo <width> <height> <frames> <smooth_radius> [sigma_deg] [warp_batch]
 // prints one line per emitted frame:  frame <index> crc <crc32> rot <9 doubles>
+//   vaw_demo --bench [frames] [warp_batch] [width] [height]
+// times the pull loop of the drop-in at 4K (no read-back; the source hands out frames synthesised once
+// into its slab) for the reference's pull pattern (one warp per call) and for batched look-ahead
+// warping, and prints one JSON line.
 #include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "../../include/vaw.h"
@@ -79,6 +84,62 @@ class ReportingWarp : public FrameSourceWarp {
     }
 };
 
+// A decoder stand-in for the timing run: `ring` NV12 frames synthesised once into pooled slots, handed
+// out round-robin as frames 0 .. n-1 (decode is out of scope; this keeps the source out of the timing).
+class RingFrameSource : public FrameSource {
+    std::vector<Frame> m_ring;
+    long m_n, m_next = 0;
+  public:
+    RingFrameSource(int w, int h, long n, int ring, int device) : m_n(n)
+    {
+        for (int i = 0; i < ring; ++i) {
+            Frame f = make_device_frame(device, VAW_FORMAT_NV12, w, h);
+            if (vaw_synth_nv12(f->data, w, h, f->pitch, f->bytes, i, 1, 20260001u, 0, device, nullptr) != VAW_OK) throw -1;
+            m_ring.push_back(f);
+        }
+        if (vaw_sync(device, nullptr) != VAW_OK) throw -1;
+    }
+    Frame view(long index)
+    {
+        if (index >= m_n) throw EOF;
+        const Frame& slot = m_ring[(size_t)(index % (long)m_ring.size())];
+        // a second handle on the slot's buffer: keeps the slot alive, frees nothing
+        auto v = std::make_shared<DeviceFrame>();
+        v->width = slot->width; v->height = slot->height; v->pitch = slot->pitch; v->format = slot->format;
+        v->device = slot->device; v->bytes = slot->bytes; v->index = index;
+        v->data = slot->data;
+        v->pool = slot->pool;
+        v->alias_of = slot;
+        return v;
+    }
+    Frame pull_frame() override { return view(m_next++); }
+    Frame peek_frame() override { return view(m_next); }
+    const Frame& slot0() const { return m_ring[0]; }
+};
+
+double run_bench(int w, int h, long n, int batch, int radius, long* emitted_out, long* launches_out)
+{
+    auto source = std::make_shared<RingFrameSource>(w, h, n, 64, 0);
+    FrameSourceWarp warped(source, GOPRO_H4B_WIDE169_MEASURED, 1.0, false, 1.0, radius, INTER_LINEAR,
+                           std::make_shared<GyroRotationSource>(0.4));
+    warped.set_warp_batch(batch);
+    long emitted = 0;
+    const auto t0 = std::chrono::steady_clock::now();
+    while (true) {
+        try {
+            Frame frame = warped.pull_frame();
+            ++emitted;
+        } catch (int err) {
+            if (err == EOF) break;
+            throw;
+        }
+    }
+    const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    *emitted_out = emitted;
+    *launches_out = warped.batch_launches();
+    return s;
+}
+
 unsigned crc32(const std::vector<uint8_t>& v)
 {
     static unsigned table[256];
@@ -100,16 +161,38 @@ unsigned crc32(const std::vector<uint8_t>& v)
 
 int main(int argc, char* argv[])
 {
+    if (argc >= 2 && std::string(argv[1]) == "--bench") {
+        const long n = argc > 2 ? std::atol(argv[2]) : 1500;
+        const int batch = argc > 3 ? std::atoi(argv[3]) : 16;
+        const int w = argc > 4 ? std::atoi(argv[4]) : 3840, h = argc > 5 ? std::atoi(argv[5]) : 2160;
+        try {
+            long e1 = 0, l1 = 0, eb = 0, lb = 0;
+            run_bench(w, h, 200, batch, 30, &eb, &lb);  // warm-up: context, pools, tensor maps
+            const double s1 = run_bench(w, h, n, 1, 30, &e1, &l1);
+            const double sb = run_bench(w, h, n, batch, 30, &eb, &lb);
+            std::printf("{\"shim\": \"FrameSourceWarp::pull_frame over a pooled ring source\", \"src\": [%d, %d], \"frames\": %ld, "
+                        "\"smooth_radius\": 30, \"fps_one_warp_per_call\": %.1f, \"warp_batch\": %d, \"fps_batched\": %.1f, "
+                        "\"batched_launches\": %ld, \"shim_fps\": %.1f}\n",
+                        w, h, e1, e1 / s1, batch, eb / sb, lb, eb / sb);
+        } catch (int err) {
+            std::fprintf(stderr, "error %d: %s\n", err, vaw_last_error(nullptr));
+            return 1;
+        }
+        frame_pool_trim();
+        return 0;
+    }
     if (argc < 5) {
         std::fprintf(stderr, "Usage: %s <width> <height> <frames> <smooth_radius> [sigma_deg]\n", argv[0]);
         return -1;
     }
     const int w = std::atoi(argv[1]), h = std::atoi(argv[2]), n = std::atoi(argv[3]), radius = std::atoi(argv[4]);
     const double sigma = argc > 5 ? std::atof(argv[5]) : 0.4;
+    const int warp_batch = argc > 6 ? std::atoi(argv[6]) : 1;
     try {
         auto source = std::make_shared<SyntheticFrameSource>(w, h, n, 0);
         auto warped = std::make_shared<ReportingWarp>(source, GOPRO_H4B_WIDE169_MEASURED, 1.0, false, 1.0, radius,
                                                       INTER_LINEAR, std::make_shared<GyroRotationSource>(sigma));
+        warped->set_warp_batch(warp_batch);
         std::printf("output %d %d\n", warped->output_width(), warped->output_height());
         long emitted = 0;
         const auto t0 = std::chrono::steady_clock::now();

@@ -34,6 +34,16 @@ def make_rotations(n, sigma_deg, radius=30, seed=ROT_SEED):
         return np.tile(np.eye(3), (n, 1, 1))
     rng = np.random.default_rng(seed)
     inc = rng.normal(0.0, np.deg2rad(sigma_deg), (n, 3))
+    return rotations_from_increments(inc, radius)
+
+
+def rotations_from_increments(inc, radius=30):
+    """Warp rotations for given per-frame axis-angle increments (n, 3): what FrameSourceWarp's
+    consume_frame / pull_frame chain (:441-475) hands warp_frame for frames 1..n when the inter-frame
+    rotation of frame i is rodrigues(inc[i-1]).  tests/test_host_shim.py feeds the same increments to the
+    C++ shim's chain and compares."""
+    inc = np.asarray(inc, np.float64)
+    n = len(inc)
     measured = np.empty((n, 3, 3))
     acc = np.eye(3)
     for i in range(n):
