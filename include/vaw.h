@@ -46,8 +46,13 @@ enum {
  *   row, Y rows 0..H-1 then H/2 rows of interleaved U,V.  W and H even.
  * VAW_FORMAT_BGR24: interleaved 8UC3 -- what the reference actually hands to
  *   warp_frame after cvtColor (opencv/FrameSourceWarp.cpp:401,445).
- * VAW_FORMAT_GRAY8: single 8-bit plane. */
-enum { VAW_FORMAT_NV12 = 0, VAW_FORMAT_BGR24 = 1, VAW_FORMAT_GRAY8 = 2 };
+ * VAW_FORMAT_GRAY8: single 8-bit plane.
+ * VAW_FORMAT_NV12_TO_BGR24: NV12 source frames, BGR24 output frames -- the reference's literal per-frame
+ *   pipeline, cvtColor(COLOR_YUV2BGR_NV12) (opencv/FrameSourceWarp.cpp:399-401) followed by the 3-channel
+ *   remap (:306-312), in ONE launch and bit-exact with doing the two steps one after the other: every
+ *   bilinear tap is a source pixel converted with OpenCV's fixed-point BT.601, the border value applies to
+ *   the converted image (border[0..2] = B, G, R).  Source sizes even, output size free; INTER_LINEAR. */
+enum { VAW_FORMAT_NV12 = 0, VAW_FORMAT_BGR24 = 1, VAW_FORMAT_GRAY8 = 2, VAW_FORMAT_NV12_TO_BGR24 = 3 };
 
 /* cv::InterpolationFlags values accepted for the constructor's `interpolation` parameter
  * (opencv/FrameSourceWarp.hpp:90).  All four are cv::remap's 8-bit fixed-point filters, bit for bit. */
@@ -165,7 +170,9 @@ int vaw_create(const vaw_params *params, int device, vaw_ctx **out);
 void vaw_destroy(vaw_ctx *ctx);
 const char *vaw_last_error(const vaw_ctx *ctx); /* ctx may be NULL: last create error */
 const char *vaw_strerror(int code);
-/* Bytes of one frame buffer with row pitch `pitch` (NV12: pitch*H*3/2). */
+/* Bytes of one frame buffer with row pitch `pitch` (NV12: pitch*H*3/2).  For a VAW_FORMAT_NV12_TO_BGR24
+ * context ask with VAW_FORMAT_NV12 for the source and VAW_FORMAT_BGR24 for the output (the combined
+ * value itself returns 0). */
 size_t vaw_frame_bytes(int format, int width, int height, int pitch);
 /* Number of this library's kernels launched through ctx so far. */
 uint64_t vaw_launch_count(const vaw_ctx *ctx);

@@ -277,6 +277,84 @@ def test_round1_tile_kernel_equals_quadrant_kernel(V, name, n):
     assert torch.equal(out[0], out[1])
 
 
+# ---- f2: cvtColor(COLOR_YUV2BGR_NV12) + 3-channel remap in ONE launch ---------------------------------
+@pytest.mark.parametrize("name,out_size,rot,white", [
+    ("C1", (1759, 998), (0.0, 0.0, 0.0), True),       # the reference's literal case: 1920x1080 -> 1759x998 BGR, odd width
+    ("C1", (1759, 998), (1.0, -2.0, 0.5), True),
+    ("C3", (3840, 2160), (2.0, -3.0, 1.5), False),
+    ("C2", (2482, 1408), (10.0, -15.0, 20.0), True),  # far outside the stabiliser's range: per-pixel pieces, rays behind the camera
+])
+def test_fused_nv12_to_bgr_equals_cvtcolor_then_remap(V, oracle, name, out_size, rot, white):
+    """NV12 in, BGR out in one launch == the reference's order of operations (FrameSourceWarp.cpp:399-401 then
+    :306-312): cvtColor on the whole frame (oracle/cvt_ref.c, pinned to cv2.cvtColor), then cv::remap's
+    integer filter on the 3-channel image with the map the kernel used.  0 LSB; also against the real
+    cv2.cvtColor + cv2.remap when cv2 is importable."""
+    from video_annotator_b200 import configs
+    w = configs.workload(name)
+    R = rotation_xyz(*rot)
+    sw, sh = w.src_size
+    border = (3, 40, 200)
+    ctx = V.WarpContext(w.input_camera, w.output_camera, fmt=V.FORMAT_NV12_TO_BGR24, out_size=out_size, border=border)
+    assert ctx.frame_shape("src") == (sh * 3 // 2, sw) and ctx.frame_shape("dst") == (out_size[1], out_size[0], 3)
+    src = oracle.synth_nv12(sw, sh, 5, white_noise=white)
+    got = _warp_one(V, ctx, src, R)
+    mx, my = [t.cpu().numpy() for t in ctx.dump_coords(R, 0)]
+    bgr = oracle.nv12_to_bgr(src, sw, sh, threads=NCPU)
+    ref = oracle.remap_u8(bgr, mx, my, border=border, threads=NCPU)
+    st = G.diff_stats(got, ref)
+    _record(f"fused_bgr_same_map_{name}_{rot}", st)
+    assert st["max"] == 0, st
+    try:
+        import cv2
+    except ImportError:
+        cv2 = None
+    if cv2 is not None:
+        cv_bgr = cv2.cvtColor(src, cv2.COLOR_YUV2BGR_NV12)
+        cv_ref = cv2.remap(cv_bgr, mx, my, cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT, borderValue=tuple(float(b) for b in border))
+        assert np.array_equal(got, cv_ref)
+    # coordinates: the same map contract as every other path (<= 1e-3 px from createMap.cl)
+    k = G.oracle_k(oracle, (w.input_camera, w.output_camera))
+    ox, oy, _ = oracle.reference_create_map(k, R, out_size[1], out_size[0], threads=NCPU)
+    assert np.array_equal(np.isnan(ox), np.isnan(mx))
+    big = max(np.abs(np.nan_to_num(ox)).max(), np.abs(np.nan_to_num(oy)).max()) > 1e4  # rays near / behind the image plane
+    if not big:
+        assert max(float(np.nanmax(np.abs(mx - ox))), float(np.nanmax(np.abs(my - oy)))) < 1e-3
+    ctx.close()
+
+
+def test_fused_nv12_to_bgr_batches_pitches_and_the_two_launch_pipeline(V, oracle):
+    """Batch == per frame; pitched output with untouched padding; and the same bytes as the two-launch pipeline
+    (vaw_nv12_to_bgr, then a BGR24 context) wherever the two contexts use the same map."""
+    import torch
+    from video_annotator_b200 import configs
+    w = configs.workload("C1")
+    sw, sh = w.src_size
+    ow, oh = 1759, 998
+    n = 3
+    rots = configs.make_rotations(40, 0.7)[20:20 + n]
+    ctx = V.WarpContext(w.input_camera, w.output_camera, fmt=V.FORMAT_NV12_TO_BGR24, out_size=(ow, oh), border=(0, 0, 0))
+    src = torch.empty((n, sh * 3 // 2, sw), dtype=torch.uint8, device="cuda")
+    V.synth_nv12(src, sw, sh, n, first_index=2, white_noise=True)
+    rdev = torch.empty(n * 9, dtype=torch.float32, device="cuda")
+    ctx.upload_rotations(rots, rdev)
+    pitch = ow * 3 + 5
+    dst = torch.full((n, oh, pitch), 77, dtype=torch.uint8, device="cuda")
+    ctx.warp_batch(src, dst, rdev, n, dst_pitch=pitch, dst_stride=oh * pitch)
+    torch.cuda.synchronize()
+    assert bool((dst[:, :, ow * 3:] == 77).all())
+    single = torch.empty((oh, ow, 3), dtype=torch.uint8, device="cuda")
+    for i in range(n):
+        ctx.warp(src[i], single, rots[i])
+        assert torch.equal(single.reshape(oh, ow * 3), dst[i, :, :ow * 3]), i
+    # two-launch pipeline through the explicit-map entry point on the same map
+    mx, my = ctx.dump_coords(rots[1], 0)
+    bgr = V.nv12_to_bgr(src[1], sw, sh)[0]
+    two = V.remap_u8(bgr, mx, my, border=(0, 0, 0))
+    torch.cuda.synchronize()
+    assert torch.equal(two.reshape(oh, ow * 3), dst[1, :, :ow * 3])
+    ctx.close()
+
+
 # ---- batching, pitches, host path -----------------------------------------------------------------
 @pytest.mark.parametrize("variant", [POLY, TILED, PIPE])
 def test_split_batches_equal_unsplit(V, variant):

@@ -84,9 +84,11 @@ def load():
     """Load libvaw.so (building it with nvcc if sources are newer)."""
     global _lib
     if _lib is None:
-        path = _build.LIB
-        if not os.path.exists(path) or _build.needs_build():
-            path = _build.build()
+        path = os.environ.get("VAW_LIBRARY")  # A/B builds of tools/build_variants.py
+        if not path:
+            path = _build.LIB
+            if not os.path.exists(path) or _build.needs_build():
+                path = _build.build()
         lib = C.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)  # AttributeError if the ABI is incomplete

@@ -47,7 +47,9 @@ struct vaw_ctx {
     vaw::Geom g{};
     float *xtab = nullptr, *ytab = nullptr;
     int16_t* cubic_tab = nullptr;  // INTER_CUBIC weights (device)
-    int channels = 1;
+    int channels = 1;      // bytes per pixel of a SOURCE row (NV12 and GRAY8: 1, BGR24: 3)
+    int dst_channels = 1;  // ... of an OUTPUT row (differs for VAW_FORMAT_NV12_TO_BGR24: NV12 in, BGR24 out)
+    int src_format = 0, dst_format = 0;  // VAW_FORMAT_NV12 / BGR24 / GRAY8 of the two sides
     size_t src_frame_bytes = 0, dst_frame_bytes = 0;  // tightly packed
     uint64_t launches = 0;
     std::string err;
@@ -137,9 +139,9 @@ int check_buffers(vaw_ctx* ctx, const void* src, int src_pitch, void* dst, int d
 {
     if (!ctx) return VAW_ERR_INVALID;
     if (!src || !dst) return fail(ctx, VAW_ERR_INVALID, "null frame pointer");
-    if (src_pitch < ctx->p.src_width * ctx->channels || dst_pitch < ctx->p.out_width * ctx->channels)
+    if (src_pitch < ctx->p.src_width * ctx->channels || dst_pitch < ctx->p.out_width * ctx->dst_channels)
         return fail(ctx, VAW_ERR_INVALID, "pitch smaller than a row");
-    if (ctx->p.format == VAW_FORMAT_NV12 &&
+    if (ctx->src_format == VAW_FORMAT_NV12 &&
         ((src_pitch & 1) || (reinterpret_cast<uintptr_t>(src) & 1)))
         return fail(ctx, VAW_ERR_INVALID, "NV12 source base and pitch must be even");
     return VAW_OK;
@@ -358,7 +360,8 @@ int launch(vaw_ctx* ctx, const uint8_t* src, int src_pitch, size_t src_stride, u
     b.dst_frame_stride = dst_stride;
     b.rots = rots;
     if (rot0) b.rot0 = *rot0;
-    const bool poly = ctx->p.format == VAW_FORMAT_NV12 && ctx->variant != VAW_VARIANT_GATHER;
+    const bool fused_bgr = ctx->p.format == VAW_FORMAT_NV12_TO_BGR24;
+    const bool poly = fused_bgr || (ctx->p.format == VAW_FORMAT_NV12 && ctx->variant != VAW_VARIANT_GATHER);
     const bool tiled = ctx->variant == VAW_VARIANT_TILED || ctx->variant == VAW_VARIANT_PIPE ||
                        ctx->variant == VAW_VARIANT_TEX;
     const bool piped = ctx->variant == VAW_VARIANT_PIPE && ctx->g.piece_h == vaw::kPieceHMax &&
@@ -451,7 +454,8 @@ int launch(vaw_ctx* ctx, const uint8_t* src, int src_pitch, size_t src_stride, u
                         VAW_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
                     }
                 }
-                if (piped) e = vaw::launch_warp_nv12_pipe(g, pb, ptab, cnt, *tm, st);
+                if (fused_bgr) e = vaw::launch_warp_nv12_to_bgr(g, pb, ptab, st);
+                else if (piped) e = vaw::launch_warp_nv12_pipe(g, pb, ptab, cnt, *tm, st);
                 else if (tiled) e = vaw::launch_warp_nv12_tile(g, pb, ptab, *tm, st);
                 else e = vaw::launch_warp_nv12_poly(g, pb, ptab, st);
                 if (e != cudaSuccess) return cuda_fail(ctx, e, "warp kernel launch");
@@ -571,6 +575,7 @@ const char* vaw_last_error(const vaw_ctx* ctx) { return ctx ? ctx->err.c_str() :
 size_t vaw_frame_bytes(int format, int width, int height, int pitch)
 {
     (void)width;
+    if (format == VAW_FORMAT_NV12_TO_BGR24) return 0;  // two formats: ask for VAW_FORMAT_NV12 (source) or VAW_FORMAT_BGR24 (output)
     if (format == VAW_FORMAT_NV12) return (size_t)pitch * (size_t)(height + height / 2);
     return (size_t)pitch * (size_t)height;
 }
@@ -603,11 +608,15 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
         return fail(nullptr, VAW_ERR_UNSUPPORTED, "only INTER_NEAREST, INTER_LINEAR, INTER_CUBIC and INTER_LANCZOS4 are implemented");
     if (p.interpolation != VAW_INTER_LINEAR && p.variant != VAW_VARIANT_AUTO && p.variant != VAW_VARIANT_GATHER)
         return fail(nullptr, VAW_ERR_UNSUPPORTED, "INTER_NEAREST, INTER_CUBIC and INTER_LANCZOS4 run on variant GATHER (or AUTO)");
-    if (p.format != VAW_FORMAT_NV12 && p.format != VAW_FORMAT_BGR24 && p.format != VAW_FORMAT_GRAY8)
+    if (p.format != VAW_FORMAT_NV12 && p.format != VAW_FORMAT_BGR24 && p.format != VAW_FORMAT_GRAY8 &&
+        p.format != VAW_FORMAT_NV12_TO_BGR24)
         return fail(nullptr, VAW_ERR_INVALID, "unknown pixel format");
+    if (p.format == VAW_FORMAT_NV12_TO_BGR24 && (p.interpolation != VAW_INTER_LINEAR ||
+                                                  (p.variant != VAW_VARIANT_AUTO && p.variant != VAW_VARIANT_POLY)))
+        return fail(nullptr, VAW_ERR_UNSUPPORTED, "NV12 -> BGR24 in one launch: INTER_LINEAR, variant AUTO or POLY");
     if (p.variant < VAW_VARIANT_AUTO || p.variant > VAW_VARIANT_TEX)
         return fail(nullptr, VAW_ERR_UNSUPPORTED, "kernel variant not available in this build");
-    if (p.variant >= VAW_VARIANT_POLY && p.format != VAW_FORMAT_NV12)
+    if (p.variant >= VAW_VARIANT_POLY && p.format != VAW_FORMAT_NV12 && p.format != VAW_FORMAT_NV12_TO_BGR24)
         return fail(nullptr, VAW_ERR_UNSUPPORTED, "variants POLY, TILED, PIPE and TEX exist for NV12 only");
     // `short` indices in createMap.cl:10-11 and int16 taps in cv::remap cap both sizes
     if (p.src_width < 2 || p.src_height < 2 || p.out_width < 1 || p.out_height < 1 ||
@@ -616,6 +625,8 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
     if (p.format == VAW_FORMAT_NV12 &&
         ((p.src_width | p.src_height | p.out_width | p.out_height) & 1))
         return fail(nullptr, VAW_ERR_INVALID, "NV12 sizes must be even");
+    if (p.format == VAW_FORMAT_NV12_TO_BGR24 && ((p.src_width | p.src_height) & 1))
+        return fail(nullptr, VAW_ERR_INVALID, "NV12 source sizes must be even");
 
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
@@ -628,7 +639,10 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
     if (!ctx) return fail(nullptr, VAW_ERR_NOMEM, "out of host memory");
     ctx->p = p;
     ctx->device = device;
-    ctx->channels = p.format == VAW_FORMAT_BGR24 ? 3 : 1;
+    ctx->src_format = p.format == VAW_FORMAT_NV12_TO_BGR24 ? VAW_FORMAT_NV12 : p.format;
+    ctx->dst_format = p.format == VAW_FORMAT_NV12_TO_BGR24 ? VAW_FORMAT_BGR24 : p.format;
+    ctx->channels = ctx->src_format == VAW_FORMAT_BGR24 ? 3 : 1;
+    ctx->dst_channels = ctx->dst_format == VAW_FORMAT_BGR24 ? 3 : 1;
     vaw::Geom& g = ctx->g;
     g.scx = (float)p.src_center_x; g.scy = (float)p.src_center_y;   // FrameSourceWarp.cpp:283-284
     g.sfx = (float)p.src_focal_x;  g.sfy = (float)p.src_focal_y;    // :285-286
@@ -648,8 +662,8 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
         if (!(std::fabs(g.kd[i]) <= 10.0f)) { delete ctx; return fail(nullptr, VAW_ERR_INVALID, "distortion coefficient out of range (|k| <= 10)"); }
         if (g.kd[i] != 0.0f) g.has_dist = 1;
     }
-    ctx->src_frame_bytes = vaw_frame_bytes(p.format, p.src_width, p.src_height, p.src_width * ctx->channels);
-    ctx->dst_frame_bytes = vaw_frame_bytes(p.format, p.out_width, p.out_height, p.out_width * ctx->channels);
+    ctx->src_frame_bytes = vaw_frame_bytes(ctx->src_format, p.src_width, p.src_height, p.src_width * ctx->channels);
+    ctx->dst_frame_bytes = vaw_frame_bytes(ctx->dst_format, p.out_width, p.out_height, p.out_width * ctx->dst_channels);
 
     DeviceGuard dg(device);
     const int n_x = ((p.out_width + 127) / 128) * 128 + 4, n_y = ((p.out_height + 15) / 16) * 16 + 2;
@@ -674,7 +688,8 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
         return rc;
     }
     ctx->variant = p.variant != VAW_VARIANT_AUTO ? p.variant
-                   : (p.format == VAW_FORMAT_NV12 && p.interpolation == VAW_INTER_LINEAR ? VAW_VARIANT_TILED : VAW_VARIANT_GATHER);
+                   : (p.format == VAW_FORMAT_NV12_TO_BGR24 ? VAW_VARIANT_POLY
+                      : (p.format == VAW_FORMAT_NV12 && p.interpolation == VAW_INTER_LINEAR ? VAW_VARIANT_TILED : VAW_VARIANT_GATHER));
     if (ctx->variant != VAW_VARIANT_GATHER) {
         // rows per piece: keep the cubic-in-v truncation error ~ 2.4e-3 * f_in * (PH / f_out)^4 px
         // (measured on the BASELINE geometries) below the certificate's 5e-5 px
@@ -826,14 +841,14 @@ int vaw_warp_batch(vaw_ctx* ctx, const uint8_t* src, int src_pitch, size_t src_f
     if (rc) return rc;
     if (n_frames < 0 || (n_frames > 0 && !rotations)) return fail(ctx, VAW_ERR_INVALID, "bad batch");
     if (n_frames == 0) return VAW_OK;
-    if (ctx->p.format == VAW_FORMAT_NV12 && (src_frame_stride & 1))
+    if (ctx->src_format == VAW_FORMAT_NV12 && (src_frame_stride & 1))
         return fail(ctx, VAW_ERR_INVALID, "NV12 frame stride must be even");
     if (n_frames > 1) {
         // output frames must not overlap (a zero or short stride would make frames overwrite each other);
         // source frames may repeat (stride 0 = the same frame under n rotations) but not interleave
-        const size_t out_rows = ctx->p.format == VAW_FORMAT_NV12 ? (size_t)ctx->p.out_height * 3 / 2 : (size_t)ctx->p.out_height;
-        const size_t src_rows = ctx->p.format == VAW_FORMAT_NV12 ? (size_t)ctx->p.src_height * 3 / 2 : (size_t)ctx->p.src_height;
-        const size_t dst_need = (out_rows - 1) * (size_t)dst_pitch + (size_t)ctx->p.out_width * ctx->channels;
+        const size_t out_rows = ctx->dst_format == VAW_FORMAT_NV12 ? (size_t)ctx->p.out_height * 3 / 2 : (size_t)ctx->p.out_height;
+        const size_t src_rows = ctx->src_format == VAW_FORMAT_NV12 ? (size_t)ctx->p.src_height * 3 / 2 : (size_t)ctx->p.src_height;
+        const size_t dst_need = (out_rows - 1) * (size_t)dst_pitch + (size_t)ctx->p.out_width * ctx->dst_channels;
         const size_t src_need = (src_rows - 1) * (size_t)src_pitch + (size_t)ctx->p.src_width * ctx->channels;
         if (dst_frame_stride < dst_need)
             return fail(ctx, VAW_ERR_INVALID, "dst_frame_stride smaller than one output frame");
@@ -853,7 +868,7 @@ int vaw_bind_clip(vaw_ctx* ctx, const uint8_t* base, int pitch, size_t frame_str
         return VAW_OK;
     }
     if (n_slots < 1 || pitch < ctx->p.src_width * ctx->channels ||
-        frame_stride < vaw_frame_bytes(ctx->p.format, ctx->p.src_width, ctx->p.src_height, pitch))
+        frame_stride < vaw_frame_bytes(ctx->src_format, ctx->p.src_width, ctx->p.src_height, pitch))
         return fail(ctx, VAW_ERR_INVALID, "bad clip layout");
     ctx->clip_base = base; ctx->clip_pitch = pitch; ctx->clip_stride = frame_stride; ctx->clip_slots = n_slots;
     return VAW_OK;
@@ -884,7 +899,7 @@ int vaw_warp_batch_host(vaw_ctx* ctx, const uint8_t* src_host, uint8_t* dst_host
     int rc = init_host_path(ctx);
     if (rc) return rc;
     const size_t sfb = ctx->src_frame_bytes, dfb = ctx->dst_frame_bytes;
-    const int src_pitch = ctx->p.src_width * ctx->channels, dst_pitch = ctx->p.out_width * ctx->channels;
+    const int src_pitch = ctx->p.src_width * ctx->channels, dst_pitch = ctx->p.out_width * ctx->dst_channels;
     // Pinned (page-locked) user buffers are copied from/to directly; pageable ones go
     // through lazily allocated pinned staging so that the copies stay asynchronous.
     const bool src_pinned = is_pinned(src_host), dst_pinned = is_pinned(dst_host);
@@ -952,7 +967,7 @@ int vaw_dump_coords(vaw_ctx* ctx, const double rotation[9], int plane, float* ma
 {
     if (!ctx) return VAW_ERR_INVALID;
     if (!rotation || !map_x || !map_y) return fail(ctx, VAW_ERR_INVALID, "null argument");
-    if (plane != 0 && !(plane == 1 && ctx->p.format == VAW_FORMAT_NV12))
+    if (plane != 0 && !(plane == 1 && ctx->p.format == VAW_FORMAT_NV12))  // (NV12 -> BGR24 samples the converted image with the luma map only)
         return fail(ctx, VAW_ERR_INVALID, "plane 1 exists for NV12 only");
     const int need = plane ? ctx->p.out_width / 2 : ctx->p.out_width;
     if (map_pitch < need) return fail(ctx, VAW_ERR_INVALID, "map pitch smaller than a row");

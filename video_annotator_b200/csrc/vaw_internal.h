@@ -31,6 +31,10 @@ cudaError_t launch_warp_packed_gather(const Geom& g, const FrameBatch& b, int ch
 // Fused map + remap, NV12, coordinates from the per-piece polynomial table (variant POLY).
 cudaError_t launch_warp_nv12_poly(const Geom& g, const FrameBatch& b, const PieceRec* table, cudaStream_t st);
 
+// NV12 in, BGR24 out in one launch (vaw_bgr.cu): cvtColor(COLOR_YUV2BGR_NV12) + 3-channel remap, coordinates
+// from the piece table.
+cudaError_t launch_warp_nv12_to_bgr(const Geom& g, const FrameBatch& b, const PieceRec* table, cudaStream_t st);
+
 // Variant TILED (vaw_tile.cu): tensor maps over the NV12 clip, viewed as a 3-D tensor of 4-byte
 // elements (pitch/4 x 3H/2 rows x frames), one per tile row pitch (box = pitch/4 x 8 rows).
 constexpr int kTileMinPitch = kStageMinPitch, kTileMaxPitch = kStageMaxPitch, kTilePitchStep = 32;

@@ -20,6 +20,7 @@
 #include "vaw_sample.cuh"
 #include "vaw_cubic.cuh"
 #include "vaw_synth.cuh"
+#include "vaw_cvt.cuh"
 
 namespace vaw {
 
@@ -287,16 +288,6 @@ cudaError_t launch_remap(const uint8_t* src, int src_w, int src_h, int src_pitch
 // A thread converts 4 x 2 luma samples (two UV pairs): two 4-byte luma loads, one 4-byte chroma
 // load, six 4-byte stores; a warp row is 128 pixels = 384 contiguous output bytes.  HBM-bound:
 // 1.5 bytes in, 3 bytes out per pixel.
-__device__ __forceinline__ unsigned sat8(int v) { return (unsigned)min(max(v, 0), 255); }
-
-__device__ __forceinline__ void yuv_pixel(int y, int u, int v, unsigned& b, unsigned& g, unsigned& r)
-{
-    const int yy = max(y - 16, 0) * 1220542 + (1 << 19);
-    b = sat8((yy + 2116026 * u) >> 20);
-    g = sat8((yy - 852492 * v - 409993 * u) >> 20);
-    r = sat8((yy + 1673527 * v) >> 20);
-}
-
 __global__ void __launch_bounds__(256)
 nv12_to_bgr_kernel(const uint8_t* __restrict__ src, int w, int h, int src_pitch, size_t src_stride,
                    uint8_t* __restrict__ dst, int dst_pitch, size_t dst_stride, int aligned)

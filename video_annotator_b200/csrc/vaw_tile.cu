@@ -248,7 +248,6 @@ warp_nv12_tile_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
 //   - per row pair a lane makes 2 x 2 luma samples and the one chroma sample of that quad; a warp
 //     store writes 64 contiguous bytes, the LDS of a warp stay within one 128-byte window per row
 //     exactly as with the round-1 pair mapping (2 columns per lane).
-constexpr int kQuadCtas = 8;          // resident CTAs per SM the kernel is compiled for (64 registers)
 constexpr int kQuadTileOffset = 128;  // [mbarrier | tile (TMA: 128-byte aligned)]
 
 struct ColPoly2 {
@@ -349,7 +348,11 @@ __device__ __forceinline__ void rows_quad(const Geom& g, const ColPoly2& cp, uns
     }
 }
 
-__global__ void __launch_bounds__(32 * kWarps, kQuadCtas)
+// kCtas = resident CTAs per SM the instantiation is compiled for: 8 (64 registers) where the tiles are small
+// enough for seven or eight CTAs to share an SM, 6 (80 registers, no spills in the fallback paths, fewer
+// rematerialised constants) where shared memory allows six or fewer anyway (measured: C5 +2.6 %, C2 +3 %).
+template <int kCtas>
+__global__ void __launch_bounds__(32 * kWarps, kCtas)
 warp_nv12_quad_kernel(const Geom g, const FrameBatch b, const PieceRec* __restrict__ table,
                       const __grid_constant__ TileMaps maps)
 {
@@ -542,10 +545,14 @@ cudaError_t launch_warp_nv12_tile(const Geom& g, const FrameBatch& b, const Piec
         cudaError_t e = cudaFuncSetAttribute(warp_nv12_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              tile_smem_bytes(kTileCapMax, 1));
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(warp_nv12_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            e = cudaFuncSetAttribute(warp_nv12_quad_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      tile_smem_bytes(kTileCapMax, 2));
-        if (e == cudaSuccess)  // all of the SM's shared memory for tiles: the taps never go through L1
-            e = cudaFuncSetAttribute(warp_nv12_quad_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(warp_nv12_quad_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     tile_smem_bytes(kTileCapMax, 2));
+        // all of the SM's shared memory for tiles: the taps never go through L1
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(warp_nv12_quad_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(warp_nv12_quad_kernel<6>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         if (e != cudaSuccess) return e;
         if (tracked) configured[dev].store(true, std::memory_order_release);
     }
@@ -553,8 +560,10 @@ cudaError_t launch_warp_nv12_tile(const Geom& g, const FrameBatch& b, const Piec
     dim3 grid(pieces_x(g.out_w), pieces_y(g.out_h, g.piece_h), b.n_frames);
     if (maps.kernel == 1)
         warp_nv12_tile_kernel<<<grid, block, tile_smem_bytes(maps.tile_cap, 1), st>>>(g, b, table, maps);
+    else if (maps.tile_cap <= tile_cap_for_ctas(7, kQuadTileOffset))
+        warp_nv12_quad_kernel<8><<<grid, block, tile_smem_bytes(maps.tile_cap, 2), st>>>(g, b, table, maps);
     else
-        warp_nv12_quad_kernel<<<grid, block, tile_smem_bytes(maps.tile_cap, 2), st>>>(g, b, table, maps);
+        warp_nv12_quad_kernel<6><<<grid, block, tile_smem_bytes(maps.tile_cap, 2), st>>>(g, b, table, maps);
     return cudaGetLastError();
 }
 

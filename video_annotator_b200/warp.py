@@ -11,7 +11,7 @@ import numpy as np
 
 from . import _lib
 
-FORMAT_NV12, FORMAT_BGR24, FORMAT_GRAY8 = 0, 1, 2
+FORMAT_NV12, FORMAT_BGR24, FORMAT_GRAY8, FORMAT_NV12_TO_BGR24 = 0, 1, 2, 3
 INTER_NEAREST = 0
 INTER_LINEAR = 1
 INTER_CUBIC = 2
@@ -116,7 +116,8 @@ class WarpContext:
         self.params = p
         self.fmt = fmt
         self.device = device
-        self.channels = 3 if fmt == FORMAT_BGR24 else 1
+        self.channels = 3 if fmt == FORMAT_BGR24 else 1              # of a source row
+        self.dst_channels = 3 if fmt in (FORMAT_BGR24, FORMAT_NV12_TO_BGR24) else 1
         h = C.c_void_p()
         _check(lib.vaw_create(C.byref(p), device, C.byref(h)))
         self._h = h
@@ -131,15 +132,23 @@ class WarpContext:
     def out_size(self):
         return self.params.out_width, self.params.out_height
 
+    def _side(self, which):
+        # (format, channels) of the source or the output side (they differ for FORMAT_NV12_TO_BGR24)
+        if self.fmt == FORMAT_NV12_TO_BGR24:
+            return (FORMAT_NV12, 1) if which == "src" else (FORMAT_BGR24, 3)
+        return self.fmt, self.channels
+
     def frame_bytes(self, which):
         w, h = self.src_size if which == "src" else self.out_size
-        return self._lib.vaw_frame_bytes(self.fmt, w, h, w * self.channels)
+        fmt, cn = self._side(which)
+        return self._lib.vaw_frame_bytes(fmt, w, h, w * cn)
 
     def frame_shape(self, which):
         w, h = self.src_size if which == "src" else self.out_size
-        if self.fmt == FORMAT_NV12:
+        fmt, _ = self._side(which)
+        if fmt == FORMAT_NV12:
             return (h * 3 // 2, w)
-        return (h, w, 3) if self.fmt == FORMAT_BGR24 else (h, w)
+        return (h, w, 3) if fmt == FORMAT_BGR24 else (h, w)
 
     @property
     def variant(self):
@@ -158,7 +167,7 @@ class WarpContext:
         """warp_frame(input, rotation), FrameSourceWarp.cpp:272-314.  src/dst: CUDA uint8 tensors."""
         _, rp = _rot_arg(rotation)
         sp = src_pitch or self.src_size[0] * self.channels
-        dp = dst_pitch or self.out_size[0] * self.channels
+        dp = dst_pitch or self.out_size[0] * self.dst_channels
         _check(self._lib.vaw_warp(self._h, src.data_ptr(), sp, dst.data_ptr(), dp, rp,
                                   _stream_handle(stream)), self._h)
         return dst
@@ -173,7 +182,7 @@ class WarpContext:
     def warp_batch(self, src, dst, rotations_dev, n_frames, stream=None, src_pitch=None,
                    dst_pitch=None, src_stride=None, dst_stride=None):
         sp = src_pitch or self.src_size[0] * self.channels
-        dp = dst_pitch or self.out_size[0] * self.channels
+        dp = dst_pitch or self.out_size[0] * self.dst_channels
         ss = src_stride if src_stride is not None else self.frame_bytes("src")
         ds = dst_stride if dst_stride is not None else self.frame_bytes("dst")
         _check(self._lib.vaw_warp_batch(self._h, src.data_ptr(), sp, ss, dst.data_ptr(), dp, ds,
