@@ -254,6 +254,13 @@ int vaw_sync(int device, void *stream);
  * warps its own range of a host-resident clip through the pinned-staging pipeline of
  * vaw_warp_batch_host.  `devices` = CUDA ordinals (NULL: 0 .. n_devices-1). */
 int vaw_shard_range(int n_frames, int n_parts, int part, int *first, int *count);
+/* Placement of the host threads that stage frames for a device (Linux): the NUMA node the device's PCIe
+ * root hangs off (-1: unknown / single node), and "bind the CALLING thread to that node's CPUs" (returns
+ * the number of CPUs bound to, 0 if nothing was changed).  Pinned staging buffers allocated by a bound
+ * thread are first-touched on the device's node, so H2D / D2H traffic does not cross the socket link.
+ * vaw_clip_warp_host binds its per-device worker threads this way. */
+int vaw_device_numa_node(int device);
+int vaw_bind_thread_to_device(int device);
 typedef struct vaw_clip vaw_clip;
 int vaw_clip_create(const vaw_params *params, int n_devices, const int *devices, vaw_clip **out);
 void vaw_clip_destroy(vaw_clip *clip);

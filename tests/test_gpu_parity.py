@@ -637,12 +637,21 @@ def test_clip_scheduler_frame_parallel(V, oracle):
     want = np.zeros((n,) + ctx.frame_shape("dst"), np.uint8)
     ctx.warp_batch_host(src_np, want, rots)
     ndev = torch.cuda.device_count()
-    devices = [0, 1 % ndev, 0]                       # three shards: 4 + 4 + 3 frames
+    devices = [0, 1 % ndev, 0] if ndev < 3 else [0, 1, 2]   # three shards: 4 + 4 + 3 frames
     clip = V.ClipWarper(ctx.params, devices)
     got = np.zeros_like(want)
     clip.warp_host(src_np, got, rots)
     assert np.array_equal(got, want)
     clip.close()
+    if ndev > 1:  # one shard per distinct device, every device of the box
+        clip = V.ClipWarper(ctx.params, list(range(ndev)))
+        got = np.zeros_like(want)
+        clip.warp_host(src_np, got, rots)
+        assert np.array_equal(got, want)
+        clip.close()
+    _record("clip_scheduler_devices", {"visible": ndev, "devices_three_shards": devices,
+                                       "all_devices_run": ndev > 1,
+                                       "numa_nodes": [int(V.load().vaw_device_numa_node(d)) for d in range(ndev)]})
     ctx.close()
 
 

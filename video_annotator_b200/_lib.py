@@ -67,6 +67,8 @@ SIGNATURES = {
     "vaw_kernel_times": (C.c_int, [C.c_void_p, C.c_int, f32p, f32p, C.POINTER(C.c_int)]),
     "vaw_kernel_times_split": (C.c_int, [C.c_void_p, C.c_int, f32p, f32p, C.POINTER(C.c_int)]),
     "vaw_shard_range": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "vaw_device_numa_node": (C.c_int, [C.c_int]),
+    "vaw_bind_thread_to_device": (C.c_int, [C.c_int]),
     "vaw_clip_create": (C.c_int, [C.POINTER(VawParams), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p)]),
     "vaw_clip_destroy": (None, [C.c_void_p]),
     "vaw_clip_warp_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, f64p, C.c_int]),

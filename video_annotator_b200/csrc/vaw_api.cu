@@ -8,8 +8,11 @@
 // There is no CPU fallback anywhere in this file.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <sched.h>
+#include <cctype>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -1064,6 +1067,64 @@ int vaw_kernel_times_split(vaw_ctx* ctx, int max_launches, float* tex_ms, float*
     }
     *n_out = (int)n;
     return VAW_OK;
+}
+
+// ---- placement of host-staging threads ----------------------------------------------------------------
+namespace {
+// "a-b,c,d-e" -> CPU set
+bool parse_cpulist(const char* text, cpu_set_t* set)
+{
+    CPU_ZERO(set);
+    int n = 0;
+    const char* p = text;
+    while (*p) {
+        char* end = nullptr;
+        long a = std::strtol(p, &end, 10);
+        if (end == p) break;
+        long b = a;
+        p = end;
+        if (*p == '-') { b = std::strtol(p + 1, &end, 10); p = end; }
+        for (long c = a; c <= b && c < CPU_SETSIZE; ++c) { CPU_SET((int)c, set); ++n; }
+        if (*p == ',') ++p; else break;
+    }
+    return n > 0;
+}
+
+bool read_small_file(const std::string& path, std::string* out)
+{
+    FILE* f = std::fopen(path.c_str(), "r");
+    if (!f) return false;
+    char buf[4096];
+    const size_t n = std::fread(buf, 1, sizeof buf - 1, f);
+    std::fclose(f);
+    buf[n] = 0;
+    *out = buf;
+    return true;
+}
+}  // namespace
+
+int vaw_device_numa_node(int device)
+{
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) { cudaGetLastError(); return -1; }
+    for (char* c = bus; *c; ++c) *c = (char)std::tolower((unsigned char)*c);
+    std::string text;
+    if (!read_small_file(std::string("/sys/bus/pci/devices/") + bus + "/numa_node", &text)) return -1;
+    return std::atoi(text.c_str());
+}
+
+int vaw_bind_thread_to_device(int device)
+{
+    const int node = vaw_device_numa_node(device);
+    if (node < 0) return 0;  // no NUMA information (single node, VM): nothing to do
+    std::string text;
+    if (!read_small_file("/sys/devices/system/node/node" + std::to_string(node) + "/cpulist", &text)) return 0;
+    cpu_set_t want, have, both;
+    if (!parse_cpulist(text.c_str(), &want)) return 0;
+    if (sched_getaffinity(0, sizeof have, &have) != 0) return 0;
+    CPU_AND(&both, &want, &have);
+    if (CPU_COUNT(&both) == 0) return 0;
+    return sched_setaffinity(0, sizeof both, &both) == 0 ? CPU_COUNT(&both) : 0;
 }
 
 int vaw_shard_range(int n_frames, int n_parts, int part, int* first, int* count)

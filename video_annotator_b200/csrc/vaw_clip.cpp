@@ -5,7 +5,8 @@
 // has its rotation the frames are independent (FrameSourceWarp.cpp:272-314), so the clip is cut
 // into contiguous ranges, one per device, and every device runs the host-buffer pipeline of
 // vaw_warp_batch_host (pinned staging, H2D -> warp -> D2H on its own streams) from its own
-// host thread.  No collective, no peer traffic: NCCL has nothing to do on this path.
+// host thread, bound to the CPUs of that device's NUMA node (so the pinned staging it allocates is
+// local to the device's PCIe root).  No collective, no peer traffic: NCCL has nothing to do on this path.
 #include <cstdint>
 #include <new>
 #include <string>
@@ -70,9 +71,11 @@ int vaw_clip_warp_host(vaw_clip* clip, const uint8_t* src_host, uint8_t* dst_hos
         return VAW_ERR_INVALID;
     }
     const int n = (int)clip->ctx.size();
-    const int ch = clip->p.format == VAW_FORMAT_BGR24 ? 3 : 1;
-    const size_t sfb = vaw_frame_bytes(clip->p.format, clip->p.src_width, clip->p.src_height, clip->p.src_width * ch);
-    const size_t dfb = vaw_frame_bytes(clip->p.format, clip->p.out_width, clip->p.out_height, clip->p.out_width * ch);
+    const int sfmt = clip->p.format == VAW_FORMAT_NV12_TO_BGR24 ? VAW_FORMAT_NV12 : clip->p.format;
+    const int dfmt = clip->p.format == VAW_FORMAT_NV12_TO_BGR24 ? VAW_FORMAT_BGR24 : clip->p.format;
+    const int sch = sfmt == VAW_FORMAT_BGR24 ? 3 : 1, dch = dfmt == VAW_FORMAT_BGR24 ? 3 : 1;
+    const size_t sfb = vaw_frame_bytes(sfmt, clip->p.src_width, clip->p.src_height, clip->p.src_width * sch);
+    const size_t dfb = vaw_frame_bytes(dfmt, clip->p.out_width, clip->p.out_height, clip->p.out_width * dch);
     std::vector<int> rc(n, VAW_OK);
     std::vector<std::thread> th;
     for (int i = 0; i < n; ++i) {
@@ -80,6 +83,7 @@ int vaw_clip_warp_host(vaw_clip* clip, const uint8_t* src_host, uint8_t* dst_hos
         vaw_shard_range(n_frames, n, i, &first, &count);
         if (count == 0) continue;
         th.emplace_back([=, &rc]() {
+            vaw_bind_thread_to_device(clip->device[i]);  // before the first pinned allocation of this context
             rc[i] = vaw_warp_batch_host(clip->ctx[i], src_host + (size_t)first * sfb, dst_host + (size_t)first * dfb,
                                         rotations_host + (size_t)first * 9, count);
         });

@@ -16,6 +16,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -71,16 +72,22 @@ class GyroRotationSource : public RotationSource {
     }
 };
 
-// FrameSourceWarp that also reports the rotation each frame was warped with.
+// FrameSourceWarp that also reports the rotation each frame was warped with (by frame index: with batched
+// look-ahead warping several frames are warped before the first of them is handed out).
 class ReportingWarp : public FrameSourceWarp {
   public:
     using FrameSourceWarp::FrameSourceWarp;
-    Mat33 last_rotation = Mat33::eye();
+    std::map<long, Mat33> rotation_of;
   protected:
     Frame warp_frame(Frame input, const Mat33& rotation) override
     {
-        last_rotation = rotation;
+        rotation_of[input->index] = rotation;
         return FrameSourceWarp::warp_frame(input, rotation);
+    }
+    std::vector<Frame> warp_frames(const std::vector<Frame>& inputs, const std::vector<Mat33>& rotations) override
+    {
+        for (size_t i = 0; i < inputs.size(); ++i) rotation_of[inputs[i]->index] = rotations[i];
+        return FrameSourceWarp::warp_frames(inputs, rotations);
     }
 };
 
@@ -202,7 +209,8 @@ int main(int argc, char* argv[])
                 std::vector<uint8_t> host(frame->bytes);
                 if (vaw_memcpy(frame->device, host.data(), frame->data, frame->bytes, 0, nullptr) != VAW_OK) throw -1;
                 std::printf("frame %ld crc %08x rot", frame->index, crc32(host));
-                for (double v : warped->last_rotation.m) std::printf(" %.17g", v);
+                for (double v : warped->rotation_of[frame->index].m) std::printf(" %.17g", v);
+                warped->rotation_of.erase(frame->index);
                 std::printf("\n");
                 ++emitted;
             } catch (int err) {
