@@ -79,6 +79,8 @@ def parse_args():
     ap.add_argument("--no-shim", action="store_true")
     ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to its GPU's NUMA node")
     ap.add_argument("--no-split-builder", action="store_true")
+    ap.add_argument("--host-stages", type=int, default=0, help="chunks in flight of the host-buffer pipeline (0 = library default)")
+    ap.add_argument("--host-chunk-mb", type=int, default=0, help="MiB of source frames per chunk of the host-buffer pipeline (0 = default)")
     ap.add_argument("--fused-bgr", action="store_true",
                     help="NV12 in, BGR24 out in one launch (cvtColor + 3-channel remap, SURVEY 8 f2) instead of NV12 -> NV12")
     ap.add_argument("--tile-kernel", type=int, default=0, help="A/B: 1 = the round-1 tile kernel, 2 = the quadrant kernel (default)")
@@ -469,6 +471,10 @@ def run_ours(args):
         ctx.set_option("split_builder", 0)
     if args.tile_kernel:
         ctx.set_option("tile_kernel", args.tile_kernel)
+    if args.host_stages:
+        ctx.set_option("host_stages", args.host_stages)
+    if args.host_chunk_mb:
+        ctx.set_option("host_chunk_mb", args.host_chunk_mb)
     # this rank's contiguous frame range of the clip, with its rotations
     rots = wl.rotations(n, first=100 + first, total=100 + clip_total)
     src = torch.empty((n,) + ctx.frame_shape("src"), dtype=torch.uint8, device=dev)

@@ -312,6 +312,11 @@ int vaw_kernel_times_split(vaw_ctx *ctx, int max_launches, float *tex_ms, float 
  * context's tile capacity (bytes), pieces that exceed it (they gather from global memory), 0}.
  * All zero for GATHER. */
 int vaw_piece_stats(vaw_ctx *ctx, const double rotation[9], uint32_t counts[8], void *stream);
+/* The flags of every piece for `rotation`, row-major (pieces_y x pieces_x pieces of 128 x piece_h pixels):
+ * bit 0 = certified polynomial coordinates (else the piece is evaluated per pixel, op for op), bit 1 = every
+ * tap inside the source, bit 2 = every tap outside (border fill).  For the accuracy sweeps of the tests. */
+int vaw_piece_flags(vaw_ctx *ctx, const double rotation[9], uint32_t *flags, int capacity, int *pieces_x_out,
+                    int *pieces_y_out, int *piece_h_out, void *stream);
 int vaw_selftest_math(int device, uint32_t seed, uint64_t n_per_thread, uint64_t mismatches[4]);
 /* Instrumented builds only (-DVAW_BOUNDS_CHECK): number of shared-memory tap addresses of variant
  * TILED that fell outside their staged tile since the library was loaded; -1 in a normal build. */

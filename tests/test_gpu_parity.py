@@ -164,6 +164,94 @@ def test_coordinates_poly_variant(V, oracle, name, rot):
     ctx.close()
 
 
+def _exact_map_f64_dist(k, R, rows, cols):
+    """createMap.cl:15-49 in float64 with the cv::fisheye distortion step (zeros = the reference's map);
+    also returns q.z (the regularity of the projection)."""
+    r = np.asarray(R, np.float64).reshape(9).astype(np.float32).astype(np.float64).reshape(3, 3)
+    u, v = np.meshgrid(np.arange(cols, dtype=np.float64), np.arange(rows, dtype=np.float64))
+    x = (u - k.map_center_x) / k.map_focal_x
+    y = (v - k.map_center_y) / k.map_focal_y
+    q = [r[i, 0] * x + r[i, 1] * y + r[i, 2] for i in range(3)]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        c0, c1 = q[0] / q[2], q[1] / q[2]
+        rad = np.sqrt(c0 * c0 + c1 * c1)
+        th = np.arctan(rad)
+        t2 = th * th
+        d = [float(v) for v in k.dist[:]]
+        th = th * (1.0 + t2 * (d[0] + t2 * (d[1] + t2 * (d[2] + t2 * d[3]))))
+        kk = th / rad
+    return k.src_center_x + c0 * kk * k.src_focal_x, k.src_center_y + c1 * kk * k.src_focal_y, q[2]
+
+
+def test_certificate_sweep_random_geometries(V, oracle):
+    """Seeded sweep over geometries the BASELINE cases do not reach: rotations to +-45 degrees per axis,
+    f_out / f_in from 0.3 to 3, 1080p to 5.3K sources, fisheye distortion on and off.  Two bars:
+      (A) wherever a piece took the CERTIFIED polynomial path, the coordinate is within half an fp32 ulp +
+          2e-4 px of the exact (float64) projection -- i.e. the builder's three-point accuracy certificate
+          (5e-5 px) did not let a bad piece through;
+      (B) every coordinate of a regular ray (q.z > 0.05) is within 1e-3 px (3 ulp where one ulp is already
+          4.9e-4 px) of createMap.cl itself (oracle/_ref; the port when the distortion extension is on).
+    The worst certified piece and the piece statistics are recorded (gpurun_out/parity.json)."""
+    rng = np.random.default_rng(20260003)
+    n_cases = int(os.environ.get("VAW_SWEEP_CASES", "520"))
+    sources = [(1920, 1080), (2704, 1520), (3840, 2160), (5312, 2988)]
+    worst = {"excess_px": -1.0}
+    stats = {"cases": 0, "pieces": 0, "certified": 0, "per_pixel": 0, "max_err_vs_reference_px": 0.0, "checked_px": 0}
+    for case in range(n_cases):
+        sw, sh = sources[case % 4]
+        cam0 = V.get_preset_camera(V.warp.GOPRO_H4B_WIDE169_MEASURED, sw, sh)
+        dist = None
+        if case % 3 == 2:
+            dist = rng.uniform(-1.0, 1.0, 4) * np.array([0.06, 0.02, 0.01, 0.004])
+        cin = V.Camera.from_matrix(cam0.K, sw, sh, model=1, distortion=dist)
+        ratio = float(np.exp(rng.uniform(np.log(0.3), np.log(3.0))))
+        f_out = cam0.K[0, 0] * ratio
+        ow, oh = 2 * int(rng.integers(192, 704)), 2 * int(rng.integers(96, 416))
+        centre = ((ow - 1) / 2.0 + float(rng.uniform(-40, 40)), (oh - 1) / 2.0 + float(rng.uniform(-40, 40)))
+        cout = V.Camera.from_matrix([[f_out, 0, centre[0]], [0, f_out * float(rng.uniform(0.97, 1.03)), centre[1]], [0, 0, 1]], ow, oh)
+        scale = 45.0 if case % 2 else 8.0          # half the cases in the stabiliser's range, half far outside
+        rot = rng.uniform(-scale, scale, 3)
+        R = rotation_xyz(*rot)
+        ctx = V.WarpContext(cin, cout, out_size=(ow, oh), variant=POLY)
+        mx, my = [t.cpu().numpy() for t in ctx.dump_coords(R, 0)]
+        flags, ph = ctx.piece_flags(R)
+        ctx.close()
+        k = oracle.intrinsics(cin.K, cout.K, dist=dist)
+        ex, ey, qz = _exact_map_f64_dist(k, R, oh, ow)
+        ox, oy, _ = oracle.reference_create_map(k, R, oh, ow, threads=NCPU)
+        cert = np.kron((flags & 1).astype(bool), np.ones((ph, 128), bool))[:oh, :ow]
+        stats["cases"] += 1
+        stats["pieces"] += int(flags.size)
+        stats["certified"] += int((flags & 1).sum())
+        stats["per_pixel"] += int(flags.size - (flags & 1).sum())
+        # (A) certified pieces against the exact projection
+        if cert.any():
+            ulp_x = np.spacing(np.abs(mx).astype(np.float32)).astype(np.float64)
+            ulp_y = np.spacing(np.abs(my).astype(np.float32)).astype(np.float64)
+            exc = np.maximum(np.abs(mx - ex) - 0.5 * ulp_x, np.abs(my - ey) - 0.5 * ulp_y)
+            exc = np.where(cert, exc, -1.0)
+            assert not np.isnan(exc[cert]).any(), (case, "NaN inside a certified piece")
+            m = float(exc.max())
+            if m > worst["excess_px"]:
+                iy, ix = np.unravel_index(int(np.argmax(exc)), exc.shape)
+                worst = {"excess_px": m, "case": case, "src": [sw, sh], "out": [ow, oh], "f_ratio": ratio,
+                         "rotation_deg": [float(v) for v in rot], "distortion": None if dist is None else [float(v) for v in dist],
+                         "pixel": [int(ix), int(iy)], "piece": [int(ix) // 128, int(iy) // ph], "piece_h": ph}
+            assert m < 2e-4, worst
+        # (B) every regular ray against createMap.cl
+        reg = (qz > 0.05) & np.isfinite(ox) & np.isfinite(oy) & (np.abs(ox) < 3e4) & (np.abs(oy) < 3e4)
+        assert np.array_equal(np.isnan(mx), np.isnan(ox)), case
+        if reg.any():
+            tol = np.maximum(1e-3, 3.0 * np.spacing(np.maximum(np.abs(ox), np.abs(oy)).astype(np.float32)).astype(np.float64))
+            err = np.maximum(np.abs(mx - ox), np.abs(my - oy))
+            bad = reg & ~(err <= tol)
+            assert not bad.any(), (case, float(err[reg].max()), [float(v) for v in rot], ratio)
+            stats["max_err_vs_reference_px"] = max(stats["max_err_vs_reference_px"], float(err[reg & (np.abs(ox) < 4096) & (np.abs(oy) < 4096)].max(initial=0.0)))
+            stats["checked_px"] += int(reg.sum())
+    _record("certificate_sweep", {"stats": stats, "worst_certified": worst})
+    assert stats["certified"] > 0.5 * stats["pieces"]
+
+
 def test_coordinates_degenerate_geometry(V, oracle):
     """r = 0 -> NaN (createMap.cl:38-39); q.z <= 0 after a large rotation is not guarded (:32-35)."""
     cin = V.Camera.from_matrix([[50.0, 0, 100.0], [0, 50.0, 80.0], [0, 0, 1]], 200, 160, model=1)

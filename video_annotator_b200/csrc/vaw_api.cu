@@ -25,9 +25,9 @@ static_assert(sizeof(vaw_params) == 128 && sizeof(vaw_camera) == 120, "C-ABI str
 
 namespace {
 
-constexpr int kStages = 4;                      // host-path pipeline depth
+constexpr int kStages = 8;                      // host-path pipeline depth: upper bound (ctx->host_stages are used)
 constexpr int kHeadFrames = 8;                  // frames whose table is built in line; the rest overlaps their sampling
-constexpr size_t kChunkBytes = 32u << 20;       // target bytes of source frames per chunk (small: short pipeline fill and drain)
+constexpr size_t kChunkBytes = 32u << 20;       // default target bytes of source frames per chunk (small: short pipeline fill and drain)
 thread_local std::string g_create_error;
 
 struct Stage {
@@ -100,6 +100,8 @@ struct vaw_ctx {
     // host path
     Stage stage[kStages];
     int chunk_frames = 0;
+    int host_stages = 4;                  // chunks in flight (option "host_stages", 2..8)
+    size_t host_chunk_bytes = kChunkBytes;  // option "host_chunk_mb"
     bool host_ready = false;
 };
 
@@ -514,9 +516,10 @@ int init_host_path(vaw_ctx* ctx)
 int init_host_path_impl(vaw_ctx* ctx)
 {
     size_t per = ctx->src_frame_bytes;
-    int cf = (int)(kChunkBytes / per);
+    int cf = (int)(ctx->host_chunk_bytes / per);
     ctx->chunk_frames = cf < 1 ? 1 : (cf > 64 ? 64 : cf);
-    for (Stage& s : ctx->stage) {
+    for (int si = 0; si < ctx->host_stages; ++si) {
+        Stage& s = ctx->stage[si];
         VAW_CUDA(ctx, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         VAW_CUDA(ctx, cudaMalloc(&s.dev_in, ctx->src_frame_bytes * ctx->chunk_frames));
         VAW_CUDA(ctx, cudaMalloc(&s.dev_out, ctx->dst_frame_bytes * ctx->chunk_frames));
@@ -803,6 +806,19 @@ int vaw_set_option(vaw_ctx* ctx, const char* name, int value)
     if (!ctx || !name) return VAW_ERR_INVALID;
     if (!std::strcmp(name, "force_exact")) { ctx->g.force_exact = value ? 1 : 0; return VAW_OK; }
     if (!std::strcmp(name, "split_builder")) { ctx->split_builder = value != 0; return VAW_OK; }
+    if (!std::strcmp(name, "host_stages") || !std::strcmp(name, "host_chunk_mb")) {  // shape of the host-buffer pipeline
+        DeviceGuard dg(ctx->device);
+        if (name[5] == 's') {
+            if (value < 2 || value > kStages) return fail(ctx, VAW_ERR_INVALID, "host_stages is 2..8");
+            free_host_path(ctx);
+            ctx->host_stages = value;
+        } else {
+            if (value < 1 || value > 1024) return fail(ctx, VAW_ERR_INVALID, "host_chunk_mb is 1..1024");
+            free_host_path(ctx);
+            ctx->host_chunk_bytes = (size_t)value << 20;
+        }
+        return VAW_OK;
+    }
     if (!std::strcmp(name, "tile_kernel")) {  // A/B of the two tile kernels (analysis only)
         if (value != 1 && value != 2) return fail(ctx, VAW_ERR_INVALID, "tile_kernel is 1 or 2");
         DeviceGuard dg(ctx->device);
@@ -953,15 +969,15 @@ int vaw_warp_batch_host(vaw_ctx* ctx, const uint8_t* src_host, uint8_t* dst_host
 
     int k = 0;
     for (int first = 0; first < n_frames; first += ctx->chunk_frames, ++k) {
-        Stage& s = ctx->stage[k % kStages];
+        Stage& s = ctx->stage[k % ctx->host_stages];
         if ((rc = drain(s))) return abort_all(rc);
         const int n = n_frames - first < ctx->chunk_frames ? n_frames - first : ctx->chunk_frames;
         s.out_staged = false;
         if ((rc = submit(s, first, n))) return abort_all(rc);
     }
     // drain in submission order
-    for (int i = 0; i < kStages; ++i)
-        if ((rc = drain(ctx->stage[(k + i) % kStages]))) return abort_all(rc);
+    for (int i = 0; i < ctx->host_stages; ++i)
+        if ((rc = drain(ctx->stage[(k + i) % ctx->host_stages]))) return abort_all(rc);
     return VAW_OK;
 }
 
@@ -1162,6 +1178,30 @@ int vaw_piece_stats(vaw_ctx* ctx, const double rotation[9], uint32_t counts[8], 
         if (nb != 0x7fffffff && (uint32_t)nb > counts[4]) counts[4] = (uint32_t)nb;
     }
     counts[5] = (uint32_t)ctx->tile_cap;
+    return VAW_OK;
+}
+
+int vaw_piece_flags(vaw_ctx* ctx, const double rotation[9], uint32_t* flags, int capacity, int* pieces_x_out,
+                    int* pieces_y_out, int* piece_h_out, void* stream)
+{
+    if (!ctx) return VAW_ERR_INVALID;
+    if (!rotation || !flags || !pieces_x_out || !pieces_y_out || !piece_h_out) return fail(ctx, VAW_ERR_INVALID, "null argument");
+    *pieces_x_out = *pieces_y_out = *piece_h_out = 0;
+    if (ctx->variant == VAW_VARIANT_GATHER) return VAW_OK;
+    if ((size_t)capacity < ctx->pieces_per_frame) return fail(ctx, VAW_ERR_INVALID, "flags buffer too small");
+    DeviceGuard dg(ctx->device);
+    const vaw::Rot R = rot_from_double(rotation);
+    cudaError_t e = vaw::launch_build_pieces(ctx->gd, ctx->basis, nullptr, R.r, 1, ctx->dump_table, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "piece table launch");
+    ctx->launches++;
+    std::string host(ctx->pieces_per_frame * sizeof(vaw::PieceRec), '\0');
+    VAW_CUDA(ctx, cudaMemcpyAsync(&host[0], ctx->dump_table, host.size(), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    VAW_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+    const vaw::PieceRec* rec = reinterpret_cast<const vaw::PieceRec*>(host.data());
+    for (size_t i = 0; i < ctx->pieces_per_frame; ++i) flags[i] = rec[i].flags;
+    *pieces_x_out = vaw::pieces_x(ctx->g.out_w);
+    *pieces_y_out = vaw::pieces_y(ctx->g.out_h, ctx->g.piece_h);
+    *piece_h_out = ctx->g.piece_h;
     return VAW_OK;
 }
 

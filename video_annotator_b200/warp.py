@@ -239,6 +239,16 @@ class WarpContext:
         return dict(zip(("pieces", "poly", "interior", "outside", "max_tile_bytes", "tile_cap", "over_cap"),
                         [int(v) for v in out]))
 
+    def piece_flags(self, rotation, stream=None):
+        # (pieces_y, pieces_x) uint32 flags of the 128 x piece_h pieces for this rotation, and piece_h (vaw_piece_flags)
+        cap = ((self.out_size[0] + 127) // 128) * ((self.out_size[1] + 7) // 8)
+        out = np.zeros(cap, np.uint32)
+        nx, ny, ph = C.c_int(0), C.c_int(0), C.c_int(0)
+        _, rp = _rot_arg(rotation)
+        _check(self._lib.vaw_piece_flags(self._h, rp, out.ctypes.data_as(C.POINTER(C.c_uint32)), cap, C.byref(nx), C.byref(ny),
+                                         C.byref(ph), _stream_handle(stream)), self._h)
+        return out[:nx.value * ny.value].reshape(ny.value, nx.value), ph.value
+
     def close(self):
         if getattr(self, "_h", None):
             self._lib.vaw_destroy(self._h)
