@@ -78,12 +78,11 @@ def parse_args():
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-shim", action="store_true")
     ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to its GPU's NUMA node")
-    ap.add_argument("--no-split-builder", action="store_true")
+    ap.add_argument("--split-builder", action="store_true", help="build all but the head frames' piece table on a side stream (measured neutral)")
     ap.add_argument("--host-stages", type=int, default=0, help="chunks in flight of the host-buffer pipeline (0 = library default)")
     ap.add_argument("--host-chunk-mb", type=int, default=0, help="MiB of source frames per chunk of the host-buffer pipeline (0 = default)")
     ap.add_argument("--fused-bgr", action="store_true",
                     help="NV12 in, BGR24 out in one launch (cvtColor + 3-channel remap, SURVEY 8 f2) instead of NV12 -> NV12")
-    ap.add_argument("--tile-kernel", type=int, default=0, help="A/B: 1 = the round-1 tile kernel, 2 = the quadrant kernel (default)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample budget")
     return ap.parse_args()
 
@@ -435,7 +434,7 @@ def shim_bench():
 
 
 KERNEL_NAMES = {1: "warp_nv12_gather_kernel", 2: "warp_nv12_poly_kernel", 3: "warp_nv12_quad_kernel",
-                4: "warp_nv12_pipe_kernel", 5: "warp_nv12_tex_kernel + warp_nv12_tile_kernel"}
+                5: "warp_nv12_tex_kernel + warp_nv12_quad_kernel"}
 
 
 def run_ours(args):
@@ -467,10 +466,8 @@ def run_ours(args):
                         border=(0, 0, 0) if args.fused_bgr else (0, 128, 128), device=local, variant=args.variant,
                         fmt=V.FORMAT_NV12_TO_BGR24 if args.fused_bgr else V.FORMAT_NV12)
     out_frame_bytes = wl.out_size[0] * wl.out_size[1] * 3 if args.fused_bgr else wl.out_frame_bytes
-    if args.no_split_builder:
-        ctx.set_option("split_builder", 0)
-    if args.tile_kernel:
-        ctx.set_option("tile_kernel", args.tile_kernel)
+    if args.split_builder:
+        ctx.set_option("split_builder", 1)
     if args.host_stages:
         ctx.set_option("host_stages", args.host_stages)
     if args.host_chunk_mb:
@@ -597,16 +594,15 @@ def run_ours(args):
                 "launches_per_step": inner, "frames_per_step": frames_all * inner,
                 "details": {"out": list(wl.out_size), "variant": args.variant, "variant_resolved": ctx.variant,
                             "pieces_128x32": pieces, "frames_this_rank": n, "numa": numa,
-                            "split_builder": not args.no_split_builder, "tile_kernel": args.tile_kernel or 2},
+                            "split_builder": bool(args.split_builder)},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": recorded_traffic(wl.name, n),
                              "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
                              "kernel": ("warp_nv12_to_bgr_kernel (fused map + cvtColor + 3-channel remap)" if args.fused_bgr else
-                                        KERNEL_NAMES.get(ctx.variant, "warp_nv12_tile_kernel") + " (fused map + remap, luma + chroma)"),
+                                        KERNEL_NAMES.get(ctx.variant, "warp_nv12_quad_kernel") + " (fused map + remap, luma + chroma)"),
                              "launch_ms": {"avg": avg_launch_ms, "median": float(np.median(warp_ms)),
                                            "best": float(np.min(warp_ms)), "launches_timed": int(len(warp_ms))},
-                             "other_kernels_ms": {"build_pieces_kernel (exposed part: the head frames; the rest "
-                                                  "overlaps the sampler on a side stream)": float(np.mean(builder_ms))},
+                             "other_kernels_ms": {"build_pieces_kernel": float(np.mean(builder_ms))},
                              "pass_ms": {"avg": avg_pass_ms, "median": statistics.median(per_step_ms) / inner,
                                          "best": min(per_step_ms) / inner},
                              "whole_step_frac": alg / (avg_pass_ms * 1e-3) / 1e9 / peak,

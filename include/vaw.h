@@ -66,14 +66,13 @@ enum { VAW_INTER_NEAREST = 0, VAW_INTER_LINEAR = 1, VAW_INTER_CUBIC = 2, VAW_INT
  *           certified tensor polynomial inside the piece (within 3e-5 px of the exact
  *           projection, i.e. the correctly rounded fp32 map up to rare last-bit
  *           differences); pieces that cannot be certified use the GATHER evaluation.
- *   TILED   POLY's coordinates; the source rectangle of every 8-row band is first copied into
- *           shared memory by the TMA engine and the taps are read from there (needs a 16-byte
- *           aligned source base / pitch / frame stride, else it gathers like POLY).
- *   PIPE    TILED's tiles, scheduled as one persistent producer/consumer pipeline per SM: a producer
- *           warp pulls pieces from a global queue and allocates exactly the bytes each source box
- *           needs from a ring in shared memory, two issuer warps start the TMA loads up to three
- *           pieces ahead, groups of four consumer warps sample, a filler warp writes the pure-border
- *           pieces.  Needs 32-row pieces (else it runs as TILED).
+ *   TILED   POLY's coordinates; the source rectangle of every piece is first copied into shared memory by
+ *           the TMA engine (32/8/4-row boxes) and the taps are read from there; one CTA per piece, each
+ *           warp a 64-column x PH/2-row quadrant with two columns per lane -- 64 registers, up to eight
+ *           CTAs per SM (needs a 16-byte aligned source base / pitch / frame stride, else it gathers
+ *           like POLY).
+ *   PIPE    (retired in round 2: a persistent producer/consumer ring pipeline over the same tiles; slower
+ *           than TILED on every workload once TILED ran eight CTAs per SM.  The value is refused.)
  *   TEX     TILED, except that pieces certified interior (every tap inside the source) are filtered
  *           by the texture units: the coordinate is rounded to 1/32 px exactly as cv::remap rounds
  *           it and the filtered value is rescaled and rounded half up like (sum + 512) >> 10.  The
@@ -82,15 +81,14 @@ enum { VAW_INTER_NEAREST = 0, VAW_INTER_LINEAR = 1, VAW_INTER_CUBIC = 2, VAW_INT
  *           than TILED (tex-pipe bound).  Kept for the comparison BASELINE.json asks for,
  *           never chosen by AUTO.  Needs a texture-aligned source base (512 bytes), a pitch that is
  *           a multiple of 32 and a frame stride that is a whole number of rows; else it runs as TILED.
- * POLY, TILED and PIPE produce identical bytes.  AUTO for NV12 = TILED, or PIPE where it measured faster:
- * when the source box of a piece is too large for six tiles per SM (5312x2988 -> 3840x2160) or small
- * enough for the ring to run four pieces ahead (2704x1520); GATHER for the packed formats. */
+ * POLY and TILED produce identical bytes.  AUTO = TILED for NV12, POLY for NV12 -> BGR24, GATHER for the
+ * packed formats and for the other interpolation filters. */
 enum {
     VAW_VARIANT_AUTO = 0,
     VAW_VARIANT_GATHER = 1,
     VAW_VARIANT_POLY = 2,
     VAW_VARIANT_TILED = 3,
-    VAW_VARIANT_PIPE = 4,
+    VAW_VARIANT_PIPE = 4, /* retired: VAW_ERR_UNSUPPORTED */
     VAW_VARIANT_TEX = 5
 };
 
@@ -293,10 +291,12 @@ int vaw_synth_nv12(uint8_t *dst, int width, int height, int pitch, size_t frame_
  * __fdiv_rn / __fsqrt_rn / the k = atan(r)/r step on random operands in the certified
  * ranges; mismatches[4] = {rcp, div, sqrt, k}. */
 int vaw_set_option(vaw_ctx *ctx, const char *name, int value);
-/* Other options: "split_builder" (default 1): batches of >= 32 frames build the piece table of all but the
- * first 8 frames on a high-priority side stream while the sampler already works on those 8, so that the
- * builder is off the critical path (two sampler launches per batch; same bytes).  "tile_kernel" 1 | 2:
- * A/B of the round-1 tile kernel against the quadrant kernel (analysis only; identical bytes). */
+/* Other options: "split_builder" (default 0): batches of >= 32 frames build the piece table of all but the
+ * first 8 frames on a high-priority side stream while the sampler already works on those 8 (two sampler
+ * launches per batch; same bytes).  Measured on B200: the builder leaves the critical path but its
+ * instructions compete with the sampler for the same issue slots -- the step time does not change
+ * (DESIGN.md), hence off by default.  "host_stages" (2..8, default 4) and "host_chunk_mb" (default 32):
+ * chunks in flight and chunk size of the host-buffer pipeline (vaw_warp_batch_host). */
 /* vaw_set_option(ctx, "time_kernels", 1) makes every NV12 launch record CUDA events on its
  * stream around the piece-table builder and the warp kernel (a ring of the last 512 launches);
  * (builder_ms covers the head frames' table, the rest of the table is built on a side stream under the

@@ -78,7 +78,7 @@ def test_fast_math_sequences_equal_ieee_intrinsics(V):
 
 
 # ---- A. coordinates ---------------------------------------------------------------------------
-GATHER, POLY, TILED, PIPE, TEX = 1, 2, 3, 4, 5
+GATHER, POLY, TILED, TEX = 1, 2, 3, 5
 COORD_CASES = [("C1", (0, 0, 0)), ("C1", (2.0, -3.0, 1.5)), ("C2", (-1.0, 2.5, 0.7)),
                ("C3", (2.0, -3.0, 1.5)), ("C5", (6.0, -8.0, 4.0))]
 
@@ -294,7 +294,7 @@ def test_remap_filter_against_cv2_golden(V):
                                             # a rotation far outside the stabiliser's range: tiles outgrow the
                                             # shared-memory budget, pieces fall back to global gathers
                                             ("C3", (10.0, -15.0, 20.0), True)])
-@pytest.mark.parametrize("variant", [GATHER, POLY, TILED, PIPE])
+@pytest.mark.parametrize("variant", [GATHER, POLY, TILED])
 def test_pixels_bit_exact_on_same_map(V, oracle, name, rot, white, variant):
     from video_annotator_b200 import configs
     w = configs.workload(name)
@@ -340,111 +340,8 @@ def test_small_golden_cv2(V, oracle):
         ctx.close()
 
 
-@pytest.mark.parametrize("name,n", [("C1", 3), ("C3", 2), ("C5", 2)])
-def test_round1_tile_kernel_equals_quadrant_kernel(V, name, n):
-    """The round-1 tile kernel (4 columns per lane, kept for A/B) and the quadrant kernel (the default)
-    sample the same map with the same filter: identical bytes, white noise, rotations incl. a large one."""
-    import torch
-    from video_annotator_b200 import configs
-    w = configs.workload(name)
-    rots = np.stack([rotation_xyz(0.7, -1.1, 0.4), rotation_xyz(9.0, -14.0, 19.0), np.eye(3)][:n])
-    sw, sh = w.src_size
-    out = []
-    for kern in (2, 1):
-        ctx = V.WarpContext(w.input_camera, w.output_camera, out_size=w.out_size, variant=TILED, border=(7, 100, 200))
-        ctx.set_option("tile_kernel", kern)
-        src = torch.empty((n,) + ctx.frame_shape("src"), dtype=torch.uint8, device="cuda")
-        V.synth_nv12(src, sw, sh, n, first_index=5, white_noise=True)
-        rdev = torch.empty(n * 9, dtype=torch.float32, device="cuda")
-        ctx.upload_rotations(rots, rdev)
-        dst = torch.zeros((n,) + ctx.frame_shape("dst"), dtype=torch.uint8, device="cuda")
-        ctx.warp_batch(src, dst, rdev, n)
-        torch.cuda.synchronize()
-        out.append(dst)
-        ctx.close()
-    assert torch.equal(out[0], out[1])
-
-
-# ---- f2: cvtColor(COLOR_YUV2BGR_NV12) + 3-channel remap in ONE launch ---------------------------------
-@pytest.mark.parametrize("name,out_size,rot,white", [
-    ("C1", (1759, 998), (0.0, 0.0, 0.0), True),       # the reference's literal case: 1920x1080 -> 1759x998 BGR, odd width
-    ("C1", (1759, 998), (1.0, -2.0, 0.5), True),
-    ("C3", (3840, 2160), (2.0, -3.0, 1.5), False),
-    ("C2", (2482, 1408), (10.0, -15.0, 20.0), True),  # far outside the stabiliser's range: per-pixel pieces, rays behind the camera
-])
-def test_fused_nv12_to_bgr_equals_cvtcolor_then_remap(V, oracle, name, out_size, rot, white):
-    """NV12 in, BGR out in one launch == the reference's order of operations (FrameSourceWarp.cpp:399-401 then
-    :306-312): cvtColor on the whole frame (oracle/cvt_ref.c, pinned to cv2.cvtColor), then cv::remap's
-    integer filter on the 3-channel image with the map the kernel used.  0 LSB; also against the real
-    cv2.cvtColor + cv2.remap when cv2 is importable."""
-    from video_annotator_b200 import configs
-    w = configs.workload(name)
-    R = rotation_xyz(*rot)
-    sw, sh = w.src_size
-    border = (3, 40, 200)
-    ctx = V.WarpContext(w.input_camera, w.output_camera, fmt=V.FORMAT_NV12_TO_BGR24, out_size=out_size, border=border)
-    assert ctx.frame_shape("src") == (sh * 3 // 2, sw) and ctx.frame_shape("dst") == (out_size[1], out_size[0], 3)
-    src = oracle.synth_nv12(sw, sh, 5, white_noise=white)
-    got = _warp_one(V, ctx, src, R)
-    mx, my = [t.cpu().numpy() for t in ctx.dump_coords(R, 0)]
-    bgr = oracle.nv12_to_bgr(src, sw, sh, threads=NCPU)
-    ref = oracle.remap_u8(bgr, mx, my, border=border, threads=NCPU)
-    st = G.diff_stats(got, ref)
-    _record(f"fused_bgr_same_map_{name}_{rot}", st)
-    assert st["max"] == 0, st
-    try:
-        import cv2
-    except ImportError:
-        cv2 = None
-    if cv2 is not None:
-        cv_bgr = cv2.cvtColor(src, cv2.COLOR_YUV2BGR_NV12)
-        cv_ref = cv2.remap(cv_bgr, mx, my, cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT, borderValue=tuple(float(b) for b in border))
-        assert np.array_equal(got, cv_ref)
-    # coordinates: the same map contract as every other path (<= 1e-3 px from createMap.cl)
-    k = G.oracle_k(oracle, (w.input_camera, w.output_camera))
-    ox, oy, _ = oracle.reference_create_map(k, R, out_size[1], out_size[0], threads=NCPU)
-    assert np.array_equal(np.isnan(ox), np.isnan(mx))
-    big = max(np.abs(np.nan_to_num(ox)).max(), np.abs(np.nan_to_num(oy)).max()) > 1e4  # rays near / behind the image plane
-    if not big:
-        assert max(float(np.nanmax(np.abs(mx - ox))), float(np.nanmax(np.abs(my - oy)))) < 1e-3
-    ctx.close()
-
-
-def test_fused_nv12_to_bgr_batches_pitches_and_the_two_launch_pipeline(V, oracle):
-    """Batch == per frame; pitched output with untouched padding; and the same bytes as the two-launch pipeline
-    (vaw_nv12_to_bgr, then a BGR24 context) wherever the two contexts use the same map."""
-    import torch
-    from video_annotator_b200 import configs
-    w = configs.workload("C1")
-    sw, sh = w.src_size
-    ow, oh = 1759, 998
-    n = 3
-    rots = configs.make_rotations(40, 0.7)[20:20 + n]
-    ctx = V.WarpContext(w.input_camera, w.output_camera, fmt=V.FORMAT_NV12_TO_BGR24, out_size=(ow, oh), border=(0, 0, 0))
-    src = torch.empty((n, sh * 3 // 2, sw), dtype=torch.uint8, device="cuda")
-    V.synth_nv12(src, sw, sh, n, first_index=2, white_noise=True)
-    rdev = torch.empty(n * 9, dtype=torch.float32, device="cuda")
-    ctx.upload_rotations(rots, rdev)
-    pitch = ow * 3 + 5
-    dst = torch.full((n, oh, pitch), 77, dtype=torch.uint8, device="cuda")
-    ctx.warp_batch(src, dst, rdev, n, dst_pitch=pitch, dst_stride=oh * pitch)
-    torch.cuda.synchronize()
-    assert bool((dst[:, :, ow * 3:] == 77).all())
-    single = torch.empty((oh, ow, 3), dtype=torch.uint8, device="cuda")
-    for i in range(n):
-        ctx.warp(src[i], single, rots[i])
-        assert torch.equal(single.reshape(oh, ow * 3), dst[i, :, :ow * 3]), i
-    # two-launch pipeline through the explicit-map entry point on the same map
-    mx, my = ctx.dump_coords(rots[1], 0)
-    bgr = V.nv12_to_bgr(src[1], sw, sh)[0]
-    two = V.remap_u8(bgr, mx, my, border=(0, 0, 0))
-    torch.cuda.synchronize()
-    assert torch.equal(two.reshape(oh, ow * 3), dst[1, :, :ow * 3])
-    ctx.close()
-
-
 # ---- batching, pitches, host path -----------------------------------------------------------------
-@pytest.mark.parametrize("variant", [POLY, TILED, PIPE])
+@pytest.mark.parametrize("variant", [POLY, TILED])
 def test_split_batches_equal_unsplit(V, variant):
     """Batches of >= 32 frames build the table of all but the first 8 frames on a side stream while the
     sampler already runs (two sampler launches): same bytes as the single-launch path, on the default
@@ -460,7 +357,6 @@ def test_split_batches_equal_unsplit(V, variant):
     V.synth_nv12(src, sw, sh, n, first_index=11, white_noise=True)
     rdev = torch.empty(n * 9, dtype=torch.float32, device="cuda")
     ctx.upload_rotations(rots, rdev)
-    ctx.set_option("split_builder", 0)
     ref = torch.zeros((n,) + ctx.frame_shape("dst"), dtype=torch.uint8, device="cuda")
     before = ctx.launch_count
     ctx.warp_batch(src, ref, rdev, n)
@@ -855,15 +751,20 @@ def test_full_size_clip_properties(V, oracle):
 
 @pytest.mark.parametrize("name,n", [("C3", 10), ("C5", 4), ("C2", 7)])
 def test_variants_produce_identical_batches(V, name, n):
-    """POLY (global gathers), TILED (one CTA per piece) and PIPE (persistent producer/consumer
-    pipeline, dynamic piece queue) share the map and the filter: identical bytes for a batch."""
+    """POLY (global gathers) and TILED (one CTA per piece, tiles staged by TMA) share the map and the
+    filter: identical bytes for a batch.  Also: the retired PIPE variant is refused, not silently remapped."""
+    from video_annotator_b200 import configs as _c
+    _w = _c.workload("C1")
+    with pytest.raises(V.VawError) as exc:
+        V.WarpContext(_w.input_camera, _w.output_camera, out_size=_w.out_size, variant=4)
+    assert exc.value.code == -4
     import torch
     from video_annotator_b200 import configs
     w = configs.workload(name)
     rots = w.rotations(n, first=50, total=200)
     sw, sh = w.src_size
     outs = []
-    for variant in (POLY, TILED, PIPE):
+    for variant in (POLY, TILED):
         ctx = V.WarpContext(w.input_camera, w.output_camera, out_size=w.out_size, variant=variant, border=(3, 100, 200))
         src = torch.empty((n,) + ctx.frame_shape("src"), dtype=torch.uint8, device="cuda")
         V.synth_nv12(src, sw, sh, n, white_noise=True)
@@ -1040,7 +941,7 @@ def test_fisheye_distortion_coordinates_and_pixels(V, oracle, variant):
     ctx.close()
 
 
-@pytest.mark.parametrize("variant", [TILED, PIPE, TEX])
+@pytest.mark.parametrize("variant", [TILED, TEX])
 @pytest.mark.parametrize("out_size,centre", [((258, 34), (129.0, 17.0)), ((130, 66), (1200.3, 600.7)),
                                              ((386, 98), (3500.2, 1900.4)), ((254, 30), (9000.0, 17.0))])
 def test_windows_of_the_4k_geometry(V, oracle, out_size, centre, variant):

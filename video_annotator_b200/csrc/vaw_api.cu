@@ -35,7 +35,6 @@ struct Stage {
     uint8_t *dev_in = nullptr, *dev_out = nullptr, *pin_in = nullptr, *pin_out = nullptr;
     float *dev_rot = nullptr, *pin_rot = nullptr;
     vaw::PieceRec* pieces = nullptr;  // this stage's polynomial table (chunk_frames frames)
-    unsigned* counter = nullptr;      // this stage's piece queue (variant PIPE)
     // pending output of the chunk in flight on this stage
     uint8_t* host_dst = nullptr;
     size_t out_bytes = 0;
@@ -76,7 +75,6 @@ struct vaw_ctx {
     const uint8_t* clip_base = nullptr;
     int clip_pitch = 0, clip_slots = 0;
     size_t clip_stride = 0;
-    int tile_kernel = 2;      // 2: quadrant kernel (default), 1: the round-1 kernel (A/B only; option "tile_kernel")
     long long tile_need = 0;  // largest tile a piece of the unrotated geometry needs (bytes)
     // variant TEX: texture objects over the clip, cached per source layout
     struct TexEntry { const void* src = nullptr; int pitch = 0; size_t stride = 0; int frames = 0; vaw::TexSet set{}; int n_groups = 0; };
@@ -84,13 +82,11 @@ struct vaw_ctx {
     TexEntry tex_cache[kTexCache];
     int tex_next = 0;
     int tex_align = 512, tex_pitch_align = 32;
-    unsigned* counter = nullptr;  // piece queue of variant PIPE (for ctx->table)
-    unsigned* counter2 = nullptr; // ... of the second sampler launch of a split batch
     // builder off the critical path: the table of all but the first kHeadFrames frames of a batch is
     // built on a high-priority side stream while the sampler already works on the head frames
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    bool split_builder = true;
+    bool split_builder = false;  // option "split_builder": measured neutral on B200 (the two kernels share the issue slots)
     // option "time_kernels": CUDA-event stamps around the kernels of every launch (bench.py's roofline)
     static constexpr int kTimeRing = 512;
     bool time_kernels = false;
@@ -240,7 +236,6 @@ const vaw::TileMaps& tile_maps(vaw_ctx* ctx, const uint8_t* src, int pitch, size
     e.src = src; e.pitch = pitch; e.stride = stride; e.frames = frames;
     e.maps.enabled = 0;
     e.maps.tile_cap = ctx->tile_cap;
-    e.maps.kernel = ctx->tile_kernel;
     const int rows_total = ctx->p.src_height + ctx->p.src_height / 2;
     EncodeTiledFn enc = encode_tiled();
     const bool ok = enc && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (pitch & 15) == 0 && (stride & 15) == 0 &&
@@ -353,7 +348,7 @@ const vaw::TexSet& tex_set(vaw_ctx* ctx, const uint8_t* src, int pitch, size_t s
 
 int launch(vaw_ctx* ctx, const uint8_t* src, int src_pitch, size_t src_stride, uint8_t* dst,
            int dst_pitch, size_t dst_stride, const float* rots, const vaw::Rot* rot0, int n_frames,
-           cudaStream_t st, vaw::PieceRec* table_override = nullptr, unsigned* counter_override = nullptr)
+           cudaStream_t st, vaw::PieceRec* table_override = nullptr)
 {
     vaw::Geom g = ctx->g;
     g.src_pitch = src_pitch;
@@ -367,10 +362,7 @@ int launch(vaw_ctx* ctx, const uint8_t* src, int src_pitch, size_t src_stride, u
     if (rot0) b.rot0 = *rot0;
     const bool fused_bgr = ctx->p.format == VAW_FORMAT_NV12_TO_BGR24;
     const bool poly = fused_bgr || (ctx->p.format == VAW_FORMAT_NV12 && ctx->variant != VAW_VARIANT_GATHER);
-    const bool tiled = ctx->variant == VAW_VARIANT_TILED || ctx->variant == VAW_VARIANT_PIPE ||
-                       ctx->variant == VAW_VARIANT_TEX;
-    const bool piped = ctx->variant == VAW_VARIANT_PIPE && ctx->g.piece_h == vaw::kPieceHMax &&
-                       vaw::pipe_smem_bytes(ctx->tile_cap) <= (227 << 10);
+    const bool tiled = ctx->variant == VAW_VARIANT_TILED || ctx->variant == VAW_VARIANT_TEX;
     // grid.z is limited to 65535 frames per launch; variant TEX to kTexGroups textures of <= 65000 rows
     int per_launch = 65535;
     if (ctx->variant == VAW_VARIANT_TEX) {
@@ -437,14 +429,13 @@ int launch(vaw_ctx* ctx, const uint8_t* src, int src_pitch, size_t src_stride, u
                     clip_frame0 = (int)(off / ctx->clip_stride);
             }
             const vaw::TileMaps* tm = nullptr;
-            if (piped || tiled)
+            if (tiled)
                 tm = clip_frame0 >= 0 ? &tile_maps(ctx, ctx->clip_base, ctx->clip_pitch, ctx->clip_stride, ctx->clip_slots)
                                       : &tile_maps(ctx, bb.src, src_pitch, src_stride, bb.n_frames);
             if (clip_frame0 >= 0) bb.tma_frame0 = clip_frame0;
             for (int part = 0; part < (split ? 2 : 1); ++part) {
                 vaw::FrameBatch pb = bb;
                 const vaw::PieceRec* ptab = tab;
-                unsigned* cnt = table_override ? counter_override : ctx->counter;
                 if (split) {
                     pb.n_frames = part ? bb.n_frames - head : head;
                     if (part) {
@@ -455,12 +446,10 @@ int launch(vaw_ctx* ctx, const uint8_t* src, int src_pitch, size_t src_stride, u
                         if (bb.rots) pb.rots = bb.rots + (size_t)head * 9;
                         pb.tma_frame0 = bb.tma_frame0 + head;
                         ptab = tab + (size_t)head * ctx->pieces_per_frame;
-                        cnt = ctx->counter2;
                         VAW_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
                     }
                 }
                 if (fused_bgr) e = vaw::launch_warp_nv12_to_bgr(g, pb, ptab, st);
-                else if (piped) e = vaw::launch_warp_nv12_pipe(g, pb, ptab, cnt, *tm, st);
                 else if (tiled) e = vaw::launch_warp_nv12_tile(g, pb, ptab, *tm, st);
                 else e = vaw::launch_warp_nv12_poly(g, pb, ptab, st);
                 if (e != cudaSuccess) return cuda_fail(ctx, e, "warp kernel launch");
@@ -490,7 +479,7 @@ void free_host_path(vaw_ctx* ctx)
 {
     for (Stage& s : ctx->stage) {
         if (s.stream) cudaStreamSynchronize(s.stream);
-        cudaFree(s.dev_in); cudaFree(s.dev_out); cudaFree(s.dev_rot); cudaFree(s.pieces); cudaFree(s.counter);
+        cudaFree(s.dev_in); cudaFree(s.dev_out); cudaFree(s.dev_rot); cudaFree(s.pieces);
         cudaFreeHost(s.pin_in); cudaFreeHost(s.pin_out); cudaFreeHost(s.pin_rot);
         if (s.stream) cudaStreamDestroy(s.stream);
         s = Stage{};
@@ -526,10 +515,7 @@ int init_host_path_impl(vaw_ctx* ctx)
         VAW_CUDA(ctx, cudaMalloc(&s.dev_rot, sizeof(float) * 9 * ctx->chunk_frames));
         VAW_CUDA(ctx, cudaMallocHost(&s.pin_rot, sizeof(float) * 9 * ctx->chunk_frames));
         if (ctx->variant != VAW_VARIANT_GATHER)
-        {
             VAW_CUDA(ctx, cudaMalloc(&s.pieces, sizeof(vaw::PieceRec) * ctx->pieces_per_frame * ctx->chunk_frames));
-            VAW_CUDA(ctx, cudaMalloc(&s.counter, 256));
-        }
     }
     ctx->host_ready = true;
     return VAW_OK;
@@ -540,9 +526,8 @@ int init_host_path_impl(vaw_ctx* ctx)
 // budget is free head-room for larger rotations.  Returns the CTA count.
 int choose_tile_cap(vaw_ctx* ctx)
 {
-    const int book = vaw::tile_smem_bytes(0, ctx->tile_kernel);
-    const int max_ctas = ctx->tile_kernel == 1 ? 6 : 8;  // register limit of the two kernels (80 / 64 registers)
-    int ctas = max_ctas;
+    const int book = vaw::tile_smem_bytes(0);
+    int ctas = 8;  // register limit of the 64-register instantiation
     while (ctas > 1 && ctx->tile_need * 106 / 100 > vaw::tile_cap_for_ctas(ctas, book)) --ctas;
     long long cap = vaw::tile_cap_for_ctas(ctas, book);
     if (cap < vaw::kTileCapMin) cap = vaw::kTileCapMin;
@@ -620,10 +605,10 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
     if (p.format == VAW_FORMAT_NV12_TO_BGR24 && (p.interpolation != VAW_INTER_LINEAR ||
                                                   (p.variant != VAW_VARIANT_AUTO && p.variant != VAW_VARIANT_POLY)))
         return fail(nullptr, VAW_ERR_UNSUPPORTED, "NV12 -> BGR24 in one launch: INTER_LINEAR, variant AUTO or POLY");
-    if (p.variant < VAW_VARIANT_AUTO || p.variant > VAW_VARIANT_TEX)
-        return fail(nullptr, VAW_ERR_UNSUPPORTED, "kernel variant not available in this build");
+    if (p.variant < VAW_VARIANT_AUTO || p.variant > VAW_VARIANT_TEX || p.variant == VAW_VARIANT_PIPE)
+        return fail(nullptr, VAW_ERR_UNSUPPORTED, "kernel variant not available in this build (PIPE was retired in round 2)");
     if (p.variant >= VAW_VARIANT_POLY && p.format != VAW_FORMAT_NV12 && p.format != VAW_FORMAT_NV12_TO_BGR24)
-        return fail(nullptr, VAW_ERR_UNSUPPORTED, "variants POLY, TILED, PIPE and TEX exist for NV12 only");
+        return fail(nullptr, VAW_ERR_UNSUPPORTED, "variants POLY, TILED and TEX exist for NV12 only");
     // `short` indices in createMap.cl:10-11 and int16 taps in cv::remap cap both sizes
     if (p.src_width < 2 || p.src_height < 2 || p.out_width < 1 || p.out_height < 1 ||
         p.src_width > 32766 || p.src_height > 32766 || p.out_width > 32766 || p.out_height > 32766)
@@ -721,8 +706,6 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
         ctx->pieces_per_frame = (size_t)vaw::pieces_x(g.out_w) * vaw::pieces_y(g.out_h, ph);
         e = cudaEventCreateWithFlags(&ctx->table_free, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaMalloc(&ctx->dump_table, ctx->pieces_per_frame * sizeof(vaw::PieceRec));
-        if (e == cudaSuccess) e = cudaMalloc(&ctx->counter, 256);
-        if (e == cudaSuccess) e = cudaMalloc(&ctx->counter2, 256);
         if (e == cudaSuccess) {
             int lo = 0, hi = 0;  // "greatest" priority is the numerically lowest
             e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
@@ -738,8 +721,7 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
                 ctx->tex_pitch_align = prop.texturePitchAlignment > 0 ? (int)prop.texturePitchAlignment : 32;
             }
         }
-        if (e == cudaSuccess && (ctx->variant == VAW_VARIANT_TILED || ctx->variant == VAW_VARIANT_PIPE ||
-                                 ctx->variant == VAW_VARIANT_TEX)) {
+        if (e == cudaSuccess && (ctx->variant == VAW_VARIANT_TILED || ctx->variant == VAW_VARIANT_TEX)) {
             // size the per-CTA tile from the source boxes of the unrotated geometry, +20 % for the
             // tilt a few degrees of rotation add; more shared memory per CTA = fewer resident CTAs
             const float eye[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
@@ -754,12 +736,7 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
                     if (nb != 0x7fffffff && nb > need) need = nb;
                 }
                 ctx->tile_need = need;
-                const int ctas = choose_tile_cap(ctx);
-                // AUTO: one CTA per piece (TILED) unless the tiles are so large that fewer than four CTAs fit an
-                // SM; then the ring pipeline (PIPE), which allocates exactly what each piece needs, keeps more
-                // tiles in flight
-                if (p.variant == VAW_VARIANT_AUTO && ph == vaw::kPieceHMax && need > 0 && ctas < 4)
-                    ctx->variant = VAW_VARIANT_PIPE;
+                choose_tile_cap(ctx);
             }
         }
         if (e != cudaSuccess) {
@@ -785,8 +762,6 @@ void vaw_destroy(vaw_ctx* ctx)
     for (vaw_ctx::TexEntry& te : ctx->tex_cache) destroy_tex_entry(te);
     cudaFree(ctx->table);
     cudaFree(ctx->dump_table);
-    cudaFree(ctx->counter);
-    cudaFree(ctx->counter2);
     if (ctx->side) cudaStreamDestroy(ctx->side);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
@@ -817,14 +792,6 @@ int vaw_set_option(vaw_ctx* ctx, const char* name, int value)
             free_host_path(ctx);
             ctx->host_chunk_bytes = (size_t)value << 20;
         }
-        return VAW_OK;
-    }
-    if (!std::strcmp(name, "tile_kernel")) {  // A/B of the two tile kernels (analysis only)
-        if (value != 1 && value != 2) return fail(ctx, VAW_ERR_INVALID, "tile_kernel is 1 or 2");
-        DeviceGuard dg(ctx->device);
-        VAW_CUDA(ctx, cudaDeviceSynchronize());
-        ctx->tile_kernel = value;
-        choose_tile_cap(ctx);
         return VAW_OK;
     }
     if (!std::strcmp(name, "time_kernels")) {
@@ -957,7 +924,7 @@ int vaw_warp_batch_host(vaw_ctx* ctx, const uint8_t* src_host, uint8_t* dst_host
         }
         VAW_CUDA(ctx, cudaMemcpyAsync(s.dev_in, hsrc, sfb * n, cudaMemcpyHostToDevice, s.stream));
         s.busy = true;  // from here on the stage has work in flight that touches the caller's buffers
-        int rc2 = launch(ctx, s.dev_in, src_pitch, sfb, s.dev_out, dst_pitch, dfb, s.dev_rot, nullptr, n, s.stream, s.pieces, s.counter);
+        int rc2 = launch(ctx, s.dev_in, src_pitch, sfb, s.dev_out, dst_pitch, dfb, s.dev_rot, nullptr, n, s.stream, s.pieces);
         if (rc2) return rc2;
         s.out_staged = !dst_pinned;
         if (s.out_staged && !s.pin_out) VAW_CUDA(ctx, cudaMallocHost(&s.pin_out, dfb * ctx->chunk_frames));

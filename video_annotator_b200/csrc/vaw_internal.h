@@ -46,25 +46,18 @@ struct alignas(64) TileMaps {
     CUtensorMap m4[kTileWidths];   // boxes of 4 rows (tile rows come in multiples of 4)
     int enabled;   // 0: no maps (layout not TMA-compatible) -> every piece gathers from global memory
     int tile_cap;  // bytes of shared memory for the luma + chroma tile of one CTA
-    int kernel;    // 2: quadrant kernel (8 CTAs per SM at 64 registers), 1: the round-1 kernel (A/B only)
-    int pad[13];
+    int pad[14];
 };
 // Tile capacity that lets `ctas` CTAs of the tile kernel share one SM: 227 KB of shared memory, 1 KB
 // reserved per CTA by the system, 128 bytes of the kernel's own bookkeeping; a multiple of 128.
 constexpr int kSmemPerSM = 227 << 10;
 inline int tile_cap_for_ctas(int ctas, int bookkeeping) { return ((kSmemPerSM / ctas - 1024 - bookkeeping) / 128) * 128; }
-// Variant PIPE (vaw_pipe.cu): persistent producer/consumer pipeline over the same tiles; `counter`
-// is one unsigned in device memory (the piece queue), reset by the launcher.
-cudaError_t launch_warp_nv12_pipe(const Geom& g, const FrameBatch& b, const PieceRec* table, unsigned* counter,
-                                  const TileMaps& maps, cudaStream_t st);
-int pipe_smem_bytes(int tile_cap);
 // bytes of tile a piece needs for its source box (what the kernel computes), 0 if it has none
 int tile_need_bytes(const PieceRec& rec);
-// dynamic shared memory of the tile kernel (version 1 or 2) for a given tile capacity
-int tile_smem_bytes(int tile_cap, int kernel = 2);
+// dynamic shared memory of the tile kernel for a given tile capacity
+int tile_smem_bytes(int tile_cap);
 // out-of-tile tap count of the instrumented build (-DVAW_BOUNDS_CHECK), -1 when not instrumented
 long long tile_oob_count();
-// Needs piece_h == 32.
 cudaError_t launch_warp_nv12_tile(const Geom& g, const FrameBatch& b, const PieceRec* table, const TileMaps& maps,
                                   cudaStream_t st);
 // Variant TEX (vaw_tex.cu): certified interior pieces are filtered by the texture units.  The clip

@@ -1,6 +1,5 @@
-// vaw_tile.cuh -- device pieces shared by the shared-memory variants (vaw_tile.cu: one CTA per
-// piece; vaw_pipe.cu: persistent producer/consumer pipeline): the TMA tensor load, the samplers
-// that read taps from a staged tile, the pair lane mapping, the border fill.
+// vaw_tile.cuh -- device pieces of the shared-memory variant (vaw_tile.cu: one CTA per piece): the TMA
+// tensor load, the samplers that read taps from a staged tile, the border fill.
 // Same arithmetic as vaw_poly.cuh: cv::remap's integer filter
 // (/root/reference/opencv/FrameSourceWarp.cpp:306-312) on the map of vaw_pieces.cuh.
 #pragma once
@@ -62,13 +61,8 @@ __device__ __forceinline__ unsigned chroma_tile(unsigned cconst, unsigned pl, fl
 #endif
 }
 
-// Lane -> column mapping of the staged path: lane l owns luma columns 2l, 2l+1 and 64+2l, 64+2l+1
-// of the piece (slot j -> column 2l + (j & 1) + 64 (j >> 1)).  One LDS instruction then serves 32
-// pixels that are 2 columns apart: at the C3 centre (1.84 source px per output px) its addresses
-// span 118 bytes = 30 banks, i.e. one shared-memory wavefront.  With four consecutive columns per
-// lane the same instruction spans 236 bytes and needs two or more (measured 2.5 wavefronts per
-// LDS, shared-memory pipe 72 % busy).  Quads (j = 0,1 and j = 2,3) stay inside a lane, so the NV12
-// chroma rule needs no shuffles; stores become 2 bytes per lane (64 contiguous bytes per warp).
+// Pair lane mapping of the texture variant (vaw_tex.cu): lane l owns luma columns 2l, 2l+1 and 64+2l, 64+2l+1
+// of the piece (slot j -> column 2l + (j & 1) + 64 (j >> 1)); stores are 2 bytes per lane.
 __device__ __forceinline__ int pair_column(int lane, int j) { return 2 * lane + (j & 1) + 64 * (j >> 1); }
 
 template <bool kRagged>
@@ -79,50 +73,6 @@ __device__ __forceinline__ void store_pair(uint8_t* p, unsigned lo, unsigned hi,
     } else if (inside) {
         p[0] = (uint8_t)lo;
         p[1] = (uint8_t)hi;
-    }
-}
-
-// nrows (even) rows starting at piece row dv0, taps from the staged tile.  o.y0 / o.y1 / o.c point
-// at column 2*lane of the piece.
-template <bool kRagged>
-__device__ __forceinline__ void rows_tile(const Geom& g, const ColPoly& cp, unsigned lconst, unsigned cconst,
-                                          unsigned pl, int dv0, int nrows, RowPtrs& o, bool in_a, bool in_b,
-                                          const TileBounds& tb)
-{
-    // t = (dv - t_off) * t_scale is a small dyadic rational: stepping it by t_scale is exact
-    float t = row_t(g, dv0);
-    const float dt = g.t_scale, dt2 = __fadd_rn(g.t_scale, g.t_scale);
-#pragma unroll 1
-    for (int dv = dv0; dv < dv0 + nrows; dv += 2) {
-        float2 m[2][4];
-        row_coords(cp, t, m[0]);
-        row_coords(cp, __fadd_rn(t, dt), m[1]);
-        t = __fadd_rn(t, dt2);
-        unsigned y[2][4];
-#pragma unroll
-        for (int r = 0; r < 2; ++r)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) y[r][i] = (unsigned)luma_tile(lconst, pl, m[r][i], tb) >> 10;
-        unsigned c[2];
-#pragma unroll
-        for (int q = 0; q < 2; ++q)
-#ifdef VAW_ABL_NO_CHROMA
-            c[q] = y[0][q] | (y[1][q] << 8);
-#else
-            c[q] = chroma_tile(cconst, pl, chroma_z(m[0][2 * q], m[0][2 * q + 1], m[1][2 * q], m[1][2 * q + 1]), tb);
-#endif
-#ifdef VAW_ABL_NO_STORE  // analysis only: results stay live, (almost) nothing is written
-        if ((y[0][0] ^ y[0][1] ^ y[0][2] ^ y[0][3] ^ y[1][0] ^ y[1][1] ^ y[1][2] ^ y[1][3] ^ c[0] ^ c[1]) == 0x12345u)
-#endif
-        {
-        store_pair<kRagged>(o.y0, y[0][0], y[0][1], in_a);
-        store_pair<kRagged>(o.y0 + 64, y[0][2], y[0][3], in_b);
-        store_pair<kRagged>(o.y1, y[1][0], y[1][1], in_a);
-        store_pair<kRagged>(o.y1 + 64, y[1][2], y[1][3], in_b);
-        store_pair<kRagged>(o.c, c[0] & 255u, c[0] >> 8, in_a);
-        store_pair<kRagged>(o.c + 64, c[1] & 255u, c[1] >> 8, in_b);
-        }
-        o.y0 += o.step_y; o.y1 += o.step_y; o.c += o.step_c;
     }
 }
 
