@@ -118,7 +118,13 @@ typedef struct vaw_params {
                                           presets set zeros, FrameSourceWarp.cpp:35, and createMap.cl
                                           ignores the field).  All zero = the reference's map, bit for
                                           bit; float like every scalar the reference hands its kernel   */
-    int32_t reserved[3];
+    int32_t projection;                /* extension: the projection pair.  0 = fisheye input, rectilinear
+                                          output: createMap.cl, the reference's only pair.  Bit 0 (value 1):
+                                          RECTILINEAR input camera (no atan step).  Bit 1 (value 2): FISHEYE
+                                          (equidistant) output camera -- CameraModel, FrameSourceWarp.hpp:23-26;
+                                          in_p / out_p = rect | fish of the wider toolchain, src/render.ts:611-618.
+                                          Non-zero values: NV12 sources, INTER_LINEAR, variants AUTO/POLY/TILED   */
+    int32_t reserved[2];
 } vaw_params;
 
 /* Camera description (opencv/FrameSourceWarp.hpp:14-34). */
@@ -151,11 +157,11 @@ int vaw_get_output_camera(const vaw_camera *input, double scale, int crop_border
                           vaw_camera *out);
 /* Fill the 8 scalars + sizes + distortion of `p` from two cameras (FrameSourceWarp.cpp:283-290);
  * for NV12 the output size is rounded down to even; interpolation = VAW_INTER_LINEAR (the
- * constructor's default, FrameSourceWarp.hpp:90) and variant = VAW_VARIANT_AUTO; border and
- * reserved fields are left untouched.  The kernels implement createMap.cl's projection pair:
- * a FISHEYE input camera and a RECTILINEAR output camera; other models -> VAW_ERR_UNSUPPORTED
- * (vaw_get_output_camera likewise for a non-fisheye input).  vaw_get_output_camera honours
- * input->distortion the way cv::fisheye::undistortPoints does (FrameSourceWarp.cpp:93-110). */
+ * constructor's default, FrameSourceWarp.hpp:90), variant = VAW_VARIANT_AUTO and `projection` from
+ * the two cameras' models (FISHEYE input + RECTILINEAR output = 0 = createMap.cl); border and
+ * reserved fields are left untouched.  vaw_get_output_camera is the reference's fisheye-only
+ * derivation (VAW_ERR_UNSUPPORTED for a rectilinear input) and honours input->distortion the way
+ * cv::fisheye::undistortPoints does (FrameSourceWarp.cpp:93-110). */
 int vaw_params_from_cameras(const vaw_camera *input, const vaw_camera *output, int format,
                             vaw_params *p);
 

@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_params_struct_layout_matches_header():
     from video_annotator_b200 import _lib
-    # 8 doubles + 6 int32 + 4 bytes + int32 + 7 int32 = 124, padded to the 8-byte alignment;
+    # 8 doubles + 6 int32 + 4 bytes + int32 + 4 floats + 3 int32 = 124, padded to the 8-byte alignment;
     # vaw_api.cu static_asserts the same numbers on the C side
     assert C.sizeof(_lib.VawParams) == 128
     assert C.sizeof(_lib.VawCamera) == 4 * 4 + 9 * 8 + 4 * 8 == 120
@@ -160,8 +160,9 @@ def test_output_camera_honours_distortion_like_cv_fisheye():
     assert V.get_output_camera(cam, 0.5).size != V.get_output_camera(cam0, 0.5).size
 
 
-def test_camera_models_other_than_fisheye_in_rectilinear_out_are_refused():
-    """createMap.cl implements one projection pair; a RECTILINEAR input camera must not be warped as fisheye."""
+def test_camera_models_select_the_projection_pair():
+    """CameraModel (FrameSourceWarp.hpp:23-26) is carried into vaw_params::projection; createMap.cl's pair
+    (FISHEYE in, RECTILINEAR out) is 0.  The reference's get_output_camera is fisheye-only."""
     import video_annotator_b200 as V
     from video_annotator_b200 import _lib
     lib = _lib.load()
@@ -170,10 +171,13 @@ def test_camera_models_other_than_fisheye_in_rectilinear_out_are_refused():
     out = _lib.VawCamera()
     assert lib.vaw_get_output_camera(C.byref(rect_in._c), 1.0, 0, 1.0, C.byref(out)) == -4
     good_out = V.get_output_camera(cam)
-    p = _lib.VawParams()
-    assert lib.vaw_params_from_cameras(C.byref(rect_in._c), C.byref(good_out._c), 0, C.byref(p)) == -4
     fish_out = V.Camera.from_matrix(good_out.K, 1758, 998, model=1)
-    assert lib.vaw_params_from_cameras(C.byref(cam._c), C.byref(fish_out._c), 0, C.byref(p)) == -4
+    p = _lib.VawParams()
+    for cin, cout, want in ((cam, good_out, 0), (rect_in, good_out, 1), (cam, fish_out, 2), (rect_in, fish_out, 3)):
+        assert lib.vaw_params_from_cameras(C.byref(cin._c), C.byref(cout._c), 0, C.byref(p)) == 0
+        assert p.projection == want
+    bad = V.Camera.from_matrix(cam.K, 1920, 1080, model=7)
+    assert lib.vaw_params_from_cameras(C.byref(bad._c), C.byref(good_out._c), 0, C.byref(p)) == -2
 
 
 def test_params_from_cameras_sets_the_reference_defaults():

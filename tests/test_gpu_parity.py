@@ -340,6 +340,160 @@ def test_small_golden_cv2(V, oracle):
         ctx.close()
 
 
+# ---- f3: the projection pairs createMap.cl does not have ----------------------------------------------------
+def _exact_map_f64_models(k, R, rows, cols, projection):
+    """float64 statement of the four projection pairs (include/vaw.h vaw_params::projection)."""
+    r = np.asarray(R, np.float64).reshape(9).astype(np.float32).astype(np.float64).reshape(3, 3)
+    u, v = np.meshgrid(np.arange(cols, dtype=np.float64), np.arange(rows, dtype=np.float64))
+    x = (u - k.map_center_x) / k.map_focal_x
+    y = (v - k.map_center_y) / k.map_focal_y
+    z = np.ones_like(x)
+    if projection & 2:   # equidistant output: distance from the centre (in focal lengths) = angle from the axis
+        th = np.sqrt(x * x + y * y)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            sinc = np.where(th > 0, np.sin(th) / th, 1.0)
+        x, y, z = x * sinc, y * sinc, np.cos(th)
+    q = [r[i, 0] * x + r[i, 1] * y + r[i, 2] * z for i in range(3)]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        c0, c1 = q[0] / q[2], q[1] / q[2]
+        if projection & 1:  # pinhole input
+            kk = 1.0
+        else:
+            rad = np.sqrt(c0 * c0 + c1 * c1)
+            kk = np.where(rad > 0, np.arctan(rad) / rad, 1.0)
+    return k.src_center_x + c0 * kk * k.src_focal_x, k.src_center_y + c1 * kk * k.src_focal_y, q[2]
+
+
+@pytest.mark.parametrize("projection,rot", [(1, (2.0, -3.0, 1.5)), (2, (2.0, -3.0, 1.5)), (3, (-4.0, 6.0, 10.0)),
+                                            (2, (0.0, 0.0, 0.0)), (1, (0.0, 0.0, 0.0))])
+@pytest.mark.parametrize("variant", [POLY, TILED])
+def test_other_projection_pairs(V, oracle, projection, rot, variant):
+    """Rectilinear input and / or fisheye (equidistant) output -- CameraModel, FrameSourceWarp.hpp:23-26; the
+    in_p / out_p options of the wider toolchain, src/render.ts:611-618.  createMap.cl has one pair only, so the
+    bar is the float64 statement of each pair (correctly rounded fp32 up to half an ulp + 2e-4 px, <= 1e-3 px),
+    the real cv2.initUndistortRectifyMap for pinhole -> pinhole, and 0 LSB for the pixels on the same map."""
+    sw, sh, ow, oh = 1920, 1080, 1280, 720
+    cam = V.get_preset_camera(V.warp.GOPRO_H4B_WIDE169_MEASURED, sw, sh)
+    cin = V.Camera.from_matrix(cam.K, sw, sh, model=0 if projection & 1 else 1)
+    f_out = 520.0 if projection & 2 else 700.0
+    cout = V.Camera.from_matrix([[f_out, 0, (ow - 1) / 2.0], [0, f_out, (oh - 1) / 2.0], [0, 0, 1]], ow, oh,
+                                model=1 if projection & 2 else 0)
+    R = rotation_xyz(*rot)
+    border = (9, 100, 180)
+    ctx = V.WarpContext(cin, cout, out_size=(ow, oh), variant=variant, border=border)
+    assert ctx.params.projection == projection
+    mx, my = [t.cpu().numpy() for t in ctx.dump_coords(R, 0)]
+    cx, cy = [t.cpu().numpy() for t in ctx.dump_coords(R, 1)]
+    k = oracle.intrinsics(cin.K, cout.K)
+    ex, ey, qz = _exact_map_f64_models(k, R, oh, ow, projection)
+    reg = qz > 0.05
+    assert reg.mean() > 0.9
+    ulp_x = np.spacing(np.abs(mx).astype(np.float32)).astype(np.float64)
+    ulp_y = np.spacing(np.abs(my).astype(np.float32)).astype(np.float64)
+    assert not np.isnan(mx[reg]).any() and not np.isnan(my[reg]).any()      # no NaN at the axis for these pairs
+    slack = max(float(np.max((np.abs(mx - ex) - 0.5 * ulp_x)[reg])), float(np.max((np.abs(my - ey) - 0.5 * ulp_y)[reg])))
+    err = max(float(np.max(np.abs(mx - ex)[reg])), float(np.max(np.abs(my - ey)[reg])))
+    _record(f"projection_{projection}_v{variant}_{rot}", {"max_err_vs_exact_px": err, "max_excess_over_half_ulp_px": slack})
+    assert slack < 2e-4 and err < 1e-3
+    if projection == 1:  # pinhole -> pinhole under a rotation: OpenCV's own map generator
+        cv2 = pytest.importorskip("cv2")
+        r32 = oracle.rot32(R).astype(np.float64).reshape(3, 3)
+        Kin = np.array([[k.src_focal_x, 0, k.src_center_x], [0, k.src_focal_y, k.src_center_y], [0, 0, 1]], np.float64)
+        Kout = np.array([[k.map_focal_x, 0, k.map_center_x], [0, k.map_focal_y, k.map_center_y], [0, 0, 1]], np.float64)
+        cvx, cvy = cv2.initUndistortRectifyMap(Kin, None, r32.T, Kout, (ow, oh), cv2.CV_32FC1)
+        assert float(np.max(np.abs(mx - cvx)[reg])) < 2e-3 and float(np.max(np.abs(my - cvy)[reg])) < 2e-3
+    # chroma map: the oracle's definition on the kernel's luma map; pixels: 0 LSB on the same map
+    ocx, ocy = oracle.chroma_map(mx, my, threads=NCPU)
+    assert G.bits_equal(cx, ocx) and G.bits_equal(cy, ocy)
+    src = oracle.synth_nv12(sw, sh, 4, white_noise=True)
+    got = _warp_one(V, ctx, src, R)
+    ref = _oracle_on_map(oracle, src, sw, sh, mx, my, cx, cy, border)
+    assert G.diff_stats(got, ref)["max"] == 0
+    ctx.close()
+    # the packed formats / the op-for-op variant implement createMap.cl's pair only
+    with pytest.raises(V.VawError) as exc:
+        V.WarpContext(cin, cout, out_size=(ow, oh), variant=GATHER)
+    assert exc.value.code == -4
+
+
+# ---- f2: cvtColor(COLOR_YUV2BGR_NV12) + 3-channel remap in ONE launch ---------------------------------
+@pytest.mark.parametrize("name,out_size,rot,white", [
+    ("C1", (1759, 998), (0.0, 0.0, 0.0), True),       # the reference's literal case: 1920x1080 -> 1759x998 BGR, odd width
+    ("C1", (1759, 998), (1.0, -2.0, 0.5), True),
+    ("C3", (3840, 2160), (2.0, -3.0, 1.5), False),
+    ("C2", (2482, 1408), (10.0, -15.0, 20.0), True),  # far outside the stabiliser's range: per-pixel pieces, rays behind the camera
+])
+def test_fused_nv12_to_bgr_equals_cvtcolor_then_remap(V, oracle, name, out_size, rot, white):
+    """NV12 in, BGR out in one launch == the reference's order of operations (FrameSourceWarp.cpp:399-401 then
+    :306-312): cvtColor on the whole frame (oracle/cvt_ref.c, pinned to cv2.cvtColor), then cv::remap's
+    integer filter on the 3-channel image with the map the kernel used.  0 LSB; also against the real
+    cv2.cvtColor + cv2.remap when cv2 is importable."""
+    from video_annotator_b200 import configs
+    w = configs.workload(name)
+    R = rotation_xyz(*rot)
+    sw, sh = w.src_size
+    border = (3, 40, 200)
+    ctx = V.WarpContext(w.input_camera, w.output_camera, fmt=V.FORMAT_NV12_TO_BGR24, out_size=out_size, border=border)
+    assert ctx.frame_shape("src") == (sh * 3 // 2, sw) and ctx.frame_shape("dst") == (out_size[1], out_size[0], 3)
+    src = oracle.synth_nv12(sw, sh, 5, white_noise=white)
+    got = _warp_one(V, ctx, src, R)
+    mx, my = [t.cpu().numpy() for t in ctx.dump_coords(R, 0)]
+    bgr = oracle.nv12_to_bgr(src, sw, sh, threads=NCPU)
+    ref = oracle.remap_u8(bgr, mx, my, border=border, threads=NCPU)
+    st = G.diff_stats(got, ref)
+    _record(f"fused_bgr_same_map_{name}_{rot}", st)
+    assert st["max"] == 0, st
+    try:
+        import cv2
+    except ImportError:
+        cv2 = None
+    if cv2 is not None:
+        cv_bgr = cv2.cvtColor(src, cv2.COLOR_YUV2BGR_NV12)
+        cv_ref = cv2.remap(cv_bgr, mx, my, cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT, borderValue=tuple(float(b) for b in border))
+        assert np.array_equal(got, cv_ref)
+    # coordinates: the same map contract as every other path (<= 1e-3 px from createMap.cl)
+    k = G.oracle_k(oracle, (w.input_camera, w.output_camera))
+    ox, oy, _ = oracle.reference_create_map(k, R, out_size[1], out_size[0], threads=NCPU)
+    assert np.array_equal(np.isnan(ox), np.isnan(mx))
+    big = max(np.abs(np.nan_to_num(ox)).max(), np.abs(np.nan_to_num(oy)).max()) > 1e4  # rays near / behind the image plane
+    if not big:
+        assert max(float(np.nanmax(np.abs(mx - ox))), float(np.nanmax(np.abs(my - oy)))) < 1e-3
+    ctx.close()
+
+
+def test_fused_nv12_to_bgr_batches_pitches_and_the_two_launch_pipeline(V, oracle):
+    """Batch == per frame; pitched output with untouched padding; and the same bytes as the two-launch pipeline
+    (vaw_nv12_to_bgr, then a BGR24 context) wherever the two contexts use the same map."""
+    import torch
+    from video_annotator_b200 import configs
+    w = configs.workload("C1")
+    sw, sh = w.src_size
+    ow, oh = 1759, 998
+    n = 3
+    rots = configs.make_rotations(40, 0.7)[20:20 + n]
+    ctx = V.WarpContext(w.input_camera, w.output_camera, fmt=V.FORMAT_NV12_TO_BGR24, out_size=(ow, oh), border=(0, 0, 0))
+    src = torch.empty((n, sh * 3 // 2, sw), dtype=torch.uint8, device="cuda")
+    V.synth_nv12(src, sw, sh, n, first_index=2, white_noise=True)
+    rdev = torch.empty(n * 9, dtype=torch.float32, device="cuda")
+    ctx.upload_rotations(rots, rdev)
+    pitch = ow * 3 + 5
+    dst = torch.full((n, oh, pitch), 77, dtype=torch.uint8, device="cuda")
+    ctx.warp_batch(src, dst, rdev, n, dst_pitch=pitch, dst_stride=oh * pitch)
+    torch.cuda.synchronize()
+    assert bool((dst[:, :, ow * 3:] == 77).all())
+    single = torch.empty((oh, ow, 3), dtype=torch.uint8, device="cuda")
+    for i in range(n):
+        ctx.warp(src[i], single, rots[i])
+        assert torch.equal(single.reshape(oh, ow * 3), dst[i, :, :ow * 3]), i
+    # two-launch pipeline through the explicit-map entry point on the same map
+    mx, my = ctx.dump_coords(rots[1], 0)
+    bgr = V.nv12_to_bgr(src[1], sw, sh)[0]
+    two = V.remap_u8(bgr, mx, my, border=(0, 0, 0))
+    torch.cuda.synchronize()
+    assert torch.equal(two.reshape(oh, ow * 3), dst[1, :, :ow * 3])
+    ctx.close()
+
+
 # ---- batching, pitches, host path -----------------------------------------------------------------
 @pytest.mark.parametrize("variant", [POLY, TILED])
 def test_split_batches_equal_unsplit(V, variant):

@@ -21,7 +21,7 @@ class VawParams(C.Structure):
         ("out_width", C.c_int32), ("out_height", C.c_int32),
         ("format", C.c_int32), ("interpolation", C.c_int32),
         ("border", C.c_uint8 * 4), ("variant", C.c_int32), ("src_distortion", C.c_float * 4),
-        ("reserved", C.c_int32 * 3),
+        ("projection", C.c_int32), ("reserved", C.c_int32 * 2),
     ]
 
 

@@ -607,6 +607,16 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
         return fail(nullptr, VAW_ERR_UNSUPPORTED, "NV12 -> BGR24 in one launch: INTER_LINEAR, variant AUTO or POLY");
     if (p.variant < VAW_VARIANT_AUTO || p.variant > VAW_VARIANT_TEX || p.variant == VAW_VARIANT_PIPE)
         return fail(nullptr, VAW_ERR_UNSUPPORTED, "kernel variant not available in this build (PIPE was retired in round 2)");
+    if (p.projection < 0 || p.projection > 3) return fail(nullptr, VAW_ERR_INVALID, "projection is 0..3");
+    if (p.projection != 0) {
+        // only createMap.cl's pair has an fp32 operation order (variant GATHER); the others exist on the
+        // polynomial variants, whose coordinates come from double-precision anchors
+        const bool poly_fmt = p.format == VAW_FORMAT_NV12 || p.format == VAW_FORMAT_NV12_TO_BGR24;
+        if (!poly_fmt || p.variant == VAW_VARIANT_GATHER || p.interpolation != VAW_INTER_LINEAR)
+            return fail(nullptr, VAW_ERR_UNSUPPORTED, "rectilinear input / fisheye output: NV12 sources, INTER_LINEAR, variants AUTO / POLY / TILED");
+        if ((p.projection & 1) && (p.src_distortion[0] != 0 || p.src_distortion[1] != 0 || p.src_distortion[2] != 0 || p.src_distortion[3] != 0))
+            return fail(nullptr, VAW_ERR_INVALID, "fisheye distortion coefficients with a rectilinear input camera");
+    }
     if (p.variant >= VAW_VARIANT_POLY && p.format != VAW_FORMAT_NV12 && p.format != VAW_FORMAT_NV12_TO_BGR24)
         return fail(nullptr, VAW_ERR_UNSUPPORTED, "variants POLY, TILED and TEX exist for NV12 only");
     // `short` indices in createMap.cl:10-11 and int16 taps in cv::remap cap both sizes
@@ -645,6 +655,7 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
                ((unsigned)p.border[3] << 24);
     g.force_exact = (!centre_ok(g.scx) || !centre_ok(g.scy)) ? 1 : 0;
     g.nearest = p.interpolation == VAW_INTER_NEAREST ? 1 : 0;
+    g.projection = p.projection;
     g.has_dist = 0;
     for (int i = 0; i < 4; ++i) {
         g.kd[i] = p.src_distortion[i];
@@ -702,6 +713,7 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
         d.has_dist = g.has_dist;
         d.src_w = g.src_w; d.src_h = g.src_h; d.out_w = g.out_w; d.out_h = g.out_h;
         d.piece_h = ph;
+        d.projection = p.projection;
         make_basis(ctx->basis, ph);
         ctx->pieces_per_frame = (size_t)vaw::pieces_x(g.out_w) * vaw::pieces_y(g.out_h, ph);
         e = cudaEventCreateWithFlags(&ctx->table_free, cudaEventDisableTiming);

@@ -132,7 +132,7 @@ extern "C" int vaw_params_from_cameras(const vaw_camera* input, const vaw_camera
                                        vaw_params* p)
 {
     if (!input || !output || !p) return VAW_ERR_INVALID;
-    if (input->model != 1 || output->model != 0) return VAW_ERR_UNSUPPORTED;  // fisheye in, rectilinear out (createMap.cl)
+    if (input->model < 0 || input->model > 1 || output->model < 0 || output->model > 1) return VAW_ERR_INVALID;
     p->src_center_x = input->matrix[2];
     p->src_center_y = input->matrix[5];
     p->src_focal_x = input->matrix[0];
@@ -152,6 +152,8 @@ extern "C" int vaw_params_from_cameras(const vaw_camera* input, const vaw_camera
     p->format = format;
     p->interpolation = VAW_INTER_LINEAR;  // the constructor's default (FrameSourceWarp.hpp:90)
     p->variant = VAW_VARIANT_AUTO;
+    // CameraModel (FrameSourceWarp.hpp:23-26): FISHEYE in + RECTILINEAR out is createMap.cl's pair (0)
+    p->projection = (input->model == 0 ? 1 : 0) | (output->model == 1 ? 2 : 0);
     for (int i = 0; i < 4; ++i) p->src_distortion[i] = (float)input->distortion[i];  // zeros for the presets (:35)
     return VAW_OK;
 }

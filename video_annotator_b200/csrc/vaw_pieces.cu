@@ -12,6 +12,7 @@
 // This is a few hundred double-precision instructions per 4096 output pixels.
 #include <math.h>
 #include "vaw_pieces.cuh"
+#include "vaw_project64.cuh"
 
 namespace vaw {
 
@@ -27,95 +28,7 @@ constexpr int kNodesU = kChunk * kDegU + 1;      // 161 shared nodes
 #endif
 constexpr int kThreads = VAW_BUILDER_THREADS;
 
-struct RotD { double r[9]; };
 struct RotF { float r[9]; };
-
-struct Ray { double mx, my, q0, q1, q2; };
-
-// atan(t) / t on t in [0, 1] as a polynomial in s = t^2 (tools/fit_atan64.py, degree 13: relative error
-// 1.8e-12, i.e. < 1e-8 px at 4K; the anchors need ~1e-10).  The library atan() costs a double-precision
-// division subroutine per call; together with 1 / q2 those calls were 16 % of the builder's instructions.
-__device__ __forceinline__ double atan_over_t(double s)
-{
-    const double c[14] = {
-9.99999999998195555e-01,
-    -3.33333332624654421e-01,
-    1.99999953399910668e-01,
-    -1.42855923902450388e-01,
-    1.11094283515041928e-01,
-    -9.07679894442711965e-02,
-    7.61425097816378765e-02,
-    -6.36609554917869219e-02,
-    5.04556591859826667e-02,
-    -3.52678487665738852e-02,
-    1.99375722877763104e-02,
-    -8.24198211827211098e-03,
-    2.16282427498169566e-03,
-    -2.66606699012429877e-04
-    };
-    double p = c[13];
-#pragma unroll
-    for (int i = 12; i >= 0; --i) p = fma(p, s, c[i]);
-    return p;
-}
-
-// 1 / x for x in the certified range [2^-6, 2^6]: single-precision seed, two Newton steps (relative error
-// 2^-23 -> 2^-46 -> double rounding).  Outside that range the piece is not certified anyway.
-__device__ __forceinline__ double rcp_newton64(double x)
-{
-    double y = (double)__frcp_rn((float)x);
-    y = fma(y, fma(-x, y, 1.0), y);
-    y = fma(y, fma(-x, y, 1.0), y);
-    return y;
-}
-
-// createMap.cl:15-49 in double precision, for a (possibly fractional) output position.
-__device__ __forceinline__ Ray project(const GeomD& g, const RotD& R, double u, double v)
-{
-    // one reciprocal per divisor (1e-16 relative error; the anchors need ~1e-10)
-    const double x = (u - g.mcx) * g.inv_mfx, y = (v - g.mcy) * g.inv_mfy;
-    Ray o;
-    o.q0 = R.r[0] * x + R.r[1] * y + R.r[2];
-    o.q1 = R.r[3] * x + R.r[4] * y + R.r[5];
-    o.q2 = R.r[6] * x + R.r[7] * y + R.r[8];
-    const double iq = rcp_newton64(o.q2);
-    const double c0 = o.q0 * iq, c1 = o.q1 * iq;
-    const double r2 = c0 * c0 + c1 * c1;
-    const double ir = rsqrt(r2);
-    const double r = r2 * ir;
-    // atan(r)/r is analytic in r^2; the series avoids 0/0 (the reference's NaN at r == 0 is
-    // reproduced by sending the piece that contains the axis to the per-pixel path)
-    // theta / r: atan(r) / r for r <= 1, (pi/2 - atan(1/r)) / r beyond; the series near the axis avoids 0 * inf
-    // (the reference's NaN at r == 0 is reproduced by sending the piece that contains the axis to the per-pixel path)
-    double k;
-    if (r > 1.0) {
-        const double t2 = ir * ir;
-        k = (1.5707963267948966 - ir * atan_over_t(t2)) * ir;
-    } else if (r > 1e-4) {
-        k = atan_over_t(r2);
-    } else {
-        k = 1.0 - r2 * (1.0 / 3.0 - r2 * 0.2);
-    }
-    if (g.has_dist) {  // extension: cv::fisheye distortion, theta_d / r = (theta / r) (1 + k1 theta^2 + ... + k4 theta^8)
-        const double th2 = k * k * r2;
-        k *= 1.0 + th2 * (g.kd[0] + th2 * (g.kd[1] + th2 * (g.kd[2] + th2 * g.kd[3])));
-    }
-    o.mx = g.scx + c0 * k * g.sfx;
-    o.my = g.scy + c1 * k * g.sfy;
-    return o;
-}
-
-// only the rotated ray (createMap.cl:22-30): enough for the regularity certificate
-__device__ __forceinline__ Ray ray_only(const GeomD& g, const RotD& R, double u, double v)
-{
-    const double x = (u - g.mcx) * g.inv_mfx, y = (v - g.mcy) * g.inv_mfy;
-    Ray o;
-    o.q0 = R.r[0] * x + R.r[1] * y + R.r[2];
-    o.q1 = R.r[3] * x + R.r[4] * y + R.r[5];
-    o.q2 = R.r[6] * x + R.r[7] * y + R.r[8];
-    o.mx = o.my = 0.0;
-    return o;
-}
 
 // Anchor node positions: 128 (ig / 5) + 128 (ig % 5) / 5 and ph (jg / 3) + ph (jg % 3) / 3.  The quotients are
 // written as correctly rounded constants (ph is a power of two, so scaling commutes with the rounding): the
@@ -261,7 +174,9 @@ build_pieces_kernel(const GeomD g, const PieceBasis basis, const float* __restri
             pos0 = pos0 && a.q0 >= eps; neg0 = neg0 && a.q0 <= -eps;
             pos1 = pos1 && a.q1 >= eps; neg1 = neg1 && a.q1 <= -eps;
         }
-        ok = ok && (pos0 || neg0 || pos1 || neg1);  // optical axis not inside (NaN pixel, createMap.cl:38-39)
+        // optical axis not inside: the reference yields NaN at r == 0 (createMap.cl:38-39), which only the per-pixel
+        // path reproduces; the other projection pairs are analytic there
+        if (g.projection == 0) ok = ok && (pos0 || neg0 || pos1 || neg1);
         PieceRec& rec = recs[p];
         // coordinate range: |offset| <= L1 norm of the non-constant coefficients (|s|, |t| <= 1)
         double lo[2], hi[2];

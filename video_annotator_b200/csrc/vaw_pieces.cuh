@@ -87,6 +87,7 @@ struct GeomD {  // the 8 fp32 scalars of FrameSourceWarp.cpp:283-290, widened ex
     int piece_h;
     int has_dist;  // any kd != 0
     int tile_cap;  // bytes of shared memory a tile may take with a 128-byte-multiple pitch (0: always the tightest pitch)
+    int projection;  // 0 = createMap.cl (fisheye in, rectilinear out); bit 0: rectilinear input; bit 1: fisheye output
 };
 
 inline __host__ __device__ int pieces_x(int out_w) { return (out_w + kPieceW - 1) / kPieceW; }

@@ -11,6 +11,7 @@
 #include "vaw_pieces.cuh"
 #include "vaw_sample.cuh"
 #include "vaw_internal.h"
+#include "vaw_project64.cuh"
 
 namespace vaw {
 
@@ -232,6 +233,27 @@ __device__ __forceinline__ void sample_rows_checked(const Geom& g, const PlaneRe
 // Per-pixel op-for-op coordinates of a row pair (pieces without a polynomial certificate).
 __device__ __forceinline__ void exact_rows(const Geom& g, const Rot& R, int u_lo, int u0, int v0, float2 (&m)[2][4])
 {
+    if (g.projection != 0) {
+        // the projection pairs createMap.cl does not have: no fp32 operation order to follow, so the few
+        // uncertified pieces get the double-precision projection, rounded once
+        GeomD d;
+        d.scx = g.scx; d.scy = g.scy; d.sfx = g.sfx; d.sfy = g.sfy;
+        d.mcx = g.mcx; d.mcy = g.mcy; d.mfx = g.mfx; d.mfy = g.mfy;
+        d.inv_mfx = 1.0 / d.mfx; d.inv_mfy = 1.0 / d.mfy;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d.kd[i] = g.kd[i];
+        d.has_dist = g.has_dist;
+        d.projection = g.projection;
+        RotD Rd;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Rd.r[i] = (double)R.r[i];
+        for (int r = 0; r < 2; ++r)
+            for (int i = 0; i < 4; ++i) {
+                const Ray p = project(d, Rd, (double)(u0 + i), (double)(v0 + r));
+                m[r][i] = make_float2((float)p.mx, (float)p.my);
+            }
+        return;
+    }
     const float4 xs = __ldg(reinterpret_cast<const float4*>(g.xtab + u0));
     const float2 ys = __ldg(reinterpret_cast<const float2*>(g.ytab + v0));
     const ColTerms c[4] = {col_terms(xs.x, R), col_terms(xs.y, R), col_terms(xs.z, R), col_terms(xs.w, R)};
