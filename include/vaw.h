@@ -282,6 +282,29 @@ int vaw_nv12_to_bgr(const uint8_t *src, int width, int height, int src_pitch, si
                     uint8_t *dst, int dst_pitch, size_t dst_frame_stride, int n_frames, int device,
                     void *stream);
 
+/* ---- motion measurement ---------------------------------------------------------------
+ * The tracking step of FrameSourceWarp::consume_frame (opencv/FrameSourceWarp.cpp:421-427 ->
+ * find_point_pairs_with_optical_flow, :242-270): cv::calcOpticalFlowPyrLK(prev_frame, current_frame,
+ * prev_corners) with OpenCV's defaults (winSize 21x21, maxLevel 3, 30 iterations / eps 0.01,
+ * minEigThreshold 1e-4) on the luma planes of consecutive frames.  A vaw_flow keeps the image pyramid
+ * (cv::pyrDown, bit-exact) and the Scharr derivatives of the previous and the current frame in device
+ * memory: vaw_flow_push_frame builds the pyramid of a new frame (a DEVICE luma plane), vaw_flow_track
+ * follows HOST point arrays (x, y pairs) from the previous into the current frame; status[i] = 1 where the
+ * flow was found (the reference keeps exactly those pairs, :262-268).  The arithmetic is OpenCV's
+ * fixed-point scheme (oracle/lk_ref.py, pinned to cv2.calcOpticalFlowPyrLK).
+ * vaw_flow_get_level: a pyramid level (which: 0 previous, 1 current) and its derivatives (dx, dy int16
+ * pairs) copied to host buffers, for parity tests. */
+typedef struct vaw_flow vaw_flow;
+int vaw_flow_create(int width, int height, int device, vaw_flow **out);
+void vaw_flow_destroy(vaw_flow *flow);
+const char *vaw_flow_last_error(const vaw_flow *flow);
+int vaw_flow_levels(const vaw_flow *flow);
+int vaw_flow_push_frame(vaw_flow *flow, const uint8_t *luma, int pitch, void *stream);
+int vaw_flow_track(vaw_flow *flow, const float *prev_pts_xy, int n, float *next_pts_xy, uint8_t *status,
+                   void *stream);
+int vaw_flow_get_level(vaw_flow *flow, int which, int level, uint8_t *image_host, int16_t *deriv_host,
+                       int *width, int *height);
+
 /* ---- synthetic frames (decode is out of scope; BASELINE.json north_star) ------------
  * Fill n_frames NV12 frames in device memory with the integer test pattern
  * (frame index first_index + i). */

@@ -182,3 +182,21 @@ if __name__ == "__main__":
     camera_table()
     nv12_small()
     print("golden fixtures written to", HERE)
+
+
+def make_lk_fixture():
+    """tests/golden/lk_small.npz: a 160x120 textured frame pair, 26 points (two of them at / outside the frame edge)
+    and the real cv2.calcOpticalFlowPyrLK / cv2.pyrDown answers (run: python tests/golden/make_golden.py --lk)."""
+    import cv2
+    from tests.test_oracle_flow import _textured_pair
+    prev, nxt = _textured_pair(120, 160, 11, angle_deg=0.8, shift=(1.7, -1.2))
+    pts = cv2.goodFeaturesToTrack(prev, 24, 0.01, 12).reshape(-1, 2).astype(np.float32)
+    pts = np.concatenate([pts, np.array([[1.0, 1.0], [-30.0, 5.0]], np.float32)])
+    ref, st, _ = cv2.calcOpticalFlowPyrLK(prev, nxt, pts, None)
+    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "lk_small.npz"), prev=prev, next=nxt, pts=pts,
+                        cv_next=ref.reshape(-1, 2), cv_status=st.reshape(-1), cv_pyr1=cv2.pyrDown(prev),
+                        cv_version=np.array(cv2.__version__))
+
+
+if __name__ == "__main__" and "--lk" in sys.argv:
+    make_lk_fixture()

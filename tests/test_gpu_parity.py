@@ -597,7 +597,7 @@ def test_pitched_buffers_and_untouched_padding(V, oracle):
     ctx.close()
 
 
-@pytest.mark.parametrize("variant", [0, 4, 5])
+@pytest.mark.parametrize("variant", [0, 5])
 @pytest.mark.parametrize("src_pitch,dst_pitch", [(3904, 3968), (3842, 3846), (3840, 3844)])
 def test_pitched_4k_frames(V, oracle, src_pitch, dst_pitch, variant):
     """Row pitches larger than the width at BASELINE size: a 16-byte-multiple source pitch keeps the
@@ -627,7 +627,7 @@ def test_pitched_4k_frames(V, oracle, src_pitch, dst_pitch, variant):
     ctx.close()
 
 
-@pytest.mark.parametrize("variant", [0, 4])
+@pytest.mark.parametrize("variant", [0, 2])
 @pytest.mark.parametrize("out_size", [(2, 2), (6, 4), (130, 18), (254, 34), (258, 30)])
 def test_ragged_output_sizes(V, oracle, out_size, variant):
     """Output sizes that do not fill a warp row / CTA tile; guard bytes after the frame stay intact."""

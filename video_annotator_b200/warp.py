@@ -302,6 +302,61 @@ class ClipWarper:
             pass
 
 
+class FlowTracker:
+    """cv::calcOpticalFlowPyrLK (defaults) between consecutive frames, on the GPU (vaw_flow_*): the tracking
+    step of FrameSourceWarp::consume_frame, FrameSourceWarp.cpp:421-427 / :242-270."""
+
+    def __init__(self, width, height, device=0):
+        lib = _lib.load()
+        h = C.c_void_p()
+        rc = lib.vaw_flow_create(width, height, device, C.byref(h))
+        if rc != 0:
+            raise VawError(rc, (lib.vaw_flow_last_error(None) or b"").decode())
+        self._h, self._lib, self.size = h, lib, (width, height)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise VawError(rc, (self._lib.vaw_flow_last_error(self._h) or b"").decode())
+
+    @property
+    def levels(self):
+        return int(self._lib.vaw_flow_levels(self._h))
+
+    def push_frame(self, luma, pitch=None, stream=None):
+        """luma: CUDA uint8 tensor holding the plane (an NV12 frame works: its first `height` rows)."""
+        self._check(self._lib.vaw_flow_push_frame(self._h, luma.data_ptr(), pitch or self.size[0], _stream_handle(stream)))
+
+    def track(self, prev_pts, stream=None):
+        """prev_pts: (N, 2) float32 host array -> (next_pts (N, 2) float32, status (N,) bool)."""
+        pts = np.ascontiguousarray(prev_pts, np.float32).reshape(-1, 2)
+        nxt = np.zeros_like(pts)
+        st = np.zeros(len(pts), np.uint8)
+        self._check(self._lib.vaw_flow_track(self._h, pts.ctypes.data_as(_lib.f32p), len(pts), nxt.ctypes.data_as(_lib.f32p),
+                                             st.ctypes.data_as(_lib.u8p), _stream_handle(stream)))
+        return nxt, st.astype(bool)
+
+    def level(self, which, level):
+        """(image (h, w) uint8, dx (h, w) int16, dy (h, w) int16) of a pyramid level; which: 0 previous, 1 current."""
+        w, h = C.c_int(0), C.c_int(0)
+        self._check(self._lib.vaw_flow_get_level(self._h, which, level, None, None, C.byref(w), C.byref(h)))
+        img = np.zeros((h.value, w.value), np.uint8)
+        der = np.zeros((h.value, w.value, 2), np.int16)
+        self._check(self._lib.vaw_flow_get_level(self._h, which, level, img.ctypes.data_as(_lib.u8p),
+                                                 der.ctypes.data_as(C.POINTER(C.c_int16)), C.byref(w), C.byref(h)))
+        return img, der[:, :, 0].copy(), der[:, :, 1].copy()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.vaw_flow_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def synth_nv12(dst, width, height, n_frames, first_index=0, seed=20260001, white_noise=False,
                device=0, stream=None):
     """Fill a CUDA uint8 tensor with n_frames tightly packed synthetic NV12 frames."""
