@@ -346,6 +346,9 @@ int vaw_piece_stats(vaw_ctx *ctx, const double rotation[9], uint32_t counts[8], 
  * tap inside the source, bit 2 = every tap outside (border fill).  For the accuracy sweeps of the tests. */
 int vaw_piece_flags(vaw_ctx *ctx, const double rotation[9], uint32_t *flags, int capacity, int *pieces_x_out,
                     int *pieces_y_out, int *piece_h_out, void *stream);
+/* Four words per piece for `rotation`, row-major: flags, shared-memory bytes the piece's source box needs
+ * (0: none, 0x7fffffff: cannot be staged), tile row pitch, luma rows | chroma rows << 16.  Analysis / tests. */
+int vaw_piece_tiles(vaw_ctx *ctx, const double rotation[9], uint32_t *out, int capacity, void *stream);
 int vaw_selftest_math(int device, uint32_t seed, uint64_t n_per_thread, uint64_t mismatches[4]);
 /* Instrumented builds only (-DVAW_BOUNDS_CHECK): number of shared-memory tap addresses of variant
  * TILED that fell outside their staged tile since the library was loaded; -1 in a normal build. */

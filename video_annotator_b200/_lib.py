@@ -83,6 +83,7 @@ SIGNATURES = {
     "vaw_piece_stats": (C.c_int, [C.c_void_p, f64p, C.POINTER(C.c_uint32), C.c_void_p]),
     "vaw_piece_flags": (C.c_int, [C.c_void_p, f64p, C.POINTER(C.c_uint32), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                   C.POINTER(C.c_int), C.c_void_p]),
+    "vaw_piece_tiles": (C.c_int, [C.c_void_p, f64p, C.POINTER(C.c_uint32), C.c_int, C.c_void_p]),
     "vaw_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "vaw_debug_oob_count": (C.c_longlong, [C.c_int]),
     "vaw_selftest_math": (C.c_int, [C.c_int, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint64)]),

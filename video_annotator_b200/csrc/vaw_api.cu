@@ -1184,6 +1184,30 @@ int vaw_piece_flags(vaw_ctx* ctx, const double rotation[9], uint32_t* flags, int
     return VAW_OK;
 }
 
+int vaw_piece_tiles(vaw_ctx* ctx, const double rotation[9], uint32_t* out, int capacity, void* stream)
+{
+    if (!ctx) return VAW_ERR_INVALID;
+    if (!rotation || !out) return fail(ctx, VAW_ERR_INVALID, "null argument");
+    if (ctx->variant == VAW_VARIANT_GATHER) return fail(ctx, VAW_ERR_UNSUPPORTED, "variant GATHER has no pieces");
+    if ((size_t)capacity < ctx->pieces_per_frame) return fail(ctx, VAW_ERR_INVALID, "buffer too small");
+    DeviceGuard dg(ctx->device);
+    const vaw::Rot R = rot_from_double(rotation);
+    cudaError_t e = vaw::launch_build_pieces(ctx->gd, ctx->basis, nullptr, R.r, 1, ctx->dump_table, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "piece table launch");
+    ctx->launches++;
+    std::string host(ctx->pieces_per_frame * sizeof(vaw::PieceRec), '\0');
+    VAW_CUDA(ctx, cudaMemcpyAsync(&host[0], ctx->dump_table, host.size(), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    VAW_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+    const vaw::PieceRec* rec = reinterpret_cast<const vaw::PieceRec*>(host.data());
+    for (size_t i = 0; i < ctx->pieces_per_frame; ++i) {
+        out[4 * i + 0] = rec[i].flags;
+        out[4 * i + 1] = (uint32_t)vaw::tile_need_bytes(rec[i]);
+        out[4 * i + 2] = rec[i].stage.pl;
+        out[4 * i + 3] = (uint32_t)rec[i].stage.nrows | ((uint32_t)rec[i].stage.cnrows << 16);
+    }
+    return VAW_OK;
+}
+
 int vaw_remap_u8(const uint8_t* src, int src_width, int src_height, int src_pitch, int channels,
                  const float* map_x, const float* map_y, int rows, int cols, int map_pitch,
                  uint8_t* dst, int dst_pitch, const uint8_t border[4], int device, void* stream)

@@ -29,6 +29,7 @@
 #include <cuda.h>
 #include <stdint.h>
 #include <algorithm>
+#include <cstdlib>
 #include <atomic>
 #include "vaw_internal.h"
 #include "vaw_poly.cuh"
@@ -57,7 +58,7 @@ constexpr int kWarps = 4;
 //   - per row pair a lane makes 2 x 2 luma samples and the one chroma sample of that quad; a warp
 //     store writes 64 contiguous bytes, the LDS of a warp stay within one 128-byte window per row
 //     exactly as with the round-1 pair mapping (2 columns per lane).
-constexpr int kQuadTileOffset = 128;  // [mbarrier | tile (TMA: 128-byte aligned)]
+constexpr int kQuadRecOffset = 16, kQuadTileOffset = 256;  // [tile mbarrier | record mbarrier | record (240 B) | tile (TMA: 128-byte aligned)]
 
 struct ColPoly2 {
     float2 a[2][kNv];  // [column][power of t]
@@ -76,7 +77,7 @@ __device__ __forceinline__ void derive2(const PieceRec* __restrict__ rec, int co
     for (int k = 0; k < kNv; ++k) {
         float2 ci[kNu];
 #pragma unroll
-        for (int i = 0; i < kNu; ++i) ci[i] = __ldg(c2 + i * kNv + k);
+        for (int i = 0; i < kNu; ++i) ci[i] = c2[i * kNv + k];
         float2 a0 = ci[kDegU], a1 = ci[kDegU];
 #pragma unroll
         for (int i = kDegU - 1; i >= 0; --i) {
@@ -157,9 +158,10 @@ __device__ __forceinline__ void rows_quad(const Geom& g, const ColPoly2& cp, uns
     }
 }
 
-// kCtas = resident CTAs per SM the instantiation is compiled for: 8 (64 registers) where the tiles are small
-// enough for seven or eight CTAs to share an SM, 6 (80 registers, no spills in the fallback paths, fewer
-// rematerialised constants) where shared memory allows six or fewer anyway (measured: C5 +2.6 %, C2 +3 %).
+// kCtas = resident CTAs per SM the instantiation is compiled for, i.e. its register budget: 8 (64 registers), 7 (72:
+// the C3 tiles let seven CTAs share an SM, and the eight registers the 64-register build gives away buy nothing
+// there -- measured 0.651 against 0.661 ms) or 6 (80 registers, no spills in the fallback paths) where shared
+// memory allows six or fewer anyway (C5 +2.6 %, C2 +3 %).
 template <int kCtas>
 __global__ void __launch_bounds__(32 * kWarps, kCtas)
 warp_nv12_quad_kernel(const Geom g, const FrameBatch b, const PieceRec* __restrict__ table,
@@ -171,13 +173,28 @@ warp_nv12_quad_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
     const int ph = g.piece_h;
     const int npx = (int)gridDim.x, npy = (int)gridDim.y;
     const PieceRec* rec = table + ((size_t)frame * npy + py) * npx + px;
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(rec));
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(rec) + 128));
-    const float4 rec_tail = __ldg(reinterpret_cast<const float4*>(rec) + 12);  // base.x, base.y, flags, pad
-    const int4 raw = __ldg(reinterpret_cast<const int4*>(rec) + 14);          // PieceStage
-    const unsigned mbar = smem_u32(smem);
-    if (tid == 0) mbar_init(mbar, 1);
-    __syncthreads();  // the barrier is initialised for every warp (nothing has been waited for yet)
+    // The record comes in by ONE bulk copy into shared memory (240 bytes, its own mbarrier); everything below reads
+    // it from there.  Round 2's profile: warps spent 60 % of their lifetime before the row loop, most of it on the
+    // ~40 dependent global loads of the record (flags, stage, 36 coefficient loads that missed L1).  The record of
+    // the same piece of the NEXT frame is pulled into L2 now: by the time its CTA starts (about one frame's worth
+    // of CTAs later) the table entry the builder wrote has long been evicted by the frame data streaming through.
+    const unsigned mbar = smem_u32(smem), mbar_rec = mbar + 8, rec_s = mbar + kQuadRecOffset;
+    if (tid == 0) {
+        mbar_init(mbar, 1);
+        mbar_init(mbar_rec, 1);
+        mbar_expect_tx(mbar_rec, (unsigned)sizeof(PieceRec));
+        bulk_g2s(rec_s, rec, (unsigned)sizeof(PieceRec), mbar_rec);
+        if (frame + 1 < (int)gridDim.z) {
+            const char* nxt = reinterpret_cast<const char*>(rec + (size_t)npy * npx);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + 128));
+        }
+    }
+    __syncthreads();  // the barriers are initialised for every warp
+    mbar_wait_parked(mbar_rec, 0, 4000);
+    const PieceRec* rs = reinterpret_cast<const PieceRec*>(smem + kQuadRecOffset);
+    const float4 rec_tail = *(reinterpret_cast<const float4*>(rs) + 12);  // base.x, base.y, flags, pad
+    const int4 raw = *(reinterpret_cast<const int4*>(rs) + 14);          // PieceStage
 
     const unsigned flags = __float_as_uint(rec_tail.z);
     const int u_lo = px * kPieceW, v_base = py * ph;
@@ -192,12 +209,13 @@ warp_nv12_quad_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
         const unsigned cw = ((g.border >> 8) & 0xffffu) * 0x00010001u;
         if (((reinterpret_cast<uintptr_t>(dst) | (uintptr_t)g.dst_pitch) & 15) == 0 && u_lo + kPieceW <= g.out_w) {
             // 16 bytes per lane: 8 lanes per row, 16 rows per pass of the CTA
+            constexpr int kPass = 4 * kWarps;
             const int sub = tid >> 3, col = (tid & 7) * 16;
             const uint4 y4 = make_uint4(yw, yw, yw, yw), c4 = make_uint4(cw, cw, cw, cw);
             uint8_t* yrow = dst + (size_t)(v_base + sub) * g.dst_pitch + u_lo + col;
-            for (int r = sub; r < rows; r += 16, yrow += 16 * (size_t)g.dst_pitch) *reinterpret_cast<uint4*>(yrow) = y4;
+            for (int r = sub; r < rows; r += kPass, yrow += kPass * (size_t)g.dst_pitch) *reinterpret_cast<uint4*>(yrow) = y4;
             uint8_t* crow = dst + (size_t)(g.out_h + (v_base >> 1) + sub) * g.dst_pitch + u_lo + col;
-            if (sub < rows / 2) *reinterpret_cast<uint4*>(crow) = c4;
+            for (int r = sub; r < rows / 2; r += kPass, crow += kPass * (size_t)g.dst_pitch) *reinterpret_cast<uint4*>(crow) = c4;
             return;
         }
         // ragged / unaligned: 4 columns per lane, rows split over the warps like the round-1 kernel
@@ -268,7 +286,11 @@ warp_nv12_quad_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
     uint8_t* ctile = ltile + nrows * pl;
 
     // ---- thread 0: launch the tile loads ------------------------------------------------------------
+#ifdef VAW_ABL_NO_TMA  // analysis only: no tile loads (the loop samples whatever the shared memory holds)
+    if (tid == 0 && g.out_w < 0) {
+#else
     if (tid == 0) {
+#endif
         mbar_expect_tx(mbar, (unsigned)(pl * (nrows + cnrows)));
         const int mi = (pl - kTileMinPitch) / kTilePitchStep;
         const CUtensorMap *map = &maps.m[mi], *map32 = &maps.m32[mi], *map4 = &maps.m4[mi];
@@ -287,10 +309,16 @@ warp_nv12_quad_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
     const int wx = w & 1, wy = w >> 1, hrows = ph >> 1;
     const int col0 = 64 * wx + 2 * lane;  // within the piece
     ColPoly2 cp;
-    derive2(rec, col0, cp);
+    derive2(rs, col0, cp);
     cp.base = make_float2(rec_tail.x, rec_tail.y);
 
-    mbar_wait(mbar, 0);  // the tile has landed
+#ifndef VAW_ABL_NO_TMA
+    mbar_wait_parked(mbar, 0, 4000);  // the tile has landed (the warp is parked, not spinning, until then)
+#endif
+#ifdef VAW_ABL_NO_LOOP  // analysis only: the per-piece set-up without the row loop
+    if (cp.a[0][0].x + cp.a[1][3].y == 12345.f) dst[0] = 1;
+    return;
+#endif
 
     if (!(flags & kPieceInterior)) {  // straddles the frame border: paint the outside cells
         const unsigned by_ = g.border & 255u, bu = (g.border >> 8) & 255u, bv = (g.border >> 16) & 255u;
@@ -344,6 +372,16 @@ int tile_need_bytes(const PieceRec& rec)
     return pl * (nrows + cnrows);
 }
 
+template <int kCtas>
+static cudaError_t configure_quad()
+{
+    cudaError_t e = cudaFuncSetAttribute(warp_nv12_quad_kernel<kCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         tile_smem_bytes(kTileCapMax));
+    // all of the SM's shared memory for tiles: the taps never go through L1
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(warp_nv12_quad_kernel<kCtas>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    return e;
+}
 cudaError_t launch_warp_nv12_tile(const Geom& g, const FrameBatch& b, const PieceRec* table, const TileMaps& maps,
                                   cudaStream_t st)
 {
@@ -354,23 +392,19 @@ cudaError_t launch_warp_nv12_tile(const Geom& g, const FrameBatch& b, const Piec
     cudaGetDevice(&dev);
     const bool tracked = dev >= 0 && dev < 64;
     if (!tracked || !configured[dev].load(std::memory_order_acquire)) {
-        cudaError_t e = cudaFuncSetAttribute(warp_nv12_quad_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             tile_smem_bytes(kTileCapMax));
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(warp_nv12_quad_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     tile_smem_bytes(kTileCapMax));
-        // all of the SM's shared memory for tiles: the taps never go through L1
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(warp_nv12_quad_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(warp_nv12_quad_kernel<6>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaError_t e = configure_quad<8>();
+        if (e == cudaSuccess) e = configure_quad<7>();
+        if (e == cudaSuccess) e = configure_quad<6>();
         if (e != cudaSuccess) return e;
         if (tracked) configured[dev].store(true, std::memory_order_release);
     }
     dim3 block(32, kWarps);
     dim3 grid(pieces_x(g.out_w), pieces_y(g.out_h, g.piece_h), b.n_frames);
-    if (maps.tile_cap <= tile_cap_for_ctas(7, kQuadTileOffset))
-        warp_nv12_quad_kernel<8><<<grid, block, tile_smem_bytes(maps.tile_cap), st>>>(g, b, table, maps);
-    else
-        warp_nv12_quad_kernel<6><<<grid, block, tile_smem_bytes(maps.tile_cap), st>>>(g, b, table, maps);
+    // the instantiation whose register budget matches the CTAs the tile capacity lets share an SM
+    const int smem = tile_smem_bytes(maps.tile_cap);
+    if (maps.tile_cap <= tile_cap_for_ctas(8, kQuadTileOffset)) warp_nv12_quad_kernel<8><<<grid, block, smem, st>>>(g, b, table, maps);
+    else if (maps.tile_cap <= tile_cap_for_ctas(7, kQuadTileOffset)) warp_nv12_quad_kernel<7><<<grid, block, smem, st>>>(g, b, table, maps);
+    else warp_nv12_quad_kernel<6><<<grid, block, smem, st>>>(g, b, table, maps);
     return cudaGetLastError();
 }
 

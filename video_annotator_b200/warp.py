@@ -239,6 +239,14 @@ class WarpContext:
         return dict(zip(("pieces", "poly", "interior", "outside", "max_tile_bytes", "tile_cap", "over_cap"),
                         [int(v) for v in out]))
 
+    def piece_tiles(self, rotation, stream=None):
+        # (pieces, 4) uint32: flags, tile bytes needed, tile pitch, luma rows | chroma rows << 16 (vaw_piece_tiles)
+        cap = ((self.out_size[0] + 127) // 128) * ((self.out_size[1] + 7) // 8)
+        out = np.zeros(cap * 4, np.uint32)
+        _, rp = _rot_arg(rotation)
+        _check(self._lib.vaw_piece_tiles(self._h, rp, out.ctypes.data_as(C.POINTER(C.c_uint32)), cap, _stream_handle(stream)), self._h)
+        return out.reshape(cap, 4)
+
     def piece_flags(self, rotation, stream=None):
         # (pieces_y, pieces_x) uint32 flags of the 128 x piece_h pieces for this rotation, and piece_h (vaw_piece_flags)
         cap = ((self.out_size[0] + 127) // 128) * ((self.out_size[1] + 7) // 8)
