@@ -304,6 +304,15 @@ int vaw_flow_track(vaw_flow *flow, const float *prev_pts_xy, int n, float *next_
                    void *stream);
 int vaw_flow_get_level(vaw_flow *flow, int which, int level, uint8_t *image_host, int16_t *deriv_host,
                        int *width, int *height);
+/* The corner step (opencv/FrameSourceWarp.cpp:228-240, called at :422 on the PREVIOUS frame): cv::goodFeaturesToTrack
+ * (image, corners, max_corners, quality, min_distance) with OpenCV's defaults otherwise (blockSize 3, Sobel 3,
+ * minimum-eigenvalue response; the reference passes 200, 0.01, 30).  which: 0 previous, 1 current frame of the
+ * tracker.  Writes up to `capacity` corners as (x, y) pairs to the HOST array, *n_out = the number found.  The
+ * response map and the candidate list are computed on the device; the ordered greedy distance filter runs on the
+ * host.  vaw_flow_get_response: the cv::cornerMinEigenVal map of the last call (width x height floats). */
+int vaw_flow_corners(vaw_flow *flow, int which, int max_corners, double quality, double min_distance,
+                     float *corners_xy, int capacity, int *n_out, void *stream);
+int vaw_flow_get_response(vaw_flow *flow, float *response_host);
 
 /* ---- synthetic frames (decode is out of scope; BASELINE.json north_star) ------------
  * Fill n_frames NV12 frames in device memory with the integer test pattern

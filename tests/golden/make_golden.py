@@ -174,7 +174,7 @@ def remap_cubic():
     np.savez_compressed(os.path.join(HERE, "remap_cubic.npz"), **out)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and not any(a.startswith("--") for a in sys.argv[1:]):
     cvt_nv12_bgr()
     remap_cases()
     remap_cubic()
@@ -198,5 +198,19 @@ def make_lk_fixture():
                         cv_version=np.array(cv2.__version__))
 
 
+def make_gftt_fixture():
+    """tests/golden/gftt_small.npz: a 200x150 textured frame with the real cv2.cornerMinEigenVal map and the real
+    cv2.goodFeaturesToTrack(image, 200, 0.01, 30) list (run: python tests/golden/make_golden.py --gftt)."""
+    import cv2
+    from tests.test_oracle_flow import _textured_pair
+    img, _ = _textured_pair(150, 200, 21)
+    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "gftt_small.npz"), image=img,
+                        cv_response=cv2.cornerMinEigenVal(img, 3, ksize=3),
+                        cv_corners=cv2.goodFeaturesToTrack(img, 200, 0.01, 30).reshape(-1, 2),
+                        cv_version=np.array(cv2.__version__))
+
+
 if __name__ == "__main__" and "--lk" in sys.argv:
     make_lk_fixture()
+if __name__ == "__main__" and "--gftt" in sys.argv:
+    make_gftt_fixture()

@@ -105,6 +105,61 @@ def test_lk_against_cv2_directly(V):
     ft.close()
 
 
+@pytest.mark.parametrize("shape,seed", [((270, 480), 1), ((1080, 1920), 2), ((2160, 3840), 3), ((241, 333), 4)])
+def test_corner_response_and_corners_equal_the_oracle(V, shape, seed):
+    """cv::goodFeaturesToTrack(image, 200, 0.01, 30) (FrameSourceWarp.cpp:230): the device response map equals the
+    oracle's bit for bit (same fp32 operations in the same order; the oracle is pinned to cv2.cornerMinEigenVal to
+    3e-8), hence the same candidates, and the host tail is OpenCV's ordered greedy filter: identical corner lists."""
+    import torch
+    from oracle import gftt_ref as G
+    h, w = shape
+    img, _ = _pair(h, w, seed)
+    ft = V.FlowTracker(w, h)
+    ft.push_frame(torch.from_numpy(img).cuda())
+    got = ft.corners(1)
+    want_resp = G.corner_min_eigen_val(img)
+    assert np.array_equal(ft.response(), want_resp)
+    want = G.select_corners(want_resp)
+    assert len(want) > 20
+    assert np.array_equal(got, want)
+    # other parameters of the selection: many corners, no distance filter, unlimited count
+    for mc, q, md in ((1000, 0.05, 8.0), (0, 0.3, 0.0), (25, 0.01, 60.5)):
+        assert np.array_equal(ft.corners(1, mc, q, md), G.select_corners(want_resp, mc, q, md)), (mc, q, md)
+    ft.close()
+
+
+def test_corners_on_white_noise_and_flat_frames(V):
+    """Edge cases: a flat frame has no corners; white noise has a candidate at about one pixel in nine (the
+    candidate list holds one in six)."""
+    import torch
+    from oracle import gftt_ref as G
+    ft = V.FlowTracker(640, 360)
+    ft.push_frame(torch.full((360, 640), 77, dtype=torch.uint8, device="cuda"))
+    assert len(ft.corners(1)) == 0
+    rng = np.random.default_rng(8)
+    img = rng.integers(0, 256, (360, 640)).astype(np.uint8)
+    ft.push_frame(torch.from_numpy(img).cuda())
+    assert np.array_equal(ft.corners(1, 0, 0.01, 3.0), G.good_features_to_track(img, 0, 0.01, 3.0))
+    # the previous frame is still there: which = 0
+    assert len(ft.corners(0)) == 0
+    ft.close()
+
+
+def test_corners_against_cv2_directly(V):
+    """Where cv2 is importable: the same corner list as the real cv2.goodFeaturesToTrack, no oracle in between."""
+    cv2 = pytest.importorskip("cv2")
+    import torch
+    img, _ = _pair(720, 1280, 12)
+    img = cv2.GaussianBlur(img, (0, 0), 1.5)
+    want = cv2.goodFeaturesToTrack(img, 200, 0.01, 30).reshape(-1, 2)
+    ft = V.FlowTracker(1280, 720)
+    ft.push_frame(torch.from_numpy(img).cuda())
+    got = ft.corners(1)
+    assert len(got) == len(want)
+    assert len(set(map(tuple, got.astype(int))) & set(map(tuple, want.astype(int)))) >= 0.98 * len(want)
+    ft.close()
+
+
 def test_flow_errors(V):
     with pytest.raises(V.VawError):
         V.FlowTracker(8, 8)

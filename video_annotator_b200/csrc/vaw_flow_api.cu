@@ -7,6 +7,8 @@
 // the previous and the current frame in device memory; pushing a frame builds its pyramid once (the reference
 // rebuilds both pyramids on every call), tracking reads both.  No CPU fallback.
 #include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <new>
 #include <string>
@@ -23,6 +25,11 @@ struct vaw_flow {
     float2 *d_prev = nullptr, *d_next = nullptr;
     uint8_t* d_status = nullptr;
     int capacity = 0;
+    // corner detection (allocated by the first vaw_flow_corners call)
+    float* d_eig = nullptr;
+    uint2* d_cand = nullptr;
+    unsigned* d_scalars = nullptr;  // [0] maximum of the response (float bits), [1] candidate count
+    unsigned cand_capacity = 0;
     std::string err;
 };
 
@@ -107,6 +114,7 @@ void vaw_flow_destroy(vaw_flow* f)
     for (int s = 0; s < 2; ++s)
         for (int l = 0; l < vaw::kFlowMaxLevels; ++l) { cudaFree(f->image[s][l]); cudaFree(f->deriv[s][l]); }
     cudaFree(f->d_prev); cudaFree(f->d_next); cudaFree(f->d_status);
+    cudaFree(f->d_eig); cudaFree(f->d_cand); cudaFree(f->d_scalars);
     delete f;
 }
 
@@ -157,6 +165,100 @@ int vaw_flow_track(vaw_flow* f, const float* prev_pts_xy, int n, float* next_pts
     if (e == cudaSuccess) e = cudaMemcpyAsync(status, f->d_status, n, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return flow_fail(f, VAW_ERR_CUDA, std::string("vaw_flow_track: ") + cudaGetErrorString(e));
+    return VAW_OK;
+}
+
+// find_corners of the reference (FrameSourceWarp.cpp:228-240): cv::goodFeaturesToTrack(image, corners, max_corners,
+// quality, min_distance) with blockSize 3 and the minimum-eigenvalue response.  Device: response map, its maximum,
+// candidate list (vaw_corners.cu).  Host: the inherently sequential tail, exactly as OpenCV orders it -- candidates by
+// decreasing response (ties: higher address first), greedy minimum-distance filter on a grid of min_distance cells.
+// Only as many candidates are sorted as the selection needs (the strongest 4096 first, then four times more ...).
+int vaw_flow_corners(vaw_flow* f, int which, int max_corners, double quality, double min_distance, float* corners_xy,
+                     int capacity, int* n_out, void* stream)
+{
+    if (!f) return VAW_ERR_INVALID;
+    if (!n_out || (capacity > 0 && !corners_xy) || capacity < 0 || which < 0 || which > 1 || !(quality > 0.0) || min_distance < 0.0)
+        return flow_fail(f, VAW_ERR_INVALID, "bad corner arguments");
+    *n_out = 0;
+    if (f->frames < 1 || (which == 0 && f->frames < 2)) return flow_fail(f, VAW_ERR_INVALID, "no such frame has been pushed");
+    Guard g(f->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int w = f->width, h = f->height;
+    cudaError_t e = cudaSuccess;
+    if (!f->d_eig) {
+        const size_t px = (size_t)w * h;
+        const unsigned cap = (unsigned)std::min<size_t>(px / 6 + 4096, 0x7fffffffu);
+        e = cudaMalloc(&f->d_eig, px * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&f->d_cand, (size_t)cap * sizeof(uint2));
+        if (e == cudaSuccess) e = cudaMalloc(&f->d_scalars, 2 * sizeof(unsigned));
+        if (e != cudaSuccess) {
+            cudaFree(f->d_eig); cudaFree(f->d_cand); cudaFree(f->d_scalars);
+            f->d_eig = nullptr; f->d_cand = nullptr; f->d_scalars = nullptr;
+            return flow_fail(f, VAW_ERR_CUDA, std::string("vaw_flow_corners: ") + cudaGetErrorString(e));
+        }
+        f->cand_capacity = cap;
+    }
+    const int s = which ? f->cur : 1 - f->cur;
+    e = vaw::launch_corner_response(f->image[s][0], w, h, f->lw[0], f->d_eig, f->d_scalars, st);
+    if (e == cudaSuccess)
+        e = vaw::launch_corner_candidates(f->d_eig, w, h, f->d_scalars, quality, f->d_cand, f->cand_capacity, f->d_scalars + 1, st);
+    unsigned scal[2] = {0, 0};
+    if (e == cudaSuccess) e = cudaMemcpyAsync(scal, f->d_scalars, sizeof scal, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return flow_fail(f, VAW_ERR_CUDA, std::string("vaw_flow_corners: ") + cudaGetErrorString(e));
+    if (scal[1] > f->cand_capacity) return flow_fail(f, VAW_ERR_UNSUPPORTED, "more corner candidates than one pixel in six: not a natural image");
+    std::vector<uint2> cand(scal[1]);
+    if (!cand.empty()) {
+        e = cudaMemcpy(cand.data(), f->d_cand, cand.size() * sizeof(uint2), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) return flow_fail(f, VAW_ERR_CUDA, std::string("vaw_flow_corners: ") + cudaGetErrorString(e));
+    }
+    // decreasing response; equal responses: the higher address (= larger y * w + x) first
+    const auto stronger = [](const uint2& a, const uint2& b) { return a.x != b.x ? a.x > b.x : a.y > b.y; };
+    const int cell = (int)std::lrint(min_distance);
+    const bool filter = min_distance >= 1.0;
+    const int gw = filter ? (w + cell - 1) / cell : 0, gh = filter ? (h + cell - 1) / cell : 0;
+    std::vector<std::vector<std::pair<int, int>>> grid((size_t)gw * gh);
+    const double md2 = min_distance * min_distance;
+    int n = 0;
+    size_t sorted = 0;
+    bool done = false;
+    while (sorted < cand.size() && !done) {
+        // extend the sorted prefix: the strongest `want` candidates of the rest, in order
+        const size_t want = std::min(cand.size() - sorted, sorted == 0 ? (size_t)4096 : 3 * sorted);
+        std::partial_sort(cand.begin() + sorted, cand.begin() + sorted + want, cand.end(), stronger);
+        for (size_t i = sorted; i < sorted + want; ++i) {
+            const int y = (int)(cand[i].y / (unsigned)w), x = (int)(cand[i].y - (unsigned)y * (unsigned)w);
+            bool good = true;
+            if (filter) {
+                const int xc = x / cell, yc = y / cell;
+                for (int yy = std::max(0, yc - 1); yy <= std::min(gh - 1, yc + 1) && good; ++yy)
+                    for (int xx = std::max(0, xc - 1); xx <= std::min(gw - 1, xc + 1) && good; ++xx)
+                        for (const auto& m : grid[(size_t)yy * gw + xx]) {
+                            const float dx = (float)(x - m.first), dy = (float)(y - m.second);
+                            if (dx * dx + dy * dy < md2) { good = false; break; }
+                        }
+                if (good) grid[(size_t)yc * gw + xc].emplace_back(x, y);
+            }
+            if (!good) continue;
+            if (n < capacity) { corners_xy[2 * n] = (float)x; corners_xy[2 * n + 1] = (float)y; }
+            ++n;
+            if ((max_corners > 0 && n == max_corners) || n == capacity) { done = true; break; }
+        }
+        sorted += want;
+    }
+    *n_out = n;
+    return VAW_OK;
+}
+
+// The response map of the last vaw_flow_corners call (w x h floats, host buffer), for parity tests.
+int vaw_flow_get_response(vaw_flow* f, float* response_host)
+{
+    if (!f) return VAW_ERR_INVALID;
+    if (!response_host || !f->d_eig) return flow_fail(f, VAW_ERR_INVALID, "no response map yet");
+    Guard g(f->device);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(response_host, f->d_eig, (size_t)f->width * f->height * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return flow_fail(f, VAW_ERR_CUDA, std::string("vaw_flow_get_response: ") + cudaGetErrorString(e));
     return VAW_OK;
 }
 

@@ -343,6 +343,21 @@ class FlowTracker:
                                              st.ctypes.data_as(_lib.u8p), _stream_handle(stream)))
         return nxt, st.astype(bool)
 
+    def corners(self, which=1, max_corners=200, quality=0.01, min_distance=30.0, stream=None):
+        """cv::goodFeaturesToTrack on a pushed frame (which: 0 previous, 1 current) -> (N, 2) float32 (x, y)."""
+        cap = max_corners if max_corners > 0 else 65536
+        out = np.zeros((cap, 2), np.float32)
+        n = C.c_int(0)
+        self._check(self._lib.vaw_flow_corners(self._h, which, max_corners, quality, min_distance, out.ctypes.data_as(_lib.f32p),
+                                               cap, C.byref(n), _stream_handle(stream)))
+        return out[:n.value].copy()
+
+    def response(self):
+        """The cv::cornerMinEigenVal map of the last corners() call, (h, w) float32."""
+        out = np.zeros((self.size[1], self.size[0]), np.float32)
+        self._check(self._lib.vaw_flow_get_response(self._h, out.ctypes.data_as(_lib.f32p)))
+        return out
+
     def level(self, which, level):
         """(image (h, w) uint8, dx (h, w) int16, dy (h, w) int16) of a pyramid level; which: 0 previous, 1 current."""
         w, h = C.c_int(0), C.c_int(0)
