@@ -314,6 +314,17 @@ int vaw_flow_corners(vaw_flow *flow, int which, int max_corners, double quality,
                      float *corners_xy, int capacity, int *n_out, void *stream);
 int vaw_flow_get_response(vaw_flow *flow, float *response_host);
 
+/* guess_camera_rotation (opencv/FrameSourceWarp.cpp:316-368): the rotation of the camera between two frames from
+ * tracked point pairs (pixels of the INPUT camera; x, y pairs).  Host only.  The reference undistorts both sets with
+ * cv::fisheye::undistortPoints, randomises the depth of the previous rays and keeps the rotation and the inlier count
+ * of cv::solvePnPRansac(100 iterations, 8 px reprojection error in the OUTPUT camera, confidence 0.99); this fits the
+ * rotation directly (two-ray RANSAC, same threshold and counts, least-squares refit over the consensus set) and
+ * agrees with that route to a few hundredths of a degree.  rotation: row-major 3x3, maps a ray of the previous frame
+ * onto the current one; *inliers: size of the consensus set (the reference ignores a result with fewer than 40,
+ * :431-438).  `seed` makes the sampling reproducible. */
+int vaw_guess_rotation(const vaw_camera *input, const vaw_camera *output, const float *prev_xy, const float *cur_xy,
+                       int n, uint32_t seed, double rotation[9], int *inliers);
+
 /* ---- synthetic frames (decode is out of scope; BASELINE.json north_star) ------------
  * Fill n_frames NV12 frames in device memory with the integer test pattern
  * (frame index first_index + i). */

@@ -98,3 +98,31 @@ def select_corners(eig, max_corners=200, quality=0.01, min_distance=30.0):
 
 def good_features_to_track(img, max_corners=200, quality=0.01, min_distance=30.0):
     return select_corners(corner_min_eigen_val(img), max_corners, quality, min_distance)
+
+
+def guess_camera_rotation_cv2(K_in, D_in, K_out, pts_prev, pts_cur, seed=0):
+    """guess_camera_rotation (FrameSourceWarp.cpp:316-368) step for step on the real OpenCV functions
+    (needs cv2: used by tests/test_oracle_rotation.py and to generate tests/golden/rotation_cases.npz).
+    The reference draws the depths from libc rand(); here from a seeded numpy generator.
+    Returns (R (3, 3) float64, number of inliers)."""
+    import cv2
+    pts_prev = np.asarray(pts_prev, np.float32).reshape(-1, 1, 2)
+    pts_cur = np.asarray(pts_cur, np.float32).reshape(-1, 1, 2)
+    K_in = np.asarray(K_in, np.float64)
+    K_out = np.asarray(K_out, np.float64)
+    D_in = np.asarray(D_in, np.float64).reshape(4, 1)
+    corners_output = cv2.fisheye.undistortPoints(pts_cur, K_in, D_in, R=np.eye(3), P=K_out)
+    prev_identity = cv2.fisheye.undistortPoints(pts_prev, K_in, D_in).reshape(-1, 2)
+    rng = np.random.default_rng(seed)
+    scale = rng.random(len(prev_identity))
+    obj = np.stack([prev_identity[:, 0] * scale, prev_identity[:, 1] * scale, scale], axis=1).astype(np.float64)
+    try:
+        ok, rvec, tvec, inliers = cv2.solvePnPRansac(obj, corners_output.reshape(-1, 2).astype(np.float64), K_out, np.zeros(4),
+                                                     useExtrinsicGuess=False, iterationsCount=100, reprojectionError=8.0,
+                                                     confidence=0.99)
+    except cv2.error:
+        return np.eye(3), 0
+    if not ok or inliers is None:
+        return np.eye(3), 0
+    R, _ = cv2.Rodrigues(rvec)
+    return R, len(inliers)

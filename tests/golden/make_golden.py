@@ -210,6 +210,23 @@ def make_gftt_fixture():
                         cv_version=np.array(cv2.__version__))
 
 
+def make_rotation_fixture():
+    """tests/golden/rotation_cases.npz: synthetic point pairs (tests/test_oracle_rotation.make_case) and what the
+    reference's guess_camera_rotation computes for them on the real cv2.fisheye.undistortPoints / cv2.solvePnPRansac
+    (oracle/gftt_ref.guess_camera_rotation_cv2); run: python tests/golden/make_golden.py --rotation."""
+    from oracle import gftt_ref as G
+    from tests.test_oracle_rotation import CASES, make_case
+    out = {"n_cases": np.array(len(CASES))}
+    for i, (seed, kw) in enumerate(CASES):
+        cam, oc, prev, cur, R_true, _ = make_case(seed, **kw)
+        R, inl = G.guess_camera_rotation_cv2(cam.K, cam.distortion, oc.K, prev, cur, seed=seed)
+        out.update({f"K_in_{i}": cam.K, f"K_out_{i}": oc.K, f"size_{i}": np.array(cam.size), f"prev_{i}": prev, f"cur_{i}": cur,
+                    f"cv_R_{i}": R, f"cv_inliers_{i}": np.array(inl), f"true_R_{i}": R_true})
+    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "rotation_cases.npz"), **out)
+
+
+if __name__ == "__main__" and "--rotation" in sys.argv:
+    make_rotation_fixture()
 if __name__ == "__main__" and "--lk" in sys.argv:
     make_lk_fixture()
 if __name__ == "__main__" and "--gftt" in sys.argv:

@@ -160,6 +160,59 @@ def test_corners_against_cv2_directly(V):
     ft.close()
 
 
+def _rot(rx, ry, rz):
+    rx, ry, rz = np.deg2rad([rx, ry, rz])
+    Rx = np.array([[1, 0, 0], [0, np.cos(rx), -np.sin(rx)], [0, np.sin(rx), np.cos(rx)]])
+    Ry = np.array([[np.cos(ry), 0, np.sin(ry)], [0, 1, 0], [-np.sin(ry), 0, np.cos(ry)]])
+    Rz = np.array([[np.cos(rz), -np.sin(rz), 0], [np.sin(rz), np.cos(rz), 0], [0, 0, 1]])
+    return Rz @ Ry @ Rx
+
+
+def test_measurement_chain_recovers_camera_rotations(V):
+    """The whole measurement of consume_frame (FrameSourceWarp.cpp:403-438) on the GPU -- corners of the previous
+    frame, pyramidal LK into the current one, rotation fit -- on frames with KNOWN camera rotations: a textured
+    fisheye frame re-projected through the library's own fisheye -> fisheye warp for a sequence of camera poses.
+    The measured inter-frame rotation must equal the pose change to 0.05 degrees (the warp's bilinear resampling
+    and LK's own accuracy bound it), with most corners tracked and kept as inliers."""
+    import torch
+    w, h = 1920, 1080
+    cam = V.get_preset_camera(4, w, h)
+    out = V.get_output_camera(cam)
+    fish_out = V.Camera.from_matrix(cam.K, w, h, model=1)      # the same fisheye camera on the output side
+    ctx = V.WarpContext(cam, fish_out, out_size=(w, h), border=(0, 128, 128))
+    luma, _ = _pair(h, w, 31)
+    base = np.concatenate([luma, np.full((h // 2, w), 128, np.uint8)])
+    src = torch.from_numpy(base).cuda().unsqueeze(0).contiguous()
+    poses = [np.eye(3)]
+    rng = np.random.default_rng(5)
+    for _ in range(6):
+        poses.append(_rot(*rng.normal(0, 0.5, 3)) @ poses[-1])
+    ft = V.FlowTracker(w, h)
+    frames = []
+    for R in poses:
+        dst = torch.empty_like(src)
+        ctx.warp(src[0], dst[0], R)
+        torch.cuda.synchronize()
+        frames.append(dst[0, :h].contiguous())
+    ft.push_frame(frames[0])
+    worst = 0.0
+    for k in range(1, len(poses)):
+        ft.push_frame(frames[k])
+        pts = ft.corners(0)                       # corners of the previous frame (:415-419)
+        assert len(pts) >= 150
+        nxt, st = ft.track(pts)
+        assert st.mean() > 0.7     # points whose window leaves the re-projected frame are lost
+        R, inl = V.guess_rotation(cam, out, pts[st], nxt[st], seed=k)
+        assert inl >= 0.9 * st.sum() and inl >= 40
+        # a pixel of view k with ray r shows the world ray poses[k] r, so rays move by poses[k]^-1 poses[k-1]
+        want = poses[k].T @ poses[k - 1]
+        err = np.rad2deg(np.arccos(np.clip((np.trace(R @ want.T) - 1) / 2, -1, 1)))
+        worst = max(worst, err)
+    assert worst < 0.05, worst
+    ft.close()
+    ctx.close()
+
+
 def test_flow_errors(V):
     with pytest.raises(V.VawError):
         V.FlowTracker(8, 8)

@@ -110,3 +110,23 @@ def test_demo_bench_mode_reports_both_pull_patterns():
     assert d["frames"] == 299 and d["warp_batch"] == 16
     assert d["fps_batched"] > 0 and d["fps_one_warp_per_call"] > 0
     assert d["batched_launches"] <= 299 // 16 + 8   # frames really went through batched launches (a few runs split at the slab's wrap)
+
+
+@pytest.mark.gpu
+def test_demo_chain_with_the_optical_flow_measurement():
+    """vaw_demo --flow: FrameSourceWarp fed by OpticalFlowRotationSource (the reference's own measurement,
+    FrameSourceWarp.cpp:403-438: corners every 20 frames or below 150 points, pyramidal LK, rotation fit, the
+    40-inlier rule) on a synthetic camera whose rotations are known.  Every frame after the first is fitted,
+    to 0.05 degrees, and the chain emits every frame but the first (which the reference drops, :403-406)."""
+    import json
+    from video_annotator_b200 import _build
+    demo = _build.build_host_shim()
+    n = 30
+    out = subprocess.run([demo, "--flow", str(n), "1920", "1080", "0.5"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.strip().split("\n")
+    d = json.loads(lines[-1])
+    assert d["emitted"] == n - 1
+    assert d["fits"] == n - 1
+    assert d["min_inliers"] >= 100
+    assert d["worst_error_deg"] < 0.05, lines

@@ -8,4 +8,4 @@ and streams.  Nothing here falls back to the CPU.
 from ._lib import VawCamera, VawParams, load  # noqa: F401
 from .warp import (FORMAT_BGR24, FORMAT_GRAY8, FORMAT_NV12, FORMAT_NV12_TO_BGR24, INTER_CUBIC, INTER_LANCZOS4, INTER_LINEAR, INTER_NEAREST, Camera, ClipWarper, FlowTracker, VawError,  # noqa: F401
                    WarpContext,
-                   get_output_camera, get_preset_camera, nv12_to_bgr, remap_u8, selftest_math, shard_range, synth_nv12)
+                   get_output_camera, get_preset_camera, guess_rotation, nv12_to_bgr, remap_u8, selftest_math, shard_range, synth_nv12)

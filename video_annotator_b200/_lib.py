@@ -82,6 +82,7 @@ SIGNATURES = {
     "vaw_flow_get_level": (C.c_int, [C.c_void_p, C.c_int, C.c_int, u8p, C.POINTER(C.c_int16), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "vaw_flow_corners": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, f32p, C.c_int, C.POINTER(C.c_int), C.c_void_p]),
     "vaw_flow_get_response": (C.c_int, [C.c_void_p, f32p]),
+    "vaw_guess_rotation": (C.c_int, [C.c_void_p, C.c_void_p, f32p, f32p, C.c_int, C.c_uint32, f64p, C.POINTER(C.c_int)]),
     "vaw_piece_stats": (C.c_int, [C.c_void_p, f64p, C.POINTER(C.c_uint32), C.c_void_p]),
     "vaw_piece_flags": (C.c_int, [C.c_void_p, f64p, C.POINTER(C.c_uint32), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                   C.POINTER(C.c_int), C.c_void_p]),

@@ -340,7 +340,8 @@ std::vector<Frame> FrameSourceWarp::warp_frames(const std::vector<Frame>& inputs
 
 void FrameSourceWarp::consume_frame(Frame input_frame)
 {
-    // :397-450 without the corner tracking: the inter-frame rotation comes from the RotationSource
+    // :397-450; the corner tracking and the rotation fit live behind the RotationSource
+    if (m_rotation_source) m_rotation_source->observe_frame(input_frame, m_frame_index);
     if (m_frame_index == 0) {
         // the reference only detects corners on the first frame and does not buffer it (:403-406)
     } else {
@@ -429,4 +430,85 @@ Frame FrameSourceWarp::pull_frame()
 Frame FrameSourceWarp::peek_frame()
 {
     return pull_frame();  // as the reference (:478-480): it advances
+}
+
+// ---- the optical-flow measurement (:228-270, :316-368, :403-438) -----------------------------------------
+namespace {
+vaw_camera to_c_camera(const Camera& c)
+{
+    vaw_camera o{};
+    o.model = c.model == FISHEYE ? 1 : 0;
+    o.width = c.width; o.height = c.height;
+    for (int i = 0; i < 9; ++i) o.matrix[i] = c.matrix.m[i];
+    for (int i = 0; i < 4; ++i) o.distortion[i] = c.distortion_coefficients[i];
+    return o;
+}
+}  // namespace
+
+OpticalFlowRotationSource::OpticalFlowRotationSource(const Camera& input_camera, const Camera& output_camera, int device)
+    : m_input_camera(input_camera), m_output_camera(output_camera), m_device(device), m_rotation(Mat33::eye())
+{
+    const int rc = vaw_flow_create(input_camera.width, input_camera.height, device, &m_flow);
+    if (rc != VAW_OK) throw rc;
+}
+
+OpticalFlowRotationSource::~OpticalFlowRotationSource() { vaw_flow_destroy(m_flow); }
+
+void OpticalFlowRotationSource::observe_frame(const Frame& frame, long frame_index)
+{
+    // frame_gray = the luma plane of the NV12 frame (:398)
+    int rc = vaw_flow_push_frame(m_flow, frame->data, frame->pitch, nullptr);
+    if (rc != VAW_OK) throw rc;
+    const int kMaxCorners = 200;
+    std::vector<float> found(2 * kMaxCorners);
+    int n = 0;
+    m_have_rotation = false;
+    if (m_last_key_frame_index == -1) {
+        // the first frame: corners of this frame, nothing to track yet (:403-406)
+        rc = vaw_flow_corners(m_flow, 1, kMaxCorners, 0.01, 30.0, found.data(), kMaxCorners, &n, nullptr);
+        if (rc != VAW_OK) throw rc;
+        found.resize(2 * (size_t)n);
+        m_last_input_frame_corners.swap(found);
+        m_last_key_frame_index = frame_index;
+        return;
+    }
+    if (frame_index - m_last_key_frame_index > 20 || m_last_input_frame_corners.size() / 2 < 150) {
+        // a fresh set, detected in the PREVIOUS frame (:415-419)
+        rc = vaw_flow_corners(m_flow, 0, kMaxCorners, 0.01, 30.0, found.data(), kMaxCorners, &n, nullptr);
+        if (rc != VAW_OK) throw rc;
+        found.resize(2 * (size_t)n);
+        m_last_input_frame_corners.swap(found);
+        m_last_key_frame_index = frame_index - 1;
+    }
+    const int np = (int)(m_last_input_frame_corners.size() / 2);
+    std::vector<float> next(2 * (size_t)np);
+    std::vector<uint8_t> status((size_t)np);
+    rc = vaw_flow_track(m_flow, m_last_input_frame_corners.data(), np, next.data(), status.data(), nullptr);
+    if (rc != VAW_OK) throw rc;
+    // the pairs for which the flow was found (:262-268)
+    std::vector<float> prev_pts, cur_pts;
+    for (int i = 0; i < np; ++i)
+        if (status[(size_t)i]) {
+            prev_pts.push_back(m_last_input_frame_corners[2 * (size_t)i]); prev_pts.push_back(m_last_input_frame_corners[2 * (size_t)i + 1]);
+            cur_pts.push_back(next[2 * (size_t)i]); cur_pts.push_back(next[2 * (size_t)i + 1]);
+        }
+    m_last_input_frame_corners = cur_pts;  // :427
+    const vaw_camera in = to_c_camera(m_input_camera), out = to_c_camera(m_output_camera);
+    double R[9];
+    int inliers = 0;
+    m_last_pairs = (int)(cur_pts.size() / 2);
+    rc = vaw_guess_rotation(&in, &out, prev_pts.data(), cur_pts.data(), m_last_pairs, (uint32_t)frame_index, R, &inliers);
+    if (rc != VAW_OK) throw rc;
+    m_last_inliers = inliers;
+    if (inliers >= 40) {  // :431
+        for (int i = 0; i < 9; ++i) m_rotation.m[i] = R[i];
+        m_have_rotation = true;
+    }
+}
+
+bool OpticalFlowRotationSource::rotation_since_last_frame(long /*frame_index*/, Mat33& out)
+{
+    if (!m_have_rotation) return false;  // the caller keeps the previous inter-frame rotation (or identity), :432-437
+    out = m_rotation;
+    return true;
 }

@@ -8,10 +8,10 @@
 //
 // What is replaced: warp_frame (:272-314) -- the createMap OpenCL kernel plus cv::remap --
 // is ONE call into libvaw.so (vaw_warp), hand-written CUDA for sm_100a; no map buffers exist.
-// What is out of scope: the optical-flow measurement of the inter-frame rotation
-// (:228-270, :316-375).  Its result enters through the RotationSource interface
-// instead, and everything downstream of the measurement (accumulation :441-442, the
-// Savitzky-Golay look-ahead filter :212/:444/:471, the correction :472-475) is kept.
+// The measurement of the inter-frame rotation (:228-270, :316-375) sits behind the RotationSource
+// interface: OpticalFlowRotationSource is the reference's own chain (corners, pyramidal LK, rotation fit) on the
+// GPU; tests and the demo also plug in synthetic gyro sources.  Everything downstream of the measurement
+// (accumulation :441-442, the Savitzky-Golay look-ahead filter :212/:444/:471, the correction :472-475) is kept.
 #ifndef VAW_FRAME_SOURCE_WARP_HPP_
 #define VAW_FRAME_SOURCE_WARP_HPP_
 
@@ -62,8 +62,38 @@ Camera get_output_camera(const Camera& input, double scale, bool crop_borders, d
  */
 class RotationSource {
   public:
+    // every consumed frame (the first one included) is shown to the source before it is asked about it
+    virtual void observe_frame(const Frame& /*frame*/, long /*frame_index*/) {}
     virtual bool rotation_since_last_frame(long frame_index, Mat33& out) = 0;
     virtual ~RotationSource() = default;
+};
+
+/**
+ * The reference's own measurement (consume_frame :403-438): corners of the previous frame
+ * (find_corners = cv::goodFeaturesToTrack(200, 0.01, 30), re-detected when the set is older than 20 frames
+ * or has shrunk below 150, :415-419), followed into the current frame with pyramidal Lucas-Kanade
+ * (find_point_pairs_with_optical_flow, :242-270), then the rotation that explains the pairs
+ * (guess_camera_rotation, :316-368; fewer than 40 inliers: keep the previous rotation, :431-438).
+ * Corners, pyramids and tracking run on the GPU (vaw_flow_*), the rotation fit on the host (vaw_guess_rotation).
+ */
+class OpticalFlowRotationSource : public RotationSource {
+    Camera m_input_camera, m_output_camera;
+    struct vaw_flow* m_flow = nullptr;
+    int m_device;
+    long m_last_key_frame_index = -1;
+    std::vector<float> m_last_input_frame_corners;  // x, y pairs in the previous frame
+    bool m_have_rotation = false;
+    Mat33 m_rotation;
+    int m_last_inliers = 0, m_last_pairs = 0;
+  public:
+    OpticalFlowRotationSource(const Camera& input_camera, const Camera& output_camera, int device = 0);
+    ~OpticalFlowRotationSource() override;
+    OpticalFlowRotationSource(const OpticalFlowRotationSource&) = delete;
+    OpticalFlowRotationSource& operator=(const OpticalFlowRotationSource&) = delete;
+    void observe_frame(const Frame& frame, long frame_index) override;
+    bool rotation_since_last_frame(long frame_index, Mat33& out) override;
+    int last_inliers() const { return m_last_inliers; }  // of the most recent fit
+    int last_pairs() const { return m_last_pairs; }      // tracked point pairs it was given
 };
 
 /**

@@ -86,6 +86,18 @@ def get_output_camera(cam, scale=1.0, crop_borders=False, zoom=1.0):
     return Camera(c)
 
 
+def guess_rotation(input_camera, output_camera, prev_pts, cur_pts, seed=1):
+    """guess_camera_rotation, FrameSourceWarp.cpp:316-368 (vaw_guess_rotation) -> (R (3, 3) float64, inliers)."""
+    p = np.ascontiguousarray(prev_pts, np.float32).reshape(-1, 2)
+    c = np.ascontiguousarray(cur_pts, np.float32).reshape(-1, 2)
+    assert len(p) == len(c)
+    R = np.zeros(9, np.float64)
+    n = C.c_int(0)
+    _check(_lib.load().vaw_guess_rotation(C.byref(input_camera._c), C.byref(output_camera._c), p.ctypes.data_as(_lib.f32p),
+                                          c.ctypes.data_as(_lib.f32p), len(p), int(seed), R.ctypes.data_as(_lib.f64p), C.byref(n)))
+    return R.reshape(3, 3), n.value
+
+
 def _rot_arg(rot):
     r = np.ascontiguousarray(np.asarray(rot, np.float64).reshape(-1))
     return r, r.ctypes.data_as(_lib.f64p)
