@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Turn the raw captures of a `tools/gpu_full.sh` run (gpurun_out/) into the committed summaries
-under profiles/: python tools/make_profiles.py r01"""
+"""Turn the raw captures of a `tools/gpu_full.sh` / `tools/gpu_r2_final.sh` run (gpurun_out/) into the committed
+summaries under profiles/: python tools/make_profiles.py r02"""
 import csv, io, json, os, subprocess, sys
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -19,7 +19,7 @@ for r in rows:
     tot[name] = tot.get(name, 0.0) + ns
 step = {k: v for k, v in tot.items() if "warp_nv12" in k or "build_pieces" in k}
 with open(os.path.join(P, f"{tag}_launches.txt"), "w") as f:
-    f.write("ncu --metrics gpu__time_duration.sum --clock-control none -c 40  python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline\n")
+    f.write("ncu --metrics gpu__time_duration.sum --clock-control none -c 60  python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-parity --no-shim\n")
     f.write("(cold-cache, serialised launches: compare SHARES, not absolutes)\n\n" + "\n".join(lines) + "\n\nshare of the step:\n")
     s = sum(step.values())
     for k, v in step.items():
@@ -33,7 +33,7 @@ open(os.path.join(P, f"{tag}_ncu_summary.txt"), "w").write(
 src = run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:warp_nv12"])
 open("/tmp/_src.csv", "w").write(src)
 open(os.path.join(P, f"{tag}_hotspots.txt"), "w").write(
-    "per-instruction samples of warp_nv12_tile_kernel (ncu --page source), aggregated by tools/ncu_hot.py\n\n"
+    "per-instruction samples of the sampler kernel (ncu --page source), aggregated by tools/ncu_hot.py\n\n"
     + run([sys.executable, "tools/ncu_hot.py", "/tmp/_src.csv", "25"]))
 
 # 3. DRAM traffic per launch of the dominant kernel -> bench.py's roofline.traffic
@@ -51,11 +51,50 @@ for r in raw[2:]:
 json.dump(traffic, open(os.path.join(P, "traffic.json"), "w"), indent=1)
 
 # 4. bench lines and parity summary of the same run
-for fn in ("bench.json", "bench_ref.json", "bench_C5.json", "bench_C2.json", "bench_C1.json"):
+# where the sampler's warps spend their time (regions of equal execution count) + the SASS that proves TMA / mbarrier / packed math
+open(os.path.join(P, f"{tag}_regions.txt"), "w").write(
+    "tools/ncu_regions.py on the same capture: runs of equal execution count; exec = share of executed warp instructions,\n"
+    "time = share of the warp-state samples (= of the time warps are resident)\n\n"
+    + run([sys.executable, "tools/ncu_regions.py", rep, "warp_nv12", "0.4"]))
+sass = run(["cuobjdump", "-sass", os.path.join(ROOT, "video_annotator_b200", "libvaw.so")])
+funcs = [f for f in sass.split("Function : ")[1:] if "warp_nv12_quad_kernelILi7" in f.split("\n", 1)[0]]
+if funcs:
+    import collections, re
+    body = funcs[0].split("\n")
+    ins = []
+    for ln in body:
+        m = re.match(r"\s+/\*([0-9a-f]{4,5})\*/\s+(.*?);", ln)
+        if m:
+            ins.append((int(m.group(1), 16), m.group(2).strip()))
+    ops = collections.Counter(re.sub(r"^@!?U?P\d+\s+", "", t).split()[0].split(".")[0] for _, t in ins)
+    # the row loop = the backward branch whose body holds 20 shared-memory tap loads and three stores
+    loop = []
+    index = {a: k for k, (a, _) in enumerate(ins)}
+    for k, (a, t) in enumerate(ins):
+        m = re.search(r"BRA(?:\.\w+)*\s+(?:\w+,\s*)?`?\(?(0x[0-9a-f]+)", t)
+        if m and int(m.group(1), 16) <= a and int(m.group(1), 16) in index:
+            cand = ins[index[int(m.group(1), 16)]:k + 1]
+            if sum(1 for _, x in cand if x.startswith("LDS")) == 20 and sum(1 for _, x in cand if "STG" in x) == 3:
+                loop = cand
+                break
+    with open(os.path.join(P, f"{tag}_sass_tile.txt"), "w") as f:
+        f.write("cuobjdump -sass video_annotator_b200/libvaw.so, function " + body[0].strip() + " (sm_100a)\n")
+        f.write("opcode counts (static, whole function): " + ", ".join(f"{k} {v}" for k, v in ops.most_common(40)) + "\n\n")
+        f.write("1. asynchronous machinery: mbarriers (SYNCS), the bulk copy of the piece record (UBLKCP), TMA tensor loads of the\n"
+                "   source tile (UTMALDG), the CTA barrier:\n\n")
+        f.write("\n".join(f"  /*{a:05x}*/ {t}" for a, t in ins if any(k in t for k in ("UTMALDG", "UBLKCP", "SYNCS", "BAR.", "CCTL"))) + "\n\n")
+        lc = collections.Counter(re.sub(r"^@!?U?P\d+\s+", "", t).split()[0].split(".")[0] for _, t in loop)
+        f.write(f"2. the row loop ({len(loop)} instructions per 2 x 2 luma pixels + 1 chroma sample of a lane): "
+                + ", ".join(f"{k} {v}" for k, v in lc.most_common()) + "\n\n")
+        f.write("\n".join(f"  /*{a:05x}*/ {t}" for a, t in loop) + "\n")
+for fn in ("bench.json", "bench_ref.json", "bench_C5.json", "bench_C2.json", "bench_C1.json", "bench_C4.json", "bench_fused_bgr.json", "modes.json"):
     if os.path.exists(os.path.join(G, fn)):
         open(os.path.join(P, f"{tag}_{fn}"), "w").write(open(os.path.join(G, fn)).read())
 if os.path.exists(os.path.join(G, "parity.json")):
     d = json.load(open(os.path.join(G, "parity.json")))
     json.dump(d, open(os.path.join(P, f"{tag}_parity.json"), "w"), indent=1)
+for fn, to in (("flow_demo.log", "flow_demo.txt"), ("abl.log", "ablations.txt")):
+    if os.path.exists(os.path.join(G, fn)):
+        open(os.path.join(P, f"{tag}_{to}"), "w").write(open(os.path.join(G, fn)).read())
 print(open(os.path.join(P, f"{tag}_launches.txt")).read()[-600:])
 print(json.dumps(traffic))
