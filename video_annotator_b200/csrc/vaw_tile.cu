@@ -125,27 +125,74 @@ __device__ __forceinline__ unsigned opaque_zero()
 
 // nrows (even) rows starting at piece row dv0 for the lane's two columns; taps from the staged tile.
 // py / pc: the lane's column pair in the first luma row / chroma row of the band.
+#ifndef VAW_ONE_WAITER
+#define VAW_ONE_WAITER 0  // 1: one thread polls the record / tile mbarriers and the others park at a CTA barrier behind it
+                          // (removes the try_wait loops, 3.3 % of the executed instructions -- and measures 0.6 % SLOWER:
+                          // the extra barrier costs more than the polling)
+#endif
+#ifndef VAW_VECTOR_CONSTS
+#define VAW_VECTOR_CONSTS 1  // the 32.0 / 16.0 scale factors of the samplers in vector registers (0: re-made from uniforms every row pair)
+#endif
+#ifndef VAW_RUNNING_PTRS
+#define VAW_RUNNING_PTRS 0
+#endif
+#ifndef VAW_SAMPLER
+#define VAW_SAMPLER 3  // 1: luma_tile / chroma_tile (shift + mask + six multiply-adds per sample); 3: luma_tile3 / chroma_tile3
+#endif
+#if VAW_SAMPLER == 3
+using TapConst = FloorConst;
+#else
+using TapConst = unsigned;
+#endif
+
 template <bool kRagged>
-__device__ __forceinline__ void rows_quad(const Geom& g, const ColPoly2& cp, unsigned lconst, unsigned cconst, unsigned pl,
+__device__ __forceinline__ void rows_quad(const Geom& g, const ColPoly2& cp, const TapConst& lconst, const TapConst& cconst, unsigned pl,
                                           int dv0, int nrows, uint8_t* __restrict__ py, uint8_t* __restrict__ pc,
                                           bool inside, const TileBounds& tb)
 {
     float t = row_t(g, dv0);
     const float dt = g.t_scale, dt2 = __fadd_rn(g.t_scale, g.t_scale);  // stepping the dyadic t is exact
-    const unsigned dpitch = (unsigned)g.dst_pitch;
-    const unsigned long long gy0 = (unsigned long long)__cvta_generic_to_global(py), gy1 = gy0 + dpitch;
+    // the pitch in a VECTOR register (threadIdx.x >> 5 is 0, which ptxas does not know): with a uniform-register
+    // multiplicand IMAD.WIDE takes no 64-bit addend and every store address costs three instructions instead of one
+    const unsigned dpitch = (unsigned)g.dst_pitch + (threadIdx.x >> 5);
+    const unsigned hpitch = dpitch >> 1;
+    const unsigned long long gy0 = (unsigned long long)__cvta_generic_to_global(py);
     const unsigned long long gc = (unsigned long long)__cvta_generic_to_global(pc);
+#if VAW_RUNNING_PTRS
+    unsigned long long q0 = gy0, q1 = gy0 + (unsigned)g.dst_pitch, qc = gc;
+    const unsigned long long step1 = (unsigned)g.dst_pitch, step2 = 2ull * (unsigned)g.dst_pitch;
+#endif
+#ifndef VAW_UNROLL2
+#define VAW_UNROLL2 1  // two row pairs per trip: 135.5 instead of 138 instructions per row pair, same registers
+#endif
+#if VAW_UNROLL2
+#pragma unroll 2
+#else
 #pragma unroll 1
+#endif
     for (unsigned j2 = opaque_zero(); j2 < (unsigned)nrows; j2 += 2) {  // rows j2, j2 + 1 of the band
         const float2 t0 = pair(t), t1 = pair(__fadd_rn(t, dt));
         t = __fadd_rn(t, dt2);
         const float2 m00 = col_coord(cp.a[0], cp.base, t0), m01 = col_coord(cp.a[1], cp.base, t0);
         const float2 m10 = col_coord(cp.a[0], cp.base, t1), m11 = col_coord(cp.a[1], cp.base, t1);
+#if VAW_SAMPLER == 3
+        const unsigned y00 = luma_tile3(lconst, pl, m00, tb) >> 10, y01 = luma_tile3(lconst, pl, m01, tb) >> 10;
+        const unsigned y10 = luma_tile3(lconst, pl, m10, tb) >> 10, y11 = luma_tile3(lconst, pl, m11, tb) >> 10;
+        const unsigned c = chroma_tile3(cconst, pl, chroma_z(m00, m01, m10, m11), tb);  // U | V << 8
+#else
         const unsigned y00 = (unsigned)luma_tile(lconst, pl, m00, tb) >> 10, y01 = (unsigned)luma_tile(lconst, pl, m01, tb) >> 10;
         const unsigned y10 = (unsigned)luma_tile(lconst, pl, m10, tb) >> 10, y11 = (unsigned)luma_tile(lconst, pl, m11, tb) >> 10;
         const unsigned c = chroma_tile(cconst, pl, chroma_z(m00, m01, m10, m11), tb);  // U | V << 8
-        const unsigned long long r0 = row_ptr(gy0, j2, dpitch), r1 = row_ptr(gy1, j2, dpitch);
-        const unsigned long long rc = row_ptr(gc, j2 >> 1, dpitch);
+#endif
+        // one IMAD.WIDE per store address: distinct multiplicands keep ptxas from sharing the product and adding the
+        // three 64-bit bases to it afterwards (two more instructions per address)
+#if VAW_RUNNING_PTRS
+        const unsigned long long r0 = q0, r1 = q1, rc = qc;
+        q0 += step2; q1 += step2; qc += step1;
+#else
+        const unsigned long long r0 = row_ptr(gy0, j2, dpitch), r1 = row_ptr(gy0, j2 + 1u, dpitch);
+        const unsigned long long rc = kRagged ? row_ptr(gc, j2 >> 1, dpitch) : row_ptr(gc, j2, hpitch);  // even pitch
+#endif
         if (!kRagged) {
             stg_u16(r0, y00 | (y01 << 8));
             stg_u16(r1, y10 | (y11 << 8));
@@ -190,8 +237,15 @@ warp_nv12_quad_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
             asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + 128));
         }
     }
+#if VAW_ONE_WAITER
+    // ONE thread polls the mbarrier, the others park at the CTA barrier behind it (round 2's profile: the try_wait
+    // loops of all four warps were 3.3 % of the kernel's executed instructions)
+    if (tid == 0) mbar_wait_parked(mbar_rec, 0, 4000);
+    __syncthreads();
+#else
     __syncthreads();  // the barriers are initialised for every warp
     mbar_wait_parked(mbar_rec, 0, 4000);
+#endif
     const PieceRec* rs = reinterpret_cast<const PieceRec*>(smem + kQuadRecOffset);
     const float4 rec_tail = *(reinterpret_cast<const float4*>(rs) + 12);  // base.x, base.y, flags, pad
     const int4 raw = *(reinterpret_cast<const int4*>(rs) + 14);          // PieceStage
@@ -313,7 +367,12 @@ warp_nv12_quad_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
     cp.base = make_float2(rec_tail.x, rec_tail.y);
 
 #ifndef VAW_ABL_NO_TMA
+#if VAW_ONE_WAITER
+    if (tid == 0) mbar_wait_parked(mbar, 0, 4000);  // the tile has landed
+    __syncthreads();
+#else
     mbar_wait_parked(mbar, 0, 4000);  // the tile has landed (the warp is parked, not spinning, until then)
+#endif
 #endif
 #ifdef VAW_ABL_NO_LOOP  // analysis only: the per-piece set-up without the row loop
     if (cp.a[0][0].x + cp.a[1][3].y == 12345.f) dst[0] = 1;
@@ -332,8 +391,20 @@ warp_nv12_quad_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
     if (my_rows <= 0) return;
     // tap address = (iy - y0) * pl + (ix - x0) + tile, with the >>5 bias of the magic constant folded in
     const unsigned upl = (unsigned)pl;
+#if VAW_SAMPLER == 3
+    // floor constants: tile origin (and, for luma, the tile's shared-memory address) folded into the round-down FMA
+    const unsigned never = (unsigned)g.out_w >> 31;  // 0 at run time: constants built from it stay loop-invariant uniforms
+#if VAW_VECTOR_CONSTS
+    const unsigned vnever = threadIdx.x >> 5;        // 0 as well, but per thread as far as ptxas knows: a vector register
+#else
+    const unsigned vnever = never;
+#endif
+    const FloorConst lconst = floor_const(-lx0, -by0, smem_u32(ltile) - 0x40000000u, upl, __uint_as_float(0x42000000u | vnever), never);
+    const FloorConst cconst = floor_const(-(cbx0 >> 1), -cy0, smem_u32(ctile) - 0x80000000u, upl, __uint_as_float(0x41800000u | vnever), never);
+#else
     const unsigned lconst = smem_u32(ltile) - (unsigned)by0 * upl - (unsigned)lx0 - kMagicShift * upl - kMagicShift;
     const unsigned cconst = ((smem_u32(ctile) - (unsigned)cy0 * upl - (unsigned)cbx0 - kMagicShift * upl) >> 1) - kMagicShift;
+#endif
     const int u0 = u_lo + col0;
     const bool inside = u0 < g.out_w;  // widths are even: the pair is inside or outside together
     const bool pair_ok = ((reinterpret_cast<uintptr_t>(dst) | (uintptr_t)g.dst_pitch) & 1) == 0 &&

@@ -94,6 +94,70 @@ __device__ __forceinline__ unsigned chroma_tile4a(unsigned cconst, unsigned pl, 
     return u | (v & 0xff00u);  // U | V << 8
 }
 
+// ---- samplers, third formulation (round 2, the row loop of the quadrant kernel) ----------------------------------
+// Same integers as luma_tile / chroma_tile, eight fewer instructions per row pair:
+//   * floor(n / 32) of BOTH coordinates in one FFMA2 with round-down: s = 32 m + 1.5 * 2^23 holds n = rint(32 m) in
+//     its mantissa; s * 2^-27 + c is exact inside the FMA and, rounded toward -inf to the 2^-22 ulp of [2, 4), leaves
+//     bits 0x40000000 + floor(n / 32) + D, D = the integer folded into c (minus the tile origin, plus the tile's
+//     shared-memory address for x).  0x40000000 * pitch vanishes modulo 2^32 (pitches are multiples of 32), so the
+//     tap address is ONE multiply-add of the two bit patterns; the 0x40000000 that x carries is cancelled by the
+//     block-uniform `ubase` inside the load's address (register + uniform register).
+//   * horizontal blend of both tap rows at once in 16-bit halves, vertical blend + rounding constant as one IDP.2A.
+struct FloorConst { float2 c; unsigned row0, row1; float scale; };  // c = 1.90625 + D * 2^-22 per coordinate; row0 / row1 = tile
+                                                      // address of the upper / lower tap row minus what x carries
+constexpr float kFloorScale = 7.450580596923828125e-09f;  // 2^-27
+constexpr float kFloorBias = 1.90625f;                    // 2 - 1.5 * 2^23 * 2^-27
+constexpr float kFloorUnit = 2.384185791015625e-07f;      // 2^-22
+
+// A value the compiler front end cannot split or fold (ptxas still sees a plain move): keeps `tile address - 2^30`
+// one loop-invariant uniform instead of an immediate added to every tap address.
+__device__ __forceinline__ unsigned opaque_u32(unsigned v)
+{
+    unsigned r;
+    asm("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
+__device__ __forceinline__ FloorConst floor_const(int dx, int dy, unsigned row0, unsigned pl, float scale, unsigned never)
+{
+    FloorConst f;
+    f.scale = scale;
+    f.c = make_float2(__fmaf_rn((float)dx, kFloorUnit, kFloorBias), __fmaf_rn((float)dy, kFloorUnit, kFloorBias));  // exact
+    // `never` is 0 at run time but unknown to ptxas: it cannot take the sums apart again, so each stays ONE uniform
+    // register that the loads add for free ([register + uniform register + immediate])
+    f.row0 = opaque_u32(row0) | never;
+    f.row1 = opaque_u32(row0 + pl) | never;
+    return f;
+}
+
+__device__ __forceinline__ unsigned luma_tile3(const FloorConst& fc, unsigned pl, float2 m, const TileBounds& tb)
+{
+    const float2 s = __ffma2_rn(m, pair(fc.scale), pair(kMagic));
+    const float2 fl = __ffma2_rd(s, pair(kFloorScale), fc.c);
+    const unsigned a = imad_u32(__float_as_uint(fl.y), pl, __float_as_uint(fl.x));
+    const unsigned a0 = a + fc.row0, a1 = a + fc.row1;  // register + uniform register inside the loads' addresses
+#ifdef VAW_BOUNDS_CHECK
+    check_taps(a0, a1, 2u, tb.l_lo, tb.l_hi);
+#endif
+    const unsigned t00 = lds_u8<0>(a0), t01 = lds_u8<1>(a0), t10 = lds_u8<0>(a1), t11 = lds_u8<1>(a1);
+    const unsigned ax = __float_as_uint(s.x) & 31u, ay = __float_as_uint(s.y) & 31u;
+    const unsigned left = __byte_perm(t00, t10, 0x5410), right = __byte_perm(t01, t11, 0x5410);  // top | bottom << 16
+    const unsigned h = imad_u32(right, ax, left * (32u - ax));  // both rows, <= 8160 per half
+    return __dp2a_lo(h, imad_u32(ay, 255u, 32u), 512u);       // top * (32 - ay) + bottom * ay + 512
+}
+
+__device__ __forceinline__ unsigned chroma_tile3(const FloorConst& fc, unsigned pl, float2 z, const TileBounds& tb)
+{
+    const float2 s = __ffma2_rn(z, pair(fc.scale), pair(kMagic));
+    const float2 fl = __ffma2_rd(s, pair(kFloorScale), fc.c);
+    const unsigned a = imad_u32(__float_as_uint(fl.x), 2u, __float_as_uint(fl.y) * pl);
+    const unsigned a0 = a + fc.row0, a1 = a + fc.row1;
+#ifdef VAW_BOUNDS_CHECK
+    check_taps(a0, a1, 4u, tb.c_lo, tb.c_hi);
+#endif
+    return blend_uv(lds_u16<0>(a0), lds_u16<2>(a0), lds_u16<0>(a1), lds_u16<2>(a1), __float_as_uint(s.x) & 31u,
+                    __float_as_uint(s.y) & 31u);
+}
+
 // Pair lane mapping of the texture variant (vaw_tex.cu): lane l owns luma columns 2l, 2l+1 and 64+2l, 64+2l+1
 // of the piece (slot j -> column 2l + (j & 1) + 64 (j >> 1)); stores are 2 bytes per lane.
 __device__ __forceinline__ int pair_column(int lane, int j) { return 2 * lane + (j & 1) + 64 * (j >> 1); }
