@@ -39,7 +39,11 @@ namespace vaw {
 
 namespace {
 
-constexpr int kWarps = 4;
+#ifndef VAW_QUAD_WARPS
+#define VAW_QUAD_WARPS 4  // warps per CTA of the quadrant kernel: 4 (64 columns x PH/2 rows each) or 2 (64 columns x PH rows each)
+#endif
+constexpr int kWarps = VAW_QUAD_WARPS;
+static_assert(kWarps == 2 || kWarps == 4, "two warps side by side, one or two deep");
 
 }  // namespace
 
@@ -360,7 +364,7 @@ warp_nv12_quad_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
     }
 
     // ---- this warp's quadrant; every lane collapses the polynomial onto its two columns ---------------
-    const int wx = w & 1, wy = w >> 1, hrows = ph >> 1;
+    const int wx = w & 1, wy = w >> 1, hrows = ph / (kWarps / 2);
     const int col0 = 64 * wx + 2 * lane;  // within the piece
     ColPoly2 cp;
     derive2(rs, col0, cp);
