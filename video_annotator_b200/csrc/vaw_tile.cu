@@ -31,6 +31,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <atomic>
+#include <type_traits>
 #include "vaw_internal.h"
 #include "vaw_poly.cuh"
 #include "vaw_tile.cuh"
@@ -62,7 +63,10 @@ static_assert(kWarps == 2 || kWarps == 4, "two warps side by side, one or two de
 //   - per row pair a lane makes 2 x 2 luma samples and the one chroma sample of that quad; a warp
 //     store writes 64 contiguous bytes, the LDS of a warp stay within one 128-byte window per row
 //     exactly as with the round-1 pair mapping (2 columns per lane).
-constexpr int kQuadRecOffset = 16, kQuadTileOffset = 256;  // [tile mbarrier | record mbarrier | record (240 B) | tile (TMA: 128-byte aligned)]
+constexpr int kQuadRecOffset = 16, kQuadTileOffset = 640;  // [tile mbarrier | record mbarrier | record (240 B) | ... | tile (TMA: 128-byte aligned)]
+// the persistent kernel's bookkeeping in the same 640 bytes: [tile mbarrier | 2 record mbarriers | pad | 2 piece slots (int4) | 2 records]
+constexpr int kPersistSlotOffset = 32, kPersistRecOffset = 64, kPersistRecStride = 240;
+static_assert(kPersistRecOffset + 2 * kPersistRecStride <= kQuadTileOffset, "bookkeeping fits in front of the tile");
 
 struct ColPoly2 {
     float2 a[2][kNv];  // [column][power of t]
@@ -209,6 +213,192 @@ __device__ __forceinline__ void rows_quad(const Geom& g, const ColPoly2& cp, con
     }
 }
 
+// One piece, from its record in shared memory (`rs`) to the stores: the body shared by the one-piece-per-CTA kernel
+// and the persistent kernel.  `rec` = the same record in the table (the gather fallbacks read it from there);
+// `tile_parity` = phase of the tile mbarrier (smem + 0) this piece's loads complete.  Returns whether the piece was staged
+// (i.e. whether that phase was consumed).
+__device__ __forceinline__ bool quad_piece(const Geom& g, const FrameBatch& b, const PieceRec* __restrict__ rec,
+                                           const PieceRec* rs, const TileMaps& maps, uint8_t* smem, int px, int py,
+                                           int frame, unsigned tile_parity, int lane, int w, int tid)
+{
+    const int ph = g.piece_h;
+    const float4 rec_tail = *(reinterpret_cast<const float4*>(rs) + 12);  // base.x, base.y, flags, pad
+    const int4 raw = *(reinterpret_cast<const int4*>(rs) + 14);          // PieceStage
+
+    const unsigned flags = __float_as_uint(rec_tail.z);
+    const int u_lo = px * kPieceW, v_base = py * ph;
+    const int rows = min(ph, g.out_h - v_base);  // even for NV12
+    uint8_t* const dst = b.dst + (size_t)frame * b.dst_frame_stride;
+
+    if (b.skip_interior && (flags & (kPiecePoly | kPieceInterior)) == (kPiecePoly | kPieceInterior))
+        return false;  // variant TEX: this piece belongs to the texture kernel
+
+    if (flags & kPieceOutside) {  // pure border: 128 threads fill the piece
+        const unsigned yw = (g.border & 255u) * 0x01010101u;
+        const unsigned cw = ((g.border >> 8) & 0xffffu) * 0x00010001u;
+        if (((reinterpret_cast<uintptr_t>(dst) | (uintptr_t)g.dst_pitch) & 15) == 0 && u_lo + kPieceW <= g.out_w) {
+            // 16 bytes per lane: 8 lanes per row, 16 rows per pass of the CTA
+            constexpr int kPass = 4 * kWarps;
+            const int sub = tid >> 3, col = (tid & 7) * 16;
+            const uint4 y4 = make_uint4(yw, yw, yw, yw), c4 = make_uint4(cw, cw, cw, cw);
+            uint8_t* yrow = dst + (size_t)(v_base + sub) * g.dst_pitch + u_lo + col;
+            for (int r = sub; r < rows; r += kPass, yrow += kPass * (size_t)g.dst_pitch) *reinterpret_cast<uint4*>(yrow) = y4;
+            uint8_t* crow = dst + (size_t)(g.out_h + (v_base >> 1) + sub) * g.dst_pitch + u_lo + col;
+            for (int r = sub; r < rows / 2; r += kPass, crow += kPass * (size_t)g.dst_pitch) *reinterpret_cast<uint4*>(crow) = c4;
+            return false;
+        }
+        // ragged / unaligned: 4 columns per lane, rows split over the warps like the round-1 kernel
+        const int u0 = u_lo + 4 * lane, valid = g.out_w - u0, rpw = ph / kWarps;
+        const int dv0 = w * rpw, my = max(0, min(rpw, rows - dv0));
+        uint8_t* y0 = dst + (size_t)(v_base + dv0) * g.dst_pitch + u0;
+        uint8_t* cc = dst + (size_t)(g.out_h + ((v_base + dv0) >> 1)) * g.dst_pitch + u0;
+        if (valid > 0)
+            for (int dv = 0; dv < my; dv += 2) {
+                store_word<true>(y0, yw, valid);
+                store_word<true>(y0 + g.dst_pitch, yw, valid);
+                store_word<true>(cc, cw, valid);
+                y0 += 2 * (size_t)g.dst_pitch; cc += g.dst_pitch;
+            }
+        return false;
+    }
+
+    // ---- the tile of this piece's source rectangle, as the builder laid it out (block-uniform) ------
+    const int lx0 = (int16_t)(raw.x & 0xffff), by0 = raw.x >> 16;
+    const int cbx0 = (int16_t)(raw.y & 0xffff), cy0 = raw.y >> 16;
+    const int pl = raw.z & 0xffff, nrows = (raw.z >> 16) & 0xffff, cnrows = raw.w & 0xffff;
+    const bool staged = (flags & kPiecePoly) && maps.enabled && pl != 0 && pl * (nrows + cnrows) <= maps.tile_cap;
+
+    if (!staged) {
+        // pieces without a polynomial certificate or whose box does not fit the tile: the gather paths of
+        // variant POLY with the 4-columns-per-lane mapping (warp w walks rows [w PH/4, (w+1) PH/4))
+        const int rpw = ph / kWarps, dv0 = w * rpw, my_rows = max(0, min(rpw, rows - dv0));
+        const int u0 = u_lo + 4 * lane, valid = g.out_w - u0;
+        if (my_rows <= 0) return false;
+        PlaneRefs f;
+        f.y = b.src + (size_t)frame * b.src_frame_stride;
+        f.uv = f.y + (size_t)g.src_pitch * g.src_h;
+        f.dst = dst;
+        if (!(flags & kPiecePoly)) {  // op-for-op per pixel
+            const Rot R = load_rot(b, frame);
+            for (int dv = dv0; dv < dv0 + my_rows; dv += 2) {
+                float2 m[2][4];
+                exact_rows(g, R, u_lo, u0, v_base + dv, m);
+                sample_rows_checked(g, f, u0, v_base + dv, m);
+            }
+            return false;
+        }
+        ColPoly cp;
+        derive(rec, lane, cp);
+        if (flags & kPieceInterior) {
+            RowPtrs o;
+            o.y0 = dst + (size_t)(v_base + dv0) * g.dst_pitch + u0;
+            o.y1 = o.y0 + g.dst_pitch;
+            o.c = dst + (size_t)(g.out_h + ((v_base + dv0) >> 1)) * g.dst_pitch + u0;
+            o.step_y = 2 * (size_t)g.dst_pitch;
+            o.step_c = (size_t)g.dst_pitch;
+            const bool word_ok = ((reinterpret_cast<uintptr_t>(dst) | (uintptr_t)g.dst_pitch) & 3) == 0 &&
+                                 u_lo + kPieceW <= g.out_w;
+            if (word_ok) band_gmem<false>(g, cp, f, dv0, my_rows, o, valid);
+            else band_gmem<true>(g, cp, f, dv0, my_rows, o, valid);
+        } else {
+            for (int dv = dv0; dv < dv0 + my_rows; dv += 2) {
+                float2 m[2][4];
+                row_coords(cp, row_t(g, dv), m[0]);
+                row_coords(cp, row_t(g, dv + 1), m[1]);
+                sample_rows_checked(g, f, u0, v_base + dv, m);
+            }
+        }
+        return false;
+    }
+
+    uint8_t* ltile = smem + kQuadTileOffset;
+    const unsigned mbar = smem_u32(smem);
+    uint8_t* ctile = ltile + nrows * pl;
+
+    // ---- thread 0: launch the tile loads ------------------------------------------------------------
+#ifdef VAW_ABL_NO_TMA  // analysis only: no tile loads (the loop samples whatever the shared memory holds)
+    if (tid == 0 && g.out_w < 0) {
+#else
+    if (tid == 0) {
+#endif
+        mbar_expect_tx(mbar, (unsigned)(pl * (nrows + cnrows)));
+        const int mi = (pl - kTileMinPitch) / kTilePitchStep;
+        const CUtensorMap *map = &maps.m[mi], *map32 = &maps.m32[mi], *map4 = &maps.m4[mi];
+        const unsigned l0 = smem_u32(ltile), c0 = smem_u32(ctile);
+        const int z = frame + b.tma_frame0;
+        int k = 0;
+        for (; k + 32 <= nrows; k += 32) tma_load_3d(l0 + (unsigned)(k * pl), map32, lx0 >> 2, by0 + k, z, mbar);
+        for (; k + 8 <= nrows; k += 8) tma_load_3d(l0 + (unsigned)(k * pl), map, lx0 >> 2, by0 + k, z, mbar);
+        if (k < nrows) tma_load_3d(l0 + (unsigned)(k * pl), map4, lx0 >> 2, by0 + k, z, mbar);
+        for (k = 0; k + 32 <= cnrows; k += 32) tma_load_3d(c0 + (unsigned)(k * pl), map32, cbx0 >> 2, g.src_h + cy0 + k, z, mbar);
+        for (; k + 8 <= cnrows; k += 8) tma_load_3d(c0 + (unsigned)(k * pl), map, cbx0 >> 2, g.src_h + cy0 + k, z, mbar);
+        if (k < cnrows) tma_load_3d(c0 + (unsigned)(k * pl), map4, cbx0 >> 2, g.src_h + cy0 + k, z, mbar);
+    }
+
+    // ---- this warp's quadrant; every lane collapses the polynomial onto its two columns ---------------
+    const int wx = w & 1, wy = w >> 1, hrows = ph / (kWarps / 2);
+    const int col0 = 64 * wx + 2 * lane;  // within the piece
+    ColPoly2 cp;
+    derive2(rs, col0, cp);
+    cp.base = make_float2(rec_tail.x, rec_tail.y);
+
+#ifndef VAW_ABL_NO_TMA
+#if VAW_ONE_WAITER
+    if (tid == 0) mbar_wait_parked(mbar, tile_parity, 4000);  // the tile has landed
+    __syncthreads();
+#else
+    mbar_wait_parked(mbar, tile_parity, 4000);  // the tile has landed (the warp is parked, not spinning, until then)
+#endif
+#endif
+#ifdef VAW_ABL_NO_LOOP  // analysis only: the per-piece set-up without the row loop
+    if (cp.a[0][0].x + cp.a[1][3].y == 12345.f) dst[0] = 1;
+    return false;
+#endif
+
+    if (!(flags & kPieceInterior)) {  // straddles the frame border: paint the outside cells
+        const unsigned by_ = g.border & 255u, bu = (g.border >> 8) & 255u, bv = (g.border >> 16) & 255u;
+        fill_border(ltile, pl, nrows, by0, g.src_h, lx0, g.src_w, by_ * 0x01010101u, tid, 32 * kWarps);
+        fill_border(ctile, pl, cnrows, cy0, g.src_h >> 1, cbx0, g.src_w, (bu | (bv << 8)) * 0x00010001u, tid, 32 * kWarps);
+        __syncthreads();
+    }
+
+    const int dv0 = wy * hrows;
+    const int my_rows = max(0, min(hrows, rows - dv0));  // 0 for a warp below the frame's last row: its row loop does not run
+    // (no early return here: inside the persistent kernel's piece loop a branch on a per-warp value puts everything
+    // behind it into a region ptxas treats as divergent, and the tap-row constants below then lose their uniform registers)
+    // tap address = (iy - y0) * pl + (ix - x0) + tile, with the >>5 bias of the magic constant folded in
+#if VAW_SHFL_UNIFORM
+    const unsigned upl = __shfl_sync(0xffffffffu, (unsigned)pl, 0);  // warp-uniform as far as ptxas is concerned: a uniform register
+#else
+    const unsigned upl = (unsigned)pl;
+#endif
+#if VAW_SAMPLER == 3
+    // floor constants: tile origin (and, for luma, the tile's shared-memory address) folded into the round-down FMA
+    const unsigned never = (unsigned)g.out_w >> 31;  // 0 at run time: constants built from it stay loop-invariant uniforms
+#if VAW_VECTOR_CONSTS
+    const unsigned vnever = threadIdx.x >> 5;        // 0 as well, but per thread as far as ptxas knows: a vector register
+#else
+    const unsigned vnever = never;
+#endif
+    const FloorConst lconst = floor_const(-lx0, -by0, smem_u32(ltile) - 0x40000000u, upl, __uint_as_float(0x42000000u | vnever), (unsigned)raw.w >> 31);  // (the stage's zero pad: with g.out_w >> 31 ptxas keeps the luma pair in vector registers)
+    const FloorConst cconst = floor_const(-(cbx0 >> 1), -cy0, smem_u32(ctile) - 0x80000000u, upl, __uint_as_float(0x41800000u | vnever), never);
+#else
+    const unsigned lconst = smem_u32(ltile) - (unsigned)by0 * upl - (unsigned)lx0 - kMagicShift * upl - kMagicShift;
+    const unsigned cconst = ((smem_u32(ctile) - (unsigned)cy0 * upl - (unsigned)cbx0 - kMagicShift * upl) >> 1) - kMagicShift;
+#endif
+    const int u0 = u_lo + col0;
+    const bool inside = u0 < g.out_w;  // widths are even: the pair is inside or outside together
+    const bool pair_ok = ((reinterpret_cast<uintptr_t>(dst) | (uintptr_t)g.dst_pitch) & 1) == 0 &&
+                         u_lo + kPieceW <= g.out_w;
+    const TileBounds tb = {smem_u32(ltile), smem_u32(ltile) + (unsigned)(nrows * pl), smem_u32(ctile),
+                           smem_u32(ctile) + (unsigned)(cnrows * pl)};
+    uint8_t* const oy = dst + (size_t)(v_base + dv0) * g.dst_pitch + u0;
+    uint8_t* const oc = dst + (size_t)(g.out_h + ((v_base + dv0) >> 1)) * g.dst_pitch + u0;
+    if (pair_ok) rows_quad<false>(g, cp, lconst, cconst, upl, dv0, my_rows, oy, oc, inside, tb);
+    else rows_quad<true>(g, cp, lconst, cconst, upl, dv0, my_rows, oy, oc, inside, tb);
+    return true;  // this piece's loads completed a phase of the tile mbarrier
+}
+
 // kCtas = resident CTAs per SM the instantiation is compiled for, i.e. its register budget: 8 (64 registers), 7 (72:
 // the C3 tiles let seven CTAs share an SM, and the eight registers the 64-register build gives away buy nothing
 // there -- measured 0.651 against 0.661 ms) or 6 (80 registers, no spills in the fallback paths) where shared
@@ -251,174 +441,120 @@ warp_nv12_quad_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
     mbar_wait_parked(mbar_rec, 0, 4000);
 #endif
     const PieceRec* rs = reinterpret_cast<const PieceRec*>(smem + kQuadRecOffset);
-    const float4 rec_tail = *(reinterpret_cast<const float4*>(rs) + 12);  // base.x, base.y, flags, pad
-    const int4 raw = *(reinterpret_cast<const int4*>(rs) + 14);          // PieceStage
+    quad_piece(g, b, rec, rs, maps, smem, px, py, frame, 0u, lane, w, tid);
+}
 
-    const unsigned flags = __float_as_uint(rec_tail.z);
-    const int u_lo = px * kPieceW, v_base = py * ph;
-    const int rows = min(ph, g.out_h - v_base);  // even for NV12
-    uint8_t* const dst = b.dst + (size_t)frame * b.dst_frame_stride;
+// Persistent form of the quadrant kernel: kCtas CTAs per SM stay resident and pull pieces from a queue in table order
+// (an atomic counter in the pad word of the table's first record, which the builder zeroes), kPersistChunk pieces per ticket.
+// What it removes from the one-piece-per-CTA kernel: the CTA launch between two pieces of a shared-memory slot, the
+// entry code of four warps per piece, and the wait for the record -- the record of the NEXT piece is copied into the
+// second record buffer while the current piece is sampled.  The tile itself cannot be fetched ahead (one tile per CTA
+// is what shared memory holds at 7 CTAs per SM).
+#ifndef VAW_PERSIST_ONE_COPY
+#define VAW_PERSIST_ONE_COPY 1
+#endif
+#ifndef VAW_PERSIST_CHUNK
+#define VAW_PERSIST_CHUNK 4
+#endif
+constexpr int kPersistChunk = VAW_PERSIST_CHUNK;
 
-    if (b.skip_interior && (flags & (kPiecePoly | kPieceInterior)) == (kPiecePoly | kPieceInterior))
-        return;  // variant TEX: this piece belongs to the texture kernel
+template <int kCtas>
+__global__ void __launch_bounds__(32 * kWarps, kCtas)
+warp_nv12_quad_persist_kernel(const Geom g, const FrameBatch b, const PieceRec* __restrict__ table,
+                              const __grid_constant__ TileMaps maps, const int npx, const int npy)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int lane = threadIdx.x, w = threadIdx.y, tid = w * 32 + lane;
+    const unsigned sbase = smem_u32(smem);
+    const unsigned mbar = sbase, mbar_rec0 = sbase + 8;
+    const unsigned per_frame = (unsigned)(npx * npy), total = per_frame * (unsigned)b.n_frames;
+    unsigned* const queue = const_cast<unsigned*>(&table[0].pad);
+    int4* const slots = reinterpret_cast<int4*>(smem + kPersistSlotOffset);  // written by thread 0, read after the next CTA barrier
 
-    if (flags & kPieceOutside) {  // pure border: 128 threads fill the piece
-        const unsigned yw = (g.border & 255u) * 0x01010101u;
-        const unsigned cw = ((g.border >> 8) & 0xffffu) * 0x00010001u;
-        if (((reinterpret_cast<uintptr_t>(dst) | (uintptr_t)g.dst_pitch) & 15) == 0 && u_lo + kPieceW <= g.out_w) {
-            // 16 bytes per lane: 8 lanes per row, 16 rows per pass of the CTA
-            constexpr int kPass = 4 * kWarps;
-            const int sub = tid >> 3, col = (tid & 7) * 16;
-            const uint4 y4 = make_uint4(yw, yw, yw, yw), c4 = make_uint4(cw, cw, cw, cw);
-            uint8_t* yrow = dst + (size_t)(v_base + sub) * g.dst_pitch + u_lo + col;
-            for (int r = sub; r < rows; r += kPass, yrow += kPass * (size_t)g.dst_pitch) *reinterpret_cast<uint4*>(yrow) = y4;
-            uint8_t* crow = dst + (size_t)(g.out_h + (v_base >> 1) + sub) * g.dst_pitch + u_lo + col;
-            for (int r = sub; r < rows / 2; r += kPass, crow += kPass * (size_t)g.dst_pitch) *reinterpret_cast<uint4*>(crow) = c4;
+    // thread 0's private queue state: pieces [cur, end) of the ticket in hand and the first piece of the next ticket,
+    // whose atomic was issued when the ticket in hand was taken up -- kPersistChunk pieces before its result is needed, so
+    // the round trip never sits in front of a tile load.  (One piece per ticket serialises the whole launch on the
+    // counter: 130 k same-address atomics took 1.04 ms, 8 ns each.)
+    unsigned cur = 0, end = 0, ahead = 0xffffffffu;
+    auto take_ticket = [&]() -> unsigned { return atomicAdd(queue, (unsigned)kPersistChunk); };
+    auto next_piece = [&]() -> unsigned {  // >= total: the queue is drained
+        if (cur == end) {
+            cur = ahead;
+            end = cur < total ? min(cur + (unsigned)kPersistChunk, total) : cur;
+            if (cur >= total) return 0xffffffffu;
+            ahead = take_ticket();
+        }
+        return cur++;
+    };
+    auto post = [&](unsigned q, int buf) {  // thread 0 only: announce piece q in slot `buf` and start its record copy
+        if (q >= total) {
+            slots[buf] = make_int4(-1, 0, 0, 0);
             return;
         }
-        // ragged / unaligned: 4 columns per lane, rows split over the warps like the round-1 kernel
-        const int u0 = u_lo + 4 * lane, valid = g.out_w - u0, rpw = ph / kWarps;
-        const int dv0 = w * rpw, my = max(0, min(rpw, rows - dv0));
-        uint8_t* y0 = dst + (size_t)(v_base + dv0) * g.dst_pitch + u0;
-        uint8_t* cc = dst + (size_t)(g.out_h + ((v_base + dv0) >> 1)) * g.dst_pitch + u0;
-        if (valid > 0)
-            for (int dv = 0; dv < my; dv += 2) {
-                store_word<true>(y0, yw, valid);
-                store_word<true>(y0 + g.dst_pitch, yw, valid);
-                store_word<true>(cc, cw, valid);
-                y0 += 2 * (size_t)g.dst_pitch; cc += g.dst_pitch;
-            }
-        return;
-    }
-
-    // ---- the tile of this piece's source rectangle, as the builder laid it out (block-uniform) ------
-    const int lx0 = (int16_t)(raw.x & 0xffff), by0 = raw.x >> 16;
-    const int cbx0 = (int16_t)(raw.y & 0xffff), cy0 = raw.y >> 16;
-    const int pl = raw.z & 0xffff, nrows = (raw.z >> 16) & 0xffff, cnrows = raw.w & 0xffff;
-    const bool staged = (flags & kPiecePoly) && maps.enabled && pl != 0 && pl * (nrows + cnrows) <= maps.tile_cap;
-
-    if (!staged) {
-        // pieces without a polynomial certificate or whose box does not fit the tile: the gather paths of
-        // variant POLY with the 4-columns-per-lane mapping (warp w walks rows [w PH/4, (w+1) PH/4))
-        const int rpw = ph / kWarps, dv0 = w * rpw, my_rows = max(0, min(rpw, rows - dv0));
-        const int u0 = u_lo + 4 * lane, valid = g.out_w - u0;
-        if (my_rows <= 0) return;
-        PlaneRefs f;
-        f.y = b.src + (size_t)frame * b.src_frame_stride;
-        f.uv = f.y + (size_t)g.src_pitch * g.src_h;
-        f.dst = dst;
-        if (!(flags & kPiecePoly)) {  // op-for-op per pixel
-            const Rot R = load_rot(b, frame);
-            for (int dv = dv0; dv < dv0 + my_rows; dv += 2) {
-                float2 m[2][4];
-                exact_rows(g, R, u_lo, u0, v_base + dv, m);
-                sample_rows_checked(g, f, u0, v_base + dv, m);
-            }
-            return;
+        const unsigned frame = q / per_frame, r = q - frame * per_frame;
+        const unsigned py = r / (unsigned)npx, px = r - py * (unsigned)npx;
+        slots[buf] = make_int4((int)q, (int)px, (int)py, (int)frame);
+        const unsigned mb = mbar_rec0 + 8u * (unsigned)buf;
+        mbar_expect_tx(mb, (unsigned)sizeof(PieceRec));
+        bulk_g2s(sbase + kPersistRecOffset + (unsigned)(buf * kPersistRecStride), table + q, (unsigned)sizeof(PieceRec), mb);
+        if (frame + 1 < (unsigned)b.n_frames) {  // the same piece of the next frame: into L2 (see the one-piece kernel)
+            const char* nxt = reinterpret_cast<const char*>(table + q + per_frame);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + 128));
         }
-        ColPoly cp;
-        derive(rec, lane, cp);
-        if (flags & kPieceInterior) {
-            RowPtrs o;
-            o.y0 = dst + (size_t)(v_base + dv0) * g.dst_pitch + u0;
-            o.y1 = o.y0 + g.dst_pitch;
-            o.c = dst + (size_t)(g.out_h + ((v_base + dv0) >> 1)) * g.dst_pitch + u0;
-            o.step_y = 2 * (size_t)g.dst_pitch;
-            o.step_c = (size_t)g.dst_pitch;
-            const bool word_ok = ((reinterpret_cast<uintptr_t>(dst) | (uintptr_t)g.dst_pitch) & 3) == 0 &&
-                                 u_lo + kPieceW <= g.out_w;
-            if (word_ok) band_gmem<false>(g, cp, f, dv0, my_rows, o, valid);
-            else band_gmem<true>(g, cp, f, dv0, my_rows, o, valid);
-        } else {
-            for (int dv = dv0; dv < dv0 + my_rows; dv += 2) {
-                float2 m[2][4];
-                row_coords(cp, row_t(g, dv), m[0]);
-                row_coords(cp, row_t(g, dv + 1), m[1]);
-                sample_rows_checked(g, f, u0, v_base + dv, m);
-            }
-        }
-        return;
-    }
+    };
 
-    uint8_t* ltile = smem + kQuadTileOffset;
-    uint8_t* ctile = ltile + nrows * pl;
-
-    // ---- thread 0: launch the tile loads ------------------------------------------------------------
-#ifdef VAW_ABL_NO_TMA  // analysis only: no tile loads (the loop samples whatever the shared memory holds)
-    if (tid == 0 && g.out_w < 0) {
-#else
     if (tid == 0) {
-#endif
-        mbar_expect_tx(mbar, (unsigned)(pl * (nrows + cnrows)));
-        const int mi = (pl - kTileMinPitch) / kTilePitchStep;
-        const CUtensorMap *map = &maps.m[mi], *map32 = &maps.m32[mi], *map4 = &maps.m4[mi];
-        const unsigned l0 = smem_u32(ltile), c0 = smem_u32(ctile);
-        const int z = frame + b.tma_frame0;
-        int k = 0;
-        for (; k + 32 <= nrows; k += 32) tma_load_3d(l0 + (unsigned)(k * pl), map32, lx0 >> 2, by0 + k, z, mbar);
-        for (; k + 8 <= nrows; k += 8) tma_load_3d(l0 + (unsigned)(k * pl), map, lx0 >> 2, by0 + k, z, mbar);
-        if (k < nrows) tma_load_3d(l0 + (unsigned)(k * pl), map4, lx0 >> 2, by0 + k, z, mbar);
-        for (k = 0; k + 32 <= cnrows; k += 32) tma_load_3d(c0 + (unsigned)(k * pl), map32, cbx0 >> 2, g.src_h + cy0 + k, z, mbar);
-        for (; k + 8 <= cnrows; k += 8) tma_load_3d(c0 + (unsigned)(k * pl), map, cbx0 >> 2, g.src_h + cy0 + k, z, mbar);
-        if (k < cnrows) tma_load_3d(c0 + (unsigned)(k * pl), map4, cbx0 >> 2, g.src_h + cy0 + k, z, mbar);
+        mbar_init(mbar, 1);
+        mbar_init(mbar_rec0, 1);
+        mbar_init(mbar_rec0 + 8, 1);
+        ahead = take_ticket();
+        post(next_piece(), 0);
     }
-
-    // ---- this warp's quadrant; every lane collapses the polynomial onto its two columns ---------------
-    const int wx = w & 1, wy = w >> 1, hrows = ph / (kWarps / 2);
-    const int col0 = 64 * wx + 2 * lane;  // within the piece
-    ColPoly2 cp;
-    derive2(rs, col0, cp);
-    cp.base = make_float2(rec_tail.x, rec_tail.y);
-
-#ifndef VAW_ABL_NO_TMA
-#if VAW_ONE_WAITER
-    if (tid == 0) mbar_wait_parked(mbar, 0, 4000);  // the tile has landed
     __syncthreads();
-#else
-    mbar_wait_parked(mbar, 0, 4000);  // the tile has landed (the warp is parked, not spinning, until then)
-#endif
-#endif
-#ifdef VAW_ABL_NO_LOOP  // analysis only: the per-piece set-up without the row loop
-    if (cp.a[0][0].x + cp.a[1][3].y == 12345.f) dst[0] = 1;
-    return;
-#endif
 
-    if (!(flags & kPieceInterior)) {  // straddles the frame border: paint the outside cells
-        const unsigned by_ = g.border & 255u, bu = (g.border >> 8) & 255u, bv = (g.border >> 16) & 255u;
-        fill_border(ltile, pl, nrows, by0, g.src_h, lx0, g.src_w, by_ * 0x01010101u, tid, 32 * kWarps);
-        fill_border(ctile, pl, cnrows, cy0, g.src_h >> 1, cbx0, g.src_w, (bu | (bv << 8)) * 0x00010001u, tid, 32 * kWarps);
+    unsigned tile_uses = 0;  // staged pieces so far: phase of the tile mbarrier
+    // One piece from record buffer kBuf.  The buffer index is a compile-time constant (the loop below is unrolled by
+    // hand over the two buffers): with `it & 1` ptxas no longer proves the record's address -- and with it the tile
+    // pitch and the tap-row constants loaded from it -- warp-uniform, and the row loop grows from 271 to 296
+    // instructions per two row pairs.
+#if VAW_PERSIST_ONE_COPY
+    auto step = [&](int kBuf, unsigned it) -> bool {
+#else
+    auto step = [&](auto buf_c, unsigned it) -> bool {
+        constexpr int kBuf = decltype(buf_c)::value;
+#endif
+        const int4 slot = slots[kBuf];
+        if (__any_sync(0xffffffffu, slot.x < 0)) return false;  // queue drained (block-uniform; the vote says so to ptxas)
+        if (tid == 0) post(next_piece(), kBuf ^ 1);
+        mbar_wait_parked(mbar_rec0 + 8u * (unsigned)kBuf, (it >> 1) & 1u, 4000);
+        const PieceRec* rs = reinterpret_cast<const PieceRec*>(smem + kPersistRecOffset + kBuf * kPersistRecStride);
+        // block-uniform mirror of quad_piece()'s `staged` decision (its own return value is per-thread as far as ptxas
+        // can tell, and a loop-carried per-thread phase costs the row loop its uniform registers)
+        const unsigned fl = rs->flags;
+        const bool uses_tile = (fl & kPiecePoly) && !(fl & kPieceOutside) && maps.enabled && rs->stage.pl != 0 &&
+                               (int)rs->stage.pl * ((int)rs->stage.nrows + (int)rs->stage.cnrows) <= maps.tile_cap &&
+                               !(b.skip_interior && (fl & kPieceInterior));
+        quad_piece(g, b, table + slot.x, rs, maps, smem, slot.y, slot.z, slot.w, tile_uses & 1u, lane, w, tid);
+        tile_uses += uses_tile ? 1u : 0u;
+        // every warp is done with the tile, the record and the slot; generic-proxy accesses to the tile (taps, border
+        // fill) are ordered before the next piece's asynchronous tile writes
+#ifndef VAW_PERSIST_NO_FENCE  // (analysis only)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
         __syncthreads();
+        return true;
+    };
+#if VAW_PERSIST_ONE_COPY
+#pragma unroll 1
+    for (unsigned it = 0;; ++it)
+        if (!step((int)(it & 1u), it)) break;
+#else
+    for (unsigned it = 0;; it += 2) {
+        if (!step(std::integral_constant<int, 0>{}, it)) break;
+        if (!step(std::integral_constant<int, 1>{}, it + 1)) break;
     }
-
-    const int dv0 = wy * hrows;
-    const int my_rows = max(0, min(hrows, rows - dv0));
-    if (my_rows <= 0) return;
-    // tap address = (iy - y0) * pl + (ix - x0) + tile, with the >>5 bias of the magic constant folded in
-    const unsigned upl = (unsigned)pl;
-#if VAW_SAMPLER == 3
-    // floor constants: tile origin (and, for luma, the tile's shared-memory address) folded into the round-down FMA
-    const unsigned never = (unsigned)g.out_w >> 31;  // 0 at run time: constants built from it stay loop-invariant uniforms
-#if VAW_VECTOR_CONSTS
-    const unsigned vnever = threadIdx.x >> 5;        // 0 as well, but per thread as far as ptxas knows: a vector register
-#else
-    const unsigned vnever = never;
 #endif
-    const FloorConst lconst = floor_const(-lx0, -by0, smem_u32(ltile) - 0x40000000u, upl, __uint_as_float(0x42000000u | vnever), never);
-    const FloorConst cconst = floor_const(-(cbx0 >> 1), -cy0, smem_u32(ctile) - 0x80000000u, upl, __uint_as_float(0x41800000u | vnever), never);
-#else
-    const unsigned lconst = smem_u32(ltile) - (unsigned)by0 * upl - (unsigned)lx0 - kMagicShift * upl - kMagicShift;
-    const unsigned cconst = ((smem_u32(ctile) - (unsigned)cy0 * upl - (unsigned)cbx0 - kMagicShift * upl) >> 1) - kMagicShift;
-#endif
-    const int u0 = u_lo + col0;
-    const bool inside = u0 < g.out_w;  // widths are even: the pair is inside or outside together
-    const bool pair_ok = ((reinterpret_cast<uintptr_t>(dst) | (uintptr_t)g.dst_pitch) & 1) == 0 &&
-                         u_lo + kPieceW <= g.out_w;
-    const TileBounds tb = {smem_u32(ltile), smem_u32(ltile) + (unsigned)(nrows * pl), smem_u32(ctile),
-                           smem_u32(ctile) + (unsigned)(cnrows * pl)};
-    uint8_t* const oy = dst + (size_t)(v_base + dv0) * g.dst_pitch + u0;
-    uint8_t* const oc = dst + (size_t)(g.out_h + ((v_base + dv0) >> 1)) * g.dst_pitch + u0;
-    if (pair_ok) rows_quad<false>(g, cp, lconst, cconst, upl, dv0, my_rows, oy, oc, inside, tb);
-    else rows_quad<true>(g, cp, lconst, cconst, upl, dv0, my_rows, oy, oc, inside, tb);
 }
 
 long long tile_oob_count()
@@ -457,6 +593,15 @@ static cudaError_t configure_quad()
         e = cudaFuncSetAttribute(warp_nv12_quad_kernel<kCtas>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     return e;
 }
+template <int kCtas>
+static cudaError_t configure_persist()
+{
+    cudaError_t e = cudaFuncSetAttribute(warp_nv12_quad_persist_kernel<kCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         tile_smem_bytes(kTileCapMax));
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(warp_nv12_quad_persist_kernel<kCtas>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    return e;
+}
 cudaError_t launch_warp_nv12_tile(const Geom& g, const FrameBatch& b, const PieceRec* table, const TileMaps& maps,
                                   cudaStream_t st)
 {
@@ -475,6 +620,31 @@ cudaError_t launch_warp_nv12_tile(const Geom& g, const FrameBatch& b, const Piec
     }
     dim3 block(32, kWarps);
     dim3 grid(pieces_x(g.out_w), pieces_y(g.out_h, g.piece_h), b.n_frames);
+    static const int persist_mode = [] { const char* e = getenv("VAW_PERSIST"); return e ? atoi(e) : 0; }();
+    if (persist_mode) {
+        static std::atomic<int> sms[64];
+        int n_sm = tracked ? sms[dev].load(std::memory_order_acquire) : 0;
+        if (n_sm == 0) {
+            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+            cudaError_t e = configure_persist<8>();
+            if (e == cudaSuccess) e = configure_persist<7>();
+            if (e == cudaSuccess) e = configure_persist<6>();
+            if (e != cudaSuccess) return e;
+            if (tracked) sms[dev].store(n_sm, std::memory_order_release);
+        }
+        const int smem = tile_smem_bytes(maps.tile_cap);
+        const int npx = (int)grid.x, npy = (int)grid.y;
+        const long long pieces = (long long)npx * npy * b.n_frames;
+        auto slots = [&](int ctas) { return (unsigned)std::min<long long>((long long)n_sm * ctas, (pieces + kPersistChunk - 1) / kPersistChunk); };
+        if (maps.tile_cap <= tile_cap_for_ctas(8, kQuadTileOffset)) warp_nv12_quad_persist_kernel<8><<<slots(8), block, smem, st>>>(g, b, table, maps, npx, npy);
+        else if (maps.tile_cap <= tile_cap_for_ctas(7, kQuadTileOffset)) warp_nv12_quad_persist_kernel<7><<<slots(7), block, smem, st>>>(g, b, table, maps, npx, npy);
+        else {
+            int ctas = 6;
+            while (ctas > 1 && maps.tile_cap > tile_cap_for_ctas(ctas, kQuadTileOffset)) --ctas;
+            warp_nv12_quad_persist_kernel<6><<<slots(ctas), block, smem, st>>>(g, b, table, maps, npx, npy);
+        }
+        return cudaGetLastError();
+    }
     // the instantiation whose register budget matches the CTAs the tile capacity lets share an SM
     const int smem = tile_smem_bytes(maps.tile_cap);
     if (maps.tile_cap <= tile_cap_for_ctas(8, kQuadTileOffset)) warp_nv12_quad_kernel<8><<<grid, block, smem, st>>>(g, b, table, maps);

@@ -103,6 +103,9 @@ __device__ __forceinline__ unsigned chroma_tile4a(unsigned cconst, unsigned pl, 
 //     tap address is ONE multiply-add of the two bit patterns; the 0x40000000 that x carries is cancelled by the
 //     block-uniform `ubase` inside the load's address (register + uniform register).
 //   * horizontal blend of both tap rows at once in 16-bit halves, vertical blend + rounding constant as one IDP.2A.
+#ifndef VAW_SHFL_UNIFORM
+#define VAW_SHFL_UNIFORM 1
+#endif
 struct FloorConst { float2 c; unsigned row0, row1; float scale; };  // c = 1.90625 + D * 2^-22 per coordinate; row0 / row1 = tile
                                                       // address of the upper / lower tap row minus what x carries
 constexpr float kFloorScale = 7.450580596923828125e-09f;  // 2^-27
@@ -126,6 +129,11 @@ __device__ __forceinline__ FloorConst floor_const(int dx, int dy, unsigned row0,
     // register that the loads add for free ([register + uniform register + immediate])
     f.row0 = opaque_u32(row0) | never;
     f.row1 = opaque_u32(row0 + pl) | never;
+#if VAW_SHFL_UNIFORM
+    // a shuffle from a fixed lane tells ptxas the value is warp-uniform (all lanes hold the same one anyway)
+    f.row0 = __shfl_sync(0xffffffffu, f.row0, 0);
+    f.row1 = __shfl_sync(0xffffffffu, f.row1, 0);
+#endif
     return f;
 }
 
