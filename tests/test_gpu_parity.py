@@ -794,9 +794,11 @@ def test_clip_scheduler_frame_parallel(V, oracle):
 
 
 # ---- the reference's literal behaviour: one remap of a BGR 8UC3 frame ---------------------------------
-def test_bgr_literal_reference_case(V, oracle):
+@pytest.mark.parametrize("variant", [GATHER, TILED])
+def test_bgr_literal_reference_case(V, oracle, variant):
     """C1-ref: 1920x1080 BGR -> 1759x998 (odd width), identity rotation, border 0
-    (FrameSourceWarp.cpp:306-312, :401, :445)."""
+    (FrameSourceWarp.cpp:306-312, :401, :445).  GATHER: the op-for-op map, bit for bit; TILED (what AUTO picks:
+    vaw_packed_tile.cu, polynomial map, TMA-staged BGR tiles): coordinates within 1e-3 px of the reference kernel."""
     import torch
     cam = V.get_preset_camera(V.warp.GOPRO_H4B_WIDE169_MEASURED, 1920, 1080)
     out = V.get_output_camera(cam)
@@ -806,17 +808,27 @@ def test_bgr_literal_reference_case(V, oracle):
     k = G.oracle_k(oracle, (cam, out))
     for rot in [(0, 0, 0), (1.0, -2.0, 0.5)]:
         R = rotation_xyz(*rot)
-        ctx = V.WarpContext(cam, out, fmt=V.FORMAT_BGR24, border=(0, 0, 0))
+        ctx = V.WarpContext(cam, out, fmt=V.FORMAT_BGR24, border=(0, 0, 0), variant=variant)
+        assert ctx.variant == variant
+        if variant == TILED:
+            auto = V.WarpContext(cam, out, fmt=V.FORMAT_BGR24, border=(0, 0, 0))
+            assert auto.variant == TILED
+            auto.close()
         dst = torch.empty(ctx.frame_shape("dst"), dtype=torch.uint8, device="cuda")
         ctx.warp(G.to_dev(src), dst, R)
         mx, my = [t.cpu().numpy() for t in ctx.dump_coords(R, 0)]
-        hx, hy = G.host_device_map(k, R, 998, 1759)
-        assert G.bits_equal(mx, hx) and G.bits_equal(my, hy)
+        if variant == GATHER:
+            hx, hy = G.host_device_map(k, R, 998, 1759)
+            assert G.bits_equal(mx, hx) and G.bits_equal(my, hy)
+        else:
+            ox, oy, _ = oracle.reference_create_map(k, R, 998, 1759, threads=NCPU)
+            assert np.array_equal(np.isnan(ox), np.isnan(mx)) and np.array_equal(np.isnan(oy), np.isnan(my))
+            assert max(float(np.nanmax(np.abs(mx - ox))), float(np.nanmax(np.abs(my - oy)))) < 1e-3
         ref = oracle.remap_u8(src, mx, my, border=(0, 0, 0), threads=NCPU)
         assert np.array_equal(dst.cpu().numpy(), ref)
         full = oracle.warp_bgr(src, 1759, 998, k, R, threads=NCPU)
         st = G.diff_stats(dst.cpu().numpy(), full)
-        _record(f"bgr_vs_oracle_path_{rot}", st)
+        _record(f"bgr_vs_oracle_path_v{variant}_{rot}", st)
         assert st["differ"] < 0.01
         ctx.close()
 
@@ -861,6 +873,53 @@ def test_gray8(V, oracle):
     mx, my = [t.cpu().numpy() for t in ctx.dump_coords(g["rot"], 0)]
     assert np.array_equal(dst.cpu().numpy(), oracle.remap_u8(src, mx, my, border=(200,)))
     ctx.close()
+
+
+@pytest.mark.parametrize("fmt", ["bgr", "gray"])
+def test_packed_formats_on_staged_tiles_4k(V, oracle, fmt):
+    """BGR24 / GRAY8 through the staged-tile kernel (vaw_packed_tile.cu) at 4K with rotation: a batch into pitched
+    buffers, distinct border channels (border-straddling pieces paint the tile with a 3-periodic colour), 0 LSB against
+    cv::remap's integer filter on the kernel's own map, the same bytes as variant GATHER's filter on that map, and
+    padding untouched."""
+    import torch
+    from video_annotator_b200 import configs
+    w = configs.workload("C3")
+    sw, sh = w.src_size
+    ow, oh = 3838, 2157  # ragged right column of pieces, odd height
+    cn = 3 if fmt == "bgr" else 1
+    border = (10, 200, 90) if cn == 3 else (77,)
+    vfmt = V.FORMAT_BGR24 if cn == 3 else V.FORMAT_GRAY8
+    ctx = V.WarpContext(w.input_camera, w.output_camera, fmt=vfmt, out_size=(ow, oh), border=border)
+    assert ctx.variant == TILED
+    n = 3
+    rots = [rotation_xyz(2.0, -3.0, 1.5), rotation_xyz(-6.0, 4.0, -9.0), rotation_xyz(0.3, 0.2, -0.1)]
+    rng = np.random.default_rng(5)
+    spitch = sw * cn + 16 * 3
+    host = rng.integers(0, 256, (n, sh, spitch), dtype=np.uint8)
+    src = G.to_dev(host)
+    dpitch = ow * cn + 7
+    dst = torch.full((n, oh, dpitch), 91, dtype=torch.uint8, device="cuda")
+    rdev = torch.empty(n * 9, dtype=torch.float32, device="cuda")
+    ctx.upload_rotations(rots, rdev)
+    ctx.warp_batch(src, dst, rdev, n, src_pitch=spitch, src_stride=sh * spitch, dst_pitch=dpitch, dst_stride=oh * dpitch)
+    torch.cuda.synchronize()
+    got = dst.cpu().numpy()
+    assert (got[:, :, ow * cn:] == 91).all()
+    for i in (0, 1, 2):
+        mx, my = [t.cpu().numpy() for t in ctx.dump_coords(rots[i], 0)]
+        img = host[i, :, :sw * cn].reshape(sh, sw, cn) if cn == 3 else host[i, :, :sw]
+        ref = oracle.remap_u8(np.ascontiguousarray(img), mx, my, border=border, threads=NCPU)
+        assert np.array_equal(got[i, :, :ow * cn].reshape(ref.shape), ref), (fmt, i)
+    # aligned, packed buffers: the 2-byte / 4-byte store paths
+    ctx2 = V.WarpContext(w.input_camera, w.output_camera, fmt=vfmt, out_size=(3840, 2160), border=border)
+    src2 = G.to_dev(np.ascontiguousarray(host[0, :, :sw * cn]))
+    dst2 = torch.empty(ctx2.frame_shape("dst"), dtype=torch.uint8, device="cuda")
+    ctx2.warp(src2, dst2, rots[1])
+    mx, my = [t.cpu().numpy() for t in ctx2.dump_coords(rots[1], 0)]
+    img = host[0, :, :sw * cn].reshape(sh, sw, cn) if cn == 3 else host[0, :, :sw]
+    ref = oracle.remap_u8(np.ascontiguousarray(img), mx, my, border=border, threads=NCPU)
+    assert np.array_equal(dst2.cpu().numpy().reshape(ref.shape), ref)
+    ctx.close(); ctx2.close()
 
 
 # ---- full-size clips through size-independent properties ----------------------------------------------

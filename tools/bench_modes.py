@@ -46,8 +46,10 @@ def main():
              ("NV12 cubic", V.FORMAT_NV12, V.INTER_CUBIC, 0),
              ("NV12 lanczos4", V.FORMAT_NV12, V.INTER_LANCZOS4, 0),
              ("NV12 in -> BGR24 out, fused (cvtColor + 3-channel remap)", V.FORMAT_NV12_TO_BGR24, V.INTER_LINEAR, 0),
-             ("BGR24 linear (the reference's literal format)", V.FORMAT_BGR24, V.INTER_LINEAR, 0),
-             ("GRAY8 linear", V.FORMAT_GRAY8, V.INTER_LINEAR, 0)]
+             ("BGR24 linear (the reference's literal format; staged-tile kernel, default)", V.FORMAT_BGR24, V.INTER_LINEAR, 0),
+             ("BGR24 linear, variant GATHER (per-pixel taps)", V.FORMAT_BGR24, V.INTER_LINEAR, 1),
+             ("GRAY8 linear (staged-tile kernel, default)", V.FORMAT_GRAY8, V.INTER_LINEAR, 0),
+             ("GRAY8 linear, variant GATHER", V.FORMAT_GRAY8, V.INTER_LINEAR, 1)]
     for name, fmt, interp, variant in modes:
         try:
             ctx = V.WarpContext(w.input_camera, w.output_camera, fmt=fmt, out_size=w.out_size, variant=variant, interpolation=interp)

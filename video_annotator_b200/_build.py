@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvaw.so")
 
-SOURCES = ["vaw_kernels.cu", "vaw_pieces.cu", "vaw_poly.cu", "vaw_tile.cu", "vaw_bgr.cu", "vaw_tex.cu", "vaw_flow.cu", "vaw_corners.cu", "vaw_flow_api.cu", "vaw_api.cu", "vaw_camera.cpp", "vaw_clip.cpp"]
+SOURCES = ["vaw_kernels.cu", "vaw_pieces.cu", "vaw_poly.cu", "vaw_tile.cu", "vaw_packed_tile.cu", "vaw_bgr.cu", "vaw_tex.cu", "vaw_flow.cu", "vaw_corners.cu", "vaw_flow_api.cu", "vaw_api.cu", "vaw_camera.cpp", "vaw_clip.cpp"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -69,6 +69,9 @@ struct vaw_ctx {
     // variant TILED: tensor maps, cached per source layout (encoding 11 maps costs ~10 us)
     struct MapEntry { const void* src = nullptr; int pitch = 0; size_t stride = 0; int frames = 0; vaw::TileMaps maps{}; };
     MapEntry map_cache[4];
+    struct PackedEntry { const void* src = nullptr; int pitch = 0; size_t stride = 0; int frames = 0; vaw::PackedMaps maps{}; };
+    PackedEntry packed_cache[2];  // the same for GRAY8 / BGR24 clips (vaw_packed_tile.cu)
+    int packed_next = 0;
     int map_next = 0;
     int tile_cap = 32 << 10;  // chosen at creation from the pieces' source boxes
     // vaw_bind_clip: a slab of equally spaced source frames; launches inside it share its tensor maps
@@ -266,6 +269,41 @@ const vaw::TileMaps& tile_maps(vaw_ctx* ctx, const uint8_t* src, int pitch, size
     return e.maps;
 }
 
+// Tensor maps for a clip of `frames` interleaved GRAY8 / BGR24 frames at `src` (vaw_packed_tile.cu).
+const vaw::PackedMaps& packed_maps(vaw_ctx* ctx, const uint8_t* src, int pitch, size_t stride, int frames)
+{
+    for (vaw_ctx::PackedEntry& e : ctx->packed_cache)
+        if (e.src == src && e.pitch == pitch && e.stride == stride && e.frames == frames && e.maps.tile_cap == ctx->tile_cap) return e.maps;
+    vaw_ctx::PackedEntry& e = ctx->packed_cache[ctx->packed_next];
+    ctx->packed_next = (ctx->packed_next + 1) % 2;
+    e.src = src; e.pitch = pitch; e.stride = stride; e.frames = frames;
+    e.maps.enabled = 0;
+    e.maps.tile_cap = ctx->tile_cap;
+    const int rows_total = ctx->p.src_height;
+    EncodeTiledFn enc = encode_tiled();
+    const bool ok = enc && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (pitch & 15) == 0 && (stride & 15) == 0 &&
+                    pitch >= 16 && rows_total >= 1 && (frames == 1 || stride >= (size_t)pitch);
+    if (!ok) return e.maps;
+    const cuuint64_t dims[3] = {(cuuint64_t)(pitch / 8), (cuuint64_t)rows_total, (cuuint64_t)frames};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch,
+                                   (cuuint64_t)(stride ? stride : (size_t)pitch * (size_t)rows_total)};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    for (int i = 0; i < vaw::kPackedWidths; ++i) {
+        const cuuint32_t box16[3] = {(cuuint32_t)((vaw::kPackedMinPitch + i * vaw::kPackedPitchStep) / 8), 16, 1};
+        CUresult r = enc(&e.maps.m16[i], CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<uint8_t*>(src), dims, strides,
+                         box16, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return e.maps;
+        const cuuint32_t box4[3] = {box16[0], 4, 1};
+        r = enc(&e.maps.m4[i], CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<uint8_t*>(src), dims, strides,
+                box4, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return e.maps;
+    }
+    e.maps.enabled = 1;
+    return e.maps;
+}
+
 void destroy_tex_entry(vaw_ctx::TexEntry& e)
 {
     for (int k = 0; k < e.n_groups; ++k) {
@@ -361,7 +399,9 @@ int launch(vaw_ctx* ctx, const uint8_t* src, int src_pitch, size_t src_stride, u
     b.rots = rots;
     if (rot0) b.rot0 = *rot0;
     const bool fused_bgr = ctx->p.format == VAW_FORMAT_NV12_TO_BGR24;
-    const bool poly = fused_bgr || (ctx->p.format == VAW_FORMAT_NV12 && ctx->variant != VAW_VARIANT_GATHER);
+    const bool packed = ctx->p.format == VAW_FORMAT_BGR24 || ctx->p.format == VAW_FORMAT_GRAY8;
+    const bool poly = fused_bgr || (ctx->p.format == VAW_FORMAT_NV12 && ctx->variant != VAW_VARIANT_GATHER) ||
+                      (packed && ctx->variant == VAW_VARIANT_TILED);
     const bool tiled = ctx->variant == VAW_VARIANT_TILED || ctx->variant == VAW_VARIANT_TEX;
     // grid.z is limited to 65535 frames per launch; variant TEX to kTexGroups textures of <= 65000 rows
     int per_launch = 65535;
@@ -429,7 +469,11 @@ int launch(vaw_ctx* ctx, const uint8_t* src, int src_pitch, size_t src_stride, u
                     clip_frame0 = (int)(off / ctx->clip_stride);
             }
             const vaw::TileMaps* tm = nullptr;
-            if (tiled)
+            const vaw::PackedMaps* pm = nullptr;
+            if (packed)
+                pm = clip_frame0 >= 0 ? &packed_maps(ctx, ctx->clip_base, ctx->clip_pitch, ctx->clip_stride, ctx->clip_slots)
+                                      : &packed_maps(ctx, bb.src, src_pitch, src_stride, bb.n_frames);
+            else if (tiled)
                 tm = clip_frame0 >= 0 ? &tile_maps(ctx, ctx->clip_base, ctx->clip_pitch, ctx->clip_stride, ctx->clip_slots)
                                       : &tile_maps(ctx, bb.src, src_pitch, src_stride, bb.n_frames);
             if (clip_frame0 >= 0) bb.tma_frame0 = clip_frame0;
@@ -449,7 +493,8 @@ int launch(vaw_ctx* ctx, const uint8_t* src, int src_pitch, size_t src_stride, u
                         VAW_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
                     }
                 }
-                if (fused_bgr) e = vaw::launch_warp_nv12_to_bgr(g, pb, ptab, st);
+                if (packed) e = vaw::launch_warp_packed_tile(g, pb, ptab, *pm, ctx->channels, st);
+                else if (fused_bgr) e = vaw::launch_warp_nv12_to_bgr(g, pb, ptab, st);
                 else if (tiled) e = vaw::launch_warp_nv12_tile(g, pb, ptab, *tm, st);
                 else e = vaw::launch_warp_nv12_poly(g, pb, ptab, st);
                 if (e != cudaSuccess) return cuda_fail(ctx, e, "warp kernel launch");
@@ -611,14 +656,13 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
     if (p.projection != 0) {
         // only createMap.cl's pair has an fp32 operation order (variant GATHER); the others exist on the
         // polynomial variants, whose coordinates come from double-precision anchors
-        const bool poly_fmt = p.format == VAW_FORMAT_NV12 || p.format == VAW_FORMAT_NV12_TO_BGR24;
-        if (!poly_fmt || p.variant == VAW_VARIANT_GATHER || p.interpolation != VAW_INTER_LINEAR)
-            return fail(nullptr, VAW_ERR_UNSUPPORTED, "rectilinear input / fisheye output: NV12 sources, INTER_LINEAR, variants AUTO / POLY / TILED");
+        if (p.variant == VAW_VARIANT_GATHER || p.interpolation != VAW_INTER_LINEAR)
+            return fail(nullptr, VAW_ERR_UNSUPPORTED, "rectilinear input / fisheye output: INTER_LINEAR, variants AUTO / POLY / TILED");
         if ((p.projection & 1) && (p.src_distortion[0] != 0 || p.src_distortion[1] != 0 || p.src_distortion[2] != 0 || p.src_distortion[3] != 0))
             return fail(nullptr, VAW_ERR_INVALID, "fisheye distortion coefficients with a rectilinear input camera");
     }
-    if (p.variant >= VAW_VARIANT_POLY && p.format != VAW_FORMAT_NV12 && p.format != VAW_FORMAT_NV12_TO_BGR24)
-        return fail(nullptr, VAW_ERR_UNSUPPORTED, "variants POLY, TILED and TEX exist for NV12 only");
+    if (p.variant >= VAW_VARIANT_POLY && p.variant != VAW_VARIANT_TILED && p.format != VAW_FORMAT_NV12 && p.format != VAW_FORMAT_NV12_TO_BGR24)
+        return fail(nullptr, VAW_ERR_UNSUPPORTED, "variants POLY and TEX exist for NV12 only (GRAY8 / BGR24: GATHER or TILED)");
     // `short` indices in createMap.cl:10-11 and int16 taps in cv::remap cap both sizes
     if (p.src_width < 2 || p.src_height < 2 || p.out_width < 1 || p.out_height < 1 ||
         p.src_width > 32766 || p.src_height > 32766 || p.out_width > 32766 || p.out_height > 32766)
@@ -689,9 +733,11 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
         cudaGetLastError();
         return rc;
     }
+    // AUTO: the staged-tile kernels wherever they exist (INTER_LINEAR: NV12 -> vaw_tile.cu, GRAY8 / BGR24 -> vaw_packed_tile.cu)
     ctx->variant = p.variant != VAW_VARIANT_AUTO ? p.variant
                    : (p.format == VAW_FORMAT_NV12_TO_BGR24 ? VAW_VARIANT_POLY
-                      : (p.format == VAW_FORMAT_NV12 && p.interpolation == VAW_INTER_LINEAR ? VAW_VARIANT_TILED : VAW_VARIANT_GATHER));
+                      : (p.interpolation == VAW_INTER_LINEAR ? VAW_VARIANT_TILED : VAW_VARIANT_GATHER));
+    const bool packed_fmt = p.format == VAW_FORMAT_BGR24 || p.format == VAW_FORMAT_GRAY8;
     if (ctx->variant != VAW_VARIANT_GATHER) {
         // rows per piece: keep the cubic-in-v truncation error ~ 2.4e-3 * f_in * (PH / f_out)^4 px
         // (measured on the BASELINE geometries) below the certificate's 5e-5 px
@@ -702,6 +748,7 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
 #define VAW_PH_RULE 5e-5  // = the builder's accuracy certificate; 2e-5 halved C1's pieces for nothing (204 k -> 247 k frames/s at 32 rows, same measured errors)
 #endif
         while (ph > 8 && 2.4e-3 * fin * std::pow(ph / fout, 4.0) > VAW_PH_RULE) ph >>= 1;
+        if (p.format == VAW_FORMAT_BGR24 && ph > 16) ph = 16;  // three bytes per source pixel: a 32-row piece needs ~60 KB of tile
         g.piece_h = ph;
         g.t_off = 0.5f * (float)(ph - 1);
         g.t_scale = 2.0f / (float)ph;
@@ -744,7 +791,7 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
                 const vaw::PieceRec* rec = reinterpret_cast<const vaw::PieceRec*>(host.data());
                 long long need = 0;
                 for (size_t i = 0; i < ctx->pieces_per_frame; ++i) {
-                    const int nb = vaw::tile_need_bytes(rec[i]);
+                    const int nb = packed_fmt ? vaw::packed_tile_need_bytes(rec[i], ctx->channels) : vaw::tile_need_bytes(rec[i]);
                     if (nb != 0x7fffffff && nb > need) need = nb;
                 }
                 ctx->tile_need = need;

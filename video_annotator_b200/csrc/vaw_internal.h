@@ -60,6 +60,21 @@ int tile_smem_bytes(int tile_cap);
 long long tile_oob_count();
 cudaError_t launch_warp_nv12_tile(const Geom& g, const FrameBatch& b, const PieceRec* table, const TileMaps& maps,
                                   cudaStream_t st);
+// Quadrant kernel for interleaved GRAY8 / BGR24 frames (vaw_packed_tile.cu): tensor maps over the clip viewed as
+// (pitch / 8, H, frames) 8-byte elements, one per tile row pitch (128 ... 1536 bytes in steps of 64), boxes of 16 and of 4 rows.
+constexpr int kPackedMinPitch = 128, kPackedMaxPitch = 1536, kPackedPitchStep = 64;
+constexpr int kPackedWidths = (kPackedMaxPitch - kPackedMinPitch) / kPackedPitchStep + 1;
+struct alignas(64) PackedMaps {
+    CUtensorMap m16[kPackedWidths];
+    CUtensorMap m4[kPackedWidths];
+    int enabled;   // 0: layout not TMA-compatible -> every piece is sampled per pixel from global memory
+    int tile_cap;  // bytes of shared memory for the tile of one CTA
+    int pad[14];
+};
+int packed_tile_need_bytes(const PieceRec& rec, int channels);
+int packed_tile_smem_bytes(int tile_cap);
+cudaError_t launch_warp_packed_tile(const Geom& g, const FrameBatch& b, const PieceRec* table, const PackedMaps& maps,
+                                    int channels, cudaStream_t st);
 // Variant TEX (vaw_tex.cu): certified interior pieces are filtered by the texture units.  The clip
 // is viewed as pitch-linear 2-D textures over groups of `group_frames` whole frames (a texture is at
 // most 65000 rows high): y[k] = 8-bit luma view, uv[k] = 2 x 8-bit view of the same rows (chroma

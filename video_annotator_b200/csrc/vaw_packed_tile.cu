@@ -1,0 +1,366 @@
+// vaw_packed_tile.cu -- fused map + remap for interleaved GRAY8 / BGR24 frames, source tiles staged in shared
+// memory by TMA: the quadrant kernel of vaw_tile.cu for the reference's LITERAL frame format.
+//
+// The reference warps BGR frames: cvtColor(COLOR_YUV2BGR_NV12), then remap on 8UC3
+// (/root/reference/opencv/FrameSourceWarp.cpp:399-401 and :306-312, map from createMap.cl).  Round 1 and most
+// of round 2 ran that format on the per-pixel-tap kernel (vaw_kernels.cu: coordinates op for op, twelve
+// global loads per pixel, 12.7 k frames/s at 4K = 10 % of the roofline for its bytes).  Here it takes the NV12
+// path's machinery instead:
+//   - coordinates from the per-piece polynomial table (vaw_pieces.cuh; the map is format-independent);
+//   - the piece's source box (pixels x0..x1, rows y0..y1 of the record) staged as bytes
+//     [kCn x0 & ~15, ...) x rows by cp.async.bulk.tensor over the clip viewed as (pitch / 8, H, frames)
+//     8-byte elements (a BGR box is up to 3 x wider than a luma box: 4-byte elements cap a TMA box at 1024 bytes);
+//   - 128 x 16-pixel pieces for BGR (a 32-row piece needs ~60 KB of tile: three CTAs per SM);
+//   - per sample the round-down-FMA floor and the 16-bit-half blend of vaw_tile.cuh, once per channel off
+//     ONE tap address (LDS.U8 [a + c], [a + kCn + c], [a + pitch + c], [a + pitch + kCn + c]).
+// Pieces without a polynomial certificate, pieces whose box does not fit the tile and layouts the TMA engine
+// cannot address are sampled per pixel from global memory (checked taps), pure-border pieces are a fill.
+// Output sizes may be odd here (1759 x 998 is the reference's own C1 case): ragged stores are per byte.
+#include <cuda.h>
+#include <stdint.h>
+#include <algorithm>
+#include <atomic>
+#include "vaw_internal.h"
+#include "vaw_poly.cuh"
+#include "vaw_tile.cuh"
+
+namespace vaw {
+
+namespace {
+
+constexpr int kWarps = 4;
+constexpr int kRecOffset = 16, kTileOffset = 256;  // [tile mbarrier | record mbarrier | record (240 B) | tile (128-byte aligned)]
+
+// Tile layout of a piece's source box for kCn interleaved channels (same integer arithmetic on the host:
+// packed_tile_need_bytes): rows are `pl` bytes apart (a multiple of 64), start at source byte bx0 (a multiple of
+// 16) of row box.y0 and come in whole 4-row boxes.
+template <int kCn>
+__host__ __device__ inline bool packed_stage(const PieceBox& b, int tile_cap, int& bx0, int& pl, int& nrows)
+{
+    bx0 = (kCn * (int)b.x0) & ~15;
+    const int wb = (kCn * ((int)b.x1 + 1) - bx0 + 15) & ~15;
+    pl = (wb + 63) & ~63;
+    if (pl < kPackedMinPitch) pl = kPackedMinPitch;
+    nrows = ((int)b.y1 - (int)b.y0 + 4) & ~3;
+    return pl <= kPackedMaxPitch && nrows > 0 && nrows < 4096 && pl * nrows <= tile_cap;
+}
+
+template <int kCn>
+__device__ __forceinline__ void store_px_checked(uint8_t* row, int u, int out_w, unsigned v)
+{
+    if (u >= out_w) return;
+#pragma unroll
+    for (int c = 0; c < kCn; ++c) row[(size_t)u * kCn + c] = (uint8_t)(v >> (8 * c));
+}
+
+template <int kCn>
+__device__ __forceinline__ unsigned sample_checked(const Geom& g, const uint8_t* __restrict__ src, float mx, float my)
+{
+    if (kCn == 1) return (unsigned)sample_c1(src, g.src_pitch, g.src_w, g.src_h, mx, my, g.border & 255);
+    return sample_c3(src, g.src_pitch, g.src_w, g.src_h, mx, my, g.border & 0xffffffu);
+}
+
+// One sample from the staged tile: B | G << 8 | R << 16 (or Y).  fc.c folds -box.x0 / -box.y0 into the round-down
+// FMA, fc.row0 / row1 = tile address + (kCn x0 - bx0) - kCn 2^30 (+ pitch): see luma_tile3 (vaw_tile.cuh).
+template <int kCn>
+__device__ __forceinline__ unsigned packed_tile_sample(const FloorConst& fc, unsigned pl, float2 m, const TileBounds& tb)
+{
+    const float2 s = __ffma2_rn(m, pair(fc.scale), pair(kMagic));
+    const float2 fl = __ffma2_rd(s, pair(kFloorScale), fc.c);
+    const unsigned a = kCn == 1 ? imad_u32(__float_as_uint(fl.y), pl, __float_as_uint(fl.x))
+                                : imad_u32(__float_as_uint(fl.x), (unsigned)kCn, __float_as_uint(fl.y) * pl);
+    const unsigned a0 = a + fc.row0, a1 = a + fc.row1;
+#ifdef VAW_BOUNDS_CHECK
+    check_taps(a0, a1, 2u * kCn, tb.l_lo, tb.l_hi);
+#endif
+    const unsigned ax = __float_as_uint(s.x) & 31u, ay = __float_as_uint(s.y) & 31u;
+    const unsigned wx = 32u - ax, wy = imad_u32(ay, 255u, 32u);  // (32 - ay) | ay << 8
+    unsigned out = 0;
+#pragma unroll
+    for (int c = 0; c < kCn; ++c) {
+        unsigned t00, t01, t10, t11;
+        if (c == 0) { t00 = lds_u8<0>(a0); t01 = lds_u8<kCn>(a0); t10 = lds_u8<0>(a1); t11 = lds_u8<kCn>(a1); }
+        else if (c == 1) { t00 = lds_u8<1>(a0); t01 = lds_u8<kCn + 1>(a0); t10 = lds_u8<1>(a1); t11 = lds_u8<kCn + 1>(a1); }
+        else { t00 = lds_u8<2>(a0); t01 = lds_u8<kCn + 2>(a0); t10 = lds_u8<2>(a1); t11 = lds_u8<kCn + 2>(a1); }
+        const unsigned left = __byte_perm(t00, t10, 0x5410), right = __byte_perm(t01, t11, 0x5410);  // top | bottom << 16
+        const unsigned h = imad_u32(right, ax, left * wx);
+        const unsigned v = __dp2a_lo(h, wy, 512u) >> 10;
+        out |= v << (8 * c);
+    }
+    return out;
+}
+
+// Overwrite the cells of the staged tile that lie outside the source with the border colour (cv::remap's
+// BORDER_CONSTANT replaces each out-of-image tap; the colour has period kCn along a row, so the 4-byte word at
+// tile word index wd starts with channel (bx0 + 4 wd) mod kCn).  Tile row r <-> source row y0 + r, tile byte c <->
+// source byte bx0 + c, valid in [0, n_bytes).  Warps run along the rows, lanes along the words.
+template <int kCn>
+__device__ __forceinline__ void fill_border_packed(uint8_t* tile, int pl, int tile_rows, int y0, int n_rows, int bx0,
+                                                   int n_bytes, unsigned border, int lane, int w)
+{
+    unsigned pw[3];  // the word that starts with channel 0, 1, 2
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        unsigned v = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v |= ((border >> (8 * ((r + i) % kCn))) & 255u) << (8 * i);
+        pw[r] = v;
+    }
+    const int wpr = pl >> 2;
+    const int r_lo = min(max(-y0, 0), tile_rows), r_hi = min(max(n_rows - y0, r_lo), tile_rows);
+    const int c_lo = min(max(-bx0, 0), pl), c_hi = min(max(n_bytes - bx0, c_lo), pl);
+    const int w_lo = c_lo >> 2, w_hi = (c_hi + 3) >> 2;  // words [w_lo, w_hi) hold at least one inside byte
+    int bm = bx0 % kCn;
+    if (bm < 0) bm += kCn;
+    const int rot0 = kCn == 1 ? 0 : (bm + lane) % kCn;  // channel of the first byte of word `lane`; 4 = 1 mod 3: +1 per word
+    unsigned* words = reinterpret_cast<unsigned*>(tile);
+    for (int r = w; r < tile_rows; r += kWarps) {
+        const bool row_out = r < r_lo || r >= r_hi;
+        unsigned* row = words + r * wpr;
+        int rot = rot0;
+        for (int wd = lane; wd < wpr; wd += 32) {
+            if (row_out || wd < w_lo || wd >= w_hi) row[wd] = pw[rot];
+            if (kCn != 1) rot = (rot + 32 % kCn) % kCn;
+        }
+        if (!row_out && (c_hi & 3) && lane == 0) {  // the inside / outside seam falls into word w_hi - 1
+            uint8_t* bytes = tile + r * pl;
+            for (int c = c_hi; c < min(4 * w_hi, pl); ++c) bytes[c] = (uint8_t)(border >> (8 * (((bm + c) % kCn + kCn) % kCn)));
+        }
+    }
+}
+
+// nrows rows starting at piece row dv0 for the lane's two columns (u0, u0 + 1); taps from the staged tile.
+template <int kCn, bool kRagged>
+__device__ __forceinline__ void rows_packed(const Geom& g, const ColPoly2& cp, const FloorConst& fc, unsigned pl, int dv0,
+                                            int nrows, uint8_t* __restrict__ out0, int u0, const TileBounds& tb)
+{
+    float t = row_t(g, dv0);
+    const float dt = g.t_scale, dt2 = __fadd_rn(g.t_scale, g.t_scale);
+    const unsigned dpitch = (unsigned)g.dst_pitch + (threadIdx.x >> 5);  // a vector register (see rows_quad)
+    const unsigned long long g0 = (unsigned long long)__cvta_generic_to_global(out0);
+#pragma unroll 1
+    for (unsigned j2 = opaque_zero(); j2 < (unsigned)nrows; j2 += 2) {
+        const float2 t0 = pair(t), t1 = pair(__fadd_rn(t, dt));
+        t = __fadd_rn(t, dt2);
+        const unsigned v00 = packed_tile_sample<kCn>(fc, pl, col_coord(cp.a[0], cp.base, t0), tb);
+        const unsigned v01 = packed_tile_sample<kCn>(fc, pl, col_coord(cp.a[1], cp.base, t0), tb);
+        const unsigned v10 = packed_tile_sample<kCn>(fc, pl, col_coord(cp.a[0], cp.base, t1), tb);
+        const unsigned v11 = packed_tile_sample<kCn>(fc, pl, col_coord(cp.a[1], cp.base, t1), tb);
+        const unsigned long long r0 = row_ptr(g0, j2, dpitch), r1 = row_ptr(g0, j2 + 1u, dpitch);
+        if (!kRagged) {
+            if (kCn == 1) {
+                stg_u16(r0, v00 | (v01 << 8));
+                stg_u16(r1, v10 | (v11 << 8));
+            } else {  // B0 G0 | R0 B1 | G1 R1
+                stg_u16(r0, v00); stg_u16(r0 + 2, (v00 >> 16) | (v01 << 8)); stg_u16(r0 + 4, v01 >> 8);
+                stg_u16(r1, v10); stg_u16(r1 + 2, (v10 >> 16) | (v11 << 8)); stg_u16(r1 + 4, v11 >> 8);
+            }
+        } else {
+            const bool in0 = u0 < g.out_w, in1 = u0 + 1 < g.out_w, second = j2 + 1u < (unsigned)nrows;
+#pragma unroll
+            for (int c = 0; c < kCn; ++c) {
+                if (in0) stg_u8(r0 + c, v00 >> (8 * c));
+                if (in1) stg_u8(r0 + kCn + c, v01 >> (8 * c));
+                if (in0 && second) stg_u8(r1 + c, v10 >> (8 * c));
+                if (in1 && second) stg_u8(r1 + kCn + c, v11 >> (8 * c));
+            }
+        }
+    }
+}
+
+template <int kCn, int kCtas>
+__global__ void __launch_bounds__(32 * kWarps, kCtas)
+warp_packed_tile_kernel(const Geom g, const FrameBatch b, const PieceRec* __restrict__ table,
+                        const __grid_constant__ PackedMaps maps)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int lane = threadIdx.x, w = threadIdx.y, tid = w * 32 + lane;
+    const int px = blockIdx.x, py = blockIdx.y, frame = blockIdx.z;
+    const int ph = g.piece_h;
+    const int npx = (int)gridDim.x, npy = (int)gridDim.y;
+    const PieceRec* rec = table + ((size_t)frame * npy + py) * npx + px;
+    const unsigned mbar = smem_u32(smem), mbar_rec = mbar + 8, rec_s = mbar + kRecOffset;
+    if (tid == 0) {
+        mbar_init(mbar, 1);
+        mbar_init(mbar_rec, 1);
+        mbar_expect_tx(mbar_rec, (unsigned)sizeof(PieceRec));
+        bulk_g2s(rec_s, rec, (unsigned)sizeof(PieceRec), mbar_rec);
+        if (frame + 1 < (int)gridDim.z) {
+            const char* nxt = reinterpret_cast<const char*>(rec + (size_t)npy * npx);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + 128));
+        }
+    }
+    __syncthreads();
+    mbar_wait_parked(mbar_rec, 0, 4000);
+    const PieceRec* rs = reinterpret_cast<const PieceRec*>(smem + kRecOffset);
+    const float4 rec_tail = *(reinterpret_cast<const float4*>(rs) + 12);  // base.x, base.y, flags, pad
+    const unsigned flags = __float_as_uint(rec_tail.z);
+    const int u_lo = px * kPieceW, v_base = py * ph;
+    const int rows = min(ph, g.out_h - v_base);
+    const uint8_t* const src = b.src + (size_t)frame * b.src_frame_stride;
+    uint8_t* const dst = b.dst + (size_t)frame * b.dst_frame_stride;
+
+    if (flags & kPieceOutside) {  // pure border
+        const unsigned border = kCn == 1 ? (g.border & 255u) : (g.border & 0xffffffu);
+        if (((reinterpret_cast<uintptr_t>(dst) | (uintptr_t)g.dst_pitch) & 3) == 0 && u_lo + kPieceW <= g.out_w) {
+            // 4-byte words: 32 kCn per row, the word at index j starts with channel (4 j) mod kCn = j mod 3
+            unsigned pw[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                unsigned v = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v |= ((border >> (8 * ((r + i) % kCn))) & 255u) << (8 * i);
+                pw[r] = v;
+            }
+            for (int r = w; r < rows; r += kWarps) {
+                unsigned* row = reinterpret_cast<unsigned*>(dst + (size_t)(v_base + r) * g.dst_pitch + (size_t)u_lo * kCn);
+#pragma unroll
+                for (int k = 0; k < kCn; ++k) row[lane + 32 * k] = pw[kCn == 1 ? 0 : (lane + 32 * k) % 3];
+            }
+            return;
+        }
+        for (int r = w; r < rows; r += kWarps) {
+            uint8_t* row = dst + (size_t)(v_base + r) * g.dst_pitch;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) store_px_checked<kCn>(row, u_lo + lane + 32 * k, g.out_w, border);
+        }
+        return;
+    }
+
+    // ---- the tile of this piece's source box ---------------------------------------------------------
+    const int4 rawbox = *(reinterpret_cast<const int4*>(rs) + 13);  // PieceBox: x0 x1 | y0 y1 | cx0 cx1 | cy0 cy1
+    PieceBox box;
+    box.x0 = (int16_t)(rawbox.x & 0xffff); box.x1 = (int16_t)(rawbox.x >> 16);
+    box.y0 = (int16_t)(rawbox.y & 0xffff); box.y1 = (int16_t)(rawbox.y >> 16);
+    int bx0 = 0, pl = 0, nrows = 0;
+    const bool staged = (flags & kPiecePoly) && maps.enabled && packed_stage<kCn>(box, maps.tile_cap, bx0, pl, nrows);
+
+    if (!staged) {
+        // per pixel from global memory, four columns per lane, warp w walks rows [w PH/4, (w + 1) PH/4)
+        const int rpw = ph / kWarps, dv0 = w * rpw, my_rows = max(0, min(rpw, rows - dv0));
+        const int u0 = u_lo + 4 * lane;
+        if (my_rows <= 0) return;
+        ColPoly cp;
+        Rot R;
+        if (flags & kPiecePoly) derive(rec, lane, cp);
+        else R = load_rot(b, frame);
+        for (int dv = dv0; dv < dv0 + my_rows; dv += 2) {
+            float2 m[2][4];
+            if (flags & kPiecePoly) {
+                row_coords(cp, row_t(g, dv), m[0]);
+                row_coords(cp, row_t(g, dv + 1), m[1]);
+            } else {
+                exact_rows(g, R, u_lo, u0, v_base + dv, m);
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                if (dv + r >= dv0 + my_rows) break;
+                uint8_t* row = dst + (size_t)(v_base + dv + r) * g.dst_pitch;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    store_px_checked<kCn>(row, u0 + i, g.out_w, sample_checked<kCn>(g, src, m[r][i].x, m[r][i].y));
+            }
+        }
+        return;
+    }
+
+    uint8_t* tile = smem + kTileOffset;
+    if (tid == 0) {
+        mbar_expect_tx(mbar, (unsigned)(pl * nrows));
+        const int mi = (pl - kPackedMinPitch) / kPackedPitchStep;
+        const CUtensorMap *map16 = &maps.m16[mi], *map4 = &maps.m4[mi];
+        const unsigned t0 = smem_u32(tile);
+        const int z = frame + b.tma_frame0;
+        int k = 0;
+        for (; k + 16 <= nrows; k += 16) tma_load_3d(t0 + (unsigned)(k * pl), map16, bx0 >> 3, box.y0 + k, z, mbar);
+        for (; k < nrows; k += 4) tma_load_3d(t0 + (unsigned)(k * pl), map4, bx0 >> 3, box.y0 + k, z, mbar);
+    }
+
+    // ---- this warp's quadrant; every lane collapses the polynomial onto its two columns ---------------
+    const int wx = w & 1, wy = w >> 1, hrows = ph >> 1;
+    const int col0 = 64 * wx + 2 * lane;
+    ColPoly2 cp;
+    derive2(rs, col0, cp);
+    cp.base = make_float2(rec_tail.x, rec_tail.y);
+
+    mbar_wait_parked(mbar, 0, 4000);  // the tile has landed
+
+    if (!(flags & kPieceInterior)) {  // straddles the frame border: paint the outside cells
+        fill_border_packed<kCn>(tile, pl, nrows, box.y0, g.src_h, bx0, g.src_w * kCn,
+                                kCn == 1 ? (g.border & 255u) : (g.border & 0xffffffu), lane, w);
+        __syncthreads();
+    }
+
+    const int dv0 = wy * hrows;
+    const int my_rows = max(0, min(hrows, rows - dv0));
+    const unsigned upl = (unsigned)pl;
+    // tap address = (iy - y0) pl + kCn (ix - x0) + (kCn x0 - bx0) + tile; x carries kCn * 2^30 out of the floor trick
+    // 0 at run time, unknown to ptxas (the zero pad of the record's stage): keeps the tap-row constants in uniform registers
+    const unsigned never = (unsigned)(*(reinterpret_cast<const int4*>(rs) + 14)).w >> 31;
+    const unsigned vnever = threadIdx.x >> 5;
+    const FloorConst fc = floor_const(-(int)box.x0, -(int)box.y0,
+                                      smem_u32(tile) + (unsigned)(kCn * (int)box.x0 - bx0) - (unsigned)kCn * 0x40000000u, upl,
+                                      __uint_as_float(0x42000000u | vnever), never);
+    const int u0 = u_lo + col0;
+    const bool pair_ok = ((reinterpret_cast<uintptr_t>(dst) | (uintptr_t)g.dst_pitch) & 1) == 0 &&
+                         u_lo + kPieceW <= g.out_w && (rows & 1) == 0 && (hrows & 1) == 0;
+    const TileBounds tb = {smem_u32(tile), smem_u32(tile) + (unsigned)(nrows * pl), 0u, 0u};
+    uint8_t* const out0 = dst + (size_t)(v_base + dv0) * g.dst_pitch + (size_t)u0 * kCn;
+    if (pair_ok) rows_packed<kCn, false>(g, cp, fc, upl, dv0, my_rows, out0, u0, tb);
+    else rows_packed<kCn, true>(g, cp, fc, upl, dv0, my_rows, out0, u0, tb);
+}
+
+template <int kCn, int kCtas>
+cudaError_t configure_packed()
+{
+    cudaError_t e = cudaFuncSetAttribute(warp_packed_tile_kernel<kCn, kCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kTileOffset + kTileCapMax);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(warp_packed_tile_kernel<kCn, kCtas>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    return e;
+}
+
+}  // namespace
+
+int packed_tile_need_bytes(const PieceRec& rec, int channels)
+{
+    if (!(rec.flags & kPiecePoly) || (rec.flags & kPieceOutside)) return 0;
+    int bx0, pl, nrows;
+    const bool ok = channels == 1 ? packed_stage<1>(rec.box, 0x7fffffff, bx0, pl, nrows)
+                                  : packed_stage<3>(rec.box, 0x7fffffff, bx0, pl, nrows);
+    return ok ? pl * nrows : 0x7fffffff;
+}
+
+int packed_tile_smem_bytes(int tile_cap) { return kTileOffset + tile_cap; }
+
+cudaError_t launch_warp_packed_tile(const Geom& g, const FrameBatch& b, const PieceRec* table, const PackedMaps& maps,
+                                    int channels, cudaStream_t st)
+{
+    static std::atomic<bool> configured[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const bool tracked = dev >= 0 && dev < 64;
+    if (!tracked || !configured[dev].load(std::memory_order_acquire)) {
+        cudaError_t e = configure_packed<1, 7>();
+        if (e == cudaSuccess) e = configure_packed<1, 5>();
+        if (e == cudaSuccess) e = configure_packed<3, 7>();
+        if (e == cudaSuccess) e = configure_packed<3, 5>();
+        if (e != cudaSuccess) return e;
+        if (tracked) configured[dev].store(true, std::memory_order_release);
+    }
+    dim3 block(32, kWarps);
+    dim3 grid(pieces_x(g.out_w), pieces_y(g.out_h, g.piece_h), b.n_frames);
+    const int smem = kTileOffset + maps.tile_cap;
+    const bool seven = maps.tile_cap <= tile_cap_for_ctas(7, kTileOffset);  // else the 96-register build for 5 CTAs or fewer
+    if (channels == 1) {
+        if (seven) warp_packed_tile_kernel<1, 7><<<grid, block, smem, st>>>(g, b, table, maps);
+        else warp_packed_tile_kernel<1, 5><<<grid, block, smem, st>>>(g, b, table, maps);
+    } else {
+        if (seven) warp_packed_tile_kernel<3, 7><<<grid, block, smem, st>>>(g, b, table, maps);
+        else warp_packed_tile_kernel<3, 5><<<grid, block, smem, st>>>(g, b, table, maps);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace vaw

@@ -31,7 +31,6 @@
 #include <algorithm>
 #include <cstdlib>
 #include <atomic>
-#include <type_traits>
 #include "vaw_internal.h"
 #include "vaw_poly.cuh"
 #include "vaw_tile.cuh"
@@ -63,73 +62,7 @@ static_assert(kWarps == 2 || kWarps == 4, "two warps side by side, one or two de
 //   - per row pair a lane makes 2 x 2 luma samples and the one chroma sample of that quad; a warp
 //     store writes 64 contiguous bytes, the LDS of a warp stay within one 128-byte window per row
 //     exactly as with the round-1 pair mapping (2 columns per lane).
-constexpr int kQuadRecOffset = 16, kQuadTileOffset = 640;  // [tile mbarrier | record mbarrier | record (240 B) | ... | tile (TMA: 128-byte aligned)]
-// the persistent kernel's bookkeeping in the same 640 bytes: [tile mbarrier | 2 record mbarriers | pad | 2 piece slots (int4) | 2 records]
-constexpr int kPersistSlotOffset = 32, kPersistRecOffset = 64, kPersistRecStride = 240;
-static_assert(kPersistRecOffset + 2 * kPersistRecStride <= kQuadTileOffset, "bookkeeping fits in front of the tile");
-
-struct ColPoly2 {
-    float2 a[2][kNv];  // [column][power of t]
-    float2 base;
-};
-
-// Collapse the piece polynomial onto the lane's two columns: per power of t one Horner chain in s per
-// column -- the operation order of collapse_column(), so the coefficients equal derive()'s bit for bit
-// (vaw_dump_coords runs derive()).  Coefficients are read per power of t (6 x 8-byte broadcast loads
-// from L1) so that at most 12 of the record's 48 coefficient registers are live at a time.
-__device__ __forceinline__ void derive2(const PieceRec* __restrict__ rec, int col0, ColPoly2& cp)
-{
-    const float2* c2 = reinterpret_cast<const float2*>(rec);  // c[i][k] at index i * kNv + k
-    const float2 s0 = pair(((float)col0 - 63.5f) * 0.015625f), s1 = pair(((float)(col0 + 1) - 63.5f) * 0.015625f);
-#pragma unroll
-    for (int k = 0; k < kNv; ++k) {
-        float2 ci[kNu];
-#pragma unroll
-        for (int i = 0; i < kNu; ++i) ci[i] = c2[i * kNv + k];
-        float2 a0 = ci[kDegU], a1 = ci[kDegU];
-#pragma unroll
-        for (int i = kDegU - 1; i >= 0; --i) {
-            a0 = __ffma2_rn(a0, s0, ci[i]);
-            a1 = __ffma2_rn(a1, s1, ci[i]);
-        }
-        cp.a[0][k] = a0;
-        cp.a[1][k] = a1;
-    }
-}
-
-__device__ __forceinline__ float2 col_coord(const float2 (&a)[kNv], float2 base, float2 tt)
-{
-    float2 p = __ffma2_rn(a[3], tt, a[2]);
-    p = __ffma2_rn(p, tt, a[1]);
-    p = __ffma2_rn(p, tt, a[0]);
-    return __fadd2_rn(base, p);  // the map value: rounded once to fp32
-}
-
-// base + index * pitch as ONE 64-bit multiply-add (IMAD.WIDE): the compiler's strength-reduced running
-// pointers cost four instructions per store here (add, add-with-carry and two moves to re-pair registers).
-__device__ __forceinline__ unsigned long long row_ptr(unsigned long long base, unsigned index, unsigned pitch)
-{
-    unsigned long long a;
-    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(a) : "r"(index), "r"(pitch), "l"(base));
-    return a;
-}
-__device__ __forceinline__ void stg_u16(unsigned long long gaddr, unsigned v)
-{
-    asm volatile("st.global.u16 [%0], %1;" ::"l"(gaddr), "h"((unsigned short)v) : "memory");
-}
-__device__ __forceinline__ void stg_u8(unsigned long long gaddr, unsigned v)
-{
-    asm volatile("st.global.u8 [%0], %1;" ::"l"(gaddr), "h"((unsigned short)(v & 255u)) : "memory");
-}
-// A zero the compiler cannot see through: a loop counter started from it stays in a vector register, so
-// that counter * pitch + pointer is one IMAD.WIDE per store instead of uniform-datapath arithmetic plus
-// a two-instruction 64-bit vector add.
-__device__ __forceinline__ unsigned opaque_zero()
-{
-    unsigned z;
-    asm volatile("mov.u32 %0, 0;" : "=r"(z));
-    return z;
-}
+constexpr int kQuadRecOffset = 16, kQuadTileOffset = 256;  // [tile mbarrier | record mbarrier | record (240 B) | tile (TMA: 128-byte aligned)]
 
 // nrows (even) rows starting at piece row dv0 for the lane's two columns; taps from the staged tile.
 // py / pc: the lane's column pair in the first luma row / chroma row of the band.
@@ -213,8 +146,9 @@ __device__ __forceinline__ void rows_quad(const Geom& g, const ColPoly2& cp, con
     }
 }
 
-// One piece, from its record in shared memory (`rs`) to the stores: the body shared by the one-piece-per-CTA kernel
-// and the persistent kernel.  `rec` = the same record in the table (the gather fallbacks read it from there);
+// One piece, from its record in shared memory (`rs`) to the stores.  (A separate function since round 2's persistent-
+// kernel experiment: resident CTAs pulling pieces from an atomic queue with the next record prefetched measured
+// 0.736 ms against 0.660 ms -- more instructions, not fewer, and longer tile waits)  `rec` = the same record in the table (the gather fallbacks read it from there);
 // `tile_parity` = phase of the tile mbarrier (smem + 0) this piece's loads complete.  Returns whether the piece was staged
 // (i.e. whether that phase was consumed).
 __device__ __forceinline__ bool quad_piece(const Geom& g, const FrameBatch& b, const PieceRec* __restrict__ rec,
@@ -364,8 +298,8 @@ __device__ __forceinline__ bool quad_piece(const Geom& g, const FrameBatch& b, c
 
     const int dv0 = wy * hrows;
     const int my_rows = max(0, min(hrows, rows - dv0));  // 0 for a warp below the frame's last row: its row loop does not run
-    // (no early return here: inside the persistent kernel's piece loop a branch on a per-warp value puts everything
-    // behind it into a region ptxas treats as divergent, and the tap-row constants below then lose their uniform registers)
+    // (no early return here: a branch on a per-warp value in front of the tap-row constants below can cost them their
+    // uniform registers -- everything behind it is divergent as far as ptxas can tell)
     // tap address = (iy - y0) * pl + (ix - x0) + tile, with the >>5 bias of the magic constant folded in
 #if VAW_SHFL_UNIFORM
     const unsigned upl = __shfl_sync(0xffffffffu, (unsigned)pl, 0);  // warp-uniform as far as ptxas is concerned: a uniform register
@@ -444,119 +378,6 @@ warp_nv12_quad_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
     quad_piece(g, b, rec, rs, maps, smem, px, py, frame, 0u, lane, w, tid);
 }
 
-// Persistent form of the quadrant kernel: kCtas CTAs per SM stay resident and pull pieces from a queue in table order
-// (an atomic counter in the pad word of the table's first record, which the builder zeroes), kPersistChunk pieces per ticket.
-// What it removes from the one-piece-per-CTA kernel: the CTA launch between two pieces of a shared-memory slot, the
-// entry code of four warps per piece, and the wait for the record -- the record of the NEXT piece is copied into the
-// second record buffer while the current piece is sampled.  The tile itself cannot be fetched ahead (one tile per CTA
-// is what shared memory holds at 7 CTAs per SM).
-#ifndef VAW_PERSIST_ONE_COPY
-#define VAW_PERSIST_ONE_COPY 1
-#endif
-#ifndef VAW_PERSIST_CHUNK
-#define VAW_PERSIST_CHUNK 4
-#endif
-constexpr int kPersistChunk = VAW_PERSIST_CHUNK;
-
-template <int kCtas>
-__global__ void __launch_bounds__(32 * kWarps, kCtas)
-warp_nv12_quad_persist_kernel(const Geom g, const FrameBatch b, const PieceRec* __restrict__ table,
-                              const __grid_constant__ TileMaps maps, const int npx, const int npy)
-{
-    extern __shared__ __align__(128) uint8_t smem[];
-    const int lane = threadIdx.x, w = threadIdx.y, tid = w * 32 + lane;
-    const unsigned sbase = smem_u32(smem);
-    const unsigned mbar = sbase, mbar_rec0 = sbase + 8;
-    const unsigned per_frame = (unsigned)(npx * npy), total = per_frame * (unsigned)b.n_frames;
-    unsigned* const queue = const_cast<unsigned*>(&table[0].pad);
-    int4* const slots = reinterpret_cast<int4*>(smem + kPersistSlotOffset);  // written by thread 0, read after the next CTA barrier
-
-    // thread 0's private queue state: pieces [cur, end) of the ticket in hand and the first piece of the next ticket,
-    // whose atomic was issued when the ticket in hand was taken up -- kPersistChunk pieces before its result is needed, so
-    // the round trip never sits in front of a tile load.  (One piece per ticket serialises the whole launch on the
-    // counter: 130 k same-address atomics took 1.04 ms, 8 ns each.)
-    unsigned cur = 0, end = 0, ahead = 0xffffffffu;
-    auto take_ticket = [&]() -> unsigned { return atomicAdd(queue, (unsigned)kPersistChunk); };
-    auto next_piece = [&]() -> unsigned {  // >= total: the queue is drained
-        if (cur == end) {
-            cur = ahead;
-            end = cur < total ? min(cur + (unsigned)kPersistChunk, total) : cur;
-            if (cur >= total) return 0xffffffffu;
-            ahead = take_ticket();
-        }
-        return cur++;
-    };
-    auto post = [&](unsigned q, int buf) {  // thread 0 only: announce piece q in slot `buf` and start its record copy
-        if (q >= total) {
-            slots[buf] = make_int4(-1, 0, 0, 0);
-            return;
-        }
-        const unsigned frame = q / per_frame, r = q - frame * per_frame;
-        const unsigned py = r / (unsigned)npx, px = r - py * (unsigned)npx;
-        slots[buf] = make_int4((int)q, (int)px, (int)py, (int)frame);
-        const unsigned mb = mbar_rec0 + 8u * (unsigned)buf;
-        mbar_expect_tx(mb, (unsigned)sizeof(PieceRec));
-        bulk_g2s(sbase + kPersistRecOffset + (unsigned)(buf * kPersistRecStride), table + q, (unsigned)sizeof(PieceRec), mb);
-        if (frame + 1 < (unsigned)b.n_frames) {  // the same piece of the next frame: into L2 (see the one-piece kernel)
-            const char* nxt = reinterpret_cast<const char*>(table + q + per_frame);
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + 128));
-        }
-    };
-
-    if (tid == 0) {
-        mbar_init(mbar, 1);
-        mbar_init(mbar_rec0, 1);
-        mbar_init(mbar_rec0 + 8, 1);
-        ahead = take_ticket();
-        post(next_piece(), 0);
-    }
-    __syncthreads();
-
-    unsigned tile_uses = 0;  // staged pieces so far: phase of the tile mbarrier
-    // One piece from record buffer kBuf.  The buffer index is a compile-time constant (the loop below is unrolled by
-    // hand over the two buffers): with `it & 1` ptxas no longer proves the record's address -- and with it the tile
-    // pitch and the tap-row constants loaded from it -- warp-uniform, and the row loop grows from 271 to 296
-    // instructions per two row pairs.
-#if VAW_PERSIST_ONE_COPY
-    auto step = [&](int kBuf, unsigned it) -> bool {
-#else
-    auto step = [&](auto buf_c, unsigned it) -> bool {
-        constexpr int kBuf = decltype(buf_c)::value;
-#endif
-        const int4 slot = slots[kBuf];
-        if (__any_sync(0xffffffffu, slot.x < 0)) return false;  // queue drained (block-uniform; the vote says so to ptxas)
-        if (tid == 0) post(next_piece(), kBuf ^ 1);
-        mbar_wait_parked(mbar_rec0 + 8u * (unsigned)kBuf, (it >> 1) & 1u, 4000);
-        const PieceRec* rs = reinterpret_cast<const PieceRec*>(smem + kPersistRecOffset + kBuf * kPersistRecStride);
-        // block-uniform mirror of quad_piece()'s `staged` decision (its own return value is per-thread as far as ptxas
-        // can tell, and a loop-carried per-thread phase costs the row loop its uniform registers)
-        const unsigned fl = rs->flags;
-        const bool uses_tile = (fl & kPiecePoly) && !(fl & kPieceOutside) && maps.enabled && rs->stage.pl != 0 &&
-                               (int)rs->stage.pl * ((int)rs->stage.nrows + (int)rs->stage.cnrows) <= maps.tile_cap &&
-                               !(b.skip_interior && (fl & kPieceInterior));
-        quad_piece(g, b, table + slot.x, rs, maps, smem, slot.y, slot.z, slot.w, tile_uses & 1u, lane, w, tid);
-        tile_uses += uses_tile ? 1u : 0u;
-        // every warp is done with the tile, the record and the slot; generic-proxy accesses to the tile (taps, border
-        // fill) are ordered before the next piece's asynchronous tile writes
-#ifndef VAW_PERSIST_NO_FENCE  // (analysis only)
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-#endif
-        __syncthreads();
-        return true;
-    };
-#if VAW_PERSIST_ONE_COPY
-#pragma unroll 1
-    for (unsigned it = 0;; ++it)
-        if (!step((int)(it & 1u), it)) break;
-#else
-    for (unsigned it = 0;; it += 2) {
-        if (!step(std::integral_constant<int, 0>{}, it)) break;
-        if (!step(std::integral_constant<int, 1>{}, it + 1)) break;
-    }
-#endif
-}
-
 long long tile_oob_count()
 {
 #ifdef VAW_BOUNDS_CHECK
@@ -593,15 +414,6 @@ static cudaError_t configure_quad()
         e = cudaFuncSetAttribute(warp_nv12_quad_kernel<kCtas>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     return e;
 }
-template <int kCtas>
-static cudaError_t configure_persist()
-{
-    cudaError_t e = cudaFuncSetAttribute(warp_nv12_quad_persist_kernel<kCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         tile_smem_bytes(kTileCapMax));
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(warp_nv12_quad_persist_kernel<kCtas>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    return e;
-}
 cudaError_t launch_warp_nv12_tile(const Geom& g, const FrameBatch& b, const PieceRec* table, const TileMaps& maps,
                                   cudaStream_t st)
 {
@@ -620,31 +432,6 @@ cudaError_t launch_warp_nv12_tile(const Geom& g, const FrameBatch& b, const Piec
     }
     dim3 block(32, kWarps);
     dim3 grid(pieces_x(g.out_w), pieces_y(g.out_h, g.piece_h), b.n_frames);
-    static const int persist_mode = [] { const char* e = getenv("VAW_PERSIST"); return e ? atoi(e) : 0; }();
-    if (persist_mode) {
-        static std::atomic<int> sms[64];
-        int n_sm = tracked ? sms[dev].load(std::memory_order_acquire) : 0;
-        if (n_sm == 0) {
-            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-            cudaError_t e = configure_persist<8>();
-            if (e == cudaSuccess) e = configure_persist<7>();
-            if (e == cudaSuccess) e = configure_persist<6>();
-            if (e != cudaSuccess) return e;
-            if (tracked) sms[dev].store(n_sm, std::memory_order_release);
-        }
-        const int smem = tile_smem_bytes(maps.tile_cap);
-        const int npx = (int)grid.x, npy = (int)grid.y;
-        const long long pieces = (long long)npx * npy * b.n_frames;
-        auto slots = [&](int ctas) { return (unsigned)std::min<long long>((long long)n_sm * ctas, (pieces + kPersistChunk - 1) / kPersistChunk); };
-        if (maps.tile_cap <= tile_cap_for_ctas(8, kQuadTileOffset)) warp_nv12_quad_persist_kernel<8><<<slots(8), block, smem, st>>>(g, b, table, maps, npx, npy);
-        else if (maps.tile_cap <= tile_cap_for_ctas(7, kQuadTileOffset)) warp_nv12_quad_persist_kernel<7><<<slots(7), block, smem, st>>>(g, b, table, maps, npx, npy);
-        else {
-            int ctas = 6;
-            while (ctas > 1 && maps.tile_cap > tile_cap_for_ctas(ctas, kQuadTileOffset)) --ctas;
-            warp_nv12_quad_persist_kernel<6><<<slots(ctas), block, smem, st>>>(g, b, table, maps, npx, npy);
-        }
-        return cudaGetLastError();
-    }
     // the instantiation whose register budget matches the CTAs the tile capacity lets share an SM
     const int smem = tile_smem_bytes(maps.tile_cap);
     if (maps.tile_cap <= tile_cap_for_ctas(8, kQuadTileOffset)) warp_nv12_quad_kernel<8><<<grid, block, smem, st>>>(g, b, table, maps);

@@ -166,6 +166,70 @@ __device__ __forceinline__ unsigned chroma_tile3(const FloorConst& fc, unsigned 
                     __float_as_uint(s.y) & 31u);
 }
 
+// ---- pieces shared by the quadrant kernels (vaw_tile.cu: NV12; vaw_packed_tile.cu: GRAY8 / BGR24) ----------------------
+struct ColPoly2 {
+    float2 a[2][kNv];  // [column][power of t]
+    float2 base;
+};
+
+// Collapse the piece polynomial onto the lane's two columns: per power of t one Horner chain in s per
+// column -- the operation order of collapse_column(), so the coefficients equal derive()'s bit for bit
+// (vaw_dump_coords runs derive()).  Coefficients are read per power of t (6 x 8-byte broadcast loads
+// from L1) so that at most 12 of the record's 48 coefficient registers are live at a time.
+__device__ __forceinline__ void derive2(const PieceRec* __restrict__ rec, int col0, ColPoly2& cp)
+{
+    const float2* c2 = reinterpret_cast<const float2*>(rec);  // c[i][k] at index i * kNv + k
+    const float2 s0 = pair(((float)col0 - 63.5f) * 0.015625f), s1 = pair(((float)(col0 + 1) - 63.5f) * 0.015625f);
+#pragma unroll
+    for (int k = 0; k < kNv; ++k) {
+        float2 ci[kNu];
+#pragma unroll
+        for (int i = 0; i < kNu; ++i) ci[i] = c2[i * kNv + k];
+        float2 a0 = ci[kDegU], a1 = ci[kDegU];
+#pragma unroll
+        for (int i = kDegU - 1; i >= 0; --i) {
+            a0 = __ffma2_rn(a0, s0, ci[i]);
+            a1 = __ffma2_rn(a1, s1, ci[i]);
+        }
+        cp.a[0][k] = a0;
+        cp.a[1][k] = a1;
+    }
+}
+
+__device__ __forceinline__ float2 col_coord(const float2 (&a)[kNv], float2 base, float2 tt)
+{
+    float2 p = __ffma2_rn(a[3], tt, a[2]);
+    p = __ffma2_rn(p, tt, a[1]);
+    p = __ffma2_rn(p, tt, a[0]);
+    return __fadd2_rn(base, p);  // the map value: rounded once to fp32
+}
+
+// base + index * pitch as ONE 64-bit multiply-add (IMAD.WIDE): the compiler's strength-reduced running
+// pointers cost four instructions per store here (add, add-with-carry and two moves to re-pair registers).
+__device__ __forceinline__ unsigned long long row_ptr(unsigned long long base, unsigned index, unsigned pitch)
+{
+    unsigned long long a;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(a) : "r"(index), "r"(pitch), "l"(base));
+    return a;
+}
+__device__ __forceinline__ void stg_u16(unsigned long long gaddr, unsigned v)
+{
+    asm volatile("st.global.u16 [%0], %1;" ::"l"(gaddr), "h"((unsigned short)v) : "memory");
+}
+__device__ __forceinline__ void stg_u8(unsigned long long gaddr, unsigned v)
+{
+    asm volatile("st.global.u8 [%0], %1;" ::"l"(gaddr), "h"((unsigned short)(v & 255u)) : "memory");
+}
+// A zero the compiler cannot see through: a loop counter started from it stays in a vector register, so
+// that counter * pitch + pointer is one IMAD.WIDE per store instead of uniform-datapath arithmetic plus
+// a two-instruction 64-bit vector add.
+__device__ __forceinline__ unsigned opaque_zero()
+{
+    unsigned z;
+    asm volatile("mov.u32 %0, 0;" : "=r"(z));
+    return z;
+}
+
 // Pair lane mapping of the texture variant (vaw_tex.cu): lane l owns luma columns 2l, 2l+1 and 64+2l, 64+2l+1
 // of the piece (slot j -> column 2l + (j & 1) + 64 (j >> 1)); stores are 2 bytes per lane.
 __device__ __forceinline__ int pair_column(int lane, int j) { return 2 * lane + (j & 1) + 64 * (j >> 1); }
