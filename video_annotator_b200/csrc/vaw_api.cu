@@ -748,23 +748,30 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
 #define VAW_PH_RULE 5e-5  // = the builder's accuracy certificate; 2e-5 halved C1's pieces for nothing (204 k -> 247 k frames/s at 32 rows, same measured errors)
 #endif
         while (ph > 8 && 2.4e-3 * fin * std::pow(ph / fout, 4.0) > VAW_PH_RULE) ph >>= 1;
-        if (p.format == VAW_FORMAT_BGR24 && ph > 16) ph = 16;  // three bytes per source pixel: a 32-row piece needs ~60 KB of tile
-        g.piece_h = ph;
-        g.t_off = 0.5f * (float)(ph - 1);
-        g.t_scale = 2.0f / (float)ph;
+        if (const char* env = getenv("VAW_EXPERIMENT_PH")) {  // analysis only: force the rows per piece (8, 16 or 32)
+            const int v = atoi(env);
+            if (v == 8 || v == 16 || v == 32) ph = v;
+        }
         vaw::GeomD& d = ctx->gd;
+        auto set_piece_rows = [&](int rows) {
+            g.piece_h = rows;
+            g.t_off = 0.5f * (float)(rows - 1);
+            g.t_scale = 2.0f / (float)rows;
+            d.piece_h = rows;
+            make_basis(ctx->basis, rows);
+            ctx->pieces_per_frame = (size_t)vaw::pieces_x(g.out_w) * vaw::pieces_y(g.out_h, rows);
+        };
         d.scx = g.scx; d.scy = g.scy; d.sfx = g.sfx; d.sfy = g.sfy;  // the fp32 scalars, widened
         d.mcx = g.mcx; d.mcy = g.mcy; d.mfx = g.mfx; d.mfy = g.mfy;
         d.inv_mfx = 1.0 / d.mfx; d.inv_mfy = 1.0 / d.mfy;
         for (int i = 0; i < 4; ++i) d.kd[i] = g.kd[i];  // the fp32 coefficients, widened
         d.has_dist = g.has_dist;
         d.src_w = g.src_w; d.src_h = g.src_h; d.out_w = g.out_w; d.out_h = g.out_h;
-        d.piece_h = ph;
         d.projection = p.projection;
-        make_basis(ctx->basis, ph);
-        ctx->pieces_per_frame = (size_t)vaw::pieces_x(g.out_w) * vaw::pieces_y(g.out_h, ph);
+        set_piece_rows(ph);
         e = cudaEventCreateWithFlags(&ctx->table_free, cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaMalloc(&ctx->dump_table, ctx->pieces_per_frame * sizeof(vaw::PieceRec));
+        // (room for the same frame cut into 16-row pieces: BGR24 may fall back to them below)
+        if (e == cudaSuccess) e = cudaMalloc(&ctx->dump_table, 2 * ctx->pieces_per_frame * sizeof(vaw::PieceRec));
         if (e == cudaSuccess) {
             int lo = 0, hi = 0;  // "greatest" priority is the numerically lowest
             e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
@@ -784,10 +791,11 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
             // size the per-CTA tile from the source boxes of the unrotated geometry, +20 % for the
             // tilt a few degrees of rotation add; more shared memory per CTA = fewer resident CTAs
             const float eye[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-            e = vaw::launch_build_pieces(ctx->gd, ctx->basis, nullptr, eye, 1, ctx->dump_table, nullptr);
-            std::string host(ctx->pieces_per_frame * sizeof(vaw::PieceRec), '\0');
-            if (e == cudaSuccess) e = cudaMemcpy(&host[0], ctx->dump_table, host.size(), cudaMemcpyDeviceToHost);
-            if (e == cudaSuccess) {
+            for (int attempt = 0; attempt < 2 && e == cudaSuccess; ++attempt) {
+                e = vaw::launch_build_pieces(ctx->gd, ctx->basis, nullptr, eye, 1, ctx->dump_table, nullptr);
+                std::string host(ctx->pieces_per_frame * sizeof(vaw::PieceRec), '\0');
+                if (e == cudaSuccess) e = cudaMemcpy(&host[0], ctx->dump_table, host.size(), cudaMemcpyDeviceToHost);
+                if (e != cudaSuccess) break;
                 const vaw::PieceRec* rec = reinterpret_cast<const vaw::PieceRec*>(host.data());
                 long long need = 0;
                 for (size_t i = 0; i < ctx->pieces_per_frame; ++i) {
@@ -795,7 +803,14 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
                     if (nb != 0x7fffffff && nb > need) need = nb;
                 }
                 ctx->tile_need = need;
-                choose_tile_cap(ctx);
+                const int ctas = choose_tile_cap(ctx);
+                // BGR24: three bytes per source pixel.  32-row pieces win while four CTAs still share an SM (C3: 52 KB
+                // tiles, 0.758 ms per 32 frames against 0.777 ms with 16-row pieces at six CTAs); larger boxes (C5: 120 KB)
+                // are cut into 16-row pieces
+                if (attempt == 0 && p.format == VAW_FORMAT_BGR24 && g.piece_h > 16 && ctas < 4 && !getenv("VAW_EXPERIMENT_PH"))
+                    set_piece_rows(16);
+                else
+                    break;
             }
         }
         if (e != cudaSuccess) {
@@ -1199,7 +1214,8 @@ int vaw_piece_stats(vaw_ctx* ctx, const double rotation[9], uint32_t counts[8], 
         if (rec[i].flags & vaw::kPiecePoly) counts[1]++;
         if (rec[i].flags & vaw::kPieceInterior) counts[2]++;
         if (rec[i].flags & vaw::kPieceOutside) counts[3]++;
-        const int nb = vaw::tile_need_bytes(rec[i]);
+        const bool packed = ctx->p.format == VAW_FORMAT_BGR24 || ctx->p.format == VAW_FORMAT_GRAY8;
+        const int nb = packed ? vaw::packed_tile_need_bytes(rec[i], ctx->channels) : vaw::tile_need_bytes(rec[i]);
         if (nb > 0 && (nb > ctx->tile_cap)) counts[6]++;
         if (nb != 0x7fffffff && (uint32_t)nb > counts[4]) counts[4] = (uint32_t)nb;
     }
@@ -1248,7 +1264,8 @@ int vaw_piece_tiles(vaw_ctx* ctx, const double rotation[9], uint32_t* out, int c
     const vaw::PieceRec* rec = reinterpret_cast<const vaw::PieceRec*>(host.data());
     for (size_t i = 0; i < ctx->pieces_per_frame; ++i) {
         out[4 * i + 0] = rec[i].flags;
-        out[4 * i + 1] = (uint32_t)vaw::tile_need_bytes(rec[i]);
+        const bool packed = ctx->p.format == VAW_FORMAT_BGR24 || ctx->p.format == VAW_FORMAT_GRAY8;
+        out[4 * i + 1] = (uint32_t)(packed ? vaw::packed_tile_need_bytes(rec[i], ctx->channels) : vaw::tile_need_bytes(rec[i]));
         out[4 * i + 2] = rec[i].stage.pl;
         out[4 * i + 3] = (uint32_t)rec[i].stage.nrows | ((uint32_t)rec[i].stage.cnrows << 16);
     }

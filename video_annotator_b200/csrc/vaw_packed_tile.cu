@@ -42,7 +42,8 @@ __host__ __device__ inline bool packed_stage(const PieceBox& b, int tile_cap, in
     pl = (wb + 63) & ~63;
     if (pl < kPackedMinPitch) pl = kPackedMinPitch;
     nrows = ((int)b.y1 - (int)b.y0 + 4) & ~3;
-    return pl <= kPackedMaxPitch && nrows > 0 && nrows < 4096 && pl * nrows <= tile_cap;
+    // (+16: the BGR sampler reads whole words, up to 6 bytes past the last tap of the last row)
+    return pl <= kPackedMaxPitch && nrows > 0 && nrows < 4096 && pl * nrows + 16 <= tile_cap;
 }
 
 template <int kCn>
@@ -88,6 +89,43 @@ __device__ __forceinline__ unsigned packed_tile_sample(const FloorConst& fc, uns
         out |= v << (8 * c);
     }
     return out;
+}
+
+// The same for BGR with HALF the shared-memory instructions (ncu on the byte-load form: l1tex 92 % busy, mio_throttle the
+// top stall, issue slots 45 % busy -- twelve LDS.U8 per sample, ~3 wavefronts each at 6 x magnification bytes between
+// lanes).  The six bytes B0 G0 R0 B1 G1 R1 of a tap row come in as three aligned words and two funnel shifts; the two
+// rows are widened to 16-bit halves (three PRMT each), blended vertically as halves (six IMAD), regrouped per channel
+// (three PRMT) and blended horizontally with the rounding constant by one IDP.2A per channel.  Same integers:
+// (t00 wy + t10 ay) wx + (t01 wy + t11 ay) ax + 512 is the exact four-weight sum in either order.
+__device__ __forceinline__ unsigned lds_u32(unsigned addr, unsigned row)
+{
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr + row));
+    return v;
+}
+__device__ __forceinline__ unsigned bgr_tile_sample(const FloorConst& fc, unsigned pl, float2 m, const TileBounds& tb)
+{
+    const float2 s = __ffma2_rn(m, pair(fc.scale), pair(kMagic));
+    const float2 fl = __ffma2_rd(s, pair(kFloorScale), fc.c);
+    const unsigned a0 = imad_u32(__float_as_uint(fl.x), 3u, __float_as_uint(fl.y) * pl) + fc.row0;  // byte address of B0, top row
+#ifdef VAW_BOUNDS_CHECK
+    check_taps(a0, a0 + pl, 6u, tb.l_lo, tb.l_hi);
+#endif
+    const unsigned w0 = a0 & ~3u, sh = (a0 & 3u) * 8u;
+    const unsigned t0 = lds_u32(w0, 0u), t1 = lds_u32(w0, 4u), t2 = lds_u32(w0, 8u);
+    const unsigned b0 = lds_u32(w0, pl), b1 = lds_u32(w0, pl + 4u), b2 = lds_u32(w0, pl + 8u);
+    const unsigned lt = __funnelshift_r(t0, t1, sh), ht = __funnelshift_r(t1, t2, sh);  // B0 G0 R0 B1 | G1 R1 . .
+    const unsigned lb = __funnelshift_r(b0, b1, sh), hb = __funnelshift_r(b1, b2, sh);
+    const unsigned ax = __float_as_uint(s.x) & 31u, ay = __float_as_uint(s.y) & 31u, wy = 32u - ay;
+    // vertical blend in 16-bit halves: B0 | G0, R0 | B1, G1 | R1  (each <= 8160)
+    const unsigned v0 = imad_u32(__byte_perm(lb, 0u, 0x4140), ay, __byte_perm(lt, 0u, 0x4140) * wy);
+    const unsigned v1 = imad_u32(__byte_perm(lb, 0u, 0x4342), ay, __byte_perm(lt, 0u, 0x4342) * wy);
+    const unsigned v2 = imad_u32(__byte_perm(hb, 0u, 0x4140), ay, __byte_perm(ht, 0u, 0x4140) * wy);
+    const unsigned wxp = imad_u32(ax, 255u, 32u);  // (32 - ax) | ax << 8
+    const unsigned b = __dp2a_lo(__byte_perm(v0, v1, 0x7610), wxp, 512u) >> 10;  // left B | right B << 16
+    const unsigned g = __dp2a_lo(__byte_perm(v0, v2, 0x5432), wxp, 512u) >> 10;
+    const unsigned r = __dp2a_lo(__byte_perm(v1, v2, 0x7610), wxp, 512u) >> 10;
+    return b | (g << 8) | (r << 16);
 }
 
 // Overwrite the cells of the staged tile that lie outside the source with the border colour (cv::remap's
@@ -138,14 +176,23 @@ __device__ __forceinline__ void rows_packed(const Geom& g, const ColPoly2& cp, c
     const float dt = g.t_scale, dt2 = __fadd_rn(g.t_scale, g.t_scale);
     const unsigned dpitch = (unsigned)g.dst_pitch + (threadIdx.x >> 5);  // a vector register (see rows_quad)
     const unsigned long long g0 = (unsigned long long)__cvta_generic_to_global(out0);
+#if VAW_PACKED_UNROLL2
+#pragma unroll 2
+#else
 #pragma unroll 1
+#endif
     for (unsigned j2 = opaque_zero(); j2 < (unsigned)nrows; j2 += 2) {
         const float2 t0 = pair(t), t1 = pair(__fadd_rn(t, dt));
         t = __fadd_rn(t, dt2);
-        const unsigned v00 = packed_tile_sample<kCn>(fc, pl, col_coord(cp.a[0], cp.base, t0), tb);
-        const unsigned v01 = packed_tile_sample<kCn>(fc, pl, col_coord(cp.a[1], cp.base, t0), tb);
-        const unsigned v10 = packed_tile_sample<kCn>(fc, pl, col_coord(cp.a[0], cp.base, t1), tb);
-        const unsigned v11 = packed_tile_sample<kCn>(fc, pl, col_coord(cp.a[1], cp.base, t1), tb);
+#if VAW_BGR_BYTE_TAPS  // (analysis: the twelve-byte-load form)
+        constexpr bool kWords = false;
+#else
+        constexpr bool kWords = kCn == 3;
+#endif
+        const unsigned v00 = kWords ? bgr_tile_sample(fc, pl, col_coord(cp.a[0], cp.base, t0), tb) : packed_tile_sample<kCn>(fc, pl, col_coord(cp.a[0], cp.base, t0), tb);
+        const unsigned v01 = kWords ? bgr_tile_sample(fc, pl, col_coord(cp.a[1], cp.base, t0), tb) : packed_tile_sample<kCn>(fc, pl, col_coord(cp.a[1], cp.base, t0), tb);
+        const unsigned v10 = kWords ? bgr_tile_sample(fc, pl, col_coord(cp.a[0], cp.base, t1), tb) : packed_tile_sample<kCn>(fc, pl, col_coord(cp.a[0], cp.base, t1), tb);
+        const unsigned v11 = kWords ? bgr_tile_sample(fc, pl, col_coord(cp.a[1], cp.base, t1), tb) : packed_tile_sample<kCn>(fc, pl, col_coord(cp.a[1], cp.base, t1), tb);
         const unsigned long long r0 = row_ptr(g0, j2, dpitch), r1 = row_ptr(g0, j2 + 1u, dpitch);
         if (!kRagged) {
             if (kCn == 1) {
@@ -343,22 +390,28 @@ cudaError_t launch_warp_packed_tile(const Geom& g, const FrameBatch& b, const Pi
     const bool tracked = dev >= 0 && dev < 64;
     if (!tracked || !configured[dev].load(std::memory_order_acquire)) {
         cudaError_t e = configure_packed<1, 7>();
-        if (e == cudaSuccess) e = configure_packed<1, 5>();
+        if (e == cudaSuccess) e = configure_packed<1, 6>();
+        if (e == cudaSuccess) e = configure_packed<1, 4>();
         if (e == cudaSuccess) e = configure_packed<3, 7>();
-        if (e == cudaSuccess) e = configure_packed<3, 5>();
+        if (e == cudaSuccess) e = configure_packed<3, 6>();
+        if (e == cudaSuccess) e = configure_packed<3, 4>();
         if (e != cudaSuccess) return e;
         if (tracked) configured[dev].store(true, std::memory_order_release);
     }
     dim3 block(32, kWarps);
     dim3 grid(pieces_x(g.out_w), pieces_y(g.out_h, g.piece_h), b.n_frames);
     const int smem = kTileOffset + maps.tile_cap;
-    const bool seven = maps.tile_cap <= tile_cap_for_ctas(7, kTileOffset);  // else the 96-register build for 5 CTAs or fewer
+    // the instantiation whose register budget matches the CTAs the tile capacity lets share an SM: 7 (72 registers),
+    // 6 (80) or 4 and fewer (128)
+    const int ctas = maps.tile_cap <= tile_cap_for_ctas(7, kTileOffset) ? 7 : (maps.tile_cap <= tile_cap_for_ctas(6, kTileOffset) ? 6 : 4);
     if (channels == 1) {
-        if (seven) warp_packed_tile_kernel<1, 7><<<grid, block, smem, st>>>(g, b, table, maps);
-        else warp_packed_tile_kernel<1, 5><<<grid, block, smem, st>>>(g, b, table, maps);
+        if (ctas == 7) warp_packed_tile_kernel<1, 7><<<grid, block, smem, st>>>(g, b, table, maps);
+        else if (ctas == 6) warp_packed_tile_kernel<1, 6><<<grid, block, smem, st>>>(g, b, table, maps);
+        else warp_packed_tile_kernel<1, 4><<<grid, block, smem, st>>>(g, b, table, maps);
     } else {
-        if (seven) warp_packed_tile_kernel<3, 7><<<grid, block, smem, st>>>(g, b, table, maps);
-        else warp_packed_tile_kernel<3, 5><<<grid, block, smem, st>>>(g, b, table, maps);
+        if (ctas == 7) warp_packed_tile_kernel<3, 7><<<grid, block, smem, st>>>(g, b, table, maps);
+        else if (ctas == 6) warp_packed_tile_kernel<3, 6><<<grid, block, smem, st>>>(g, b, table, maps);
+        else warp_packed_tile_kernel<3, 4><<<grid, block, smem, st>>>(g, b, table, maps);
     }
     return cudaGetLastError();
 }
