@@ -82,7 +82,7 @@ def parse_args():
     ap.add_argument("--host-stages", type=int, default=0, help="chunks in flight of the host-buffer pipeline (0 = library default)")
     ap.add_argument("--host-chunk-mb", type=int, default=0, help="MiB of source frames per chunk of the host-buffer pipeline (0 = default)")
     ap.add_argument("--fused-bgr", action="store_true",
-                    help="NV12 in, BGR24 out in one launch (cvtColor + 3-channel remap, SURVEY 8 f2) instead of NV12 -> NV12")
+                    help="NV12 in, BGR24 out (cvtColor + 3-channel remap, SURVEY 8 f2; --variant 2 = in one launch) instead of NV12 -> NV12")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample budget")
     return ap.parse_args()
 
@@ -100,7 +100,7 @@ def config_dict(args, world):
     desc, src, sigma = WORKLOADS[args.workload]
     c4 = args.workload == "C4"
     return {"workload": f"{args.workload}: {desc}", "src": list(src),
-            "format": "NV12 -> BGR24 (cvtColor + 3-channel remap fused)" if getattr(args, "fused_bgr", False) else "NV12",
+            "format": "NV12 -> BGR24 (cvtColor + 3-channel remap)" if getattr(args, "fused_bgr", False) else "NV12",
             "frames_per_launch_per_gpu": (C4_FRAMES // world) if c4 else args.batch,
             "clip_frames": C4_FRAMES if c4 else args.batch * world,
             "sharding": ("frame-parallel, contiguous ranges of 600/N frames per GPU, no collective" if c4 else
@@ -598,7 +598,8 @@ def run_ours(args):
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": recorded_traffic(wl.name, n),
                              "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
-                             "kernel": ("warp_nv12_to_bgr_kernel (fused map + cvtColor + 3-channel remap)" if args.fused_bgr else
+                             "kernel": (("nv12_to_bgr_kernel + warp_packed_tile_kernel<3> per L2-sized chunk (cvtColor, then fused map + 3-channel remap on staged tiles)"
+                                         if ctx.variant == 3 else "warp_nv12_to_bgr_kernel (fused map + cvtColor + 3-channel remap)") if args.fused_bgr else
                                         KERNEL_NAMES.get(ctx.variant, "warp_nv12_quad_kernel") + " (fused map + remap, luma + chroma)"),
                              "launch_ms": {"avg": avg_launch_ms, "median": float(np.median(warp_ms)),
                                            "best": float(np.min(warp_ms)), "launches_timed": int(len(warp_ms))},

@@ -49,9 +49,12 @@ enum {
  * VAW_FORMAT_GRAY8: single 8-bit plane.
  * VAW_FORMAT_NV12_TO_BGR24: NV12 source frames, BGR24 output frames -- the reference's literal per-frame
  *   pipeline, cvtColor(COLOR_YUV2BGR_NV12) (opencv/FrameSourceWarp.cpp:399-401) followed by the 3-channel
- *   remap (:306-312), in ONE launch and bit-exact with doing the two steps one after the other: every
+ *   remap (:306-312), bit-exact with doing the two steps one after the other on whole frames: every
  *   bilinear tap is a source pixel converted with OpenCV's fixed-point BT.601, the border value applies to
- *   the converted image (border[0..2] = B, G, R).  Source sizes even, output size free; INTER_LINEAR. */
+ *   the converted image (border[0..2] = B, G, R).  Source sizes even, output size free; INTER_LINEAR.
+ *   Variant TILED (what AUTO picks): a few frames at a time are converted into a scratch that stays in L2 and
+ *   warped from there by the staged BGR kernel; variant POLY: ONE launch, each tap converted on the fly
+ *   (no intermediate image at all, 2.2x slower). */
 enum { VAW_FORMAT_NV12 = 0, VAW_FORMAT_BGR24 = 1, VAW_FORMAT_GRAY8 = 2, VAW_FORMAT_NV12_TO_BGR24 = 3 };
 
 /* cv::InterpolationFlags values accepted for the constructor's `interpolation` parameter
@@ -68,9 +71,10 @@ enum { VAW_INTER_NEAREST = 0, VAW_INTER_LINEAR = 1, VAW_INTER_CUBIC = 2, VAW_INT
  *           differences); pieces that cannot be certified use the GATHER evaluation.
  *   TILED   POLY's coordinates; the source rectangle of every piece is first copied into shared memory by
  *           the TMA engine (32/8/4-row boxes) and the taps are read from there; one CTA per piece, each
- *           warp a 64-column x PH/2-row quadrant with two columns per lane -- 64 registers, up to eight
+ *           warp a 64-column x PH/2-row quadrant with two columns per lane -- 64 / 72 registers, up to eight
  *           CTAs per SM (needs a 16-byte aligned source base / pitch / frame stride, else it gathers
- *           like POLY).
+ *           like POLY).  Exists for NV12 (csrc/vaw_tile.cu) and for GRAY8 / BGR24 (csrc/vaw_packed_tile.cu:
+ *           the reference's literal 8UC3 frames, three bytes per tap address).
  *   PIPE    (retired in round 2: a persistent producer/consumer ring pipeline over the same tiles; slower
  *           than TILED on every workload once TILED ran eight CTAs per SM.  The value is refused.)
  *   TEX     TILED, except that pieces certified interior (every tap inside the source) are filtered
@@ -81,8 +85,8 @@ enum { VAW_INTER_NEAREST = 0, VAW_INTER_LINEAR = 1, VAW_INTER_CUBIC = 2, VAW_INT
  *           than TILED (tex-pipe bound).  Kept for the comparison BASELINE.json asks for,
  *           never chosen by AUTO.  Needs a texture-aligned source base (512 bytes), a pitch that is
  *           a multiple of 32 and a frame stride that is a whole number of rows; else it runs as TILED.
- * POLY and TILED produce identical bytes.  AUTO = TILED for NV12, POLY for NV12 -> BGR24, GATHER for the
- * packed formats and for the other interpolation filters. */
+ * POLY and TILED produce identical bytes on NV12.  AUTO = TILED with INTER_LINEAR (every format), GATHER for the
+ * other interpolation filters.  GRAY8 / BGR24 accept GATHER and TILED, NV12 -> BGR24 POLY and TILED. */
 enum {
     VAW_VARIANT_AUTO = 0,
     VAW_VARIANT_GATHER = 1,

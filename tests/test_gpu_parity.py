@@ -423,7 +423,8 @@ def test_other_projection_pairs(V, oracle, projection, rot, variant):
     ("C3", (3840, 2160), (2.0, -3.0, 1.5), False),
     ("C2", (2482, 1408), (10.0, -15.0, 20.0), True),  # far outside the stabiliser's range: per-pixel pieces, rays behind the camera
 ])
-def test_fused_nv12_to_bgr_equals_cvtcolor_then_remap(V, oracle, name, out_size, rot, white):
+@pytest.mark.parametrize("variant", [POLY, TILED])
+def test_fused_nv12_to_bgr_equals_cvtcolor_then_remap(V, oracle, name, out_size, rot, white, variant):
     """NV12 in, BGR out in one launch == the reference's order of operations (FrameSourceWarp.cpp:399-401 then
     :306-312): cvtColor on the whole frame (oracle/cvt_ref.c, pinned to cv2.cvtColor), then cv::remap's
     integer filter on the 3-channel image with the map the kernel used.  0 LSB; also against the real
@@ -433,7 +434,9 @@ def test_fused_nv12_to_bgr_equals_cvtcolor_then_remap(V, oracle, name, out_size,
     R = rotation_xyz(*rot)
     sw, sh = w.src_size
     border = (3, 40, 200)
-    ctx = V.WarpContext(w.input_camera, w.output_camera, fmt=V.FORMAT_NV12_TO_BGR24, out_size=out_size, border=border)
+    # POLY: one launch (vaw_bgr.cu); TILED: cvtColor into an L2-sized scratch, then the staged BGR kernel, chunk by chunk
+    ctx = V.WarpContext(w.input_camera, w.output_camera, fmt=V.FORMAT_NV12_TO_BGR24, out_size=out_size, border=border, variant=variant)
+    assert ctx.variant == variant
     assert ctx.frame_shape("src") == (sh * 3 // 2, sw) and ctx.frame_shape("dst") == (out_size[1], out_size[0], 3)
     src = oracle.synth_nv12(sw, sh, 5, white_noise=white)
     got = _warp_one(V, ctx, src, R)
@@ -441,7 +444,7 @@ def test_fused_nv12_to_bgr_equals_cvtcolor_then_remap(V, oracle, name, out_size,
     bgr = oracle.nv12_to_bgr(src, sw, sh, threads=NCPU)
     ref = oracle.remap_u8(bgr, mx, my, border=border, threads=NCPU)
     st = G.diff_stats(got, ref)
-    _record(f"fused_bgr_same_map_{name}_{rot}", st)
+    _record(f"fused_bgr_same_map_v{variant}_{name}_{rot}", st)
     assert st["max"] == 0, st
     try:
         import cv2
@@ -461,7 +464,8 @@ def test_fused_nv12_to_bgr_equals_cvtcolor_then_remap(V, oracle, name, out_size,
     ctx.close()
 
 
-def test_fused_nv12_to_bgr_batches_pitches_and_the_two_launch_pipeline(V, oracle):
+@pytest.mark.parametrize("variant", [POLY, TILED])
+def test_fused_nv12_to_bgr_batches_pitches_and_the_two_launch_pipeline(V, oracle, variant):
     """Batch == per frame; pitched output with untouched padding; and the same bytes as the two-launch pipeline
     (vaw_nv12_to_bgr, then a BGR24 context) wherever the two contexts use the same map."""
     import torch
@@ -469,9 +473,9 @@ def test_fused_nv12_to_bgr_batches_pitches_and_the_two_launch_pipeline(V, oracle
     w = configs.workload("C1")
     sw, sh = w.src_size
     ow, oh = 1759, 998
-    n = 3
-    rots = configs.make_rotations(40, 0.7)[20:20 + n]
-    ctx = V.WarpContext(w.input_camera, w.output_camera, fmt=V.FORMAT_NV12_TO_BGR24, out_size=(ow, oh), border=(0, 0, 0))
+    n = 19 if variant == TILED else 3  # TILED: more frames than one scratch chunk (16 at 1080p)
+    rots = configs.make_rotations(60, 0.7)[20:20 + n]
+    ctx = V.WarpContext(w.input_camera, w.output_camera, fmt=V.FORMAT_NV12_TO_BGR24, out_size=(ow, oh), border=(0, 0, 0), variant=variant)
     src = torch.empty((n, sh * 3 // 2, sw), dtype=torch.uint8, device="cuda")
     V.synth_nv12(src, sw, sh, n, first_index=2, white_noise=True)
     rdev = torch.empty(n * 9, dtype=torch.float32, device="cuda")
