@@ -74,7 +74,8 @@ if funcs:
         m = re.search(r"BRA(?:\.\w+)*\s+(?:\w+,\s*)?`?\(?(0x[0-9a-f]+)", t)
         if m and int(m.group(1), 16) <= a and int(m.group(1), 16) in index:
             cand = ins[index[int(m.group(1), 16)]:k + 1]
-            if sum(1 for _, x in cand if x.startswith("LDS")) == 20 and sum(1 for _, x in cand if "STG" in x) == 3:
+            n_lds, n_stg = sum(1 for _, x in cand if x.startswith("LDS")), sum(1 for _, x in cand if "STG" in x)
+            if (n_lds, n_stg) in ((20, 3), (40, 6)):  # one row pair per trip, or two (unrolled)
                 loop = cand
                 break
     with open(os.path.join(P, f"{tag}_sass_tile.txt"), "w") as f:
@@ -84,16 +85,26 @@ if funcs:
                 "   source tile (UTMALDG), the CTA barrier:\n\n")
         f.write("\n".join(f"  /*{a:05x}*/ {t}" for a, t in ins if any(k in t for k in ("UTMALDG", "UBLKCP", "SYNCS", "BAR.", "CCTL"))) + "\n\n")
         lc = collections.Counter(re.sub(r"^@!?U?P\d+\s+", "", t).split()[0].split(".")[0] for _, t in loop)
-        f.write(f"2. the row loop ({len(loop)} instructions per 2 x 2 luma pixels + 1 chroma sample of a lane): "
+        pairs = 2 if sum(1 for _, x in loop if x.startswith("LDS")) == 40 else 1
+        f.write(f"2. the row loop ({len(loop)} instructions per trip = {pairs} row pair(s); a row pair = 2 x 2 luma pixels + 1 chroma sample of a lane): "
                 + ", ".join(f"{k} {v}" for k, v in lc.most_common()) + "\n\n")
         f.write("\n".join(f"  /*{a:05x}*/ {t}" for a, t in loop) + "\n")
-for fn in ("bench.json", "bench_ref.json", "bench_C5.json", "bench_C2.json", "bench_C1.json", "bench_C4.json", "bench_fused_bgr.json", "modes.json"):
+for fn in ("bench.json", "bench_ref.json", "bench_C5.json", "bench_C2.json", "bench_C1.json", "bench_C4.json", "bench_fused_bgr.json",
+           "bench_fused_bgr_one_launch.json", "modes.json"):
     if os.path.exists(os.path.join(G, fn)):
         open(os.path.join(P, f"{tag}_{fn}"), "w").write(open(os.path.join(G, fn)).read())
 if os.path.exists(os.path.join(G, "parity.json")):
     d = json.load(open(os.path.join(G, "parity.json")))
     json.dump(d, open(os.path.join(P, f"{tag}_parity.json"), "w"), indent=1)
-for fn, to in (("flow_demo.log", "flow_demo.txt"), ("abl.log", "ablations.txt")):
+if os.path.exists(os.path.join(G, "packed.jsonl")):
+    open(os.path.join(P, f"{tag}_packed.txt"), "w").write(
+        "tools/bench_packed.py: BGR24 / GRAY8 through the staged-tile kernel (vaw_packed_tile.cu), device-resident frames\n\n"
+        + open(os.path.join(G, "packed.jsonl")).read())
+if os.path.exists(os.path.join(G, "prof_bgr.ncu-rep")):
+    open(os.path.join(P, f"{tag}_ncu_bgr.txt"), "w").write(
+        "ncu --set full --clock-control none -k regex:packed_tile -s 4 -c 1  python tools/bench_packed.py C3 32 bgr\n\n"
+        + run([sys.executable, "tools/ncu_summary.py", os.path.join(G, "prof_bgr.ncu-rep")]))
+for fn, to in (("flow_demo.log", "flow_demo.txt"),):
     if os.path.exists(os.path.join(G, fn)):
         open(os.path.join(P, f"{tag}_{to}"), "w").write(open(os.path.join(G, fn)).read())
 print(open(os.path.join(P, f"{tag}_launches.txt")).read()[-600:])
