@@ -1092,7 +1092,8 @@ int vaw_dump_coords(vaw_ctx* ctx, const double rotation[9], int plane, float* ma
 long long vaw_debug_oob_count(int device)
 {
     DeviceGuard dg(device);
-    return vaw::tile_oob_count();
+    const long long a = vaw::tile_oob_count(), b = vaw::packed_tile_oob_count();
+    return (a < 0 || b < 0) ? (a < b ? a : b) : a + b;  // NV12 and GRAY8 / BGR24 staged kernels
 }
 
 int vaw_malloc(int device, size_t bytes, void** out)

@@ -73,6 +73,7 @@ struct alignas(64) PackedMaps {
 };
 int packed_tile_need_bytes(const PieceRec& rec, int channels);
 int packed_tile_smem_bytes(int tile_cap);
+long long packed_tile_oob_count();  // -1 when not instrumented
 cudaError_t launch_warp_packed_tile(const Geom& g, const FrameBatch& b, const PieceRec* table, const PackedMaps& maps,
                                     int channels, cudaStream_t st);
 // Variant TEX (vaw_tex.cu): certified interior pieces are filtered by the texture units.  The clip

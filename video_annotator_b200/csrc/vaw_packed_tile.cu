@@ -381,6 +381,17 @@ int packed_tile_need_bytes(const PieceRec& rec, int channels)
 
 int packed_tile_smem_bytes(int tile_cap) { return kTileOffset + tile_cap; }
 
+long long packed_tile_oob_count()  // this translation unit's own counter of the instrumented build (vaw_tile.cuh)
+{
+#ifdef VAW_BOUNDS_CHECK
+    unsigned long long v = 0;
+    if (cudaMemcpyFromSymbol(&v, g_oob_taps, sizeof v) != cudaSuccess) return -2;
+    return (long long)v;
+#else
+    return -1;
+#endif
+}
+
 cudaError_t launch_warp_packed_tile(const Geom& g, const FrameBatch& b, const PieceRec* table, const PackedMaps& maps,
                                     int channels, cudaStream_t st)
 {
