@@ -926,6 +926,43 @@ def test_packed_formats_on_staged_tiles_4k(V, oracle, fmt):
     ctx.close(); ctx2.close()
 
 
+@pytest.mark.parametrize("fmt", ["nv12", "bgr", "gray"])
+def test_inter_nearest_staged_4k(V, oracle, fmt):
+    """INTER_NEAREST on the staged kernels at 4K with a rotation that brings border-straddling pieces in: 0 LSB against
+    cv::remap's nearest (the oracle's filter on the rounded map the kernel used)."""
+    import torch
+    from video_annotator_b200 import configs
+    w = configs.workload("C3")
+    sw, sh = w.src_size
+    R = rotation_xyz(-6.0, 4.0, -9.0)
+    if fmt == "nv12":
+        border = (16, 100, 200)
+        ctx = V.WarpContext(w.input_camera, w.output_camera, out_size=w.out_size, border=border, interpolation=V.INTER_NEAREST)
+        assert ctx.variant == TILED
+        src = oracle.synth_nv12(sw, sh, 2, white_noise=True)
+        got = _warp_one(V, ctx, src, R)
+        mx, my = [t.cpu().numpy() for t in ctx.dump_coords(R, 0)]
+        cx, cy = [t.cpu().numpy() for t in ctx.dump_coords(R, 1)]
+        ref = _oracle_on_map(oracle, src, sw, sh, np.rint(mx), np.rint(my), np.rint(cx), np.rint(cy), border)
+        assert np.array_equal(got, ref)
+    else:
+        cn = 3 if fmt == "bgr" else 1
+        border = (10, 200, 90) if cn == 3 else (77,)
+        ow, oh = 3838, 2157
+        ctx = V.WarpContext(w.input_camera, w.output_camera, fmt=V.FORMAT_BGR24 if cn == 3 else V.FORMAT_GRAY8, out_size=(ow, oh),
+                            border=border, interpolation=V.INTER_NEAREST)
+        assert ctx.variant == TILED
+        rng = np.random.default_rng(9)
+        src = rng.integers(0, 256, (sh, sw, cn) if cn == 3 else (sh, sw), dtype=np.uint8)
+        dst = torch.empty(ctx.frame_shape("dst"), dtype=torch.uint8, device="cuda")
+        ctx.warp(G.to_dev(src), dst, R)
+        torch.cuda.synchronize()
+        mx, my = [t.cpu().numpy() for t in ctx.dump_coords(R, 0)]
+        ref = oracle.remap_u8(src, np.rint(mx), np.rint(my), border=border, threads=NCPU)
+        assert np.array_equal(dst.cpu().numpy().reshape(ref.shape), ref)
+    ctx.close()
+
+
 # ---- full-size clips through size-independent properties ----------------------------------------------
 def test_full_size_clip_properties(V, oracle):
     """C3 at BASELINE size, 24 frames in one launch: spot frames against the oracle, a constant
@@ -1222,21 +1259,25 @@ def test_shorter_pieces_for_short_focal_lengths(V, oracle, focal_scale, rows):
     ctx.close()
 
 
+@pytest.mark.parametrize("variant", [GATHER, TILED])
 @pytest.mark.parametrize("fmt", ["nv12", "bgr"])
-def test_inter_nearest(V, oracle, fmt):
+def test_inter_nearest(V, oracle, fmt, variant):
     """FrameSourceWarp's `interpolation` parameter (FrameSourceWarp.hpp:90) with cv::INTER_NEAREST:
-    cv::remap's cvRound of the map, implemented as the integer filter on whole-pixel coordinates
-    (tests/test_oracle_remap.py pins that identity on the real cv2.remap).  0 LSB."""
+    cv::remap's cvRound of the map -- GATHER: the integer filter on whole-pixel coordinates (tests/test_oracle_remap.py
+    pins that identity on the real cv2.remap); TILED (what AUTO picks): one tap per sample from the staged tile.  0 LSB."""
     import torch
     from video_annotator_b200 import configs
     w = configs.workload("C1")
     sw, sh = w.src_size
     R = rotation_xyz(1.0, -2.0, 0.5)
+    auto = V.WarpContext(w.input_camera, w.output_camera, out_size=w.out_size, interpolation=V.INTER_NEAREST)
+    assert auto.variant == TILED
+    auto.close()
     if fmt == "nv12":
         border = (16, 128, 128)
         ctx = V.WarpContext(w.input_camera, w.output_camera, out_size=w.out_size, border=border,
-                            interpolation=V.INTER_NEAREST)
-        assert ctx.variant == GATHER
+                            interpolation=V.INTER_NEAREST, variant=variant)
+        assert ctx.variant == variant
         src = oracle.synth_nv12(sw, sh, 4, white_noise=True)
         got = _warp_one(V, ctx, src, R)
         mx, my = [t.cpu().numpy() for t in ctx.dump_coords(R, 0)]
@@ -1250,7 +1291,8 @@ def test_inter_nearest(V, oracle, fmt):
         ow, oh = w.output_camera.size
         border = (10, 20, 30)
         ctx = V.WarpContext(w.input_camera, w.output_camera, fmt=V.FORMAT_BGR24, border=border,
-                            interpolation=V.INTER_NEAREST)
+                            interpolation=V.INTER_NEAREST, variant=variant)
+        assert ctx.variant == variant
         rng = np.random.default_rng(3)
         src = rng.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
         dst = torch.empty((oh, ow, 3), dtype=torch.uint8, device="cuda")
@@ -1261,7 +1303,9 @@ def test_inter_nearest(V, oracle, fmt):
         assert np.array_equal(dst.cpu().numpy(), ref.reshape(oh, ow, 3))
     ctx.close()
     with pytest.raises(V.VawError):
-        V.WarpContext(w.input_camera, w.output_camera, out_size=w.out_size, interpolation=V.INTER_NEAREST, variant=TILED)
+        V.WarpContext(w.input_camera, w.output_camera, out_size=w.out_size, interpolation=V.INTER_NEAREST, variant=POLY)
+    with pytest.raises(V.VawError):
+        V.WarpContext(w.input_camera, w.output_camera, out_size=w.out_size, interpolation=V.INTER_CUBIC, variant=TILED)
 
 
 @pytest.mark.parametrize("interp", ["cubic", "lanczos4"])

@@ -42,7 +42,9 @@ def main():
     modes = [("NV12 linear (tile kernel, default)", V.FORMAT_NV12, V.INTER_LINEAR, 0),
              ("NV12 linear, variant POLY (L1 gathers)", V.FORMAT_NV12, V.INTER_LINEAR, 2),
              ("NV12 linear, variant GATHER (op-for-op map)", V.FORMAT_NV12, V.INTER_LINEAR, 1),
-             ("NV12 nearest", V.FORMAT_NV12, V.INTER_NEAREST, 0),
+             ("NV12 nearest (staged-tile kernel, default)", V.FORMAT_NV12, V.INTER_NEAREST, 0),
+             ("NV12 nearest, variant GATHER", V.FORMAT_NV12, V.INTER_NEAREST, 1),
+             ("BGR24 nearest (staged-tile kernel, default)", V.FORMAT_BGR24, V.INTER_NEAREST, 0),
              ("NV12 cubic", V.FORMAT_NV12, V.INTER_CUBIC, 0),
              ("NV12 lanczos4", V.FORMAT_NV12, V.INTER_LANCZOS4, 0),
              ("NV12 in -> BGR24 out, one launch (cvtColor + 3-channel remap fused, variant POLY)", V.FORMAT_NV12_TO_BGR24, V.INTER_LINEAR, 2),

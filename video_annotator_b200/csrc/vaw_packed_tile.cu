@@ -57,6 +57,7 @@ __device__ __forceinline__ void store_px_checked(uint8_t* row, int u, int out_w,
 template <int kCn>
 __device__ __forceinline__ unsigned sample_checked(const Geom& g, const uint8_t* __restrict__ src, float mx, float my)
 {
+    if (g.nearest) { mx = nearest_coord(mx); my = nearest_coord(my); }  // INTER_NEAREST = the filter on whole-pixel coordinates
     if (kCn == 1) return (unsigned)sample_c1(src, g.src_pitch, g.src_w, g.src_h, mx, my, g.border & 255);
     return sample_c3(src, g.src_pitch, g.src_w, g.src_h, mx, my, g.border & 0xffffffu);
 }
@@ -88,6 +89,19 @@ __device__ __forceinline__ unsigned packed_tile_sample(const FloorConst& fc, uns
         const unsigned v = __dp2a_lo(h, wy, 512u) >> 10;
         out |= v << (8 * c);
     }
+    return out;
+}
+
+// cv::INTER_NEAREST: the sample at (cvRound(x), cvRound(y)) (see luma_tile_nearest, vaw_tile.cuh);
+// row = tile address - y0 * pitch - bx0 - 0x4B400000 * (pitch + kCn)
+template <int kCn>
+__device__ __forceinline__ unsigned packed_tile_nearest(unsigned row, unsigned pl, float2 m)
+{
+    const float2 s = __fadd2_rn(m, pair(kMagic));
+    const unsigned a = (kCn == 1 ? imad_u32(__float_as_uint(s.y), pl, __float_as_uint(s.x))
+                                 : imad_u32(__float_as_uint(s.x), (unsigned)kCn, __float_as_uint(s.y) * pl)) + row;
+    unsigned out = lds_u8<0>(a);
+    if (kCn == 3) out |= (lds_u8<1>(a) << 8) | (lds_u8<2>(a) << 16);
     return out;
 }
 
@@ -168,7 +182,7 @@ __device__ __forceinline__ void fill_border_packed(uint8_t* tile, int pl, int ti
 }
 
 // nrows rows starting at piece row dv0 for the lane's two columns (u0, u0 + 1); taps from the staged tile.
-template <int kCn, bool kRagged>
+template <int kCn, bool kRagged, bool kNearest>
 __device__ __forceinline__ void rows_packed(const Geom& g, const ColPoly2& cp, const FloorConst& fc, unsigned pl, int dv0,
                                             int nrows, uint8_t* __restrict__ out0, int u0, const TileBounds& tb)
 {
@@ -189,10 +203,18 @@ __device__ __forceinline__ void rows_packed(const Geom& g, const ColPoly2& cp, c
 #else
         constexpr bool kWords = kCn == 3;
 #endif
-        const unsigned v00 = kWords ? bgr_tile_sample(fc, pl, col_coord(cp.a[0], cp.base, t0), tb) : packed_tile_sample<kCn>(fc, pl, col_coord(cp.a[0], cp.base, t0), tb);
-        const unsigned v01 = kWords ? bgr_tile_sample(fc, pl, col_coord(cp.a[1], cp.base, t0), tb) : packed_tile_sample<kCn>(fc, pl, col_coord(cp.a[1], cp.base, t0), tb);
-        const unsigned v10 = kWords ? bgr_tile_sample(fc, pl, col_coord(cp.a[0], cp.base, t1), tb) : packed_tile_sample<kCn>(fc, pl, col_coord(cp.a[0], cp.base, t1), tb);
-        const unsigned v11 = kWords ? bgr_tile_sample(fc, pl, col_coord(cp.a[1], cp.base, t1), tb) : packed_tile_sample<kCn>(fc, pl, col_coord(cp.a[1], cp.base, t1), tb);
+        unsigned v00, v01, v10, v11;
+        if (kNearest) {
+            v00 = packed_tile_nearest<kCn>(fc.row0, pl, col_coord(cp.a[0], cp.base, t0));
+            v01 = packed_tile_nearest<kCn>(fc.row0, pl, col_coord(cp.a[1], cp.base, t0));
+            v10 = packed_tile_nearest<kCn>(fc.row0, pl, col_coord(cp.a[0], cp.base, t1));
+            v11 = packed_tile_nearest<kCn>(fc.row0, pl, col_coord(cp.a[1], cp.base, t1));
+        } else {
+        v00 = kWords ? bgr_tile_sample(fc, pl, col_coord(cp.a[0], cp.base, t0), tb) : packed_tile_sample<kCn>(fc, pl, col_coord(cp.a[0], cp.base, t0), tb);
+        v01 = kWords ? bgr_tile_sample(fc, pl, col_coord(cp.a[1], cp.base, t0), tb) : packed_tile_sample<kCn>(fc, pl, col_coord(cp.a[1], cp.base, t0), tb);
+        v10 = kWords ? bgr_tile_sample(fc, pl, col_coord(cp.a[0], cp.base, t1), tb) : packed_tile_sample<kCn>(fc, pl, col_coord(cp.a[0], cp.base, t1), tb);
+        v11 = kWords ? bgr_tile_sample(fc, pl, col_coord(cp.a[1], cp.base, t1), tb) : packed_tile_sample<kCn>(fc, pl, col_coord(cp.a[1], cp.base, t1), tb);
+        }
         const unsigned long long r0 = row_ptr(g0, j2, dpitch), r1 = row_ptr(g0, j2 + 1u, dpitch);
         if (!kRagged) {
             if (kCn == 1) {
@@ -215,7 +237,7 @@ __device__ __forceinline__ void rows_packed(const Geom& g, const ColPoly2& cp, c
     }
 }
 
-template <int kCn, int kCtas>
+template <int kCn, int kCtas, bool kNearest = false>
 __global__ void __launch_bounds__(32 * kWarps, kCtas)
 warp_packed_tile_kernel(const Geom g, const FrameBatch b, const PieceRec* __restrict__ table,
                         const __grid_constant__ PackedMaps maps)
@@ -354,17 +376,24 @@ warp_packed_tile_kernel(const Geom g, const FrameBatch b, const PieceRec* __rest
                          u_lo + kPieceW <= g.out_w && (rows & 1) == 0 && (hrows & 1) == 0;
     const TileBounds tb = {smem_u32(tile), smem_u32(tile) + (unsigned)(nrows * pl), 0u, 0u};
     uint8_t* const out0 = dst + (size_t)(v_base + dv0) * g.dst_pitch + (size_t)u0 * kCn;
-    if (pair_ok) rows_packed<kCn, false>(g, cp, fc, upl, dv0, my_rows, out0, u0, tb);
-    else rows_packed<kCn, true>(g, cp, fc, upl, dv0, my_rows, out0, u0, tb);
+    if (kNearest) {
+        const FloorConst fn = floor_const(0, 0, smem_u32(tile) - (unsigned)box.y0 * upl - (unsigned)bx0 - (unsigned)kMagicBits * (upl + (unsigned)kCn),
+                                          upl, 0.f, never);
+        if (pair_ok) rows_packed<kCn, false, true>(g, cp, fn, upl, dv0, my_rows, out0, u0, tb);
+        else rows_packed<kCn, true, true>(g, cp, fn, upl, dv0, my_rows, out0, u0, tb);
+        return;
+    }
+    if (pair_ok) rows_packed<kCn, false, false>(g, cp, fc, upl, dv0, my_rows, out0, u0, tb);
+    else rows_packed<kCn, true, false>(g, cp, fc, upl, dv0, my_rows, out0, u0, tb);
 }
 
-template <int kCn, int kCtas>
+template <int kCn, int kCtas, bool kNearest = false>
 cudaError_t configure_packed()
 {
-    cudaError_t e = cudaFuncSetAttribute(warp_packed_tile_kernel<kCn, kCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(warp_packed_tile_kernel<kCn, kCtas, kNearest>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          kTileOffset + kTileCapMax);
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(warp_packed_tile_kernel<kCn, kCtas>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        e = cudaFuncSetAttribute(warp_packed_tile_kernel<kCn, kCtas, kNearest>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     return e;
 }
 
@@ -406,6 +435,8 @@ cudaError_t launch_warp_packed_tile(const Geom& g, const FrameBatch& b, const Pi
         if (e == cudaSuccess) e = configure_packed<3, 7>();
         if (e == cudaSuccess) e = configure_packed<3, 6>();
         if (e == cudaSuccess) e = configure_packed<3, 4>();
+        if (e == cudaSuccess) e = configure_packed<1, 7, true>();
+        if (e == cudaSuccess) e = configure_packed<3, 7, true>();
         if (e != cudaSuccess) return e;
         if (tracked) configured[dev].store(true, std::memory_order_release);
     }
@@ -415,6 +446,11 @@ cudaError_t launch_warp_packed_tile(const Geom& g, const FrameBatch& b, const Pi
     // the instantiation whose register budget matches the CTAs the tile capacity lets share an SM: 7 (72 registers),
     // 6 (80) or 4 and fewer (128)
     const int ctas = maps.tile_cap <= tile_cap_for_ctas(7, kTileOffset) ? 7 : (maps.tile_cap <= tile_cap_for_ctas(6, kTileOffset) ? 6 : 4);
+    if (g.nearest) {  // cv::INTER_NEAREST: one light instantiation per format
+        if (channels == 1) warp_packed_tile_kernel<1, 7, true><<<grid, block, smem, st>>>(g, b, table, maps);
+        else warp_packed_tile_kernel<3, 7, true><<<grid, block, smem, st>>>(g, b, table, maps);
+        return cudaGetLastError();
+    }
     if (channels == 1) {
         if (ctas == 7) warp_packed_tile_kernel<1, 7><<<grid, block, smem, st>>>(g, b, table, maps);
         else if (ctas == 6) warp_packed_tile_kernel<1, 6><<<grid, block, smem, st>>>(g, b, table, maps);

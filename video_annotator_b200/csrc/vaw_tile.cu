@@ -86,7 +86,7 @@ using TapConst = FloorConst;
 using TapConst = unsigned;
 #endif
 
-template <bool kRagged>
+template <bool kRagged, bool kNearest>
 __device__ __forceinline__ void rows_quad(const Geom& g, const ColPoly2& cp, const TapConst& lconst, const TapConst& cconst, unsigned pl,
                                           int dv0, int nrows, uint8_t* __restrict__ py, uint8_t* __restrict__ pc,
                                           bool inside, const TileBounds& tb)
@@ -117,9 +117,16 @@ __device__ __forceinline__ void rows_quad(const Geom& g, const ColPoly2& cp, con
         const float2 m00 = col_coord(cp.a[0], cp.base, t0), m01 = col_coord(cp.a[1], cp.base, t0);
         const float2 m10 = col_coord(cp.a[0], cp.base, t1), m11 = col_coord(cp.a[1], cp.base, t1);
 #if VAW_SAMPLER == 3
-        const unsigned y00 = luma_tile3(lconst, pl, m00, tb) >> 10, y01 = luma_tile3(lconst, pl, m01, tb) >> 10;
-        const unsigned y10 = luma_tile3(lconst, pl, m10, tb) >> 10, y11 = luma_tile3(lconst, pl, m11, tb) >> 10;
-        const unsigned c = chroma_tile3(cconst, pl, chroma_z(m00, m01, m10, m11), tb);  // U | V << 8
+        unsigned y00, y01, y10, y11, c;
+        if (kNearest) {  // cv::INTER_NEAREST: one tap per sample (lconst / cconst carry the nearest row constants)
+            y00 = luma_tile_nearest(lconst.row0, pl, m00); y01 = luma_tile_nearest(lconst.row0, pl, m01);
+            y10 = luma_tile_nearest(lconst.row0, pl, m10); y11 = luma_tile_nearest(lconst.row0, pl, m11);
+            c = chroma_tile_nearest(cconst.row0, pl, chroma_z(m00, m01, m10, m11));
+        } else {
+            y00 = luma_tile3(lconst, pl, m00, tb) >> 10; y01 = luma_tile3(lconst, pl, m01, tb) >> 10;
+            y10 = luma_tile3(lconst, pl, m10, tb) >> 10; y11 = luma_tile3(lconst, pl, m11, tb) >> 10;
+            c = chroma_tile3(cconst, pl, chroma_z(m00, m01, m10, m11), tb);  // U | V << 8
+        }
 #else
         const unsigned y00 = (unsigned)luma_tile(lconst, pl, m00, tb) >> 10, y01 = (unsigned)luma_tile(lconst, pl, m01, tb) >> 10;
         const unsigned y10 = (unsigned)luma_tile(lconst, pl, m10, tb) >> 10, y11 = (unsigned)luma_tile(lconst, pl, m11, tb) >> 10;
@@ -151,6 +158,7 @@ __device__ __forceinline__ void rows_quad(const Geom& g, const ColPoly2& cp, con
 // 0.736 ms against 0.660 ms -- more instructions, not fewer, and longer tile waits)  `rec` = the same record in the table (the gather fallbacks read it from there);
 // `tile_parity` = phase of the tile mbarrier (smem + 0) this piece's loads complete.  Returns whether the piece was staged
 // (i.e. whether that phase was consumed).
+template <bool kNearest>
 __device__ __forceinline__ bool quad_piece(const Geom& g, const FrameBatch& b, const PieceRec* __restrict__ rec,
                                            const PieceRec* rs, const TileMaps& maps, uint8_t* smem, int px, int py,
                                            int frame, unsigned tile_parity, int lane, int w, int tid)
@@ -217,13 +225,13 @@ __device__ __forceinline__ bool quad_piece(const Geom& g, const FrameBatch& b, c
             for (int dv = dv0; dv < dv0 + my_rows; dv += 2) {
                 float2 m[2][4];
                 exact_rows(g, R, u_lo, u0, v_base + dv, m);
-                sample_rows_checked(g, f, u0, v_base + dv, m);
+                sample_rows_checked<kNearest>(g, f, u0, v_base + dv, m);
             }
             return false;
         }
         ColPoly cp;
         derive(rec, lane, cp);
-        if (flags & kPieceInterior) {
+        if (!kNearest && (flags & kPieceInterior)) {
             RowPtrs o;
             o.y0 = dst + (size_t)(v_base + dv0) * g.dst_pitch + u0;
             o.y1 = o.y0 + g.dst_pitch;
@@ -239,7 +247,7 @@ __device__ __forceinline__ bool quad_piece(const Geom& g, const FrameBatch& b, c
                 float2 m[2][4];
                 row_coords(cp, row_t(g, dv), m[0]);
                 row_coords(cp, row_t(g, dv + 1), m[1]);
-                sample_rows_checked(g, f, u0, v_base + dv, m);
+                sample_rows_checked<kNearest>(g, f, u0, v_base + dv, m);
             }
         }
         return false;
@@ -316,6 +324,9 @@ __device__ __forceinline__ bool quad_piece(const Geom& g, const FrameBatch& b, c
 #endif
     const FloorConst lconst = floor_const(-lx0, -by0, smem_u32(ltile) - 0x40000000u, upl, __uint_as_float(0x42000000u | vnever), (unsigned)raw.w >> 31);  // (the stage's zero pad: with g.out_w >> 31 ptxas keeps the luma pair in vector registers)
     const FloorConst cconst = floor_const(-(cbx0 >> 1), -cy0, smem_u32(ctile) - 0x80000000u, upl, __uint_as_float(0x41800000u | vnever), never);
+    // INTER_NEAREST: the row constants of luma_tile_nearest / chroma_tile_nearest instead (same uniform-register treatment)
+    const FloorConst lnear = floor_const(0, 0, smem_u32(ltile) - (unsigned)by0 * upl - (unsigned)lx0 - (unsigned)kMagicBits * (upl + 1u), upl, 0.f, (unsigned)raw.w >> 31);
+    const FloorConst cnear = floor_const(0, 0, smem_u32(ctile) - (unsigned)cy0 * upl - (unsigned)cbx0 - (unsigned)kMagicBits * (upl + 2u), upl, 0.f, never);
 #else
     const unsigned lconst = smem_u32(ltile) - (unsigned)by0 * upl - (unsigned)lx0 - kMagicShift * upl - kMagicShift;
     const unsigned cconst = ((smem_u32(ctile) - (unsigned)cy0 * upl - (unsigned)cbx0 - kMagicShift * upl) >> 1) - kMagicShift;
@@ -328,8 +339,15 @@ __device__ __forceinline__ bool quad_piece(const Geom& g, const FrameBatch& b, c
                            smem_u32(ctile) + (unsigned)(cnrows * pl)};
     uint8_t* const oy = dst + (size_t)(v_base + dv0) * g.dst_pitch + u0;
     uint8_t* const oc = dst + (size_t)(g.out_h + ((v_base + dv0) >> 1)) * g.dst_pitch + u0;
-    if (pair_ok) rows_quad<false>(g, cp, lconst, cconst, upl, dv0, my_rows, oy, oc, inside, tb);
-    else rows_quad<true>(g, cp, lconst, cconst, upl, dv0, my_rows, oy, oc, inside, tb);
+#if VAW_SAMPLER == 3
+    if (kNearest) {
+        if (pair_ok) rows_quad<false, true>(g, cp, lnear, cnear, upl, dv0, my_rows, oy, oc, inside, tb);
+        else rows_quad<true, true>(g, cp, lnear, cnear, upl, dv0, my_rows, oy, oc, inside, tb);
+        return true;
+    }
+#endif
+    if (pair_ok) rows_quad<false, false>(g, cp, lconst, cconst, upl, dv0, my_rows, oy, oc, inside, tb);
+    else rows_quad<true, false>(g, cp, lconst, cconst, upl, dv0, my_rows, oy, oc, inside, tb);
     return true;  // this piece's loads completed a phase of the tile mbarrier
 }
 
@@ -337,7 +355,7 @@ __device__ __forceinline__ bool quad_piece(const Geom& g, const FrameBatch& b, c
 // the C3 tiles let seven CTAs share an SM, and the eight registers the 64-register build gives away buy nothing
 // there -- measured 0.651 against 0.661 ms) or 6 (80 registers, no spills in the fallback paths) where shared
 // memory allows six or fewer anyway (C5 +2.6 %, C2 +3 %).
-template <int kCtas>
+template <int kCtas, bool kNearest = false>
 __global__ void __launch_bounds__(32 * kWarps, kCtas)
 warp_nv12_quad_kernel(const Geom g, const FrameBatch b, const PieceRec* __restrict__ table,
                       const __grid_constant__ TileMaps maps)
@@ -375,7 +393,7 @@ warp_nv12_quad_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
     mbar_wait_parked(mbar_rec, 0, 4000);
 #endif
     const PieceRec* rs = reinterpret_cast<const PieceRec*>(smem + kQuadRecOffset);
-    quad_piece(g, b, rec, rs, maps, smem, px, py, frame, 0u, lane, w, tid);
+    quad_piece<kNearest>(g, b, rec, rs, maps, smem, px, py, frame, 0u, lane, w, tid);
 }
 
 long long tile_oob_count()
@@ -404,14 +422,14 @@ int tile_need_bytes(const PieceRec& rec)
     return pl * (nrows + cnrows);
 }
 
-template <int kCtas>
+template <int kCtas, bool kNearest = false>
 static cudaError_t configure_quad()
 {
-    cudaError_t e = cudaFuncSetAttribute(warp_nv12_quad_kernel<kCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(warp_nv12_quad_kernel<kCtas, kNearest>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          tile_smem_bytes(kTileCapMax));
     // all of the SM's shared memory for tiles: the taps never go through L1
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(warp_nv12_quad_kernel<kCtas>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        e = cudaFuncSetAttribute(warp_nv12_quad_kernel<kCtas, kNearest>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     return e;
 }
 cudaError_t launch_warp_nv12_tile(const Geom& g, const FrameBatch& b, const PieceRec* table, const TileMaps& maps,
@@ -427,6 +445,7 @@ cudaError_t launch_warp_nv12_tile(const Geom& g, const FrameBatch& b, const Piec
         cudaError_t e = configure_quad<8>();
         if (e == cudaSuccess) e = configure_quad<7>();
         if (e == cudaSuccess) e = configure_quad<6>();
+        if (e == cudaSuccess) e = configure_quad<8, true>();
         if (e != cudaSuccess) return e;
         if (tracked) configured[dev].store(true, std::memory_order_release);
     }
@@ -434,7 +453,9 @@ cudaError_t launch_warp_nv12_tile(const Geom& g, const FrameBatch& b, const Piec
     dim3 grid(pieces_x(g.out_w), pieces_y(g.out_h, g.piece_h), b.n_frames);
     // the instantiation whose register budget matches the CTAs the tile capacity lets share an SM
     const int smem = tile_smem_bytes(maps.tile_cap);
-    if (maps.tile_cap <= tile_cap_for_ctas(8, kQuadTileOffset)) warp_nv12_quad_kernel<8><<<grid, block, smem, st>>>(g, b, table, maps);
+    // cv::INTER_NEAREST: one light instantiation (64 registers are plenty for one tap per sample)
+    if (g.nearest) warp_nv12_quad_kernel<8, true><<<grid, block, smem, st>>>(g, b, table, maps);
+    else if (maps.tile_cap <= tile_cap_for_ctas(8, kQuadTileOffset)) warp_nv12_quad_kernel<8><<<grid, block, smem, st>>>(g, b, table, maps);
     else if (maps.tile_cap <= tile_cap_for_ctas(7, kQuadTileOffset)) warp_nv12_quad_kernel<7><<<grid, block, smem, st>>>(g, b, table, maps);
     else warp_nv12_quad_kernel<6><<<grid, block, smem, st>>>(g, b, table, maps);
     return cudaGetLastError();

@@ -166,6 +166,23 @@ __device__ __forceinline__ unsigned chroma_tile3(const FloorConst& fc, unsigned 
                     __float_as_uint(s.y) & 31u);
 }
 
+// ---- cv::INTER_NEAREST from the staged tile (FrameSourceWarp.hpp:90's `interpolation`): cv::remap takes the sample at
+// (cvRound(x), cvRound(y)), i.e. round-half-even of the map value itself -- one magic-constant add per coordinate pair,
+// one multiply-add for the address, one load.  `row` = tile address - y0 * pitch - x0 - 0x4B400000 * (pitch + step)
+// (block-uniform; the bit patterns' exponent part cancels modulo 2^32).  The tap always lies inside the box the tile
+// was staged for (floor(m) <= rint(m) <= floor(m) + 1).
+__device__ __forceinline__ unsigned luma_tile_nearest(unsigned row, unsigned pl, float2 m)
+{
+    const float2 s = __fadd2_rn(m, pair(kMagic));
+    return lds_u8<0>(imad_u32(__float_as_uint(s.y), pl, __float_as_uint(s.x)) + row);
+}
+// z = twice the chroma coordinate (chroma_z): the coordinate itself is z / 2 exactly; returns U | V << 8
+__device__ __forceinline__ unsigned chroma_tile_nearest(unsigned row, unsigned pl, float2 z)
+{
+    const float2 s = __fadd2_rn(__fmul2_rn(z, pair(0.5f)), pair(kMagic));
+    return lds_u16<0>(imad_u32(__float_as_uint(s.x), 2u, __float_as_uint(s.y) * pl) + row);
+}
+
 // ---- pieces shared by the quadrant kernels (vaw_tile.cu: NV12; vaw_packed_tile.cu: GRAY8 / BGR24) ----------------------
 struct ColPoly2 {
     float2 a[2][kNv];  // [column][power of t]
