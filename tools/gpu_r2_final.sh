@@ -16,6 +16,7 @@ timeout 600 python bench.py --fused-bgr --variant 2 --no-cpu-baseline --no-e2e -
 (PYTHONPATH=. timeout 300 python tools/bench_packed.py C3 32 bgr gray; PYTHONPATH=. timeout 300 python tools/bench_packed.py C1 32 bgr gray; PYTHONPATH=. timeout 300 python tools/bench_packed.py C5 16 bgr gray) > gpurun_out/packed.jsonl 2>> gpurun_out/bench.err
 PYTHONPATH=. timeout 600 python tools/bench_modes.py > gpurun_out/modes.json 2>> gpurun_out/bench.err
 ./video_annotator_b200/host/vaw_demo --flow 40 3840 2160 0.5 > gpurun_out/flow_demo.log 2>&1; tail -1 gpurun_out/flow_demo.log
+for b in 8 16 24 30; do ./video_annotator_b200/host/vaw_demo --bench 1500 $b 2>&1 | grep "^{" ; done > gpurun_out/shim_batch.log; cat gpurun_out/shim_batch.log
 CMD="python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-parity --no-shim"
 timeout 300 $CMD > gpurun_out/plain.log 2>&1 &&
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1

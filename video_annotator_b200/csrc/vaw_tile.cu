@@ -275,6 +275,18 @@ __device__ __forceinline__ bool quad_piece(const Geom& g, const FrameBatch& b, c
         for (k = 0; k + 32 <= cnrows; k += 32) tma_load_3d(c0 + (unsigned)(k * pl), map32, cbx0 >> 2, g.src_h + cy0 + k, z, mbar);
         for (; k + 8 <= cnrows; k += 8) tma_load_3d(c0 + (unsigned)(k * pl), map, cbx0 >> 2, g.src_h + cy0 + k, z, mbar);
         if (k < cnrows) tma_load_3d(c0 + (unsigned)(k * pl), map4, cbx0 >> 2, g.src_h + cy0 + k, z, mbar);
+#if VAW_PREFETCH_NEXT_FRAME
+        // the same boxes of the NEXT frame into L2: consecutive frames' rotations differ by a fraction of a degree, so
+        // the next frame's piece at this position reads (nearly) this rectangle about one frame's worth of CTAs from now
+        if (frame + 1 < (int)gridDim.z) {
+            for (k = 0; k + 32 <= nrows; k += 32) tma_prefetch_3d(map32, lx0 >> 2, by0 + k, z + 1);
+            for (; k + 8 <= nrows; k += 8) tma_prefetch_3d(map, lx0 >> 2, by0 + k, z + 1);
+            if (k < nrows) tma_prefetch_3d(map4, lx0 >> 2, by0 + k, z + 1);
+            for (k = 0; k + 32 <= cnrows; k += 32) tma_prefetch_3d(map32, cbx0 >> 2, g.src_h + cy0 + k, z + 1);
+            for (; k + 8 <= cnrows; k += 8) tma_prefetch_3d(map, cbx0 >> 2, g.src_h + cy0 + k, z + 1);
+            if (k < cnrows) tma_prefetch_3d(map4, cbx0 >> 2, g.src_h + cy0 + k, z + 1);
+        }
+#endif
     }
 
     // ---- this warp's quadrant; every lane collapses the polynomial onto its two columns ---------------

@@ -17,6 +17,13 @@ __device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* map
         : "memory");
 }
 
+// The same box pulled into L2 only (no shared-memory destination, no completion to wait for).
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int x, int y, int z)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(z) : "memory");
+}
+
 // Instrumented build (-DVAW_BOUNDS_CHECK, tests only: compute-sanitizer is not available on the GPU
 // pool): every tap address of the staged samplers is checked against the plane's tile and counted
 // when it falls outside; vaw_debug_oob_count() returns the count (-1 when not instrumented).
