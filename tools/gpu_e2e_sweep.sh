@@ -5,7 +5,7 @@ N=${1:-8}
 mkdir -p gpurun_out
 LAUNCH="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533"
 [ "$N" = 1 ] && LAUNCH=python
-for cfg in "4 32" "8 32" "4 96" "8 96" "6 200" "3 400"; do
+for cfg in ${SWEEP:-"4 32" "8 32" "4 128" "8 128"}; do
   set -- $cfg
   timeout 300 $LAUNCH bench.py --gpus $N --no-cpu-baseline --no-parity --no-shim --steps 5 --host-stages $1 --host-chunk-mb $2 2>> gpurun_out/sweep.err | python -c "
 import json,sys
