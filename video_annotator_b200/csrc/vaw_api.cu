@@ -609,6 +609,10 @@ int choose_tile_cap(vaw_ctx* ctx)
 {
     const int book = vaw::tile_smem_bytes(0);
     int ctas = 8;  // register limit of the 64-register instantiation
+    if (const char* env = getenv("VAW_EXPERIMENT_MAX_CTAS")) {  // analysis only (two-warp CTAs: more of them fit)
+        const int v = atoi(env);
+        if (v >= 1 && v <= 32) ctas = v;
+    }
     while (ctas > 1 && ctx->tile_need * 106 / 100 > vaw::tile_cap_for_ctas(ctas, book)) --ctas;
     long long cap = vaw::tile_cap_for_ctas(ctas, book);
     if (cap < vaw::kTileCapMin) cap = vaw::kTileCapMin;
