@@ -763,6 +763,35 @@ def test_host_buffer_path_equals_device_path(V, oracle):
     ctx.close()
 
 
+@pytest.mark.parametrize("fmt", ["bgr", "nv12_to_bgr"])
+def test_host_buffer_path_packed_formats(V, oracle, fmt):
+    """vaw_warp_batch_host for the reference's literal formats: BGR24 frames and NV12 in -> BGR24 out (staged kernels,
+    per-stage piece tables, the L2-sized conversion scratch) equal the device path, over several chunks."""
+    import torch
+    from video_annotator_b200 import configs
+    w = configs.workload("C1")
+    n = 23
+    rots = configs.make_rotations(80, 0.6)[30:30 + n]
+    vfmt = V.FORMAT_BGR24 if fmt == "bgr" else V.FORMAT_NV12_TO_BGR24
+    ctx = V.WarpContext(w.input_camera, w.output_camera, fmt=vfmt, out_size=(1759, 998), border=(5, 60, 250))
+    assert ctx.variant == TILED
+    ctx.set_option("host_chunk_mb", 16)                 # several chunks in flight even at 1080p
+    sw, sh = w.src_size
+    rng = np.random.default_rng(17)
+    src_np = rng.integers(0, 256, (n,) + tuple(ctx.frame_shape("src")), dtype=np.uint8)
+    src = G.to_dev(src_np)
+    rdev = torch.empty(n * 9, dtype=torch.float32, device="cuda")
+    ctx.upload_rotations(rots, rdev)
+    dst = torch.empty((n,) + tuple(ctx.frame_shape("dst")), dtype=torch.uint8, device="cuda")
+    ctx.warp_batch(src, dst, rdev, n)
+    torch.cuda.synchronize()
+    want = dst.cpu().numpy()
+    out_np = np.zeros_like(want)
+    ctx.warp_batch_host(src_np, out_np, rots)
+    assert np.array_equal(out_np, want)
+    ctx.close()
+
+
 def test_clip_scheduler_frame_parallel(V, oracle):
     """vaw_clip_*: contiguous frame ranges on several contexts / host threads (two contexts on
     the one GPU here, two GPUs under `gpurun --gpus 2`) equal the single-context result."""
