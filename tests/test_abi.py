@@ -84,8 +84,11 @@ def test_create_validates_before_touching_cuda():
     with pytest.raises(V.VawError) as e:  # cv::INTER_AREA (FrameSourceWarp.hpp:90): not a remap filter, not implemented
         V.WarpContext(cam, out, interpolation=3)
     assert e.value.code == -4
-    with pytest.raises(V.VawError) as e:  # nearest / cubic run on variant GATHER only
-        V.WarpContext(cam, out, interpolation=V.INTER_CUBIC, variant=3)
+    with pytest.raises(V.VawError) as e:  # cubic / Lanczos4 are staged (variant TILED) for NV12 only, never on POLY
+        V.WarpContext(cam, out, fmt=V.FORMAT_BGR24, interpolation=V.INTER_CUBIC, variant=3)
+    assert e.value.code == -4
+    with pytest.raises(V.VawError) as e:
+        V.WarpContext(cam, out, interpolation=V.INTER_CUBIC, variant=2)
     assert e.value.code == -4
     with pytest.raises(V.VawError) as e:  # NV12 needs even sizes
         V.WarpContext(cam, out, out_size=(1759, 998))

@@ -1333,34 +1333,32 @@ def test_inter_nearest(V, oracle, fmt, variant):
     ctx.close()
     with pytest.raises(V.VawError):
         V.WarpContext(w.input_camera, w.output_camera, out_size=w.out_size, interpolation=V.INTER_NEAREST, variant=POLY)
-    with pytest.raises(V.VawError):
-        V.WarpContext(w.input_camera, w.output_camera, out_size=w.out_size, interpolation=V.INTER_CUBIC, variant=TILED)
+    with pytest.raises(V.VawError):  # the table filters are staged for NV12 only
+        V.WarpContext(w.input_camera, w.output_camera, fmt=V.FORMAT_BGR24, interpolation=V.INTER_CUBIC, variant=TILED)
 
 
 @pytest.mark.parametrize("interp", ["cubic", "lanczos4"])
-@pytest.mark.parametrize("fmt", ["nv12", "bgr"])
+@pytest.mark.parametrize("fmt", ["nv12", "nv12-gather", "bgr"])
 def test_inter_cubic(V, oracle, fmt, interp):
     """cv::INTER_CUBIC / cv::INTER_LANCZOS4 for FrameSourceWarp's `interpolation` parameter (FrameSourceWarp.hpp:90):
     cv::remap's 4 x 4 / 8 x 8 fixed-point filters (oracle/remap_cubic_ref.c, pinned on the real cv2.remap) on the
-    kernel's own map.  0 LSB, white noise (overshoot and saturation included), border-straddling pixels included."""
+    kernel's own map.  0 LSB, white noise (overshoot and saturation included), border-straddling pixels included.
+    NV12: AUTO = the staged-tile kernel (tiles with the filter's halo); variant GATHER = per-pixel taps."""
     import torch
     from video_annotator_b200 import configs
     w = configs.workload("C1")
     sw, sh = w.src_size
     R = rotation_xyz(1.0, -2.0, 0.5)
     flag, kw = (V.INTER_CUBIC, {"cubic": True}) if interp == "cubic" else (V.INTER_LANCZOS4, {"lanczos4": True})
-    if fmt == "nv12":
+    if fmt.startswith("nv12"):
         border = (16, 128, 128)
+        variant = GATHER if fmt == "nv12-gather" else 0
         ctx = V.WarpContext(w.input_camera, w.output_camera, out_size=w.out_size, border=border,
-                            interpolation=flag)
-        assert ctx.variant == GATHER
+                            interpolation=flag, variant=variant)
+        assert ctx.variant == (GATHER if variant else TILED)
         src = oracle.synth_nv12(sw, sh, 4, white_noise=True)
         got = _warp_one(V, ctx, src, R)
-        mx, my = [t.cpu().numpy() for t in ctx.dump_coords(R, 0)]
-        cx, cy = [t.cpu().numpy() for t in ctx.dump_coords(R, 1)]
-        y = oracle.remap_u8(src[:sh], mx, my, border=border[:1], threads=NCPU, **kw)
-        uv = oracle.remap_u8(src[sh:].reshape(sh // 2, sw // 2, 2), cx, cy, border=border[1:3], threads=NCPU, **kw)
-        ref = np.concatenate([y, uv.reshape(y.shape[0] // 2, y.shape[1])], axis=0)
+        ref = _table_filter_on_own_map(oracle, ctx, src, sw, sh, R, border, kw)
         assert np.array_equal(got, ref)
     else:
         ow, oh = w.output_camera.size
@@ -1375,4 +1373,53 @@ def test_inter_cubic(V, oracle, fmt, interp):
         mx, my = [t.cpu().numpy() for t in ctx.dump_coords(R, 0)]
         ref = oracle.remap_u8(src, mx, my, border=border, threads=NCPU, **kw)
         assert np.array_equal(dst.cpu().numpy(), ref.reshape(oh, ow, 3))
+    ctx.close()
+
+
+def _table_filter_on_own_map(oracle, ctx, src, sw, sh, R, border, kw):
+    """cv::remap's cubic / Lanczos4 filter (the oracle's) on the map the context samples with, NV12 planes."""
+    mx, my = [t.cpu().numpy() for t in ctx.dump_coords(R, 0)]
+    cx, cy = [t.cpu().numpy() for t in ctx.dump_coords(R, 1)]
+    y = oracle.remap_u8(src[:sh], mx, my, border=border[:1], threads=NCPU, **kw)
+    uv = oracle.remap_u8(src[sh:].reshape(sh // 2, sw // 2, 2), cx, cy, border=border[1:3], threads=NCPU, **kw)
+    return np.concatenate([y, uv.reshape(y.shape[0] // 2, y.shape[1])], axis=0)
+
+
+@pytest.mark.parametrize("case", ["4k-tilted", "4k-far", "ragged", "short-pieces"])
+@pytest.mark.parametrize("interp", ["cubic", "lanczos4"])
+def test_table_filters_staged(V, oracle, interp, case):
+    """INTER_CUBIC / INTER_LANCZOS4 on the staged-tile kernel beyond C1: 4K with rotations that bring border-straddling
+    and pure-border pieces in (the halo reaches outside the frame there), a large rotation (pieces whose box no longer
+    fits a tile take the per-pixel fallback), a ragged output size with pitched buffers, and a short focal length
+    (16-row pieces).  0 LSB against the oracle's filter on the kernel's own map; the two variants agree wherever their
+    maps round to the same 1/32-px bucket (spot check: they are the same filter)."""
+    import torch
+    from video_annotator_b200 import configs
+    flag, kw = (V.INTER_CUBIC, {"cubic": True}) if interp == "cubic" else (V.INTER_LANCZOS4, {"lanczos4": True})
+    border = (31, 90, 200)
+    if case in ("4k-tilted", "4k-far"):
+        w = configs.workload("C3")
+        R = rotation_xyz(-6.0, 4.0, -9.0) if case == "4k-tilted" else rotation_xyz(25.0, -30.0, 40.0)
+        out_size = w.out_size
+        cam_in, cam_out = w.input_camera, w.output_camera
+    elif case == "ragged":
+        w = configs.workload("C1")
+        R = rotation_xyz(3.0, 5.0, -7.0)
+        out_size = (1758 - 64, 998 - 36)  # 1694 x 962: the last piece column is 30 pixels wide, the last piece row 2 rows
+        cam_in, cam_out = w.input_camera, w.output_camera
+    else:
+        w = configs.workload("C1")
+        R = rotation_xyz(-2.0, 1.0, 3.0)
+        out_size = (642, 362)
+        f = w.output_camera.K[0, 0] * 0.78  # 16-row pieces (test_shorter_pieces_for_short_focal_lengths)
+        cam_in = w.input_camera
+        cam_out = V.Camera.from_matrix([[f, 0, (out_size[0] - 1) / 2.0], [0, f, (out_size[1] - 1) / 2.0], [0, 0, 1]], *out_size)
+    sw, sh = w.src_size
+    ctx = V.WarpContext(cam_in, cam_out, out_size=out_size, border=border, interpolation=flag)
+    assert ctx.variant == TILED
+    src = oracle.synth_nv12(sw, sh, 7, white_noise=True)
+    got = _warp_one(V, ctx, src, R)
+    ref = _table_filter_on_own_map(oracle, ctx, src, sw, sh, R, border, kw)
+    assert got.shape == ref.shape
+    assert np.array_equal(got, ref)
     ctx.close()

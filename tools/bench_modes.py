@@ -45,14 +45,19 @@ def main():
              ("NV12 nearest (staged-tile kernel, default)", V.FORMAT_NV12, V.INTER_NEAREST, 0),
              ("NV12 nearest, variant GATHER", V.FORMAT_NV12, V.INTER_NEAREST, 1),
              ("BGR24 nearest (staged-tile kernel, default)", V.FORMAT_BGR24, V.INTER_NEAREST, 0),
-             ("NV12 cubic", V.FORMAT_NV12, V.INTER_CUBIC, 0),
-             ("NV12 lanczos4", V.FORMAT_NV12, V.INTER_LANCZOS4, 0),
+             ("NV12 cubic (staged-tile kernel, default)", V.FORMAT_NV12, V.INTER_CUBIC, 0),
+             ("NV12 cubic, variant GATHER (per-pixel taps)", V.FORMAT_NV12, V.INTER_CUBIC, 1),
+             ("NV12 lanczos4 (staged-tile kernel, default)", V.FORMAT_NV12, V.INTER_LANCZOS4, 0),
+             ("NV12 lanczos4, variant GATHER (per-pixel taps)", V.FORMAT_NV12, V.INTER_LANCZOS4, 1),
              ("NV12 in -> BGR24 out, one launch (cvtColor + 3-channel remap fused, variant POLY)", V.FORMAT_NV12_TO_BGR24, V.INTER_LINEAR, 2),
              ("NV12 in -> BGR24 out, cvtColor into an L2-resident scratch + staged BGR kernel (variant TILED)", V.FORMAT_NV12_TO_BGR24, V.INTER_LINEAR, 3),
              ("BGR24 linear (the reference's literal format; staged-tile kernel, default)", V.FORMAT_BGR24, V.INTER_LINEAR, 0),
              ("BGR24 linear, variant GATHER (per-pixel taps)", V.FORMAT_BGR24, V.INTER_LINEAR, 1),
              ("GRAY8 linear (staged-tile kernel, default)", V.FORMAT_GRAY8, V.INTER_LINEAR, 0),
              ("GRAY8 linear, variant GATHER", V.FORMAT_GRAY8, V.INTER_LINEAR, 1)]
+    only = os.environ.get("VAW_BENCH_MODES")  # substring filter, e.g. "cubic": just those modes, no motion measurement
+    if only:
+        modes = [m for m in modes if any(k in m[0] for k in only.split(","))]
     for name, fmt, interp, variant in modes:
         try:
             ctx = V.WarpContext(w.input_camera, w.output_camera, fmt=fmt, out_size=w.out_size, variant=variant, interpolation=interp)
@@ -69,6 +74,9 @@ def main():
                     "algorithmic_bytes_per_frame": nbytes, "roofline_frac": round(nbytes * n / ms / 1e6 / PEAK, 4)})
         ctx.close()
         del src, dst
+    if only:
+        print(json.dumps({"workload": "C3 geometry, 16 frames per launch", "peak_gbs": PEAK, "modes": out}, indent=1))
+        return
     # motion measurement at 4K: pyramid + derivatives of a new frame, corners of the previous frame, 200 points tracked
     h, wd = 2160, 3840
     rng = np.random.default_rng(1)

@@ -78,6 +78,7 @@ struct vaw_ctx {
     int packed_next = 0;
     int map_next = 0;
     int tile_cap = 32 << 10;  // chosen at creation from the pieces' source boxes
+    int table_ctas = 0;       // INTER_CUBIC / INTER_LANCZOS4 on staged tiles: CTAs per SM the tile capacity was sized for
     // vaw_bind_clip: a slab of equally spaced source frames; launches inside it share its tensor maps
     const uint8_t* clip_base = nullptr;
     int clip_pitch = 0, clip_slots = 0;
@@ -243,6 +244,7 @@ const vaw::TileMaps& tile_maps(vaw_ctx* ctx, const uint8_t* src, int pitch, size
     e.src = src; e.pitch = pitch; e.stride = stride; e.frames = frames;
     e.maps.enabled = 0;
     e.maps.tile_cap = ctx->tile_cap;
+    e.maps.table_ctas = ctx->table_ctas;
     const int rows_total = ctx->p.src_height + ctx->p.src_height / 2;
     EncodeTiledFn enc = encode_tiled();
     const bool ok = enc && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (pitch & 15) == 0 && (stride & 15) == 0 &&
@@ -613,8 +615,18 @@ int choose_tile_cap(vaw_ctx* ctx)
         const int v = atoi(env);
         if (v >= 1 && v <= 32) ctas = v;
     }
+    // INTER_CUBIC / INTER_LANCZOS4: four CTAs per SM (128 registers each); more CTAs would leave L1 too small for the
+    // weight table (cubic, C3: 16.7 k frames/s at six CTAs = no L1 to speak of, 23.9 k at five, 24.3 k at four, 23.4 k at three)
+    if (ctx->gd.halo && !getenv("VAW_EXPERIMENT_MAX_CTAS")) ctas = 4;
     while (ctas > 1 && ctx->tile_need * 106 / 100 > vaw::tile_cap_for_ctas(ctas, book)) --ctas;
     long long cap = vaw::tile_cap_for_ctas(ctas, book);
+    if (ctx->gd.halo) {
+        // every sample of these filters reads its 32 / 128 bytes of weights (a 32 KB / 128 KB table) through L1: the tiles
+        // get what they need (+25 % for tilt) instead of the whole SM, the launcher leaves the rest to L1
+        const long long want = ((ctx->tile_need * 125 / 100 + 127) / 128) * 128;
+        if (want < cap && !getenv("VAW_EXPERIMENT_FULL_SMEM")) cap = want;
+        ctx->table_ctas = ctas;
+    }
     if (cap < vaw::kTileCapMin) cap = vaw::kTileCapMin;
     if (cap > vaw::kTileCapMax) cap = vaw::kTileCapMax;
     ctx->tile_cap = (int)cap;
@@ -682,9 +694,11 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
     if (p.interpolation != VAW_INTER_LINEAR && p.interpolation != VAW_INTER_NEAREST && p.interpolation != VAW_INTER_CUBIC &&
         p.interpolation != VAW_INTER_LANCZOS4)
         return fail(nullptr, VAW_ERR_UNSUPPORTED, "only INTER_NEAREST, INTER_LINEAR, INTER_CUBIC and INTER_LANCZOS4 are implemented");
+    const bool table_filter = p.interpolation == VAW_INTER_CUBIC || p.interpolation == VAW_INTER_LANCZOS4;
     if (p.interpolation != VAW_INTER_LINEAR && p.variant != VAW_VARIANT_AUTO && p.variant != VAW_VARIANT_GATHER &&
-        !(p.interpolation == VAW_INTER_NEAREST && p.variant == VAW_VARIANT_TILED))
-        return fail(nullptr, VAW_ERR_UNSUPPORTED, "INTER_CUBIC and INTER_LANCZOS4 run on variant GATHER (or AUTO); INTER_NEAREST on GATHER or TILED");
+        !(p.interpolation == VAW_INTER_NEAREST && p.variant == VAW_VARIANT_TILED) &&
+        !(table_filter && p.variant == VAW_VARIANT_TILED && p.format == VAW_FORMAT_NV12))
+        return fail(nullptr, VAW_ERR_UNSUPPORTED, "INTER_NEAREST runs on GATHER or TILED; INTER_CUBIC and INTER_LANCZOS4 on GATHER, and on TILED for NV12 (AUTO picks)");
     if (p.format != VAW_FORMAT_NV12 && p.format != VAW_FORMAT_BGR24 && p.format != VAW_FORMAT_GRAY8 &&
         p.format != VAW_FORMAT_NV12_TO_BGR24)
         return fail(nullptr, VAW_ERR_INVALID, "unknown pixel format");
@@ -777,7 +791,8 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
     }
     // AUTO: the staged-tile kernels wherever they exist (INTER_LINEAR: NV12 -> vaw_tile.cu, GRAY8 / BGR24 -> vaw_packed_tile.cu)
     ctx->variant = p.variant != VAW_VARIANT_AUTO ? p.variant
-                   : ((p.interpolation == VAW_INTER_LINEAR || (p.interpolation == VAW_INTER_NEAREST && p.projection == 0))
+                   : ((p.interpolation == VAW_INTER_LINEAR || (p.interpolation == VAW_INTER_NEAREST && p.projection == 0) ||
+                       (table_filter && p.format == VAW_FORMAT_NV12 && p.projection == 0))
                           ? VAW_VARIANT_TILED : VAW_VARIANT_GATHER);
     // (NV12 -> BGR24: TILED = cvtColor into an L2-resident scratch + the staged BGR kernel, 30.9 k frames/s at 4K;
     //  POLY = everything in one launch with per-tap conversion, 13.8 k)
@@ -814,6 +829,8 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
         d.has_dist = g.has_dist;
         d.src_w = g.src_w; d.src_h = g.src_h; d.out_w = g.out_w; d.out_h = g.out_h;
         d.projection = p.projection;
+        // INTER_CUBIC / INTER_LANCZOS4 on staged tiles (NV12): the boxes carry the filter's halo
+        d.halo = (table_filter && ctx->variant == VAW_VARIANT_TILED) ? (p.interpolation == VAW_INTER_CUBIC ? 1 : 3) : 0;
         set_piece_rows(ph);
         e = cudaEventCreateWithFlags(&ctx->table_free, cudaEventDisableTiming);
         // (room for the same frame cut into 16-row pieces: BGR24 may fall back to them below)
@@ -845,7 +862,7 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
                 const vaw::PieceRec* rec = reinterpret_cast<const vaw::PieceRec*>(host.data());
                 long long need = 0;
                 for (size_t i = 0; i < ctx->pieces_per_frame; ++i) {
-                    const int nb = packed_fmt ? vaw::packed_tile_need_bytes(rec[i], tile_channels) : vaw::tile_need_bytes(rec[i]);
+                    const int nb = packed_fmt ? vaw::packed_tile_need_bytes(rec[i], tile_channels) : vaw::tile_need_bytes(rec[i], ctx->gd.halo);
                     if (nb != 0x7fffffff && nb > need) need = nb;
                 }
                 ctx->tile_need = need;
@@ -1263,7 +1280,7 @@ int vaw_piece_stats(vaw_ctx* ctx, const double rotation[9], uint32_t counts[8], 
         if (rec[i].flags & vaw::kPieceInterior) counts[2]++;
         if (rec[i].flags & vaw::kPieceOutside) counts[3]++;
         const bool packed = ctx->p.format == VAW_FORMAT_BGR24 || ctx->p.format == VAW_FORMAT_GRAY8;
-        const int nb = packed ? vaw::packed_tile_need_bytes(rec[i], ctx->channels) : vaw::tile_need_bytes(rec[i]);
+        const int nb = packed ? vaw::packed_tile_need_bytes(rec[i], ctx->channels) : vaw::tile_need_bytes(rec[i], ctx->gd.halo);
         if (nb > 0 && (nb > ctx->tile_cap)) counts[6]++;
         if (nb != 0x7fffffff && (uint32_t)nb > counts[4]) counts[4] = (uint32_t)nb;
     }
@@ -1313,7 +1330,7 @@ int vaw_piece_tiles(vaw_ctx* ctx, const double rotation[9], uint32_t* out, int c
     for (size_t i = 0; i < ctx->pieces_per_frame; ++i) {
         out[4 * i + 0] = rec[i].flags;
         const bool packed = ctx->p.format == VAW_FORMAT_BGR24 || ctx->p.format == VAW_FORMAT_GRAY8;
-        out[4 * i + 1] = (uint32_t)(packed ? vaw::packed_tile_need_bytes(rec[i], ctx->channels) : vaw::tile_need_bytes(rec[i]));
+        out[4 * i + 1] = (uint32_t)(packed ? vaw::packed_tile_need_bytes(rec[i], ctx->channels) : vaw::tile_need_bytes(rec[i], ctx->gd.halo));
         out[4 * i + 2] = rec[i].stage.pl;
         out[4 * i + 3] = (uint32_t)rec[i].stage.nrows | ((uint32_t)rec[i].stage.cnrows << 16);
     }

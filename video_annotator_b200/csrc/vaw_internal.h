@@ -46,14 +46,15 @@ struct alignas(64) TileMaps {
     CUtensorMap m4[kTileWidths];   // boxes of 4 rows (tile rows come in multiples of 4)
     int enabled;   // 0: no maps (layout not TMA-compatible) -> every piece gathers from global memory
     int tile_cap;  // bytes of shared memory for the luma + chroma tile of one CTA
-    int pad[14];
+    int table_ctas;  // INTER_CUBIC / INTER_LANCZOS4: CTAs per SM the capacity was sized for (the launcher's L1 / shared split)
+    int pad[13];
 };
 // Tile capacity that lets `ctas` CTAs of the tile kernel share one SM: 227 KB of shared memory, 1 KB
 // reserved per CTA by the system, 128 bytes of the kernel's own bookkeeping; a multiple of 128.
 constexpr int kSmemPerSM = 227 << 10;
 inline int tile_cap_for_ctas(int ctas, int bookkeeping) { return ((kSmemPerSM / ctas - 1024 - bookkeeping) / 128) * 128; }
 // bytes of tile a piece needs for its source box (what the kernel computes), 0 if it has none
-int tile_need_bytes(const PieceRec& rec);
+int tile_need_bytes(const PieceRec& rec, int halo = 0);  // halo = GeomD::halo the table was built with
 // dynamic shared memory of the tile kernel for a given tile capacity
 int tile_smem_bytes(int tile_cap);
 // out-of-tile tap count of the instrumented build (-DVAW_BOUNDS_CHECK), -1 when not instrumented

@@ -198,17 +198,19 @@ build_pieces_kernel(const GeomD g, const PieceBasis basis, const float* __restri
         if (ok) {
             flags |= kPiecePoly;
             const double W = g.src_w, H = g.src_h;
-            // luma taps ix, ix+1 in [0, W-1]  <=>  0 <= m < W-1;  chroma: 0.5 <= mean < W-1.5
-            if (lo[0] >= 0.55 && hi[0] <= W - 1.55 && lo[1] >= 0.55 && hi[1] <= H - 1.55) flags |= kPieceInterior;
+            // luma taps ix, ix+1 in [0, W-1]  <=>  0 <= m < W-1;  chroma: 0.5 <= mean < W-1.5.  With a halo of h taps per
+            // side (INTER_CUBIC 1, INTER_LANCZOS4 3) the luma range shrinks by h, the chroma range by 2 h luma pixels.
+            const double h = (double)g.halo, h2 = 2.0 * h;
+            if (lo[0] >= 0.55 + h2 && hi[0] <= W - 1.55 - h2 && lo[1] >= 0.55 + h2 && hi[1] <= H - 1.55 - h2) flags |= kPieceInterior;
             // every luma and chroma tap outside in x, or in y
-            if (hi[0] < -1.6 || lo[0] > W + 0.55 || hi[1] < -1.6 || lo[1] > H + 0.55) flags |= kPieceOutside;
+            if (hi[0] < -1.6 - h2 || lo[0] > W + 0.55 + h2 || hi[1] < -1.6 - h2 || lo[1] > H + 0.55 + h2) flags |= kPieceOutside;
             if (!(flags & kPieceOutside)) {
-                // source rectangle of the taps (for the shared-memory staging): luma taps floor(m),
-                // floor(m)+1; chroma coordinate = (mean - 0.5) / 2
-                box.x0 = (int16_t)floor(lo[0] - 0.01); box.x1 = (int16_t)(floor(hi[0] + 0.01) + 1.0);
-                box.y0 = (int16_t)floor(lo[1] - 0.01); box.y1 = (int16_t)(floor(hi[1] + 0.01) + 1.0);
-                box.cx0 = (int16_t)floor((lo[0] - 0.5) * 0.5 - 0.01); box.cx1 = (int16_t)(floor((hi[0] - 0.5) * 0.5 + 0.01) + 1.0);
-                box.cy0 = (int16_t)floor((lo[1] - 0.5) * 0.5 - 0.01); box.cy1 = (int16_t)(floor((hi[1] - 0.5) * 0.5 + 0.01) + 1.0);
+                // source rectangle of the taps (for the shared-memory staging): luma taps floor(m) - h ...
+                // floor(m) + 1 + h; chroma coordinate = (mean - 0.5) / 2
+                box.x0 = (int16_t)(floor(lo[0] - 0.01) - h); box.x1 = (int16_t)(floor(hi[0] + 0.01) + 1.0 + h);
+                box.y0 = (int16_t)(floor(lo[1] - 0.01) - h); box.y1 = (int16_t)(floor(hi[1] + 0.01) + 1.0 + h);
+                box.cx0 = (int16_t)(floor((lo[0] - 0.5) * 0.5 - 0.01) - h); box.cx1 = (int16_t)(floor((hi[0] - 0.5) * 0.5 + 0.01) + 1.0 + h);
+                box.cy0 = (int16_t)(floor((lo[1] - 0.5) * 0.5 - 0.01) - h); box.cy1 = (int16_t)(floor((hi[1] - 0.5) * 0.5 + 0.01) + 1.0 + h);
             }
         }
         rec.flags = flags;

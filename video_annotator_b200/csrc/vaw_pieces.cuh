@@ -88,6 +88,9 @@ struct GeomD {  // the 8 fp32 scalars of FrameSourceWarp.cpp:283-290, widened ex
     int has_dist;  // any kd != 0
     int tile_cap;  // bytes of shared memory a tile may take with a 128-byte-multiple pitch (0: always the tightest pitch)
     int projection;  // 0 = createMap.cl (fisheye in, rectilinear out); bit 0: rectilinear input; bit 1: fisheye output
+    int halo;  // extra taps on every side of the bilinear pair that the staged sampler reads: 0 (INTER_LINEAR / INTER_NEAREST),
+               // 1 (INTER_CUBIC: 4 x 4 taps from floor - 1) or 3 (INTER_LANCZOS4: 8 x 8 taps from floor - 3); the source boxes
+               // and the interior / outside classification of the pieces account for it
 };
 
 inline __host__ __device__ int pieces_x(int out_w) { return (out_w + kPieceW - 1) / kPieceW; }

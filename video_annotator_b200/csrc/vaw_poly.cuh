@@ -10,6 +10,7 @@
 #include "vaw_coords.cuh"
 #include "vaw_pieces.cuh"
 #include "vaw_sample.cuh"
+#include "vaw_cubic.cuh"
 #include "vaw_internal.h"
 #include "vaw_project64.cuh"
 
@@ -203,13 +204,15 @@ struct PlaneRefs {
     uint8_t* dst;       // output frame
 };
 
-// Checked sampling of one row pair from given coordinates (mixed pieces, per-pixel fallback).  kNearest: cv::INTER_NEAREST
+// Checked sampling of one row pair from given coordinates (mixed pieces, per-pixel fallback).  kMode 1: cv::INTER_NEAREST
 // = the same integer filter on coordinates rounded to whole pixels (luma: the map values; chroma: the chroma
-// coordinate derived from the UNROUNDED luma map).
-template <bool kNearest = false>
+// coordinate derived from the UNROUNDED luma map); kMode 2: the context's INTER_CUBIC / INTER_LANCZOS4 table filter.
+enum { kModeLinear = 0, kModeNearest = 1, kModeTable = 2 };
+template <int kMode = kModeLinear>
 __device__ __forceinline__ void sample_rows_checked(const Geom& g, const PlaneRefs& f, int u0, int v0,
                                                     const float2 (&m)[2][4])
 {
+    constexpr bool kNearest = kMode == kModeNearest;
     const int border_y = g.border & 255;
     const unsigned border_uv = (g.border >> 8) & 0xffffu;
     const int valid = g.out_w - u0;
@@ -217,16 +220,23 @@ __device__ __forceinline__ void sample_rows_checked(const Geom& g, const PlaneRe
 #pragma unroll
     for (int r = 0; r < 2; ++r)
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-            yw[r] |= (unsigned)sample_c1(f.y, g.src_pitch, g.src_w, g.src_h, kNearest ? nearest_coord(m[r][i].x) : m[r][i].x,
-                                         kNearest ? nearest_coord(m[r][i].y) : m[r][i].y, border_y) << (8 * i);
+        for (int i = 0; i < 4; ++i) {
+            if (kMode == kModeTable)
+                yw[r] |= sample_hi<1>(f.y, g.src_pitch, g.src_w, g.src_h, m[r][i].x, m[r][i].y, (unsigned)border_y, g.cubic_tab, g.tab_ks) << (8 * i);
+            else
+                yw[r] |= (unsigned)sample_c1(f.y, g.src_pitch, g.src_w, g.src_h, kNearest ? nearest_coord(m[r][i].x) : m[r][i].x,
+                                             kNearest ? nearest_coord(m[r][i].y) : m[r][i].y, border_y) << (8 * i);
+        }
     unsigned cw = 0u;
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
         const float cx = chroma_coord(m[0][2 * q].x, m[0][2 * q + 1].x, m[1][2 * q].x, m[1][2 * q + 1].x);
         const float cy = chroma_coord(m[0][2 * q].y, m[0][2 * q + 1].y, m[1][2 * q].y, m[1][2 * q + 1].y);
-        cw |= sample_c2(f.uv, g.src_pitch, g.src_w >> 1, g.src_h >> 1, kNearest ? nearest_coord(cx) : cx,
-                        kNearest ? nearest_coord(cy) : cy, border_uv) << (16 * q);
+        if (kMode == kModeTable)
+            cw |= sample_hi<2>(f.uv, g.src_pitch, g.src_w >> 1, g.src_h >> 1, cx, cy, border_uv, g.cubic_tab, g.tab_ks) << (16 * q);
+        else
+            cw |= sample_c2(f.uv, g.src_pitch, g.src_w >> 1, g.src_h >> 1, kNearest ? nearest_coord(cx) : cx,
+                            kNearest ? nearest_coord(cy) : cy, border_uv) << (16 * q);
     }
     if (valid > 0) {
         store_word<true>(f.dst + (size_t)v0 * g.dst_pitch + u0, yw[0], valid);

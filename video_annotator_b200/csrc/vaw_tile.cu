@@ -86,7 +86,9 @@ using TapConst = FloorConst;
 using TapConst = unsigned;
 #endif
 
-template <bool kRagged, bool kNearest>
+// kMode: 0 cv::INTER_LINEAR, 1 cv::INTER_NEAREST, 2 cv::INTER_CUBIC, 3 cv::INTER_LANCZOS4 (2, 3: vaw_tile.cuh's table samplers
+// on tiles staged with a halo)
+template <bool kRagged, int kMode>
 __device__ __forceinline__ void rows_quad(const Geom& g, const ColPoly2& cp, const TapConst& lconst, const TapConst& cconst, unsigned pl,
                                           int dv0, int nrows, uint8_t* __restrict__ py, uint8_t* __restrict__ pc,
                                           bool inside, const TileBounds& tb)
@@ -118,7 +120,12 @@ __device__ __forceinline__ void rows_quad(const Geom& g, const ColPoly2& cp, con
         const float2 m10 = col_coord(cp.a[0], cp.base, t1), m11 = col_coord(cp.a[1], cp.base, t1);
 #if VAW_SAMPLER == 3
         unsigned y00, y01, y10, y11, c;
-        if (kNearest) {  // cv::INTER_NEAREST: one tap per sample (lconst / cconst carry the nearest row constants)
+        if (kMode >= 2) {  // cv::INTER_CUBIC / cv::INTER_LANCZOS4: lconst / cconst carry the block's top-left tap
+            constexpr int kKs = kMode == 2 ? 4 : 8;
+            y00 = luma_tile_hi<kKs>(lconst, pl, m00, g.cubic_tab, tb); y01 = luma_tile_hi<kKs>(lconst, pl, m01, g.cubic_tab, tb);
+            y10 = luma_tile_hi<kKs>(lconst, pl, m10, g.cubic_tab, tb); y11 = luma_tile_hi<kKs>(lconst, pl, m11, g.cubic_tab, tb);
+            c = chroma_tile_hi<kKs>(cconst, pl, chroma_z(m00, m01, m10, m11), g.cubic_tab, tb);
+        } else if (kMode == 1) {  // cv::INTER_NEAREST: one tap per sample (lconst / cconst carry the nearest row constants)
             y00 = luma_tile_nearest(lconst.row0, pl, m00); y01 = luma_tile_nearest(lconst.row0, pl, m01);
             y10 = luma_tile_nearest(lconst.row0, pl, m10); y11 = luma_tile_nearest(lconst.row0, pl, m11);
             c = chroma_tile_nearest(cconst.row0, pl, chroma_z(m00, m01, m10, m11));
@@ -158,7 +165,7 @@ __device__ __forceinline__ void rows_quad(const Geom& g, const ColPoly2& cp, con
 // 0.736 ms against 0.660 ms -- more instructions, not fewer, and longer tile waits)  `rec` = the same record in the table (the gather fallbacks read it from there);
 // `tile_parity` = phase of the tile mbarrier (smem + 0) this piece's loads complete.  Returns whether the piece was staged
 // (i.e. whether that phase was consumed).
-template <bool kNearest>
+template <int kMode>
 __device__ __forceinline__ bool quad_piece(const Geom& g, const FrameBatch& b, const PieceRec* __restrict__ rec,
                                            const PieceRec* rs, const TileMaps& maps, uint8_t* smem, int px, int py,
                                            int frame, unsigned tile_parity, int lane, int w, int tid)
@@ -208,7 +215,11 @@ __device__ __forceinline__ bool quad_piece(const Geom& g, const FrameBatch& b, c
     const int lx0 = (int16_t)(raw.x & 0xffff), by0 = raw.x >> 16;
     const int cbx0 = (int16_t)(raw.y & 0xffff), cy0 = raw.y >> 16;
     const int pl = raw.z & 0xffff, nrows = (raw.z >> 16) & 0xffff, cnrows = raw.w & 0xffff;
-    const bool staged = (flags & kPiecePoly) && maps.enabled && pl != 0 && pl * (nrows + cnrows) <= maps.tile_cap;
+    constexpr bool kNearest = kMode == 1;
+    constexpr int kChecked = kMode >= 2 ? (int)kModeTable : kMode;  // the per-pixel fallbacks' filter
+    constexpr int kHalo = kMode == 2 ? 1 : (kMode == 3 ? 3 : 0);    // = GeomD::halo of the builder
+    const bool staged = (flags & kPiecePoly) && maps.enabled && pl != 0 &&
+                        pl * (nrows + cnrows) + (kMode >= 2 ? kTileSlack : 0) <= maps.tile_cap;
 
     if (!staged) {
         // pieces without a polynomial certificate or whose box does not fit the tile: the gather paths of
@@ -225,13 +236,13 @@ __device__ __forceinline__ bool quad_piece(const Geom& g, const FrameBatch& b, c
             for (int dv = dv0; dv < dv0 + my_rows; dv += 2) {
                 float2 m[2][4];
                 exact_rows(g, R, u_lo, u0, v_base + dv, m);
-                sample_rows_checked<kNearest>(g, f, u0, v_base + dv, m);
+                sample_rows_checked<kChecked>(g, f, u0, v_base + dv, m);
             }
             return false;
         }
         ColPoly cp;
         derive(rec, lane, cp);
-        if (!kNearest && (flags & kPieceInterior)) {
+        if (kMode == 0 && (flags & kPieceInterior)) {
             RowPtrs o;
             o.y0 = dst + (size_t)(v_base + dv0) * g.dst_pitch + u0;
             o.y1 = o.y0 + g.dst_pitch;
@@ -247,7 +258,7 @@ __device__ __forceinline__ bool quad_piece(const Geom& g, const FrameBatch& b, c
                 float2 m[2][4];
                 row_coords(cp, row_t(g, dv), m[0]);
                 row_coords(cp, row_t(g, dv + 1), m[1]);
-                sample_rows_checked<kNearest>(g, f, u0, v_base + dv, m);
+                sample_rows_checked<kChecked>(g, f, u0, v_base + dv, m);
             }
         }
         return false;
@@ -334,8 +345,8 @@ __device__ __forceinline__ bool quad_piece(const Geom& g, const FrameBatch& b, c
 #else
     const unsigned vnever = never;
 #endif
-    const FloorConst lconst = floor_const(-lx0, -by0, smem_u32(ltile) - 0x40000000u, upl, __uint_as_float(0x42000000u | vnever), (unsigned)raw.w >> 31);  // (the stage's zero pad: with g.out_w >> 31 ptxas keeps the luma pair in vector registers)
-    const FloorConst cconst = floor_const(-(cbx0 >> 1), -cy0, smem_u32(ctile) - 0x80000000u, upl, __uint_as_float(0x41800000u | vnever), never);
+    const FloorConst lconst = floor_const(-lx0 - kHalo, -by0 - kHalo, smem_u32(ltile) - 0x40000000u, upl, __uint_as_float(0x42000000u | vnever), (unsigned)raw.w >> 31);  // (the stage's zero pad: with g.out_w >> 31 ptxas keeps the luma pair in vector registers)
+    const FloorConst cconst = floor_const(-(cbx0 >> 1) - kHalo, -cy0 - kHalo, smem_u32(ctile) - 0x80000000u, upl, __uint_as_float(0x41800000u | vnever), never);
     // INTER_NEAREST: the row constants of luma_tile_nearest / chroma_tile_nearest instead (same uniform-register treatment)
     const FloorConst lnear = floor_const(0, 0, smem_u32(ltile) - (unsigned)by0 * upl - (unsigned)lx0 - (unsigned)kMagicBits * (upl + 1u), upl, 0.f, (unsigned)raw.w >> 31);
     const FloorConst cnear = floor_const(0, 0, smem_u32(ctile) - (unsigned)cy0 * upl - (unsigned)cbx0 - (unsigned)kMagicBits * (upl + 2u), upl, 0.f, never);
@@ -353,13 +364,13 @@ __device__ __forceinline__ bool quad_piece(const Geom& g, const FrameBatch& b, c
     uint8_t* const oc = dst + (size_t)(g.out_h + ((v_base + dv0) >> 1)) * g.dst_pitch + u0;
 #if VAW_SAMPLER == 3
     if (kNearest) {
-        if (pair_ok) rows_quad<false, true>(g, cp, lnear, cnear, upl, dv0, my_rows, oy, oc, inside, tb);
-        else rows_quad<true, true>(g, cp, lnear, cnear, upl, dv0, my_rows, oy, oc, inside, tb);
+        if (pair_ok) rows_quad<false, 1>(g, cp, lnear, cnear, upl, dv0, my_rows, oy, oc, inside, tb);
+        else rows_quad<true, 1>(g, cp, lnear, cnear, upl, dv0, my_rows, oy, oc, inside, tb);
         return true;
     }
 #endif
-    if (pair_ok) rows_quad<false, false>(g, cp, lconst, cconst, upl, dv0, my_rows, oy, oc, inside, tb);
-    else rows_quad<true, false>(g, cp, lconst, cconst, upl, dv0, my_rows, oy, oc, inside, tb);
+    if (pair_ok) rows_quad<false, kMode>(g, cp, lconst, cconst, upl, dv0, my_rows, oy, oc, inside, tb);
+    else rows_quad<true, kMode>(g, cp, lconst, cconst, upl, dv0, my_rows, oy, oc, inside, tb);
     return true;  // this piece's loads completed a phase of the tile mbarrier
 }
 
@@ -367,7 +378,7 @@ __device__ __forceinline__ bool quad_piece(const Geom& g, const FrameBatch& b, c
 // the C3 tiles let seven CTAs share an SM, and the eight registers the 64-register build gives away buy nothing
 // there -- measured 0.651 against 0.661 ms) or 6 (80 registers, no spills in the fallback paths) where shared
 // memory allows six or fewer anyway (C5 +2.6 %, C2 +3 %).
-template <int kCtas, bool kNearest = false>
+template <int kCtas, int kMode = 0>
 __global__ void __launch_bounds__(32 * kWarps, kCtas)
 warp_nv12_quad_kernel(const Geom g, const FrameBatch b, const PieceRec* __restrict__ table,
                       const __grid_constant__ TileMaps maps)
@@ -405,7 +416,7 @@ warp_nv12_quad_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
     mbar_wait_parked(mbar_rec, 0, 4000);
 #endif
     const PieceRec* rs = reinterpret_cast<const PieceRec*>(smem + kQuadRecOffset);
-    quad_piece<kNearest>(g, b, rec, rs, maps, smem, px, py, frame, 0u, lane, w, tid);
+    quad_piece<kMode>(g, b, rec, rs, maps, smem, px, py, frame, 0u, lane, w, tid);
 }
 
 long long tile_oob_count()
@@ -422,7 +433,7 @@ long long tile_oob_count()
 int tile_smem_bytes(int tile_cap) { return kQuadTileOffset + tile_cap; }
 
 // Host mirror of the kernel's tile sizing (same integer arithmetic).
-int tile_need_bytes(const PieceRec& rec)
+int tile_need_bytes(const PieceRec& rec, int halo)
 {
     if (!(rec.flags & kPiecePoly) || (rec.flags & kPieceOutside)) return 0;
     const PieceBox& b = rec.box;
@@ -431,17 +442,18 @@ int tile_need_bytes(const PieceRec& rec)
     const int nrows = (b.y1 - b.y0 + 4) & ~3, cnrows = (b.cy1 - b.cy0 + 4) & ~3;
     const int pl = std::max(kTileMinPitch, (std::max(wb, cwb) + 31) & ~31);
     if (pl > kTileMaxPitch || nrows <= 0 || cnrows <= 0) return 0x7fffffff;
-    return pl * (nrows + cnrows);
+    return pl * (nrows + cnrows) + (halo ? kTileSlack : 0);  // (the box already includes the halo: GeomD::halo)
 }
 
-template <int kCtas, bool kNearest = false>
+constexpr int kCubicCtas = 4, kLanczosCtas = 4;  // register budget of the table-filter instantiations (128: vaw_api.cu's choose_tile_cap sizes for four CTAs)
+template <int kCtas, int kMode = 0>
 static cudaError_t configure_quad()
 {
-    cudaError_t e = cudaFuncSetAttribute(warp_nv12_quad_kernel<kCtas, kNearest>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(warp_nv12_quad_kernel<kCtas, kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          tile_smem_bytes(kTileCapMax));
     // all of the SM's shared memory for tiles: the taps never go through L1
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(warp_nv12_quad_kernel<kCtas, kNearest>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        e = cudaFuncSetAttribute(warp_nv12_quad_kernel<kCtas, kMode>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     return e;
 }
 cudaError_t launch_warp_nv12_tile(const Geom& g, const FrameBatch& b, const PieceRec* table, const TileMaps& maps,
@@ -457,7 +469,9 @@ cudaError_t launch_warp_nv12_tile(const Geom& g, const FrameBatch& b, const Piec
         cudaError_t e = configure_quad<8>();
         if (e == cudaSuccess) e = configure_quad<7>();
         if (e == cudaSuccess) e = configure_quad<6>();
-        if (e == cudaSuccess) e = configure_quad<8, true>();
+        if (e == cudaSuccess) e = configure_quad<8, 1>();
+        if (e == cudaSuccess) e = configure_quad<kCubicCtas, 2>();
+        if (e == cudaSuccess) e = configure_quad<kLanczosCtas, 3>();
         if (e != cudaSuccess) return e;
         if (tracked) configured[dev].store(true, std::memory_order_release);
     }
@@ -466,7 +480,21 @@ cudaError_t launch_warp_nv12_tile(const Geom& g, const FrameBatch& b, const Piec
     // the instantiation whose register budget matches the CTAs the tile capacity lets share an SM
     const int smem = tile_smem_bytes(maps.tile_cap);
     // cv::INTER_NEAREST: one light instantiation (64 registers are plenty for one tap per sample)
-    if (g.nearest) warp_nv12_quad_kernel<8, true><<<grid, block, smem, st>>>(g, b, table, maps);
+    // cv::INTER_CUBIC / cv::INTER_LANCZOS4: one instantiation each
+    if (g.cubic_tab) {
+        // shared memory for the resident CTAs' tiles, the rest of the SM's 256 KB to L1 (the weight table lives there)
+        const int smem_h = smem;  // (the slack behind the last tile row is part of the tile capacity: quad_piece, tile_need_bytes)
+        int pct = (int)(((long long)std::max(1, maps.table_ctas) * (smem_h + 1024) * 100 + (kSmemPerSM - 1)) / kSmemPerSM);
+        if (getenv("VAW_EXPERIMENT_FULL_SMEM")) pct = 100;
+        pct = std::min(100, std::max(1, pct));
+        cudaError_t e = g.tab_ks == 4
+            ? cudaFuncSetAttribute(warp_nv12_quad_kernel<kCubicCtas, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, pct)
+            : cudaFuncSetAttribute(warp_nv12_quad_kernel<kLanczosCtas, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        if (e != cudaSuccess) return e;
+        if (g.tab_ks == 4) warp_nv12_quad_kernel<kCubicCtas, 2><<<grid, block, smem_h, st>>>(g, b, table, maps);
+        else warp_nv12_quad_kernel<kLanczosCtas, 3><<<grid, block, smem_h, st>>>(g, b, table, maps);
+    }
+    else if (g.nearest) warp_nv12_quad_kernel<8, 1><<<grid, block, smem, st>>>(g, b, table, maps);
     else if (maps.tile_cap <= tile_cap_for_ctas(8, kQuadTileOffset)) warp_nv12_quad_kernel<8><<<grid, block, smem, st>>>(g, b, table, maps);
     else if (maps.tile_cap <= tile_cap_for_ctas(7, kQuadTileOffset)) warp_nv12_quad_kernel<7><<<grid, block, smem, st>>>(g, b, table, maps);
     else warp_nv12_quad_kernel<6><<<grid, block, smem, st>>>(g, b, table, maps);

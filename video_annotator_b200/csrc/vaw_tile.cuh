@@ -190,6 +190,124 @@ __device__ __forceinline__ unsigned chroma_tile_nearest(unsigned row, unsigned p
     return lds_u16<0>(imad_u32(__float_as_uint(s.x), 2u, __float_as_uint(s.y) * pl) + row);
 }
 
+// ---- cv::INTER_CUBIC / cv::INTER_LANCZOS4 from the staged tile (FrameSourceWarp.hpp:90's `interpolation`) ---------
+// cv::remap's kKs x kKs fixed-point filter (vaw_cubic.cuh has the scheme and the weight tables): the coordinate is
+// rounded to 1/32 px exactly as for the bilinear filter, the block of taps starts kKs / 2 - 1 samples up and left of
+// floor(), the kKs^2 weights (shorts scaled by 2^15, one table entry per pair of 5-bit fractions) come from global
+// memory through L1 (16-byte loads), the result is saturate_cast<uchar>((sum + 2^14) >> 15).  The piece's tile was
+// staged with that halo (GeomD::halo), border cells painted, so there are no range tests here either.
+//   * taps: a row of kKs bytes starts at an arbitrary byte address -> the aligned words around it (kKs / 4 + 1 LDS.32)
+//     and one funnel shift per word put the row into registers four taps at a time;
+//   * multiply-accumulate: IDP.2A with signed 16-bit weight pairs against unsigned tap bytes (dp2a.lo / .hi): two taps per
+//     instruction, the accumulator threaded through.
+// The aligned loads read up to 4 bytes past the last tap of a row (into the next tile row, or into the kTileSlack
+// bytes behind the tile).
+constexpr int kTileSlack = 16;
+
+__device__ __forceinline__ unsigned lds_w32(unsigned addr)
+{
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+// c + w.lo16 * t.byte0 + w.hi16 * t.byte1 (weights signed, taps unsigned); _hi: bytes 2 and 3
+__device__ __forceinline__ int dp2a_lo_su(unsigned w, unsigned t, int c)
+{
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(t), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi_su(unsigned w, unsigned t, int c)
+{
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(t), "r"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned sat_u8_q15(int sum) { return (unsigned)min(255, max(0, sum >> 15)); }
+
+// fc: floor constants with the halo folded into the origin (the address is that of the block's top-left tap)
+template <int kKs>
+__device__ __forceinline__ unsigned luma_tile_hi(const FloorConst& fc, unsigned pl, float2 m, const int16_t* __restrict__ tab,
+                                                 const TileBounds& tb)
+{
+    const float2 s = __ffma2_rn(m, pair(fc.scale), pair(kMagic));
+    const float2 fl = __ffma2_rd(s, pair(kFloorScale), fc.c);
+    const unsigned a0 = imad_u32(__float_as_uint(fl.y), pl, __float_as_uint(fl.x)) + fc.row0;
+#ifdef VAW_BOUNDS_CHECK
+    check_taps(a0, a0 + (unsigned)(kKs - 1) * pl, (unsigned)kKs, tb.l_lo, tb.l_hi);
+#endif
+    const unsigned aw = a0 & ~3u, sh = a0 << 3;  // the funnel shift takes its count modulo 32: 8 (a0 & 3)
+    const unsigned idx = ((__float_as_uint(s.y) & 31u) << 5) | (__float_as_uint(s.x) & 31u);
+    const uint4* __restrict__ wt = reinterpret_cast<const uint4*>(tab) + idx * (unsigned)(kKs * kKs / 8);
+    int sum = 1 << 14;
+    unsigned row = aw;
+    if (kKs == 4) {
+        const uint4 q0 = __ldg(wt), q1 = __ldg(wt + 1);  // rows 0, 1 | rows 2, 3
+        const unsigned wp[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+        for (int r = 0; r < 4; ++r, row += pl) {
+            const unsigned t = __funnelshift_r(lds_w32(row), lds_w32(row + 4u), sh);
+            sum = dp2a_hi_su(wp[2 * r + 1], t, dp2a_lo_su(wp[2 * r], t, sum));
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 8; ++r, row += pl) {
+            const uint4 q = __ldg(wt + r);
+            const unsigned w0 = lds_w32(row), w1 = lds_w32(row + 4u), w2 = lds_w32(row + 8u);
+            const unsigned t0 = __funnelshift_r(w0, w1, sh), t1 = __funnelshift_r(w1, w2, sh);
+            sum = dp2a_hi_su(q.y, t0, dp2a_lo_su(q.x, t0, sum));
+            sum = dp2a_hi_su(q.w, t1, dp2a_lo_su(q.z, t1, sum));
+        }
+    }
+    return sat_u8_q15(sum);
+}
+
+// z = twice the chroma coordinate (chroma_z); a row of the block is kKs (U, V) pairs; returns U | V << 8
+template <int kKs>
+__device__ __forceinline__ unsigned chroma_tile_hi(const FloorConst& fc, unsigned pl, float2 z, const int16_t* __restrict__ tab,
+                                                   const TileBounds& tb)
+{
+    const float2 s = __ffma2_rn(z, pair(fc.scale), pair(kMagic));
+    const float2 fl = __ffma2_rd(s, pair(kFloorScale), fc.c);
+    const unsigned a0 = imad_u32(__float_as_uint(fl.x), 2u, __float_as_uint(fl.y) * pl) + fc.row0;  // even
+#ifdef VAW_BOUNDS_CHECK
+    check_taps(a0, a0 + (unsigned)(kKs - 1) * pl, 2u * (unsigned)kKs, tb.c_lo, tb.c_hi);
+#endif
+    const unsigned aw = a0 & ~3u, sh = a0 << 3;  // 0 or 16
+    const unsigned idx = ((__float_as_uint(s.y) & 31u) << 5) | (__float_as_uint(s.x) & 31u);
+    const uint4* __restrict__ wt = reinterpret_cast<const uint4*>(tab) + idx * (unsigned)(kKs * kKs / 8);
+    int su = 1 << 14, sv = 1 << 14;
+    unsigned row = aw;
+    if (kKs == 4) {
+        const uint4 q0 = __ldg(wt), q1 = __ldg(wt + 1);
+        const unsigned wp[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+        for (int r = 0; r < 4; ++r, row += pl) {
+            const unsigned w0 = lds_w32(row), w1 = lds_w32(row + 4u), w2 = lds_w32(row + 8u);
+            const unsigned t0 = __funnelshift_r(w0, w1, sh), t1 = __funnelshift_r(w1, w2, sh);  // U0 V0 U1 V1 | U2 V2 U3 V3
+            const unsigned u = __byte_perm(t0, t1, 0x6420), v = __byte_perm(t0, t1, 0x7531);
+            su = dp2a_hi_su(wp[2 * r + 1], u, dp2a_lo_su(wp[2 * r], u, su));
+            sv = dp2a_hi_su(wp[2 * r + 1], v, dp2a_lo_su(wp[2 * r], v, sv));
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 8; ++r, row += pl) {
+            const uint4 q = __ldg(wt + r);
+            const unsigned w0 = lds_w32(row), w1 = lds_w32(row + 4u), w2 = lds_w32(row + 8u), w3 = lds_w32(row + 12u),
+                           w4 = lds_w32(row + 16u);
+            const unsigned t0 = __funnelshift_r(w0, w1, sh), t1 = __funnelshift_r(w1, w2, sh);
+            const unsigned t2 = __funnelshift_r(w2, w3, sh), t3 = __funnelshift_r(w3, w4, sh);
+            const unsigned u0 = __byte_perm(t0, t1, 0x6420), v0 = __byte_perm(t0, t1, 0x7531);
+            const unsigned u1 = __byte_perm(t2, t3, 0x6420), v1 = __byte_perm(t2, t3, 0x7531);
+            su = dp2a_hi_su(q.y, u0, dp2a_lo_su(q.x, u0, su));
+            su = dp2a_hi_su(q.w, u1, dp2a_lo_su(q.z, u1, su));
+            sv = dp2a_hi_su(q.y, v0, dp2a_lo_su(q.x, v0, sv));
+            sv = dp2a_hi_su(q.w, v1, dp2a_lo_su(q.z, v1, sv));
+        }
+    }
+    return sat_u8_q15(su) | (sat_u8_q15(sv) << 8);
+}
+
 // ---- pieces shared by the quadrant kernels (vaw_tile.cu: NV12; vaw_packed_tile.cu: GRAY8 / BGR24) ----------------------
 struct ColPoly2 {
     float2 a[2][kNv];  // [column][power of t]
