@@ -615,9 +615,10 @@ int choose_tile_cap(vaw_ctx* ctx)
         const int v = atoi(env);
         if (v >= 1 && v <= 32) ctas = v;
     }
-    // INTER_CUBIC / INTER_LANCZOS4: four CTAs per SM (128 registers each); more CTAs would leave L1 too small for the
-    // weight table (cubic, C3: 16.7 k frames/s at six CTAs = no L1 to speak of, 23.9 k at five, 24.3 k at four, 23.4 k at three)
-    if (ctx->gd.halo && !getenv("VAW_EXPERIMENT_MAX_CTAS")) ctas = 4;
+    // INTER_CUBIC: four CTAs per SM (128 registers each); more CTAs would leave L1 too small for the 32 KB weight table
+    // (C3: 16.7 k frames/s at six CTAs = no L1 to speak of, 23.9 k at five, 24.3 k at four, 23.4 k at three).
+    // INTER_LANCZOS4: two, so that the 128 KB table fits L1 (4.8 k frames/s at four CTAs, 5.7 k at three, 6.1 k at two).
+    if (ctx->gd.halo && !getenv("VAW_EXPERIMENT_MAX_CTAS")) ctas = ctx->gd.halo == 1 ? 4 : 2;
     while (ctas > 1 && ctx->tile_need * 106 / 100 > vaw::tile_cap_for_ctas(ctas, book)) --ctas;
     long long cap = vaw::tile_cap_for_ctas(ctas, book);
     if (ctx->gd.halo) {

@@ -223,6 +223,26 @@ __device__ __forceinline__ int dp2a_hi_su(unsigned w, unsigned t, int c)
     asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(t), "r"(c));
     return d;
 }
+// The weights of one table entry: sm_100's 256-bit global load (SASS LDG.E.ENL2.256) fetches 16 shorts in one
+// instruction.  The threads of a warp read 32 different entries, so every load instruction costs the L1 a tag
+// look-up per thread: halving the instruction count is what counts (VAW_TABLE_LDG256=0: 128-bit loads, for the A/B).
+#ifndef VAW_TABLE_LDG256
+#define VAW_TABLE_LDG256 1
+#endif
+struct Weights8 { unsigned w[8]; };  // 16 shorts: two rows of a 4 x 4 block, or one row of an 8 x 8 block
+__device__ __forceinline__ Weights8 ldg_weights8(const uint4* __restrict__ p)
+{
+    Weights8 r;
+#if VAW_TABLE_LDG256
+    asm("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7]) : "l"(p));
+#else
+    const uint4 a = __ldg(p), b = __ldg(p + 1);
+    r.w[0] = a.x; r.w[1] = a.y; r.w[2] = a.z; r.w[3] = a.w; r.w[4] = b.x; r.w[5] = b.y; r.w[6] = b.z; r.w[7] = b.w;
+#endif
+    return r;
+}
+
 __device__ __forceinline__ unsigned sat_u8_q15(int sum) { return (unsigned)min(255, max(0, sum >> 15)); }
 
 // fc: floor constants with the halo folded into the origin (the address is that of the block's top-left tap)
@@ -242,8 +262,8 @@ __device__ __forceinline__ unsigned luma_tile_hi(const FloorConst& fc, unsigned 
     int sum = 1 << 14;
     unsigned row = aw;
     if (kKs == 4) {
-        const uint4 q0 = __ldg(wt), q1 = __ldg(wt + 1);  // rows 0, 1 | rows 2, 3
-        const unsigned wp[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        const Weights8 q0 = ldg_weights8(wt);  // the whole 4 x 4 block: 16 shorts
+        const unsigned wp[8] = {q0.w[0], q0.w[1], q0.w[2], q0.w[3], q0.w[4], q0.w[5], q0.w[6], q0.w[7]};
 #pragma unroll
         for (int r = 0; r < 4; ++r, row += pl) {
             const unsigned t = __funnelshift_r(lds_w32(row), lds_w32(row + 4u), sh);
@@ -251,12 +271,15 @@ __device__ __forceinline__ unsigned luma_tile_hi(const FloorConst& fc, unsigned 
         }
     } else {
 #pragma unroll
-        for (int r = 0; r < 8; ++r, row += pl) {
-            const uint4 q = __ldg(wt + r);
-            const unsigned w0 = lds_w32(row), w1 = lds_w32(row + 4u), w2 = lds_w32(row + 8u);
-            const unsigned t0 = __funnelshift_r(w0, w1, sh), t1 = __funnelshift_r(w1, w2, sh);
-            sum = dp2a_hi_su(q.y, t0, dp2a_lo_su(q.x, t0, sum));
-            sum = dp2a_hi_su(q.w, t1, dp2a_lo_su(q.z, t1, sum));
+        for (int rr = 0; rr < 4; ++rr) {
+            const Weights8 q = ldg_weights8(wt + 2 * rr);  // rows 2 rr, 2 rr + 1
+#pragma unroll
+            for (int k = 0; k < 2; ++k, row += pl) {
+                const unsigned w0 = lds_w32(row), w1 = lds_w32(row + 4u), w2 = lds_w32(row + 8u);
+                const unsigned t0 = __funnelshift_r(w0, w1, sh), t1 = __funnelshift_r(w1, w2, sh);
+                sum = dp2a_hi_su(q.w[4 * k + 1], t0, dp2a_lo_su(q.w[4 * k], t0, sum));
+                sum = dp2a_hi_su(q.w[4 * k + 3], t1, dp2a_lo_su(q.w[4 * k + 2], t1, sum));
+            }
         }
     }
     return sat_u8_q15(sum);
@@ -279,8 +302,8 @@ __device__ __forceinline__ unsigned chroma_tile_hi(const FloorConst& fc, unsigne
     int su = 1 << 14, sv = 1 << 14;
     unsigned row = aw;
     if (kKs == 4) {
-        const uint4 q0 = __ldg(wt), q1 = __ldg(wt + 1);
-        const unsigned wp[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        const Weights8 q0 = ldg_weights8(wt);
+        const unsigned wp[8] = {q0.w[0], q0.w[1], q0.w[2], q0.w[3], q0.w[4], q0.w[5], q0.w[6], q0.w[7]};
 #pragma unroll
         for (int r = 0; r < 4; ++r, row += pl) {
             const unsigned w0 = lds_w32(row), w1 = lds_w32(row + 4u), w2 = lds_w32(row + 8u);
@@ -291,18 +314,21 @@ __device__ __forceinline__ unsigned chroma_tile_hi(const FloorConst& fc, unsigne
         }
     } else {
 #pragma unroll
-        for (int r = 0; r < 8; ++r, row += pl) {
-            const uint4 q = __ldg(wt + r);
-            const unsigned w0 = lds_w32(row), w1 = lds_w32(row + 4u), w2 = lds_w32(row + 8u), w3 = lds_w32(row + 12u),
-                           w4 = lds_w32(row + 16u);
-            const unsigned t0 = __funnelshift_r(w0, w1, sh), t1 = __funnelshift_r(w1, w2, sh);
-            const unsigned t2 = __funnelshift_r(w2, w3, sh), t3 = __funnelshift_r(w3, w4, sh);
-            const unsigned u0 = __byte_perm(t0, t1, 0x6420), v0 = __byte_perm(t0, t1, 0x7531);
-            const unsigned u1 = __byte_perm(t2, t3, 0x6420), v1 = __byte_perm(t2, t3, 0x7531);
-            su = dp2a_hi_su(q.y, u0, dp2a_lo_su(q.x, u0, su));
-            su = dp2a_hi_su(q.w, u1, dp2a_lo_su(q.z, u1, su));
-            sv = dp2a_hi_su(q.y, v0, dp2a_lo_su(q.x, v0, sv));
-            sv = dp2a_hi_su(q.w, v1, dp2a_lo_su(q.z, v1, sv));
+        for (int rr = 0; rr < 4; ++rr) {
+            const Weights8 q = ldg_weights8(wt + 2 * rr);  // rows 2 rr, 2 rr + 1
+#pragma unroll
+            for (int k = 0; k < 2; ++k, row += pl) {
+                const unsigned w0 = lds_w32(row), w1 = lds_w32(row + 4u), w2 = lds_w32(row + 8u), w3 = lds_w32(row + 12u),
+                               w4 = lds_w32(row + 16u);
+                const unsigned t0 = __funnelshift_r(w0, w1, sh), t1 = __funnelshift_r(w1, w2, sh);
+                const unsigned t2 = __funnelshift_r(w2, w3, sh), t3 = __funnelshift_r(w3, w4, sh);
+                const unsigned u0 = __byte_perm(t0, t1, 0x6420), v0 = __byte_perm(t0, t1, 0x7531);
+                const unsigned u1 = __byte_perm(t2, t3, 0x6420), v1 = __byte_perm(t2, t3, 0x7531);
+                su = dp2a_hi_su(q.w[4 * k + 1], u0, dp2a_lo_su(q.w[4 * k], u0, su));
+                su = dp2a_hi_su(q.w[4 * k + 3], u1, dp2a_lo_su(q.w[4 * k + 2], u1, su));
+                sv = dp2a_hi_su(q.w[4 * k + 1], v0, dp2a_lo_su(q.w[4 * k], v0, sv));
+                sv = dp2a_hi_su(q.w[4 * k + 3], v1, dp2a_lo_su(q.w[4 * k + 2], v1, sv));
+            }
         }
     }
     return sat_u8_q15(su) | (sat_u8_q15(sv) << 8);
