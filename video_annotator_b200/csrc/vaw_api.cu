@@ -624,7 +624,9 @@ int choose_tile_cap(vaw_ctx* ctx)
     if (ctx->gd.halo) {
         // every sample of these filters reads its 32 / 128 bytes of weights (a 32 KB / 128 KB table) through L1: the tiles
         // get what they need (+25 % for tilt) instead of the whole SM, the launcher leaves the rest to L1
-        const long long want = ((ctx->tile_need * 125 / 100 + 127) / 128) * 128;
+        int pad = 125;
+        if (const char* env = getenv("VAW_EXPERIMENT_TABLE_PAD")) pad = atoi(env) >= 100 ? atoi(env) : pad;  // analysis only
+        const long long want = ((ctx->tile_need * pad / 100 + 127) / 128) * 128;
         if (want < cap && !getenv("VAW_EXPERIMENT_FULL_SMEM")) cap = want;
         ctx->table_ctas = ctas;
     }
