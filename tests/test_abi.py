@@ -84,8 +84,8 @@ def test_create_validates_before_touching_cuda():
     with pytest.raises(V.VawError) as e:  # cv::INTER_AREA (FrameSourceWarp.hpp:90): not a remap filter, not implemented
         V.WarpContext(cam, out, interpolation=3)
     assert e.value.code == -4
-    with pytest.raises(V.VawError) as e:  # cubic / Lanczos4 are staged (variant TILED) for NV12 only, never on POLY
-        V.WarpContext(cam, out, fmt=V.FORMAT_BGR24, interpolation=V.INTER_CUBIC, variant=3)
+    with pytest.raises(V.VawError) as e:  # Lanczos4 is staged (variant TILED) for NV12 and GRAY8 only; no table filter on POLY
+        V.WarpContext(cam, out, fmt=V.FORMAT_BGR24, interpolation=V.INTER_LANCZOS4, variant=3)
     assert e.value.code == -4
     with pytest.raises(V.VawError) as e:
         V.WarpContext(cam, out, interpolation=V.INTER_CUBIC, variant=2)

@@ -1333,8 +1333,8 @@ def test_inter_nearest(V, oracle, fmt, variant):
     ctx.close()
     with pytest.raises(V.VawError):
         V.WarpContext(w.input_camera, w.output_camera, out_size=w.out_size, interpolation=V.INTER_NEAREST, variant=POLY)
-    with pytest.raises(V.VawError):  # the table filters are staged for NV12 only
-        V.WarpContext(w.input_camera, w.output_camera, fmt=V.FORMAT_BGR24, interpolation=V.INTER_CUBIC, variant=TILED)
+    with pytest.raises(V.VawError):  # BGR24: the cubic filter is staged, Lanczos4 is not
+        V.WarpContext(w.input_camera, w.output_camera, fmt=V.FORMAT_BGR24, interpolation=V.INTER_LANCZOS4, variant=TILED)
 
 
 @pytest.mark.parametrize("interp", ["cubic", "lanczos4"])
@@ -1365,6 +1365,7 @@ def test_inter_cubic(V, oracle, fmt, interp):
         border = (10, 20, 30)
         ctx = V.WarpContext(w.input_camera, w.output_camera, fmt=V.FORMAT_BGR24, border=border,
                             interpolation=flag)
+        assert ctx.variant == (TILED if interp == "cubic" else GATHER)  # BGR24: the cubic filter is staged, Lanczos4 is not
         rng = np.random.default_rng(3)
         src = rng.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
         dst = torch.empty((oh, ow, 3), dtype=torch.uint8, device="cuda")
@@ -1373,6 +1374,41 @@ def test_inter_cubic(V, oracle, fmt, interp):
         mx, my = [t.cpu().numpy() for t in ctx.dump_coords(R, 0)]
         ref = oracle.remap_u8(src, mx, my, border=border, threads=NCPU, **kw)
         assert np.array_equal(dst.cpu().numpy(), ref.reshape(oh, ow, 3))
+    ctx.close()
+
+
+@pytest.mark.parametrize("case", ["c1-ref-size", "4k-tilted", "4k-far"])
+@pytest.mark.parametrize("fmt,interp", [("bgr", "cubic"), ("gray", "cubic"), ("gray", "lanczos4"), ("bgr-gather", "cubic")])
+def test_table_filters_packed_formats(V, oracle, fmt, interp, case):
+    """INTER_CUBIC on the staged BGR24 / GRAY8 kernel (and INTER_LANCZOS4 for GRAY8): the reference's literal 8UC3 frames with
+    its `interpolation` parameter.  C1 at the reference's own odd output size 1759 x 998 (ragged stores), 4K with
+    border-straddling and pure-border pieces, and a large rotation (unstaged pieces take the per-pixel fallback).
+    0 LSB against the oracle's filter (pinned on cv2.remap) on the kernel's own map."""
+    import torch
+    from video_annotator_b200 import configs
+    flag, kw = (V.INTER_CUBIC, {"cubic": True}) if interp == "cubic" else (V.INTER_LANCZOS4, {"lanczos4": True})
+    cn = 1 if fmt == "gray" else 3
+    border = (77,) if cn == 1 else (10, 200, 90)
+    if case == "c1-ref-size":
+        w = configs.workload("C1")
+        ow, oh = 1759, 998
+        R = rotation_xyz(1.0, -2.0, 0.5)
+    else:
+        w = configs.workload("C3")
+        ow, oh = 3838, 2157
+        R = rotation_xyz(-6.0, 4.0, -9.0) if case == "4k-tilted" else rotation_xyz(25.0, -30.0, 40.0)
+    sw, sh = w.src_size
+    ctx = V.WarpContext(w.input_camera, w.output_camera, fmt=V.FORMAT_GRAY8 if cn == 1 else V.FORMAT_BGR24, out_size=(ow, oh),
+                        border=border, interpolation=flag, variant=GATHER if fmt == "bgr-gather" else 0)
+    assert ctx.variant == (GATHER if fmt == "bgr-gather" else TILED)
+    rng = np.random.default_rng(11)
+    src = rng.integers(0, 256, (sh, sw, cn) if cn == 3 else (sh, sw), dtype=np.uint8)
+    dst = torch.empty(ctx.frame_shape("dst"), dtype=torch.uint8, device="cuda")
+    ctx.warp(G.to_dev(src), dst, R)
+    torch.cuda.synchronize()
+    mx, my = [t.cpu().numpy() for t in ctx.dump_coords(R, 0)]
+    ref = oracle.remap_u8(src, mx, my, border=border, threads=NCPU, **kw)
+    assert np.array_equal(dst.cpu().numpy().reshape(ref.shape), ref)
     ctx.close()
 
 

@@ -49,6 +49,11 @@ def main():
              ("NV12 cubic, variant GATHER (per-pixel taps)", V.FORMAT_NV12, V.INTER_CUBIC, 1),
              ("NV12 lanczos4 (staged-tile kernel, default)", V.FORMAT_NV12, V.INTER_LANCZOS4, 0),
              ("NV12 lanczos4, variant GATHER (per-pixel taps)", V.FORMAT_NV12, V.INTER_LANCZOS4, 1),
+             ("BGR24 cubic (staged-tile kernel, default)", V.FORMAT_BGR24, V.INTER_CUBIC, 0),
+             ("BGR24 cubic, variant GATHER (per-pixel taps)", V.FORMAT_BGR24, V.INTER_CUBIC, 1),
+             ("GRAY8 cubic (staged-tile kernel, default)", V.FORMAT_GRAY8, V.INTER_CUBIC, 0),
+             ("GRAY8 cubic, variant GATHER (per-pixel taps)", V.FORMAT_GRAY8, V.INTER_CUBIC, 1),
+             ("GRAY8 lanczos4 (staged-tile kernel, default)", V.FORMAT_GRAY8, V.INTER_LANCZOS4, 0),
              ("NV12 in -> BGR24 out, one launch (cvtColor + 3-channel remap fused, variant POLY)", V.FORMAT_NV12_TO_BGR24, V.INTER_LINEAR, 2),
              ("NV12 in -> BGR24 out, cvtColor into an L2-resident scratch + staged BGR kernel (variant TILED)", V.FORMAT_NV12_TO_BGR24, V.INTER_LINEAR, 3),
              ("BGR24 linear (the reference's literal format; staged-tile kernel, default)", V.FORMAT_BGR24, V.INTER_LINEAR, 0),

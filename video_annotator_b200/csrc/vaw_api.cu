@@ -285,6 +285,7 @@ const vaw::PackedMaps& packed_maps(vaw_ctx* ctx, const uint8_t* src, int pitch, 
     e.src = src; e.pitch = pitch; e.stride = stride; e.frames = frames;
     e.maps.enabled = 0;
     e.maps.tile_cap = ctx->tile_cap;
+    e.maps.table_ctas = ctx->table_ctas;
     const int rows_total = ctx->p.src_height;
     EncodeTiledFn enc = encode_tiled();
     const bool ok = enc && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (pitch & 15) == 0 && (stride & 15) == 0 &&
@@ -698,10 +699,13 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
         p.interpolation != VAW_INTER_LANCZOS4)
         return fail(nullptr, VAW_ERR_UNSUPPORTED, "only INTER_NEAREST, INTER_LINEAR, INTER_CUBIC and INTER_LANCZOS4 are implemented");
     const bool table_filter = p.interpolation == VAW_INTER_CUBIC || p.interpolation == VAW_INTER_LANCZOS4;
+    // the formats whose staged-tile kernels carry the table filters (vaw_tile.cu, vaw_packed_tile.cu)
+    const bool table_staged = p.format == VAW_FORMAT_NV12 || p.format == VAW_FORMAT_GRAY8 ||
+                              (p.format == VAW_FORMAT_BGR24 && p.interpolation == VAW_INTER_CUBIC);
     if (p.interpolation != VAW_INTER_LINEAR && p.variant != VAW_VARIANT_AUTO && p.variant != VAW_VARIANT_GATHER &&
         !(p.interpolation == VAW_INTER_NEAREST && p.variant == VAW_VARIANT_TILED) &&
-        !(table_filter && p.variant == VAW_VARIANT_TILED && p.format == VAW_FORMAT_NV12))
-        return fail(nullptr, VAW_ERR_UNSUPPORTED, "INTER_NEAREST runs on GATHER or TILED; INTER_CUBIC and INTER_LANCZOS4 on GATHER, and on TILED for NV12 (AUTO picks)");
+        !(table_filter && p.variant == VAW_VARIANT_TILED && table_staged))
+        return fail(nullptr, VAW_ERR_UNSUPPORTED, "INTER_NEAREST runs on GATHER or TILED; INTER_CUBIC and INTER_LANCZOS4 on GATHER, and on TILED for NV12 / GRAY8 (BGR24: cubic only); AUTO picks");
     if (p.format != VAW_FORMAT_NV12 && p.format != VAW_FORMAT_BGR24 && p.format != VAW_FORMAT_GRAY8 &&
         p.format != VAW_FORMAT_NV12_TO_BGR24)
         return fail(nullptr, VAW_ERR_INVALID, "unknown pixel format");
@@ -795,7 +799,7 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
     // AUTO: the staged-tile kernels wherever they exist (INTER_LINEAR: NV12 -> vaw_tile.cu, GRAY8 / BGR24 -> vaw_packed_tile.cu)
     ctx->variant = p.variant != VAW_VARIANT_AUTO ? p.variant
                    : ((p.interpolation == VAW_INTER_LINEAR || (p.interpolation == VAW_INTER_NEAREST && p.projection == 0) ||
-                       (table_filter && p.format == VAW_FORMAT_NV12 && p.projection == 0))
+                       (table_filter && table_staged && p.projection == 0))
                           ? VAW_VARIANT_TILED : VAW_VARIANT_GATHER);
     // (NV12 -> BGR24: TILED = cvtColor into an L2-resident scratch + the staged BGR kernel, 30.9 k frames/s at 4K;
     //  POLY = everything in one launch with per-tap conversion, 13.8 k)
@@ -873,7 +877,7 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
                 // BGR24: three bytes per source pixel.  32-row pieces win while four CTAs still share an SM (C3: 52 KB
                 // tiles, 0.758 ms per 32 frames against 0.777 ms with 16-row pieces at six CTAs); larger boxes (C5: 120 KB)
                 // are cut into 16-row pieces
-                if (attempt == 0 && (p.format == VAW_FORMAT_BGR24 || fused_tiled) && g.piece_h > 16 && ctas < 4 && !getenv("VAW_EXPERIMENT_PH"))
+                if (attempt == 0 && (p.format == VAW_FORMAT_BGR24 || fused_tiled) && g.piece_h > 16 && (ctas < 4 || ctx->gd.halo) && !getenv("VAW_EXPERIMENT_PH"))  // (cubic: small tiles leave L1 to the weight table)
                     set_piece_rows(16);
                 else
                     break;

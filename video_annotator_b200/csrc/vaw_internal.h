@@ -70,7 +70,8 @@ struct alignas(64) PackedMaps {
     CUtensorMap m4[kPackedWidths];
     int enabled;   // 0: layout not TMA-compatible -> every piece is sampled per pixel from global memory
     int tile_cap;  // bytes of shared memory for the tile of one CTA
-    int pad[14];
+    int table_ctas;  // INTER_CUBIC / INTER_LANCZOS4: CTAs per SM the capacity was sized for (the launcher's L1 / shared split)
+    int pad[13];
 };
 int packed_tile_need_bytes(const PieceRec& rec, int channels);
 int packed_tile_smem_bytes(int tile_cap);

@@ -20,6 +20,7 @@
 #include <stdint.h>
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include "vaw_internal.h"
 #include "vaw_poly.cuh"
 #include "vaw_tile.cuh"
@@ -54,9 +55,12 @@ __device__ __forceinline__ void store_px_checked(uint8_t* row, int u, int out_w,
     for (int c = 0; c < kCn; ++c) row[(size_t)u * kCn + c] = (uint8_t)(v >> (8 * c));
 }
 
-template <int kCn>
+template <int kCn, int kMode>
 __device__ __forceinline__ unsigned sample_checked(const Geom& g, const uint8_t* __restrict__ src, float mx, float my)
 {
+    if (kMode >= 2)  // INTER_CUBIC / INTER_LANCZOS4: the context's table filter, per tap from global memory
+        return sample_hi<kCn>(src, g.src_pitch, g.src_w, g.src_h, mx, my, kCn == 1 ? (g.border & 255u) : (g.border & 0xffffffu),
+                              g.cubic_tab, g.tab_ks);
     if (g.nearest) { mx = nearest_coord(mx); my = nearest_coord(my); }  // INTER_NEAREST = the filter on whole-pixel coordinates
     if (kCn == 1) return (unsigned)sample_c1(src, g.src_pitch, g.src_w, g.src_h, mx, my, g.border & 255);
     return sample_c3(src, g.src_pitch, g.src_w, g.src_h, mx, my, g.border & 0xffffffu);
@@ -142,6 +146,39 @@ __device__ __forceinline__ unsigned bgr_tile_sample(const FloorConst& fc, unsign
     return b | (g << 8) | (r << 16);
 }
 
+// cv::INTER_CUBIC for BGR from the staged tile (the scheme of luma_tile_hi, vaw_tile.cuh): the twelve bytes
+// B0 G0 R0 ... B3 G3 R3 of a tap row come in as four aligned words and three funnel shifts, two PRMT per channel
+// gather its four taps into one register, two IDP.2A (signed 16-bit weight pairs x unsigned tap bytes) accumulate
+// them.  fc carries the block's top-left tap (halo folded into the floor constants).
+__device__ __forceinline__ unsigned bgr_tile_cubic(const FloorConst& fc, unsigned pl, float2 m, const int16_t* __restrict__ tab,
+                                                   const TileBounds& tb)
+{
+    const float2 s = __ffma2_rn(m, pair(fc.scale), pair(kMagic));
+    const float2 fl = __ffma2_rd(s, pair(kFloorScale), fc.c);
+    const unsigned a0 = imad_u32(__float_as_uint(fl.x), 3u, __float_as_uint(fl.y) * pl) + fc.row0;  // B of the top-left tap
+#ifdef VAW_BOUNDS_CHECK
+    check_taps(a0, a0 + 3u * pl, 12u, tb.l_lo, tb.l_hi);
+#endif
+    const unsigned aw = a0 & ~3u, sh = a0 << 3;
+    const unsigned idx = ((__float_as_uint(s.y) & 31u) << 5) | (__float_as_uint(s.x) & 31u);
+    const Weights8 q = ldg_weights8(reinterpret_cast<const uint4*>(tab) + idx * 2u);
+    int sb = 1 << 14, sg = 1 << 14, sr = 1 << 14;
+    unsigned row = aw;
+#pragma unroll
+    for (int r = 0; r < 4; ++r, row += pl) {
+        const unsigned w0 = lds_w32(row), w1 = lds_w32(row + 4u), w2 = lds_w32(row + 8u), w3 = lds_w32(row + 12u);
+        const unsigned t0 = __funnelshift_r(w0, w1, sh), t1 = __funnelshift_r(w1, w2, sh), t2 = __funnelshift_r(w2, w3, sh);
+        // t0 = B0 G0 R0 B1, t1 = G1 R1 B2 G2, t2 = R2 B3 G3 R3
+        const unsigned qb = __byte_perm(__byte_perm(t0, t1, 0x0630), t2, 0x5210);
+        const unsigned qg = __byte_perm(__byte_perm(t0, t1, 0x0741), t2, 0x6210);
+        const unsigned qr = __byte_perm(__byte_perm(t0, t1, 0x0052), t2, 0x7410);
+        sb = dp2a_hi_su(q.w[2 * r + 1], qb, dp2a_lo_su(q.w[2 * r], qb, sb));
+        sg = dp2a_hi_su(q.w[2 * r + 1], qg, dp2a_lo_su(q.w[2 * r], qg, sg));
+        sr = dp2a_hi_su(q.w[2 * r + 1], qr, dp2a_lo_su(q.w[2 * r], qr, sr));
+    }
+    return sat_u8_q15(sb) | (sat_u8_q15(sg) << 8) | (sat_u8_q15(sr) << 16);
+}
+
 // Overwrite the cells of the staged tile that lie outside the source with the border colour (cv::remap's
 // BORDER_CONSTANT replaces each out-of-image tap; the colour has period kCn along a row, so the 4-byte word at
 // tile word index wd starts with channel (bx0 + 4 wd) mod kCn).  Tile row r <-> source row y0 + r, tile byte c <->
@@ -182,7 +219,8 @@ __device__ __forceinline__ void fill_border_packed(uint8_t* tile, int pl, int ti
 }
 
 // nrows rows starting at piece row dv0 for the lane's two columns (u0, u0 + 1); taps from the staged tile.
-template <int kCn, bool kRagged, bool kNearest>
+// kMode: 0 cv::INTER_LINEAR, 1 cv::INTER_NEAREST, 2 cv::INTER_CUBIC, 3 cv::INTER_LANCZOS4 (GRAY8 only)
+template <int kCn, bool kRagged, int kMode>
 __device__ __forceinline__ void rows_packed(const Geom& g, const ColPoly2& cp, const FloorConst& fc, unsigned pl, int dv0,
                                             int nrows, uint8_t* __restrict__ out0, int u0, const TileBounds& tb)
 {
@@ -204,7 +242,18 @@ __device__ __forceinline__ void rows_packed(const Geom& g, const ColPoly2& cp, c
         constexpr bool kWords = kCn == 3;
 #endif
         unsigned v00, v01, v10, v11;
-        if (kNearest) {
+        if (kMode >= 2) {
+            const float2 m00 = col_coord(cp.a[0], cp.base, t0), m01 = col_coord(cp.a[1], cp.base, t0);
+            const float2 m10 = col_coord(cp.a[0], cp.base, t1), m11 = col_coord(cp.a[1], cp.base, t1);
+            if (kCn == 1) {
+                constexpr int kKs = kMode == 2 ? 4 : 8;
+                v00 = luma_tile_hi<kKs>(fc, pl, m00, g.cubic_tab, tb); v01 = luma_tile_hi<kKs>(fc, pl, m01, g.cubic_tab, tb);
+                v10 = luma_tile_hi<kKs>(fc, pl, m10, g.cubic_tab, tb); v11 = luma_tile_hi<kKs>(fc, pl, m11, g.cubic_tab, tb);
+            } else {
+                v00 = bgr_tile_cubic(fc, pl, m00, g.cubic_tab, tb); v01 = bgr_tile_cubic(fc, pl, m01, g.cubic_tab, tb);
+                v10 = bgr_tile_cubic(fc, pl, m10, g.cubic_tab, tb); v11 = bgr_tile_cubic(fc, pl, m11, g.cubic_tab, tb);
+            }
+        } else if (kMode == 1) {
             v00 = packed_tile_nearest<kCn>(fc.row0, pl, col_coord(cp.a[0], cp.base, t0));
             v01 = packed_tile_nearest<kCn>(fc.row0, pl, col_coord(cp.a[1], cp.base, t0));
             v10 = packed_tile_nearest<kCn>(fc.row0, pl, col_coord(cp.a[0], cp.base, t1));
@@ -237,7 +286,7 @@ __device__ __forceinline__ void rows_packed(const Geom& g, const ColPoly2& cp, c
     }
 }
 
-template <int kCn, int kCtas, bool kNearest = false>
+template <int kCn, int kCtas, int kMode = 0>
 __global__ void __launch_bounds__(32 * kWarps, kCtas)
 warp_packed_tile_kernel(const Geom g, const FrameBatch b, const PieceRec* __restrict__ table,
                         const __grid_constant__ PackedMaps maps)
@@ -328,7 +377,7 @@ warp_packed_tile_kernel(const Geom g, const FrameBatch b, const PieceRec* __rest
                 uint8_t* row = dst + (size_t)(v_base + dv + r) * g.dst_pitch;
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-                    store_px_checked<kCn>(row, u0 + i, g.out_w, sample_checked<kCn>(g, src, m[r][i].x, m[r][i].y));
+                    store_px_checked<kCn>(row, u0 + i, g.out_w, sample_checked<kCn, kMode>(g, src, m[r][i].x, m[r][i].y));
             }
         }
         return;
@@ -368,7 +417,8 @@ warp_packed_tile_kernel(const Geom g, const FrameBatch b, const PieceRec* __rest
     // 0 at run time, unknown to ptxas (the zero pad of the record's stage): keeps the tap-row constants in uniform registers
     const unsigned never = (unsigned)(*(reinterpret_cast<const int4*>(rs) + 14)).w >> 31;
     const unsigned vnever = threadIdx.x >> 5;
-    const FloorConst fc = floor_const(-(int)box.x0, -(int)box.y0,
+    constexpr int kHalo = kMode == 2 ? 1 : (kMode == 3 ? 3 : 0);  // = GeomD::halo: the box carries it, the block starts there
+    const FloorConst fc = floor_const(-(int)box.x0 - kHalo, -(int)box.y0 - kHalo,
                                       smem_u32(tile) + (unsigned)(kCn * (int)box.x0 - bx0) - (unsigned)kCn * 0x40000000u, upl,
                                       __uint_as_float(0x42000000u | vnever), never);
     const int u0 = u_lo + col0;
@@ -376,25 +426,38 @@ warp_packed_tile_kernel(const Geom g, const FrameBatch b, const PieceRec* __rest
                          u_lo + kPieceW <= g.out_w && (rows & 1) == 0 && (hrows & 1) == 0;
     const TileBounds tb = {smem_u32(tile), smem_u32(tile) + (unsigned)(nrows * pl), 0u, 0u};
     uint8_t* const out0 = dst + (size_t)(v_base + dv0) * g.dst_pitch + (size_t)u0 * kCn;
-    if (kNearest) {
+    if (kMode == 1) {
         const FloorConst fn = floor_const(0, 0, smem_u32(tile) - (unsigned)box.y0 * upl - (unsigned)bx0 - (unsigned)kMagicBits * (upl + (unsigned)kCn),
                                           upl, 0.f, never);
-        if (pair_ok) rows_packed<kCn, false, true>(g, cp, fn, upl, dv0, my_rows, out0, u0, tb);
-        else rows_packed<kCn, true, true>(g, cp, fn, upl, dv0, my_rows, out0, u0, tb);
+        if (pair_ok) rows_packed<kCn, false, 1>(g, cp, fn, upl, dv0, my_rows, out0, u0, tb);
+        else rows_packed<kCn, true, 1>(g, cp, fn, upl, dv0, my_rows, out0, u0, tb);
         return;
     }
-    if (pair_ok) rows_packed<kCn, false, false>(g, cp, fc, upl, dv0, my_rows, out0, u0, tb);
-    else rows_packed<kCn, true, false>(g, cp, fc, upl, dv0, my_rows, out0, u0, tb);
+    if (pair_ok) rows_packed<kCn, false, kMode>(g, cp, fc, upl, dv0, my_rows, out0, u0, tb);
+    else rows_packed<kCn, true, kMode>(g, cp, fc, upl, dv0, my_rows, out0, u0, tb);
 }
 
-template <int kCn, int kCtas, bool kNearest = false>
+template <int kCn, int kCtas, int kMode = 0>
 cudaError_t configure_packed()
 {
-    cudaError_t e = cudaFuncSetAttribute(warp_packed_tile_kernel<kCn, kCtas, kNearest>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(warp_packed_tile_kernel<kCn, kCtas, kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          kTileOffset + kTileCapMax);
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(warp_packed_tile_kernel<kCn, kCtas, kNearest>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        e = cudaFuncSetAttribute(warp_packed_tile_kernel<kCn, kCtas, kMode>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     return e;
+}
+// INTER_CUBIC / INTER_LANCZOS4: shared memory for the resident CTAs' tiles, the rest of the SM to L1 (the weight table)
+template <int kCn, int kMode>
+cudaError_t launch_packed_table(const Geom& g, const FrameBatch& b, const PieceRec* table, const PackedMaps& maps, dim3 grid,
+                                dim3 block, int smem, cudaStream_t st)
+{
+    int pct = (int)(((long long)std::max(1, maps.table_ctas) * (smem + 1024) * 100 + (kSmemPerSM - 1)) / kSmemPerSM);
+    if (getenv("VAW_EXPERIMENT_FULL_SMEM")) pct = 100;
+    pct = std::min(100, std::max(1, pct));
+    cudaError_t e = cudaFuncSetAttribute(warp_packed_tile_kernel<kCn, 4, kMode>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    if (e != cudaSuccess) return e;
+    warp_packed_tile_kernel<kCn, 4, kMode><<<grid, block, smem, st>>>(g, b, table, maps);
+    return cudaGetLastError();
 }
 
 }  // namespace
@@ -435,8 +498,11 @@ cudaError_t launch_warp_packed_tile(const Geom& g, const FrameBatch& b, const Pi
         if (e == cudaSuccess) e = configure_packed<3, 7>();
         if (e == cudaSuccess) e = configure_packed<3, 6>();
         if (e == cudaSuccess) e = configure_packed<3, 4>();
-        if (e == cudaSuccess) e = configure_packed<1, 7, true>();
-        if (e == cudaSuccess) e = configure_packed<3, 7, true>();
+        if (e == cudaSuccess) e = configure_packed<1, 7, 1>();
+        if (e == cudaSuccess) e = configure_packed<3, 7, 1>();
+        if (e == cudaSuccess) e = configure_packed<1, 4, 2>();
+        if (e == cudaSuccess) e = configure_packed<1, 4, 3>();
+        if (e == cudaSuccess) e = configure_packed<3, 4, 2>();
         if (e != cudaSuccess) return e;
         if (tracked) configured[dev].store(true, std::memory_order_release);
     }
@@ -446,9 +512,15 @@ cudaError_t launch_warp_packed_tile(const Geom& g, const FrameBatch& b, const Pi
     // the instantiation whose register budget matches the CTAs the tile capacity lets share an SM: 7 (72 registers),
     // 6 (80) or 4 and fewer (128)
     const int ctas = maps.tile_cap <= tile_cap_for_ctas(7, kTileOffset) ? 7 : (maps.tile_cap <= tile_cap_for_ctas(6, kTileOffset) ? 6 : 4);
+    if (g.cubic_tab) {  // cv::INTER_CUBIC (GRAY8, BGR24) / cv::INTER_LANCZOS4 (GRAY8)
+        if (channels == 1) return g.tab_ks == 4 ? launch_packed_table<1, 2>(g, b, table, maps, grid, block, smem, st)
+                                                : launch_packed_table<1, 3>(g, b, table, maps, grid, block, smem, st);
+        if (g.tab_ks != 4) return cudaErrorInvalidValue;  // (vaw_create never routes BGR24 Lanczos4 here)
+        return launch_packed_table<3, 2>(g, b, table, maps, grid, block, smem, st);
+    }
     if (g.nearest) {  // cv::INTER_NEAREST: one light instantiation per format
-        if (channels == 1) warp_packed_tile_kernel<1, 7, true><<<grid, block, smem, st>>>(g, b, table, maps);
-        else warp_packed_tile_kernel<3, 7, true><<<grid, block, smem, st>>>(g, b, table, maps);
+        if (channels == 1) warp_packed_tile_kernel<1, 7, 1><<<grid, block, smem, st>>>(g, b, table, maps);
+        else warp_packed_tile_kernel<3, 7, 1><<<grid, block, smem, st>>>(g, b, table, maps);
         return cudaGetLastError();
     }
     if (channels == 1) {
