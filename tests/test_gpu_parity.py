@@ -464,6 +464,36 @@ def test_fused_nv12_to_bgr_equals_cvtcolor_then_remap(V, oracle, name, out_size,
     ctx.close()
 
 
+@pytest.mark.parametrize("interp", ["nearest", "cubic"])
+@pytest.mark.parametrize("name,out_size,rot", [("C1", (1759, 998), (1.0, -2.0, 0.5)), ("C3", (3840, 2160), (-6.0, 4.0, -9.0))])
+def test_fused_nv12_to_bgr_other_filters(V, oracle, name, out_size, rot, interp):
+    """The reference's literal per-frame pipeline with its `interpolation` parameter (FrameSourceWarp.hpp:90): cvtColor, then
+    cv::remap(INTER_NEAREST / INTER_CUBIC) on the 8UC3 image.  Runs as TILED's chain (conversion into the L2-resident
+    scratch, then the staged BGR kernel with that filter).  0 LSB against the oracle chain on the kernel's map."""
+    from video_annotator_b200 import configs
+    w = configs.workload(name)
+    R = rotation_xyz(*rot)
+    sw, sh = w.src_size
+    border = (3, 40, 200)
+    flag = V.INTER_NEAREST if interp == "nearest" else V.INTER_CUBIC
+    ctx = V.WarpContext(w.input_camera, w.output_camera, fmt=V.FORMAT_NV12_TO_BGR24, out_size=out_size, border=border, interpolation=flag)
+    assert ctx.variant == TILED
+    src = oracle.synth_nv12(sw, sh, 5, white_noise=True)
+    got = _warp_one(V, ctx, src, R)
+    mx, my = [t.cpu().numpy() for t in ctx.dump_coords(R, 0)]
+    bgr = oracle.nv12_to_bgr(src, sw, sh, threads=NCPU)
+    if interp == "nearest":
+        ref = oracle.remap_u8(bgr, np.rint(mx), np.rint(my), border=border, threads=NCPU)
+    else:
+        ref = oracle.remap_u8(bgr, mx, my, border=border, threads=NCPU, cubic=True)
+    assert np.array_equal(got, ref.reshape(got.shape))
+    ctx.close()
+    with pytest.raises(V.VawError):  # the one-launch form exists for INTER_LINEAR only
+        V.WarpContext(w.input_camera, w.output_camera, fmt=V.FORMAT_NV12_TO_BGR24, out_size=out_size, interpolation=flag, variant=POLY)
+    with pytest.raises(V.VawError):
+        V.WarpContext(w.input_camera, w.output_camera, fmt=V.FORMAT_NV12_TO_BGR24, out_size=out_size, interpolation=V.INTER_LANCZOS4)
+
+
 @pytest.mark.parametrize("variant", [POLY, TILED])
 def test_fused_nv12_to_bgr_batches_pitches_and_the_two_launch_pipeline(V, oracle, variant):
     """Batch == per frame; pitched output with untouched padding; and the same bytes as the two-launch pipeline

@@ -21,11 +21,10 @@ def main():
     dst = torch.empty_like(src)
     rdev = torch.empty(n * 9, dtype=torch.float32, device="cuda")
     for interp, name in ((V.INTER_CUBIC, "cubic"), (V.INTER_LANCZOS4, "lanczos4")):
-        for env in ({}, {"VAW_EXPERIMENT_FULL_SMEM": "1"}, {"VAW_EXPERIMENT_MAX_CTAS": "5"}, {"VAW_EXPERIMENT_MAX_CTAS": "4"},
+        for env in ({}, {"VAW_EXPERIMENT_PITCH64": "1"}, {"VAW_EXPERIMENT_FULL_SMEM": "1"}, {"VAW_EXPERIMENT_MAX_CTAS": "5"},
                     {"VAW_EXPERIMENT_MAX_CTAS": "3"}, {"VAW_EXPERIMENT_MAX_CTAS": "2"}, {"VAW_EXPERIMENT_TABLE_PAD": "110"},
-                    {"VAW_EXPERIMENT_TABLE_PAD": "140"}, {"VAW_EXPERIMENT_TABLE_PAD": "160"}, {"VAW_EXPERIMENT_TABLE_PAD": "180"},
-                    {"VAW_EXPERIMENT_TABLE_PAD": "160", "VAW_EXPERIMENT_MAX_CTAS": "3"}):
-            for k in ("VAW_EXPERIMENT_FULL_SMEM", "VAW_EXPERIMENT_MAX_CTAS", "VAW_EXPERIMENT_TABLE_PAD"):
+                    {"VAW_EXPERIMENT_TABLE_PAD": "160"}):
+            for k in ("VAW_EXPERIMENT_FULL_SMEM", "VAW_EXPERIMENT_MAX_CTAS", "VAW_EXPERIMENT_TABLE_PAD", "VAW_EXPERIMENT_PITCH64"):
                 os.environ.pop(k, None)
             os.environ.update(env)
             ctx = V.WarpContext(w.input_camera, w.output_camera, out_size=w.out_size, interpolation=interp)

@@ -633,8 +633,14 @@ int choose_tile_cap(vaw_ctx* ctx)
     }
     if (cap < vaw::kTileCapMin) cap = vaw::kTileCapMin;
     if (cap > vaw::kTileCapMax) cap = vaw::kTileCapMax;
+    if (const char* env = getenv("VAW_EXPERIMENT_FORCE_CTAS")) {  // analysis only: the capacity of exactly this many CTAs, whatever the tiles need
+        const int v = atoi(env);
+        if (v >= 1 && v <= 16) { ctas = v; cap = vaw::tile_cap_for_ctas(v, book); }
+    }
     ctx->tile_cap = (int)cap;
     ctx->gd.tile_cap = ctx->tile_cap;  // the builder picks the tile pitch of every piece against it
+    if (const char* env = getenv("VAW_EXPERIMENT_PITCH64")) ctx->gd.pitch64 = atoi(env);  // analysis only
+    if (getenv("VAW_EXPERIMENT_TIGHT_PITCH")) ctx->gd.tile_cap = 0;  // analysis only: always the tightest multiple of 32
     for (vaw_ctx::MapEntry& e : ctx->map_cache) e = vaw_ctx::MapEntry{};
     return ctas;
 }
@@ -701,7 +707,7 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
     const bool table_filter = p.interpolation == VAW_INTER_CUBIC || p.interpolation == VAW_INTER_LANCZOS4;
     // the formats whose staged-tile kernels carry the table filters (vaw_tile.cu, vaw_packed_tile.cu)
     const bool table_staged = p.format == VAW_FORMAT_NV12 || p.format == VAW_FORMAT_GRAY8 ||
-                              (p.format == VAW_FORMAT_BGR24 && p.interpolation == VAW_INTER_CUBIC);
+                              ((p.format == VAW_FORMAT_BGR24 || p.format == VAW_FORMAT_NV12_TO_BGR24) && p.interpolation == VAW_INTER_CUBIC);
     if (p.interpolation != VAW_INTER_LINEAR && p.variant != VAW_VARIANT_AUTO && p.variant != VAW_VARIANT_GATHER &&
         !(p.interpolation == VAW_INTER_NEAREST && p.variant == VAW_VARIANT_TILED) &&
         !(table_filter && p.variant == VAW_VARIANT_TILED && table_staged))
@@ -709,9 +715,12 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
     if (p.format != VAW_FORMAT_NV12 && p.format != VAW_FORMAT_BGR24 && p.format != VAW_FORMAT_GRAY8 &&
         p.format != VAW_FORMAT_NV12_TO_BGR24)
         return fail(nullptr, VAW_ERR_INVALID, "unknown pixel format");
-    if (p.format == VAW_FORMAT_NV12_TO_BGR24 && (p.interpolation != VAW_INTER_LINEAR ||
-                                                  (p.variant != VAW_VARIANT_AUTO && p.variant != VAW_VARIANT_POLY && p.variant != VAW_VARIANT_TILED)))
-        return fail(nullptr, VAW_ERR_UNSUPPORTED, "NV12 -> BGR24: INTER_LINEAR, variant AUTO, POLY (one launch) or TILED (conversion + staged BGR kernel)");
+    // NV12 -> BGR24: INTER_LINEAR on POLY (one launch) or TILED; INTER_NEAREST and INTER_CUBIC through TILED's chain only
+    // (cvtColor into the L2-resident scratch, then the staged BGR kernel with that filter)
+    if (p.format == VAW_FORMAT_NV12_TO_BGR24 &&
+        ((p.interpolation != VAW_INTER_LINEAR && p.interpolation != VAW_INTER_NEAREST && p.interpolation != VAW_INTER_CUBIC) ||
+         (p.variant != VAW_VARIANT_AUTO && p.variant != VAW_VARIANT_TILED && !(p.variant == VAW_VARIANT_POLY && p.interpolation == VAW_INTER_LINEAR))))
+        return fail(nullptr, VAW_ERR_UNSUPPORTED, "NV12 -> BGR24: INTER_LINEAR on variant AUTO, POLY (one launch) or TILED (conversion + staged BGR kernel); INTER_NEAREST / INTER_CUBIC on AUTO or TILED");
     if (p.variant < VAW_VARIANT_AUTO || p.variant > VAW_VARIANT_TEX || p.variant == VAW_VARIANT_PIPE)
         return fail(nullptr, VAW_ERR_UNSUPPORTED, "kernel variant not available in this build (PIPE was retired in round 2)");
     if (p.projection < 0 || p.projection > 3) return fail(nullptr, VAW_ERR_INVALID, "projection is 0..3");
@@ -838,6 +847,10 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
         d.projection = p.projection;
         // INTER_CUBIC / INTER_LANCZOS4 on staged tiles (NV12): the boxes carry the filter's halo
         d.halo = (table_filter && ctx->variant == VAW_VARIANT_TILED) ? (p.interpolation == VAW_INTER_CUBIC ? 1 : 3) : 0;
+        // their kernels are bound by the shared-memory / L1 data pipe: tile pitches of 64 modulo 128 bytes halve the bank
+        // conflicts between lanes that share a source column in adjacent rows (NV12 cubic 28.9 k -> 30.7 k frames/s at 4K;
+        // the INTER_LINEAR kernel is issue-bound and measures the same either way, so it keeps its pitches)
+        d.pitch64 = d.halo ? 1 : 0;
         set_piece_rows(ph);
         e = cudaEventCreateWithFlags(&ctx->table_free, cudaEventDisableTiming);
         // (room for the same frame cut into 16-row pieces: BGR24 may fall back to them below)

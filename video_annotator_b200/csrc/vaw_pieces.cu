@@ -223,7 +223,9 @@ build_pieces_kernel(const GeomD g, const PieceBasis basis, const float* __restri
             const int nrows = (box.y1 - box.y0 + 4) & ~3, cnrows = (box.cy1 - box.cy0 + 4) & ~3;  // rows, rounded up to whole 4-row boxes
             const int want = max(wb, cwb);
             const int pl128 = (want + 127) & ~127, pl32 = max(kStageMinPitch, (want + 31) & ~31);
-            const int pl = (pl128 <= kStageMaxPitch && pl128 * (nrows + cnrows) <= g.tile_cap) ? pl128 : pl32;
+            const int pl64 = (((want - 64 + 127) & ~127) + 64 < kStageMinPitch) ? kStageMinPitch + 64 : ((want - 64 + 127) & ~127) + 64;
+            const int pl = (g.pitch64 && pl64 <= kStageMaxPitch && pl64 * (nrows + cnrows) <= g.tile_cap) ? pl64
+                           : ((pl128 <= kStageMaxPitch && pl128 * (nrows + cnrows) <= g.tile_cap) ? pl128 : pl32);
             if (pl <= kStageMaxPitch && nrows > 0 && cnrows > 0 && nrows < 65536 && cnrows < 65536) {
                 st.lx0 = (int16_t)lx0; st.by0 = box.y0; st.cbx0 = (int16_t)cbx0; st.cy0 = box.cy0;
                 st.pl = (uint16_t)pl; st.nrows = (uint16_t)nrows; st.cnrows = (uint16_t)cnrows;

@@ -88,6 +88,9 @@ struct GeomD {  // the 8 fp32 scalars of FrameSourceWarp.cpp:283-290, widened ex
     int has_dist;  // any kd != 0
     int tile_cap;  // bytes of shared memory a tile may take with a 128-byte-multiple pitch (0: always the tightest pitch)
     int projection;  // 0 = createMap.cl (fisheye in, rectilinear out); bit 0: rectilinear input; bit 1: fisheye output
+    int pitch64;  // tile pitch policy: 0 = a multiple of 128 bytes when the tile capacity allows, else the tightest multiple of 32;
+                  // 1 = the smallest pitch that is 64 modulo 128 (adjacent tile rows sit 16 banks apart: lanes that share a
+                  // source column in neighbouring rows no longer collide)
     int halo;  // extra taps on every side of the bilinear pair that the staged sampler reads: 0 (INTER_LINEAR / INTER_NEAREST),
                // 1 (INTER_CUBIC: 4 x 4 taps from floor - 1) or 3 (INTER_LANCZOS4: 8 x 8 taps from floor - 3); the source boxes
                // and the interior / outside classification of the pieces account for it
