@@ -86,8 +86,7 @@ enum { VAW_INTER_NEAREST = 0, VAW_INTER_LINEAR = 1, VAW_INTER_CUBIC = 2, VAW_INT
  *           never chosen by AUTO.  Needs a texture-aligned source base (512 bytes), a pitch that is
  *           a multiple of 32 and a frame stride that is a whole number of rows; else it runs as TILED.
  * POLY and TILED produce identical bytes on NV12.  AUTO = TILED for every format and filter the staged kernels carry
- * (INTER_LINEAR / NEAREST / CUBIC / LANCZOS4 with createMap.cl's projection pair; not BGR24 with LANCZOS4), else
- * GATHER.  GRAY8 / BGR24 accept GATHER and TILED, NV12 -> BGR24 POLY and TILED (INTER_LINEAR). */
+ * (INTER_LINEAR / NEAREST / CUBIC / LANCZOS4 with createMap.cl's projection pair), else GATHER.  GRAY8 / BGR24 accept GATHER and TILED, NV12 -> BGR24 POLY and TILED (INTER_LINEAR). */
 enum {
     VAW_VARIANT_AUTO = 0,
     VAW_VARIANT_GATHER = 1,
@@ -113,8 +112,7 @@ typedef struct vaw_params {
                                           cvRound of the map); VAW_INTER_CUBIC and
                                           VAW_INTER_LANCZOS4 (its 4x4 / 8x8 fixed-point
                                           filters).  All of them run on the staged-tile
-                                          kernels (variant TILED, what AUTO picks) except
-                                          BGR24 with LANCZOS4 (variant GATHER)         */
+                                          kernels (variant TILED, what AUTO picks)     */
     uint8_t border[4];                 /* NV12: Y,U,V  BGR24: B,G,R  (cv::remap's
                                           borderValue; OpenCV default is 0; the NV12
                                           neutral chroma is 128)                     */

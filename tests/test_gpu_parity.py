@@ -464,18 +464,18 @@ def test_fused_nv12_to_bgr_equals_cvtcolor_then_remap(V, oracle, name, out_size,
     ctx.close()
 
 
-@pytest.mark.parametrize("interp", ["nearest", "cubic"])
+@pytest.mark.parametrize("interp", ["nearest", "cubic", "lanczos4"])
 @pytest.mark.parametrize("name,out_size,rot", [("C1", (1759, 998), (1.0, -2.0, 0.5)), ("C3", (3840, 2160), (-6.0, 4.0, -9.0))])
 def test_fused_nv12_to_bgr_other_filters(V, oracle, name, out_size, rot, interp):
     """The reference's literal per-frame pipeline with its `interpolation` parameter (FrameSourceWarp.hpp:90): cvtColor, then
-    cv::remap(INTER_NEAREST / INTER_CUBIC) on the 8UC3 image.  Runs as TILED's chain (conversion into the L2-resident
+    cv::remap(INTER_NEAREST / INTER_CUBIC / INTER_LANCZOS4) on the 8UC3 image.  Runs as TILED's chain (conversion into the L2-resident
     scratch, then the staged BGR kernel with that filter).  0 LSB against the oracle chain on the kernel's map."""
     from video_annotator_b200 import configs
     w = configs.workload(name)
     R = rotation_xyz(*rot)
     sw, sh = w.src_size
     border = (3, 40, 200)
-    flag = V.INTER_NEAREST if interp == "nearest" else V.INTER_CUBIC
+    flag = {"nearest": V.INTER_NEAREST, "cubic": V.INTER_CUBIC, "lanczos4": V.INTER_LANCZOS4}[interp]
     ctx = V.WarpContext(w.input_camera, w.output_camera, fmt=V.FORMAT_NV12_TO_BGR24, out_size=out_size, border=border, interpolation=flag)
     assert ctx.variant == TILED
     src = oracle.synth_nv12(sw, sh, 5, white_noise=True)
@@ -485,13 +485,11 @@ def test_fused_nv12_to_bgr_other_filters(V, oracle, name, out_size, rot, interp)
     if interp == "nearest":
         ref = oracle.remap_u8(bgr, np.rint(mx), np.rint(my), border=border, threads=NCPU)
     else:
-        ref = oracle.remap_u8(bgr, mx, my, border=border, threads=NCPU, cubic=True)
+        ref = oracle.remap_u8(bgr, mx, my, border=border, threads=NCPU, **({"cubic": True} if interp == "cubic" else {"lanczos4": True}))
     assert np.array_equal(got, ref.reshape(got.shape))
     ctx.close()
     with pytest.raises(V.VawError):  # the one-launch form exists for INTER_LINEAR only
         V.WarpContext(w.input_camera, w.output_camera, fmt=V.FORMAT_NV12_TO_BGR24, out_size=out_size, interpolation=flag, variant=POLY)
-    with pytest.raises(V.VawError):
-        V.WarpContext(w.input_camera, w.output_camera, fmt=V.FORMAT_NV12_TO_BGR24, out_size=out_size, interpolation=V.INTER_LANCZOS4)
 
 
 @pytest.mark.parametrize("variant", [POLY, TILED])
@@ -1363,8 +1361,8 @@ def test_inter_nearest(V, oracle, fmt, variant):
     ctx.close()
     with pytest.raises(V.VawError):
         V.WarpContext(w.input_camera, w.output_camera, out_size=w.out_size, interpolation=V.INTER_NEAREST, variant=POLY)
-    with pytest.raises(V.VawError):  # BGR24: the cubic filter is staged, Lanczos4 is not
-        V.WarpContext(w.input_camera, w.output_camera, fmt=V.FORMAT_BGR24, interpolation=V.INTER_LANCZOS4, variant=TILED)
+    with pytest.raises(V.VawError):  # no table filter on variant POLY
+        V.WarpContext(w.input_camera, w.output_camera, out_size=w.out_size, interpolation=V.INTER_CUBIC, variant=POLY)
 
 
 @pytest.mark.parametrize("interp", ["cubic", "lanczos4"])
@@ -1395,7 +1393,7 @@ def test_inter_cubic(V, oracle, fmt, interp):
         border = (10, 20, 30)
         ctx = V.WarpContext(w.input_camera, w.output_camera, fmt=V.FORMAT_BGR24, border=border,
                             interpolation=flag)
-        assert ctx.variant == (TILED if interp == "cubic" else GATHER)  # BGR24: the cubic filter is staged, Lanczos4 is not
+        assert ctx.variant == TILED
         rng = np.random.default_rng(3)
         src = rng.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
         dst = torch.empty((oh, ow, 3), dtype=torch.uint8, device="cuda")
@@ -1408,7 +1406,7 @@ def test_inter_cubic(V, oracle, fmt, interp):
 
 
 @pytest.mark.parametrize("case", ["c1-ref-size", "4k-tilted", "4k-far"])
-@pytest.mark.parametrize("fmt,interp", [("bgr", "cubic"), ("gray", "cubic"), ("gray", "lanczos4"), ("bgr-gather", "cubic")])
+@pytest.mark.parametrize("fmt,interp", [("bgr", "cubic"), ("bgr", "lanczos4"), ("gray", "cubic"), ("gray", "lanczos4"), ("bgr-gather", "cubic")])
 def test_table_filters_packed_formats(V, oracle, fmt, interp, case):
     """INTER_CUBIC on the staged BGR24 / GRAY8 kernel (and INTER_LANCZOS4 for GRAY8): the reference's literal 8UC3 frames with
     its `interpolation` parameter.  C1 at the reference's own odd output size 1759 x 998 (ragged stores), 4K with

@@ -51,6 +51,8 @@ def main():
              ("NV12 lanczos4, variant GATHER (per-pixel taps)", V.FORMAT_NV12, V.INTER_LANCZOS4, 1),
              ("BGR24 cubic (staged-tile kernel, default)", V.FORMAT_BGR24, V.INTER_CUBIC, 0),
              ("BGR24 cubic, variant GATHER (per-pixel taps)", V.FORMAT_BGR24, V.INTER_CUBIC, 1),
+             ("BGR24 lanczos4 (staged-tile kernel, default)", V.FORMAT_BGR24, V.INTER_LANCZOS4, 0),
+             ("BGR24 lanczos4, variant GATHER (per-pixel taps)", V.FORMAT_BGR24, V.INTER_LANCZOS4, 1),
              ("GRAY8 cubic (staged-tile kernel, default)", V.FORMAT_GRAY8, V.INTER_CUBIC, 0),
              ("GRAY8 cubic, variant GATHER (per-pixel taps)", V.FORMAT_GRAY8, V.INTER_CUBIC, 1),
              ("GRAY8 lanczos4 (staged-tile kernel, default)", V.FORMAT_GRAY8, V.INTER_LANCZOS4, 0),

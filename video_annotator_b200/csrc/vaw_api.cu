@@ -706,21 +706,19 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
         return fail(nullptr, VAW_ERR_UNSUPPORTED, "only INTER_NEAREST, INTER_LINEAR, INTER_CUBIC and INTER_LANCZOS4 are implemented");
     const bool table_filter = p.interpolation == VAW_INTER_CUBIC || p.interpolation == VAW_INTER_LANCZOS4;
     // the formats whose staged-tile kernels carry the table filters (vaw_tile.cu, vaw_packed_tile.cu)
-    const bool table_staged = p.format == VAW_FORMAT_NV12 || p.format == VAW_FORMAT_GRAY8 ||
-                              ((p.format == VAW_FORMAT_BGR24 || p.format == VAW_FORMAT_NV12_TO_BGR24) && p.interpolation == VAW_INTER_CUBIC);
+    const bool table_staged = true;  // (every format since the BGR24 Lanczos4 sampler)
     if (p.interpolation != VAW_INTER_LINEAR && p.variant != VAW_VARIANT_AUTO && p.variant != VAW_VARIANT_GATHER &&
         !(p.interpolation == VAW_INTER_NEAREST && p.variant == VAW_VARIANT_TILED) &&
         !(table_filter && p.variant == VAW_VARIANT_TILED && table_staged))
-        return fail(nullptr, VAW_ERR_UNSUPPORTED, "INTER_NEAREST runs on GATHER or TILED; INTER_CUBIC and INTER_LANCZOS4 on GATHER, and on TILED for NV12 / GRAY8 (BGR24: cubic only); AUTO picks");
+        return fail(nullptr, VAW_ERR_UNSUPPORTED, "INTER_NEAREST runs on GATHER or TILED; INTER_CUBIC and INTER_LANCZOS4 on GATHER or TILED; AUTO picks TILED");
     if (p.format != VAW_FORMAT_NV12 && p.format != VAW_FORMAT_BGR24 && p.format != VAW_FORMAT_GRAY8 &&
         p.format != VAW_FORMAT_NV12_TO_BGR24)
         return fail(nullptr, VAW_ERR_INVALID, "unknown pixel format");
-    // NV12 -> BGR24: INTER_LINEAR on POLY (one launch) or TILED; INTER_NEAREST and INTER_CUBIC through TILED's chain only
+    // NV12 -> BGR24: INTER_LINEAR on POLY (one launch) or TILED; the other filters through TILED's chain only
     // (cvtColor into the L2-resident scratch, then the staged BGR kernel with that filter)
     if (p.format == VAW_FORMAT_NV12_TO_BGR24 &&
-        ((p.interpolation != VAW_INTER_LINEAR && p.interpolation != VAW_INTER_NEAREST && p.interpolation != VAW_INTER_CUBIC) ||
-         (p.variant != VAW_VARIANT_AUTO && p.variant != VAW_VARIANT_TILED && !(p.variant == VAW_VARIANT_POLY && p.interpolation == VAW_INTER_LINEAR))))
-        return fail(nullptr, VAW_ERR_UNSUPPORTED, "NV12 -> BGR24: INTER_LINEAR on variant AUTO, POLY (one launch) or TILED (conversion + staged BGR kernel); INTER_NEAREST / INTER_CUBIC on AUTO or TILED");
+        ((p.variant != VAW_VARIANT_AUTO && p.variant != VAW_VARIANT_TILED && !(p.variant == VAW_VARIANT_POLY && p.interpolation == VAW_INTER_LINEAR))))
+        return fail(nullptr, VAW_ERR_UNSUPPORTED, "NV12 -> BGR24: INTER_LINEAR on variant AUTO, POLY (one launch) or TILED (conversion + staged BGR kernel); the other filters on AUTO or TILED");
     if (p.variant < VAW_VARIANT_AUTO || p.variant > VAW_VARIANT_TEX || p.variant == VAW_VARIANT_PIPE)
         return fail(nullptr, VAW_ERR_UNSUPPORTED, "kernel variant not available in this build (PIPE was retired in round 2)");
     if (p.projection < 0 || p.projection > 3) return fail(nullptr, VAW_ERR_INVALID, "projection is 0..3");

@@ -146,35 +146,47 @@ __device__ __forceinline__ unsigned bgr_tile_sample(const FloorConst& fc, unsign
     return b | (g << 8) | (r << 16);
 }
 
-// cv::INTER_CUBIC for BGR from the staged tile (the scheme of luma_tile_hi, vaw_tile.cuh): the twelve bytes
-// B0 G0 R0 ... B3 G3 R3 of a tap row come in as four aligned words and three funnel shifts, two PRMT per channel
-// gather its four taps into one register, two IDP.2A (signed 16-bit weight pairs x unsigned tap bytes) accumulate
-// them.  fc carries the block's top-left tap (halo folded into the floor constants).
-__device__ __forceinline__ unsigned bgr_tile_cubic(const FloorConst& fc, unsigned pl, float2 m, const int16_t* __restrict__ tab,
-                                                   const TileBounds& tb)
+// cv::INTER_CUBIC / cv::INTER_LANCZOS4 for BGR from the staged tile (the scheme of luma_tile_hi, vaw_tile.cuh): the
+// twelve bytes B0 G0 R0 ... B3 G3 R3 of four taps come in as four aligned words and three funnel shifts, two PRMT per
+// channel gather its four taps into one register, two IDP.2A (signed 16-bit weight pairs x unsigned tap bytes)
+// accumulate them; a Lanczos4 row is two such groups.  fc carries the block's top-left tap (halo folded into the
+// floor constants).
+template <int kKs>
+__device__ __forceinline__ unsigned bgr_tile_hi(const FloorConst& fc, unsigned pl, float2 m, const int16_t* __restrict__ tab,
+                                                const TileBounds& tb)
 {
     const float2 s = __ffma2_rn(m, pair(fc.scale), pair(kMagic));
     const float2 fl = __ffma2_rd(s, pair(kFloorScale), fc.c);
     const unsigned a0 = imad_u32(__float_as_uint(fl.x), 3u, __float_as_uint(fl.y) * pl) + fc.row0;  // B of the top-left tap
 #ifdef VAW_BOUNDS_CHECK
-    check_taps(a0, a0 + 3u * pl, 12u, tb.l_lo, tb.l_hi);
+    check_taps(a0, a0 + (unsigned)(kKs - 1) * pl, 3u * (unsigned)kKs, tb.l_lo, tb.l_hi);
 #endif
     const unsigned aw = a0 & ~3u, sh = a0 << 3;
     const unsigned idx = ((__float_as_uint(s.y) & 31u) << 5) | (__float_as_uint(s.x) & 31u);
-    const Weights8 q = ldg_weights8(reinterpret_cast<const uint4*>(tab) + idx * 2u);
+    const uint4* __restrict__ wt = reinterpret_cast<const uint4*>(tab) + idx * (unsigned)(kKs * kKs / 8);
     int sb = 1 << 14, sg = 1 << 14, sr = 1 << 14;
     unsigned row = aw;
+    constexpr int kRowsPerLoad = 16 / kKs;  // 16 weights per 256-bit load: four rows of a 4 x 4 block, two of an 8 x 8 block
 #pragma unroll
-    for (int r = 0; r < 4; ++r, row += pl) {
-        const unsigned w0 = lds_w32(row), w1 = lds_w32(row + 4u), w2 = lds_w32(row + 8u), w3 = lds_w32(row + 12u);
-        const unsigned t0 = __funnelshift_r(w0, w1, sh), t1 = __funnelshift_r(w1, w2, sh), t2 = __funnelshift_r(w2, w3, sh);
-        // t0 = B0 G0 R0 B1, t1 = G1 R1 B2 G2, t2 = R2 B3 G3 R3
-        const unsigned qb = __byte_perm(__byte_perm(t0, t1, 0x0630), t2, 0x5210);
-        const unsigned qg = __byte_perm(__byte_perm(t0, t1, 0x0741), t2, 0x6210);
-        const unsigned qr = __byte_perm(__byte_perm(t0, t1, 0x0052), t2, 0x7410);
-        sb = dp2a_hi_su(q.w[2 * r + 1], qb, dp2a_lo_su(q.w[2 * r], qb, sb));
-        sg = dp2a_hi_su(q.w[2 * r + 1], qg, dp2a_lo_su(q.w[2 * r], qg, sg));
-        sr = dp2a_hi_su(q.w[2 * r + 1], qr, dp2a_lo_su(q.w[2 * r], qr, sr));
+    for (int r0 = 0; r0 < kKs; r0 += kRowsPerLoad) {
+        const Weights8 q = ldg_weights8(wt + 2 * (r0 / kRowsPerLoad));
+#pragma unroll
+        for (int k = 0; k < kRowsPerLoad; ++k, row += pl) {
+#pragma unroll
+            for (int grp = 0; grp < kKs / 4; ++grp) {  // four taps = twelve bytes
+                const unsigned w0 = lds_w32(row + 12u * grp), w1 = lds_w32(row + 12u * grp + 4u), w2 = lds_w32(row + 12u * grp + 8u),
+                               w3 = lds_w32(row + 12u * grp + 12u);
+                const unsigned t0 = __funnelshift_r(w0, w1, sh), t1 = __funnelshift_r(w1, w2, sh), t2 = __funnelshift_r(w2, w3, sh);
+                // t0 = B0 G0 R0 B1, t1 = G1 R1 B2 G2, t2 = R2 B3 G3 R3
+                const unsigned qb = __byte_perm(__byte_perm(t0, t1, 0x0630), t2, 0x5210);
+                const unsigned qg = __byte_perm(__byte_perm(t0, t1, 0x0741), t2, 0x6210);
+                const unsigned qr = __byte_perm(__byte_perm(t0, t1, 0x0052), t2, 0x7410);
+                const unsigned wa = q.w[(kKs / 2) * k + 2 * grp], wb = q.w[(kKs / 2) * k + 2 * grp + 1];
+                sb = dp2a_hi_su(wb, qb, dp2a_lo_su(wa, qb, sb));
+                sg = dp2a_hi_su(wb, qg, dp2a_lo_su(wa, qg, sg));
+                sr = dp2a_hi_su(wb, qr, dp2a_lo_su(wa, qr, sr));
+            }
+        }
     }
     return sat_u8_q15(sb) | (sat_u8_q15(sg) << 8) | (sat_u8_q15(sr) << 16);
 }
@@ -219,7 +231,7 @@ __device__ __forceinline__ void fill_border_packed(uint8_t* tile, int pl, int ti
 }
 
 // nrows rows starting at piece row dv0 for the lane's two columns (u0, u0 + 1); taps from the staged tile.
-// kMode: 0 cv::INTER_LINEAR, 1 cv::INTER_NEAREST, 2 cv::INTER_CUBIC, 3 cv::INTER_LANCZOS4 (GRAY8 only)
+// kMode: 0 cv::INTER_LINEAR, 1 cv::INTER_NEAREST, 2 cv::INTER_CUBIC, 3 cv::INTER_LANCZOS4
 template <int kCn, bool kRagged, int kMode>
 __device__ __forceinline__ void rows_packed(const Geom& g, const ColPoly2& cp, const FloorConst& fc, unsigned pl, int dv0,
                                             int nrows, uint8_t* __restrict__ out0, int u0, const TileBounds& tb)
@@ -250,8 +262,9 @@ __device__ __forceinline__ void rows_packed(const Geom& g, const ColPoly2& cp, c
                 v00 = luma_tile_hi<kKs>(fc, pl, m00, g.cubic_tab, tb); v01 = luma_tile_hi<kKs>(fc, pl, m01, g.cubic_tab, tb);
                 v10 = luma_tile_hi<kKs>(fc, pl, m10, g.cubic_tab, tb); v11 = luma_tile_hi<kKs>(fc, pl, m11, g.cubic_tab, tb);
             } else {
-                v00 = bgr_tile_cubic(fc, pl, m00, g.cubic_tab, tb); v01 = bgr_tile_cubic(fc, pl, m01, g.cubic_tab, tb);
-                v10 = bgr_tile_cubic(fc, pl, m10, g.cubic_tab, tb); v11 = bgr_tile_cubic(fc, pl, m11, g.cubic_tab, tb);
+                constexpr int kKs = kMode == 2 ? 4 : 8;
+                v00 = bgr_tile_hi<kKs>(fc, pl, m00, g.cubic_tab, tb); v01 = bgr_tile_hi<kKs>(fc, pl, m01, g.cubic_tab, tb);
+                v10 = bgr_tile_hi<kKs>(fc, pl, m10, g.cubic_tab, tb); v11 = bgr_tile_hi<kKs>(fc, pl, m11, g.cubic_tab, tb);
             }
         } else if (kMode == 1) {
             v00 = packed_tile_nearest<kCn>(fc.row0, pl, col_coord(cp.a[0], cp.base, t0));
@@ -503,6 +516,7 @@ cudaError_t launch_warp_packed_tile(const Geom& g, const FrameBatch& b, const Pi
         if (e == cudaSuccess) e = configure_packed<1, 4, 2>();
         if (e == cudaSuccess) e = configure_packed<1, 4, 3>();
         if (e == cudaSuccess) e = configure_packed<3, 4, 2>();
+        if (e == cudaSuccess) e = configure_packed<3, 4, 3>();
         if (e != cudaSuccess) return e;
         if (tracked) configured[dev].store(true, std::memory_order_release);
     }
@@ -512,11 +526,11 @@ cudaError_t launch_warp_packed_tile(const Geom& g, const FrameBatch& b, const Pi
     // the instantiation whose register budget matches the CTAs the tile capacity lets share an SM: 7 (72 registers),
     // 6 (80) or 4 and fewer (128)
     const int ctas = maps.tile_cap <= tile_cap_for_ctas(7, kTileOffset) ? 7 : (maps.tile_cap <= tile_cap_for_ctas(6, kTileOffset) ? 6 : 4);
-    if (g.cubic_tab) {  // cv::INTER_CUBIC (GRAY8, BGR24) / cv::INTER_LANCZOS4 (GRAY8)
+    if (g.cubic_tab) {  // cv::INTER_CUBIC / cv::INTER_LANCZOS4
         if (channels == 1) return g.tab_ks == 4 ? launch_packed_table<1, 2>(g, b, table, maps, grid, block, smem, st)
                                                 : launch_packed_table<1, 3>(g, b, table, maps, grid, block, smem, st);
-        if (g.tab_ks != 4) return cudaErrorInvalidValue;  // (vaw_create never routes BGR24 Lanczos4 here)
-        return launch_packed_table<3, 2>(g, b, table, maps, grid, block, smem, st);
+        return g.tab_ks == 4 ? launch_packed_table<3, 2>(g, b, table, maps, grid, block, smem, st)
+                             : launch_packed_table<3, 3>(g, b, table, maps, grid, block, smem, st);
     }
     if (g.nearest) {  // cv::INTER_NEAREST: one light instantiation per format
         if (channels == 1) warp_packed_tile_kernel<1, 7, 1><<<grid, block, smem, st>>>(g, b, table, maps);
