@@ -15,6 +15,7 @@ timeout 600 python bench.py --fused-bgr --no-cpu-baseline --no-e2e --no-shim > g
 timeout 600 python bench.py --fused-bgr --variant 2 --no-cpu-baseline --no-e2e --no-shim > gpurun_out/bench_fused_bgr_one_launch.json 2>> gpurun_out/bench.err
 (PYTHONPATH=. timeout 300 python tools/bench_packed.py C3 32 bgr gray; PYTHONPATH=. timeout 300 python tools/bench_packed.py C1 32 bgr gray; PYTHONPATH=. timeout 300 python tools/bench_packed.py C5 16 bgr gray) > gpurun_out/packed.jsonl 2>> gpurun_out/bench.err
 PYTHONPATH=. timeout 600 python tools/bench_modes.py > gpurun_out/modes.json 2>> gpurun_out/bench.err
+PYTHONPATH=. timeout 300 python tools/bench_table_filters.py > gpurun_out/table_filters_final.txt 2>> gpurun_out/bench.err
 ./video_annotator_b200/host/vaw_demo --flow 40 3840 2160 0.5 > gpurun_out/flow_demo.log 2>&1; tail -1 gpurun_out/flow_demo.log
 for b in 8 16 24 30; do ./video_annotator_b200/host/vaw_demo --bench 1500 $b 2>&1 | grep "^{" ; done > gpurun_out/shim_batch.log; cat gpurun_out/shim_batch.log
 CMD="python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-parity --no-shim"
@@ -23,6 +24,8 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --cs
 timeout 300 $CMD > gpurun_out/plain2.log 2>&1 &&
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"warp_nv12|build_pieces" -s 6 -c 2 -f -o gpurun_out/prof_tiled $CMD > gpurun_out/ncu_full.log 2>&1
 PYTHONPATH=. timeout 600 ncu --set full --clock-control none --import-source on -k regex:"packed_tile" -s 4 -c 1 -f -o gpurun_out/prof_bgr python tools/bench_packed.py C3 32 bgr > gpurun_out/ncu_bgr.log 2>&1
+timeout 60 python tools/run_mode.py cubic > gpurun_out/run_cubic.log 2>&1 &&
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:warp_nv12_quad -s 2 -c 1 -f -o gpurun_out/prof_cubic python tools/run_mode.py cubic > gpurun_out/ncu_cubic.log 2>&1
 python - <<'PY'
 import json
 for f in ("bench", "bench_ref", "bench_C1", "bench_C2", "bench_C5", "bench_C4", "bench_fused_bgr"):

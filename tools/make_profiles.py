@@ -104,6 +104,33 @@ if os.path.exists(os.path.join(G, "prof_bgr.ncu-rep")):
     open(os.path.join(P, f"{tag}_ncu_bgr.txt"), "w").write(
         "ncu --set full --clock-control none -k regex:packed_tile -s 4 -c 1  python tools/bench_packed.py C3 32 bgr\n\n"
         + run([sys.executable, "tools/ncu_summary.py", os.path.join(G, "prof_bgr.ncu-rep")]))
+if os.path.exists(os.path.join(G, "prof_cubic.ncu-rep")):
+    rep_c = os.path.join(G, "prof_cubic.ncu-rep")
+    rawc = list(csv.reader(io.StringIO(run(["ncu", "-i", rep_c, "--page", "raw", "--csv"]))))
+    hc, uc, rc_ = rawc[0], rawc[1], rawc[2]
+    extra = []
+    for k in ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum",
+              "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum"):
+        if k in hc:
+            extra.append(f"  {k:75s} {rc_[hc.index(k)]:>18s} {uc[hc.index(k)]}")
+    for i, k in enumerate(hc):
+        if k.endswith("l1tex__data_pipe_lsu_wavefronts_mem_lgds.avg") or k.endswith("l1tex__data_pipe_lsu_wavefronts_mem_shared.avg"):
+            extra.append(f"  {k:75s} {rc_[i]:>18s} per SM")
+    open(os.path.join(P, f"{tag}_ncu_cubic.txt"), "w").write(
+        "ncu --set full --clock-control none --import-source on -k regex:warp_nv12_quad -s 2 -c 1  python tools/run_mode.py cubic\n"
+        "(INTER_CUBIC on the staged-tile kernel, C3 geometry, 16 frames per launch; tools/ncu_summary.py + the l1tex data-pipe split)\n\n"
+        + run([sys.executable, "tools/ncu_summary.py", rep_c]) + "\n".join(extra) + "\n\n"
+        "Reading: the l1tex data pipe is the busiest unit by far (issue slots ~40 %): the weight loads (3.75 M warp-wide requests of 32\n"
+        "different 32-byte table entries each: ~20 data-pipe wavefronts per request at an L1 hit rate of 95 %) and the tap words (a\n"
+        "share of them bank-conflict replays: lanes that share a source column in adjacent rows; tile pitches of 64 modulo 128 bytes\n"
+        "halve those).  The filter is bound by gathering 32 bytes of weights per sample, not by arithmetic or HBM (DRAM traffic is\n"
+        "below the algorithmic bytes: border pieces read nothing).\n")
+if os.path.exists(os.path.join(G, "table_filters_final.txt")):
+    path = os.path.join(P, f"{tag}_table_filters.txt")
+    old = open(path).read() if os.path.exists(path) else ""
+    marker = "\nfinal pass (tools/gpu_r2_final.sh; the defaults include the 64-modulo-128 tile pitches):\n"
+    old = old.split(marker)[0]
+    open(path, "w").write(old + marker + "".join("   " + ln for ln in open(os.path.join(G, "table_filters_final.txt"))))
 for fn, to in (("flow_demo.log", "flow_demo.txt"),):
     if os.path.exists(os.path.join(G, fn)):
         open(os.path.join(P, f"{tag}_{to}"), "w").write(open(os.path.join(G, fn)).read())
