@@ -705,12 +705,9 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
         p.interpolation != VAW_INTER_LANCZOS4)
         return fail(nullptr, VAW_ERR_UNSUPPORTED, "only INTER_NEAREST, INTER_LINEAR, INTER_CUBIC and INTER_LANCZOS4 are implemented");
     const bool table_filter = p.interpolation == VAW_INTER_CUBIC || p.interpolation == VAW_INTER_LANCZOS4;
-    // the formats whose staged-tile kernels carry the table filters (vaw_tile.cu, vaw_packed_tile.cu)
-    const bool table_staged = true;  // (every format since the BGR24 Lanczos4 sampler)
-    if (p.interpolation != VAW_INTER_LINEAR && p.variant != VAW_VARIANT_AUTO && p.variant != VAW_VARIANT_GATHER &&
-        !(p.interpolation == VAW_INTER_NEAREST && p.variant == VAW_VARIANT_TILED) &&
-        !(table_filter && p.variant == VAW_VARIANT_TILED && table_staged))
-        return fail(nullptr, VAW_ERR_UNSUPPORTED, "INTER_NEAREST runs on GATHER or TILED; INTER_CUBIC and INTER_LANCZOS4 on GATHER or TILED; AUTO picks TILED");
+    // (the staged-tile kernels of every format carry every filter: vaw_tile.cu, vaw_packed_tile.cu; POLY and TEX are INTER_LINEAR only)
+    if (p.interpolation != VAW_INTER_LINEAR && p.variant != VAW_VARIANT_AUTO && p.variant != VAW_VARIANT_GATHER && p.variant != VAW_VARIANT_TILED)
+        return fail(nullptr, VAW_ERR_UNSUPPORTED, "INTER_NEAREST, INTER_CUBIC and INTER_LANCZOS4 run on variants GATHER and TILED (AUTO picks TILED)");
     if (p.format != VAW_FORMAT_NV12 && p.format != VAW_FORMAT_BGR24 && p.format != VAW_FORMAT_GRAY8 &&
         p.format != VAW_FORMAT_NV12_TO_BGR24)
         return fail(nullptr, VAW_ERR_INVALID, "unknown pixel format");
@@ -806,7 +803,7 @@ int vaw_create(const vaw_params* params, int device, vaw_ctx** out)
     // AUTO: the staged-tile kernels wherever they exist (INTER_LINEAR: NV12 -> vaw_tile.cu, GRAY8 / BGR24 -> vaw_packed_tile.cu)
     ctx->variant = p.variant != VAW_VARIANT_AUTO ? p.variant
                    : ((p.interpolation == VAW_INTER_LINEAR || (p.interpolation == VAW_INTER_NEAREST && p.projection == 0) ||
-                       (table_filter && table_staged && p.projection == 0))
+                       (table_filter && p.projection == 0))
                           ? VAW_VARIANT_TILED : VAW_VARIANT_GATHER);
     // (NV12 -> BGR24: TILED = cvtColor into an L2-resident scratch + the staged BGR kernel, 30.9 k frames/s at 4K;
     //  POLY = everything in one launch with per-tap conversion, 13.8 k)
