@@ -347,7 +347,9 @@ __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)_
 __device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+#ifndef VAW_ABL_NO_INIT_FENCE  // analysis only (timing of the fence; the init must be fenced before the async proxy uses the barrier)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
 }
 __device__ __forceinline__ void mbar_expect_tx(unsigned mbar, unsigned bytes)
 {

@@ -66,6 +66,9 @@ constexpr int kQuadRecOffset = 16, kQuadTileOffset = 256;  // [tile mbarrier | r
 
 // nrows (even) rows starting at piece row dv0 for the lane's two columns; taps from the staged tile.
 // py / pc: the lane's column pair in the first luma row / chroma row of the band.
+#ifndef VAW_PREFETCH_AFTER_BARRIER
+#define VAW_PREFETCH_AFTER_BARRIER 0
+#endif
 #ifndef VAW_ONE_WAITER
 #define VAW_ONE_WAITER 0  // 1: one thread polls the record / tile mbarriers and the others park at a CTA barrier behind it
                           // (removes the try_wait loops, 3.3 % of the executed instructions -- and measures 0.6 % SLOWER:
@@ -400,11 +403,13 @@ warp_nv12_quad_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
         mbar_init(mbar_rec, 1);
         mbar_expect_tx(mbar_rec, (unsigned)sizeof(PieceRec));
         bulk_g2s(rec_s, rec, (unsigned)sizeof(PieceRec), mbar_rec);
+#if !VAW_PREFETCH_AFTER_BARRIER
         if (frame + 1 < (int)gridDim.z) {
             const char* nxt = reinterpret_cast<const char*>(rec + (size_t)npy * npx);
             asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + 128));
         }
+#endif
     }
 #if VAW_ONE_WAITER
     // ONE thread polls the mbarrier, the others park at the CTA barrier behind it (round 2's profile: the try_wait
@@ -413,6 +418,13 @@ warp_nv12_quad_kernel(const Geom g, const FrameBatch b, const PieceRec* __restri
     __syncthreads();
 #else
     __syncthreads();  // the barriers are initialised for every warp
+#if VAW_PREFETCH_AFTER_BARRIER  // (A/B: the next frame's record prefetch behind the CTA barrier instead of in front of it)
+    if (tid == 0 && frame + 1 < (int)gridDim.z) {
+        const char* nxt = reinterpret_cast<const char*>(rec + (size_t)npy * npx);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + 128));
+    }
+#endif
     mbar_wait_parked(mbar_rec, 0, 4000);
 #endif
     const PieceRec* rs = reinterpret_cast<const PieceRec*>(smem + kQuadRecOffset);
