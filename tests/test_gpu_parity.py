@@ -1440,6 +1440,52 @@ def test_table_filters_packed_formats(V, oracle, fmt, interp, case):
     ctx.close()
 
 
+@pytest.mark.parametrize("fmt", ["nv12", "bgr"])
+def test_table_filters_batches_pitches_and_host_buffers(V, oracle, fmt):
+    """INTER_CUBIC beyond one tightly packed frame: a batch of three frames with per-frame rotations in pitched
+    buffers (16-byte-multiple source pitch: the tiles stay TMA-staged; padding untouched) and the host-buffer
+    pipeline (vaw_warp_batch_host) give the bytes of three single-frame calls."""
+    import torch
+    from video_annotator_b200 import configs
+    w = configs.workload("C1")
+    sw, sh = w.src_size
+    n = 3
+    rots = w.rotations(n, first=20)
+    if fmt == "nv12":
+        ctx = V.WarpContext(w.input_camera, w.output_camera, out_size=w.out_size, border=(16, 128, 128), interpolation=V.INTER_CUBIC)
+        frames = [oracle.synth_nv12(sw, sh, 30 + i, white_noise=True) for i in range(n)]
+    else:
+        ctx = V.WarpContext(w.input_camera, w.output_camera, fmt=V.FORMAT_BGR24, border=(1, 2, 3), interpolation=V.INTER_CUBIC)
+        rng = np.random.default_rng(5)
+        frames = [rng.integers(0, 256, (sh, sw * 3), dtype=np.uint8) for _ in range(n)]
+    assert ctx.variant == TILED
+    want = [_warp_one(V, ctx, f.reshape(ctx.frame_shape("src")), r).reshape(ctx.frame_shape("dst")[0], -1) for f, r in zip(frames, rots)]
+    srows, srow_bytes = frames[0].shape[0], frames[0].shape[1]
+    drows, drow_bytes = want[0].shape
+    sp, dp = srow_bytes + 48, drow_bytes + 20
+    sstride, dstride = sp * srows + 256, dp * drows + 64
+    src = torch.full((n * sstride,), 0x5A, dtype=torch.uint8, device="cuda")
+    dst = torch.full((n * dstride,), 0xA5, dtype=torch.uint8, device="cuda")
+    for i, f in enumerate(frames):
+        src[i * sstride:i * sstride + sp * srows].view(srows, sp)[:, :srow_bytes] = G.to_dev(f)
+    rdev = torch.empty(n * 9, dtype=torch.float32, device="cuda")
+    ctx.upload_rotations(rots, rdev)
+    ctx.warp_batch(src, dst, rdev, n, src_pitch=sp, dst_pitch=dp, src_stride=sstride, dst_stride=dstride)
+    torch.cuda.synchronize()
+    out = dst.cpu().numpy()
+    for i in range(n):
+        frame = out[i * dstride:i * dstride + dp * drows].reshape(drows, dp)
+        assert np.array_equal(frame[:, :drow_bytes], want[i]), i
+        assert (frame[:, drow_bytes:] == 0xA5).all()
+    # host buffers in, host buffers out
+    hs = np.stack([f.reshape(-1) for f in frames])
+    hd = np.zeros((n, want[0].size), np.uint8)
+    ctx.warp_batch_host(hs, hd, rots)
+    for i in range(n):
+        assert np.array_equal(hd[i].reshape(want[i].shape), want[i]), i
+    ctx.close()
+
+
 def _table_filter_on_own_map(oracle, ctx, src, sw, sh, R, border, kw):
     """cv::remap's cubic / Lanczos4 filter (the oracle's) on the map the context samples with, NV12 planes."""
     mx, my = [t.cpu().numpy() for t in ctx.dump_coords(R, 0)]
