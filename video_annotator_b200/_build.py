@@ -20,6 +20,7 @@ NVCC_FLAGS = [
     "-fmad=false",
     "-Xcompiler", "-fPIC,-O2,-Wall,-pthread",
     "--shared", "-cudart", "static",
+    "--threads", "0",  # the translation units in parallel
 ]
 
 
