@@ -66,12 +66,15 @@ int main()
     {  // algebra
         const Mat33 a{{2, 1, 0, 0, 3, 1, 1, 0, 4}};
         CHECK(dist_to_identity(a * a.inv()) < 1e-14);
-        RotationFilter f(30);
         const Mat33 r{{0, -1, 0, 1, 0, 0, 0, 0, 1}};
-        f.add(r);
+        RotationFilter f(30);                            // the library's start-up: a window of zero matrices
+        for (int i = 0; i < 31; ++i) f.add(r);           // the reference's first filter() comes after radius + 1 samples (:453)
         const Mat33 s = f.filter();
-        CHECK(dist_to_identity(s * r.t()) < 1e-12);      // a constant sequence is its own smoothing
+        CHECK(dist_to_identity(s * r.t()) < 1e-12);      // a constant sequence is its own smoothing (one-sided window included)
         CHECK(dist_to_identity(s * s.t()) < 1e-12);      // result is orthonormal
+        RotationFilter g(30, RotationFilter::StartUp::FirstSample);  // round 1's convention
+        g.add(r);
+        CHECK(dist_to_identity(g.filter() * r.t()) < 1e-12);
     }
     {  // no rotation: frame 0 dropped, order kept, look-ahead latency, EOF drain
         const int n = 10, radius = 3;
@@ -102,7 +105,7 @@ int main()
         try { while (true) w.pull_frame(); } catch (int err) { CHECK(err == EOF); }
         CHECK((int)w.rotations.size() == n - 1);
         for (size_t i = 2 * radius; i + radius + 1 < w.rotations.size(); ++i) CHECK(dist_to_identity(w.rotations[i]) < 2e-4);
-        // at the start the filter still sees the "camera was still" padding: a real correction
+        // at the start the window is one-sided (zero matrices on the past side): a real correction
         CHECK(dist_to_identity(w.rotations[0]) > 1e-3);
         for (const Mat33& r : w.rotations) CHECK(std::fabs((r * r.t()).m[0] - 1.0) < 1e-9);
     }

@@ -169,7 +169,7 @@ Camera get_output_camera(const Camera& input, double scale, bool crop_borders, d
 }
 
 // ---- rotation smoothing --------------------------------------------------------------------------
-RotationFilter::RotationFilter(int radius) : m_radius(radius < 0 ? 0 : radius)
+RotationFilter::RotationFilter(int radius, StartUp start) : m_radius(radius < 0 ? 0 : radius), m_start(start)
 {
     // least-squares weights of a degree-2 fit over 2m+1 samples, evaluated at the centre
     const int m = m_radius;
@@ -182,8 +182,8 @@ RotationFilter::RotationFilter(int radius) : m_radius(radius < 0 ? 0 : radius)
 void RotationFilter::add(const Mat33& rotation)
 {
     const size_t n = 2 * (size_t)m_radius + 1;
-    if (m_window.empty())
-        for (size_t i = 0; i < n; ++i) m_window.push_back(rotation);  // start-up: as if the camera had been still
+    if (m_window.empty())  // start-up: the library's zero matrices, or (round 1's convention) as if the camera had been still
+        for (size_t i = 0; i < n; ++i) m_window.push_back(m_start == StartUp::Zeros ? Mat33{} : rotation);
     m_window.push_back(rotation);
     while (m_window.size() > n) m_window.pop_front();
 }

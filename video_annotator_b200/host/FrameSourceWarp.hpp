@@ -100,15 +100,29 @@ class OpticalFlowRotationSource : public RotationSource {
  * Savitzky-Golay smoothing of a rotation sequence, evaluated at the centre of a window of
  * 2*radius+1 samples (the reference builds gram_sg::RotationFilter from
  * SavitzkyGolayFilterConfig(radius, 0, 2, 0), :212): weights applied element-wise to the
- * matrices, result projected back to SO(3).  The library is not vendored in the reference
- * (meson.build:37, no version pin): parity of this stage is unpinned.
+ * matrices, result projected back to SO(3) (U V^T of the SVD = the orthogonal polar factor).
+ *
+ * Start-up.  The reference only ever calls add() (:444, :459) and filter() (:471), and its first
+ * filter() comes after radius + 1 add() calls (:453) although the library's Savitzky-Golay filter
+ * needs a full window of 2*radius+1 samples: the window is therefore pre-filled by the library's
+ * constructor, which cannot know any sample -- gram_sg::RotationFilter's constructor resets its
+ * circular buffer to ZERO matrices (spatial_filters.cpp of the published library, restated; add()
+ * is a plain push_back).  So until 2*radius+1 real samples have arrived the smoothed rotation is
+ * the polar factor of a ONE-SIDED weighted sum, not a centred one.  StartUp::Zeros (default)
+ * reproduces that; StartUp::FirstSample is round 1's convention (window pre-filled with the first
+ * sample, "as if the camera had been still").  The library is not vendored in the reference
+ * (meson.build:37, no version pin), so this stage stays formally unpinned.
  */
 class RotationFilter {
+  public:
+    enum class StartUp { Zeros, FirstSample };
+  private:
     int m_radius;
+    StartUp m_start;
     std::vector<double> m_weights;
     std::deque<Mat33> m_window;
   public:
-    explicit RotationFilter(int radius);
+    explicit RotationFilter(int radius, StartUp start = StartUp::Zeros);
     void add(const Mat33& rotation);
     Mat33 filter() const;
 };

@@ -37,11 +37,15 @@ def make_rotations(n, sigma_deg, radius=30, seed=ROT_SEED):
     return rotations_from_increments(inc, radius)
 
 
-def rotations_from_increments(inc, radius=30):
+def rotations_from_increments(inc, radius=30, start="zeros"):
     """Warp rotations for given per-frame axis-angle increments (n, 3): what FrameSourceWarp's
     consume_frame / pull_frame chain (:441-475) hands warp_frame for frames 1..n when the inter-frame
     rotation of frame i is rodrigues(inc[i-1]).  tests/test_host_shim.py feeds the same increments to the
-    C++ shim's chain and compares."""
+    C++ shim's chain and compares.
+
+    start: what the smoothing window holds before the first 2*radius+1 samples -- "zeros" (the library's
+    constructor fills its buffer with zero matrices; host/FrameSourceWarp.hpp has the argument) or "first"
+    (round 1's convention: the first sample replicated)."""
     inc = np.asarray(inc, np.float64)
     n = len(inc)
     measured = np.empty((n, 3, 3))
@@ -50,8 +54,8 @@ def rotations_from_increments(inc, radius=30):
         acc = _rodrigues(inc[i]) @ acc          # FrameSourceWarp.cpp:441-442
         measured[i] = acc
     w = sg_weights(radius)
-    pad = np.concatenate([np.repeat(measured[:1], radius, 0), measured,
-                          np.repeat(measured[-1:], radius, 0)])  # :456-461 pads with the last rotation
+    head = np.zeros((radius, 3, 3)) if start == "zeros" else np.repeat(measured[:1], radius, 0)
+    pad = np.concatenate([head, measured, np.repeat(measured[-1:], radius, 0)])  # :456-461 pads with the last rotation
     out = np.empty_like(measured)
     for i in range(n):
         m = np.tensordot(w, pad[i:i + 2 * radius + 1], axes=(0, 0))
